@@ -1,0 +1,146 @@
+"""Synthetic inputs for the mapping-core kernels (generators are ours; RandomReads3 needs a JVM).
+
+SURVEY.md §8(d) names the workloads.  G4 is the MultiStateAligner11ts microbenchmark of
+BASELINE.json configs[2]: (read, candidate window) pairs with read length in {100,150,250},
+70% true locus with ~1% substitutions, 20% true locus with one 1-40 bp indel, 10% unrelated
+locus (exercises the fail path); window = locus +- SLOW_ALIGN_PADDING (4, reference
+current/align2/BBMap.java:57).  minScore follows BBMapThread.scoreSlow
+(current/align2/BBMapThread.java:255-260,306): max(scoreNoIndels, (int)(ratio*maxQ) - CLEARZONE1e).
+All randomness is numpy PCG64 with the stated seed.
+"""
+import numpy as np
+
+TASK_DTYPE = np.dtype([("read_off", "<i8"), ("ref_off", "<i8"), ("read_len", "<i4"), ("ref_len", "<i4"),
+                       ("ref_start", "<i4"), ("ref_end", "<i4"), ("min_score", "<i4"), ("flags", "<i4")], align=True)
+OUT_DTYPE = np.dtype([("result", "<i4", (5,)), ("path", "<i4"), ("iterations", "<i8"), ("score", "<i4", (8,)),
+                      ("score_len", "<i4"), ("match_len", "<i4"), ("status", "<i4"), ("pad_", "<i4")], align=True)
+
+TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK = 1, 2, 4, 8, 16
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+CLEARZONE1e = 258          # current/align2/AbstractMapThread.java:142
+SLOW_ALIGN_PADDING = 4     # current/align2/BBMap.java:57
+POINTS_MATCH, POINTS_MATCH2 = 70, 100
+
+
+def max_quality(n):
+    """MultiStateAligner11tsJNI.maxQuality(int): MATCH + (n-1)*MATCH2."""
+    return POINTS_MATCH + (n - 1) * POINTS_MATCH2
+
+
+def random_genome(length, seed=1):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return ACGT[rng.integers(0, 4, size=length, dtype=np.uint8)]
+
+
+def score_no_indels_batch(reads2d, refs2d):
+    """Vectorised MultiStateAligner11tsJNI.scoreNoIndels (…JNI.java:1033-1089) for in-bounds windows.
+    reads2d, refs2d: (n, L) uint8.  Returns int32 scores."""
+    n, L = reads2d.shape
+    score = np.zeros(n, np.int32)
+    mode = np.full(n, -1, np.int8)      # -1 none, 0 MS, 3 SUB
+    tim = np.zeros(n, np.int32)
+    N = ord("N")
+    for i in range(L):
+        c = reads2d[:, i]; r = refs2d[:, i]
+        match = (c == r) & (c != N)
+        nocall = ~match & (c == N)
+        noref = ~match & ~nocall & (r == N)
+        sub = ~match & ~nocall & ~noref
+        # match
+        cont = match & (mode == 0)
+        score += np.where(cont, POINTS_MATCH2, 0).astype(np.int32)
+        score += np.where(match & ~cont, POINTS_MATCH, 0).astype(np.int32)
+        tim = np.where(cont, tim + 1, np.where(match, 0, tim))
+        mode = np.where(match, 0, mode)
+        # sub
+        scont = sub & (mode == 3)
+        tim = np.where(scont, tim + 1, np.where(sub, 0, tim))
+        t1 = tim + 1
+        pts = np.where(t1 > 5, -25, np.where(t1 > 1, -51, -127))
+        score += np.where(sub, pts, 0).astype(np.int32)
+        mode = np.where(sub, 3, mode)
+    return score
+
+
+def make_msa_tasks(genome, n, seed=2, lengths=(100, 150, 250), ratio=0.56, flags=TF_SCORE | TF_TRACEBACK,
+                   frac_indel=0.2, frac_unrelated=0.1, sub_rate=0.01, n_rate=0.0005, pad=SLOW_ALIGN_PADDING,
+                   max_indel=40, tight=True):
+    """G4: returns (reads uint8[], tasks TASK_DTYPE[n]).  ref_off=0, ref_len=len(genome) for every task."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    G = len(genome)
+    tasks = np.zeros(n, TASK_DTYPE)
+    which = rng.integers(0, len(lengths), size=n)
+    lens = np.asarray(lengths, np.int32)[which]
+    read_off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=read_off[1:])
+    reads = np.empty(int(read_off[-1]), np.uint8)
+    kind = rng.random(n)
+    is_unrel = kind < frac_unrelated
+    is_indel = (~is_unrel) & (kind < frac_unrelated + frac_indel)
+    margin = pad + max_indel + 64
+    for L in lengths:
+        idx = np.nonzero(lens == L)[0]
+        m = len(idx)
+        if m == 0:
+            continue
+        pos = rng.integers(margin, G - L - margin, size=m)
+        ar = np.arange(L, dtype=np.int64)[None, :]
+        # indels: +d = deletion from the read (ref span grows), -d = insertion into the read (ref span shrinks)
+        ind = is_indel[idx]
+        dlen = np.where(ind, rng.integers(1, max_indel + 1, size=m), 0)
+        is_del = rng.random(m) < 0.5
+        kpos = rng.integers(10, L - 10 - 1, size=m)[:, None]
+        d = dlen[:, None]
+        ilen = np.minimum(d, L - 20 - 1)  # keep insertions inside the read
+        src_del = ar + np.where(ar >= kpos, d, 0)
+        src_ins = ar - np.clip(ar - kpos, 0, ilen)
+        src = np.where(is_del[:, None], src_del, src_ins)
+        base = genome[pos[:, None] + src]
+        inserted = (~is_del[:, None]) & (ar >= kpos) & (ar < kpos + ilen) & ind[:, None]
+        rnd = ACGT[rng.integers(0, 4, size=(m, L), dtype=np.uint8)]
+        base = np.where(inserted, rnd, base)
+        # substitutions
+        submask = rng.random((m, L)) < sub_rate
+        code = np.searchsorted(ACGT, base)  # ACGT is sorted: A<C<G<T
+        sub = ACGT[(code + rng.integers(1, 4, size=(m, L))) % 4]
+        base = np.where(submask, sub, base)
+        # unrelated reads: fully random
+        un = is_unrel[idx]
+        base = np.where(un[:, None], rnd, base)
+        # a few no-calls
+        base = np.where(rng.random((m, L)) < n_rate, np.uint8(ord("N")), base)
+        span = np.where(ind, np.where(is_del, L + dlen, L - np.minimum(dlen, L - 21)), L)
+        a = pos - pad
+        b = pos + span - 1 + pad
+        maxq = max_quality(L)
+        min_limit = int(ratio * maxq) - CLEARZONE1e
+        if tight:
+            ni = score_no_indels_batch(base, genome[pos[:, None] + ar])
+            ms = np.maximum(ni, min_limit)
+        else:
+            ms = np.full(m, min_limit, np.int32)
+        flat = (read_off[idx][:, None] + ar).ravel()
+        reads[flat] = base.ravel()
+        tasks["read_len"][idx] = L
+        tasks["ref_start"][idx] = a
+        tasks["ref_end"][idx] = b
+        tasks["min_score"][idx] = ms
+    tasks["read_off"] = read_off[:-1]
+    tasks["ref_off"] = 0
+    tasks["ref_len"] = G
+    tasks["flags"] = flags
+    return reads, tasks
+
+
+def match_offsets(tasks, extra=0):
+    """Match-string slot per task: rows + columns (+extra) bytes (Java allocates rows+cols-1, …JNI.java:380)."""
+    a = tasks["ref_start"].astype(np.int64); b = tasks["ref_end"].astype(np.int64)
+    clamp = (tasks["flags"] & TF_CLAMP) != 0
+    a = np.where(clamp, np.maximum(a, 0), a)
+    b = np.where(clamp, np.minimum(b, tasks["ref_len"].astype(np.int64) - 1), b)
+    cap = tasks["read_len"].astype(np.int64) + np.maximum(b - a + 1, 0) + extra
+    cap = (cap + 3) & ~np.int64(3)
+    off = np.zeros(len(tasks) + 1, np.int64)
+    np.cumsum(cap, out=off[1:])
+    return off

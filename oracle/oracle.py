@@ -1,0 +1,153 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes bindings for the CPU oracle.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (bbmap_b200/) never does.
+
+Two libraries:
+  oracle/liborc.so          the "port": a C restatement of the reference's algorithm
+  oracle/_ref/libbbref.so   the reference's own C (jni/*.c) compiled unmodified from
+                            /root/reference against a stand-in jni.h; present only if it
+                            was built in the dev container (it travels to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TABLE_LEN = 604
+
+# task / out records — byte-compatible with include/bbmap_cuda.h (bbm_msa_task / bbm_msa_out)
+TASK_DTYPE = np.dtype([("read_off", "<i8"), ("ref_off", "<i8"), ("read_len", "<i4"), ("ref_len", "<i4"),
+                       ("ref_start", "<i4"), ("ref_end", "<i4"), ("min_score", "<i4"), ("flags", "<i4")], align=True)
+OUT_DTYPE = np.dtype([("result", "<i4", (5,)), ("path", "<i4"), ("iterations", "<i8"), ("score", "<i4", (8,)),
+                      ("score_len", "<i4"), ("match_len", "<i4"), ("status", "<i4"), ("pad_", "<i4")], align=True)
+assert TASK_DTYPE.itemsize == 40 and OUT_DTYPE.itemsize == 80
+
+TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK = 1, 2, 4, 8, 16
+
+
+def build(quiet=True):
+    """(Re)build liborc.so and, when /root/reference is mounted, _ref/libbbref.so."""
+    subprocess.run(["make", "-C", HERE] + (["-s"] if quiet else []), check=True)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self):
+        so = os.path.join(HERE, "liborc.so")
+        if not os.path.exists(so):
+            build()
+        self.lib = C.CDLL(so)
+        L = self.lib
+        L.orc_msa_new.restype = C.c_void_p
+        L.orc_msa_new.argtypes = [C.c_int, C.c_int]
+        L.orc_msa_free.argtypes = [C.c_void_p]
+        L.orc_msa_packed.restype = C.c_void_p
+        L.orc_msa_packed.argtypes = [C.c_void_p]
+        L.orc_msa_iterations.restype = C.c_int64
+        L.orc_msa_iterations.argtypes = [C.c_void_p, C.c_int]
+        L.orc_msa_set_band.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.orc_msa_set_backend.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_msa_set_shape.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_msa_last_path.argtypes = [C.c_void_p]
+        L.orc_batch_run.restype = C.c_int64
+        L.orc_set_reference_fns.argtypes = [C.c_void_p, C.c_void_p]
+        self.ref = None
+        refso = os.path.join(HERE, "_ref", "libbbref.so")
+        if os.path.exists(refso):
+            self.ref = C.CDLL(refso)
+            fl = C.cast(self.ref.fillLimitedX, C.c_void_p).value
+            fu = C.cast(self.ref.fillUnlimited, C.c_void_p).value
+            L.orc_set_reference_fns(fl, fu)
+        self.sub = np.zeros(TABLE_LEN, np.int32)
+        self.ins = np.zeros(TABLE_LEN, np.int32)
+        self.insC = np.zeros(TABLE_LEN, np.int32)
+        L.orc_msa_tables(_p(self.sub), _p(self.ins), _p(self.insC), None, None, None)
+        self.b2n = np.zeros(128, np.int8)
+        L.orc_base_to_number(_p(self.b2n))
+
+    @property
+    def has_reference(self):
+        return self.ref is not None
+
+    # ---------------- raw fills on a caller-owned packed matrix ----------------
+    def new_packed(self, maxRows, maxColumns):
+        """A fresh `packed` initialised like the Java constructor (MSA11tsJNI.java:98-112)."""
+        m = self.lib.orc_msa_new(maxRows, maxColumns)
+        n = 3 * (maxRows + 1) * (maxColumns + 1)
+        arr = np.ctypeslib.as_array(C.cast(self.lib.orc_msa_packed(m), C.POINTER(C.c_int32)), shape=(n,)).copy()
+        self.lib.orc_msa_free(m)
+        return arr
+
+    def _fn(self, name, kind):
+        if kind == "reference":
+            if not self.ref:
+                raise RuntimeError("oracle/_ref/libbbref.so not built")
+            return getattr(self.ref, {"limited": "fillLimitedX", "unlimited": "fillUnlimited"}[name])
+        return getattr(self.lib, {"limited": "orc_fill_limitedX", "unlimited": "orc_fill_unlimited"}[name])
+
+    def fill_limited(self, read, ref, a, b, minScore, packed, maxRows, maxColumns, bandwidth=0, ratio=0.0, kind="port",
+                     vl=None, hl=None):
+        read = np.ascontiguousarray(read, np.int8); ref = np.ascontiguousarray(ref, np.int8)
+        res = np.zeros(5, np.int32); it = np.zeros(1, np.int64)
+        vl = np.zeros(maxRows + 1, np.int32) if vl is None else vl
+        hl = np.zeros(maxColumns + 1, np.int32) if hl is None else hl
+        f = self._fn("limited", kind); f.restype = None
+        f(_p(read), _p(ref), C.c_int(len(read)), C.c_int(len(ref)), C.c_int(a), C.c_int(b), C.c_int(minScore), _p(res), _p(it),
+          _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns), C.c_int(bandwidth), C.c_float(ratio),
+          _p(vl), _p(hl), _p(self.b2n), _p(self.insC))
+        return res, int(it[0])
+
+    def fill_unlimited(self, read, ref, a, b, packed, maxRows, maxColumns, kind="port"):
+        read = np.ascontiguousarray(read, np.int8); ref = np.ascontiguousarray(ref, np.int8)
+        res = np.zeros(4, np.int32); it = np.zeros(1, np.int64)
+        f = self._fn("unlimited", kind); f.restype = None
+        f(_p(read), _p(ref), C.c_int(len(read)), C.c_int(len(ref)), C.c_int(a), C.c_int(b), _p(res), _p(it),
+          _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns))
+        return res, int(it[0])
+
+    # ---------------- batch driver ----------------
+    def run_batch(self, reads, refs, tasks, match_off=None, bandwidth=0, ratio=0.0, maxRows=601, maxColumns=3000,
+                  kind="port", threads=1):
+        """Returns (outs, match_buf, cells). `tasks` is a TASK_DTYPE array."""
+        reads = np.ascontiguousarray(reads, np.int8); refs = np.ascontiguousarray(refs, np.int8)
+        tasks = np.ascontiguousarray(tasks, TASK_DTYPE)
+        outs = np.zeros(len(tasks), OUT_DTYPE)
+        if match_off is None:
+            match_off = match_offsets(tasks)
+        match_off = np.ascontiguousarray(match_off, np.int64)
+        mbuf = np.zeros(max(int(match_off[-1]), 1), np.int8)
+        cells = self.lib.orc_batch_run(_p(reads), _p(refs), _p(tasks), _p(outs), C.c_int64(len(tasks)), _p(mbuf), _p(match_off),
+                                       C.c_int(bandwidth), C.c_float(ratio), C.c_int(maxRows), C.c_int(maxColumns),
+                                       C.c_int(1 if kind == "reference" else 0), C.c_int(threads))
+        if cells < 0:
+            raise RuntimeError("reference fill backend unavailable")
+        return outs, mbuf, int(cells)
+
+
+def match_offsets(tasks, extra=0):
+    """Per-task match-string slots: rows + columns (+extra) bytes each (Java allocates rows+cols-1, MSA11tsJNI.java:380)."""
+    a = tasks["ref_start"].astype(np.int64); b = tasks["ref_end"].astype(np.int64)
+    clamp = (tasks["flags"] & TF_CLAMP) != 0
+    a = np.where(clamp, np.maximum(a, 0), a)
+    b = np.where(clamp, np.minimum(b, tasks["ref_len"].astype(np.int64) - 1), b)
+    cap = tasks["read_len"].astype(np.int64) + np.maximum(b - a + 1, 0) + extra
+    cap = (cap + 3) & ~np.int64(3)
+    off = np.zeros(len(tasks) + 1, np.int64)
+    np.cumsum(cap, out=off[1:])
+    return off
+
+
+_ORACLE = None
+
+
+def get():
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
