@@ -1,0 +1,263 @@
+// capi.cu — the C ABI of libbbmapcuda.so (see include/bbmap_cuda.h).  Host-side glue only: device buffers, streams,
+// launches.  No CPU implementation of any compute path lives here: without a device every call fails loudly.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <cuda_runtime.h>
+#include "msa_common.cuh"
+
+using namespace bbm;
+
+#define DECL_W(W) extern "C" int bbm_launch_msa_tiled_w##W(const MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
+DECL_W(4) DECL_W(5) DECL_W(6) DECL_W(8) DECL_W(9) DECL_W(12) DECL_W(16)
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* counts, cudaStream_t stream);
+extern "C" int bbm_launch_msa_scatter(long long ntasks, const unsigned char* cls, unsigned int* cursors, int* lists, cudaStream_t stream);
+extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
+extern "C" int bbm_msa_warps_per_block();
+extern "C" int bbm_msa_num_wclass();
+extern "C" long long bbm_generic_scratch_ints(int rows, int cols);
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(BBM_E_CUDA, #call, e_); } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return -1; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return -1; }
+        cap = want; return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct bbm_ctx {
+    int device = 0;
+    int sms = 0;
+    int blocks = 0;             // persistent grid of the tiled kernel
+    int bandwidth = 0; float ratio = 0.f;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf scratch, counters, overflow, gscratch, lists, cls;
+    DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump;   // staging for the host-buffer entry point
+    PinBuf h_stage;
+    std::vector<void*> uploads;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+extern "C" const char* bbm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int bbm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int bbm_init(int device, bbm_ctx** out) {
+    if (!out) return fail(BBM_E_ARG, "bbm_init: out is null");
+    int n = bbm_device_count();
+    if (n <= 0) return fail(BBM_E_NODEVICE, "no CUDA device: libbbmapcuda has no CPU fallback");
+    if (device < 0 || device >= n) return fail(BBM_E_ARG, "bbm_init: bad device ordinal");
+    CK(cudaSetDevice(device));
+    bbm_ctx* c = new bbm_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    c->blocks = c->sms * 4;     // 4 blocks x 4 warps per SM (register-bound); the kernel is persistent over a task counter
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    if (c->counters.ensure(64 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
+    *out = c;
+    return BBM_OK;
+}
+
+extern "C" void bbm_destroy(bbm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->uploads) cudaFree(p);
+    c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release();
+    c->h_stage.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int bbm_set_band(bbm_ctx* c, int32_t bandwidth, float ratio) {
+    if (!c) return fail(BBM_E_ARG, "null ctx");
+    c->bandwidth = bandwidth; c->ratio = ratio;
+    return BBM_OK;
+}
+
+extern "C" int bbm_upload(bbm_ctx* c, const void* host, int64_t nbytes, void** dev_out) {
+    if (!c || !host || nbytes < 0 || !dev_out) return fail(BBM_E_ARG, "bbm_upload: bad argument");
+    CK(cudaSetDevice(c->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)nbytes + 256));
+    CK(cudaMemcpy(p, host, (size_t)nbytes, cudaMemcpyHostToDevice));
+    CK(cudaMemset((char*)p + nbytes, 'N', 256));
+    c->uploads.push_back(p);
+    *dev_out = p;
+    return BBM_OK;
+}
+
+extern "C" int bbm_free_dev(bbm_ctx* c, void* dev) {
+    if (!c) return fail(BBM_E_ARG, "null ctx");
+    for (size_t i = 0; i < c->uploads.size(); ++i)
+        if (c->uploads[i] == dev) { cudaFree(dev); c->uploads.erase(c->uploads.begin() + i); return BBM_OK; }
+    return fail(BBM_E_ARG, "bbm_free_dev: unknown pointer");
+}
+
+extern "C" int64_t bbm_launch_count(const bbm_ctx* c) { return c ? c->launches : 0; }
+
+// Counter block layout (32-bit words): [0..8] class counts, [16..24] scatter cursors, [32..40] per-class work counters,
+// [48] overflow count (banded right-edge misses reported by the tiled kernels).
+static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_msa_task* d_tasks, bbm_msa_out* d_outs,
+                   int64_t ntasks, int8_t* d_match, const int64_t* d_moff, int max_rows, int max_cols, cudaStream_t st,
+                   float* ms_out, int* d_dump) {
+    if (ntasks <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (ntasks > 0x7fffffffLL) return fail(BBM_E_ARG, "too many tasks in one batch (max 2^31-1)");
+    if (max_rows < 1) max_rows = MAXR;
+    if (max_cols < 1) max_cols = 3000;
+    const int wpb = bbm_msa_warps_per_block();
+    const int nw = bbm_msa_num_wclass();
+    const int tiledRows = max_rows < MAXR ? max_rows : MAXR;
+    const long long words = (long long)(tiledRows + 40) * 32;           // one 64-bit code word per (step,lane)
+    if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
+    if (c->overflow.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc overflow list");
+    if (c->lists.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc class lists");
+    if (c->cls.ensure((size_t)ntasks + 16)) return fail(BBM_E_CUDA, "cudaMalloc class ids");
+    unsigned int* cnt = (unsigned int*)c->counters.p;
+    MsaParams P;
+    P.reads = d_reads; P.refs = d_refs; P.tasks = d_tasks; P.outs = d_outs; P.ntasks = ntasks;
+    P.match_buf = d_match; P.match_off = (const long long*)d_moff;
+    P.bandwidth = c->bandwidth; P.ratio = c->ratio;
+    P.scratch = (unsigned long long*)c->scratch.p; P.scratch_words = words;
+    P.counter = nullptr; P.overflow_count = cnt + 48;
+    P.overflow_list = (int*)c->overflow.p;
+    P.dump = d_dump;
+    CK(cudaMemsetAsync(c->counters.p, 0, 64 * 4, st));
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cnt, st);
+    if (e) return fail(BBM_E_CUDA, "msa_classify_kernel launch", (cudaError_t)e);
+    c->launches++;
+    unsigned int h_cnt[16];
+    CK(cudaMemcpyAsync(h_cnt, cnt, 16 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    unsigned int h_base[16]; unsigned int acc = 0;
+    for (int k = 0; k <= nw; ++k) { h_base[k] = acc; acc += h_cnt[k]; }
+    for (int k = nw + 1; k < 16; ++k) h_base[k] = acc;
+    CK(cudaMemcpyAsync(cnt + 16, h_base, 16 * 4, cudaMemcpyHostToDevice, st));
+    e = bbm_launch_msa_scatter(ntasks, (const unsigned char*)c->cls.p, cnt + 16, (int*)c->lists.p, st);
+    if (e) return fail(BBM_E_CUDA, "msa_scatter_kernel launch", (cudaError_t)e);
+    c->launches++;
+    typedef int (*launch_fn)(const MsaParams*, const int*, int, unsigned int*, int, int, cudaStream_t);
+    static const launch_fn fns[7] = { bbm_launch_msa_tiled_w4, bbm_launch_msa_tiled_w5, bbm_launch_msa_tiled_w6, bbm_launch_msa_tiled_w8,
+                                      bbm_launch_msa_tiled_w9, bbm_launch_msa_tiled_w12, bbm_launch_msa_tiled_w16 };
+    for (int k = 0; k < nw; ++k) {
+        if (!h_cnt[k]) continue;
+        int blocks = c->blocks;
+        const long long needBlocks = ((long long)h_cnt[k] + wpb - 1) / wpb;
+        if (needBlocks < blocks) blocks = (int)needBlocks;
+        e = fns[k](&P, (const int*)c->lists.p + h_base[k], (int)h_cnt[k], cnt + 32 + k, blocks, d_dump != nullptr, st);
+        if (e) return fail(BBM_E_CUDA, "msa_tiled_kernel launch", (cudaError_t)e);
+        c->launches++;
+    }
+    const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
+    long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
+    if (chunk < 1) chunk = 1;
+    auto run_generic = [&](const int* list, long long n) -> int {
+        if (n <= 0) return BBM_OK;
+        const long long ch = chunk > n ? n : chunk;
+        if (c->gscratch.ensure((size_t)ch * (size_t)gstride * 4)) return fail(BBM_E_CUDA, "cudaMalloc generic scratch");
+        for (long long done = 0; done < n; done += ch) {
+            const int m = (int)((n - done) < ch ? (n - done) : ch);
+            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, st);
+            if (e2) return fail(BBM_E_CUDA, "msa_generic_kernel launch", (cudaError_t)e2);
+            c->launches++;
+        }
+        return BBM_OK;
+    };
+    int rc = run_generic((const int*)c->lists.p + h_base[nw], h_cnt[nw]);       // shapes outside the tiled kernels
+    if (rc) return rc;
+    if (c->bandwidth > 0 || c->ratio > 0.f) {
+        unsigned int nover = 0;
+        CK(cudaMemcpyAsync(&nover, cnt + 48, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        rc = run_generic((const int*)c->overflow.p, nover);                   // banded right-edge misses
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_msa_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_msa_task* d_tasks,
+                                 bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match_buf, const int64_t* d_match_off,
+                                 int32_t max_rows, int32_t max_cols, void* stream, float* kernel_ms_out) {
+    if (!c || !d_reads || !d_refs || !d_tasks || !d_outs) return fail(BBM_E_ARG, "bbm_msa_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return run_msa(c, d_reads, d_refs, d_tasks, d_outs, ntasks, d_match_buf, d_match_off, max_rows, max_cols, st, kernel_ms_out, nullptr);
+}
+
+extern "C" int bbm_msa_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs,
+                                  const bbm_msa_task* tasks, bbm_msa_out* outs, int64_t ntasks,
+                                  int8_t* match_buf, const int64_t* match_off) {
+    if (!c || !reads || !d_refs || !tasks || !outs || reads_bytes < 0) return fail(BBM_E_ARG, "bbm_msa_batch_host: bad argument");
+    if (ntasks <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int max_rows = 1, max_cols = 1;
+    for (int64_t i = 0; i < ntasks; ++i) {
+        if (tasks[i].read_len > max_rows) max_rows = tasks[i].read_len;
+        const int cols = tasks[i].ref_end - tasks[i].ref_start + 1;
+        if (cols > max_cols) max_cols = cols;
+    }
+    const size_t tb = (size_t)ntasks * sizeof(bbm_msa_task), ob = (size_t)ntasks * sizeof(bbm_msa_out);
+    const size_t mb = match_buf && match_off ? (size_t)match_off[ntasks] : 0, fb = (size_t)(ntasks + 1) * 8;
+    if (c->d_reads.ensure((size_t)reads_bytes + 16) || c->d_tasks.ensure(tb) || c->d_outs.ensure(ob) ||
+        c->d_match.ensure(mb + 16) || c->d_moff.ensure(fb))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(c->d_reads.p, reads, (size_t)reads_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, tasks, tb, cudaMemcpyHostToDevice, st));
+    if (mb) CK(cudaMemcpyAsync(c->d_moff.p, match_off, fb, cudaMemcpyHostToDevice, st));
+    int rc = run_msa(c, (const int8_t*)c->d_reads.p, d_refs, (const bbm_msa_task*)c->d_tasks.p, (bbm_msa_out*)c->d_outs.p, ntasks,
+                     mb ? (int8_t*)c->d_match.p : nullptr, mb ? (const int64_t*)c->d_moff.p : nullptr, max_rows, max_cols, st, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
+    if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}

@@ -1,0 +1,90 @@
+// msa_kernels.cuh — kernel templates shared by the per-width translation units (msa_w*.cu) and msa_kernels.cu.
+#pragma once
+#include <climits>
+#include "msa_tiled.cuh"
+
+namespace bbm {
+
+// MultiStateAligner11tsJNI.fillLimitedX's halfband (…JNI.java:137-138 == jni/...JNI.c:392-393)
+__device__ __forceinline__ int calc_halfband(int bandwidth, float ratio, int rows, int cols) {
+    if (bandwidth < 1 && ratio <= 0.f) return 0;
+    const int x = bandwidth < 1 ? 9999999 : bandwidth;
+    const int y = ratio <= 0.f ? 9999999 : 8 + (int)(rows * ratio);   // float multiply then truncation, like the C
+    return imax(imin(x, y), cols - rows + 8) / 2;
+}
+
+// Resolve what the reference would run for this task (…JNI.java:132-144; MSA.java:104-105)
+__device__ __forceinline__ bool resolve_task(const bbm_msa_task& t, int bandwidth, float ratio, TaskCtx& T) {
+    int a = t.ref_start, b = t.ref_end;
+    if (t.flags & BBM_TF_CLAMP) { a = imax(0, a); b = imin(t.ref_len - 1, b); }
+    T.a = a; T.b = b; T.rows = t.read_len; T.cols = b - a + 1; T.flags = t.flags;
+    T.minScore = t.min_score;
+    T.limited = 0; T.halfband = 0;
+    if (T.rows < 1 || T.cols < 1 || a < 0 || b >= t.ref_len) return false;
+    T.halfband = calc_halfband(bandwidth, ratio, T.rows, T.cols);
+    if (t.flags & BBM_TF_RAW_UNLIMITED) { T.limited = 0; }
+    else if (t.flags & BBM_TF_RAW_LIMITED) { T.limited = 1; }
+    else {
+        const int hb = T.halfband;
+        const bool unl = (T.minScore < 1) || (T.cols + T.rows < 90) ||
+                         ((hb < 1 || hb * 3 > T.cols) && (T.cols > T.rows + imin(170, T.rows + 20)));
+        T.limited = unl ? 0 : 1;
+        if (!unl) T.minScore -= MIN_SCORE_ADJUST;
+    }
+    if (!T.limited) T.halfband = 0;
+    return true;
+}
+
+// width classes of the register-tiled kernel: columns per lane
+constexpr int NUM_WCLASS = 7;
+__host__ __device__ constexpr int wclass_width(int k) { return k == 0 ? 4 : k == 1 ? 5 : k == 2 ? 6 : k == 3 ? 8 : k == 4 ? 9 : k == 5 ? 12 : 16; }
+constexpr int CLASS_GENERIC = NUM_WCLASS;      // row-sequential kernel
+constexpr int CLASS_BAD = NUM_WCLASS + 1;      // invalid task
+constexpr int NUM_CLASS = NUM_WCLASS + 2;
+
+__device__ __forceinline__ int classify(const TaskCtx& T) {
+    const int w = (T.cols + 31) >> 5;
+    if (T.rows > MAXR - 2 || w > 16) return CLASS_GENERIC;
+    return w <= 4 ? 0 : w == 5 ? 1 : w == 6 ? 2 : w <= 8 ? 3 : w == 9 ? 4 : w <= 12 ? 5 : 6;
+}
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+template <int W, bool DUMP>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) msa_tiled_kernel(MsaParams P, const int* __restrict__ list, int nlist, unsigned int* counter) {
+    __shared__ BlockShared bs;
+    __shared__ WarpShared wsAll[WARPS_PER_BLOCK];
+    for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) { bs.insc[i] = ins_score_offset(i); bs.delc[i] = del_score_offset(i); }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpShared& ws = wsAll[warp];
+    const long long gwarp = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    unsigned long long* scratch = P.scratch + gwarp * P.scratch_words;
+    for (;;) {
+        unsigned k = 0;
+        if (lane == 0) k = atomicAdd(counter, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= (unsigned)nlist) break;
+        const int id = list ? list[k] : (int)k;
+        const bbm_msa_task task = P.tasks[id];
+        bbm_msa_out* out = P.outs + id;
+        TaskCtx T;
+        resolve_task(task, P.bandwidth, P.ratio, T);
+        if (!T.limited) msa_fill_task<W, false, false, DUMP>(P, T, task, id, ws, bs, scratch, out);
+        else if (T.halfband < 1) msa_fill_task<W, true, false, DUMP>(P, T, task, id, ws, bs, scratch, out);
+        else msa_fill_task<W, true, true, DUMP>(P, T, task, id, ws, bs, scratch, out);
+        __syncwarp();
+    }
+}
+
+#define BBM_DECLARE_TILED_LAUNCH(W) \
+    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
+
+#define BBM_DEFINE_TILED_LAUNCH(W) \
+    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream) { \
+        if (dump) bbm::msa_tiled_kernel<W, true><<<1, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, counter); \
+        else bbm::msa_tiled_kernel<W, false><<<blocks, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, counter); \
+        return (int)cudaGetLastError(); \
+    }
+
+}  // namespace bbm

@@ -1,0 +1,3 @@
+// register-tiled MultiStateAligner11ts kernel, 16 columns per lane (see msa_tiled.cuh)
+#include "msa_kernels.cuh"
+BBM_DEFINE_TILED_LAUNCH(16)

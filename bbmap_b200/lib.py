@@ -1,0 +1,56 @@
+"""ctypes loader for libbbmapcuda.so (C ABI in include/bbmap_cuda.h).
+
+There is no CPU fallback anywhere in this package: if the CUDA extension is missing or no
+device is visible, construction raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libbbmapcuda.so")
+
+BBM_OK, BBM_E_NODEVICE, BBM_E_CUDA, BBM_E_ARG, BBM_E_SHAPE, BBM_E_CAPACITY = 0, -1, -2, -3, -4, -5
+
+# every symbol include/bbmap_cuda.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "bbm_init", "bbm_destroy", "bbm_set_band", "bbm_last_error", "bbm_device_count", "bbm_upload", "bbm_free_dev",
+    "bbm_msa_batch_dev", "bbm_msa_batch_host", "bbm_launch_count", "bbm_fillUnlimited", "bbm_fillLimitedX",
+]
+
+
+class BbmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building is __graft_entry__.build()'s job). Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise BbmError("libbbmapcuda.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "bbmap_b200 has no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    L.bbm_last_error.restype = C.c_char_p
+    L.bbm_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.bbm_destroy.argtypes = [C.c_void_p]
+    L.bbm_destroy.restype = None
+    L.bbm_set_band.argtypes = [C.c_void_p, C.c_int32, C.c_float]
+    L.bbm_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.bbm_free_dev.argtypes = [C.c_void_p, C.c_void_p]
+    L.bbm_launch_count.argtypes = [C.c_void_p]
+    L.bbm_launch_count.restype = C.c_int64
+    L.bbm_msa_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+    L.bbm_msa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise BbmError("%s failed (%d): %s" % (what, rc, load().bbm_last_error().decode()))

@@ -1,0 +1,111 @@
+/*
+ * bbmap_cuda.h — C ABI of libbbmapcuda.so, the B200 (sm_100a) drop-in for BBMap's native plug-in.
+ *
+ * What it replaces in the reference (cavelandiah/BBMap, BBTools 36.19):
+ *   - libbbtoolsjni's MultiStateAligner11ts fill kernels  jni/MultiStateAligner11tsJNI.c:100-314 (fillUnlimited),
+ *     :361-704 (fillLimitedX) and their JNI shims :707-812 (header jni/align2_MultiStateAligner11tsJNI.h:165-174),
+ *     loaded by current/align2/MultiStateAligner11tsJNI.java:11-42 when Shared.USE_JNI (current/align2/MSA.java:44-49);
+ *   - the Java half that consumes the filled matrix: fillLimited dispatch (MultiStateAligner11tsJNI.java:116-164),
+ *     score/score2 (:499-658), traceback/traceback2 (:362-495), MSA.fillAndScoreLimited (MSA.java:103-134) —
+ *     moved onto the device so the `packed` matrix never has to exist in memory;
+ *   - BandedAligner  jni/BandedAlignerJNI.c:123-585 and shims :588-757 (header jni/align2_BandedAlignerJNI.h:17-41).
+ *
+ * Conventions: plain pointers and sizes only.  Every entry point returns 0 on success or a negative BBM_E_* code;
+ * nothing ever calls exit() (the reference does, jni/MultiStateAligner11tsJNI.c:130-132 — documented deviation).
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns BBM_E_NODEVICE.
+ */
+#ifndef BBMAP_CUDA_H
+#define BBMAP_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBM_OK            0
+#define BBM_E_NODEVICE   -1   /* no CUDA device / driver */
+#define BBM_E_CUDA       -2   /* a CUDA call failed; see bbm_last_error() */
+#define BBM_E_ARG        -3   /* bad argument */
+#define BBM_E_SHAPE      -4   /* rows/columns outside what the kernels support */
+#define BBM_E_CAPACITY   -5   /* an output buffer was too small */
+
+/* ---- task flags (bbm_msa_task.flags) ---- */
+#define BBM_TF_RAW_LIMITED    1  /* exactly fillLimitedX(...minScore...)   (jni/...JNI.c:361): no dispatch rule, no -120 */
+#define BBM_TF_RAW_UNLIMITED  2  /* exactly fillUnlimited(...)             (jni/...JNI.c:100) */
+                                 /* neither bit: MultiStateAligner11tsJNI.fillLimited semantics (…JNI.java:132-164):
+                                    limited-vs-unlimited rule, then minScore-=MIN_SCORE_ADJUST(120) */
+#define BBM_TF_CLAMP          4  /* clamp the window to [0, ref_len-1] like MSA.fillAndScoreLimited (MSA.java:104-105) */
+#define BBM_TF_SCORE          8  /* also run score2  (…JNI.java:537-658) */
+#define BBM_TF_TRACEBACK     16  /* also run traceback2 (…JNI.java:376-495) and emit the match string */
+
+/* One (read, candidate window) alignment.  40 bytes. */
+typedef struct {
+    int64_t read_off;   /* byte offset of the read in the reads buffer */
+    int64_t ref_off;    /* byte offset of the reference array (chromosome) in the reference buffer */
+    int32_t read_len;   /* rows */
+    int32_t ref_len;    /* length of that reference array (Java: ref.length) */
+    int32_t ref_start;  /* refStartLoc, inclusive, relative to ref_off */
+    int32_t ref_end;    /* refEndLoc, inclusive */
+    int32_t min_score;  /* minScore (ignored by RAW_UNLIMITED) */
+    int32_t flags;
+} bbm_msa_task;
+
+/* Result of one alignment.  80 bytes. */
+typedef struct {
+    int32_t result[5];   /* {rows, maxCol, maxState, maxScore, fail} exactly as the C writes them (unlimited: fail=0);
+                            in Java-semantics mode a failed limited fill gives {rows,0,0,0,1} (Java returns null) */
+    int32_t path;        /* 0 = fillLimitedX ran, 1 = fillUnlimited ran */
+    int64_t iterations;  /* the reference's iterationsLimited/iterationsUnlimited increment for this call */
+    int32_t score[8];    /* score2: {score,bestRefStart,bestRefStop,maxRow,maxCol,maxState,padLeft,padRight} */
+    int32_t score_len;   /* 0 (not requested / fill failed), 6, or 8 (padding suggested) */
+    int32_t match_len;   /* -1 (not requested / fill failed) or length of the match string */
+    int32_t status;      /* 0 or BBM_E_* for this task */
+    int32_t pad_;
+} bbm_msa_out;
+
+typedef struct bbm_ctx bbm_ctx;
+
+/* Lifecycle.  `device` is a CUDA ordinal.  MSA.bandwidth / MSA.bandwidthRatio (MSA.java:864-865) are per-context. */
+int  bbm_init(int device, bbm_ctx** out);
+void bbm_destroy(bbm_ctx* ctx);
+int  bbm_set_band(bbm_ctx* ctx, int32_t bandwidth, float bandwidthRatio);
+const char* bbm_last_error(void);
+int  bbm_device_count(void);
+
+/* Reference / read residency: copy host bytes to device buffers owned by the context (returns device pointer). */
+int  bbm_upload(bbm_ctx* ctx, const void* host, int64_t nbytes, void** dev_out);
+int  bbm_free_dev(bbm_ctx* ctx, void* dev);
+
+/* Batched MultiStateAligner11ts — everything already resident in device memory (pointers are device pointers).
+ * match_off has ntasks+1 entries; task i's match string is written at match_buf+match_off[i] (capacity
+ * match_off[i+1]-match_off[i], rows+columns is always enough without '-' symbols).  `stream` is a cudaStream_t (or 0).
+ * kernel_ms_out (optional, host) receives the device time of the launches measured with CUDA events. */
+int  bbm_msa_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_refs, const bbm_msa_task* d_tasks,
+                       bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match_buf, const int64_t* d_match_off,
+                       int32_t max_rows, int32_t max_cols, void* stream, float* kernel_ms_out);
+
+/* Same, from HOST buffers: copies tasks/reads in, runs, copies outs/match strings back (the reference-facing call;
+ * the reference arrays `d_refs` stay resident, uploaded once with bbm_upload like the reference keeps chromosomes
+ * in memory, dna/Data.java).  reads_bytes = size of the reads buffer. */
+int  bbm_msa_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs,
+                        const bbm_msa_task* tasks, bbm_msa_out* outs, int64_t ntasks,
+                        int8_t* match_buf, const int64_t* match_off);
+
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+int64_t bbm_launch_count(const bbm_ctx* ctx);
+
+/* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
+ * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
+ * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2
+ * keep working on it; the penalty tables are fixed to the 11ts constants (the arrays are accepted and ignored). */
+int  bbm_fillUnlimited(bbm_ctx* ctx, const int8_t* read, const int8_t* ref, int32_t read_length, int32_t ref_length,
+                       int32_t refStartLoc, int32_t refEndLoc, int32_t* result4, int64_t* iterationsUnlimited,
+                       int32_t* packed, int32_t maxRows, int32_t maxColumns);
+int  bbm_fillLimitedX(bbm_ctx* ctx, const int8_t* read, const int8_t* ref, int32_t read_length, int32_t ref_length,
+                      int32_t refStartLoc, int32_t refEndLoc, int32_t minScore, int32_t* result5, int64_t* iterationsLimited,
+                      int32_t* packed, int32_t maxRows, int32_t maxColumns, int32_t bandwidth, float bandwidthRatio,
+                      int32_t* vertLimit, int32_t* horizLimit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBMAP_CUDA_H */

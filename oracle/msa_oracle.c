@@ -181,6 +181,10 @@ void orc_fill_unlimited(const int8_t* read, const int8_t* ref, int32_t read_leng
     result[0] = rows; result[1] = maxCol; result[2] = maxState; result[3] = maxScore >> TBITS;
 }
 
+/* optional per-row trace of the visited interval (analysis aid for kernel design; not thread-safe) */
+static int32_t* g_row_trace = 0;
+void orc_set_row_trace(int32_t* buf) { g_row_trace = buf; }
+
 /* ---- port of fillLimitedX (jni/...JNI.c:361-704) ---- */
 void orc_fill_limitedX(const int8_t* read, const int8_t* ref, int32_t read_length, int32_t ref_length,
                        int32_t refStartLoc, int32_t refEndLoc, int32_t minScore, int32_t* result, int64_t* iterations,
@@ -227,6 +231,7 @@ void orc_fill_limitedX(const int8_t* read, const int8_t* ref, int32_t read_lengt
         const int32_t vlimit = vertLimit[row];
         if (colStart < 0 || colStop < colStart) break;
         const int64_t up = (int64_t)(row - 1) * stride, cur = (int64_t)row * stride;
+        if (g_row_trace) { g_row_trace[2 * row] = colStart; g_row_trace[2 * row + 1] = colStart - 1; }
         if (colStart > 1) { M[cur + colStart - 1] = subfloor; I[cur + colStart - 1] = subfloor; D[cur + colStart - 1] = subfloor; }
         const int8_t c1 = read[row - 1], c0 = row < 2 ? (int8_t)'?' : read[row - 2];
 
@@ -297,6 +302,7 @@ void orc_fill_limitedX(const int8_t* read, const int8_t* ref, int32_t read_lengt
                 if (score >= limit2) { maxGoodCol = col; if (minGoodCol < 0) minGoodCol = col; } else score = subfloor;
                 I[cur + col] = score | clampt(time);
             }
+            if (g_row_trace) g_row_trace[2 * row + 1] = col;
             if (col >= colStop) {
                 if (col > colStop && (maxGoodCol < col || halfband > 0)) break;
                 if (row > 1) { M[up + col + 1] = subfloor; I[up + col + 1] = subfloor; D[up + col + 1] = subfloor; }

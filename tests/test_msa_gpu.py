@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA MultiStateAligner11ts path (through the C ABI) vs the CPU oracle, bit-exact:
+result vector, which fill ran, the reference's iteration counter, score2 vector, match string."""
+import numpy as np
+import pytest
+
+from bbmap_b200 import workloads as wl
+from kat import KATS, REF, MINSCORE, B, rle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def msa():
+    from bbmap_b200.msa import MultiStateAligner11tsCUDA
+    m = MultiStateAligner11tsCUDA()
+    yield m
+    m.close()
+
+
+def _compare(oracle, msa, reads, genome, tasks, bw=0, ratio=0.0, kind="port"):
+    moff = wl.match_offsets(tasks)
+    exp, emb, cells = oracle.run_batch(reads, genome, tasks, match_off=moff, bandwidth=bw, ratio=ratio, kind=kind, threads=8)
+    msa.set_band(bw, ratio)
+    d_ref = msa.load_reference(genome)
+    try:
+        got, gmb = msa.align_batch(reads, d_ref, tasks, match_off=moff)
+    finally:
+        msa.free(d_ref)
+    bad = [i for i in range(len(tasks)) if got[i].tobytes() != exp[i].tobytes()]
+    if bad:
+        i = bad[0]
+        raise AssertionError("%d/%d tasks differ; first %d\n task=%s\n got=%s\n exp=%s" % (len(bad), len(tasks), i, tasks[i], got[i], exp[i]))
+    for i in range(len(tasks)):
+        n = exp[i]["match_len"]
+        if n > 0:
+            a = moff[i]
+            assert gmb[a:a + n].tobytes() == emb[a:a + n].tobytes(), "match string differs for task %d: %s vs %s" % (
+                i, rle(gmb[a:a + n]), rle(emb[a:a + n]))
+    return exp
+
+
+def test_kats(oracle, msa):
+    ref = B(REF)
+    for name, read, a, b, fn, bw, result, iters, score2, match in KATS:
+        r = B(read)
+        tasks = np.zeros(1, wl.TASK_DTYPE)
+        tasks[0] = (0, 0, len(r), len(ref), a, b, MINSCORE, (wl.TF_RAW_LIMITED if fn == "limited" else wl.TF_RAW_UNLIMITED) | wl.TF_SCORE | wl.TF_TRACEBACK)
+        msa.set_band(bw, 0.0)
+        d_ref = msa.load_reference(ref)
+        outs, mbuf = msa.align_batch(r, d_ref, tasks)
+        msa.free(d_ref)
+        o = outs[0]
+        assert o["status"] == 0, name
+        assert o["result"][: len(result)].tolist() == result, name
+        if iters is not None:
+            assert o["iterations"] == iters, name
+        if score2 is None:
+            assert o["score_len"] == 0 and o["match_len"] == -1
+        else:
+            assert o["score"][: len(score2)].tolist() == score2 and o["score_len"] == len(score2), name
+            assert rle(mbuf[: o["match_len"]]) == match, name
+
+
+@pytest.mark.parametrize("mode", ["java", "raw_limited", "raw_unlimited"])
+@pytest.mark.parametrize("tight", [True, False])
+def test_random_noband(oracle, msa, mode, tight):
+    genome = wl.random_genome(50000, seed=21)
+    flags = wl.TF_SCORE | wl.TF_TRACEBACK | {"java": 0, "raw_limited": wl.TF_RAW_LIMITED, "raw_unlimited": wl.TF_RAW_UNLIMITED}[mode]
+    reads, tasks = wl.make_msa_tasks(genome, 3000 if mode != "raw_unlimited" else 600, seed=31, flags=flags, tight=tight,
+                                     ratio=0.56 if tight else 0.336)
+    if mode == "raw_limited":
+        tasks["min_score"] -= 120
+    exp = _compare(oracle, msa, reads, genome, tasks)
+    if mode != "raw_unlimited":
+        assert (exp["result"][:, 4] == 1).any() and (exp["match_len"] > 0).any()
+
+
+@pytest.mark.parametrize("bw,ratio", [(12, 0.0), (40, 0.0), (0, 0.18), (8, 0.3)])
+def test_random_banded(oracle, msa, bw, ratio):
+    genome = wl.random_genome(50000, seed=22)
+    for tight in (True, False):
+        reads, tasks = wl.make_msa_tasks(genome, 1500, seed=41 + bw, flags=wl.TF_SCORE | wl.TF_TRACEBACK, tight=tight)
+        _compare(oracle, msa, reads, genome, tasks, bw=bw, ratio=ratio)
+
+
+def test_odd_shapes(oracle, msa):
+    """short reads (unlimited rule), long reads, wide windows (generic kernel), N-rich reference, clamped windows."""
+    genome = wl.random_genome(30000, seed=23).copy()
+    genome[5000:5040] = ord("N")
+    genome[:50] = ord("N")
+    genome[-50:] = ord("N")
+    rng = np.random.Generator(np.random.PCG64(7))
+    reads_l, tasks_l, off = [], [], 0
+    def add(pos, L, a, b, ms, flags):
+        nonlocal off
+        r = genome[pos:pos + L].copy()
+        for k in rng.integers(0, L, size=max(1, L // 60)):
+            r[k] = wl.ACGT[rng.integers(0, 4)]
+        reads_l.append(r)
+        tasks_l.append((off, 0, L, len(genome), a, b, ms, flags))
+        off += L
+    F = wl.TF_SCORE | wl.TF_TRACEBACK
+    for L in (20, 31, 40, 45, 64, 100, 199, 250, 300, 400, 600):
+        for pad in (0, 4, 17, 60):
+            pos = int(rng.integers(200, len(genome) - L - 300))
+            add(pos, L, pos - pad, pos + L - 1 + pad, int(0.5 * wl.max_quality(L)), F)
+            add(pos, L, pos - pad, pos + L - 1 + pad, int(0.5 * wl.max_quality(L)), F | wl.TF_RAW_LIMITED)
+            add(pos, L, pos - pad, pos + L - 1 + pad, 0, F | wl.TF_RAW_UNLIMITED)
+    # windows over the N block, over the array ends (clamped), and narrower than the read
+    for L in (100, 150):
+        add(4960, L, 4950, 4960 + L + 10, 2000, F)
+        add(10, L, -5, 10 + L + 3, 2000, F | wl.TF_CLAMP)
+        add(len(genome) - L - 10, L, len(genome) - L - 14, len(genome) + 5, 2000, F | wl.TF_CLAMP)
+        add(7000, L, 7004, 7000 + L - 5, 1000, F)
+        add(7000, L, 7000, 7000 + L + 700, 3000, F)            # wide: unlimited by the Java rule
+        add(7000, L, 6990, 7000 + L + 900, 3000, F | wl.TF_RAW_LIMITED)   # wider than 512 columns: generic kernel
+    reads = np.concatenate(reads_l)
+    tasks = np.array(tasks_l, dtype=wl.TASK_DTYPE)
+    _compare(oracle, msa, reads, genome, tasks)
+    _compare(oracle, msa, reads, genome, tasks, bw=20)
+
+
+def test_reference_kind_agrees(oracle, msa):
+    """Same comparison against the reference's own C (oracle/_ref), when it was built."""
+    if not oracle.has_reference:
+        pytest.skip("oracle/_ref not present")
+    genome = wl.random_genome(50000, seed=24)
+    reads, tasks = wl.make_msa_tasks(genome, 1500, seed=51, flags=wl.TF_SCORE | wl.TF_TRACEBACK)
+    _compare(oracle, msa, reads, genome, tasks, kind="reference")
+
+
+def test_invalid_and_empty(msa):
+    genome = wl.random_genome(1000, seed=25)
+    d_ref = msa.load_reference(genome)
+    outs, _ = msa.align_batch(np.zeros(4, np.int8), d_ref, np.zeros(0, wl.TASK_DTYPE))
+    assert len(outs) == 0
+    tasks = np.zeros(2, wl.TASK_DTYPE)
+    tasks[0] = (0, 0, 0, 1000, 10, 50, 100, 0)          # empty read
+    tasks[1] = (0, 0, 4, 1000, 60, 50, 100, 0)          # refEnd < refStart
+    outs, _ = msa.align_batch(np.frombuffer(b"ACGT", np.int8), d_ref, tasks)
+    assert (outs["status"] == -3).all()
+    msa.free(d_ref)
