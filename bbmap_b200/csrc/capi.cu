@@ -11,10 +11,14 @@
 
 using namespace bbm;
 
-#define DECL_W(W) extern "C" int bbm_launch_msa_tiled_w##W(const MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
+#define DECL_W(W) extern "C" int bbm_launch_msa_tiled_w##W(const MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
 DECL_W(4) DECL_W(5) DECL_W(6) DECL_W(8) DECL_W(9) DECL_W(12) DECL_W(16)
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* counts, cudaStream_t stream);
-extern "C" int bbm_launch_msa_scatter(long long ntasks, const unsigned char* cls, unsigned int* cursors, int* lists, cudaStream_t stream);
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, cudaStream_t stream);
+extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream);
+extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n, unsigned int* cb, unsigned long long* tb, long long tbWordsPerWarp,
+                                     int* lists, int blocks, cudaStream_t stream);
+extern "C" int bbm_msa_narrow_threads();
+extern "C" int bbm_msa_narrow_buckets();
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
 extern "C" int bbm_msa_num_wclass();
@@ -61,7 +65,9 @@ struct bbm_ctx {
     int bandwidth = 0; float ratio = 0.f;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf scratch, counters, overflow, gscratch, lists, cls;
+    DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
+    int use_narrow = 1;
+    long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
     DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump;   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
@@ -92,7 +98,7 @@ extern "C" int bbm_init(int device, bbm_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    if (c->counters.ensure(64 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
+    if (c->counters.ensure(256 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
     *out = c;
     return BBM_OK;
 }
@@ -102,7 +108,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
-    c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release();
+    c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
     c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release();
     c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -138,8 +144,7 @@ extern "C" int bbm_free_dev(bbm_ctx* c, void* dev) {
 
 extern "C" int64_t bbm_launch_count(const bbm_ctx* c) { return c ? c->launches : 0; }
 
-// Counter block layout (32-bit words): [0..8] class counts, [16..24] scatter cursors, [32..40] per-class work counters,
-// [48] overflow count (banded right-edge misses reported by the tiled kernels).
+// Counter block layout: see CB_* in msa_kernels.cuh.
 static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_msa_task* d_tasks, bbm_msa_out* d_outs,
                    int64_t ntasks, int8_t* d_match, const int64_t* d_moff, int max_rows, int max_cols, cudaStream_t st,
                    float* ms_out, int* d_dump) {
@@ -149,45 +154,61 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     if (max_cols < 1) max_cols = 3000;
     const int wpb = bbm_msa_warps_per_block();
     const int nw = bbm_msa_num_wclass();
+    const int nb = bbm_msa_narrow_buckets();
     const int tiledRows = max_rows < MAXR ? max_rows : MAXR;
     const long long words = (long long)(tiledRows + 40) * 32;           // one 64-bit code word per (step,lane)
+    const int narrowBlocks = c->sms * 3;
+    const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
+    const int useNarrow = (c->use_narrow && d_dump == nullptr) ? 1 : 0;
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
+    if (useNarrow && c->nscratch.ensure((size_t)narrowWarps * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc narrow traceback scratch");
     if (c->overflow.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc overflow list");
     if (c->lists.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc class lists");
+    if (useNarrow && c->nlist.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc narrow list");
     if (c->cls.ensure((size_t)ntasks + 16)) return fail(BBM_E_CUDA, "cudaMalloc class ids");
-    unsigned int* cnt = (unsigned int*)c->counters.p;
+    unsigned int* cb = (unsigned int*)c->counters.p;
     MsaParams P;
     P.reads = d_reads; P.refs = d_refs; P.tasks = d_tasks; P.outs = d_outs; P.ntasks = ntasks;
     P.match_buf = d_match; P.match_off = (const long long*)d_moff;
     P.bandwidth = c->bandwidth; P.ratio = c->ratio;
     P.scratch = (unsigned long long*)c->scratch.p; P.scratch_words = words;
-    P.counter = nullptr; P.overflow_count = cnt + 48;
+    P.counter = nullptr; P.overflow_count = cb + 48;
     P.overflow_list = (int*)c->overflow.p;
     P.dump = d_dump;
-    CK(cudaMemsetAsync(c->counters.p, 0, 64 * 4, st));
+    CK(cudaMemsetAsync(c->counters.p, 0, 192 * 4, st));
     CK(cudaEventRecord(c->ev0, st));
-    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cnt, st);
+    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cb, useNarrow, st);
     if (e) return fail(BBM_E_CUDA, "msa_classify_kernel launch", (cudaError_t)e);
     c->launches++;
-    unsigned int h_cnt[16];
-    CK(cudaMemcpyAsync(h_cnt, cnt, 16 * 4, cudaMemcpyDeviceToHost, st));
+    unsigned int h[192];
+    CK(cudaMemcpyAsync(h, cb, 192 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    unsigned int h_base[16]; unsigned int acc = 0;
-    for (int k = 0; k <= nw; ++k) { h_base[k] = acc; acc += h_cnt[k]; }
-    for (int k = nw + 1; k < 16; ++k) h_base[k] = acc;
-    CK(cudaMemcpyAsync(cnt + 16, h_base, 16 * 4, cudaMemcpyHostToDevice, st));
-    e = bbm_launch_msa_scatter(ntasks, (const unsigned char*)c->cls.p, cnt + 16, (int*)c->lists.p, st);
+    unsigned int base[16]; unsigned int acc = 0;
+    for (int k = 0; k < 16; ++k) { base[k] = acc; if (k <= nw) acc += h[k]; }
+    unsigned int nbase[64]; unsigned int nacc = 0;
+    for (int k = 0; k < 64; ++k) { nbase[k] = nacc; if (k < nb) nacc += h[64 + k]; }
+    CK(cudaMemcpyAsync(cb + 16, base, 16 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cb + 128, nbase, 64 * 4, cudaMemcpyHostToDevice, st));
+    e = bbm_launch_msa_scatter(&P, (const unsigned char*)c->cls.p, cb, (int*)c->lists.p, (int*)c->nlist.p, st);
     if (e) return fail(BBM_E_CUDA, "msa_scatter_kernel launch", (cudaError_t)e);
     c->launches++;
-    typedef int (*launch_fn)(const MsaParams*, const int*, int, unsigned int*, int, int, cudaStream_t);
+    if (nacc > 0) {
+        int blocks = narrowBlocks;
+        const long long need = ((long long)nacc + bbm_msa_narrow_threads() - 1) / bbm_msa_narrow_threads();
+        if (need < blocks) blocks = (int)need;
+        e = bbm_launch_msa_narrow(&P, (const int*)c->nlist.p, (int)nacc, cb, (unsigned long long*)c->nscratch.p, words, (int*)c->lists.p, blocks, st);
+        if (e) return fail(BBM_E_CUDA, "msa_narrow_kernel launch", (cudaError_t)e);
+        c->launches++;
+    }
+    typedef int (*launch_fn)(const MsaParams*, const int*, int, const unsigned int*, unsigned int, unsigned int*, int, int, cudaStream_t);
     static const launch_fn fns[7] = { bbm_launch_msa_tiled_w4, bbm_launch_msa_tiled_w5, bbm_launch_msa_tiled_w6, bbm_launch_msa_tiled_w8,
                                       bbm_launch_msa_tiled_w9, bbm_launch_msa_tiled_w12, bbm_launch_msa_tiled_w16 };
     for (int k = 0; k < nw; ++k) {
-        if (!h_cnt[k]) continue;
+        if (!h[k]) continue;                       // no task of this width at all (narrow hand-overs included in h[k])
         int blocks = c->blocks;
-        const long long needBlocks = ((long long)h_cnt[k] + wpb - 1) / wpb;
+        const long long needBlocks = ((long long)h[k] + wpb - 1) / wpb;
         if (needBlocks < blocks) blocks = (int)needBlocks;
-        e = fns[k](&P, (const int*)c->lists.p + h_base[k], (int)h_cnt[k], cnt + 32 + k, blocks, d_dump != nullptr, st);
+        e = fns[k](&P, (const int*)c->lists.p + base[k], 0, cb + 16 + k, base[k], cb + 32 + k, blocks, d_dump != nullptr, st);
         if (e) return fail(BBM_E_CUDA, "msa_tiled_kernel launch", (cudaError_t)e);
         c->launches++;
     }
@@ -206,19 +227,47 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
         }
         return BBM_OK;
     };
-    int rc = run_generic((const int*)c->lists.p + h_base[nw], h_cnt[nw]);       // shapes outside the tiled kernels
+    int rc = run_generic((const int*)c->lists.p + base[nw], h[nw]);       // shapes outside the tiled kernels
     if (rc) return rc;
     if (c->bandwidth > 0 || c->ratio > 0.f) {
         unsigned int nover = 0;
-        CK(cudaMemcpyAsync(&nover, cnt + 48, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&nover, cb + 48, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         rc = run_generic((const int*)c->overflow.p, nover);                   // banded right-edge misses
         if (rc) return rc;
+        c->band_misses += nover;
     }
     CK(cudaEventRecord(c->ev1, st));
+    unsigned int hend[16];
+    CK(cudaMemcpyAsync(hend, cb + 16, 16 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    {   // bookkeeping: how many alignments the narrow kernel tried / handed over to the tiled kernels
+        long long tiledTotal = 0;
+        for (int k = 0; k < nw; ++k) tiledTotal += (long long)hend[k] - base[k];
+        long long direct = 0;
+        for (int k = 0; k < nw; ++k) direct += h[k];
+        direct -= nacc;                                   // tasks that went straight to a tiled list
+        c->narrow_tried += nacc;
+        c->narrow_handed_over += tiledTotal - direct;
+        c->tasks_total += ntasks;
+    }
     return BBM_OK;
+}
+
+extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
+    if (!c || !key) return fail(BBM_E_ARG, "bbm_set_option: null");
+    if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
+    return fail(BBM_E_ARG, "bbm_set_option: unknown key");
+}
+extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
+    if (!c || !key) return -1;
+    if (!strcmp(key, "band_misses")) return c->band_misses;
+    if (!strcmp(key, "launches")) return c->launches;
+    if (!strcmp(key, "narrow_tried")) return c->narrow_tried;
+    if (!strcmp(key, "narrow_handed_over")) return c->narrow_handed_over;
+    if (!strcmp(key, "tasks_total")) return c->tasks_total;
+    return -1;
 }
 
 extern "C" int bbm_msa_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_msa_task* d_tasks,

@@ -2,34 +2,45 @@
 #include <cstdio>
 #include "msa_kernels.cuh"
 #include "msa_generic.cuh"
+#include "msa_narrow.cuh"
 
 namespace bbm {
 
 // pass 1: class of every task + per-class counts; pass 2: scatter ids into per-class lists
-__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* counts) {
+__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* cb, int useNarrow) {
     __shared__ unsigned int local[NUM_CLASS];
+    __shared__ unsigned int localNb[NARROW_BUCKETS];
     if (threadIdx.x < NUM_CLASS) local[threadIdx.x] = 0;
+    if (threadIdx.x < NARROW_BUCKETS) localNb[threadIdx.x] = 0;
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.ntasks) {
         TaskCtx T;
         const bbm_msa_task task = P.tasks[i];
         int k = CLASS_BAD;
-        if (resolve_task(task, P.bandwidth, P.ratio, T)) k = classify(T);
-        else { bbm_msa_out o = {}; o.status = BBM_E_ARG; o.match_len = -1; P.outs[i] = o; }
+        if (resolve_task(task, P.bandwidth, P.ratio, T)) {
+            k = classify(T);
+            atomicAdd(&local[k], 1u);
+            if (useNarrow && narrow_eligible(T)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
+        } else { bbm_msa_out o = {}; o.status = BBM_E_ARG; o.match_len = -1; P.outs[i] = o; }
         cls[i] = (unsigned char)k;
-        atomicAdd(&local[k], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < NUM_CLASS && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], local[threadIdx.x]);
+    if (threadIdx.x < NUM_CLASS && local[threadIdx.x]) atomicAdd(&cb[CB_COUNTS + threadIdx.x], local[threadIdx.x]);
+    if (threadIdx.x < NARROW_BUCKETS && localNb[threadIdx.x]) atomicAdd(&cb[CB_NB_COUNTS + threadIdx.x], localNb[threadIdx.x]);
 }
 
-__global__ void msa_scatter_kernel(long long ntasks, const unsigned char* cls, unsigned int* cursors, int* lists) {
+__global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntasks) return;
+    if (i >= P.ntasks) return;
     const int k = cls[i];
+    if (k & CLS_NARROW_BIT) {
+        const unsigned pos = atomicAdd(&cb[CB_NB_CURSORS + narrow_bucket(P.tasks[i].read_len)], 1u);
+        nlist[pos] = (int)i;
+        return;
+    }
     if (k >= CLASS_BAD) return;
-    const unsigned pos = atomicAdd(&cursors[k], 1u);
+    const unsigned pos = atomicAdd(&cb[CB_CURSORS + k], 1u);
     lists[pos] = (int)i;
 }
 
@@ -47,16 +58,23 @@ __global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int*
 
 using namespace bbm;
 
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* counts, cudaStream_t stream) {
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, cudaStream_t stream) {
     const int threads = 256;
-    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, counts);
+    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, useNarrow);
     return (int)cudaGetLastError();
 }
-extern "C" int bbm_launch_msa_scatter(long long ntasks, const unsigned char* cls, unsigned int* cursors, int* lists, cudaStream_t stream) {
+extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream) {
     const int threads = 256;
-    msa_scatter_kernel<<<(unsigned)((ntasks + threads - 1) / threads), threads, 0, stream>>>(ntasks, cls, cursors, lists);
+    msa_scatter_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, lists, nlist);
     return (int)cudaGetLastError();
 }
+extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n, unsigned int* cb, unsigned long long* tb, long long tbWordsPerWarp,
+                                     int* lists, int blocks, cudaStream_t stream) {
+    msa_narrow_kernel<<<blocks, NARROW_THREADS, 0, stream>>>(*P, nlist, n, cb + CB_NARROW_WORK, tb, tbWordsPerWarp, cb + CB_CURSORS, lists);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_msa_narrow_threads() { return NARROW_THREADS; }
+extern "C" int bbm_msa_narrow_buckets() { return NARROW_BUCKETS; }
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream) {
     const int threads = 64;
     msa_generic_kernel<<<(nlist + threads - 1) / threads, threads, 0, stream>>>(*P, list, nlist, gscratch, gstride);

@@ -41,6 +41,12 @@ __host__ __device__ constexpr int wclass_width(int k) { return k == 0 ? 4 : k ==
 constexpr int CLASS_GENERIC = NUM_WCLASS;      // row-sequential kernel
 constexpr int CLASS_BAD = NUM_WCLASS + 1;      // invalid task
 constexpr int NUM_CLASS = NUM_WCLASS + 2;
+constexpr int CLS_NARROW_BIT = 0x80;           // class byte flag: first try the thread-per-alignment narrow kernel
+// counter block (32-bit words)
+constexpr int CB_COUNTS = 0, CB_CURSORS = 16, CB_WORK = 32, CB_OVERFLOW = 48, CB_NARROW_WORK = 49;
+constexpr int CB_NB_COUNTS = 64, CB_NB_CURSORS = 128, CB_WORDS = 192;
+constexpr int NARROW_BUCKETS = 40;             // narrow list is ordered by read length (rows-1)/16 so warps are uniform
+__host__ __device__ constexpr int narrow_bucket(int rows) { return (rows - 1) / 16 < NARROW_BUCKETS - 1 ? (rows - 1) / 16 : NARROW_BUCKETS - 1; }
 
 __device__ __forceinline__ int classify(const TaskCtx& T) {
     const int w = (T.cols + 31) >> 5;
@@ -51,7 +57,7 @@ __device__ __forceinline__ int classify(const TaskCtx& T) {
 constexpr int WARPS_PER_BLOCK = 4;
 
 template <int W, bool DUMP>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) msa_tiled_kernel(MsaParams P, const int* __restrict__ list, int nlist, unsigned int* counter) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) msa_tiled_kernel(MsaParams P, const int* __restrict__ list, int nlist, const unsigned int* __restrict__ endPtr, unsigned int base, unsigned int* counter) {
     __shared__ BlockShared bs;
     __shared__ WarpShared wsAll[WARPS_PER_BLOCK];
     for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) { bs.insc[i] = ins_score_offset(i); bs.delc[i] = del_score_offset(i); }
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) msa_tiled_kernel(MsaPara
     WarpShared& ws = wsAll[warp];
     const long long gwarp = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     unsigned long long* scratch = P.scratch + gwarp * P.scratch_words;
+    if (endPtr) nlist = (int)(*endPtr - base);        // list length decided on the device (narrow-kernel hand-overs included)
     for (;;) {
         unsigned k = 0;
         if (lane == 0) k = atomicAdd(counter, 1u);
@@ -78,12 +85,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) msa_tiled_kernel(MsaPara
 }
 
 #define BBM_DECLARE_TILED_LAUNCH(W) \
-    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
+    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
 
 #define BBM_DEFINE_TILED_LAUNCH(W) \
-    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, unsigned int* counter, int blocks, int dump, cudaStream_t stream) { \
-        if (dump) bbm::msa_tiled_kernel<W, true><<<1, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, counter); \
-        else bbm::msa_tiled_kernel<W, false><<<blocks, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, counter); \
+    extern "C" int bbm_launch_msa_tiled_w##W(const bbm::MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, unsigned int* counter, int blocks, int dump, cudaStream_t stream) { \
+        if (dump) bbm::msa_tiled_kernel<W, true><<<1, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, endPtr, base, counter); \
+        else bbm::msa_tiled_kernel<W, false><<<blocks, bbm::WARPS_PER_BLOCK * 32, 0, stream>>>(*P, list, nlist, endPtr, base, counter); \
         return (int)cudaGetLastError(); \
     }
 

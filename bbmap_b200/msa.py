@@ -68,22 +68,30 @@ class MultiStateAligner11tsCUDA:
     def free(self, d):
         _lib.check(self.L.bbm_free_dev(self.h, d), "bbm_free_dev")
 
+    def set_option(self, key, value):
+        _lib.check(self.L.bbm_set_option(self.h, key.encode(), int(value)), "bbm_set_option")
+
+    def stat(self, key):
+        return int(self.L.bbm_get_stat(self.h, key.encode()))
+
     @property
     def launches(self):
         return int(self.L.bbm_launch_count(self.h))
 
     # -- the batched plug-in call (host buffers in, host buffers out) --
-    def align_batch(self, reads, d_ref, tasks, match_off=None):
+    def align_batch(self, reads, d_ref, tasks, match_off=None, outs=None, mbuf=None):
         """Runs every task (see include/bbmap_cuda.h: bbm_msa_task) and returns (outs, match_buf).
         tasks['flags'] selects fillLimited (Java rule), raw fillLimitedX or raw fillUnlimited, and whether
         score2 / traceback2 follow."""
         reads = np.ascontiguousarray(reads).view(np.int8)
         tasks = np.ascontiguousarray(tasks, TASK_DTYPE)
-        outs = np.zeros(len(tasks), OUT_DTYPE)
+        if outs is None:
+            outs = np.zeros(len(tasks), OUT_DTYPE)
         want_tb = bool(len(tasks)) and bool((tasks["flags"] & TF_TRACEBACK).any())
         if want_tb and match_off is None:
             match_off = match_offsets(tasks)
-        mbuf = np.zeros(int(match_off[-1]) if want_tb else 1, np.int8)
+        if mbuf is None:
+            mbuf = np.zeros(int(match_off[-1]) if want_tb else 1, np.int8)
         moff = np.ascontiguousarray(match_off, np.int64) if want_tb else None
         _lib.check(self.L.bbm_msa_batch_host(self.h, _p(reads), reads.size, d_ref, _p(tasks), _p(outs), len(tasks),
                                             _p(mbuf) if want_tb else None, _p(moff) if want_tb else None), "bbm_msa_batch_host")

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — MultiStateAligner11ts microbenchmark (BASELINE.json configs[2], SURVEY.md §8d workload G4).
+
+One "step" = one pass of the hot path (fillLimited rule -> fillLimitedX/fillUnlimited -> score2 -> traceback2) over one
+batch of synthetic (read, candidate window) tasks.  Metric: DP GCUPS = the reference's own cell counter
+(iterationsLimited+iterationsUnlimited, jni/MultiStateAligner11tsJNI.c:138,471) summed over the batch / seconds.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--tasks T] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer
+plug-in call (H2D of tasks+reads and D2H of results inside the timed region).  `--impl reference` times the
+reference's own C (oracle/_ref, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bbmap_b200 import workloads as wl  # noqa: E402
+
+GENOME_LEN = 4_600_000      # "E. coli-sized" resident reference the windows point into
+METRIC = "MSA fill GCUPS (MultiStateAligner11ts fillLimited+score+traceback, reference cell count / s)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--tasks", type=int, default=400_000, help="alignments per step per GPU")
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--bandwidth", type=int, default=0)
+    ap.add_argument("--ratio", type=float, default=0.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-narrow", action="store_true", help="disable the thread-per-alignment narrow kernel (A/B)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(reads, genome, tasks, moff, bw, ratio, budget_s=15.0, threads=None):
+    """Times the reference's own C (oracle/_ref) — or the port if it is absent — on a bounded sample."""
+    from oracle import oracle as orc
+    o = orc.get()
+    kind = "reference" if o.has_reference else "port"
+    threads = threads or (os.cpu_count() or 1)
+    probe = min(len(tasks), 64 * threads)
+    t0 = time.perf_counter()
+    _, _, cells = o.run_batch(reads, genome, tasks[:probe], match_off=moff[:probe + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
+    dt = time.perf_counter() - t0
+    n = int(min(len(tasks), max(probe, probe * budget_s / max(dt, 1e-4))))
+    t0 = time.perf_counter()
+    outs, _, cells = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
+            "sample": "first %d of %d alignments of the step batch, %.1f s, %d threads, one private packed matrix per thread" % (n, len(tasks), dt, threads),
+            "seconds": dt, "cells": cells, "tasks": n}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    lengths = (100, 150, 250)
+    config = {"workload": "configs[2] MSA11ts microbenchmark G4: %d alignments/step/GPU, read length {100,150,250}, window = locus +-4, "
+                          "70%% ~1%% subs / 20%% 1-40bp indel / 10%% unrelated, minScore=max(scoreNoIndels, 0.56*maxQ-258), "
+                          "fillLimited rule + score2 + traceback2; resident %d bp reference" % (args.tasks, GENOME_LEN),
+              "tasks_per_step_per_gpu": args.tasks, "bandwidth": args.bandwidth, "bandwidthRatio": args.ratio,
+              "l2": "inputs larger than L2 (tasks+reads+outs+match > 200 MB per step)"}
+
+    genome = wl.random_genome(GENOME_LEN, seed=1)
+    reads, tasks = wl.make_msa_tasks(genome, args.tasks, seed=2 + rank, lengths=lengths, flags=wl.TF_SCORE | wl.TF_TRACEBACK)
+    moff = wl.match_offsets(tasks)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # each step = a bounded sample sized so steps+warmup finish within minutes
+        from oracle import oracle as orc
+        o = orc.get()
+        kind = "reference" if o.has_reference else "port"
+        threads = os.cpu_count() or 1
+        n = min(len(tasks), 20000)
+        times, cells = [], 0
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _, _, c = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=args.bandwidth, ratio=args.ratio,
+                                  kind=kind, threads=threads)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt); cells += c
+        total = sum(times)
+        v = cells / total / 1e9
+        sample = "first %d alignments of the step batch per step, %d threads" % (n, threads)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
+                          "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import ctypes as C
+    from bbmap_b200.msa import MultiStateAligner11tsCUDA
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (bbmap_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    msa = MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio)
+    if args.no_narrow:
+        msa.set_option("narrow", 0)
+    dev = torch.device("cuda", local)
+    # resident inputs (torch owns the device memory; the C ABI takes raw pointers)
+    d_genome = torch.from_numpy(np.concatenate([genome, np.full(256, ord("N"), np.uint8)])).to(dev)
+    d_reads = torch.from_numpy(reads).to(dev)
+    d_tasks = torch.from_numpy(tasks.view(np.uint8)).to(dev)
+    d_moff = torch.from_numpy(moff).to(dev)
+    d_outs = torch.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_match = torch.zeros(int(moff[-1]) + 16, dtype=torch.uint8, device=dev)
+    max_rows = int(tasks["read_len"].max()); max_cols = int((tasks["ref_end"] - tasks["ref_start"] + 1).max())
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        return msa.align_batch_dev(d_reads.data_ptr(), d_genome.data_ptr(), d_tasks.data_ptr(), d_outs.data_ptr(), len(tasks),
+                                   d_match.data_ptr(), d_moff.data_ptr(), max_rows, max_cols, C.c_void_p(stream.cuda_stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    outs = np.frombuffer(d_outs.cpu().numpy().tobytes(), dtype=wl.OUT_DTYPE)
+    cells_per_step = int(outs["iterations"].sum())
+    assert (outs["status"] == 0).all(), "bench: some alignments returned an error status"
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    l0 = msa.launches
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        kernel_ms += step_dev()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = msa.launches - l0
+    # e2e: host buffers through the plug-in call, copies inside the timed region
+    d_ref_ptr = C.c_void_p(d_genome.data_ptr())
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()           # pinned host buffers, as a production host would hold
+    reads_p = pin(reads); tasks_p = pin(tasks.view(np.uint8)).view(wl.TASK_DTYPE); moff_p = pin(moff)
+    outs_p = pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE)
+    mbuf_p = pin(np.zeros(int(moff[-1]), np.int8))
+    msa.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=outs_p, mbuf=mbuf_p)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        h_outs, h_match = msa.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=outs_p, mbuf=mbuf_p)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish()
+    assert h_outs.tobytes() == outs.tobytes(), "host-buffer path and resident path disagree"
+
+    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, kernel_ms], dtype=torch.float64, device=dev)
+    c = torch.tensor([float(cells_per_step)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms_all, e2e_ms_step, kernel_ms_all = [float(x) for x in t.tolist()]
+    total_cells_step = float(c.item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = total_cells_step * args.steps / (ms_all / 1e3) / 1e9
+    e2e_value = total_cells_step / (e2e_ms_step / 1e3) / 1e9
+    pk, pk_kind = peaks()
+    # algorithmic HBM bytes per step: task + read + window + result + match string
+    cols = (tasks["ref_end"] - tasks["ref_start"] + 1).astype(np.int64)
+    alg_bytes = int(len(tasks) * (40 + 80) + tasks["read_len"].sum() + cols.sum() + np.maximum(outs["match_len"], 0).sum())
+    step_s = ms_all / 1e3 / args.steps
+    hbm_ach = alg_bytes / step_s / 1e9
+    h2d = int(tasks.nbytes + reads.nbytes + moff.nbytes)
+    d2h = int(outs.nbytes + moff[-1])
+    line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": config,
+            "alignments_per_s": len(tasks) * world / step_s,
+            "computed_cells_gcups": float((tasks["read_len"].astype(np.int64) * cols).sum()) * world / step_s / 1e9,
+            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_step},
+            "gpu_launches": int(launches),
+            "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
+                           "narrow_handed_over": msa.stat("narrow_handed_over"), "band_misses": msa.stat("band_misses")},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
+                         "traffic": None, "peak_kind": pk_kind,
+                         "note": "integer-issue-bound DP: algorithmic bytes/cell ~0.1; see DESIGN.md for the issue-slot roofline"}}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_run(reads, genome, tasks, moff, args.bandwidth, args.ratio)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

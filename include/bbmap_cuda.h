@@ -90,6 +90,12 @@ int  bbm_msa_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, 
                         const bbm_msa_task* tasks, bbm_msa_out* outs, int64_t ntasks,
                         int8_t* match_buf, const int64_t* match_off);
 
+/* Tuning / introspection.  bbm_set_option keys: "narrow" (1 = route near-diagonal limited fills through the
+ * thread-per-alignment kernel first; 0 = register-tiled kernel only).  bbm_get_stat keys: "launches", "band_misses"
+ * (banded alignments re-run by the row-sequential kernel). */
+int     bbm_set_option(bbm_ctx* ctx, const char* key, int value);
+int64_t bbm_get_stat(const bbm_ctx* ctx, const char* key);
+
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 
