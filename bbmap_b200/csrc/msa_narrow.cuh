@@ -16,6 +16,7 @@
 // iteration counter (from per-row minGoodCol/maxGoodCol), score2, traceback2 — is the same as the reference's.
 #pragma once
 #include "msa_kernels.cuh"
+#include "msa_cell.cuh"
 
 namespace bbm {
 
@@ -59,6 +60,7 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
     const int floor_ = minScore_off - maxGain;
     const int subfloor = floor_ - 5 * P_MATCH2;
     const int D = cols - rows;
+    CellConst K; K.floor_ = floor_; K.subfloor = subfloor;
 
     bool bail = false;
     // ---- suffix costs of the limits (jni/...JNI.c:413-438).  No '-' in the window => all costs >= 0, so
@@ -159,9 +161,10 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
         if (run) {
             const int cr = r + NDLO;                          // column of slot 0
             const int call1 = read[r - 1];
-            const bool callN = (call1 == 'N');
-            const int vlimit = (r == rows) ? minScore_off : imax(minScore_off - SvRun, floor_);
-            const bool delBar = (r < 3) || (r > rows - 3);
+            CellRow R;
+            R.call1 = call1; R.call0 = call0; R.callN = (call1 == 'N');
+            R.vlimit = (r == rows) ? minScore_off : imax(minScore_off - SvRun, floor_);
+            R.delBar = (r < 3) || (r > rows - 3);
             const bool insTop = (r < 2), insBot = (r > rows - 2);
             const int colStart = minGoodPrev;                 // halfband == 0 here
             const int col0 = sh.insc[imin(r, PEN_TAB - 1)];
@@ -176,93 +179,18 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
                 int uMS = subfloor, uIN = subfloor;                         // (r-1, c): diagonal to the right
                 if (j + 1 < NDW) { uMS = MS[j + 1]; uIN = IN[j + 1]; }
                 const int ref1 = rf[j];
-                int nMS = subfloor, nDL = subfloor, nIN = subfloor;
-                unsigned code = 0;
-                bool good = false;
                 const bool visit = (c >= colStart) && (c >= 1) && (c <= cols);
-                if (NDLO + j < 0 && c == 0) {
-                    nMS = col0; nDL = col0; nIN = col0;                    // column 0 of the matrix (…JNI.java:105-111)
-                } else if (visit) {
-                    const bool refN = (ref1 == 0x100);
-                    const bool match = (call1 == ref1);
-                    const bool prevMatch = (call0 == ref0);
-                    const int limit = imax(vlimit, hlr[j]);
-                    const int limit3 = imax(floor_, match ? limit - P_MATCH2 : limit - P_SUB3);
-                    const int delNeeded = (-(NDLO + j) - 1) > 0 ? (-(NDLO + j) - 1) : 0;      // max(0,row-col-1): fixed per diagonal
-                    const int insNeeded = imax(0, NDLO + j - D - 1);                            // max(0,(rows-row)-(cols-col)-1)
-                    int lim2MS = limit, lim2DL = limit, lim2IN = limit;
-                    if (delNeeded > 0 || insNeeded > 0) {
-                        const int delPen = del_score_offset(delNeeded);
-                        const int insPen = sh.insc[imin(insNeeded, PEN_TAB - 1)];
-                        lim2MS = delNeeded > 0 ? limit - delPen : limit - insPen;
-                        lim2DL = insNeeded > 0 ? limit - insPen : limit;
-                        lim2IN = delNeeded > 0 ? limit - delPen : limit;
-                    }
-                    {   // MS
-                        const int sM = dMS & SMASK, sD = dDL & SMASK, sI = dIN & SMASK, streak = dMS & TMASK;
-                        const bool skip = imax3(sM, sD, sI) <= limit3;
-                        int addMS, o;
-                        if (match) { addMS = prevMatch ? P_MATCH2 : P_MATCH; o = P_MATCH; }
-                        else {
-                            o = P_SUB;
-                            addMS = (refN || callN) ? 0 : (prevMatch ? (streak <= 1 ? P_SUBR : P_SUB)
-                                                                       : (streak == 0 ? P_SUB : (streak < 5 ? P_SUB2 : P_SUB3)));
-                        }
-                        const int a_ = sM + addMS, mx = imax(sD, sI) + o;
-                        const bool msWins = a_ >= mx;
-                        int score = imax(a_, mx);
-                        const int time = (msWins && (match == prevMatch)) ? streak + 1 : 1;
-                        code |= (time > 1) ? 0u : ((sM >= sD && sM >= sI) ? 0u : (sD >= sI ? 1u : 2u));
-                        const bool ok = score >= lim2MS;
-                        good = good || (ok && !skip);
-                        if (!ok) score = subfloor;
-                        nMS = skip ? subfloor : (score | time);
-                    }
-                    {   // DEL
-                        const int sM = lMS & SMASK, sD = lDL & SMASK, streak = lDL & TMASK;
-                        const bool skip = delBar || (imax(sM, sD) <= limit);
-                        const int ext = streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
-                                        (((streak & 3) == 0) ? P_DEL5 : 0))));
-                        const int adj = refN ? P_DEL_REF_N : 0;
-                        const int a_ = sM + P_DEL + adj, b_ = sD + ext + adj;
-                        const bool msWins = a_ >= b_;
-                        int score = imax(a_, b_);
-                        const int time = msWins ? 1 : streak + 1;
-                        int lim2 = lim2DL;
-                        if (delNeeded > 0) { if (insNeeded == 0) lim2 = limit - del_score_offset(time + delNeeded) + del_score_offset(time); }
-                        const bool ok = score >= lim2;
-                        good = good || (ok && !skip);
-                        if (!ok) score = subfloor;
-                        code |= ((time > 1) ? 1u : (sM >= sD ? 0u : 1u)) << 2;
-                        nDL = skip ? subfloor : (score | time);
-                    }
-                    {   // INS
-                        const int sM = uMS & SMASK, sI = uIN & SMASK, streak = uIN & TMASK;
-                        const bool skip = (insTop && c > 1) || (insBot && c < cols - 1) || (imax(sM, sI) <= limit);
-                        const int ext = streak == 0 ? P_INS : (streak < LIM3 ? P_INS2 : (streak < LIM4 ? P_INS3 : P_INS4));
-                        const int a_ = sM + P_INS, b_ = sI + ext;
-                        const bool msWins = a_ >= b_;
-                        int score = imax(a_, b_);
-                        const int time = msWins ? 1 : streak + 1;
-                        int lim2 = lim2IN;
-                        if (delNeeded == 0 && insNeeded > 0)
-                            lim2 = limit - sh.insc[imin(time + insNeeded, PEN_TAB - 1)] + sh.insc[imin(time, PEN_TAB - 1)];
-                        const bool ok = score >= lim2;
-                        good = good || (ok && !skip);
-                        if (!ok) score = subfloor;
-                        code |= ((time > 1) ? 1u : (sM >= sI ? 0u : 1u)) << 3;
-                        nIN = skip ? subfloor : (score | time);
-                    }
-                }
+                const int delNeeded = (-(NDLO + j) - 1) > 0 ? (-(NDLO + j) - 1) : 0;      // max(0,row-col-1): fixed per diagonal
+                const int insNeeded = imax(0, NDLO + j - D - 1);                            // max(0,(rows-row)-(cols-col)-1)
+                const bool insBar = (insTop && c > 1) || (insBot && c < cols - 1);
+                const CellOut o = msa_cell<true, false>(K, R, dMS, dDL, dIN, lMS, lDL, uMS, uIN, ref1, ref0,
+                                                        ref1 == 0x100, false, insBar, hlr[j], delNeeded, insNeeded, sh.insc, sh.delc);
+                int nMS = visit ? o.ms : subfloor, nDL = visit ? o.del : subfloor, nIN = visit ? o.ins : subfloor;
+                const unsigned code = o.code;
+                const bool good = visit && o.good;
+                if (NDLO + j < 0) { if (c == 0) { nMS = col0; nDL = col0; nIN = col0; } }   // column 0 of the matrix (…JNI.java:105-111)
                 word |= (unsigned long long)code << (4 * j);
-                if (good) gmask |= 1u << j;
-                if (r == rows && visit) {
-                    // final scan candidates (jni/...JNI.c:672-686): state-major, first max wins
-                    const int s0 = nMS & SMASK, s1 = nDL & SMASK, s2 = nIN & SMASK;
-                    if (s0 > bestScore || (s0 == bestScore && 0 < bestState)) { bestScore = s0; bestCol = c; bestState = 0; bestPacked = nMS; }
-                    if (s1 > bestScore || (s1 == bestScore && 1 < bestState)) { bestScore = s1; bestCol = c; bestState = 1; bestPacked = nDL; }
-                    if (s2 > bestScore) { bestScore = s2; bestCol = c; bestState = 2; bestPacked = nIN; }
-                }
+                gmask |= (good ? 1u : 0u) << j;
                 MS[j] = nMS; DL[j] = nDL; IN[j] = nIN;
                 lMS = nMS; lDL = nDL;
                 ref0 = ref1;
@@ -303,6 +231,20 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
     }
 
     if (!alive) return;
+    if (!bail && !broke) {
+        // final scan candidates (jni/...JNI.c:672-686): state-major, first max wins; registers hold the last row
+#pragma unroll
+        for (int st = 0; st < 3; ++st) {
+#pragma unroll
+            for (int j = 0; j < NDW; ++j) {
+                const int c = rows + NDLO + j;
+                const bool visit = (c >= lastColStart) && (c >= 1) && (c <= cols);
+                const int v = st == 0 ? MS[j] : (st == 1 ? DL[j] : IN[j]);
+                const int x = v & SMASK;
+                if (visit && x > bestScore) { bestScore = x; bestCol = c; bestState = st; bestPacked = v; }
+            }
+        }
+    }
     if (bail) {
         // hand over to the register-tiled kernel of the right width
         const int kcls = classify(T);

@@ -22,6 +22,7 @@
 // assumption is detected exactly and the alignment is re-run by the row-sequential generic kernel (msa_generic.cuh).
 #pragma once
 #include "msa_common.cuh"
+#include "msa_cell.cuh"
 
 namespace bbm {
 
@@ -88,6 +89,7 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
     const int floor_ = LIMITED ? minScore_off - maxGain : 0;
     const int subfloor = LIMITED ? floor_ - 5 * P_MATCH2 : 0 - 2 * maxGain;
     const int hb = T.halfband;
+    CellConst K; K.floor_ = floor_; K.subfloor = subfloor;
 
     // ---- stage the read; vertLimit (jni/...JNI.c:413-425) ----
     for (int i = lane; i < rows; i += 32) ws.read[i] = read[i];
@@ -213,24 +215,21 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
             mmInCur = MM_NONE; mmInPrev = MM_NONE;
         }
         if (active) {
-            const int call1 = ws.read[r - 1];
-            const int call0 = r < 2 ? '?' : ws.read[r - 2];
-            const bool callN = (call1 == 'N');
-            const int vlimit = LIMITED ? ws.vl[r] : 0;
-            const bool delBar = (r < 3) || (r > rows - 3);
+            CellRow R;
+            R.call1 = ws.read[r - 1];
+            R.call0 = r < 2 ? '?' : ws.read[r - 2];
+            R.callN = (R.call1 == 'N');
+            R.vlimit = LIMITED ? ws.vl[r] : 0;
+            R.delBar = (r < 3) || (r > rows - 3);
             const bool insTop = (r < 2), insBot = (r > rows - 2);
             const bool inP = LIMITED ? ((r == 1) || (mmInPrev != MM_NONE)) : true;
             unsigned gCur = 0;
             tbw word = 0;
             int ref0 = refLeft;
-            int lINSdump = 0;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const int c = c0 + j;
                 const int ref1 = refc[j];
-                int nMS, nDEL, nINS;
-                unsigned code = 0;
-                bool good = false;
                 const bool inRange = (c <= cols);
                 bool visit = inRange;
                 if (LIMITED) {
@@ -238,106 +237,21 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
                     visit = visit && leftOK;
                     if (BAND) visit = visit && (c >= r - hb) && (c <= r + 2 * hb);
                 }
-                if (visit) {
-                    const bool gap = (gapmask >> j) & 1u;
-                    const bool refN = (nmask >> j) & 1u;
-                    const bool match = (call1 == ref1);
-                    const bool prevMatch = (call0 == ref0);
-                    int limit = 0, limit3 = 0, lim2MS = 0, lim2DELbase = 0, lim2INSbase = 0;
-                    int delNeeded = 0, insNeeded = 0;
-                    if (LIMITED) {
-                        limit = imax(vlimit, hl[j]);
-                        limit3 = imax(floor_, match ? limit - P_MATCH2 : limit - P_SUB3);
-                        delNeeded = imax(0, r - c - 1);
-                        insNeeded = imax(0, (rows - r) - (cols - c) - 1);
-                        lim2MS = limit; lim2DELbase = limit; lim2INSbase = limit;
-                        if ((delNeeded | insNeeded) != 0) {
-                            const int delPen = bs.delc[imin(delNeeded, PEN_TAB - 1)];
-                            const int insPen = bs.insc[imin(insNeeded, PEN_TAB - 1)];
-                            lim2MS = delNeeded > 0 ? limit - delPen : limit - insPen;
-                            lim2DELbase = insNeeded > 0 ? limit - insPen : limit;      // delNeeded>0 handled with `time` below
-                            lim2INSbase = delNeeded > 0 ? limit - delPen : limit;      // insNeeded>0 handled with `time` below
-                        }
-                    }
-                    // ---------------- MS ----------------
-                    {
-                        const int sM = dMS & SMASK, sD = dDEL & SMASK, sI = dINS & SMASK, streak = dMS & TMASK;
-                        bool skip = gap;
-                        if (LIMITED) skip = skip || (imax3(sM, sD, sI) <= limit3);
-                        int addMS, o;
-                        if (match) { addMS = prevMatch ? P_MATCH2 : P_MATCH; o = P_MATCH; }
-                        else {
-                            o = P_SUB;
-                            addMS = (refN || callN) ? 0 : (prevMatch ? (streak <= 1 ? P_SUBR : P_SUB)
-                                                                       : (streak == 0 ? P_SUB : (streak < 5 ? P_SUB2 : P_SUB3)));
-                        }
-                        const int a_ = sM + addMS, b_ = sD + o, c_ = sI + o;
-                        const int mx = imax(b_, c_);
-                        const bool msWins = a_ >= mx;
-                        int score = imax(a_, mx);
-                        int time = (msWins && (match == prevMatch)) ? streak + 1 : 1;
-                        if (time > MAX_TIME) time = TIME_WRAP;
-                        const unsigned raw = (sM >= sD && sM >= sI) ? 0u : (sD >= sI ? 1u : 2u);
-                        code |= (time > 1) ? 0u : raw;
-                        if (LIMITED) {
-                            const bool ok = score >= lim2MS;
-                            good = good || (ok && !skip);
-                            if (!ok) score = subfloor;
-                        }
-                        nMS = skip ? subfloor : (score | time);
-                    }
-                    // ---------------- DEL ----------------
-                    {
-                        const int sM = lMS & SMASK, sD = lDEL & SMASK, streak = lDEL & TMASK;
-                        bool skip = delBar;
-                        if (LIMITED) skip = skip || (imax(sM, sD) <= limit);
-                        const int ext = streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
-                                        (((streak & 3) == 0) ? P_DEL5 : 0))));
-                        const int adj = refN ? P_DEL_REF_N : (gap ? P_GAP : 0);
-                        const int a_ = sM + P_DEL + adj, b_ = sD + ext + adj;
-                        const bool msWins = a_ >= b_;
-                        int score = imax(a_, b_);
-                        int time = msWins ? 1 : streak + 1;
-                        if (LIMITED) {
-                            int lim2 = lim2DELbase;
-                            if (insNeeded == 0 && delNeeded > 0) lim2 = limit - del_score_offset(time + delNeeded) + del_score_offset(time);
-                            const bool ok = score >= lim2;
-                            good = good || (ok && !skip);
-                            if (!ok) score = subfloor;
-                        }
-                        if (time > MAX_TIME) time = TIME_WRAP;
-                        code |= ((time > 1) ? 1u : (sM >= sD ? 0u : 1u)) << 2;
-                        nDEL = skip ? subfloor : (score | time);
-                    }
-                    // ---------------- INS ----------------
-                    {
-                        const int uMS = pMS[j], uINS = pINS[j];
-                        const int sM = uMS & SMASK, sI = uINS & SMASK, streak = uINS & TMASK;
-                        bool skip = gap || (insTop && c > 1) || (insBot && c < cols - 1);
-                        if (LIMITED) skip = skip || (imax(sM, sI) <= limit);
-                        const int ext = streak == 0 ? P_INS : (streak < LIM3 ? P_INS2 : (streak < LIM4 ? P_INS3 : P_INS4));
-                        const int a_ = sM + P_INS, b_ = sI + ext;
-                        const bool msWins = a_ >= b_;
-                        int score = imax(a_, b_);
-                        int time = msWins ? 1 : streak + 1;
-                        if (LIMITED) {
-                            int lim2 = lim2INSbase;
-                            if (delNeeded == 0 && insNeeded > 0)
-                                lim2 = limit - bs.insc[imin(time + insNeeded, PEN_TAB - 1)] + bs.insc[imin(time, PEN_TAB - 1)];
-                            const bool ok = score >= lim2;
-                            good = good || (ok && !skip);
-                            if (!ok) score = subfloor;
-                        }
-                        if (time > MAX_TIME) time = TIME_WRAP;
-                        code |= ((time > 1) ? 1u : (sM >= sI ? 0u : 1u)) << 3;
-                        nINS = skip ? subfloor : (score | time);
-                    }
-                } else {
-                    nMS = subfloor; nDEL = subfloor; nINS = subfloor;
+                int delNeeded = 0, insNeeded = 0;
+                if (LIMITED) {
+                    delNeeded = imax(0, r - c - 1);
+                    insNeeded = imin(imax(0, (rows - r) - (cols - c) - 1), PEN_TAB - 1);
                 }
+                const bool insBar = (insTop && c > 1) || (insBot && c < cols - 1);
+                const CellOut o = msa_cell<LIMITED, false>(K, R, dMS, dDEL, dINS, lMS, lDEL, pMS[j], pINS[j], ref1, ref0,
+                                                          (nmask >> j) & 1u, (gapmask >> j) & 1u, insBar, LIMITED ? hl[j] : 0,
+                                                          delNeeded, insNeeded, bs.insc, bs.delc);
+                const int nMS = visit ? o.ms : subfloor, nDEL = visit ? o.del : subfloor, nINS = visit ? o.ins : subfloor;
+                const unsigned code = o.code;
+                const bool good = visit && o.good;
+                word |= (tbw)code << (4 * j);
+                gCur |= (good ? 1u : 0u) << j;
                 if (inRange) {
-                    word |= (tbw)code << (4 * j);
-                    if (good) gCur |= 1u << j;
                     if (DUMP && P.dump) {
                         // dense dump [3][rows+1][cols+2]; the host replays the reference's write pattern from it
                         const long long plane = (long long)(rows + 1) * (cols + 2);

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--bandwidth", type=int, default=0)
     ap.add_argument("--ratio", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lengths", default="100,150,250")
     ap.add_argument("--no-narrow", action="store_true", help="disable the thread-per-alignment narrow kernel (A/B)")
     return ap.parse_args()
 
@@ -119,10 +120,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    lengths = (100, 150, 250)
-    config = {"workload": "configs[2] MSA11ts microbenchmark G4: %d alignments/step/GPU, read length {100,150,250}, window = locus +-4, "
+    lengths = tuple(int(x) for x in args.lengths.split(","))
+    config = {"workload": "configs[2] MSA11ts microbenchmark G4: %d alignments/step/GPU, read length {%s}, window = locus +-4, "
                           "70%% ~1%% subs / 20%% 1-40bp indel / 10%% unrelated, minScore=max(scoreNoIndels, 0.56*maxQ-258), "
-                          "fillLimited rule + score2 + traceback2; resident %d bp reference" % (args.tasks, GENOME_LEN),
+                          "fillLimited rule + score2 + traceback2; resident %d bp reference" % (args.tasks, args.lengths, GENOME_LEN),
               "tasks_per_step_per_gpu": args.tasks, "bandwidth": args.bandwidth, "bandwidthRatio": args.ratio,
               "l2": "inputs larger than L2 (tasks+reads+outs+match > 200 MB per step)"}
 
