@@ -19,6 +19,7 @@ extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n
                                      int* lists, int blocks, cudaStream_t stream);
 extern "C" int bbm_msa_narrow_threads();
 extern "C" int bbm_msa_narrow_buckets();
+extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
 extern "C" int bbm_msa_num_wclass();
@@ -157,7 +158,7 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const int nb = bbm_msa_narrow_buckets();
     const int tiledRows = max_rows < MAXR ? max_rows : MAXR;
     const long long words = (long long)(tiledRows + 40) * 32;           // one 64-bit code word per (step,lane)
-    const int narrowBlocks = c->sms * 3;
+    const int narrowBlocks = c->sms * 4;
     const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
     const int useNarrow = (c->use_narrow && d_dump == nullptr) ? 1 : 0;
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
@@ -308,5 +309,149 @@ extern "C" int bbm_msa_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads
     CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
     if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  single-alignment twins of the reference's C entry points  =====================
+// The kernels dump every evaluated cell into a dense [3][rows+1][cols+2] buffer; the host then replays the reference's
+// *write pattern* (which cells fillLimitedX touches, its explicit subfloor writes and the BADoff reset of the last row:
+// jni/MultiStateAligner11tsJNI.c:398-403, 451-456, 660-668) into the caller's `packed`, so the Java side's
+// score2/traceback2 read exactly what the C would have left there.
+
+static int single_fill(bbm_ctx* c, const int8_t* read, const int8_t* ref, int rows, int ref_length, int a, int b, int minScore,
+                       bool limitedMode, int bandwidth, float ratio, std::vector<int>& dump, bbm_msa_out& out) {
+    const int cols = b - a + 1;
+    if (rows < 1 || cols < 1 || a < 0 || b >= ref_length) return fail(BBM_E_ARG, "fill: window outside the reference array");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t dumpInts = (size_t)3 * (rows + 1) * (cols + 2);
+    if (c->d_reads.ensure((size_t)rows + cols + 64) || c->d_tasks.ensure(sizeof(bbm_msa_task)) || c->d_outs.ensure(sizeof(bbm_msa_out)) ||
+        c->d_dump.ensure(dumpInts * 4))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    bbm_msa_task t;
+    t.read_off = 0; t.ref_off = rows; t.read_len = rows; t.ref_len = cols; t.ref_start = 0; t.ref_end = cols - 1;
+    t.min_score = minScore; t.flags = limitedMode ? BBM_TF_RAW_LIMITED : BBM_TF_RAW_UNLIMITED;
+    CK(cudaMemcpyAsync(c->d_reads.p, read, (size_t)rows, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((char*)c->d_reads.p + rows, ref + a, (size_t)cols, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+    const int bw0 = c->bandwidth; const float r0 = c->ratio;
+    c->bandwidth = bandwidth; c->ratio = ratio;
+    int rc = run_msa(c, (const int8_t*)c->d_reads.p, (const int8_t*)c->d_reads.p, (const bbm_msa_task*)c->d_tasks.p, (bbm_msa_out*)c->d_outs.p, 1,
+                     nullptr, nullptr, rows, cols, st, nullptr, (int*)c->d_dump.p);
+    c->bandwidth = bw0; c->ratio = r0;
+    if (rc) return rc;
+    dump.resize(dumpInts);
+    CK(cudaMemcpyAsync(dump.data(), c->d_dump.p, dumpInts * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&out, c->d_outs.p, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (out.status != 0) return fail(out.status, "fill: kernel reported an error status");
+    return BBM_OK;
+}
+
+extern "C" int bbm_fillUnlimited(bbm_ctx* c, const int8_t* read, const int8_t* ref, int32_t read_length, int32_t ref_length,
+                                 int32_t refStartLoc, int32_t refEndLoc, int32_t* result4, int64_t* iterationsUnlimited,
+                                 int32_t* packed, int32_t maxRows, int32_t maxColumns) {
+    if (!c || !read || !ref || !result4 || !packed) return fail(BBM_E_ARG, "bbm_fillUnlimited: null pointer");
+    const int rows = read_length, cols = refEndLoc - refStartLoc + 1;
+    if (rows > maxRows || cols > maxColumns) return fail(BBM_E_SHAPE, "bbm_fillUnlimited: rows>maxRows or columns>maxColumns (the reference exit()s here)");
+    std::vector<int> dump; bbm_msa_out out;
+    int rc = single_fill(c, read, ref, rows, ref_length, refStartLoc, refEndLoc, 0, false, 0, 0.f, dump, out);
+    if (rc) return rc;
+    const long long stride = (long long)maxColumns + 1, plane = (long long)(maxRows + 1) * stride;
+    const long long dplane = (long long)(rows + 1) * (cols + 2);
+    for (int s = 0; s < 3; ++s)
+        for (int r = 1; r <= rows; ++r)
+            memcpy(packed + s * plane + r * stride + 1, dump.data() + s * dplane + (long long)r * (cols + 2) + 1, (size_t)cols * 4);
+    for (int k = 0; k < 4; ++k) result4[k] = out.result[k];
+    if (iterationsUnlimited) *iterationsUnlimited += out.iterations;
+    return BBM_OK;
+}
+
+static inline bool host_defined(int ch) { return ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'U' || ch == 'a' || ch == 'c' || ch == 'g' || ch == 't' || ch == 'u'; }
+
+extern "C" int bbm_fillLimitedX(bbm_ctx* c, const int8_t* read, const int8_t* ref, int32_t read_length, int32_t ref_length,
+                                int32_t refStartLoc, int32_t refEndLoc, int32_t minScore, int32_t* result5, int64_t* iterationsLimited,
+                                int32_t* packed, int32_t maxRows, int32_t maxColumns, int32_t bandwidth, float bandwidthRatio,
+                                int32_t* vertLimit, int32_t* horizLimit) {
+    if (!c || !read || !ref || !result5 || !packed) return fail(BBM_E_ARG, "bbm_fillLimitedX: null pointer");
+    const int rows = read_length, cols = refEndLoc - refStartLoc + 1;
+    if (rows > maxRows || cols > maxColumns) return fail(BBM_E_SHAPE, "bbm_fillLimitedX: rows>maxRows or columns>maxColumns");
+    std::vector<int> dump; bbm_msa_out out;
+    int rc = single_fill(c, read, ref, rows, ref_length, refStartLoc, refEndLoc, minScore, true, bandwidth, bandwidthRatio, dump, out);
+    if (rc) return rc;
+    const long long stride = (long long)maxColumns + 1, plane = (long long)(maxRows + 1) * stride;
+    const long long dstride = cols + 2, dplane = (long long)(rows + 1) * dstride;
+    const int minScore_off = (int)((unsigned)minScore << TBITS);
+    const int maxGain = (rows - 1) * P_MATCH2 + P_MATCH;
+    const int floor_ = minScore_off - maxGain, subfloor = floor_ - 5 * P_MATCH2;
+    int halfband = 0;
+    if (!(bandwidth < 1 && bandwidthRatio <= 0.f)) {
+        const int x = bandwidth < 1 ? 9999999 : bandwidth, y = bandwidthRatio <= 0.f ? 9999999 : 8 + (int)(rows * bandwidthRatio);
+        const int m = x < y ? x : y, n = cols - rows + 8;
+        halfband = (m > n ? m : n) / 2;
+    }
+    // vertLimit / horizLimit are outputs of the reference call too (jni/...JNI.c:413-438)
+    if (vertLimit) {
+        vertLimit[rows] = minScore_off; bool pd = false;
+        for (int i = rows - 1; i >= 0; --i) { const bool d = host_defined(read[i]); const int v = vertLimit[i + 1] - (d ? (pd ? P_MATCH2 : P_MATCH) : 0); vertLimit[i] = v > floor_ ? v : floor_; pd = d; }
+    }
+    if (horizLimit) {
+        horizLimit[cols] = minScore_off; bool pd = false;
+        for (int i = cols - 1; i >= 0; --i) {
+            const int ch = ref[refStartLoc + i]; const bool d = host_defined(ch);
+            const int v = horizLimit[i + 1] - (d ? (pd ? P_MATCH2 : P_MATCH) : ((pd && ch == '-') ? P_DEL : 0));
+            horizLimit[i] = v > floor_ ? v : floor_; pd = d;
+        }
+    }
+    // replay the write pattern
+    for (int s = 0; s < 3; ++s) for (int i = 1; i <= cols; ++i) packed[s * plane + (long long)rows * stride + i] = BADOFF;
+    auto cellGood = [&](int r, int col) -> bool {
+        const long long idx = (long long)r * dstride + col;
+        return (dump[idx] & SMASK) != subfloor || (dump[dplane + idx] & SMASK) != subfloor || (dump[2 * dplane + idx] & SMASK) != subfloor;
+    };
+    int minGood = 1, maxGood = cols;
+    for (int row = 1; row <= rows; ++row) {
+        const int colStart = halfband < 1 ? minGood : (minGood > row - halfband ? minGood : row - halfband);
+        const int colStop = halfband < 1 ? maxGood : (maxGood < row + halfband * 2 - 1 ? maxGood : row + halfband * 2 - 1);
+        minGood = -1; maxGood = -2;
+        if (colStart < 0 || colStop < colStart) break;
+        if (colStart > 1) for (int s = 0; s < 3; ++s) packed[s * plane + (long long)row * stride + colStart - 1] = subfloor;
+        for (int col = colStart; col <= cols; ++col) {
+            for (int s = 0; s < 3; ++s) packed[s * plane + (long long)row * stride + col] = dump[s * dplane + (long long)row * dstride + col];
+            if (cellGood(row, col)) { maxGood = col; if (minGood < 0) minGood = col; }
+            if (col >= colStop) {
+                if (col > colStop && (maxGood < col || halfband > 0)) break;
+                if (row > 1) for (int s = 0; s < 3; ++s) packed[s * plane + (long long)(row - 1) * stride + col + 1] = subfloor;
+            }
+        }
+    }
+    for (int k = 0; k < 5; ++k) result5[k] = out.result[k];
+    if (iterationsLimited) *iterationsLimited += out.iterations;
+    return BBM_OK;
+}
+
+// Integer / DPX pipe peak: lane-ops per second of instruction kind `kind` (0 IADD3, 1 LOP3, 2 VIMNMX3, 3 VIADDMNMX, 4 IMAD,
+// 5 half IMAD + half LOP3, 6 compare+select).  8 independent chains x 256 threads x 8 blocks per SM.
+extern "C" int bbm_int_peak(bbm_ctx* c, int kind, double* gops_out) {
+    if (!c || !gops_out) return fail(BBM_E_ARG, "bbm_int_peak: null");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (c->d_dump.ensure(64)) return fail(BBM_E_CUDA, "cudaMalloc");
+    const int blocks = c->sms * 8, iters = 1024;
+    cudaStream_t st = c->stream;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(c->ev0, st));
+        int e = bbm_launch_peak(kind, blocks, iters, (int*)c->d_dump.p, st);
+        if (e) return fail(BBM_E_CUDA, "peak kernel launch", (cudaError_t)e);
+        c->launches++;
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double ops = (double)blocks * 256.0 * iters * 8.0;
+    *gops_out = ops / (best * 1e-3) / 1e9;
     return BBM_OK;
 }

@@ -1,0 +1,80 @@
+// jni_shims.cu — the JNI entry points of the reference's native library, re-implemented on top of the CUDA path.
+//
+// Same exported symbols and signatures as reference jni/MultiStateAligner11tsJNI.c:707-812
+// (header jni/align2_MultiStateAligner11tsJNI.h:165-174), so `-Djava.library.path=` can point at a directory holding
+// libbbmapcuda.so under the name the loader expects (System.loadLibrary("bbtoolsjni"),
+// current/align2/MultiStateAligner11tsJNI.java:11-14) — see INTEGRATION.md.  Built against include/bbm_jni_min.h (the three
+// JNIEnv slots the reference uses, at their specified indices); unverified against a live JVM (none in this image).
+//
+// One process-wide context on device $BBM_DEVICE (default 0); calls from concurrent Java threads serialise on it — this is
+// the compatibility path (one alignment per call); throughput callers use bbm_msa_batch_*.
+#include <cstdlib>
+#include <cstdio>
+#include <mutex>
+#include "../../include/bbm_jni_min.h"
+#include "../../include/bbmap_cuda.h"
+
+static bbm_ctx* g_ctx = nullptr;
+static std::once_flag g_once;
+static int g_init_rc = 0;
+
+static bbm_ctx* default_ctx() {
+    std::call_once(g_once, [] {
+        const char* d = getenv("BBM_DEVICE");
+        g_init_rc = bbm_init(d ? atoi(d) : 0, &g_ctx);
+        if (g_init_rc) { fprintf(stderr, "libbbmapcuda: %s\n", bbm_last_error()); g_ctx = nullptr; }
+    });
+    return g_ctx;
+}
+
+extern "C" bbm_ctx* bbm_default_ctx(void) { return default_ctx(); }
+
+extern "C" JNIEXPORT void JNICALL Java_align2_MultiStateAligner11tsJNI_fillUnlimitedJNI(
+    JNIEnv* env, jobject obj, jbyteArray read, jbyteArray ref, jint refStartLoc, jint refEndLoc, jintArray result,
+    jlongArray iterationsUnlimited, jintArray packed, jintArray POINTSoff_SUB_ARRAY, jintArray POINTSoff_INS_ARRAY,
+    jint maxRows, jint maxColumns) {
+    (void)obj; (void)POINTSoff_SUB_ARRAY; (void)POINTSoff_INS_ARRAY;   // tables are the fixed 11ts constants on the device
+    bbm_ctx* c = default_ctx();
+    const jsize rlen = (*env)->GetArrayLength(env, read), reflen = (*env)->GetArrayLength(env, ref);
+    jint* jpacked = (jint*)(*env)->GetPrimitiveArrayCritical(env, packed, nullptr);
+    jbyte* jread = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, read, nullptr);
+    jbyte* jref = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, ref, nullptr);
+    jint* jresult = (jint*)(*env)->GetPrimitiveArrayCritical(env, result, nullptr);
+    jlong* jit = (jlong*)(*env)->GetPrimitiveArrayCritical(env, iterationsUnlimited, nullptr);
+    int rc = c ? bbm_fillUnlimited(c, jread, jref, rlen, reflen, refStartLoc, refEndLoc, jresult, (int64_t*)jit, jpacked, maxRows, maxColumns)
+               : BBM_E_NODEVICE;
+    if (rc) { fprintf(stderr, "libbbmapcuda: fillUnlimitedJNI failed (%d): %s\n", rc, bbm_last_error()); jresult[0] = -1; }
+    (*env)->ReleasePrimitiveArrayCritical(env, result, jresult, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, iterationsUnlimited, jit, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, read, jread, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, ref, jref, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, packed, jpacked, 0);
+}
+
+extern "C" JNIEXPORT void JNICALL Java_align2_MultiStateAligner11tsJNI_fillLimitedXJNI(
+    JNIEnv* env, jobject obj, jbyteArray read, jbyteArray ref, jint refStartLoc, jint refEndLoc, jint minScore, jintArray result,
+    jlongArray iterationsLimited, jintArray packed, jintArray POINTSoff_SUB_ARRAY, jintArray POINTSoff_INS_ARRAY, jint maxRows,
+    jint maxColumns, jint bandwidth, jfloat bandwidthRatio, jintArray vertLimit, jintArray horizLimit, jbyteArray baseToNumber,
+    jintArray POINTSoff_INS_ARRAY_C) {
+    (void)obj; (void)POINTSoff_SUB_ARRAY; (void)POINTSoff_INS_ARRAY; (void)baseToNumber; (void)POINTSoff_INS_ARRAY_C;
+    bbm_ctx* c = default_ctx();
+    const jsize rlen = (*env)->GetArrayLength(env, read), reflen = (*env)->GetArrayLength(env, ref);
+    jint* jpacked = (jint*)(*env)->GetPrimitiveArrayCritical(env, packed, nullptr);
+    jbyte* jread = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, read, nullptr);
+    jbyte* jref = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, ref, nullptr);
+    jint* jresult = (jint*)(*env)->GetPrimitiveArrayCritical(env, result, nullptr);
+    jlong* jit = (jlong*)(*env)->GetPrimitiveArrayCritical(env, iterationsLimited, nullptr);
+    jint* jvl = (jint*)(*env)->GetPrimitiveArrayCritical(env, vertLimit, nullptr);
+    jint* jhl = (jint*)(*env)->GetPrimitiveArrayCritical(env, horizLimit, nullptr);
+    int rc = c ? bbm_fillLimitedX(c, jread, jref, rlen, reflen, refStartLoc, refEndLoc, minScore, jresult, (int64_t*)jit, jpacked,
+                                  maxRows, maxColumns, bandwidth, bandwidthRatio, jvl, jhl)
+               : BBM_E_NODEVICE;
+    if (rc) { fprintf(stderr, "libbbmapcuda: fillLimitedXJNI failed (%d): %s\n", rc, bbm_last_error()); jresult[4] = 1; }
+    (*env)->ReleasePrimitiveArrayCritical(env, result, jresult, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, iterationsLimited, jit, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, read, jread, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, ref, jref, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, packed, jpacked, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, vertLimit, jvl, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, horizLimit, jhl, 0);
+}

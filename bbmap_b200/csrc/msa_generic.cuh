@@ -160,6 +160,10 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                 }
             }
             tb[(long long)row * tbStride + col] = (unsigned char)code;
+            if (P.dump) {   // dense dump [3][rows+1][cols+2] for the single-alignment twins (capi.cu replays the reference's writes)
+                const long long plane = (long long)(rows + 1) * (cols + 2), idx = (long long)row * (cols + 2) + col;
+                P.dump[idx] = cM[col]; P.dump[plane + idx] = cD[col]; P.dump[2 * plane + idx] = cI[col];
+            }
             if (limited) {
                 if (good) { maxGood = col; if (minGood < 0) minGood = col; }
                 if (col >= colStop) {

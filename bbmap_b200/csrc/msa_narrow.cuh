@@ -319,7 +319,7 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
     out->match_len = nOps;
 }
 
-__global__ void __launch_bounds__(NARROW_THREADS, 3) msa_narrow_kernel(MsaParams P, const int* __restrict__ list, int nlist, unsigned int* counter,
+__global__ void __launch_bounds__(NARROW_THREADS, 4) msa_narrow_kernel(MsaParams P, const int* __restrict__ list, int nlist, unsigned int* counter,
                                                                      unsigned long long* tbAll, long long tbWordsPerWarp,
                                                                      unsigned int* classCursors, int* classLists) {
     __shared__ NarrowShared sh;

@@ -74,6 +74,12 @@ class MultiStateAligner11tsCUDA:
     def stat(self, key):
         return int(self.L.bbm_get_stat(self.h, key.encode()))
 
+    def int_peak(self, kind):
+        """Measured giga lane-ops/s of one integer instruction kind (see bbm_int_peak)."""
+        g = C.c_double(0)
+        _lib.check(self.L.bbm_int_peak(self.h, int(kind), C.byref(g)), "bbm_int_peak")
+        return g.value
+
     @property
     def launches(self):
         return int(self.L.bbm_launch_count(self.h))

@@ -192,6 +192,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # integer / DPX pipe peaks of this very GPU (the DP kernels' roofline denominators; not in MEASURED_PEAKS.json)
+    kinds = ["iadd3", "lop3", "vimnmx3_dpx", "viaddmnmx_dpx", "imad", "half_imad_half_lop3", "cmp_select"]
+    int_peaks = {k: msa.int_peak(i) for i, k in enumerate(kinds)} if rank == 0 else {}
     for _ in range(max(args.warmup, 3)):
         step_dev()
     outs = np.frombuffer(d_outs.cpu().numpy().tobytes(), dtype=wl.OUT_DTYPE)
@@ -260,6 +263,7 @@ def main():
             "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
                            "narrow_handed_over": msa.stat("narrow_handed_over"), "band_misses": msa.stat("band_misses")},
             "clocks": clocks,
+            "int_peaks_glops": int_peaks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
                          "traffic": None, "peak_kind": pk_kind,
                          "note": "integer-issue-bound DP: algorithmic bytes/cell ~0.1; see DESIGN.md for the issue-slot roofline"}}

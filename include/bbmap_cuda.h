@@ -96,6 +96,10 @@ int  bbm_msa_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, 
 int     bbm_set_option(bbm_ctx* ctx, const char* key, int value);
 int64_t bbm_get_stat(const bbm_ctx* ctx, const char* key);
 
+/* Measures the integer / DPX issue peak of this GPU (roofline denominator for the DP kernels): giga lane-ops per second of
+ * instruction kind 0 IADD3, 1 LOP3, 2 VIMNMX3 (DPX), 3 VIADDMNMX (DPX), 4 IMAD, 5 half IMAD + half LOP3, 6 compare+select. */
+int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
+
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 

@@ -1,0 +1,57 @@
+"""GPU: the single-alignment twins of the reference's C entry points and the Java_align2_* JNI symbols, driven through a
+fake JNIEnv, leave the caller's `packed` matrix, result, iteration counter, vertLimit and horizLimit bit-identical to the
+reference's own C (or the port) run on the same sequence of calls with a persistent matrix."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bbmap_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+MAXR, MAXC = 601, 3000
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_jni_twins_bit_exact(oracle):
+    from bbmap_b200 import lib as L
+    lib = L.load()
+    kind = "reference" if oracle.has_reference else "port"
+    orc = oracle.lib
+    fnL = C.cast(lib.Java_align2_MultiStateAligner11tsJNI_fillLimitedXJNI, C.c_void_p)
+    fnU = C.cast(lib.Java_align2_MultiStateAligner11tsJNI_fillUnlimitedJNI, C.c_void_p)
+    genome = wl.random_genome(30000, seed=61)
+    reads, tasks = wl.make_msa_tasks(genome, 60, seed=62, flags=0)
+    g8 = genome.view(np.int8)
+    pa = oracle.new_packed(MAXR, MAXC); pb = pa.copy()
+    vla = np.zeros(MAXR + 1, np.int32); hla = np.zeros(MAXC + 1, np.int32)
+    vlb = vla.copy(); hlb = hla.copy()
+    ita = np.zeros(1, np.int64); itb = 0
+    n_fail = 0
+    for i, t in enumerate(tasks):
+        r = np.ascontiguousarray(reads[t["read_off"]: t["read_off"] + t["read_len"]].view(np.int8))
+        bw, ratio = [(0, 0.0), (12, 0.0), (0, 0.2), (40, 0.0)][i % 4]
+        ms = int(t["min_score"]) - 120
+        res = np.zeros(5, np.int32)
+        if i % 7 == 3:
+            pins = orc.fake_call_fillUnlimitedJNI(fnU, _p(r), len(r), _p(g8), len(g8), int(t["ref_start"]), int(t["ref_end"]), _p(res), _p(ita),
+                                                  _p(pa), len(pa), _p(oracle.sub), _p(oracle.ins), 604, MAXR, MAXC)
+            exp, it = oracle.fill_unlimited(r, g8, int(t["ref_start"]), int(t["ref_end"]), pb, MAXR, MAXC, kind=kind)
+            assert res[:4].tolist() == exp.tolist()
+        else:
+            pins = orc.fake_call_fillLimitedXJNI(fnL, _p(r), len(r), _p(g8), len(g8), int(t["ref_start"]), int(t["ref_end"]), ms, _p(res), _p(ita),
+                                                 _p(pa), len(pa), _p(oracle.sub), _p(oracle.ins), 604, MAXR, MAXC, bw, C.c_float(ratio),
+                                                 _p(vla), _p(hla), _p(oracle.b2n), _p(oracle.insC))
+            exp, it = oracle.fill_limited(r, g8, int(t["ref_start"]), int(t["ref_end"]), ms, pb, MAXR, MAXC, bandwidth=bw, ratio=ratio,
+                                          kind=kind, vl=vlb, hl=hlb)
+            assert res.tolist() == exp.tolist(), (i, res, exp)
+            n_fail += int(exp[4])
+            assert np.array_equal(vla, vlb) and np.array_equal(hla, hlb)
+        assert pins == 0
+        itb += it
+        assert int(ita[0]) == itb
+        assert np.array_equal(pa, pb), "packed differs after call %d" % i
+    assert 0 < n_fail < len(tasks)
