@@ -19,6 +19,8 @@ extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n
                                      int* lists, int blocks, cudaStream_t stream);
 extern "C" int bbm_msa_narrow_threads();
 extern "C" int bbm_msa_narrow_buckets();
+extern "C" int bbm_launch_banded(const int8_t* q, const int8_t* r, const bbm_band_task* t, bbm_band_out* o, long long n,
+                                 unsigned int* counter, int blocks, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -69,7 +71,7 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1;
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
-    DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump;   // staging for the host-buffer entry point
+    DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2;   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
     long long launches = 0;
@@ -110,7 +112,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release();
     c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -453,5 +455,52 @@ extern "C" int bbm_int_peak(bbm_ctx* c, int kind, double* gops_out) {
     }
     const double ops = (double)blocks * 256.0 * iters * 8.0;
     *gops_out = ops / (best * 1e-3) / 1e9;
+    return BBM_OK;
+}
+
+// =====================  BandedAligner  =====================
+static int run_banded(bbm_ctx* c, const int8_t* dq, const int8_t* dr, const bbm_band_task* dt, bbm_band_out* dout, int64_t n,
+                      cudaStream_t st, float* ms_out) {
+    if (n <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    unsigned int* cb = (unsigned int*)c->counters.p;
+    CK(cudaMemsetAsync(cb + 200, 0, 4, st));
+    CK(cudaEventRecord(c->ev0, st));
+    int blocks = c->sms * 8;
+    const long long need = (n + 3) / 4;
+    if (need < blocks) blocks = (int)need;
+    int e = bbm_launch_banded(dq, dr, dt, dout, n, cb + 200, blocks, st);
+    if (e) return fail(BBM_E_CUDA, "banded_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_banded_batch_dev(bbm_ctx* c, const int8_t* d_queries, const int8_t* d_refs, const bbm_band_task* d_tasks,
+                                    bbm_band_out* d_outs, int64_t ntasks, void* stream, float* kernel_ms_out) {
+    if (!c || !d_queries || !d_refs || !d_tasks || !d_outs) return fail(BBM_E_ARG, "bbm_banded_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_banded(c, d_queries, d_refs, d_tasks, d_outs, ntasks, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_banded_batch_host(bbm_ctx* c, const int8_t* queries, int64_t query_bytes, const int8_t* refs, int64_t ref_bytes,
+                                     const bbm_band_task* tasks, bbm_band_out* outs, int64_t ntasks) {
+    if (!c || !queries || !refs || !tasks || !outs) return fail(BBM_E_ARG, "bbm_banded_batch_host: null pointer");
+    if (ntasks <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t tb = (size_t)ntasks * sizeof(bbm_band_task), ob = (size_t)ntasks * sizeof(bbm_band_out);
+    if (c->d_reads.ensure((size_t)query_bytes + 16) || c->d_refs2.ensure((size_t)ref_bytes + 16) || c->d_tasks.ensure(tb) || c->d_outs.ensure(ob))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(c->d_reads.p, queries, (size_t)query_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_refs2.p, refs, (size_t)ref_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, tasks, tb, cudaMemcpyHostToDevice, st));
+    int rc = run_banded(c, (const int8_t*)c->d_reads.p, (const int8_t*)c->d_refs2.p, (const bbm_band_task*)c->d_tasks.p, (bbm_band_out*)c->d_outs.p, ntasks, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }

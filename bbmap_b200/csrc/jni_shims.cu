@@ -78,3 +78,40 @@ extern "C" JNIEXPORT void JNICALL Java_align2_MultiStateAligner11tsJNI_fillLimit
     (*env)->ReleasePrimitiveArrayCritical(env, vertLimit, jvl, 0);
     (*env)->ReleasePrimitiveArrayCritical(env, horizLimit, jhl, 0);
 }
+
+// ---- BandedAligner (reference jni/BandedAlignerJNI.c:588-757; header jni/align2_BandedAlignerJNI.h:17-41) ----
+static jint banded_jni(JNIEnv* env, jbyteArray query, jbyteArray ref, jint qstart, jint rstart, jint maxEdits, jboolean exact,
+                       jint maxWidth, jintArray returnVals, int dir) {
+    bbm_ctx* c = default_ctx();
+    const jint rlen = (*env)->GetArrayLength(env, ref), qlen = (*env)->GetArrayLength(env, query);
+    jbyte* jref = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, ref, nullptr);
+    jbyte* jquery = (jbyte*)(*env)->GetPrimitiveArrayCritical(env, query, nullptr);
+    jint* jrv = (jint*)(*env)->GetPrimitiveArrayCritical(env, returnVals, nullptr);
+    bbm_band_task t; t.query_off = 0; t.ref_off = 0; t.query_len = qlen; t.ref_len = rlen; t.qstart = qstart; t.rstart = rstart;
+    t.max_edits = maxEdits; t.max_width = maxWidth; t.exact = exact ? 1 : 0; t.dir = dir;
+    bbm_band_out o = {};
+    int rc = c ? bbm_banded_batch_host(c, jquery, qlen, jref, rlen, &t, &o, 1) : BBM_E_NODEVICE;
+    if (rc == 0 && o.status != 0) rc = o.status;
+    if (rc) fprintf(stderr, "libbbmapcuda: BandedAlignerJNI failed (%d): %s\n", rc, bbm_last_error());
+    for (int k = 0; k < 5; ++k) jrv[k] = o.rv[k];
+    (*env)->ReleasePrimitiveArrayCritical(env, ref, jref, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, query, jquery, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, returnVals, jrv, 0);
+    return o.edits;
+}
+extern "C" JNIEXPORT jint JNICALL Java_align2_BandedAlignerJNI_alignForwardJNI(JNIEnv* env, jobject obj, jbyteArray query, jbyteArray ref,
+    jint qstart, jint rstart, jint maxEdits, jboolean exact, jint maxWidth, jbyteArray baseToNumber, jintArray returnVals) {
+    (void)obj; (void)baseToNumber; return banded_jni(env, query, ref, qstart, rstart, maxEdits, exact, maxWidth, returnVals, BBM_DIR_FORWARD);
+}
+extern "C" JNIEXPORT jint JNICALL Java_align2_BandedAlignerJNI_alignForwardRCJNI(JNIEnv* env, jobject obj, jbyteArray query, jbyteArray ref,
+    jint qstart, jint rstart, jint maxEdits, jboolean exact, jint maxWidth, jbyteArray baseToNumber, jbyteArray baseToComplementExtended, jintArray returnVals) {
+    (void)obj; (void)baseToNumber; (void)baseToComplementExtended; return banded_jni(env, query, ref, qstart, rstart, maxEdits, exact, maxWidth, returnVals, BBM_DIR_FORWARD_RC);
+}
+extern "C" JNIEXPORT jint JNICALL Java_align2_BandedAlignerJNI_alignReverseJNI(JNIEnv* env, jobject obj, jbyteArray query, jbyteArray ref,
+    jint qstart, jint rstart, jint maxEdits, jboolean exact, jint maxWidth, jbyteArray baseToNumber, jintArray returnVals) {
+    (void)obj; (void)baseToNumber; return banded_jni(env, query, ref, qstart, rstart, maxEdits, exact, maxWidth, returnVals, BBM_DIR_REVERSE);
+}
+extern "C" JNIEXPORT jint JNICALL Java_align2_BandedAlignerJNI_alignReverseRCJNI(JNIEnv* env, jobject obj, jbyteArray query, jbyteArray ref,
+    jint qstart, jint rstart, jint maxEdits, jboolean exact, jint maxWidth, jbyteArray baseToNumber, jbyteArray baseToComplementExtended, jintArray returnVals) {
+    (void)obj; (void)baseToNumber; (void)baseToComplementExtended; return banded_jni(env, query, ref, qstart, rstart, maxEdits, exact, maxWidth, returnVals, BBM_DIR_REVERSE_RC);
+}

@@ -144,3 +144,80 @@ def match_offsets(tasks, extra=0):
     off = np.zeros(len(tasks) + 1, np.int64)
     np.cumsum(cap, out=off[1:])
     return off
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# G6: BandedAligner tasks: (query, ref) pairs as Dedupe would pass them (reads / contigs), 0-3% edits,
+# maxEdits in {2,5,26}, maxWidth = max(min(bw, 2*maxEdits+1), 3) | 1 with Dedupe's default bw=9 (jgi/Dedupe.java:5715-5717)
+# unless `widths` overrides it; all four directions; exact in {0,1}.
+BAND_TASK_DTYPE = np.dtype([("query_off", "<i8"), ("ref_off", "<i8"), ("query_len", "<i4"), ("ref_len", "<i4"), ("qstart", "<i4"),
+                            ("rstart", "<i4"), ("max_edits", "<i4"), ("max_width", "<i4"), ("exact", "<i4"), ("dir", "<i4")], align=True)
+BAND_OUT_DTYPE = np.dtype([("edits", "<i4"), ("rv", "<i4", (5,)), ("status", "<i4"), ("pad_", "<i4")], align=True)
+DIR_FORWARD, DIR_FORWARD_RC, DIR_REVERSE, DIR_REVERSE_RC = 0, 1, 2, 3
+_COMP = np.zeros(256, np.uint8)
+for _a, _b in zip(b"ACGTNacgtn", b"TGCANtgcan"):
+    _COMP[_a] = _b
+
+
+def revcomp(a):
+    return _COMP[a[::-1]]
+
+
+def make_banded_tasks(n, seed=6, min_len=150, max_len=5000, edit_rate=0.03, max_edits=(2, 5, 26), bw=9, widths=None,
+                      n_rate=0.001, ragged=True):
+    """Returns (queries uint8[], refs uint8[], tasks BAND_TASK_DTYPE[n])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tasks = np.zeros(n, BAND_TASK_DTYPE)
+    qs, rs = [], []
+    qoff = roff = 0
+    for i in range(n):
+        L = int(rng.integers(min_len, max_len + 1))
+        ref = ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        q = ref.copy()
+        rate = float(rng.random()) * edit_rate
+        ne = int(rng.binomial(L, rate))
+        for _ in range(ne):
+            p = int(rng.integers(0, len(q)))
+            k = rng.random()
+            if k < 0.6:
+                q[p] = ACGT[(np.searchsorted(ACGT, q[p]) + rng.integers(1, 4)) % 4]
+            elif k < 0.8 and len(q) > 20:
+                q = np.delete(q, p)
+            else:
+                q = np.insert(q, p, ACGT[rng.integers(0, 4)])
+        if n_rate > 0:
+            m = rng.random(len(q)) < n_rate
+            q = np.where(m, np.uint8(ord("N")), q)
+        if ragged and rng.random() < 0.3:          # unequal lengths: exercises the query/ref swap rules
+            cut = int(rng.integers(1, max(2, L // 4)))
+            if rng.random() < 0.5:
+                q = q[:-cut] if len(q) > cut + 10 else q
+            else:
+                ref = ref[:-cut] if len(ref) > cut + 10 else ref
+        d = int(rng.integers(0, 4))
+        me = int(max_edits[int(rng.integers(0, len(max_edits)))])
+        if widths is None:
+            mw = max(min(bw, 2 * me + 1), 3) | 1
+        else:
+            mw = int(widths[int(rng.integers(0, len(widths)))])
+        if d in (DIR_FORWARD_RC, DIR_REVERSE_RC):
+            q = revcomp(q)
+        ql, rl = len(q), len(ref)
+        if d == DIR_FORWARD:
+            qstart, rstart = 0, 0
+        elif d == DIR_FORWARD_RC:
+            qstart, rstart = ql - 1, 0
+        elif d == DIR_REVERSE:
+            qstart, rstart = ql - 1, rl - 1
+        else:
+            qstart, rstart = 0, rl - 1
+        if rng.random() < 0.15:                     # interior starts
+            sh = int(rng.integers(0, 20))
+            if d == DIR_FORWARD:
+                qstart, rstart = sh, sh
+            elif d == DIR_REVERSE:
+                qstart, rstart = ql - 1 - sh, rl - 1 - sh
+        tasks[i] = (qoff, roff, ql, rl, qstart, rstart, me, mw, int(rng.random() < 0.5), d)
+        qs.append(q); rs.append(ref)
+        qoff += ql; roff += rl
+    return np.concatenate(qs), np.concatenate(rs), tasks

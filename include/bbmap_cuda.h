@@ -103,6 +103,26 @@ int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 
+/* ---- BandedAligner (jni/BandedAlignerJNI.c) ---- */
+#define BBM_DIR_FORWARD     0   /* alignForward    jni/BandedAlignerJNI.c:123-239 */
+#define BBM_DIR_FORWARD_RC  1   /* alignForwardRC  :241-355 */
+#define BBM_DIR_REVERSE     2   /* alignReverse    :357-470 */
+#define BBM_DIR_REVERSE_RC  3   /* alignReverseRC  :472-585 */
+typedef struct {                /* 48 bytes; argument meaning as in the C signatures */
+    int64_t query_off, ref_off; /* byte offsets into the query / reference buffers */
+    int32_t query_len, ref_len, qstart, rstart, max_edits, max_width, exact, dir;
+} bbm_band_task;
+typedef struct {                /* 32 bytes */
+    int32_t edits;              /* return value */
+    int32_t rv[5];              /* {lastQueryLoc,lastRefLoc,lastRow,lastEdits,lastOffset} (BandedAlignerJNI.java returnVals) */
+    int32_t status, pad_;
+} bbm_band_out;
+/* Batched, device-resident buffers / host buffers.  Band widths up to 127 cells (maxEdits<=63) are supported. */
+int  bbm_banded_batch_dev(bbm_ctx* ctx, const int8_t* d_queries, const int8_t* d_refs, const bbm_band_task* d_tasks,
+                          bbm_band_out* d_outs, int64_t ntasks, void* stream, float* kernel_ms_out);
+int  bbm_banded_batch_host(bbm_ctx* ctx, const int8_t* queries, int64_t query_bytes, const int8_t* refs, int64_t ref_bytes,
+                           const bbm_band_task* tasks, bbm_band_out* outs, int64_t ntasks);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

@@ -27,6 +27,12 @@ assert TASK_DTYPE.itemsize == 40 and OUT_DTYPE.itemsize == 80
 
 TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK = 1, 2, 4, 8, 16
 
+BAND_TASK_DTYPE = np.dtype([("query_off", "<i8"), ("ref_off", "<i8"), ("query_len", "<i4"), ("ref_len", "<i4"), ("qstart", "<i4"),
+                            ("rstart", "<i4"), ("max_edits", "<i4"), ("max_width", "<i4"), ("exact", "<i4"), ("dir", "<i4")], align=True)
+BAND_OUT_DTYPE = np.dtype([("edits", "<i4"), ("rv", "<i4", (5,)), ("status", "<i4"), ("pad_", "<i4")], align=True)
+assert BAND_TASK_DTYPE.itemsize == 48 and BAND_OUT_DTYPE.itemsize == 32
+DIR_FORWARD, DIR_FORWARD_RC, DIR_REVERSE, DIR_REVERSE_RC = 0, 1, 2, 3
+
 
 def build(quiet=True):
     """(Re)build liborc.so and, when /root/reference is mounted, _ref/libbbref.so."""
@@ -64,6 +70,9 @@ class Oracle:
             fl = C.cast(self.ref.fillLimitedX, C.c_void_p).value
             fu = C.cast(self.ref.fillUnlimited, C.c_void_p).value
             L.orc_set_reference_fns(fl, fu)
+            L.orc_banded_set_reference_fns.argtypes = [C.c_void_p] * 4
+            L.orc_banded_set_reference_fns(*[C.cast(getattr(self.ref, n), C.c_void_p).value
+                                             for n in ("alignForward", "alignForwardRC", "alignReverse", "alignReverseRC")])
         self.sub = np.zeros(TABLE_LEN, np.int32)
         self.ins = np.zeros(TABLE_LEN, np.int32)
         self.insC = np.zeros(TABLE_LEN, np.int32)
@@ -110,6 +119,24 @@ class Oracle:
         f(_p(read), _p(ref), C.c_int(len(read)), C.c_int(len(ref)), C.c_int(a), C.c_int(b), _p(res), _p(it),
           _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns))
         return res, int(it[0])
+
+    # ---------------- BandedAligner ----------------
+    def banded(self, dir, query, ref, qstart, rstart, maxEdits, exact, maxWidth):
+        q = np.ascontiguousarray(query, np.int8); r = np.ascontiguousarray(ref, np.int8)
+        rv = np.zeros(5, np.int32)
+        e = self.lib.orc_banded_align(C.c_int(dir), _p(q), _p(r), C.c_int(len(q)), C.c_int(len(r)), C.c_int(qstart), C.c_int(rstart),
+                                      C.c_int(maxEdits), C.c_int(1 if exact else 0), C.c_int(maxWidth), _p(rv))
+        return int(e), rv.tolist()
+
+    def banded_batch(self, queries, refs, tasks, kind="port", threads=1):
+        queries = np.ascontiguousarray(queries, np.int8); refs = np.ascontiguousarray(refs, np.int8)
+        tasks = np.ascontiguousarray(tasks, BAND_TASK_DTYPE)
+        outs = np.zeros(len(tasks), BAND_OUT_DTYPE)
+        rc = self.lib.orc_banded_batch(_p(queries), _p(refs), _p(tasks), _p(outs), C.c_int64(len(tasks)),
+                                       C.c_int(1 if kind == "reference" else 0), C.c_int(threads))
+        if rc != 0:
+            raise RuntimeError("reference banded backend unavailable")
+        return outs
 
     # ---------------- batch driver ----------------
     def run_batch(self, reads, refs, tasks, match_off=None, bandwidth=0, ratio=0.0, maxRows=601, maxColumns=3000,
