@@ -13,6 +13,11 @@ JNI_SYMBOLS = [
     # jni/align2_MultiStateAligner11tsJNI.h:165-174
     "Java_align2_MultiStateAligner11tsJNI_fillUnlimitedJNI",
     "Java_align2_MultiStateAligner11tsJNI_fillLimitedXJNI",
+    # jni/align2_BandedAlignerJNI.h:17-41
+    "Java_align2_BandedAlignerJNI_alignForwardJNI",
+    "Java_align2_BandedAlignerJNI_alignForwardRCJNI",
+    "Java_align2_BandedAlignerJNI_alignReverseJNI",
+    "Java_align2_BandedAlignerJNI_alignReverseRCJNI",
 ]
 
 

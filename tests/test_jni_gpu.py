@@ -55,3 +55,30 @@ def test_jni_twins_bit_exact(oracle):
         assert int(ita[0]) == itb
         assert np.array_equal(pa, pb), "packed differs after call %d" % i
     assert 0 < n_fail < len(tasks)
+
+
+def test_banded_jni_symbols(oracle):
+    """The four Java_align2_BandedAlignerJNI_* entry points, through the fake JNIEnv, against the oracle."""
+    from bbmap_b200 import lib as L
+    lib = L.load()
+    orc = oracle.lib
+    orc.fake_call_bandedJNI.restype = C.c_int
+    orc.fake_call_bandedRCJNI.restype = C.c_int
+    names = ["alignForwardJNI", "alignForwardRCJNI", "alignReverseJNI", "alignReverseRCJNI"]
+    fns = [C.cast(getattr(lib, "Java_align2_BandedAlignerJNI_" + n), C.c_void_p) for n in names]
+    b2n = np.zeros(128, np.int8); comp = np.zeros(128, np.int8)
+    orc.orc_banded_tables(_p(b2n), _p(comp))
+    q, r, tasks = wl.make_banded_tasks(40, seed=71, min_len=30, max_len=400)
+    for t in tasks:
+        qq = np.ascontiguousarray(q[t["query_off"]: t["query_off"] + t["query_len"]].view(np.int8))
+        rr = np.ascontiguousarray(r[t["ref_off"]: t["ref_off"] + t["ref_len"]].view(np.int8))
+        rv = np.zeros(5, np.int32)
+        d = int(t["dir"])
+        if d in (0, 2):
+            e = orc.fake_call_bandedJNI(fns[d], _p(qq), len(qq), _p(rr), len(rr), int(t["qstart"]), int(t["rstart"]), int(t["max_edits"]),
+                                        C.c_ubyte(int(t["exact"])), int(t["max_width"]), _p(b2n), _p(rv))
+        else:
+            e = orc.fake_call_bandedRCJNI(fns[d], _p(qq), len(qq), _p(rr), len(rr), int(t["qstart"]), int(t["rstart"]), int(t["max_edits"]),
+                                          C.c_ubyte(int(t["exact"])), int(t["max_width"]), _p(b2n), _p(comp), _p(rv))
+        exp = oracle.banded(d, qq, rr, int(t["qstart"]), int(t["rstart"]), int(t["max_edits"]), bool(t["exact"]), int(t["max_width"]))
+        assert (int(e), rv.tolist()) == exp
