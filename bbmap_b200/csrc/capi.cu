@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <cmath>
 #include <cuda_runtime.h>
 #include "msa_common.cuh"
 
@@ -21,6 +22,13 @@ extern "C" int bbm_msa_narrow_threads();
 extern "C" int bbm_msa_narrow_buckets();
 extern "C" int bbm_launch_banded(const int8_t* q, const int8_t* r, const bbm_band_task* t, bbm_band_out* o, long long n,
                                  unsigned int* counter, int blocks, cudaStream_t st);
+extern "C" int bbm_seed_upload_tables(const float* pc, const float* pci);
+extern "C" int bbm_launch_seed(const int8_t* bases, const int8_t* quality, const long long* read_off, long long nreads, const bbm_seed_cfg* cfg,
+                               int maxKeys, int* nkeys, int* offsets, int* keys, int* keyScores, int8_t* baseScores,
+                               float* probScratch, int blocks, int maxProbLen, unsigned int* counter, cudaStream_t st);
+extern "C" int bbm_launch_seed_reverse(const int* nkeys, const int* offsets, const int* keys, const long long* read_off, long long nreads,
+                                       int maxKeys, int keylen, int* offsetsM, int* keysM, cudaStream_t st);
+extern "C" int bbm_seed_threads();
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -71,7 +79,8 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1;
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
-    DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2;   // staging for the host-buffer entry point
+    DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2, seedScratch, d_seed[8];
+    bool seed_tables = false;   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
     long long launches = 0;
@@ -112,7 +121,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release();
     c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -501,6 +510,88 @@ extern "C" int bbm_banded_batch_host(bbm_ctx* c, const int8_t* queries, int64_t 
     int rc = run_banded(c, (const int8_t*)c->d_reads.p, (const int8_t*)c->d_refs2.p, (const bbm_band_task*)c->d_tasks.p, (bbm_band_out*)c->d_outs.p, ntasks, st, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  KeyRing seeding  =====================
+static int run_seed(bbm_ctx* c, const int8_t* db, const int8_t* dq, const int64_t* doff, int64_t nreads, int max_len, const bbm_seed_cfg* cfg,
+                    int maxKeys, int* dn, int* dof, int* dk, int* dks, int8_t* dbs, int* dofM, int* dkM, cudaStream_t st, float* ms_out) {
+    if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (!c->seed_tables) {
+        // QualityTools.PROB_ERROR / PROB_CORRECT / PROB_CORRECT_INVERSE (current/align2/QualityTools.java:475-480, 519-539)
+        float pc[127], pci[127];
+        for (int i = 0; i < 127; ++i) { float pe = (float)pow(10.0, 0 - .1 * i); if (i == 0) pe = .8f; pc[i] = 1 - pe; pci[i] = 1 / pc[i]; }
+        int e = bbm_seed_upload_tables(pc, pci);
+        if (e) return fail(BBM_E_CUDA, "seed tables upload", (cudaError_t)e);
+        c->seed_tables = true;
+    }
+    const int T = bbm_seed_threads();
+    int blocks = c->sms * 4;
+    const long long need = (nreads + T - 1) / T;
+    if (need < blocks) blocks = (int)need;
+    const int maxProbLen = max_len - cfg->keylen + 1 > 1 ? max_len - cfg->keylen + 1 : 1;
+    if (c->seedScratch.ensure((size_t)blocks * T * (size_t)maxProbLen * 4)) return fail(BBM_E_CUDA, "cudaMalloc seed scratch");
+    unsigned int* cb = (unsigned int*)c->counters.p;
+    CK(cudaMemsetAsync(cb + 201, 0, 4, st));
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_seed(db, dq, (const long long*)doff, nreads, cfg, maxKeys, dn, dof, dk, dks, dbs, (float*)c->seedScratch.p, blocks, maxProbLen, cb + 201, st);
+    if (e) return fail(BBM_E_CUDA, "seed_kernel launch", (cudaError_t)e);
+    c->launches++;
+    if (dofM && dkM) {
+        e = bbm_launch_seed_reverse(dn, dof, dk, (const long long*)doff, nreads, maxKeys, cfg->keylen, dofM, dkM, st);
+        if (e) return fail(BBM_E_CUDA, "seed_reverse_kernel launch", (cudaError_t)e);
+        c->launches++;
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_seed_batch_dev(bbm_ctx* c, const int8_t* d_bases, const int8_t* d_quality, const int64_t* d_read_off, int64_t nreads,
+                                  int32_t max_read_len, const bbm_seed_cfg* cfg, int32_t maxKeys, int32_t* d_nkeys, int32_t* d_offsets,
+                                  int32_t* d_keys, int32_t* d_keyScores, int8_t* d_baseScores, int32_t* d_offsetsM, int32_t* d_keysM,
+                                  void* stream, float* kernel_ms_out) {
+    if (!c || !d_bases || !d_read_off || !cfg || !d_nkeys || !d_offsets || !d_keys || !d_keyScores || !d_baseScores || maxKeys < 1)
+        return fail(BBM_E_ARG, "bbm_seed_batch_dev: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_seed(c, d_bases, d_quality, d_read_off, nreads, max_read_len, cfg, maxKeys, d_nkeys, d_offsets, d_keys, d_keyScores, d_baseScores,
+                    d_offsetsM, d_keysM, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_seed_batch_host(bbm_ctx* c, const int8_t* bases, const int8_t* quality, const int64_t* read_off, int64_t nreads,
+                                   const bbm_seed_cfg* cfg, int32_t maxKeys, int32_t* nkeys, int32_t* offsets, int32_t* keys,
+                                   int32_t* keyScores, int8_t* baseScores, int32_t* offsetsM, int32_t* keysM) {
+    if (!c || !bases || !read_off || !cfg || !nkeys || !offsets || !keys || !keyScores || !baseScores || maxKeys < 1)
+        return fail(BBM_E_ARG, "bbm_seed_batch_host: bad argument");
+    if (nreads <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nb = (size_t)read_off[nreads], kb = (size_t)nreads * maxKeys * 4;
+    int max_len = 1;
+    for (int64_t i = 0; i < nreads; ++i) { const int l = (int)(read_off[i + 1] - read_off[i]); if (l > max_len) max_len = l; }
+    DevBuf* B = c->d_seed;   // 0 bases, 1 qual, 2 off, 3 nkeys, 4 offsets|keys|scores, 5 baseScores, 6 offsetsM|keysM
+    if (B[0].ensure(nb + 32) || (quality && B[1].ensure(nb + 32)) || B[2].ensure((size_t)(nreads + 1) * 8) || B[3].ensure((size_t)nreads * 4) ||
+        B[4].ensure(3 * kb) || B[5].ensure(nb + 32) || B[6].ensure(2 * kb))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(B[0].p, bases, nb, cudaMemcpyHostToDevice, st));
+    if (quality) CK(cudaMemcpyAsync(B[1].p, quality, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[2].p, read_off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    int* d4 = (int*)B[4].p; int* d6 = (int*)B[6].p;
+    const bool rev = offsetsM && keysM;
+    int rc = run_seed(c, (const int8_t*)B[0].p, quality ? (const int8_t*)B[1].p : nullptr, (const int64_t*)B[2].p, nreads, max_len, cfg, maxKeys,
+                      (int*)B[3].p, d4, d4 + (size_t)nreads * maxKeys, d4 + 2 * (size_t)nreads * maxKeys, (int8_t*)B[5].p,
+                      rev ? d6 : nullptr, rev ? d6 + (size_t)nreads * maxKeys : nullptr, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(nkeys, B[3].p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(offsets, d4, kb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(keys, d4 + (size_t)nreads * maxKeys, kb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(keyScores, d4 + 2 * (size_t)nreads * maxKeys, kb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(baseScores, B[5].p, nb, cudaMemcpyDeviceToHost, st));
+    if (rev) { CK(cudaMemcpyAsync(offsetsM, d6, kb, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(keysM, d6 + (size_t)nreads * maxKeys, kb, cudaMemcpyDeviceToHost, st)); }
     CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }

@@ -221,3 +221,29 @@ def make_banded_tasks(n, seed=6, min_len=150, max_len=5000, edit_rate=0.03, max_
         qs.append(q); rs.append(ref)
         qoff += ql; roff += rl
     return np.concatenate(qs), np.concatenate(rs), tasks
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Read batches for the seeding kernels: bases + phred qualities (offset removed), as Read.validate leaves them
+# (stream/Read.java:81-215: qualities clamped to [2,41] for ACGT, 0 for undefined bases).
+def make_read_batch(n, seed=9, lengths=(100, 150, 250), flat_q=None, n_rate=0.002, lowq_tail=0.3):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens = np.asarray(lengths, np.int64)[rng.integers(0, len(lengths), size=n)]
+    off = np.zeros(n + 1, np.int64); np.cumsum(lens, out=off[1:])
+    total = int(off[-1])
+    bases = ACGT[rng.integers(0, 4, size=total, dtype=np.uint8)]
+    if flat_q is not None:
+        qual = np.full(total, flat_q, np.uint8)
+    else:
+        qual = rng.integers(2, 42, size=total).astype(np.uint8)
+        hi = rng.random(total) < 0.8
+        qual = np.where(hi, np.maximum(qual, 30), qual).astype(np.uint8)
+        # degrade read tails like Illumina reads
+        for r in np.nonzero(rng.random(n) < lowq_tail)[0]:
+            L = int(lens[r]); t = int(rng.integers(5, max(6, L // 2)))
+            qual[off[r] + L - t: off[r] + L] = rng.integers(2, 12, size=t)
+    nmask = rng.random(total) < n_rate
+    bases = np.where(nmask, np.uint8(ord("N")), bases)
+    qual = np.where(nmask, 0, qual).astype(np.uint8)
+    # a few reads that are mostly N / shorter than k
+    return bases, qual, off

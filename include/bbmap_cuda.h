@@ -103,6 +103,27 @@ int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 
+/* ---- KeyRing seeding (AbstractMapThread.quickMap up to the index search; QualityTools / KeyRing) ---- */
+typedef struct {                /* 32 bytes; defaults = BBMap.setDefaults (current/align2/BBMap.java:45-65) */
+    int32_t keylen;             /* 13 */
+    int32_t maxDesiredKeys;     /* 15 */
+    int32_t baseKeyHitScore;    /* BASE_HIT_SCORE*keylen = 1300 (AbstractIndex.java:17) */
+    int32_t minApproxHitsToKeep;/* 1 */
+    float keyDensity, maxKeyDensity, minKeyDensity, pad_;   /* 1.9, 3.0, 1.5 */
+} bbm_seed_cfg;
+/* reads: concatenated bases (ASCII) and, optionally, qualities (phred, offset removed; NULL = FASTA path); read_off has
+ * nreads+1 entries.  Per read r: nkeys[r] = number of seeds (>=1), 0 (shorter than k) or -1 (discarded by quickMap's rules);
+ * offsets/keys/keyScores are [nreads][maxKeys] (unused slots -1/-1/0); baseScores is parallel to bases.  With
+ * offsetsM/keysM non-NULL also emits the minus-strand lists (KeyRing.reverseOffsets / reverseComplementKeys).
+ * Everything device-resident for *_dev; *_host copies in and out. */
+int  bbm_seed_batch_dev(bbm_ctx* ctx, const int8_t* d_bases, const int8_t* d_quality, const int64_t* d_read_off, int64_t nreads,
+                        int32_t max_read_len, const bbm_seed_cfg* cfg, int32_t maxKeys, int32_t* d_nkeys, int32_t* d_offsets,
+                        int32_t* d_keys, int32_t* d_keyScores, int8_t* d_baseScores, int32_t* d_offsetsM, int32_t* d_keysM,
+                        void* stream, float* kernel_ms_out);
+int  bbm_seed_batch_host(bbm_ctx* ctx, const int8_t* bases, const int8_t* quality, const int64_t* read_off, int64_t nreads,
+                         const bbm_seed_cfg* cfg, int32_t maxKeys, int32_t* nkeys, int32_t* offsets, int32_t* keys,
+                         int32_t* keyScores, int8_t* baseScores, int32_t* offsetsM, int32_t* keysM);
+
 /* ---- BandedAligner (jni/BandedAlignerJNI.c) ---- */
 #define BBM_DIR_FORWARD     0   /* alignForward    jni/BandedAlignerJNI.c:123-239 */
 #define BBM_DIR_FORWARD_RC  1   /* alignForwardRC  :241-355 */

@@ -120,6 +120,29 @@ class Oracle:
           _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns))
         return res, int(it[0])
 
+    # ---------------- KeyRing seeding ----------------
+    def seed_batch(self, bases, quality, read_off, cfg, maxKeys=96):
+        bases = np.ascontiguousarray(bases).view(np.int8)
+        quality = None if quality is None else np.ascontiguousarray(quality).view(np.int8)
+        read_off = np.ascontiguousarray(read_off, np.int64)
+        n = len(read_off) - 1
+        out = dict(nkeys=np.zeros(n, np.int32), offsets=np.zeros((n, maxKeys), np.int32), keys=np.zeros((n, maxKeys), np.int32),
+                   keyScores=np.zeros((n, maxKeys), np.int32), baseScores=np.zeros(len(bases), np.int8))
+        self.lib.orc_seed_batch.restype = None
+        self.lib.orc_seed_batch(_p(bases), None if quality is None else _p(quality), _p(read_off), C.c_int64(n), _p(cfg), C.c_int32(maxKeys),
+                                _p(out["nkeys"]), _p(out["offsets"]), _p(out["keys"]), _p(out["keyScores"]), _p(out["baseScores"]))
+        k = int(cfg["keylen"][0])
+        self.lib.orc_rcomp_key_fast.restype = C.c_int
+        om = np.full((n, maxKeys), -1, np.int32); km = np.full((n, maxKeys), -1, np.int32)
+        lens = np.diff(read_off)
+        for r in range(n):
+            m = int(out["nkeys"][r])
+            for i in range(max(m, 0)):
+                om[r, i] = lens[r] - (out["offsets"][r, m - 1 - i] + k)
+                km[r, i] = self.lib.orc_rcomp_key_fast(C.c_int(int(out["keys"][r, m - 1 - i])), C.c_int(k))
+        out["offsetsM"] = om; out["keysM"] = km
+        return out
+
     # ---------------- BandedAligner ----------------
     def banded(self, dir, query, ref, qstart, rstart, maxEdits, exact, maxWidth):
         q = np.ascontiguousarray(query, np.int8); r = np.ascontiguousarray(ref, np.int8)
