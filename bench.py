@@ -96,23 +96,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(reads, genome, tasks, moff, bw, ratio, budget_s=15.0, threads=None):
-    """Times the reference's own C (oracle/_ref) — or the port if it is absent — on a bounded sample."""
+def cpu_reference_run(reads, genome, tasks, moff, bw, ratio, budget_s=12.0, threads=None):
+    """Times the reference's own C (oracle/_ref) — or the port if it is absent — on a bounded sample: whole passes over
+    (a prefix of) the step batch until ~budget_s seconds of wall time have been spent."""
     from oracle import oracle as orc
     o = orc.get()
     kind = "reference" if o.has_reference else "port"
     threads = threads or (os.cpu_count() or 1)
-    probe = min(len(tasks), 64 * threads)
-    t0 = time.perf_counter()
-    _, _, cells = o.run_batch(reads, genome, tasks[:probe], match_off=moff[:probe + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
-    dt = time.perf_counter() - t0
-    n = int(min(len(tasks), max(probe, probe * budget_s / max(dt, 1e-4))))
-    t0 = time.perf_counter()
-    outs, _, cells = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
-    dt = time.perf_counter() - t0
-    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
-            "sample": "first %d of %d alignments of the step batch, %.1f s, %d threads, one private packed matrix per thread" % (n, len(tasks), dt, threads),
-            "seconds": dt, "cells": cells, "tasks": n}
+    n = int(min(len(tasks), 100_000))
+    cells = 0; secs = 0.0; passes = 0
+    while secs < budget_s and passes < 64:
+        t0 = time.perf_counter()
+        _, _, c = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
+        secs += time.perf_counter() - t0
+        cells += c; passes += 1
+    return {"value": cells / secs / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
+            "sample": "%d passes over the first %d alignments of the step batch, %.1f s, %d threads, one private packed matrix per thread"
+                      % (passes, n, secs, threads),
+            "seconds": secs, "cells": cells, "tasks": n * passes}
 
 
 def main():
@@ -231,13 +232,9 @@ def main():
     clocks = sampler.finish()
     assert h_outs.tobytes() == outs.tobytes(), "host-buffer path and resident path disagree"
 
-    t = torch.tensor([ms, e2e_s * 1e3 / e2e_steps, kernel_ms], dtype=torch.float64, device=dev)
-    c = torch.tensor([float(cells_per_step)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    ms_all, e2e_ms_step, kernel_ms_all = [float(x) for x in t.tolist()]
-    total_cells_step = float(c.item())
+    from bbmap_b200 import shard
+    ms_all, e2e_ms_step, kernel_ms_all = shard.max_over_ranks([ms, e2e_s * 1e3 / e2e_steps, kernel_ms], device=dev)
+    total_cells_step, = shard.sum_over_ranks([float(cells_per_step)], device=dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
