@@ -30,101 +30,121 @@ struct CellOut {
     bool good;
 };
 
-// Penalty tables live in shared memory: insc[i]=POINTSoff_INS_ARRAY_C[i], delc[i]=calcDelScoreOffset(i); both [0]=0.
-template <bool LIMITED, bool CLAMP_TIME>
+// Look-up tables in shared memory (one copy per block).  The streak-dependent penalties are read from tables instead of being
+// recomputed with compare/select ladders: the recurrence is bound by the integer ALU pipe, table reads go through the idle LSU.
+struct CellTables {
+    int insc[PEN_TAB];        // POINTSoff_INS_ARRAY_C[i]  (also column 0 of the matrix)
+    int delc[PEN_TAB];        // calcDelScoreOffset(i)
+    int delExt[PEN_TAB];      // extension cost of a DEL run of length `streak`   (jni/...JNI.c:572-576)
+    int insExt[PEN_TAB];      // POINTSoff_INS_ARRAY[streak+1]                     (…JNI.java:1583-1603)
+    int subExt[PEN_TAB];      // POINTSoff_SUB_ARRAY[streak+1]                     (…JNI.java:1610-1625)
+};
+
+__device__ __forceinline__ void cell_tables_init(CellTables& t) {
+    for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) {
+        t.insc[i] = ins_score_offset(i);
+        t.delc[i] = del_score_offset(i);
+        t.delExt[i] = i == 0 ? P_DEL : (i < LIM3 ? P_DEL2 : (i < LIM4 ? P_DEL3 : (i < LIM5 ? P_DEL4 : (((i & 3) == 0) ? P_DEL5 : 0))));
+        t.insExt[i] = i == 0 ? P_INS : (i < LIM3 ? P_INS2 : (i < LIM4 ? P_INS3 : P_INS4));
+        t.subExt[i] = i == 0 ? P_SUB : (i < 5 ? P_SUB2 : P_SUB3);
+    }
+}
+
+// One cell.  Streaks never exceed PEN_TAB-1 here (rows <= 606, columns <= 512 in the kernels that use this function), so the
+// tables need no index clamp and `time` never reaches MAX_TIME (the generic kernel handles the wrap for wider windows).
+template <bool LIMITED>
 __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R,
                                             int dMS, int dDEL, int dINS,        // (row-1,col-1)
                                             int lMS, int lDEL,                  // (row,  col-1)
                                             int uMS, int uINS,                  // (row-1,col)
                                             int ref1, int ref0,                 // mapped reference bytes ('N' -> 0x100)
-                                            bool refN, bool gap, bool insBar,   // insBar: INS state is barred at this cell
+                                            bool insBar,                        // INS state is barred at this cell
                                             int hlimit,                         // horizLimit[col]
                                             int delNeeded, int insNeeded,
-                                            const int* __restrict__ insc, const int* __restrict__ delc) {
+                                            const CellTables& T) {
     CellOut o;
     const bool match = (R.call1 == ref1);
     const bool prevMatch = (R.call0 == ref0);
-    int limit = 0, limit3 = 0, lim2MS = 0, lim2DEL = 0, lim2INS = 0;
+    const bool refN = (ref1 == 0x100);
+    const bool gap = (ref1 == '-');
+    int limit = 0, lim2MS = 0, lim2DEL = 0, lim2INS = 0;
+    bool skipMS = gap, skipDEL = R.delBar, skipINS = gap || insBar;
+    const int sMd = dMS & SMASK, sDd = dDEL & SMASK, sId = dINS & SMASK, streakM = dMS & TMASK;
+    const int sMl = lMS & SMASK, sDl = lDEL & SMASK, streakD = lDEL & TMASK;
+    const int sMu = uMS & SMASK, sIu = uINS & SMASK, streakI = uINS & TMASK;
+    const int mxDI = imax(sDd, sId);
     if (LIMITED) {
         limit = imax(R.vlimit, hlimit);
-        limit3 = imax(K.floor_, limit - (match ? P_MATCH2 : P_SUB3));
-        const int delPen = delc[delNeeded];                 // 0 when delNeeded==0
-        const int insPen = insc[insNeeded];                 // 0 when insNeeded==0
+        const int limit3 = __viaddmax_s32(limit, match ? -P_MATCH2 : -P_SUB3, K.floor_);
+        const int delPen = T.delc[delNeeded];               // 0 when delNeeded==0
+        const int insPen = T.insc[insNeeded];               // 0 when insNeeded==0
         lim2MS = limit - (delNeeded > 0 ? delPen : insPen);
         lim2DEL = limit - insPen;                           // delNeeded>0 && insNeeded==0 refined below (needs `time`)
         lim2INS = limit - delPen;                           // insNeeded>0 && delNeeded==0 refined below
+        skipMS = skipMS || (imax(sMd, mxDI) <= limit3);
+        skipDEL = skipDEL || (imax(sMl, sDl) <= limit);
+        skipINS = skipINS || (imax(sMu, sIu) <= limit);
     }
     bool good = false;
     unsigned code;
     // ---------------- MS (jni/...JNI.c:491-564) ----------------
     {
-        const int sM = dMS & SMASK, sD = dDEL & SMASK, sI = dINS & SMASK, streak = dMS & TMASK;
         const int addMatch = prevMatch ? P_MATCH2 : P_MATCH;
-        const int subNoPrev = streak == 0 ? P_SUB : (streak < 5 ? P_SUB2 : P_SUB3);      // POINTSoff_SUB_ARRAY[streak+1]
-        const int subPrev = streak <= 1 ? P_SUBR : P_SUB;
-        const int addSub = (refN || R.callN) ? 0 : (prevMatch ? subPrev : subNoPrev);
-        const int a_ = sM + (match ? addMatch : addSub);
-        const int mx = imax(sD, sI) + (match ? P_MATCH : P_SUB);
+        const int subPrev = streakM <= 1 ? P_SUBR : P_SUB;
+        int addSub = prevMatch ? subPrev : T.subExt[streakM];
+        addSub = (refN || R.callN) ? 0 : addSub;
+        const int a_ = sMd + (match ? addMatch : addSub);
+        const int mx = mxDI + (match ? P_MATCH : P_SUB);
         const bool msWins = a_ >= mx;
         int score = imax(a_, mx);
-        int time = (msWins && (match == prevMatch)) ? streak + 1 : 1;
-        if (CLAMP_TIME) time = time > MAX_TIME ? TIME_WRAP : time;
-        const unsigned raw = (sM >= sD && sM >= sI) ? 0u : (sD >= sI ? 1u : 2u);
-        code = (time > 1) ? 0u : raw;
-        bool skip = gap;
+        const bool keep = msWins && (match == prevMatch);
+        const int time = keep ? streakM + 1 : 1;
+        // predecessor the traceback would pick: MS if time>1, else the raw arg-max of the three diagonal scores
+        const bool preMS = (keep && streakM >= 1) || (sMd >= mxDI);
+        code = preMS ? 0u : (sDd >= sId ? 1u : 2u);
         if (LIMITED) {
-            skip = skip || (imax3(sM, sD, sI) <= limit3);
             const bool ok = score >= lim2MS;
-            good = ok && !skip;
+            good = ok && !skipMS;
             score = ok ? score : K.subfloor;
         }
-        o.ms = skip ? K.subfloor : (score | time);
+        o.ms = skipMS ? K.subfloor : (score | time);
     }
     // ---------------- DEL (jni/...JNI.c:566-617) ----------------
     {
-        const int sM = lMS & SMASK, sD = lDEL & SMASK, streak = lDEL & TMASK;
-        const int ext = streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
-                        (((streak & 3) == 0) ? P_DEL5 : 0))));
         const int adj = refN ? P_DEL_REF_N : (gap ? P_GAP : 0);
-        const int a_ = sM + P_DEL, b_ = sD + ext;
+        const int a_ = sMl + P_DEL, b_ = sDl + T.delExt[streakD];
         const bool msWins = a_ >= b_;
         int score = imax(a_, b_) + adj;
-        int time = msWins ? 1 : streak + 1;
-        bool skip = R.delBar;
+        const int time = msWins ? 1 : streakD + 1;
         if (LIMITED) {
-            skip = skip || (imax(sM, sD) <= limit);
             int lim2 = lim2DEL;
-            if (delNeeded > 0 && insNeeded == 0 && !skip)           // rare: below the diagonal with a live DEL state
+            if (delNeeded > 0 && insNeeded == 0 && !skipDEL)         // rare: below the diagonal with a live DEL state
                 lim2 = limit - del_score_offset(time + delNeeded) + del_score_offset(time);
             const bool ok = score >= lim2;
-            good = good || (ok && !skip);
+            good = good || (ok && !skipDEL);
             score = ok ? score : K.subfloor;
         }
-        if (CLAMP_TIME) time = time > MAX_TIME ? TIME_WRAP : time;
-        code |= ((time > 1) ? 1u : (sM >= sD ? 0u : 1u)) << 2;
-        o.del = skip ? K.subfloor : (score | time);
+        const bool preDEL = (!msWins && streakD >= 1) || (sMl < sDl);
+        code |= preDEL ? 4u : 0u;
+        o.del = skipDEL ? K.subfloor : (score | time);
     }
     // ---------------- INS (jni/...JNI.c:619-658) ----------------
     {
-        const int sM = uMS & SMASK, sI = uINS & SMASK, streak = uINS & TMASK;
-        const int ext = streak == 0 ? P_INS : (streak < LIM3 ? P_INS2 : (streak < LIM4 ? P_INS3 : P_INS4));   // POINTSoff_INS_ARRAY[streak+1]
-        const int a_ = sM + P_INS, b_ = sI + ext;
+        const int a_ = sMu + P_INS, b_ = sIu + T.insExt[streakI];
         const bool msWins = a_ >= b_;
         int score = imax(a_, b_);
-        int time = msWins ? 1 : streak + 1;
-        bool skip = gap || insBar;
+        const int time = msWins ? 1 : streakI + 1;
         if (LIMITED) {
-            skip = skip || (imax(sM, sI) <= limit);
             int lim2 = lim2INS;
-            if (insNeeded > 0 && delNeeded == 0 && !skip)           // rare: right of the end diagonal with a live INS state
-                lim2 = limit - insc[imin(time + insNeeded, PEN_TAB - 1)] + insc[imin(time, PEN_TAB - 1)];
+            if (insNeeded > 0 && delNeeded == 0 && !skipINS)         // rare: right of the end diagonal with a live INS state
+                lim2 = limit - T.insc[imin(time + insNeeded, PEN_TAB - 1)] + T.insc[time];
             const bool ok = score >= lim2;
-            good = good || (ok && !skip);
+            good = good || (ok && !skipINS);
             score = ok ? score : K.subfloor;
         }
-        if (CLAMP_TIME) time = time > MAX_TIME ? TIME_WRAP : time;
-        code |= ((time > 1) ? 1u : (sM >= sI ? 0u : 1u)) << 3;
-        o.ins = skip ? K.subfloor : (score | time);
+        const bool preINS = (!msWins && streakI >= 1) || (sMu < sIu);
+        code |= preINS ? 8u : 0u;
+        o.ins = skipINS ? K.subfloor : (score | time);
     }
     o.code = code;
     o.good = good;

@@ -60,7 +60,7 @@ template <int W, bool DUMP>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, (W <= 9 ? 4 : (W <= 12 ? 3 : 2))) msa_tiled_kernel(MsaParams P, const int* __restrict__ list, int nlist, const unsigned int* __restrict__ endPtr, unsigned int base, unsigned int* counter) {
     __shared__ BlockShared bs;
     __shared__ WarpShared wsAll[WARPS_PER_BLOCK];
-    for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) { bs.insc[i] = ins_score_offset(i); bs.delc[i] = del_score_offset(i); }
+    cell_tables_init(bs);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpShared& ws = wsAll[warp];

@@ -24,10 +24,7 @@ constexpr int NDW = 16;        // diagonals per thread
 constexpr int NDLO = -3;       // first diagonal of the window (col - row)
 constexpr int NARROW_THREADS = 128;
 
-struct NarrowShared {
-    int insc[PEN_TAB];
-    int delc[PEN_TAB];
-};
+typedef CellTables NarrowShared;
 
 __device__ __forceinline__ bool narrow_eligible(const TaskCtx& T) {
     const int D = T.cols - T.rows;
@@ -183,8 +180,8 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
                 const int delNeeded = (-(NDLO + j) - 1) > 0 ? (-(NDLO + j) - 1) : 0;      // max(0,row-col-1): fixed per diagonal
                 const int insNeeded = imax(0, NDLO + j - D - 1);                            // max(0,(rows-row)-(cols-col)-1)
                 const bool insBar = (insTop && c > 1) || (insBot && c < cols - 1);
-                const CellOut o = msa_cell<true, false>(K, R, dMS, dDL, dIN, lMS, lDL, uMS, uIN, ref1, ref0,
-                                                        ref1 == 0x100, false, insBar, hlr[j], delNeeded, insNeeded, sh.insc, sh.delc);
+                const CellOut o = msa_cell<true>(K, R, dMS, dDL, dIN, lMS, lDL, uMS, uIN, ref1, ref0,
+                                                 insBar, hlr[j], delNeeded, insNeeded, sh);
                 int nMS = visit ? o.ms : subfloor, nDL = visit ? o.del : subfloor, nIN = visit ? o.ins : subfloor;
                 const unsigned code = o.code;
                 const bool good = visit && o.good;
@@ -323,7 +320,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 4) msa_narrow_kernel(MsaParams
                                                                      unsigned long long* tbAll, long long tbWordsPerWarp,
                                                                      unsigned int* classCursors, int* classLists) {
     __shared__ NarrowShared sh;
-    for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) { sh.insc[i] = ins_score_offset(i); sh.delc[i] = del_score_offset(i); }
+    cell_tables_init(sh);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long gwarp = (long long)blockIdx.x * (NARROW_THREADS / 32) + (threadIdx.x >> 5);

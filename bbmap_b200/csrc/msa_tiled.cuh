@@ -44,10 +44,7 @@ struct WarpShared {
     signed char read[MAXR + 8];
 };
 
-struct BlockShared {
-    int insc[PEN_TAB];         // POINTSoff_INS_ARRAY_C[i] (also column 0 of the matrix)
-    int delc[PEN_TAB];         // calcDelScoreOffset(i)
-};
+typedef CellTables BlockShared;
 
 struct TaskCtx {
     int rows, cols, a, b;       // window [a,b] inside the reference array
@@ -223,6 +220,7 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
             R.delBar = (r < 3) || (r > rows - 3);
             const bool insTop = (r < 2), insBot = (r > rows - 2);
             const bool inP = LIMITED ? ((r == 1) || (mmInPrev != MM_NONE)) : true;
+            const int dn0 = r - c0 - 1, in0 = (rows - r) - (cols - c0) - 1;
             unsigned gCur = 0;
             tbw word = 0;
             int ref0 = refLeft;
@@ -239,13 +237,12 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
                 }
                 int delNeeded = 0, insNeeded = 0;
                 if (LIMITED) {
-                    delNeeded = imax(0, r - c - 1);
-                    insNeeded = imin(imax(0, (rows - r) - (cols - c) - 1), PEN_TAB - 1);
+                    delNeeded = imax(0, dn0 - j);            // max(0,row-col-1)
+                    insNeeded = imax(0, in0 + j);            // max(0,(rows-row)-(cols-col)-1)  (<= rows)
                 }
                 const bool insBar = (insTop && c > 1) || (insBot && c < cols - 1);
-                const CellOut o = msa_cell<LIMITED, false>(K, R, dMS, dDEL, dINS, lMS, lDEL, pMS[j], pINS[j], ref1, ref0,
-                                                          (nmask >> j) & 1u, (gapmask >> j) & 1u, insBar, LIMITED ? hl[j] : 0,
-                                                          delNeeded, insNeeded, bs.insc, bs.delc);
+                const CellOut o = msa_cell<LIMITED>(K, R, dMS, dDEL, dINS, lMS, lDEL, pMS[j], pINS[j], ref1, ref0,
+                                                   insBar, LIMITED ? hl[j] : 0, delNeeded, insNeeded, bs);
                 const int nMS = visit ? o.ms : subfloor, nDEL = visit ? o.del : subfloor, nINS = visit ? o.ins : subfloor;
                 const unsigned code = o.code;
                 const bool good = visit && o.good;
