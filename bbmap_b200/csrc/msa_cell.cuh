@@ -34,7 +34,7 @@ struct CellOut {
 // recomputed with compare/select ladders: the recurrence is bound by the integer ALU pipe, table reads go through the idle LSU.
 struct CellTables {
     int insc[PEN_TAB];        // POINTSoff_INS_ARRAY_C[i]  (also column 0 of the matrix)
-    int delc[PEN_TAB];        // calcDelScoreOffset(i)
+    int delc[DELC_TAB];       // calcDelScoreOffset(i), i up to columns+rows
     int delExt[PEN_TAB];      // extension cost of a DEL run of length `streak`   (jni/...JNI.c:572-576)
     int insExt[PEN_TAB];      // POINTSoff_INS_ARRAY[streak+1]                     (…JNI.java:1583-1603)
     int subExt[PEN_TAB];      // POINTSoff_SUB_ARRAY[streak+1]                     (…JNI.java:1610-1625)
@@ -43,11 +43,11 @@ struct CellTables {
 __device__ __forceinline__ void cell_tables_init(CellTables& t) {
     for (int i = threadIdx.x; i < PEN_TAB; i += blockDim.x) {
         t.insc[i] = ins_score_offset(i);
-        t.delc[i] = del_score_offset(i);
         t.delExt[i] = i == 0 ? P_DEL : (i < LIM3 ? P_DEL2 : (i < LIM4 ? P_DEL3 : (i < LIM5 ? P_DEL4 : (((i & 3) == 0) ? P_DEL5 : 0))));
         t.insExt[i] = i == 0 ? P_INS : (i < LIM3 ? P_INS2 : (i < LIM4 ? P_INS3 : P_INS4));
         t.subExt[i] = i == 0 ? P_SUB : (i < 5 ? P_SUB2 : P_SUB3);
     }
+    for (int i = threadIdx.x; i < DELC_TAB; i += blockDim.x) t.delc[i] = del_score_offset(i);
 }
 
 // One cell.  Streaks never exceed PEN_TAB-1 here (rows <= 606, columns <= 512 in the kernels that use this function), so the
@@ -119,7 +119,7 @@ __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R
         if (LIMITED) {
             int lim2 = lim2DEL;
             if (delNeeded > 0 && insNeeded == 0 && !skipDEL)         // rare: below the diagonal with a live DEL state
-                lim2 = limit - del_score_offset(time + delNeeded) + del_score_offset(time);
+                lim2 = limit - (T.delc[time + delNeeded] - T.delc[time]);
             const bool ok = score >= lim2;
             good = good || (ok && !skipDEL);
             score = ok ? score : K.subfloor;
@@ -137,7 +137,7 @@ __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R
         if (LIMITED) {
             int lim2 = lim2INS;
             if (insNeeded > 0 && delNeeded == 0 && !skipINS)         // rare: right of the end diagonal with a live INS state
-                lim2 = limit - T.insc[imin(time + insNeeded, PEN_TAB - 1)] + T.insc[time];
+                lim2 = limit - (T.insc[time + insNeeded] - T.insc[time]);
             const bool ok = score >= lim2;
             good = good || (ok && !skipINS);
             score = ok ? score : K.subfloor;

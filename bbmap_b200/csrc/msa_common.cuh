@@ -33,6 +33,7 @@ constexpr int ST_MS = 0, ST_DEL = 1, ST_INS = 2;
 // Largest read the register-tiled kernels take (reference ALIGN_ROWS=601, BBMapThread.java:28)
 constexpr int MAXR = 608;
 constexpr int PEN_TAB = MAXR + 8;
+constexpr int DELC_TAB = MAXR + 512 + 32;   // DEL run length (<= columns of the tiled kernels) + delNeeded (<= rows)
 
 __device__ __forceinline__ int imax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int imin(int a, int b) { return min(a, b); }

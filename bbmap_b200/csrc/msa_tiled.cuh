@@ -196,6 +196,7 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
     for (int t = 1; t <= steps; ++t) {
         const int r = t - lane;
         const bool active = (r >= 1) && (r <= rows) && (lane < nAct);
+        bool deadNow = false;
         // values from the lane on my left
         int dMS = __shfl_up_sync(FULL, lastOldMS, 1);
         int dDEL = __shfl_up_sync(FULL, lastOldDEL, 1);
@@ -301,11 +302,14 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
                             else lastc = imin(cols, imax(colStop, curMax) + 1);
                             iters += lastc - colStart + 1;
                             prevMin = curMin; prevMax = curMax;
+                            // an empty row ends the fill at the next row (colStart<0, jni/...JNI.c:449): nothing after it is visited
+                            if (curMin < 0 && r < rows) { broke = true; deadNow = true; }
                         }
                     }
                 }
             }
         }
+        if (LIMITED) { if (__any_sync(FULL, deadNow)) break; }
     }
     __syncwarp();
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libbbmapcuda.so")
+SO_PATH = os.environ.get("BBM_SO") or os.path.join(HERE, "libbbmapcuda.so")   # BBM_SO: A/B builds while tuning
 
 BBM_OK, BBM_E_NODEVICE, BBM_E_CUDA, BBM_E_ARG, BBM_E_SHAPE, BBM_E_CAPACITY = 0, -1, -2, -3, -4, -5
 
