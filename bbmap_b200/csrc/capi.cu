@@ -29,6 +29,8 @@ extern "C" int bbm_launch_seed(const int8_t* bases, const int8_t* quality, const
 extern "C" int bbm_launch_seed_reverse(const int* nkeys, const int* offsets, const int* keys, const long long* read_off, long long nreads,
                                        int maxKeys, int keylen, int* offsetsM, int* keysM, cudaStream_t st);
 extern "C" int bbm_seed_threads();
+extern "C" int bbm_launch_noindel(const int8_t* reads, const int8_t* refs, const bbm_noindel_task* tasks, int* scores,
+                                  int8_t* match_buf, const long long* match_off, long long n, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -592,6 +594,49 @@ extern "C" int bbm_seed_batch_host(bbm_ctx* c, const int8_t* bases, const int8_t
     CK(cudaMemcpyAsync(keyScores, d4 + 2 * (size_t)nreads * maxKeys, kb, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(baseScores, B[5].p, nb, cudaMemcpyDeviceToHost, st));
     if (rev) { CK(cudaMemcpyAsync(offsetsM, d6, kb, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(keysM, d6 + (size_t)nreads * maxKeys, kb, cudaMemcpyDeviceToHost, st)); }
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  ungapped site scoring  =====================
+static int run_noindel(bbm_ctx* c, const int8_t* dr, const int8_t* dref, const bbm_noindel_task* dt, int* ds, int8_t* dm, const int64_t* dmo,
+                       int64_t n, cudaStream_t st, float* ms_out) {
+    if (n <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_noindel(dr, dref, dt, ds, dm, (const long long*)dmo, n, st);
+    if (e) return fail(BBM_E_CUDA, "noindel_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+extern "C" int bbm_noindel_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_noindel_task* d_tasks, int32_t* d_scores,
+                                     int8_t* d_match_buf, const int64_t* d_match_off, int64_t ntasks, void* stream, float* kernel_ms_out) {
+    if (!c || !d_reads || !d_refs || !d_tasks || !d_scores) return fail(BBM_E_ARG, "bbm_noindel_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_noindel(c, d_reads, d_refs, d_tasks, d_scores, d_match_buf, d_match_off, ntasks, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+extern "C" int bbm_noindel_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_noindel_task* tasks,
+                                      int32_t* scores, int8_t* match_buf, const int64_t* match_off, int64_t ntasks) {
+    if (!c || !reads || !d_refs || !tasks || !scores) return fail(BBM_E_ARG, "bbm_noindel_batch_host: null pointer");
+    if (ntasks <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t tb = (size_t)ntasks * sizeof(bbm_noindel_task), sb = (size_t)ntasks * 4;
+    const size_t mb = match_buf && match_off ? (size_t)match_off[ntasks] : 0, fb = (size_t)(ntasks + 1) * 8;
+    if (c->d_reads.ensure((size_t)reads_bytes + 16) || c->d_tasks.ensure(tb) || c->d_outs.ensure(sb) || c->d_match.ensure(mb + 16) || c->d_moff.ensure(fb))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(c->d_reads.p, reads, (size_t)reads_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, tasks, tb, cudaMemcpyHostToDevice, st));
+    if (mb) { CK(cudaMemcpyAsync(c->d_moff.p, match_off, fb, cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(c->d_match.p, 0, mb, st)); }
+    int rc = run_noindel(c, (const int8_t*)c->d_reads.p, d_refs, (const bbm_noindel_task*)c->d_tasks.p, (int*)c->d_outs.p,
+                         mb ? (int8_t*)c->d_match.p : nullptr, mb ? (const int64_t*)c->d_moff.p : nullptr, ntasks, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(scores, c->d_outs.p, sb, cudaMemcpyDeviceToHost, st));
+    if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }

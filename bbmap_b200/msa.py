@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .workloads import TASK_DTYPE, OUT_DTYPE, TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK, match_offsets
+from .workloads import NOINDEL_TASK_DTYPE, TASK_DTYPE, OUT_DTYPE, TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK, match_offsets
 
 
 def _p(a):
@@ -112,6 +112,19 @@ class MultiStateAligner11tsCUDA:
         _lib.check(self.L.bbm_msa_batch_dev(self.h, d_reads, d_ref, d_tasks, d_outs, ntasks, d_match, d_moff,
                                            max_rows, max_cols, stream, C.byref(ms)), "bbm_msa_batch_dev")
         return ms.value
+
+    def scoreNoIndels(self, reads, d_ref, tasks, match_off=None):
+        """MSA.scoreNoIndels for a batch of (read, site) pairs (…JNI.java:1033-1089); with match_off also the match strings
+        of scoreNoIndelsAndMakeMatchString (:1243-1318).  Returns (scores, match_buf)."""
+        reads = np.ascontiguousarray(reads).view(np.int8)
+        tasks = np.ascontiguousarray(tasks, NOINDEL_TASK_DTYPE)
+        scores = np.zeros(len(tasks), np.int32)
+        mbuf = np.zeros(int(match_off[-1]) if match_off is not None else 1, np.int8)
+        moff = None if match_off is None else np.ascontiguousarray(match_off, np.int64)
+        _lib.check(self.L.bbm_noindel_batch_host(self.h, _p(reads), reads.size, d_ref, _p(tasks), _p(scores),
+                                                _p(mbuf) if moff is not None else None, _p(moff) if moff is not None else None, len(tasks)),
+                   "bbm_noindel_batch_host")
+        return scores, mbuf
 
     # -- reference-named conveniences over align_batch (argument meaning as in MSA.java / …JNI.java) --
     def fillAndScoreLimited(self, reads, d_ref, tasks):

@@ -103,6 +103,18 @@ int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 
+/* ---- ungapped site scoring: MSA.scoreNoIndels / scoreNoIndelsAndMakeMatchString (…JNI.java:1033-1089, 1243-1318) ---- */
+typedef struct {                /* 32 bytes */
+    int64_t read_off, ref_off;  /* byte offsets of the read / of the reference array */
+    int32_t read_len, ref_len;  /* ref_len = length of the reference array (Java ref.length) */
+    int32_t ref_start;          /* refStart (may be negative / run past the end: scored as POINTS_NOREF) */
+    int32_t flags;              /* bit0: also write the match string ('m','S','N'); then out-of-bounds sites score -99999 */
+} bbm_noindel_task;
+int  bbm_noindel_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_refs, const bbm_noindel_task* d_tasks, int32_t* d_scores,
+                           int8_t* d_match_buf, const int64_t* d_match_off, int64_t ntasks, void* stream, float* kernel_ms_out);
+int  bbm_noindel_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_noindel_task* tasks,
+                            int32_t* scores, int8_t* match_buf, const int64_t* match_off, int64_t ntasks);
+
 /* ---- KeyRing seeding (AbstractMapThread.quickMap up to the index search; QualityTools / KeyRing) ---- */
 typedef struct {                /* 32 bytes; defaults = BBMap.setDefaults (current/align2/BBMap.java:45-65) */
     int32_t keylen;             /* 13 */

@@ -199,3 +199,37 @@ void orc_seed_batch(const int8_t* bases, const int8_t* quality, const int64_t* r
         if (nkeys[r] <= 0) { for (int i = 0; i < maxKeys; i++) { of[i] = -1; ke[i] = -1; ks[i] = 0; } memset(baseScores + o, 0, (size_t)len); }
     }
 }
+
+/* ---- MSA.scoreNoIndels / scoreNoIndelsAndMakeMatchString (MultiStateAligner11tsJNI.java:1033-1089, 1243-1318) ---- */
+int orc_score_no_indels(const int8_t* read, int len, const int8_t* ref, int refLen, int refStart, int8_t* match /* NULL = plain scoreNoIndels */) {
+    int score = 0, mode = -1, timeInMode = 0, readStart = 0, readStop = len;
+    const long long refStop = (long long)refStart + len;
+    if (match && (refStart < 0 || refStop > refLen)) return -99999;
+    if (refStart < 0) readStart = -refStart;            /* POINTS_NOREF*readStart == 0 */
+    if (refStop > refLen) readStop -= (int)(refStop - refLen);
+    for (int i = readStart; i < readStop; i++) {
+        const int8_t c = read[i], r = ref[refStart + i];
+        if (c == r && c != 'N') {
+            if (mode == 0) { timeInMode++; score += 100; } else { timeInMode = 0; score += 70; }
+            if (match) match[i] = 'm';
+            mode = 0;
+        } else if (c < 0 || c == 'N') { if (match) match[i] = 'N'; }
+        else if (r < 0 || r == 'N') { if (match) match[i] = 'N'; }
+        else {
+            if (match) match[i] = 'S';
+            if (mode == 3) timeInMode++; else timeInMode = 0;
+            const int t = timeInMode + 1;
+            score += t > 5 ? -25 : (t > 1 ? -51 : -127);
+            mode = 3;
+        }
+    }
+    return score;
+}
+void orc_noindel_batch(const int8_t* reads, const int8_t* refs, const orc_noindel_task* tasks, int32_t* scores, int8_t* match_buf,
+                       const int64_t* match_off, int64_t n) {
+    for (int64_t i = 0; i < n; i++) {
+        const orc_noindel_task* T = &tasks[i];
+        int8_t* m = ((T->flags & 1) && match_buf) ? match_buf + match_off[i] : 0;
+        scores[i] = orc_score_no_indels(reads + T->read_off, T->read_len, refs + T->ref_off, T->ref_len, T->ref_start, m);
+    }
+}

@@ -10,4 +10,8 @@ int orc_rcomp_key_fast(int kmer, int k);
 int orc_quickmap_seed(const int8_t* bases, const int8_t* quality, int len, const orc_seed_cfg* cfg, int32_t* offsets, int32_t* keys, int32_t* keyScores, int8_t* baseScores, float* keyProbsScratch);
 void orc_seed_batch(const int8_t* bases, const int8_t* quality, const int64_t* read_off, int64_t nreads, const orc_seed_cfg* cfg,
                     int32_t maxKeys, int32_t* nkeys, int32_t* offsets, int32_t* keys, int32_t* keyScores, int8_t* baseScores);
+typedef struct { int64_t read_off, ref_off; int32_t read_len, ref_len, ref_start, flags; } orc_noindel_task; /* 32 B */
+int orc_score_no_indels(const int8_t* read, int len, const int8_t* ref, int refLen, int refStart, int8_t* match);
+void orc_noindel_batch(const int8_t* reads, const int8_t* refs, const orc_noindel_task* tasks, int32_t* scores, int8_t* match_buf,
+                       const int64_t* match_off, int64_t n);
 #endif

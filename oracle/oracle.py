@@ -120,6 +120,17 @@ class Oracle:
           _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns))
         return res, int(it[0])
 
+    # ---------------- scoreNoIndels ----------------
+    def noindel_batch(self, reads, refs, tasks, match_off=None):
+        reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
+        tasks = np.ascontiguousarray(tasks)
+        scores = np.zeros(len(tasks), np.int32)
+        mbuf = np.zeros(int(match_off[-1]) if match_off is not None else 1, np.int8)
+        self.lib.orc_noindel_batch.restype = None
+        self.lib.orc_noindel_batch(_p(reads), _p(refs), _p(tasks), _p(scores), _p(mbuf) if match_off is not None else None,
+                                   _p(np.ascontiguousarray(match_off, np.int64)) if match_off is not None else None, C.c_int64(len(tasks)))
+        return scores, mbuf
+
     # ---------------- KeyRing seeding ----------------
     def seed_batch(self, bases, quality, read_off, cfg, maxKeys=96):
         bases = np.ascontiguousarray(bases).view(np.int8)

@@ -140,3 +140,33 @@ def test_invalid_and_empty(msa):
     outs, _ = msa.align_batch(np.frombuffer(b"ACGT", np.int8), d_ref, tasks)
     assert (outs["status"] == -3).all()
     msa.free(d_ref)
+
+
+def test_score_no_indels(oracle, msa):
+    """a10: ungapped site scoring, incl. N, sites hanging over both ends of the reference array, and match strings."""
+    genome = wl.random_genome(30000, seed=26).copy()
+    genome[100:130] = ord("N")
+    reads, tasks = wl.make_msa_tasks(genome, 4000, seed=27, flags=0)
+    nt = np.zeros(len(tasks) + 40, wl.NOINDEL_TASK_DTYPE)
+    nt["read_off"][: len(tasks)] = tasks["read_off"]; nt["read_len"][: len(tasks)] = tasks["read_len"]
+    nt["ref_len"] = len(genome); nt["ref_start"][: len(tasks)] = tasks["ref_start"] + 4
+    for k in range(40):                      # overhanging / N-block sites
+        j = len(tasks) + k
+        nt["read_off"][j] = tasks["read_off"][k]; nt["read_len"][j] = tasks["read_len"][k]
+        nt["ref_start"][j] = [-7, -1, len(genome) - 30, len(genome) - 1, 90, 120][k % 6]
+    for flags in (0, 1):
+        nt["flags"] = flags
+        moff = np.zeros(len(nt) + 1, np.int64); np.cumsum(nt["read_len"], out=moff[1:])
+        exp, em = oracle.noindel_batch(reads, genome, nt, match_off=moff if flags else None)
+        d_ref = msa.load_reference(genome)
+        got, gm = msa.scoreNoIndels(reads, d_ref, nt, match_off=moff if flags else None)
+        msa.free(d_ref)
+        assert np.array_equal(got, exp)
+        if flags:
+            assert gm.tobytes() == em.tobytes() and (exp == -99999).any()
+    # the generator's vectorised scoreNoIndels agrees with the restatement on in-bounds sites
+    L = 150
+    sel = np.nonzero(tasks["read_len"] == L)[0][:500]
+    r2 = np.stack([reads[tasks["read_off"][i]: tasks["read_off"][i] + L] for i in sel])
+    g2 = np.stack([genome[tasks["ref_start"][i] + 4: tasks["ref_start"][i] + 4 + L] for i in sel])
+    assert np.array_equal(wl.score_no_indels_batch(r2, g2), exp[sel])
