@@ -7,6 +7,7 @@
 #include <vector>
 #include <mutex>
 #include <cmath>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "msa_common.cuh"
 
@@ -31,6 +32,15 @@ extern "C" int bbm_launch_seed_reverse(const int* nkeys, const int* offsets, con
 extern "C" int bbm_seed_threads();
 extern "C" int bbm_launch_noindel(const int8_t* reads, const int8_t* refs, const bbm_noindel_task* tasks, int* scores,
                                   int8_t* match_buf, const long long* match_off, long long n, cudaStream_t st);
+extern "C" int bbm_index_emit(const int8_t* chrom, int chromLen, int k, int siteHigh, unsigned* keys, int* vals, long long outBase, int* sizes,
+                              unsigned invalidKey, cudaStream_t st);
+extern "C" int bbm_index_sort_pairs(void* temp, size_t* tempBytes, const unsigned* keysIn, unsigned* keysOut, const int* valsIn, int* valsOut,
+                                    long long n, int endBit, cudaStream_t st);
+extern "C" int bbm_index_scan(void* temp, size_t* tempBytes, const int* in, int* out, long long n, cudaStream_t st);
+extern "C" int bbm_index_count_defined(const int8_t* bytes, long long n, unsigned long long* out, cudaStream_t st);
+extern "C" int bbm_index_analyze_block(const int* starts, const int* sites, int k, int* COUNTS, unsigned long long* clump, cudaStream_t st);
+extern "C" int bbm_index_finish_counts(int k, int* COUNTS, const unsigned long long* clump, int* maxOut, cudaStream_t st);
+extern "C" int bbm_index_lenhist(int k, const int* COUNTS, int* lenCounts, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -82,12 +92,18 @@ struct bbm_ctx {
     int use_narrow = 1;
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
     DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2, seedScratch, d_seed[8];
-    bool seed_tables = false;   // staging for the host-buffer entry point
+    bool seed_tables = false;
+    struct IndexBlock { int* starts = nullptr; int* sites = nullptr; long long nsites = 0; int minChrom = 0, maxChrom = 0; };
+    std::vector<IndexBlock> iblocks;
+    int* d_counts = nullptr; int ihist[1001]; bbm_index_cfg icfg; bool has_index = false;
+    const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
     long long launches = 0;
     std::mutex mu;
 };
+
+static void index_free(bbm_ctx* c);
 
 extern "C" const char* bbm_last_error(void) { return g_err.c_str(); }
 
@@ -125,6 +141,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
     c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release();
     c->h_stage.release();
+    index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -638,5 +655,155 @@ extern "C" int bbm_noindel_batch_host(bbm_ctx* c, const int8_t* reads, int64_t r
     CK(cudaMemcpyAsync(scores, c->d_outs.p, sb, cudaMemcpyDeviceToHost, st));
     if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  k-mer index build + analysis  =====================
+static void index_free(bbm_ctx* c) {
+    for (auto& b : c->iblocks) { if (b.starts) cudaFree(b.starts); if (b.sites) cudaFree(b.sites); }
+    c->iblocks.clear();
+    if (c->d_counts) cudaFree(c->d_counts);
+    c->d_counts = nullptr; c->has_index = false;
+}
+
+static void index_cfg_init(bbm_index_cfg* c, int k, int chrombits, long long numDefinedBases) {
+    // BBIndex statics (current/align2/BBIndex.java:3169-3262) + the small-genome retune of BBMap.loadIndex (BBMap.java:367-382)
+    memset(c, 0, sizeof(*c));
+    c->keylen = k; c->chrombits = chrombits;
+    c->max_hits_reduction2 = 2; c->maximum_max_hits_reduction = 3; c->hit_reduction_div = 5;
+    float f = 0.03f;
+    if (numDefinedBases < 300000000LL) {
+        c->max_hits_reduction2 += 1; c->maximum_max_hits_reduction += 1;
+        if (numDefinedBases < 30000000LL) { f = f * 0.5f; c->maximum_max_hits_reduction += 1; c->hit_reduction_div = std::max(c->hit_reduction_div - 1, 3); }
+        else if (numDefinedBases < 100000000LL) f = f * 0.6f;
+        else f = f * 0.75f;
+    }
+    c->fraction_to_exclude = f;
+    c->min_index_to_drop_long_hit_list = (int)(1000 * (1 - 3.5 * f));      // setFractionToExclude: double arithmetic
+    c->max_average_list_to_search = (int)(1000 * (1 - 2.3 * f));
+    c->max_average_list_to_search2 = (int)(1000 * (1 - 1.4 * f));
+    c->max_single_list_to_search = (int)(1000 * (1 - 1.0 * f));
+    c->max_shortest_list_to_search = (int)(1000 * (1 - 2.8 * f));
+    c->shift_length = 32 - 1 - chrombits;
+    c->chroms_per_block = 1 << chrombits;
+}
+
+extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
+                               bbm_index_cfg* cfg_out, int32_t* nblocks_out) {
+    if (!c || !d_chroms || !chrom_off || nchroms < 1 || keylen < 8 || keylen > 15) return fail(BBM_E_ARG, "bbm_index_build: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    index_free(c);
+    const int k = keylen;
+    const long long keyspace = 1LL << (2 * k);
+    long long maxLen = 0, total = chrom_off[nchroms] - chrom_off[0];
+    for (int i = 0; i < nchroms; ++i) maxLen = std::max<long long>(maxLen, chrom_off[i + 1] - chrom_off[i]);
+    if (chrombits < 0) { int nlz = maxLen == 0 ? 32 : __builtin_clz((unsigned)maxLen); chrombits = std::min(nlz - 1, 16); }
+    if (maxLen - 1 > (long long)(~((-1) << (32 - 1 - chrombits)))) return fail(BBM_E_ARG, "bbm_index_build: chromosome longer than MAX_ALLOWED_CHROM_INDEX for these chrombits");
+    // numDefinedBases
+    unsigned long long* d_def = nullptr; CK(cudaMalloc(&d_def, 8)); CK(cudaMemsetAsync(d_def, 0, 8, st));
+    int e = bbm_index_count_defined(d_chroms + chrom_off[0], total, d_def, st);
+    if (e) return fail(BBM_E_CUDA, "count_defined", (cudaError_t)e);
+    unsigned long long nDefined = 0; CK(cudaMemcpyAsync(&nDefined, d_def, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(d_def);
+    c->launches++;
+    index_cfg_init(&c->icfg, k, chrombits, (long long)nDefined);
+    const int cpb = c->icfg.chroms_per_block, low = cpb - 1, shift = c->icfg.shift_length;
+    // blocks: chromosomes sharing (chrom & ~low); chrom numbers are 1-based (IndexMaker4.makeIndex :44-62)
+    for (int chrom = 1; chrom <= nchroms;) {
+        const int a = std::max(1, chrom & ~low), b = std::min(nchroms, (chrom & ~low) + cpb - 1);
+        bbm_ctx::IndexBlock B; B.minChrom = a; B.maxChrom = b;
+        long long n = 0;
+        for (int ch = a; ch <= b; ++ch) n += chrom_off[ch] - chrom_off[ch - 1];
+        unsigned *k0 = nullptr, *k1 = nullptr; int *v0 = nullptr, *v1 = nullptr, *sizes = nullptr;
+        CK(cudaMalloc(&k0, (size_t)n * 4 + 16)); CK(cudaMalloc(&k1, (size_t)n * 4 + 16)); CK(cudaMalloc(&v0, (size_t)n * 4 + 16)); CK(cudaMalloc(&v1, (size_t)n * 4 + 16));
+        CK(cudaMalloc(&sizes, (size_t)(keyspace + 1) * 4)); CK(cudaMemsetAsync(sizes, 0, (size_t)(keyspace + 1) * 4, st));
+        CK(cudaMalloc(&B.starts, (size_t)(keyspace + 1) * 4));
+        const unsigned invalid = 1u << (2 * k);
+        long long base = 0;
+        for (int ch = a; ch <= b; ++ch) {
+            const int len = (int)(chrom_off[ch] - chrom_off[ch - 1]);
+            e = bbm_index_emit(d_chroms + chrom_off[ch - 1], len, k, (ch & low) << shift, k0, v0, base, sizes, invalid, st);
+            if (e) return fail(BBM_E_CUDA, "index_emit_kernel", (cudaError_t)e);
+            c->launches++;
+            base += len;
+        }
+        size_t tb1 = 0, tb2 = 0;
+        bbm_index_sort_pairs(nullptr, &tb1, k0, k1, v0, v1, n, 2 * k + 1, st);
+        bbm_index_scan(nullptr, &tb2, sizes, B.starts, keyspace + 1, st);
+        void* temp = nullptr; CK(cudaMalloc(&temp, std::max(tb1, tb2) + 16));
+        e = bbm_index_sort_pairs(temp, &tb1, k0, k1, v0, v1, n, 2 * k + 1, st);
+        if (e) return fail(BBM_E_CUDA, "radix sort", (cudaError_t)e);
+        e = bbm_index_scan(temp, &tb2, sizes, B.starts, keyspace + 1, st);
+        if (e) return fail(BBM_E_CUDA, "scan", (cudaError_t)e);
+        c->launches += 2;
+        int nsites = 0;
+        CK(cudaMemcpyAsync(&nsites, B.starts + keyspace, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        B.nsites = nsites;
+        CK(cudaMalloc(&B.sites, (size_t)std::max(nsites, 1) * 4));
+        CK(cudaMemcpyAsync(B.sites, v1, (size_t)nsites * 4, cudaMemcpyDeviceToDevice, st));      // valid pairs sort before the invalid key
+        CK(cudaStreamSynchronize(st));
+        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(sizes); cudaFree(temp);
+        c->iblocks.push_back(B);
+        chrom = b + 1;
+    }
+    // analyzeIndex
+    unsigned long long* d_clump = nullptr; int* d_max = nullptr;
+    CK(cudaMalloc(&c->d_counts, (size_t)keyspace * 4)); CK(cudaMemsetAsync(c->d_counts, 0, (size_t)keyspace * 4, st));
+    CK(cudaMalloc(&d_clump, (size_t)keyspace * 8)); CK(cudaMemsetAsync(d_clump, 0, (size_t)keyspace * 8, st));
+    CK(cudaMalloc(&d_max, 4)); CK(cudaMemsetAsync(d_max, 0, 4, st));
+    for (auto& B : c->iblocks) { e = bbm_index_analyze_block(B.starts, B.sites, k, c->d_counts, d_clump, st); if (e) return fail(BBM_E_CUDA, "analyze_block", (cudaError_t)e); c->launches++; }
+    e = bbm_index_finish_counts(k, c->d_counts, d_clump, d_max, st);
+    if (e) return fail(BBM_E_CUDA, "finish_counts", (cudaError_t)e);
+    c->launches += 3;
+    int maxv = 0; CK(cudaMemcpyAsync(&maxv, d_max, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    int* d_len = nullptr; CK(cudaMalloc(&d_len, (size_t)(maxv + 1) * 4)); CK(cudaMemsetAsync(d_len, 0, (size_t)(maxv + 1) * 4, st));
+    e = bbm_index_lenhist(k, c->d_counts, d_len, st);
+    if (e) return fail(BBM_E_CUDA, "lenhist", (cudaError_t)e);
+    c->launches++;
+    std::vector<int> lenCounts((size_t)maxv + 1);
+    CK(cudaMemcpyAsync(lenCounts.data(), d_len, (size_t)(maxv + 1) * 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    cudaFree(d_clump); cudaFree(d_max); cudaFree(d_len);
+    {   // Tools.makeLengthHistogram4 (Tools.java:1817-1850), buckets=1000, on the (small) histogram of list lengths
+        long long tot = 0;
+        for (int i = 1; i <= maxv; ++i) tot += (long long)i * lenCounts[i];
+        long long sum = 0; int ptr = 0; const int buckets = 1000;
+        for (int i = 0; i < buckets; ++i) {
+            const long long nextLimit = ((tot * i) + buckets / 2) / buckets;
+            while (ptr < maxv + 1 && sum < nextLimit) { sum += (int)(lenCounts[ptr] * ptr); ptr++; }
+            c->ihist[i] = std::max(0, ptr - 1);
+        }
+        c->ihist[buckets] = maxv;
+        const float f = c->icfg.fraction_to_exclude;
+        c->icfg.max_usable_length = std::max(2 * 20, c->ihist[(int)((1 - f) * (1001 - 1))]);
+        c->icfg.max_usable_length2 = std::max(6 * 20, c->ihist[(int)((1 - f * 0.25f) * (1001 - 1))]);
+        int pps = (int)floor((double)((-50 * 4000.f) / std::max(2 * 20, c->ihist[c->icfg.max_average_list_to_search])));
+        if (pps == 0) pps = -1;
+        c->icfg.points_per_site = pps;
+    }
+    c->d_chroms = d_chroms; c->chrom_off.assign(chrom_off, chrom_off + nchroms + 1);
+    c->has_index = true;
+    if (cfg_out) *cfg_out = c->icfg;
+    if (nblocks_out) *nblocks_out = (int)c->iblocks.size();
+    return BBM_OK;
+}
+
+extern "C" int bbm_index_block_sites(bbm_ctx* c, int32_t block, int64_t* nsites_out) {
+    if (!c || !c->has_index || block < 0 || block >= (int)c->iblocks.size() || !nsites_out) return fail(BBM_E_ARG, "bbm_index_block_sites: bad argument");
+    *nsites_out = c->iblocks[block].nsites;
+    return BBM_OK;
+}
+
+extern "C" int bbm_index_download(bbm_ctx* c, int32_t block, int32_t* starts, int32_t* sites, int32_t* counts, int32_t* hist1001) {
+    if (!c || !c->has_index || block < 0 || block >= (int)c->iblocks.size()) return fail(BBM_E_ARG, "bbm_index_download: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const long long keyspace = 1LL << (2 * c->icfg.keylen);
+    const auto& B = c->iblocks[block];
+    if (starts) CK(cudaMemcpy(starts, B.starts, (size_t)(keyspace + 1) * 4, cudaMemcpyDeviceToHost));
+    if (sites && B.nsites) CK(cudaMemcpy(sites, B.sites, (size_t)B.nsites * 4, cudaMemcpyDeviceToHost));
+    if (counts) CK(cudaMemcpy(counts, c->d_counts, (size_t)keyspace * 4, cudaMemcpyDeviceToHost));
+    if (hist1001) memcpy(hist1001, c->ihist, sizeof(c->ihist));
     return BBM_OK;
 }

@@ -103,6 +103,24 @@ int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
 
+/* ---- k-mer index: IndexMaker4 (build) + BBIndex.analyzeIndex (current/align2/IndexMaker4.java:160-421, BBIndex.java:101-191) ---- */
+typedef struct {        /* 80 bytes: the BBIndex statics as they stand after BBMap.loadIndex + analyzeIndex for this genome */
+    int32_t keylen, chrombits, shift_length, chroms_per_block;
+    int32_t max_hits_reduction2, maximum_max_hits_reduction, hit_reduction_div, points_per_site;
+    int32_t min_index_to_drop_long_hit_list, max_average_list_to_search, max_average_list_to_search2, max_single_list_to_search;
+    int32_t max_shortest_list_to_search, max_usable_length, max_usable_length2, pad_;
+    float fraction_to_exclude, padf_[3];
+} bbm_index_cfg;
+/* d_chroms: the chromosome arrays (upper-case ACGTN bytes, N-padded exactly as FastaToChromArrays2 lays them out),
+ * concatenated, device-resident; chrom_off (HOST) has nchroms+1 byte offsets; chromosome numbers are 1-based.
+ * chrombits<0 = automatic (BBMap.java:317-321).  The index stays resident in the context. */
+int  bbm_index_build(bbm_ctx* ctx, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
+                     bbm_index_cfg* cfg_out, int32_t* nblocks_out);
+/* Sizes / contents for inspection and parity tests: nsites of a block; copies of starts[4^k+1], sites[nsites] of one block;
+ * COUNTS[4^k] and lengthHistogram[1001] (either may be NULL). */
+int  bbm_index_block_sites(bbm_ctx* ctx, int32_t block, int64_t* nsites_out);
+int  bbm_index_download(bbm_ctx* ctx, int32_t block, int32_t* starts, int32_t* sites, int32_t* counts, int32_t* hist1001);
+
 /* ---- ungapped site scoring: MSA.scoreNoIndels / scoreNoIndelsAndMakeMatchString (…JNI.java:1033-1089, 1243-1318) ---- */
 typedef struct {                /* 32 bytes */
     int64_t read_off, ref_off;  /* byte offsets of the read / of the reference array */

@@ -120,6 +120,37 @@ class Oracle:
           _p(packed), _p(self.sub), _p(self.ins), C.c_int(maxRows), C.c_int(maxColumns))
         return res, int(it[0])
 
+    # ---------------- index build + analysis ----------------
+    def index_build(self, chrom_bytes, chrom_off, keylen, chrombits=-1):
+        """Returns (cfg structured array[1], [(starts, sites) per block], COUNTS, hist1001)."""
+        from bbmap_b200.index import INDEX_CFG_DTYPE
+        L = self.lib
+        b = np.ascontiguousarray(chrom_bytes).view(np.int8); off = np.ascontiguousarray(chrom_off, np.int64)
+        nch = len(off) - 1
+        if chrombits < 0:
+            chrombits = L.orc_auto_chrombits(_p(off), C.c_int(nch))
+        ndef = int(np.isin(b.view(np.uint8), np.frombuffer(b"ACGTUacgtu", np.uint8)).sum())
+        cfg = np.zeros(1, INDEX_CFG_DTYPE)
+        L.orc_index_cfg_init(_p(cfg), C.c_int(keylen), C.c_int(chrombits), C.c_int64(ndef))
+        cpb = int(cfg["chroms_per_block"][0]); low = cpb - 1
+        ks = 1 << (2 * keylen)
+        blocks = []
+        chrom = 1
+        L.orc_index_build_block.restype = C.c_int64
+        while chrom <= nch:
+            a = max(1, chrom & ~low); bmax = min(nch, (chrom & ~low) + cpb - 1)
+            starts = np.zeros(ks + 1, np.int32)
+            ptr = C.POINTER(C.c_int32)()
+            n = L.orc_index_build_block(_p(b), _p(off), C.c_int(a), C.c_int(bmax), _p(cfg), _p(starts), C.byref(ptr))
+            sites = np.ctypeslib.as_array(ptr, shape=(max(int(n), 1),)).copy()[: int(n)]
+            blocks.append((starts, sites))
+            chrom = bmax + 1
+        counts = np.zeros(ks, np.int32); hist = np.zeros(1001, np.int32)
+        sp = (C.c_void_p * len(blocks))(*[s.ctypes.data for s, _ in blocks])
+        tp = (C.c_void_p * len(blocks))(*[(t if len(t) else np.zeros(1, np.int32)).ctypes.data for _, t in blocks])
+        L.orc_index_analyze(C.c_int(len(blocks)), sp, tp, _p(cfg), _p(counts), _p(hist))
+        return cfg, blocks, counts, hist
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
