@@ -41,6 +41,13 @@ extern "C" int bbm_index_count_defined(const int8_t* bytes, long long n, unsigne
 extern "C" int bbm_index_analyze_block(const int* starts, const int* sites, int k, int* COUNTS, unsigned long long* clump, cudaStream_t st);
 extern "C" int bbm_index_finish_counts(int k, int* COUNTS, const unsigned long long* clump, int* maxOut, cudaStream_t st);
 extern "C" int bbm_index_lenhist(int k, const int* COUNTS, int* lenCounts, cudaStream_t st);
+extern "C" size_t bbm_search_ctx_bytes();
+extern "C" int bbm_search_threads();
+extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
+                                 const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
+                                 const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
+                                 int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* ctxPool, int8_t* revPool,
+                                 unsigned int* counter, int blocks, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -96,7 +103,9 @@ struct bbm_ctx {
     struct IndexBlock { int* starts = nullptr; int* sites = nullptr; long long nsites = 0; int minChrom = 0, maxChrom = 0; };
     std::vector<IndexBlock> iblocks;
     int* d_counts = nullptr; int ihist[1001]; bbm_index_cfg icfg; bool has_index = false;
-    const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;   // staging for the host-buffer entry point
+    const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;
+    void* d_icfg = nullptr; void* d_iblocks = nullptr; int* d_ihist = nullptr; long long* d_chrom_off = nullptr;
+    DevBuf searchCtx, searchRev, d_srch[8];   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
     long long launches = 0;
@@ -139,7 +148,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -664,6 +673,8 @@ static void index_free(bbm_ctx* c) {
     c->iblocks.clear();
     if (c->d_counts) cudaFree(c->d_counts);
     c->d_counts = nullptr; c->has_index = false;
+    if (c->d_icfg) cudaFree(c->d_icfg); if (c->d_iblocks) cudaFree(c->d_iblocks); if (c->d_ihist) cudaFree(c->d_ihist); if (c->d_chrom_off) cudaFree(c->d_chrom_off);
+    c->d_icfg = c->d_iblocks = nullptr; c->d_ihist = nullptr; c->d_chrom_off = nullptr;
 }
 
 static void index_cfg_init(bbm_index_cfg* c, int k, int chrombits, long long numDefinedBases) {
@@ -783,6 +794,17 @@ extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t
         c->icfg.points_per_site = pps;
     }
     c->d_chroms = d_chroms; c->chrom_off.assign(chrom_off, chrom_off + nchroms + 1);
+    {   // device-side descriptors for the search kernel
+        struct Blk { const int* starts; const int* sites; };
+        std::vector<Blk> hb;
+        for (auto& B : c->iblocks) hb.push_back(Blk{B.starts, B.sites});
+        CK(cudaMalloc(&c->d_icfg, sizeof(bbm_index_cfg))); CK(cudaMemcpy(c->d_icfg, &c->icfg, sizeof(bbm_index_cfg), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_iblocks, hb.size() * sizeof(Blk))); CK(cudaMemcpy(c->d_iblocks, hb.data(), hb.size() * sizeof(Blk), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_ihist, sizeof(c->ihist))); CK(cudaMemcpy(c->d_ihist, c->ihist, sizeof(c->ihist), cudaMemcpyHostToDevice));
+        std::vector<long long> rel(nchroms + 1);
+        for (int i = 0; i <= nchroms; ++i) rel[i] = chrom_off[i];
+        CK(cudaMalloc(&c->d_chrom_off, rel.size() * 8)); CK(cudaMemcpy(c->d_chrom_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice));
+    }
     c->has_index = true;
     if (cfg_out) *cfg_out = c->icfg;
     if (nblocks_out) *nblocks_out = (int)c->iblocks.size();
@@ -805,5 +827,73 @@ extern "C" int bbm_index_download(bbm_ctx* c, int32_t block, int32_t* starts, in
     if (sites && B.nsites) CK(cudaMemcpy(sites, B.sites, (size_t)B.nsites * 4, cudaMemcpyDeviceToHost));
     if (counts) CK(cudaMemcpy(counts, c->d_counts, (size_t)keyspace * 4, cudaMemcpyDeviceToHost));
     if (hist1001) memcpy(hist1001, c->ihist, sizeof(c->ihist));
+    return BBM_OK;
+}
+
+// =====================  index search (BBIndex.find)  =====================
+static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int64_t* doff, int64_t nreads, const int* dn, const int* dof,
+                      const int* dks, int maxKeys, int quit2, bbm_search_head* dh, bbm_site* ds, int maxSites, cudaStream_t st, float* ms_out) {
+    if (!c->has_index) return fail(BBM_E_ARG, "bbm_search: no index in this context (call bbm_index_build first)");
+    if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if ((int)c->iblocks.size() > 64) return fail(BBM_E_SHAPE, "bbm_search: more than 64 index blocks");
+    const int T = bbm_search_threads();
+    int blocks = c->sms * 8;
+    const long long need = (nreads + T - 1) / T;
+    if (need < blocks) blocks = (int)need;
+    if (c->searchCtx.ensure((size_t)c->sms * 8 * T * bbm_search_ctx_bytes()) || c->searchRev.ensure((size_t)c->sms * 8 * T * 2 * 608))
+        return fail(BBM_E_CUDA, "cudaMalloc search scratch");
+    unsigned int* cb = (unsigned int*)c->counters.p;
+    CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, (int)c->iblocks.size(), (int)c->chrom_off.size() - 1, c->d_counts, c->d_ihist,
+                              c->d_chroms, c->d_chrom_off, db, dbs, (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites,
+                              c->searchCtx.p, (int8_t*)c->searchRev.p, cb + 202, blocks, st);
+    if (e) return fail(BBM_E_CUDA, "search_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_search_batch_dev(bbm_ctx* c, const int8_t* d_bases, const int8_t* d_baseScores, const int64_t* d_read_off, int64_t nreads,
+                                    const int32_t* d_nkeys, const int32_t* d_offsets, const int32_t* d_keyScores, int32_t maxKeys,
+                                    int32_t quit2, bbm_search_head* d_heads, bbm_site* d_sites, int32_t max_sites, void* stream, float* kernel_ms_out) {
+    if (!c || !d_bases || !d_baseScores || !d_read_off || !d_nkeys || !d_offsets || !d_keyScores || !d_heads || !d_sites || max_sites < 1 || maxKeys < 1 || maxKeys > 96)
+        return fail(BBM_E_ARG, "bbm_search_batch_dev: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_search(c, d_bases, d_baseScores, d_read_off, nreads, d_nkeys, d_offsets, d_keyScores, maxKeys, quit2, d_heads, d_sites, max_sites,
+                      stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_search_batch_host(bbm_ctx* c, const int8_t* bases, const int8_t* baseScores, const int64_t* read_off, int64_t nreads,
+                                     const int32_t* nkeys, const int32_t* offsets, const int32_t* keyScores, int32_t maxKeys,
+                                     int32_t quit2, bbm_search_head* heads, bbm_site* sites, int32_t max_sites) {
+    if (!c || !bases || !baseScores || !read_off || !nkeys || !offsets || !keyScores || !heads || !sites || max_sites < 1 || maxKeys < 1 || maxKeys > 96)
+        return fail(BBM_E_ARG, "bbm_search_batch_host: bad argument");
+    if (nreads <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nb = (size_t)read_off[nreads], kb = (size_t)nreads * maxKeys * 4;
+    const size_t hb = (size_t)nreads * sizeof(bbm_search_head), sb = (size_t)nreads * max_sites * sizeof(bbm_site);
+    DevBuf* B = c->d_srch;   // 0 bases, 1 baseScores, 2 off, 3 nkeys, 4 offsets, 5 keyScores, 6 heads, 7 sites
+    if (B[0].ensure(nb + 32) || B[1].ensure(nb + 32) || B[2].ensure((size_t)(nreads + 1) * 8) || B[3].ensure((size_t)nreads * 4) || B[4].ensure(kb) ||
+        B[5].ensure(kb) || B[6].ensure(hb) || B[7].ensure(sb))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(B[0].p, bases, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[1].p, baseScores, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[2].p, read_off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[3].p, nkeys, (size_t)nreads * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[4].p, offsets, kb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[5].p, keyScores, kb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(B[7].p, 0, sb, st));
+    int rc = run_search(c, (const int8_t*)B[0].p, (const int8_t*)B[1].p, (const int64_t*)B[2].p, nreads, (const int*)B[3].p, (const int*)B[4].p,
+                        (const int*)B[5].p, maxKeys, quit2, (bbm_search_head*)B[6].p, (bbm_site*)B[7].p, max_sites, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(heads, B[6].p, hb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sites, B[7].p, sb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }

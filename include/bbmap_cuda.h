@@ -121,6 +121,33 @@ int  bbm_index_build(bbm_ctx* ctx, const int8_t* d_chroms, const int64_t* chrom_
 int  bbm_index_block_sites(bbm_ctx* ctx, int32_t block, int64_t* nsites_out);
 int  bbm_index_download(bbm_ctx* ctx, int32_t block, int32_t* starts, int32_t* sites, int32_t* counts, int32_t* hist1001);
 
+/* ---- index search: BBIndex.find (current/align2/BBIndex.java:403-639) — seeds -> candidate sites (SiteScore) ---- */
+#define BBM_MAX_GAPS 10
+#define BBM_ST_ANOMALY        1   /* extendScore located no base (the reference prints an anomaly and scores -99999) */
+#define BBM_ST_SITE_OVERFLOW  2   /* more sites than max_sites for one read (extra sites dropped) */
+#define BBM_ST_GAP_OVERFLOW   4   /* gap array longer than 9 ints */
+#define BBM_ST_GAPFIX         8   /* subsumption into a site that carries gaps: GapTools.fixGaps is not implemented */
+#define BBM_ST_BADARG        16
+typedef struct {            /* 64 bytes: one SiteScore as BBIndex emits it (stream/SiteScore.java) */
+    int32_t chrom, start, stop, hits, score, ngaps;
+    int8_t strand, perfect, semiperfect, pad_;
+    int32_t gaps[BBM_MAX_GAPS - 1];
+} bbm_site;
+typedef struct {            /* 48 bytes per read */
+    int32_t nsites, status, num_hits, max_score, max_quick_score, pad_;
+    int32_t best_scores[6];     /* bestScores[] at the end of find(): top score, max hits, qcutoff, best qscore, maxQuickScore, perfects */
+} bbm_search_head;
+/* Uses the index resident in the context (bbm_index_build).  Inputs are the seeding outputs (bbm_seed_batch_*): per read
+ * nkeys, offsets[maxKeys], keyScores[maxKeys] and the base scores; sites is [nreads][max_sites].  quit_after_two_perfects
+ * mirrors AbstractIndex.QUIT_AFTER_TWO_PERFECTS (true single-ended, false paired: BBMap.java:434). */
+int  bbm_search_batch_dev(bbm_ctx* ctx, const int8_t* d_bases, const int8_t* d_baseScores, const int64_t* d_read_off, int64_t nreads,
+                          const int32_t* d_nkeys, const int32_t* d_offsets, const int32_t* d_keyScores, int32_t maxKeys,
+                          int32_t quit_after_two_perfects, bbm_search_head* d_heads, bbm_site* d_sites, int32_t max_sites,
+                          void* stream, float* kernel_ms_out);
+int  bbm_search_batch_host(bbm_ctx* ctx, const int8_t* bases, const int8_t* baseScores, const int64_t* read_off, int64_t nreads,
+                           const int32_t* nkeys, const int32_t* offsets, const int32_t* keyScores, int32_t maxKeys,
+                           int32_t quit_after_two_perfects, bbm_search_head* heads, bbm_site* sites, int32_t max_sites);
+
 /* ---- ungapped site scoring: MSA.scoreNoIndels / scoreNoIndelsAndMakeMatchString (…JNI.java:1033-1089, 1243-1318) ---- */
 typedef struct {                /* 32 bytes */
     int64_t read_off, ref_off;  /* byte offsets of the read / of the reference array */

@@ -45,7 +45,7 @@ def _p(a):
 
 class Oracle:
     def __init__(self):
-        so = os.path.join(HERE, "liborc.so")
+        so = os.environ.get("ORC_SO", os.path.join(HERE, "liborc.so"))
         if not os.path.exists(so):
             build()
         self.lib = C.CDLL(so)
@@ -150,6 +150,34 @@ class Oracle:
         tp = (C.c_void_p * len(blocks))(*[(t if len(t) else np.zeros(1, np.int32)).ctypes.data for _, t in blocks])
         L.orc_index_analyze(C.c_int(len(blocks)), sp, tp, _p(cfg), _p(counts), _p(hist))
         return cfg, blocks, counts, hist
+
+    # ---------------- index search (BBIndex.find) ----------------
+    def search_batch(self, index, chrom_bytes, chrom_off, bases, baseScores, read_off, seeds, quit_after_two_perfects=True):
+        """index = (cfg, blocks, counts, hist) from index_build; seeds = dict(nkeys, offsets, keyScores) from seed_batch.
+        Returns a SEARCH_RESULT_DTYPE array."""
+        from bbmap_b200.search import SEARCH_RESULT_DTYPE
+        cfg, blocks, counts, hist = index
+        L = self.lib
+
+        class Blk(C.Structure):
+            _fields_ = [("starts", C.c_void_p), ("sites", C.c_void_p)]
+
+        class Idx(C.Structure):
+            _fields_ = [("cfg", C.c_void_p), ("blocks", C.c_void_p), ("nblocks", C.c_int32), ("nchroms", C.c_int32),
+                        ("counts", C.c_void_p), ("hist", C.c_void_p), ("chroms", C.c_void_p), ("chrom_off", C.c_void_p)]
+        keep = [(np.ascontiguousarray(s_), np.ascontiguousarray(t_ if len(t_) else np.zeros(1, np.int32))) for s_, t_ in blocks]
+        barr = (Blk * len(keep))(*[Blk(a.ctypes.data, b.ctypes.data) for a, b in keep])
+        cb = np.ascontiguousarray(chrom_bytes).view(np.int8); co = np.ascontiguousarray(chrom_off, np.int64)
+        X = Idx(cfg.ctypes.data, C.addressof(barr), len(keep), len(co) - 1, counts.ctypes.data, hist.ctypes.data, cb.ctypes.data, co.ctypes.data)
+        bases = np.ascontiguousarray(bases).view(np.int8); bs = np.ascontiguousarray(baseScores).view(np.int8)
+        ro = np.ascontiguousarray(read_off, np.int64)
+        n = len(ro) - 1
+        res = np.zeros(n, SEARCH_RESULT_DTYPE)
+        nk = np.ascontiguousarray(seeds["nkeys"], np.int32); of = np.ascontiguousarray(seeds["offsets"], np.int32); ks = np.ascontiguousarray(seeds["keyScores"], np.int32)
+        L.orc_search_batch.restype = None
+        L.orc_search_batch(C.byref(X), _p(bases), _p(bs), _p(ro), C.c_int64(n), _p(nk), _p(of), _p(ks), C.c_int32(of.shape[1]),
+                           C.c_int(1 if quit_after_two_perfects else 0), _p(res))
+        return res
 
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):

@@ -1,0 +1,119 @@
+"""GPU parity: BBIndex.find on the device (key filtering, prescan, slowWalk3, extendScore, site emission) vs the C
+restatement — every field of every emitted site and the final bestScores[], bit-exact; plus the position-level truth check
+the reference uses for synthetic reads (true origin must be the top site)."""
+import numpy as np
+import pytest
+
+from bbmap_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(seed, sizes, n, L, k, paired=False, repeats=True, chrombits=-1, max_length=None):
+    from bbmap_b200.index import pack_chromosomes
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scafs = []
+    for sz in sizes:
+        s = wl.ACGT[rng.integers(0, 4, size=sz, dtype=np.uint8)].copy()
+        if repeats and sz > 5000:
+            unit = s[200:900].copy()
+            for r in range(4):
+                p = int(rng.integers(1000, sz - 800)); s[p:p + 700] = unit
+                for q in rng.integers(0, 700, size=5):
+                    s[p + q] = wl.ACGT[rng.integers(0, 4)]
+            s[sz // 2: sz // 2 + 30] = ord("N")
+        scafs.append(s)
+    cb, co, table = pack_chromosomes(scafs, **({"max_length": max_length} if max_length else {}))
+    reads, truth = [], []
+    for i in range(n):
+        si = int(rng.integers(0, len(scafs))); sc = scafs[si]
+        p = int(rng.integers(0, len(sc) - L - 50))
+        r = sc[p:p + L].copy()
+        kind = rng.random()
+        for q in rng.integers(0, L, size=int(rng.integers(0, 4))):
+            r[q] = wl.ACGT[rng.integers(0, 4)]
+        if kind < 0.15:      # small deletion / insertion
+            q = int(rng.integers(20, L - 20)); d = int(rng.integers(1, 6))
+            r = np.concatenate([sc[p:p + q], sc[p + q + d:p + L + d]]) if kind < 0.08 else np.concatenate([r[:q], wl.ACGT[rng.integers(0, 4, size=d, dtype=np.uint8)], r[q:L - d]])
+        elif kind < 0.2:     # unrelated
+            r = wl.ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        if rng.random() < 0.03:
+            r[int(rng.integers(0, L))] = ord("N")
+        st = int(rng.integers(0, 2))
+        if st:
+            r = wl.revcomp(r)
+        reads.append(r); truth.append((table[si][0], st, table[si][1] + p, kind))
+    bases = np.concatenate(reads)
+    off = np.zeros(n + 1, np.int64); np.cumsum([len(r) for r in reads], out=off[1:])
+    qual = rng.integers(20, 41, size=len(bases)).astype(np.uint8)
+    qual[bases == ord("N")] = 0
+    return cb, co, bases, qual, off, truth
+
+
+@pytest.mark.parametrize("sizes,k,L,chrombits,maxlen", [((150000, 40000), 13, 150, -1, None), ((60000,) * 4, 11, 100, 1, 90000), ((30000,), 10, 250, 0, None)])
+@pytest.mark.parametrize("quit2", [True, False])
+def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
+    from bbmap_b200.index import BBIndexCUDA
+    from bbmap_b200.keyring import KeyRingCUDA, default_cfg
+    from bbmap_b200 import search
+    cb, co, bases, qual, off, truth = _make(7 + k, sizes, 1500, L, k, chrombits=chrombits, max_length=maxlen)
+    cfg = default_cfg(); cfg["keylen"] = k; cfg["baseKeyHitScore"] = 100 * k
+    eidx = oracle.index_build(cb, co, k, chrombits)
+    eseeds = oracle.seed_batch(bases, qual, off, cfg, 96)
+    exp = oracle.search_batch(eidx, cb, co, bases, eseeds["baseScores"], off, eseeds, quit_after_two_perfects=quit2)
+    idx = BBIndexCUDA(cb, co, keylen=k, chrombits=chrombits)
+    try:
+        kr = KeyRingCUDA(ctx=idx.h)
+        seeds = kr.seed_batch(bases, qual, off, cfg, 96)
+        for key in ("nkeys", "offsets", "keyScores", "baseScores"):
+            assert np.array_equal(seeds[key], eseeds[key])
+        heads, sites = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2)
+    finally:
+        idx.close()
+    for f in ("nsites", "status", "num_hits", "max_score", "max_quick_score", "best_scores"):
+        assert np.array_equal(heads[f], exp[f]), f
+    assert ((exp["status"] & ~4) == 0).all()      # only "gap array longer than 9 ints" may be flagged (tiny genome, k=10)
+    for i in range(len(heads)):
+        ns = exp["nsites"][i]
+        assert sites[i, :ns].tobytes() == exp["sites"][i, :ns].tobytes(), (i, sites[i, :ns], exp["sites"][i, :ns])
+    # position-level truth (AbstractMapThread.isCorrectHit-style): related reads map to their origin with the top score
+    good = tot = 0
+    for i, (chrom, st, pos, kind) in enumerate(truth):
+        if kind >= 0.15 and kind < 0.2:
+            continue
+        tot += 1
+        ns = heads["nsites"][i]
+        if ns == 0:
+            continue
+        s = sites[i, :ns]; best = s[np.argmax(s["score"])]
+        good += int(best["chrom"] == chrom and best["strand"] == st and abs(int(best["start"]) - pos) <= 8)
+    assert good >= 0.95 * tot, (good, tot)
+    assert (heads["nsites"] > 1).any()
+
+
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_search_phix_fixture(oracle, tag):
+    """The reference's own shipped test reads (configs[0]): device == oracle bit for bit, and the true origin (in the read
+    name) is the top site for >= 95 of 100 reads."""
+    from test_search_oracle import phix, top_site_correct
+    from bbmap_b200.index import BBIndexCUDA
+    from bbmap_b200.keyring import KeyRingCUDA, default_cfg
+    from bbmap_b200 import search
+    d, cb, co, table = phix()
+    b, q, off, truth = d[tag + "_bases"], d[tag + "_qual"], d[tag + "_off"], d[tag + "_truth"]
+    eidx = oracle.index_build(cb, co, 13, -1)
+    eseeds = oracle.seed_batch(b, q, off, default_cfg(), 96)
+    idx = BBIndexCUDA(cb, co, keylen=13)
+    try:
+        seeds = KeyRingCUDA(ctx=idx.h).seed_batch(b, q, off, default_cfg(), 96)
+        for quit2 in (True, False):
+            exp = oracle.search_batch(eidx, cb, co, b, eseeds["baseScores"], off, eseeds, quit_after_two_perfects=quit2)
+            heads, sites = search.search_batch(idx, b, seeds["baseScores"], off, seeds, quit_after_two_perfects=quit2)
+            for f in ("nsites", "status", "num_hits", "max_score", "max_quick_score", "best_scores"):
+                assert np.array_equal(heads[f], exp[f]), f
+            for i in range(len(heads)):
+                ns = exp["nsites"][i]
+                assert sites[i, :ns].tobytes() == exp["sites"][i, :ns].tobytes()
+            assert sum(top_site_correct(sites[i], heads["nsites"][i], truth[i]) for i in range(len(truth))) >= 95
+    finally:
+        idx.close()
