@@ -41,6 +41,13 @@ extern "C" int bbm_index_count_defined(const int8_t* bytes, long long n, unsigne
 extern "C" int bbm_index_analyze_block(const int* starts, const int* sites, int k, int* COUNTS, unsigned long long* clump, cudaStream_t st);
 extern "C" int bbm_index_finish_counts(int k, int* COUNTS, const unsigned long long* clump, int* maxOut, cudaStream_t st);
 extern "C" int bbm_index_lenhist(int k, const int* COUNTS, int* lenCounts, cudaStream_t st);
+extern "C" int bbm_launch_gref_build(const int8_t* refs, const bbm_gapped_task* gt, const int* gaps, long long n, int8_t* pool, int stride,
+                                     int greflen, bbm_gref_info* info, bbm_msa_task* tasksOut, cudaStream_t st);
+extern "C" int bbm_launch_gref_translate(const bbm_gapped_task* gt, long long n, const int8_t* pool, int stride, const bbm_gref_info* info,
+                                         bbm_msa_out* outs, cudaStream_t st);
+extern "C" int bbm_ingest_threads();
+extern "C" int bbm_launch_ingest(int8_t* bases, int8_t* quality, const long long* read_off, long long nreads, int8_t* basesM, int* readFlags,
+                                 int flags, int readsPerBlock, int stageBytes, int blocks, cudaStream_t st);
 extern "C" size_t bbm_search_ctx_bytes();
 extern "C" int bbm_search_threads();
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
@@ -105,7 +112,9 @@ struct bbm_ctx {
     int* d_counts = nullptr; int ihist[1001]; bbm_index_cfg icfg; bool has_index = false;
     const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;
     void* d_icfg = nullptr; void* d_iblocks = nullptr; int* d_ihist = nullptr; long long* d_chrom_off = nullptr;
-    DevBuf searchCtx, searchRev, d_srch[8];   // staging for the host-buffer entry point
+    DevBuf searchCtx, searchRev, d_srch[8];
+    DevBuf d_ing[5];   // staging for bbm_ingest_batch_host
+    DevBuf grefPool, grefInfo, grefTasks, d_gtasks, d_gaps;   // gapped references (a15)   // staging for the host-buffer entry point
     PinBuf h_stage;
     std::vector<void*> uploads;
     long long launches = 0;
@@ -148,7 +157,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_srch) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -344,6 +353,67 @@ extern "C" int bbm_msa_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads
     if (mb) CK(cudaMemcpyAsync(c->d_moff.p, match_off, fb, cudaMemcpyHostToDevice, st));
     int rc = run_msa(c, (const int8_t*)c->d_reads.p, d_refs, (const bbm_msa_task*)c->d_tasks.p, (bbm_msa_out*)c->d_outs.p, ntasks,
                      mb ? (int8_t*)c->d_match.p : nullptr, mb ? (const int64_t*)c->d_moff.p : nullptr, max_rows, max_cols, st, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
+    if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  gapped references (makeGref + coordinate translation, a15)  =====================
+static const int GREF_LEN = 3002, GREF_STRIDE = 3008;      // grefbuffer = new byte[maxColumns+2] (MultiStateAligner11tsJNI.java:88)
+
+static int run_msa_gapped(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_gapped_task* d_gt, const int32_t* d_gaps,
+                          bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match, const int64_t* d_moff, cudaStream_t st, float* ms_out) {
+    if (ntasks <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (c->grefPool.ensure((size_t)ntasks * GREF_STRIDE) || c->grefInfo.ensure((size_t)ntasks * sizeof(bbm_gref_info)) ||
+        c->grefTasks.ensure((size_t)ntasks * sizeof(bbm_msa_task)))
+        return fail(BBM_E_CUDA, "cudaMalloc gref pool");
+    int e = bbm_launch_gref_build(d_refs, d_gt, d_gaps, ntasks, (int8_t*)c->grefPool.p, GREF_STRIDE, GREF_LEN, (bbm_gref_info*)c->grefInfo.p,
+                                  (bbm_msa_task*)c->grefTasks.p, st);
+    if (e) return fail(BBM_E_CUDA, "gref_build_kernel launch", (cudaError_t)e);
+    c->launches++;
+    int rc = run_msa(c, d_reads, d_refs, (const bbm_msa_task*)c->grefTasks.p, d_outs, ntasks, d_match, d_moff, MAXR, GREF_LEN, st, ms_out, nullptr);
+    if (rc) return rc;
+    e = bbm_launch_gref_translate(d_gt, ntasks, (const int8_t*)c->grefPool.p, GREF_STRIDE, (const bbm_gref_info*)c->grefInfo.p, d_outs, st);
+    if (e) return fail(BBM_E_CUDA, "gref_translate_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+extern "C" int bbm_msa_gapped_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_gapped_task* d_tasks,
+                                        const int32_t* d_gaps, bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match_buf,
+                                        const int64_t* d_match_off, void* stream, float* kernel_ms_out) {
+    if (!c || !d_reads || !d_refs || !d_tasks || !d_gaps || !d_outs) return fail(BBM_E_ARG, "bbm_msa_gapped_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_msa_gapped(c, d_reads, d_refs, d_tasks, d_gaps, d_outs, ntasks, d_match_buf, d_match_off, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_msa_gapped_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs,
+                                         const bbm_gapped_task* tasks, const int32_t* gaps, int64_t ngap_ints, bbm_msa_out* outs,
+                                         int64_t ntasks, int8_t* match_buf, const int64_t* match_off) {
+    if (!c || !reads || !d_refs || !tasks || !outs || reads_bytes < 0 || ngap_ints < 0 || (ngap_ints > 0 && !gaps))
+        return fail(BBM_E_ARG, "bbm_msa_gapped_batch_host: bad argument");
+    if (ntasks <= 0) return BBM_OK;
+    for (int64_t i = 0; i < ntasks; ++i)
+        if (tasks[i].ngaps < 0 || (tasks[i].ngaps > 0 && (tasks[i].gaps_off < 0 || (int64_t)tasks[i].gaps_off + tasks[i].ngaps > ngap_ints)))
+            return fail(BBM_E_ARG, "bbm_msa_gapped_batch_host: gap array outside the gaps buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t tb = (size_t)ntasks * sizeof(bbm_gapped_task), ob = (size_t)ntasks * sizeof(bbm_msa_out);
+    const size_t mb = match_buf && match_off ? (size_t)match_off[ntasks] : 0, fb = (size_t)(ntasks + 1) * 8;
+    if (c->d_reads.ensure((size_t)reads_bytes + 16) || c->d_gtasks.ensure(tb) || c->d_outs.ensure(ob) || c->d_gaps.ensure((size_t)ngap_ints * 4 + 16) ||
+        c->d_match.ensure(mb + 16) || c->d_moff.ensure(fb))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(c->d_reads.p, reads, (size_t)reads_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_gtasks.p, tasks, tb, cudaMemcpyHostToDevice, st));
+    if (ngap_ints) CK(cudaMemcpyAsync(c->d_gaps.p, gaps, (size_t)ngap_ints * 4, cudaMemcpyHostToDevice, st));
+    if (mb) CK(cudaMemcpyAsync(c->d_moff.p, match_off, fb, cudaMemcpyHostToDevice, st));
+    int rc = run_msa_gapped(c, (const int8_t*)c->d_reads.p, d_refs, (const bbm_gapped_task*)c->d_gtasks.p, (const int32_t*)c->d_gaps.p,
+                            (bbm_msa_out*)c->d_outs.p, ntasks, mb ? (int8_t*)c->d_match.p : nullptr, mb ? (const int64_t*)c->d_moff.p : nullptr, st, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
     if (mb) CK(cudaMemcpyAsync(match_buf, c->d_match.p, mb, cudaMemcpyDeviceToHost, st));
@@ -827,6 +897,64 @@ extern "C" int bbm_index_download(bbm_ctx* c, int32_t block, int32_t* starts, in
     if (sites && B.nsites) CK(cudaMemcpy(sites, B.sites, (size_t)B.nsites * 4, cudaMemcpyDeviceToHost));
     if (counts) CK(cudaMemcpy(counts, c->d_counts, (size_t)keyspace * 4, cudaMemcpyDeviceToHost));
     if (hist1001) memcpy(hist1001, c->ihist, sizeof(c->ihist));
+    return BBM_OK;
+}
+
+// =====================  read ingest (Read.validate + reverse complement, a0)  =====================
+static int run_ingest(bbm_ctx* c, int8_t* db, int8_t* dq, const int64_t* doff, int64_t nreads, int max_len, int flags, int8_t* dm, int* df,
+                      cudaStream_t st, float* ms_out) {
+    if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (max_len < 1) return fail(BBM_E_ARG, "bbm_ingest: max_len < 1");
+    int rpb = 64;                                             // reads per block; three staged arrays must fit 192 KB of shared memory
+    while (rpb > 1 && (long long)rpb * max_len + 48 > 64 * 1024) rpb >>= 1;
+    if ((long long)rpb * max_len + 48 > 64 * 1024) return fail(BBM_E_SHAPE, "bbm_ingest: read longer than 65488 bases");
+    const int stage = (int)((((long long)rpb * max_len + 32) + 15) & ~15LL);
+    long long blocks = (nreads + rpb - 1) / rpb;
+    const long long cap = (long long)c->sms * 4;
+    if (blocks > cap) blocks = cap;
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_ingest(db, dq, (const long long*)doff, nreads, dm, df, flags, rpb, stage, (int)blocks, st);
+    if (e) return fail(BBM_E_CUDA, "ingest_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_ingest_batch_dev(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int64_t* d_read_off, int64_t nreads, int32_t max_len,
+                                    int32_t flags, int8_t* d_basesM, int32_t* d_read_flags, void* stream, float* kernel_ms_out) {
+    if (!c || !d_bases || !d_read_off) return fail(BBM_E_ARG, "bbm_ingest_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_ingest(c, d_bases, d_quality, d_read_off, nreads, max_len, flags, d_basesM, d_read_flags, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_ingest_batch_host(bbm_ctx* c, int8_t* bases, int8_t* quality, const int64_t* read_off, int64_t nreads, int32_t flags,
+                                     int8_t* basesM, int32_t* read_flags) {
+    if (!c || !bases || !read_off) return fail(BBM_E_ARG, "bbm_ingest_batch_host: null pointer");
+    if (nreads <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t nb = (size_t)(read_off[nreads] - read_off[0]);
+    int max_len = 1;
+    for (int64_t i = 0; i < nreads; ++i) { const int64_t l = read_off[i + 1] - read_off[i]; if (l < 0) return fail(BBM_E_ARG, "read_off not ascending"); if (l > max_len) max_len = (int)l; }
+    if (read_off[0] != 0) return fail(BBM_E_ARG, "bbm_ingest_batch_host: read_off[0] must be 0");
+    DevBuf* B = c->d_ing;   // 0 bases, 1 quality, 2 offsets, 3 basesM, 4 flags
+    if (B[0].ensure(nb + 32) || B[1].ensure(nb + 32) || B[2].ensure((size_t)(nreads + 1) * 8) || B[3].ensure(nb + 32) || B[4].ensure((size_t)nreads * 4))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(B[0].p, bases, nb, cudaMemcpyHostToDevice, st));
+    if (quality) CK(cudaMemcpyAsync(B[1].p, quality, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[2].p, read_off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = run_ingest(c, (int8_t*)B[0].p, quality ? (int8_t*)B[1].p : nullptr, (const int64_t*)B[2].p, nreads, max_len, flags,
+                        basesM ? (int8_t*)B[3].p : nullptr, read_flags ? (int*)B[4].p : nullptr, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(bases, B[0].p, nb, cudaMemcpyDeviceToHost, st));
+    if (quality) CK(cudaMemcpyAsync(quality, B[1].p, nb, cudaMemcpyDeviceToHost, st));
+    if (basesM) CK(cudaMemcpyAsync(basesM, B[3].p, nb, cudaMemcpyDeviceToHost, st));
+    if (read_flags) CK(cudaMemcpyAsync(read_flags, B[4].p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }
 

@@ -240,8 +240,8 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
         int padLeft = 0, padRight = 0;
         if (bestRefStart < T.a) padLeft = max(0, T.a - bestRefStart);
         else if (bestRefStart == T.a && state == ST_INS) padLeft = stateTime;
-        if (bestRefStop > T.b) padRight = max(0, bestRefStop - T.b);
-        else if (bestRefStop == T.b && maxState == ST_INS) padRight = maxPacked & TMASK;
+        if (bestRefStop > score_ref_end(T)) padRight = max(0, bestRefStop - score_ref_end(T));
+        else if (bestRefStop == score_ref_end(T) && maxState == ST_INS) padRight = maxPacked & TMASK;
         out->score[0] = maxScore >> TBITS; out->score[1] = bestRefStart; out->score[2] = bestRefStop;
         out->score[3] = rows; out->score[4] = maxCol; out->score[5] = maxState; out->score[6] = padLeft; out->score[7] = padRight;
         out->score_len = (padLeft > 0 || padRight > 0) ? 8 : 6;

@@ -53,6 +53,9 @@ struct TaskCtx {
     int halfband;
     int flags;
 };
+// refEndLoc as score2 sees it: on a gapped reference the fill ran on [0, greflimit] but score() passes gstop = greflimit-1
+// (MultiStateAligner11tsJNI.java:127 vs :508-516)
+__device__ __forceinline__ int score_ref_end(const TaskCtx& T) { return T.b - ((T.flags & BBM_TF_GAPPED) ? 1 : 0); }
 
 // ---- suffix "limit" recurrences  h[i] = max(h[i+1] - cost_i, floor)  as a scan over g(x)=max(x-A,B) ----
 struct GFun { int A, B; };
@@ -422,8 +425,8 @@ __device__ void msa_fill_task(const MsaParams& P, const TaskCtx& T, const bbm_ms
             int padLeft = 0, padRight = 0;
             if (bestRefStart < T.a) padLeft = imax(0, T.a - bestRefStart);
             else if (bestRefStart == T.a && state == ST_INS) padLeft = stateTime;
-            if (bestRefStop > T.b) padRight = imax(0, bestRefStop - T.b);
-            else if (bestRefStop == T.b && maxState == ST_INS) padRight = maxPacked & TMASK;
+            if (bestRefStop > score_ref_end(T)) padRight = imax(0, bestRefStop - score_ref_end(T));
+            else if (bestRefStop == score_ref_end(T) && maxState == ST_INS) padRight = maxPacked & TMASK;
             out->score[0] = maxScoreOff >> TBITS; out->score[1] = bestRefStart; out->score[2] = bestRefStop;
             out->score[3] = rows; out->score[4] = maxCol; out->score[5] = maxState;
             out->score[6] = padLeft; out->score[7] = padRight;

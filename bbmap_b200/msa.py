@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .workloads import NOINDEL_TASK_DTYPE, TASK_DTYPE, OUT_DTYPE, TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK, match_offsets
+from .workloads import GAPPED_TASK_DTYPE, NOINDEL_TASK_DTYPE, TASK_DTYPE, OUT_DTYPE, TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK, match_offsets
 
 
 def _p(a):
@@ -104,6 +104,20 @@ class MultiStateAligner11tsCUDA:
         lim = outs["path"] == 0
         self.iterationsLimited += int(outs["iterations"][lim].sum())
         self.iterationsUnlimited += int(outs["iterations"][~lim].sum())
+        return outs, mbuf
+
+    def align_batch_gapped(self, reads, d_ref, gtasks, gaps, match_off):
+        """MSA.fillAndScoreLimited(read, ref, start-thresh, stop+thresh, minScore, gaps) [+ traceback] for a batch
+        (MSA.java:103-134): tasks with ngaps>0 are aligned against the gapped reference makeGref builds
+        (MultiStateAligner11tsJNI.java:668-757), on the device; score[1:3] come back in chromosome coordinates."""
+        reads = np.ascontiguousarray(reads).view(np.int8)
+        gtasks = np.ascontiguousarray(gtasks, GAPPED_TASK_DTYPE)
+        gaps = np.ascontiguousarray(gaps, np.int32)
+        outs = np.zeros(len(gtasks), OUT_DTYPE)
+        moff = np.ascontiguousarray(match_off, np.int64)
+        mbuf = np.zeros(max(int(moff[-1]), 1), np.int8)
+        _lib.check(self.L.bbm_msa_gapped_batch_host(self.h, _p(reads), reads.size, d_ref, _p(gtasks), _p(gaps) if len(gaps) else None,
+                                                   len(gaps), _p(outs), len(gtasks), _p(mbuf), _p(moff)), "bbm_msa_gapped_batch_host")
         return outs, mbuf
 
     def align_batch_dev(self, d_reads, d_ref, d_tasks, d_outs, ntasks, d_match, d_moff, max_rows, max_cols, stream=None):

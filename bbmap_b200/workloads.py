@@ -16,6 +16,7 @@ OUT_DTYPE = np.dtype([("result", "<i4", (5,)), ("path", "<i4"), ("iterations", "
                       ("score_len", "<i4"), ("match_len", "<i4"), ("status", "<i4"), ("pad_", "<i4")], align=True)
 
 TF_RAW_LIMITED, TF_RAW_UNLIMITED, TF_CLAMP, TF_SCORE, TF_TRACEBACK = 1, 2, 4, 8, 16
+GAPPED_TASK_DTYPE = np.dtype([("t", TASK_DTYPE), ("gaps_off", "<i4"), ("ngaps", "<i4")], align=True)     # bbm_gapped_task, 48 bytes
 NOINDEL_TASK_DTYPE = np.dtype([("read_off", "<i8"), ("ref_off", "<i8"), ("read_len", "<i4"), ("ref_len", "<i4"),
                                ("ref_start", "<i4"), ("flags", "<i4")], align=True)
 

@@ -36,6 +36,8 @@ extern "C" {
 #define BBM_TF_CLAMP          4  /* clamp the window to [0, ref_len-1] like MSA.fillAndScoreLimited (MSA.java:104-105) */
 #define BBM_TF_SCORE          8  /* also run score2  (…JNI.java:537-658) */
 #define BBM_TF_TRACEBACK     16  /* also run traceback2 (…JNI.java:376-495) and emit the match string */
+#define BBM_TF_GAPPED        32  /* set by the library on tasks it rewrote onto a gapped reference: the fill runs on
+                                    [0, greflimit] but score2 is called with refEndLoc = greflimit-1 (…JNI.java:127, 508-516) */
 
 /* One (read, candidate window) alignment.  40 bytes. */
 typedef struct {
@@ -90,6 +92,25 @@ int  bbm_msa_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, 
                         const bbm_msa_task* tasks, bbm_msa_out* outs, int64_t ntasks,
                         int8_t* match_buf, const int64_t* match_off);
 
+/* ---- gapped references: MSA.fillAndScoreLimited(read, ref, start-thresh, stop+thresh, minScore, gaps) (MSA.java:103-134) ->
+ * makeGref (…JNI.java:668-757) + translateFromGappedCoordinate (:759-779).  A task with ngaps>0 is aligned against the
+ * gapped reference built on the device from its gap array {start0,stop0,start1,stop1,...} (SiteScore.gaps); bestRefStart /
+ * bestRefStop (score[1], score[2]) come back in chromosome coordinates.  Tasks with ngaps==0 behave as in bbm_msa_batch_*.
+ * A gapped reference longer than ALIGN_COLUMNS+2 = 3002 bytes gives status BBM_E_SHAPE (the reference asserts).
+ * match_off capacity per gapped task: rows + columns + 127 * ('-' symbols). */
+typedef struct {                /* 48 bytes */
+    bbm_msa_task t;             /* ref_start/ref_end = the window before clamping; flags: BBM_TF_SCORE / BBM_TF_TRACEBACK */
+    int32_t gaps_off;           /* index of the first int of this task's gap array in the gaps buffer */
+    int32_t ngaps;              /* ints in the gap array (even); 0 = no gaps */
+} bbm_gapped_task;
+typedef struct { int32_t origin, greflimit, greflimit2, status; } bbm_gref_info;   /* grefRefOrigin, greflimit, greflimit2 */
+int  bbm_msa_gapped_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_refs, const bbm_gapped_task* d_tasks,
+                              const int32_t* d_gaps, bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match_buf,
+                              const int64_t* d_match_off, void* stream, float* kernel_ms_out);
+int  bbm_msa_gapped_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs,
+                               const bbm_gapped_task* tasks, const int32_t* gaps, int64_t ngap_ints, bbm_msa_out* outs,
+                               int64_t ntasks, int8_t* match_buf, const int64_t* match_off);
+
 /* Tuning / introspection.  bbm_set_option keys: "narrow" (1 = route near-diagonal limited fills through the
  * thread-per-alignment kernel first; 0 = register-tiled kernel only).  bbm_get_stat keys: "launches", "band_misses"
  * (banded alignments re-run by the row-sequential kernel). */
@@ -102,6 +123,21 @@ int  bbm_int_peak(bbm_ctx* ctx, int kind, double* gops_out);
 
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t bbm_launch_count(const bbm_ctx* ctx);
+
+/* ---- read ingest: Read.validate (current/stream/Read.java:81-215; switches :3406-3418) applied in place to a read batch, plus
+ * the minus-strand copy AminoAcid.reverseComplementBases (current/dna/AminoAcid.java:203-211) the mapper makes once per read
+ * (AbstractMapThread.java:492-503).  quality holds phred values with the ASCII offset removed, or NULL (FASTA input).
+ * flags mirror the reference's switches (all off = BBMap defaults).  basesM / read_flags may be NULL.  Device buffers must be
+ * 16-byte aligned and readable up to 16 bytes past read_off[nreads] (the kernel moves whole 16-byte vectors). */
+#define BBM_ING_FIX_JUNK         1   /* Read.FIX_JUNK (fixjunk): non-IUPAC bytes become 'N' instead of flagging the read */
+#define BBM_ING_U_TO_T           2   /* Read.U_TO_T */
+#define BBM_ING_TO_UPPER_CASE    4   /* Read.TO_UPPER_CASE (touppercase) */
+#define BBM_ING_LOWER_CASE_TO_N  8   /* Read.LOWER_CASE_TO_N (lowercaseton) */
+#define BBM_READ_JUNK            1   /* read_flags bit: Read.junk() */
+int  bbm_ingest_batch_dev(bbm_ctx* ctx, int8_t* d_bases, int8_t* d_quality, const int64_t* d_read_off, int64_t nreads, int32_t max_len,
+                          int32_t flags, int8_t* d_basesM, int32_t* d_read_flags, void* stream, float* kernel_ms_out);
+int  bbm_ingest_batch_host(bbm_ctx* ctx, int8_t* bases, int8_t* quality, const int64_t* read_off, int64_t nreads, int32_t flags,
+                           int8_t* basesM, int32_t* read_flags);
 
 /* ---- k-mer index: IndexMaker4 (build) + BBIndex.analyzeIndex (current/align2/IndexMaker4.java:160-421, BBIndex.java:101-191) ---- */
 typedef struct {        /* 80 bytes: the BBIndex statics as they stand after BBMap.loadIndex + analyzeIndex for this genome */

@@ -17,6 +17,7 @@
  * (offsets strictly ascending and in range, BBIndex.checkOffsets :200-205) — not by Java outputs.
  */
 #pragma GCC optimize ("fp-contract=off")
+#include <ctype.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -231,5 +232,61 @@ void orc_noindel_batch(const int8_t* reads, const int8_t* refs, const orc_noinde
         const orc_noindel_task* T = &tasks[i];
         int8_t* m = ((T->flags & 1) && match_buf) ? match_buf + match_off[i] : 0;
         scores[i] = orc_score_no_indels(reads + T->read_off, T->read_len, refs + T->ref_off, T->ref_len, T->ref_start, m);
+    }
+}
+
+/* ---------------- Read.validate + AminoAcid.reverseComplementBases ----------------
+ * current/stream/Read.java:81-215 with the switches of :3406-3418 passed as `flags` (1 FIX_JUNK, 2 U_TO_T, 4 TO_UPPER_CASE,
+ * 8 LOWER_CASE_TO_N); nucleotide reads only.  Tables: current/dna/AminoAcid.java:110-133, 586-595, 615-647.
+ * Returns 1 if the read was flagged junk. */
+static int8_t g_b2nExt[128], g_compExt[128], g_ing_init = 0;
+static void ingest_init(void) {
+    static const char* ext = " ACMGRSVTWYHKDBNX"; static const char* cext = " TGKCYWBASRDMHVNX";
+    memset(g_b2nExt, -1, 128); memset(g_compExt, -1, 128);
+    for (int i = 0; ext[i]; i++) {
+        const int x = ext[i], x2 = cext[i];
+        if (x != ' ') { g_b2nExt[x] = (int8_t)i; g_b2nExt[tolower(x)] = (int8_t)i; }
+        g_compExt[x] = (int8_t)x2; g_compExt[tolower(x)] = (int8_t)tolower(x2);
+    }
+    g_b2nExt['U'] = 8; g_b2nExt['u'] = 8;
+    g_compExt['U'] = 'A'; g_compExt['u'] = 'a'; g_compExt['?'] = '?'; g_compExt[' '] = ' '; g_compExt['-'] = '-'; g_compExt['*'] = '*'; g_compExt['.'] = '.';
+    g_ing_init = 1;
+}
+static int fully_defined(int8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'U' || b == 'a' || b == 'c' || b == 'g' || b == 't' || b == 'u'; }
+
+int orc_ingest_read(int8_t* bases, int8_t* quality, int len, int flags, int8_t* basesM) {
+    if (!g_ing_init) ingest_init();
+    const int fixJunk = flags & 1, uToT = flags & 2, toUpper = flags & 4, lowerToN = flags & 8;
+    int junk = 0;
+    if (uToT) for (int i = 0; i < len; i++) { if (bases[i] == 'U') bases[i] = 'T'; else if (bases[i] == 'u') bases[i] = 't'; }
+    for (int i = 0; i < len; i++) {
+        const int8_t b = bases[i];
+        const int num = b < 0 ? -1 : g_b2nExt[(int)b];      /* Java would throw on a negative index; treated as junk */
+        if (num < 0) { if (fixJunk) bases[i] = 'N'; else { junk = 1; break; } }
+    }
+    if (quality) {
+        for (int i = 0; i < len; i++) {
+            const int8_t b = bases[i], q = quality[i];
+            if (fully_defined(b)) { if (q < 2) quality[i] = 2; else if (q > 41) quality[i] = 41; }
+            else { quality[i] = 0; if (b == '-' || b == '.' || b == 'X' || b == 'n') bases[i] = 'N'; }
+            if (toUpper && b > 90) bases[i] -= 32;
+            else if (lowerToN && b > 90) bases[i] = 'N';
+        }
+    } else if (toUpper) {
+        for (int i = 0; i < len; i++) { const int8_t b = bases[i]; if (b > 90) bases[i] -= 32; if (b == '-' || b == '.' || b == 'X') bases[i] = 'N'; }
+    } else if (lowerToN) {
+        for (int i = 0; i < len; i++) { const int8_t b = bases[i]; if (b > 90) bases[i] = 'N'; else if (b == '-' || b == '.' || b == 'X') bases[i] = 'N'; }
+    } else {
+        for (int i = 0; i < len; i++) { const int8_t b = bases[i]; if (b == '-' || b == '.' || b == 'X') bases[i] = 'N'; }
+    }
+    if (basesM) for (int i = 0; i < len; i++) { const int8_t b = bases[len - 1 - i]; basesM[i] = b < 0 ? -1 : g_compExt[(int)b]; }
+    return junk;
+}
+
+void orc_ingest_batch(int8_t* bases, int8_t* quality, const int64_t* read_off, int64_t nreads, int flags, int8_t* basesM, int32_t* readFlags) {
+    for (int64_t r = 0; r < nreads; r++) {
+        const int64_t o = read_off[r]; const int len = (int)(read_off[r + 1] - o);
+        const int j = orc_ingest_read(bases + o, quality ? quality + o : 0, len, flags, basesM ? basesM + o : 0);
+        if (readFlags) readFlags[r] = j;
     }
 }

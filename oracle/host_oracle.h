@@ -14,4 +14,6 @@ typedef struct { int64_t read_off, ref_off; int32_t read_len, ref_len, ref_start
 int orc_score_no_indels(const int8_t* read, int len, const int8_t* ref, int refLen, int refStart, int8_t* match);
 void orc_noindel_batch(const int8_t* reads, const int8_t* refs, const orc_noindel_task* tasks, int32_t* scores, int8_t* match_buf,
                        const int64_t* match_off, int64_t n);
+int orc_ingest_read(int8_t* bases, int8_t* quality, int len, int flags, int8_t* basesM);
+void orc_ingest_batch(int8_t* bases, int8_t* quality, const int64_t* read_off, int64_t nreads, int flags, int8_t* basesM, int32_t* readFlags);
 #endif

@@ -179,6 +179,32 @@ class Oracle:
                            C.c_int(1 if quit_after_two_perfects else 0), _p(res))
         return res
 
+    # ---------------- gapped alignment (makeGref) ----------------
+    def fill_and_score_limited_gapped(self, read, ref, refStart, refEnd, minScore, gaps, traceback=True, maxRows=601, maxColumns=3000):
+        """MSA.fillAndScoreLimited(read, ref, refStart, refEnd, minScore, gaps) then msa.traceback(…, gapped) as
+        BBMapThread.scoreSlow does (BBMapThread.java:306-356).  Returns (score8 list or None, match bytes or None, max4)."""
+        L = self.lib
+        L.orc_msa_new.restype = C.c_void_p
+        m = C.c_void_p(L.orc_msa_new(C.c_int32(maxRows), C.c_int32(maxColumns)))
+        try:
+            read = np.ascontiguousarray(read).view(np.int8); ref = np.ascontiguousarray(ref).view(np.int8)
+            g = None if gaps is None or len(gaps) == 0 else np.ascontiguousarray(gaps, np.int32).copy()
+            max4 = np.zeros(4, np.int32); out8 = np.zeros(8, np.int32)
+            n = L.orc_msa_fillAndScoreLimited(m, _p(read), C.c_int32(len(read)), _p(ref), C.c_int32(len(ref)), C.c_int32(refStart), C.c_int32(refEnd),
+                                              C.c_int32(minScore), None if g is None else _p(g), C.c_int32(0 if g is None else len(g)), _p(max4), _p(out8))
+            if n <= 0:
+                return None, None, max4
+            match = None
+            if traceback:
+                a, b = max(0, refStart), min(len(ref) - 1, refEnd)
+                buf = np.zeros(len(read) + 3002 + 128 * 64, np.int8)
+                k = L.orc_msa_traceback(m, _p(read), _p(ref), C.c_int32(a), C.c_int32(b), C.c_int32(int(max4[0])), C.c_int32(int(max4[1])),
+                                        C.c_int32(int(max4[2])), C.c_int(0 if g is None else 1), _p(buf), C.c_int32(len(buf)))
+                match = buf[:k].copy()
+            return out8[:n].tolist(), match, max4
+        finally:
+            L.orc_msa_free(m)
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
@@ -189,6 +215,17 @@ class Oracle:
         self.lib.orc_noindel_batch(_p(reads), _p(refs), _p(tasks), _p(scores), _p(mbuf) if match_off is not None else None,
                                    _p(np.ascontiguousarray(match_off, np.int64)) if match_off is not None else None, C.c_int64(len(tasks)))
         return scores, mbuf
+
+    # ---------------- read ingest (Read.validate + reverse complement) ----------------
+    def ingest_batch(self, bases, quality, read_off, flags=0):
+        """Returns (bases, quality, basesM, read_flags) after Read.validate / reverseComplementBases; inputs are not modified."""
+        b = np.ascontiguousarray(bases).view(np.int8).copy()
+        q = None if quality is None else np.ascontiguousarray(quality).view(np.int8).copy()
+        ro = np.ascontiguousarray(read_off, np.int64); n = len(ro) - 1
+        bm = np.zeros(len(b), np.int8); fl = np.zeros(n, np.int32)
+        self.lib.orc_ingest_batch.restype = None
+        self.lib.orc_ingest_batch(_p(b), None if q is None else _p(q), _p(ro), C.c_int64(n), C.c_int(flags), _p(bm), _p(fl))
+        return b, q, bm, fl
 
     # ---------------- KeyRing seeding ----------------
     def seed_batch(self, bases, quality, read_off, cfg, maxKeys=96):

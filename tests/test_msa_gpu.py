@@ -170,3 +170,68 @@ def test_score_no_indels(oracle, msa):
     r2 = np.stack([reads[tasks["read_off"][i]: tasks["read_off"][i] + L] for i in sel])
     g2 = np.stack([genome[tasks["ref_start"][i] + 4: tasks["ref_start"][i] + 4 + L] for i in sel])
     assert np.array_equal(wl.score_no_indels_batch(r2, g2), exp[sel])
+
+
+def _spliced_case(rng, genome, L):
+    """A read made of 2-3 exons separated by introns of 300-2500 bp, and the SiteScore-style gap array for it."""
+    nex = int(rng.integers(2, 4))
+    cuts = np.sort(rng.choice(np.arange(25, L - 25), size=nex - 1, replace=False))
+    lens = np.diff(np.concatenate([[0], cuts, [L]]))
+    pos = int(rng.integers(9000, len(genome) - 12000))
+    exons, gaps, p = [], [], pos
+    for i, ln in enumerate(lens):
+        exons.append(genome[p:p + ln].copy()); gaps += [p, p + ln - 1]
+        p += ln + int(rng.integers(300, 2500))
+    read = np.concatenate(exons)
+    for q in rng.integers(0, L, size=int(rng.integers(0, 3))):
+        read[q] = wl.ACGT[rng.integers(0, 4)]
+    return read, np.array(gaps, np.int32)
+
+
+def test_gapped_reference_parity(oracle):
+    """a15: makeGref + fill on the gapped reference + translateFromGappedCoordinate + traceback with '-' expansion, against the
+    restatement (oracle/msa_oracle.c make_gref/from_gapped, MultiStateAligner11tsJNI.java:668-801), mixed with ungapped tasks."""
+    from bbmap_b200.msa import MultiStateAligner11tsCUDA
+    rng = np.random.Generator(np.random.PCG64(21))
+    genome = wl.random_genome(60000, seed=8)
+    reads, gt, gaps_all, cases = [], [], [], []
+    off = 0
+    for i in range(160):
+        L = int(rng.choice([100, 150, 250]))
+        if i % 4 == 3:      # ungapped task in the same batch
+            p = int(rng.integers(9000, 40000)); read = genome[p:p + L].copy(); g = np.zeros(0, np.int32); lo, hi = p, p + L - 1
+        else:
+            read, g = _spliced_case(rng, genome, L); lo, hi = int(g[0]), int(g[-1])
+        pad = int(rng.integers(0, 12))
+        ms = int(0.3 * wl.max_quality(L)) if i % 5 else 0
+        t = np.zeros(1, wl.GAPPED_TASK_DTYPE)
+        t["t"]["read_off"] = off; t["t"]["ref_off"] = 0; t["t"]["read_len"] = L; t["t"]["ref_len"] = len(genome)
+        t["t"]["ref_start"] = lo - pad; t["t"]["ref_end"] = hi + pad; t["t"]["min_score"] = ms
+        t["t"]["flags"] = wl.TF_CLAMP | wl.TF_SCORE | wl.TF_TRACEBACK
+        t["gaps_off"] = len(gaps_all); t["ngaps"] = len(g)
+        gaps_all += g.tolist(); gt.append(t); reads.append(read); off += L
+        cases.append((read, lo - pad, hi + pad, ms, g))
+    gt = np.concatenate(gt); reads = np.concatenate(reads)
+    cap = gt["t"]["read_len"].astype(np.int64) + 3002 + 128 * 30
+    moff = np.zeros(len(gt) + 1, np.int64); np.cumsum(cap, out=moff[1:])
+    msa = MultiStateAligner11tsCUDA(device=0)
+    try:
+        d_ref = msa.load_reference(genome)
+        outs, mbuf = msa.align_batch_gapped(reads, d_ref, gt, np.array(gaps_all, np.int32), moff)
+    finally:
+        msa.close()
+    ngapped_ok = 0
+    for i, (read, a, b, ms, g) in enumerate(cases):
+        sc, match, max4 = oracle.fill_and_score_limited_gapped(read, genome, a, b, ms, g)
+        o = outs[i]
+        assert o["status"] == 0, (i, o)
+        if sc is None:
+            assert o["score_len"] == 0 and o["result"][4] == 1, (i, o)
+            continue
+        assert o["score_len"] == len(sc) and o["score"][:len(sc)].tolist() == sc, (i, o["score"], sc)
+        assert o["result"][:4].tolist() == max4.tolist()
+        assert o["match_len"] == len(match) and mbuf[moff[i]:moff[i] + len(match)].tobytes() == match.tobytes(), i
+        if len(g):
+            ngapped_ok += 1
+            assert (match == ord("D")).sum() >= 128          # an intron went through '-' symbols
+    assert ngapped_ok >= 100
