@@ -15,10 +15,17 @@ using namespace bbm;
 
 #define DECL_W(W) extern "C" int bbm_launch_msa_tiled_w##W(const MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
 DECL_W(4) DECL_W(5) DECL_W(6) DECL_W(8) DECL_W(9) DECL_W(12) DECL_W(16)
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, cudaStream_t stream);
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, cudaStream_t stream);
+extern "C" int bbm_msa_class_strip();
+extern "C" int bbm_msa_strip_max_cols();
+extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols);
+extern "C" size_t bbm_msa_strip_fixed_bytes(int chunkCount, int maxRows, int blocks);
+extern "C" int bbm_launch_msa_strip(const MsaParams* P, const int* list, const unsigned int* endPtr, unsigned int base, int chunkStart, int chunkCount,
+                                    int maxRows, void* scratch, size_t scratchBytes, unsigned int* counter, unsigned long long* poolCursor,
+                                    int blocks, int debug, cudaStream_t st);
 extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream);
 extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n, unsigned int* cb, unsigned long long* tb, long long tbWordsPerWarp,
-                                     int* lists, int blocks, cudaStream_t stream);
+                                     int* lists, int blocks, int useStrip, cudaStream_t stream);
 extern "C" int bbm_msa_narrow_threads();
 extern "C" int bbm_msa_narrow_buckets();
 extern "C" int bbm_launch_banded(const int8_t* q, const int8_t* r, const bbm_band_task* t, bbm_band_out* o, long long n,
@@ -103,7 +110,10 @@ struct bbm_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1;
+    int use_narrow = 1, use_strip = 1, strip_debug = 0;
+    size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
+    DevBuf stripScratch;
+    long long strip_tasks = 0;
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
     DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2, seedScratch, d_seed[8];
     bool seed_tables = false;
@@ -147,6 +157,10 @@ extern "C" int bbm_init(int device, bbm_ctx** out) {
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     if (c->counters.ensure(256 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
+    {   // strip-kernel scratch budget: a third of what is free now, at most 32 GB (B200: 180 GB of HBM3e)
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && freeB / 3 < c->strip_budget) c->strip_budget = freeB / 3;
+    }
     *out = c;
     return BBM_OK;
 }
@@ -157,7 +171,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -209,6 +223,8 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const int narrowBlocks = c->sms * 4;
     const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
     const int useNarrow = (c->use_narrow && d_dump == nullptr) ? 1 : 0;
+    const int useStrip = (c->use_strip && d_dump == nullptr) ? 1 : 0;
+    const int CS = bbm_msa_class_strip();
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
     if (useNarrow && c->nscratch.ensure((size_t)narrowWarps * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc narrow traceback scratch");
     if (c->overflow.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc overflow list");
@@ -226,18 +242,26 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     P.dump = d_dump;
     CK(cudaMemsetAsync(c->counters.p, 0, 192 * 4, st));
     CK(cudaEventRecord(c->ev0, st));
-    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cb, useNarrow, st);
+    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cb, useNarrow, useStrip, st);
     if (e) return fail(BBM_E_CUDA, "msa_classify_kernel launch", (cudaError_t)e);
     c->launches++;
     unsigned int h[192];
     CK(cudaMemcpyAsync(h, cb, 192 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     unsigned int base[16]; unsigned int acc = 0;
-    for (int k = 0; k < 16; ++k) { base[k] = acc; if (k <= nw) acc += h[k]; }
+    for (int k = 0; k < 16; ++k) { base[k] = acc; if (k <= nw || k == CS) acc += h[k]; }
     unsigned int nbase[64]; unsigned int nacc = 0;
     for (int k = 0; k < 64; ++k) { nbase[k] = nacc; if (k < nb) nacc += h[64 + k]; }
-    CK(cudaMemcpyAsync(cb + 16, base, 16 * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cb + 128, nbase, 64 * 4, cudaMemcpyHostToDevice, st));
+    unsigned int curs[16]; memcpy(curs, base, sizeof(curs));
+    unsigned int sbBase[16];
+    {   // strip list: direct tasks ordered by estimated work (largest bucket first), narrow-kernel hand-overs appended after them
+        unsigned int cur = base[CS];
+        for (int b = 15; b >= 0; --b) { sbBase[b] = cur; cur += h[104 + b]; }
+        curs[CS] = cur;
+    }
+    CK(cudaMemcpyAsync(cb + 16, curs, 16 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cb + 168, sbBase, 16 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cb + 128, nbase, (size_t)nb * 4, cudaMemcpyHostToDevice, st));       // narrow bucket cursors only: 168.. are the strip buckets
     e = bbm_launch_msa_scatter(&P, (const unsigned char*)c->cls.p, cb, (int*)c->lists.p, (int*)c->nlist.p, st);
     if (e) return fail(BBM_E_CUDA, "msa_scatter_kernel launch", (cudaError_t)e);
     c->launches++;
@@ -245,7 +269,7 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
         int blocks = narrowBlocks;
         const long long need = ((long long)nacc + bbm_msa_narrow_threads() - 1) / bbm_msa_narrow_threads();
         if (need < blocks) blocks = (int)need;
-        e = bbm_launch_msa_narrow(&P, (const int*)c->nlist.p, (int)nacc, cb, (unsigned long long*)c->nscratch.p, words, (int*)c->lists.p, blocks, st);
+        e = bbm_launch_msa_narrow(&P, (const int*)c->nlist.p, (int)nacc, cb, (unsigned long long*)c->nscratch.p, words, (int*)c->lists.p, blocks, useStrip, st);
         if (e) return fail(BBM_E_CUDA, "msa_narrow_kernel launch", (cudaError_t)e);
         c->launches++;
     }
@@ -260,6 +284,40 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
         e = fns[k](&P, (const int*)c->lists.p + base[k], 0, cb + 16 + k, base[k], cb + 32 + k, blocks, d_dump != nullptr, st);
         if (e) return fail(BBM_E_CUDA, "msa_tiled_kernel launch", (cudaError_t)e);
         c->launches++;
+    }
+    if (useStrip && h[CS]) {
+        // limited, un-banded fills (narrow-kernel hand-overs included): thread-per-alignment strip kernel.  Scratch = fixed part + one
+        // block per alignment sized from its own rows/columns; the classifier summed those sizes (an upper bound: it includes the
+        // alignments the narrow kernel has finished meanwhile).  If that does not fit the budget the list is processed in chunks.
+        unsigned int cur = 0;
+        CK(cudaMemcpyAsync(&cur, cb + 16 + CS, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const long long nstrip = (long long)cur - base[CS];
+        const int sRows = max_rows < MAXR ? max_rows : MAXR;
+        const int sCols = max_cols < bbm_msa_strip_max_cols() ? max_cols : bbm_msa_strip_max_cols();
+        unsigned long long totalBytes = 0; memcpy(&totalBytes, &h[184], 8);
+        const unsigned long long perMax = bbm_msa_strip_task_bytes(sRows, sCols);
+        if (totalBytes > (unsigned long long)nstrip * perMax) totalBytes = (unsigned long long)nstrip * perMax;
+        const int blocksMax = c->sms * 4;
+        long long chunk = nstrip;
+        if (totalBytes > c->strip_budget) { chunk = (long long)(c->strip_budget / perMax); if (chunk < 1024) chunk = 1024; if (chunk > nstrip) chunk = nstrip; }
+        const unsigned long long poolBytes = (chunk == nstrip) ? totalBytes : (unsigned long long)chunk * perMax;
+        for (long long start = 0; start < nstrip; start += chunk) {
+            const int cnt = (int)((nstrip - start) < chunk ? (nstrip - start) : chunk);
+            // the list is ordered longest-first: the first wave takes the expensive alignments, the cheap ones fill in behind them
+            long long blocks = ((long long)cnt + 127) / 128;
+            if (blocks > blocksMax) blocks = blocksMax;
+            if (blocks < 1) blocks = 1;
+            const size_t need = bbm_msa_strip_fixed_bytes(cnt, sRows, (int)blocks) + (size_t)poolBytes + 256;
+            if (c->stripScratch.ensure(need)) return fail(BBM_E_CUDA, "cudaMalloc strip scratch");
+            CK(cudaMemsetAsync(cb + 50, 0, 4, st));
+            CK(cudaMemsetAsync(cb + 186, 0, 8, st));
+            e = bbm_launch_msa_strip(&P, (const int*)c->lists.p + base[CS], cb + 16 + CS, base[CS], (int)start, cnt, sRows, c->stripScratch.p, c->stripScratch.cap,
+                                     cb + 50, (unsigned long long*)(cb + 186), (int)blocks, c->strip_debug, st);
+            if (e) return fail(BBM_E_CUDA, "msa_strip kernels launch", (cudaError_t)e);
+            c->launches += 3;
+        }
+        c->strip_tasks += nstrip;
     }
     const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
     long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
@@ -294,8 +352,10 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     {   // bookkeeping: how many alignments the narrow kernel tried / handed over to the tiled kernels
         long long tiledTotal = 0;
         for (int k = 0; k < nw; ++k) tiledTotal += (long long)hend[k] - base[k];
+        if (useStrip) tiledTotal += (long long)hend[CS] - base[CS];
         long long direct = 0;
         for (int k = 0; k < nw; ++k) direct += h[k];
+        if (useStrip) direct += h[CS];
         direct -= nacc;                                   // tasks that went straight to a tiled list
         c->narrow_tried += nacc;
         c->narrow_handed_over += tiledTotal - direct;
@@ -307,6 +367,9 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
 extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(BBM_E_ARG, "bbm_set_option: null");
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
+    if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
+    if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }
+    if (!strcmp(key, "strip_budget_mb")) { c->strip_budget = (size_t)value << 20; return BBM_OK; }
     return fail(BBM_E_ARG, "bbm_set_option: unknown key");
 }
 extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
@@ -316,6 +379,7 @@ extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
     if (!strcmp(key, "narrow_tried")) return c->narrow_tried;
     if (!strcmp(key, "narrow_handed_over")) return c->narrow_handed_over;
     if (!strcmp(key, "tasks_total")) return c->tasks_total;
+    if (!strcmp(key, "strip_tasks")) return c->strip_tasks;
     return -1;
 }
 

@@ -7,9 +7,13 @@
 namespace bbm {
 
 // pass 1: class of every task + per-class counts; pass 2: scatter ids into per-class lists
-__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* cb, int useNarrow) {
+__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip) {
     __shared__ unsigned int local[NUM_CLASS];
     __shared__ unsigned int localNb[NARROW_BUCKETS];
+    __shared__ unsigned int localSb[STRIP_BUCKETS];
+    __shared__ unsigned long long localBytes;
+    if (threadIdx.x < STRIP_BUCKETS) localSb[threadIdx.x] = 0;
+    if (threadIdx.x == 0) localBytes = 0;
     if (threadIdx.x < NUM_CLASS) local[threadIdx.x] = 0;
     if (threadIdx.x < NARROW_BUCKETS) localNb[threadIdx.x] = 0;
     __syncthreads();
@@ -19,15 +23,19 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
         const bbm_msa_task task = P.tasks[i];
         int k = CLASS_BAD;
         if (resolve_task(task, P.bandwidth, P.ratio, T)) {
-            k = classify(T);
+            k = (useStrip && strip_eligible(T)) ? CLASS_STRIP : classify(T);
             atomicAdd(&local[k], 1u);
+            if (k == CLASS_STRIP) atomicAdd(&localBytes, strip_task_bytes(T.rows, T.cols));
             if (useNarrow && narrow_eligible(T)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
+            else if (k == CLASS_STRIP) atomicAdd(&localSb[strip_bucket(T)], 1u);
         } else { bbm_msa_out o = {}; o.status = BBM_E_ARG; o.match_len = -1; P.outs[i] = o; }
         cls[i] = (unsigned char)k;
     }
     __syncthreads();
     if (threadIdx.x < NUM_CLASS && local[threadIdx.x]) atomicAdd(&cb[CB_COUNTS + threadIdx.x], local[threadIdx.x]);
     if (threadIdx.x < NARROW_BUCKETS && localNb[threadIdx.x]) atomicAdd(&cb[CB_NB_COUNTS + threadIdx.x], localNb[threadIdx.x]);
+    if (threadIdx.x < STRIP_BUCKETS && localSb[threadIdx.x]) atomicAdd(&cb[CB_SB_COUNTS + threadIdx.x], localSb[threadIdx.x]);
+    if (threadIdx.x == 0 && localBytes) atomicAdd(reinterpret_cast<unsigned long long*>(cb + CB_STRIP_BYTES), localBytes);
 }
 
 __global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist) {
@@ -39,7 +47,14 @@ __global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsign
         nlist[pos] = (int)i;
         return;
     }
-    if (k >= CLASS_BAD) return;
+    if (k == CLASS_BAD) return;
+    if (k == CLASS_STRIP) {
+        TaskCtx T;
+        resolve_task(P.tasks[i], P.bandwidth, P.ratio, T);
+        const unsigned pos = atomicAdd(&cb[CB_SB_CURSORS + strip_bucket(T)], 1u);
+        lists[pos] = (int)i;
+        return;
+    }
     const unsigned pos = atomicAdd(&cb[CB_CURSORS + k], 1u);
     lists[pos] = (int)i;
 }
@@ -58,9 +73,9 @@ __global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int*
 
 using namespace bbm;
 
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, cudaStream_t stream) {
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, cudaStream_t stream) {
     const int threads = 256;
-    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, useNarrow);
+    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, useNarrow, useStrip);
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream) {
@@ -69,8 +84,8 @@ extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* c
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n, unsigned int* cb, unsigned long long* tb, long long tbWordsPerWarp,
-                                     int* lists, int blocks, cudaStream_t stream) {
-    msa_narrow_kernel<<<blocks, NARROW_THREADS, 0, stream>>>(*P, nlist, n, cb + CB_NARROW_WORK, tb, tbWordsPerWarp, cb + CB_CURSORS, lists);
+                                     int* lists, int blocks, int useStrip, cudaStream_t stream) {
+    msa_narrow_kernel<<<blocks, NARROW_THREADS, 0, stream>>>(*P, nlist, n, cb + CB_NARROW_WORK, tb, tbWordsPerWarp, cb + CB_CURSORS, lists, useStrip);
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_msa_narrow_threads() { return NARROW_THREADS; }
@@ -82,5 +97,6 @@ extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int n
 }
 extern "C" int bbm_msa_warps_per_block() { return WARPS_PER_BLOCK; }
 extern "C" int bbm_msa_num_wclass() { return NUM_WCLASS; }
+extern "C" int bbm_msa_class_strip() { return CLASS_STRIP; }
 extern "C" int bbm_msa_wclass_width(int k) { return wclass_width(k); }
 extern "C" long long bbm_generic_scratch_ints(int rows, int cols) { return msa_generic_scratch_ints(rows, cols); }

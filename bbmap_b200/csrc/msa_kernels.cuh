@@ -40,11 +40,15 @@ constexpr int NUM_WCLASS = 7;
 __host__ __device__ constexpr int wclass_width(int k) { return k == 0 ? 4 : k == 1 ? 5 : k == 2 ? 6 : k == 3 ? 8 : k == 4 ? 9 : k == 5 ? 12 : 16; }
 constexpr int CLASS_GENERIC = NUM_WCLASS;      // row-sequential kernel
 constexpr int CLASS_BAD = NUM_WCLASS + 1;      // invalid task
-constexpr int NUM_CLASS = NUM_WCLASS + 2;
+constexpr int CLASS_STRIP = NUM_WCLASS + 2;    // limited, un-banded fills: thread-per-alignment strip kernel (msa_strip.cu)
+constexpr int NUM_CLASS = NUM_WCLASS + 3;
+constexpr int STRIP_MAX_COLS = 512;            // CellTables cover DEL/INS runs up to this (msa_cell.cuh)
 constexpr int CLS_NARROW_BIT = 0x80;           // class byte flag: first try the thread-per-alignment narrow kernel
 // counter block (32-bit words)
 constexpr int CB_COUNTS = 0, CB_CURSORS = 16, CB_WORK = 32, CB_OVERFLOW = 48, CB_NARROW_WORK = 49;
 constexpr int CB_NB_COUNTS = 64, CB_NB_CURSORS = 128, CB_WORDS = 192;
+constexpr int STRIP_BUCKETS = 16;              // strip list is ordered by estimated work, largest first (longest-processing-time-first)
+constexpr int CB_SB_COUNTS = 104, CB_SB_CURSORS = 168, CB_STRIP_BYTES = 184 /* 64-bit */, CB_STRIP_WORK = 50, CB_STRIP_POOL = 186 /* 64-bit */;
 constexpr int NARROW_BUCKETS = 40;             // narrow list is ordered by read length (rows-1)/16 so warps are uniform
 __host__ __device__ constexpr int narrow_bucket(int rows) { return (rows - 1) / 16 < NARROW_BUCKETS - 1 ? (rows - 1) / 16 : NARROW_BUCKETS - 1; }
 
@@ -52,6 +56,25 @@ __device__ __forceinline__ int classify(const TaskCtx& T) {
     const int w = (T.cols + 31) >> 5;
     if (T.rows > MAXR - 2 || w > 16) return CLASS_GENERIC;
     return w <= 4 ? 0 : w == 5 ? 1 : w == 6 ? 2 : w <= 8 ? 3 : w == 9 ? 4 : w <= 12 ? 5 : 6;
+}
+
+__device__ __forceinline__ bool strip_eligible(const TaskCtx& T) {
+    return T.limited && T.halfband < 1 && T.rows >= 2 && T.rows <= MAXR - 2 && T.cols <= STRIP_MAX_COLS;
+}
+
+constexpr int SW = 8;                           // columns per strip (msa_strip.cu)
+// estimated work of a limited fill: rows x (width of the band a path may wander given the slack between the best possible score
+// and minScore); only used to order the strip list
+__device__ __forceinline__ int strip_bucket(const TaskCtx& T) {
+    const int maxQ = (T.rows - 1) * 100 + 70;
+    const int slack = imax(0, maxQ - T.minScore);
+    const long long w = (long long)T.rows * imin(T.cols, slack / 32 + 16);
+    const int lg = 63 - __clzll(w | 1);
+    return imin(STRIP_BUCKETS - 1, imax(0, lg - 9));
+}
+__host__ __device__ inline unsigned long long strip_task_bytes(int rows, int cols) {
+    const unsigned long long ns = (unsigned long long)(cols + SW - 1) / SW, rs = (unsigned long long)rows + 2;
+    return ((8 * rs + 4 * SW * ns + 4 * ns * rs) + 15ull) & ~15ull;
 }
 
 constexpr int WARPS_PER_BLOCK = 4;

@@ -35,7 +35,7 @@ __device__ __forceinline__ bool narrow_eligible(const TaskCtx& T) {
 __device__ __forceinline__ int map_ref(int v) { return v == 'N' ? 0x100 : v; }
 
 __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list, int first, int nlist,
-                                const NarrowShared& sh, unsigned long long* tbWarp, unsigned int* classCursors, int* classLists) {
+                                const NarrowShared& sh, unsigned long long* tbWarp, unsigned int* classCursors, int* classLists, int useStrip) {
     const int lane = threadIdx.x & 31;
     const int k = first + lane;
     bool alive = k < nlist;
@@ -244,7 +244,7 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
     }
     if (bail) {
         // hand over to the register-tiled kernel of the right width
-        const int kcls = classify(T);
+        const int kcls = (useStrip && strip_eligible(T)) ? CLASS_STRIP : classify(T);
         const unsigned pos = atomicAdd(&classCursors[kcls], 1u);
         classLists[pos] = id;
         return;
@@ -318,7 +318,7 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
 
 __global__ void __launch_bounds__(NARROW_THREADS, 4) msa_narrow_kernel(MsaParams P, const int* __restrict__ list, int nlist, unsigned int* counter,
                                                                      unsigned long long* tbAll, long long tbWordsPerWarp,
-                                                                     unsigned int* classCursors, int* classLists) {
+                                                                     unsigned int* classCursors, int* classLists, int useStrip) {
     __shared__ NarrowShared sh;
     cell_tables_init(sh);
     __syncthreads();
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 4) msa_narrow_kernel(MsaParams
         if (lane == 0) first = atomicAdd(counter, 32u);
         first = __shfl_sync(FULL, first, 0);
         if (first >= (unsigned)nlist) break;
-        msa_narrow_warp(P, list, (int)first, nlist, sh, tbWarp, classCursors, classLists);
+        msa_narrow_warp(P, list, (int)first, nlist, sh, tbWarp, classCursors, classLists, useStrip);
         __syncwarp();
     }
 }

@@ -250,3 +250,51 @@ def make_read_batch(n, seed=9, lengths=(100, 150, 250), flat_q=None, n_rate=0.00
     qual = np.where(nmask, 0, qual).astype(np.uint8)
     # a few reads that are mostly N / shorter than k
     return bases, qual, off
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# G2 / G3: paired 2x150 reads drawn from a packed reference — insert size uniform 200-500, each base substituted
+# with probability `sub_rate`, and with probability `indel_rate*L` one 1-3 bp insertion or deletion per read; Q=30 flat
+# (Shared.FAKE_QUAL).  Mate 2 is the reverse complement of the far end of the fragment (Illumina FR).  Vectorised numpy.
+def make_mapping_reads(chrom_bytes, chrom_off, table, npairs, L=150, seed=2, sub_rate=0.01, indel_rate=0.01 / 3, insert=(200, 500), qual=30):
+    """chrom_bytes/chrom_off/table as returned by bbmap_b200.index.pack_chromosomes.  Returns dict(bases, qual, off, truth) where
+    reads 2i and 2i+1 are the mates of pair i and truth[r] = (chrom, strand, start, stop) in chromosome coordinates."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tab = np.asarray(table, np.int64)                       # (chrom 1-based, start, length)
+    w = tab[:, 2].astype(np.float64); w /= w.sum()
+    sc = rng.choice(len(tab), size=npairs, p=w)
+    ins = rng.integers(insert[0], insert[1] + 1, size=npairs)
+    ins = np.minimum(ins, tab[sc, 2] - 8)
+    fstart = tab[sc, 1] + (rng.random(npairs) * (tab[sc, 2] - ins - 4)).astype(np.int64)     # fragment start in the chromosome
+    fstrand = rng.integers(0, 2, size=npairs)
+    n = 2 * npairs
+    # genomic start of each read's footprint on the plus strand
+    start = np.empty(n, np.int64); strand = np.empty(n, np.int64); chrom = np.repeat(tab[sc, 0], 2)
+    left, right = fstart, fstart + ins - L
+    start[0::2] = np.where(fstrand == 0, left, right); strand[0::2] = fstrand
+    start[1::2] = np.where(fstrand == 0, right, left); strand[1::2] = 1 - fstrand
+    return _reads_from_footprints(chrom_bytes, chrom, start, strand, L, rng, sub_rate, indel_rate, qual, chrom_off)
+
+
+def _reads_from_footprints(chrom_bytes, chrom, start, strand, L, rng, sub_rate, indel_rate, qual, chrom_off=None):
+    n = len(start)
+    j = np.arange(L, dtype=np.int64)[None, :]
+    has_indel = rng.random(n) < indel_rate * L
+    is_del = rng.random(n) < 0.5
+    d = rng.integers(1, 4, size=n)
+    q = rng.integers(20, L - 20, size=n)
+    shift = np.where((has_indel & is_del)[:, None] & (j >= q[:, None]), d[:, None], 0)
+    shift = shift - np.where((has_indel & ~is_del)[:, None] & (j >= (q + d)[:, None]), d[:, None], 0)
+    idx = start[:, None] + j + shift
+    base0 = np.zeros(n, np.int64) if chrom_off is None else np.asarray(chrom_off, np.int64)[chrom - 1]
+    reads = chrom_bytes[np.minimum(idx + base0[:, None], len(chrom_bytes) - 1)]
+    insmask = (has_indel & ~is_del)[:, None] & (j >= q[:, None]) & (j < (q + d)[:, None])
+    reads = np.where(insmask, ACGT[rng.integers(0, 4, size=(n, L), dtype=np.uint8)], reads)
+    sub = rng.random((n, L)) < sub_rate
+    reads = np.where(sub, ACGT[(np.searchsorted(ACGT, np.minimum(reads, ord("T"))) + rng.integers(1, 4, size=(n, L))) % 4], reads).astype(np.uint8)
+    span = L + np.where(has_indel, np.where(is_del, d, -d), 0)
+    minus = strand == 1
+    reads[minus] = revcomp(reads[minus].reshape(-1)).reshape(-1, L)[::-1]
+    truth = np.stack([chrom, strand, start, start + span - 1], axis=1).astype(np.int32)
+    off = np.arange(n + 1, dtype=np.int64) * L
+    return {"bases": reads.reshape(-1), "qual": np.full(n * L, qual, np.uint8), "off": off, "truth": truth}

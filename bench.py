@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lengths", default="100,150,250")
     ap.add_argument("--no-narrow", action="store_true", help="disable the thread-per-alignment narrow kernel (A/B)")
+    ap.add_argument("--no-strip", action="store_true", help="route limited fills through the register-tiled kernel instead of the strip kernel (A/B)")
+    ap.add_argument("--strip-budget-mb", type=int, default=0)
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage timings (ingest/seed/index/search/scoreNoIndels) of bench/stages.py")
+    ap.add_argument("--stage-pairs", type=int, default=200_000)
     return ap.parse_args()
 
 
@@ -172,6 +176,10 @@ def main():
     msa = MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio)
     if args.no_narrow:
         msa.set_option("narrow", 0)
+    if args.no_strip:
+        msa.set_option("strip", 0)
+    if args.strip_budget_mb:
+        msa.set_option("strip_budget_mb", args.strip_budget_mb)
     dev = torch.device("cuda", local)
     # resident inputs (torch owns the device memory; the C ABI takes raw pointers)
     d_genome = torch.from_numpy(np.concatenate([genome, np.full(256, ord("N"), np.uint8)])).to(dev)
@@ -258,12 +266,18 @@ def main():
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
             "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
-                           "narrow_handed_over": msa.stat("narrow_handed_over"), "band_misses": msa.stat("band_misses")},
+                           "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "band_misses": msa.stat("band_misses")},
             "clocks": clocks,
             "int_peaks_glops": int_peaks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
                          "traffic": None, "peak_kind": pk_kind,
                          "note": "integer-issue-bound DP: algorithmic bytes/cell ~0.1; see DESIGN.md for the issue-slot roofline"}}
+    if not args.no_stages:
+        # the other kernels of the path on configs[1]-shaped input, each against the HBM roofline
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        import stages
+        msa.close()
+        line["stages"] = stages.run(pairs=args.stage_pairs, device=local, hbm_peak=pk["hbm_gbs"])
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_run(reads, genome, tasks, moff, args.bandwidth, args.ratio)
     print(json.dumps(line))

@@ -1,0 +1,131 @@
+"""Per-stage device timings of the mapping core on BASELINE configs[1]-shaped input: E. coli-sized random
+reference, 2x150 bp pairs with ~1% substitutions and 1-3 bp indels, Q=30.  Every stage runs through the C ABI with inputs
+resident in HBM; times are the library's own CUDA-event measurements on its stream (kernel_ms_out).
+
+    python bench/stages.py [--pairs 200000] [--genome 4600000] [--reps 5] [--stage all|ingest|seed|index|search|noindel|banded]
+
+Prints one JSON object; bench.py embeds it as `stages`."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bbmap_b200 import lib as _lib, workloads as wl  # noqa: E402
+from bbmap_b200.index import BBIndexCUDA, pack_chromosomes  # noqa: E402
+from bbmap_b200.keyring import default_cfg  # noqa: E402
+from bbmap_b200.search import HEAD_DTYPE, SITE_DTYPE  # noqa: E402
+
+MAXK = 32          # slots per read for offsets/keys/keyScores (18 keys at 150 bp)
+MAX_SITES = 16
+
+
+def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False):
+    import torch
+    L = _lib.load()
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(device)
+    genome = wl.random_genome(genome_len, seed=1)
+    cb, co, table = pack_chromosomes([genome])
+    R = wl.make_mapping_reads(cb, co, table, pairs, seed=2)
+    n = 2 * pairs
+    nb = len(R["bases"])
+    out = {"workload": "configs[1]-shaped: %d bp random reference (1 scaffold), %d pairs 2x150, 1%% subs, 1-3 bp indel in ~50%% of reads, Q30" % (genome_len, pairs),
+           "reads": n}
+    t0 = time.perf_counter()
+    idx = BBIndexCUDA(cb, co, keylen=13, device=device)
+    torch.cuda.synchronize()
+    out["index_build"] = {"ms": 1e3 * (time.perf_counter() - t0), "sites": int(idx.download(0)[1].size), "note": "wall clock incl. upload of the reference; emit + radix sort + scan + analyzeIndex"}
+    h = idx.h
+    pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
+    d_bases = pad(R["bases"]); d_qual = pad(R["qual"]); d_off = torch.from_numpy(R["off"]).to(dev)
+    d_basesM = torch.zeros(nb + 64, dtype=torch.uint8, device=dev); d_flags = torch.zeros(n, dtype=torch.int32, device=dev)
+    ms = C.c_float(0)
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def timed(fn):
+        best = []
+        for _ in range(reps):
+            fn(); best.append(ms.value)
+        return float(np.median(best))
+
+    # ---- a0 ingest ----
+    t = timed(lambda: _lib.check(L.bbm_ingest_batch_dev(h, p(d_bases), p(d_qual), p(d_off), n, 150, 0, p(d_basesM), p(d_flags), None, C.byref(ms)), "ingest"))
+    alg = 5 * nb + 8 * n + 4 * n
+    out["ingest"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
+                     "bytes_per_read": alg / n}
+    # ---- a1-a4 seed ----
+    cfg = default_cfg()
+    d_nkeys = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_offsets = torch.zeros(n * MAXK, dtype=torch.int32, device=dev); d_keys = torch.zeros_like(d_offsets); d_ks = torch.zeros_like(d_offsets)
+    d_offM = torch.zeros_like(d_offsets); d_keysM = torch.zeros_like(d_offsets)
+    d_bs = torch.zeros(nb + 64, dtype=torch.int8, device=dev)
+    t = timed(lambda: _lib.check(L.bbm_seed_batch_dev(h, p(d_bases), p(d_qual), p(d_off), n, 150, cfg.ctypes.data_as(C.c_void_p), MAXK, p(d_nkeys), p(d_offsets),
+                                                     p(d_keys), p(d_ks), p(d_bs), p(d_offM), p(d_keysM), None, C.byref(ms)), "seed"))
+    nk = d_nkeys.cpu().numpy()
+    alg = 2 * nb + nb + int(np.maximum(nk, 0).sum()) * 4 * 5 + 12 * n
+    out["seed"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
+                   "bytes_per_read": alg / n, "mean_keys": float(nk.mean())}
+    # ---- a6-a9 search ----
+    d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_sites = torch.zeros(n * MAX_SITES * SITE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    t = timed(lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 1 if quit2 else 0,
+                                                       p(d_heads), p(d_sites), MAX_SITES, None, C.byref(ms)), "search"))
+    heads = np.frombuffer(d_heads.cpu().numpy().tobytes(), HEAD_DTYPE)
+    sites = np.frombuffer(d_sites.cpu().numpy().tobytes(), SITE_DTYPE).reshape(n, MAX_SITES)
+    # position-level truth: the top-scoring site is the read's origin
+    ns = heads["nsites"]; tr = R["truth"]
+    sc = np.where(np.arange(MAX_SITES)[None, :] < ns[:, None], sites["score"], -10 ** 9)
+    bi = sc.argmax(axis=1); best = sites[np.arange(n), bi]
+    correct = (ns > 0) & (best["chrom"] == tr[:, 0]) & (best["strand"] == tr[:, 1]) & ((np.abs(best["start"] - tr[:, 2]) <= 8) | (np.abs(best["stop"] - tr[:, 3]) <= 8))
+    # algorithmic bytes: COUNTS gathers 4/key + per strand (starts pair 8 + list 4*len) for prescan and walk + ~2*(L+k) reference bytes per extended key
+    counts = idx.download(0)[2]
+    keys = d_keys.cpu().numpy().reshape(n, MAXK)
+    valid = np.arange(MAXK)[None, :] < np.maximum(nk, 0)[:, None]
+    listlen = np.where(valid & (keys >= 0), counts[np.maximum(keys, 0)], 0).astype(np.int64)
+    alg = int(valid.sum()) * 4 + 2 * (int(valid.sum()) * 2 * 8 + int(listlen.sum()) * 4) + int(valid.sum()) * (150 + 13) + n * (300 + 48) + int(ns.sum()) * 64
+    out["search"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
+                     "bytes_per_read": alg / n, "mean_sites": float(ns.mean()), "reads_with_site": float((ns > 0).mean()), "top_site_is_origin": float(correct.mean()),
+                     "status_nonzero": int((heads["status"] != 0).sum())}
+    # ---- a10 scoreNoIndels over every emitted site ----
+    rid, sj = np.nonzero(np.arange(MAX_SITES)[None, :] < ns[:, None])
+    S = sites[rid, sj]
+    tasks = np.zeros(len(S), wl.NOINDEL_TASK_DTYPE)
+    tasks["read_off"] = R["off"][rid]; tasks["ref_off"] = co[S["chrom"] - 1]; tasks["read_len"] = 150
+    tasks["ref_len"] = (co[S["chrom"]] - co[S["chrom"] - 1]); tasks["ref_start"] = S["start"]
+    plus = S["strand"] == 0
+    d_tasks = torch.from_numpy(tasks.view(np.uint8)).to(dev); d_scores = torch.zeros(len(S), dtype=torch.int32, device=dev)
+    d_chroms = C.c_void_p(idx.d_chroms.value)
+    # minus-strand sites score the reverse complement: run the two strands against the matching read buffer
+    ids = np.nonzero(plus)[0]
+    tp = np.ascontiguousarray(tasks[ids]); d_tp = torch.from_numpy(tp.view(np.uint8)).to(dev)
+    t1 = timed(lambda: _lib.check(L.bbm_noindel_batch_dev(h, p(d_bases), d_chroms, p(d_tp), p(d_scores), None, None, len(tp), None, C.byref(ms)), "noindel"))
+    idm = np.nonzero(~plus)[0]
+    tm = np.ascontiguousarray(tasks[idm]); d_tm = torch.from_numpy(tm.view(np.uint8)).to(dev)
+    t2 = timed(lambda: _lib.check(L.bbm_noindel_batch_dev(h, p(d_basesM), d_chroms, p(d_tm), p(d_scores), None, None, len(tm), None, C.byref(ms)), "noindel"))
+    t = t1 + t2
+    alg = len(S) * (32 + 4 + 300)
+    out["noindel"] = {"ms": t, "sites_per_s": len(S) / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak}
+    idx.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=200_000)
+    ap.add_argument("--genome", type=int, default=4_600_000)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
+    print(json.dumps(run(a.pairs, a.genome, a.reps, hbm_peak=hbm)))
+
+
+if __name__ == "__main__":
+    main()
