@@ -110,7 +110,7 @@ struct bbm_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1, use_strip = 1, strip_debug = 0;
+    int use_narrow = 1, use_strip = 16, strip_debug = 0;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0;
@@ -223,7 +223,8 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const int narrowBlocks = c->sms * 4;
     const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
     const int useNarrow = (c->use_narrow && d_dump == nullptr) ? 1 : 0;
-    const int useStrip = (c->use_strip && d_dump == nullptr) ? 1 : 0;
+    // 0 = off; n>0: limited un-banded fills whose work estimate falls in buckets < n go to the strip kernel, larger ones to the tiled kernel
+    const int useStrip = (c->use_strip && d_dump == nullptr) ? c->use_strip : 0;
     const int CS = bbm_msa_class_strip();
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
     if (useNarrow && c->nscratch.ensure((size_t)narrowWarps * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc narrow traceback scratch");

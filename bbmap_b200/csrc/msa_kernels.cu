@@ -23,7 +23,7 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
         const bbm_msa_task task = P.tasks[i];
         int k = CLASS_BAD;
         if (resolve_task(task, P.bandwidth, P.ratio, T)) {
-            k = (useStrip && strip_eligible(T)) ? CLASS_STRIP : classify(T);
+            k = (useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T);
             atomicAdd(&local[k], 1u);
             if (k == CLASS_STRIP) atomicAdd(&localBytes, strip_task_bytes(T.rows, T.cols));
             if (useNarrow && narrow_eligible(T)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }

@@ -69,8 +69,7 @@ __device__ __forceinline__ int strip_bucket(const TaskCtx& T) {
     const int maxQ = (T.rows - 1) * 100 + 70;
     const int slack = imax(0, maxQ - T.minScore);
     const long long w = (long long)T.rows * imin(T.cols, slack / 32 + 16);
-    const int lg = 63 - __clzll(w | 1);
-    return imin(STRIP_BUCKETS - 1, imax(0, lg - 9));
+    return (int)(w >> 12) < STRIP_BUCKETS - 1 ? (int)(w >> 12) : STRIP_BUCKETS - 1;      // buckets of 4096 cells
 }
 __host__ __device__ inline unsigned long long strip_task_bytes(int rows, int cols) {
     const unsigned long long ns = (unsigned long long)(cols + SW - 1) / SW, rs = (unsigned long long)rows + 2;

@@ -244,7 +244,7 @@ __device__ void msa_narrow_warp(const MsaParams& P, const int* __restrict__ list
     }
     if (bail) {
         // hand over to the register-tiled kernel of the right width
-        const int kcls = (useStrip && strip_eligible(T)) ? CLASS_STRIP : classify(T);
+        const int kcls = (useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T);
         const unsigned pos = atomicAdd(&classCursors[kcls], 1u);
         classLists[pos] = id;
         return;

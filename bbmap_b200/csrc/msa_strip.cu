@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
     unsigned gPrev = 0;
     int dM = 0, dD = 0, dI = 0;               // left neighbour column at row r-1
     int lM = 0, lD = 0, lI = 0, vlim = 0;     // left neighbour column at row r; vertLimit[r]
+    int mmRow = MM_NONE, call1 = 0, call0 = 0; // (minGood,maxGood) of row r so far; read[r-1], read[r-2]
     int loP = 1, hiP = 0, loC = INT_MAX, hiC = -1;
     int bestScore = INT_MIN, bestCol = -1, bestState = -1, bestPacked = 0;
 
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
             if (s == 0) { const int v = tab.insc[r]; lM = v; lD = v; lI = v; }           // column 0 (…JNI.java:105-111)
             else if (r >= loP && r <= hiP) { const int4 q = rec[r]; lM = q.x; lD = q.y; lI = q.z; }
             else { lM = K.subfloor; lD = K.subfloor; lI = K.subfloor; }
-            vlim = A[r].x;
+            { const int2 a = A[r]; vlim = a.x; mmRow = a.y; }
+            call1 = read[r - 1]; call0 = r < 2 ? '?' : read[r - 2];        // issued with the loads above: one memory round trip per row
             const int Lmin = imax(imax(vlim, hlMin) - P_MATCH2, K.floor_);
             const int prevTop = (r == 1) ? 0 : (gPrev ? INT_MAX : K.subfloor);
             const int bmax = imax(imax3(dM & SMASK, dD & SMASK, dI & SMASK), imax(lM & SMASK, lD & SMASK));
@@ -217,8 +219,8 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
         // ---- phase B: one row of W cells (convergent) ----
         {
             CellRow R;
-            R.call1 = read[r - 1];
-            R.call0 = r < 2 ? '?' : read[r - 2];
+            R.call1 = call1;
+            R.call0 = call0;
             R.callN = (R.call1 == 'N');
             R.vlimit = vlim;
             R.delBar = (r < 3) || (r > rows - 3);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
             }
             tbT[(long long)s * rs + r] = word;
             if (gCur) {
-                const int old = A[r].y;
+                const int old = mmRow;
                 const int first = c0 + __ffs(gCur) - 1, lastc = c0 + 31 - __clz(gCur);
                 const int mn = (old == MM_NONE) ? first : (old >> 16);
                 A[r].y = (mn << 16) | lastc;

@@ -66,10 +66,22 @@ def score_no_indels_batch(reads2d, refs2d):
     return score
 
 
-def make_msa_tasks(genome, n, seed=2, lengths=(100, 150, 250), ratio=0.56, flags=TF_SCORE | TF_TRACEBACK,
-                   frac_indel=0.2, frac_unrelated=0.1, sub_rate=0.01, n_rate=0.0005, pad=SLOW_ALIGN_PADDING,
-                   max_indel=40, tight=True):
-    """G4: returns (reads uint8[], tasks TASK_DTYPE[n]).  ref_off=0, ref_len=len(genome) for every task."""
+def make_msa_tasks(genome, n, seed=2, block=100_000, **kw):
+    """G4: returns (reads uint8[], tasks TASK_DTYPE[n]).  ref_off=0, ref_len=len(genome) for every task.  Generated in blocks of
+    `block` tasks seeded (seed, block index), so the first k blocks of a large batch equal a smaller batch with the same seed."""
+    if n <= block:
+        return _make_msa_tasks_block(genome, n, seed, **kw)
+    reads, tasks, off = [], [], 0
+    for b in range((n + block - 1) // block):
+        r, t = _make_msa_tasks_block(genome, min(block, n - b * block), seed if b == 0 else [seed, b], **kw)
+        t["read_off"] += off; off += len(r)
+        reads.append(r); tasks.append(t)
+    return np.concatenate(reads), np.concatenate(tasks)
+
+
+def _make_msa_tasks_block(genome, n, seed=2, lengths=(100, 150, 250), ratio=0.56, flags=TF_SCORE | TF_TRACEBACK,
+                          frac_indel=0.2, frac_unrelated=0.1, sub_rate=0.01, n_rate=0.0005, pad=SLOW_ALIGN_PADDING,
+                          max_indel=40, tight=True):
     rng = np.random.Generator(np.random.PCG64(seed))
     G = len(genome)
     tasks = np.zeros(n, TASK_DTYPE)

@@ -9,12 +9,12 @@ from kat import KATS, REF, MINSCORE, B, rle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["strip", "tiled"])
+@pytest.fixture(scope="module", params=["strip", "tiled", "mixed"])
 def msa(request):
     """Both routings of limited un-banded fills: the thread-per-alignment strip kernel (default) and the register-tiled kernel."""
     from bbmap_b200.msa import MultiStateAligner11tsCUDA
     m = MultiStateAligner11tsCUDA()
-    m.set_option("strip", 1 if request.param == "strip" else 0)
+    m.set_option("strip", {"strip": 16, "tiled": 0, "mixed": 3}[request.param])
     yield m
     m.close()
 
