@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 #include <mutex>
 #include <cmath>
 #include <algorithm>
@@ -55,8 +56,8 @@ extern "C" int bbm_launch_gref_translate(const bbm_gapped_task* gt, long long n,
 extern "C" int bbm_ingest_threads();
 extern "C" int bbm_launch_ingest(int8_t* bases, int8_t* quality, const long long* read_off, long long nreads, int8_t* basesM, int* readFlags,
                                  int flags, int readsPerBlock, int stageBytes, int blocks, cudaStream_t st);
-extern "C" size_t bbm_search_ctx_bytes();
 extern "C" int bbm_search_threads();
+extern "C" size_t bbm_search_ctx_bytes();
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
@@ -113,7 +114,7 @@ struct bbm_ctx {
     int use_narrow = 1, use_strip = 16, strip_debug = 0;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
-    long long strip_tasks = 0;
+    long long strip_tasks = 0, index_build_us = 0;
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
     DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2, seedScratch, d_seed[8];
     bool seed_tables = false;
@@ -381,6 +382,7 @@ extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
     if (!strcmp(key, "narrow_handed_over")) return c->narrow_handed_over;
     if (!strcmp(key, "tasks_total")) return c->tasks_total;
     if (!strcmp(key, "strip_tasks")) return c->strip_tasks;
+    if (!strcmp(key, "index_build_us")) return c->index_build_us;        // host wall time of the last bbm_index_build (reference already resident)
     return -1;
 }
 
@@ -841,6 +843,7 @@ extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     index_free(c);
+    const auto t_build0 = std::chrono::steady_clock::now();
     const int k = keylen;
     const long long keyspace = 1LL << (2 * k);
     long long maxLen = 0, total = chrom_off[nchroms] - chrom_off[0];
@@ -940,6 +943,8 @@ extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t
         for (int i = 0; i <= nchroms; ++i) rel[i] = chrom_off[i];
         CK(cudaMalloc(&c->d_chrom_off, rel.size() * 8)); CK(cudaMemcpy(c->d_chrom_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice));
     }
+    CK(cudaStreamSynchronize(st));
+    c->index_build_us = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_build0).count();
     c->has_index = true;
     if (cfg_out) *cfg_out = c->icfg;
     if (nblocks_out) *nblocks_out = (int)c->iblocks.size();
@@ -1025,7 +1030,7 @@ extern "C" int bbm_ingest_batch_host(bbm_ctx* c, int8_t* bases, int8_t* quality,
 
 // =====================  index search (BBIndex.find)  =====================
 static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int64_t* doff, int64_t nreads, const int* dn, const int* dof,
-                      const int* dks, int maxKeys, int quit2, bbm_search_head* dh, bbm_site* ds, int maxSites, cudaStream_t st, float* ms_out) {
+                      const int* dks, int maxKeys, int quit2, bbm_search_head* dh, bbm_site* ds, int maxSites, int maxReadLen, cudaStream_t st, float* ms_out) {
     if (!c->has_index) return fail(BBM_E_ARG, "bbm_search: no index in this context (call bbm_index_build first)");
     if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
     if ((int)c->iblocks.size() > 64) return fail(BBM_E_SHAPE, "bbm_search: more than 64 index blocks");
@@ -1033,6 +1038,7 @@ static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int
     int blocks = c->sms * 8;
     const long long need = (nreads + T - 1) / T;
     if (need < blocks) blocks = (int)need;
+    (void)maxReadLen;     // reserved: lets a later kernel size its per-read working set to the batch
     if (c->searchCtx.ensure((size_t)c->sms * 8 * T * bbm_search_ctx_bytes()) || c->searchRev.ensure((size_t)c->sms * 8 * T * 2 * 608))
         return fail(BBM_E_CUDA, "cudaMalloc search scratch");
     unsigned int* cb = (unsigned int*)c->counters.p;
@@ -1051,13 +1057,13 @@ static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int
 
 extern "C" int bbm_search_batch_dev(bbm_ctx* c, const int8_t* d_bases, const int8_t* d_baseScores, const int64_t* d_read_off, int64_t nreads,
                                     const int32_t* d_nkeys, const int32_t* d_offsets, const int32_t* d_keyScores, int32_t maxKeys,
-                                    int32_t quit2, bbm_search_head* d_heads, bbm_site* d_sites, int32_t max_sites, void* stream, float* kernel_ms_out) {
+                                    int32_t quit2, bbm_search_head* d_heads, bbm_site* d_sites, int32_t max_sites, int32_t max_read_len, void* stream, float* kernel_ms_out) {
     if (!c || !d_bases || !d_baseScores || !d_read_off || !d_nkeys || !d_offsets || !d_keyScores || !d_heads || !d_sites || max_sites < 1 || maxKeys < 1 || maxKeys > 96)
         return fail(BBM_E_ARG, "bbm_search_batch_dev: bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     return run_search(c, d_bases, d_baseScores, d_read_off, nreads, d_nkeys, d_offsets, d_keyScores, maxKeys, quit2, d_heads, d_sites, max_sites,
-                      stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+                      max_read_len, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
 }
 
 extern "C" int bbm_search_batch_host(bbm_ctx* c, const int8_t* bases, const int8_t* baseScores, const int64_t* read_off, int64_t nreads,
@@ -1070,6 +1076,8 @@ extern "C" int bbm_search_batch_host(bbm_ctx* c, const int8_t* bases, const int8
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const size_t nb = (size_t)read_off[nreads], kb = (size_t)nreads * maxKeys * 4;
+    int max_len = 1;
+    for (int64_t i = 0; i < nreads; ++i) { const int64_t l = read_off[i + 1] - read_off[i]; if (l > max_len) max_len = (int)(l > 100000 ? 100000 : l); }
     const size_t hb = (size_t)nreads * sizeof(bbm_search_head), sb = (size_t)nreads * max_sites * sizeof(bbm_site);
     DevBuf* B = c->d_srch;   // 0 bases, 1 baseScores, 2 off, 3 nkeys, 4 offsets, 5 keyScores, 6 heads, 7 sites
     if (B[0].ensure(nb + 32) || B[1].ensure(nb + 32) || B[2].ensure((size_t)(nreads + 1) * 8) || B[3].ensure((size_t)nreads * 4) || B[4].ensure(kb) ||
@@ -1083,7 +1091,7 @@ extern "C" int bbm_search_batch_host(bbm_ctx* c, const int8_t* bases, const int8
     CK(cudaMemcpyAsync(B[5].p, keyScores, kb, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(B[7].p, 0, sb, st));
     int rc = run_search(c, (const int8_t*)B[0].p, (const int8_t*)B[1].p, (const int64_t*)B[2].p, nreads, (const int*)B[3].p, (const int*)B[4].p,
-                        (const int*)B[5].p, maxKeys, quit2, (bbm_search_head*)B[6].p, (bbm_site*)B[7].p, max_sites, st, nullptr);
+                        (const int*)B[5].p, maxKeys, quit2, (bbm_search_head*)B[6].p, (bbm_site*)B[7].p, max_sites, max_len, st, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(heads, B[6].p, hb, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(sites, B[7].p, sb, cudaMemcpyDeviceToHost, st));

@@ -106,9 +106,36 @@ __global__ void index_max_kernel(const int* __restrict__ COUNTS, long long n, in
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
-__global__ void index_lenhist_kernel(const int* __restrict__ COUNTS, long long n, int* __restrict__ lenCounts) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i < n; i += (long long)gridDim.x * blockDim.x) { const int a = COUNTS[i]; if (a >= 0) atomicAdd(&lenCounts[a], 1); }
+// counts[a]++ over COUNTS (Tools.makeLengthHistogram3, current/align2/Tools.java:1797-1815).  Nearly every k-mer of a genome-sized
+// index occurs 0-3 times, so those four bins are counted in registers and everything below 1024 in shared memory; only the rare long
+// lists touch global atomics (a plain global atomicAdd per element serialises on four addresses: 38 ms for k=13).
+__global__ void __launch_bounds__(256) index_lenhist_kernel(const int* __restrict__ COUNTS, long long n, int* __restrict__ lenCounts) {
+    __shared__ int sh[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        int v[4];
+        if (i + 3 < n) { const int4 q = *reinterpret_cast<const int4*>(COUNTS + i); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else { for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? COUNTS[i + j] : -1; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = v[j];
+            if (a < 0) continue;
+            if (a == 0) ++c0; else if (a == 1) ++c1; else if (a == 2) ++c2; else if (a == 3) ++c3;
+            else if (a < 1024) atomicAdd(&sh[a], 1);
+            else atomicAdd(&lenCounts[a], 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], c0); atomicAdd(&sh[1], c1); atomicAdd(&sh[2], c2); atomicAdd(&sh[3], c3); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) if (sh[i]) atomicAdd(&lenCounts[i], sh[i]);
 }
 
 }  // namespace bbm
@@ -145,6 +172,6 @@ extern "C" int bbm_index_finish_counts(int k, int* COUNTS, const unsigned long l
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_index_lenhist(int k, const int* COUNTS, int* lenCounts, cudaStream_t st) {
-    index_lenhist_kernel<<<1024, 256, 0, st>>>(COUNTS, 1LL << (2 * k), lenCounts);
+    index_lenhist_kernel<<<1184, 256, 0, st>>>(COUNTS, 1LL << (2 * k), lenCounts);
     return (int)cudaGetLastError();
 }

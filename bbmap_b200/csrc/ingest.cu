@@ -55,7 +55,8 @@ struct IngestParams {
 __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(IngestParams P) {
     extern __shared__ __align__(16) int8_t smem[];
     int8_t* sB = smem; int8_t* sQ = sB + P.stageBytes; int8_t* sM = sQ + P.stageBytes;
-    __shared__ int sJunkAt[64];                       // first junk position per read of this block (Read.validate stops there)
+    __shared__ int sOff[66];                          // byte offsets (relative to the staging window) of this block's reads
+    __shared__ int sJunk[64];                         // Read.junk() per read of this block
     const int tid = threadIdx.x;
     const bool fixJunk = P.flags & BBM_ING_FIX_JUNK, uToT = P.flags & BBM_ING_U_TO_T, toUpper = P.flags & BBM_ING_TO_UPPER_CASE,
                lowerToN = P.flags & BBM_ING_LOWER_CASE_TO_N;
@@ -67,49 +68,48 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(IngestParams P) 
         const int span = (int)(byte1 - a0), lead = (int)(byte0 - a0);
         const int nvec = (span + 15) >> 4;
         __syncthreads();
+        if (tid <= nr) sOff[tid] = (int)(P.read_off[first + tid] - a0);
+        if (tid < nr) sJunk[tid] = 0;
         for (int v = tid; v < nvec; v += INGEST_THREADS) {
             reinterpret_cast<int4*>(sB)[v] = reinterpret_cast<const int4*>(P.bases + a0)[v];
             if (P.quality) reinterpret_cast<int4*>(sQ)[v] = reinterpret_cast<const int4*>(P.quality + a0)[v];
         }
-        if (tid < nr) sJunkAt[tid] = 0x7fffffff;
         __syncthreads();
-        // pass 1 (Read.java:113-146): U->T, then junk detection / repair
-        for (int r = 0; r < nr; ++r) {
-            const int o = (int)(P.read_off[first + r] - a0), len = (int)(P.read_off[first + r + 1] - a0) - o;
-            for (int i = tid; i < len; i += INGEST_THREADS) {
-                int b = sB[o + i];
-                if (uToT && (b == 'U' || b == 'u')) { b = (b == 'U' ? 'T' : 't'); sB[o + i] = (int8_t)b; }
-                if (!iupac_known(b)) { if (fixJunk) sB[o + i] = 'N'; else atomicMin(&sJunkAt[r], i); }
-            }
-        }
-        __syncthreads();
-        // pass 2 (Read.java:156-214) + reverse complement
-        for (int r = 0; r < nr; ++r) {
-            const int o = (int)(P.read_off[first + r] - a0), len = (int)(P.read_off[first + r + 1] - a0) - o;
-            for (int i = tid; i < len; i += INGEST_THREADS) {
-                const int b = sB[o + i];
-                int nb = b;
+        // one thread per 16 staged bytes: find the read of its first byte once, then walk (Read.java:113-214 is elementwise apart
+        // from the junk flag of the read; the reverse complement is a permutation inside the read)
+        for (int v = tid; v < nvec; v += INGEST_THREADS) {
+            const int lo = imax(v << 4, lead), hi = imin((v << 4) + 16, span);
+            if (lo >= hi) continue;
+            int a = 0, b = nr;                         // largest r with sOff[r] <= lo
+            while (b - a > 1) { const int m = (a + b) >> 1; if (sOff[m] <= lo) a = m; else b = m; }
+            int r = a;
+            for (int p = lo; p < hi; ++p) {
+                while (p >= sOff[r + 1]) ++r;          // empty reads are stepped over
+                int bch = sB[p];
+                if (uToT && (bch == 'U' || bch == 'u')) bch = (bch == 'U' ? 'T' : 't');
+                if (!iupac_known(bch)) { if (fixJunk) bch = 'N'; else sJunk[r] = 1; }
+                int nb = bch;
                 if (P.quality) {
-                    int q = sQ[o + i];
-                    if (base_defined(b)) { q = q < 2 ? 2 : (q > 41 ? 41 : q); }
-                    else { q = 0; if (b == '-' || b == '.' || b == 'X' || b == 'n') nb = 'N'; }
-                    if (toUpper && b > 90) nb -= 32;
-                    else if (lowerToN && b > 90) nb = 'N';
-                    sQ[o + i] = (int8_t)q;
+                    int q = sQ[p];
+                    if (base_defined(bch)) { q = q < 2 ? 2 : (q > 41 ? 41 : q); }
+                    else { q = 0; if (bch == '-' || bch == '.' || bch == 'X' || bch == 'n') nb = 'N'; }
+                    if (toUpper && bch > 90) nb -= 32;
+                    else if (lowerToN && bch > 90) nb = 'N';
+                    sQ[p] = (int8_t)q;
                 } else if (toUpper) {
-                    if (b > 90) nb -= 32;
-                    if (b == '-' || b == '.' || b == 'X') nb = 'N';
+                    if (bch > 90) nb -= 32;
+                    if (bch == '-' || bch == '.' || bch == 'X') nb = 'N';
                 } else if (lowerToN) {
-                    if (b > 90) nb = 'N'; else if (b == '-' || b == '.' || b == 'X') nb = 'N';
+                    if (bch > 90) nb = 'N'; else if (bch == '-' || bch == '.' || bch == 'X') nb = 'N';
                 } else {
-                    if (b == '-' || b == '.' || b == 'X') nb = 'N';
+                    if (bch == '-' || bch == '.' || bch == 'X') nb = 'N';
                 }
-                sB[o + i] = (int8_t)nb;
-                if (P.basesM) sM[o + len - 1 - i] = (int8_t)complement_extended(nb);
+                sB[p] = (int8_t)nb;
+                if (P.basesM) sM[sOff[r] + sOff[r + 1] - 1 - p] = (int8_t)complement_extended(nb);
             }
-            if (tid == 0 && P.readFlags) P.readFlags[first + r] = (sJunkAt[r] != 0x7fffffff) ? BBM_READ_JUNK : 0;
         }
         __syncthreads();
+        if (tid < nr && P.readFlags) P.readFlags[first + tid] = sJunk[tid] ? BBM_READ_JUNK : 0;
         // write back: whole 16-byte vectors inside the span, single bytes at the two ragged edges (they belong to other blocks)
         for (int v = tid; v < nvec; v += INGEST_THREADS) {
             const int lo = v << 4, hi = lo + 16;

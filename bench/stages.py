@@ -26,7 +26,30 @@ MAXK = 32          # slots per read for offsets/keys/keyScores (18 keys at 150 b
 MAX_SITES = 16
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False):
+def cpu_side(R, cb, co, n_cpu=20000):
+    """The same stages through the CPU oracle (C restatements, one host thread) on the first n_cpu reads — a reported baseline."""
+    from oracle import oracle as orc
+    o = orc.get()
+    m = min(n_cpu, len(R["off"]) - 1)
+    off = R["off"][:m + 1]; nb = int(off[-1])
+    bases = R["bases"][:nb]; qual = R["qual"][:nb]
+    out = {"reads": m, "cores": 1, "kind": "port"}
+    t0 = time.perf_counter(); o.ingest_batch(bases, qual, off, 0); out["ingest_reads_per_s"] = m / (time.perf_counter() - t0)
+    cfg = default_cfg()
+    t0 = time.perf_counter(); seeds = o.seed_batch(bases, qual, off, cfg, MAXK); out["seed_reads_per_s"] = m / (time.perf_counter() - t0)
+    t0 = time.perf_counter(); idx = o.index_build(cb, co, 13, -1); out["index_build_ms"] = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter(); res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=False)
+    out["search_reads_per_s"] = m / (time.perf_counter() - t0)
+    ns = res["nsites"]; rid, sj = np.nonzero(np.arange(res["sites"].shape[1])[None, :] < ns[:, None])
+    S = res["sites"][rid, sj]; S = S[S["strand"] == 0]; rid = rid[res["sites"][rid, sj]["strand"] == 0]
+    tasks = np.zeros(len(S), wl.NOINDEL_TASK_DTYPE)
+    tasks["read_off"] = off[rid]; tasks["ref_off"] = co[S["chrom"] - 1]; tasks["read_len"] = 150
+    tasks["ref_len"] = (co[S["chrom"]] - co[S["chrom"] - 1]); tasks["ref_start"] = S["start"]
+    t0 = time.perf_counter(); o.noindel_batch(bases, cb, tasks); out["noindel_sites_per_s"] = len(S) / (time.perf_counter() - t0)
+    return out
+
+
+def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False, cpu=True):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
@@ -41,7 +64,9 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     t0 = time.perf_counter()
     idx = BBIndexCUDA(cb, co, keylen=13, device=device)
     torch.cuda.synchronize()
-    out["index_build"] = {"ms": 1e3 * (time.perf_counter() - t0), "sites": int(idx.download(0)[1].size), "note": "wall clock incl. upload of the reference; emit + radix sort + scan + analyzeIndex"}
+    L.bbm_get_stat.restype = C.c_int64
+    out["index_build"] = {"ms": L.bbm_get_stat(idx.h, b"index_build_us") / 1e3, "ms_with_upload_and_context": 1e3 * (time.perf_counter() - t0), "sites": int(idx.download(0)[1].size),
+                          "note": "bbm_index_build with the reference resident: emit + radix sort + scan + analyzeIndex (COUNTS, clumpy keys, lengthHistogram), host-timed around a stream sync"}
     h = idx.h
     pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
     d_bases = pad(R["bases"]); d_qual = pad(R["qual"]); d_off = torch.from_numpy(R["off"]).to(dev)
@@ -76,7 +101,7 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_sites = torch.zeros(n * MAX_SITES * SITE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     t = timed(lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 1 if quit2 else 0,
-                                                       p(d_heads), p(d_sites), MAX_SITES, None, C.byref(ms)), "search"))
+                                                       p(d_heads), p(d_sites), MAX_SITES, 150, None, C.byref(ms)), "search"))
     heads = np.frombuffer(d_heads.cpu().numpy().tobytes(), HEAD_DTYPE)
     sites = np.frombuffer(d_sites.cpu().numpy().tobytes(), SITE_DTYPE).reshape(n, MAX_SITES)
     # position-level truth: the top-scoring site is the read's origin
@@ -113,6 +138,22 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     alg = len(S) * (32 + 4 + 300)
     out["noindel"] = {"ms": t, "sites_per_s": len(S) / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak}
     idx.close()
+    # ---- a16 BandedAligner on G6-shaped pairs ----
+    q, rf, bt = wl.make_banded_tasks(20_000, seed=6)
+    from bbmap_b200.banded import BAND_OUT_DTYPE
+    hb = C.c_void_p(); _lib.check(L.bbm_init(device, C.byref(hb)), "bbm_init")
+    d_q = pad(q); d_r = pad(rf); d_bt = torch.from_numpy(bt.view(np.uint8)).to(dev)
+    d_bo = torch.zeros(len(bt) * BAND_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    t = timed(lambda: _lib.check(L.bbm_banded_batch_dev(hb, p(d_q), p(d_r), p(d_bt), p(d_bo), len(bt), None, C.byref(ms)), "banded"))
+    bo = np.frombuffer(d_bo.cpu().numpy().tobytes(), BAND_OUT_DTYPE)
+    width = np.minimum(bt["max_width"], 2 * bt["max_edits"] + 1).astype(np.int64)
+    cells = int((np.minimum(bt["query_len"], bt["ref_len"]).astype(np.int64) * width).sum())
+    alg = int(bt["query_len"].sum() + bt["ref_len"].sum()) + len(bt) * (48 + 32)
+    out["banded"] = {"ms": t, "pairs_per_s": len(bt) / (t / 1e3), "band_cells_upper_bound_gcups": cells / (t / 1e3) / 1e9, "alg_bytes": alg,
+                     "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak, "mean_edits": float(bo["edits"].mean())}
+    L.bbm_destroy(hb)
+    if cpu:
+        out["cpu_baseline"] = cpu_side(R, cb, co)
     return out
 
 

@@ -179,7 +179,7 @@ typedef struct {            /* 48 bytes per read */
 int  bbm_search_batch_dev(bbm_ctx* ctx, const int8_t* d_bases, const int8_t* d_baseScores, const int64_t* d_read_off, int64_t nreads,
                           const int32_t* d_nkeys, const int32_t* d_offsets, const int32_t* d_keyScores, int32_t maxKeys,
                           int32_t quit_after_two_perfects, bbm_search_head* d_heads, bbm_site* d_sites, int32_t max_sites,
-                          void* stream, float* kernel_ms_out);
+                          int32_t max_read_len /* longest read of the batch, 0 = unknown */, void* stream, float* kernel_ms_out);
 int  bbm_search_batch_host(bbm_ctx* ctx, const int8_t* bases, const int8_t* baseScores, const int64_t* read_off, int64_t nreads,
                            const int32_t* nkeys, const int32_t* offsets, const int32_t* keyScores, int32_t maxKeys,
                            int32_t quit_after_two_perfects, bbm_search_head* heads, bbm_site* sites, int32_t max_sites);
