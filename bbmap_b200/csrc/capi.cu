@@ -23,7 +23,7 @@ extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols);
 extern "C" size_t bbm_msa_strip_fixed_bytes(int chunkCount, int maxRows, int blocks);
 extern "C" int bbm_launch_msa_strip(const MsaParams* P, const int* list, const unsigned int* endPtr, unsigned int base, int chunkStart, int chunkCount,
                                     int maxRows, void* scratch, size_t scratchBytes, unsigned int* counter, unsigned long long* poolCursor,
-                                    int blocks, int debug, cudaStream_t st);
+                                    int blocks, int debug, unsigned long long* stats, cudaStream_t st);
 extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream);
 extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n, unsigned int* cb, unsigned long long* tb, long long tbWordsPerWarp,
                                      int* lists, int blocks, int useStrip, cudaStream_t stream);
@@ -62,7 +62,7 @@ extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_block
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
                                  int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* ctxPool, int8_t* revPool,
-                                 unsigned int* counter, int blocks, cudaStream_t st);
+                                 unsigned int* counter, unsigned long long* prof, int blocks, int blocksPerSm, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -111,10 +111,12 @@ struct bbm_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1, use_strip = 16, strip_debug = 0;
+    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_bps = 8;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
+    unsigned long long strip_units = 0, strip_lane_iters = 0;
+    int search_prof = 0; unsigned long long search_cycles[5] = {0, 0, 0, 0, 0};
     long long band_misses = 0, narrow_tried = 0, narrow_handed_over = 0, tasks_total = 0;
     DevBuf d_reads, d_tasks, d_outs, d_match, d_moff, d_dump, d_refs2, seedScratch, d_seed[8];
     bool seed_tables = false;
@@ -223,7 +225,8 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const long long words = (long long)(tiledRows + 40) * 32;           // one 64-bit code word per (step,lane)
     const int narrowBlocks = c->sms * 4;
     const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
-    const int useNarrow = (c->use_narrow && d_dump == nullptr) ? 1 : 0;
+    // 0 = off, 1 = try every shape-eligible alignment, n>1 = only those with (best possible score - minScore) <= n points
+    const int useNarrow = (c->use_narrow && d_dump == nullptr) ? c->use_narrow : 0;
     // 0 = off; n>0: limited un-banded fills whose work estimate falls in buckets < n go to the strip kernel, larger ones to the tiled kernel
     const int useStrip = (c->use_strip && d_dump == nullptr) ? c->use_strip : 0;
     const int CS = bbm_msa_class_strip();
@@ -315,11 +318,12 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
             CK(cudaMemsetAsync(cb + 50, 0, 4, st));
             CK(cudaMemsetAsync(cb + 186, 0, 8, st));
             e = bbm_launch_msa_strip(&P, (const int*)c->lists.p + base[CS], cb + 16 + CS, base[CS], (int)start, cnt, sRows, c->stripScratch.p, c->stripScratch.cap,
-                                     cb + 50, (unsigned long long*)(cb + 186), (int)blocks, c->strip_debug, st);
+                                     cb + 50, (unsigned long long*)(cb + 186), (int)blocks, c->strip_debug, (unsigned long long*)(cb + 220), st);
             if (e) return fail(BBM_E_CUDA, "msa_strip kernels launch", (cudaError_t)e);
             c->launches += 3;
         }
         c->strip_tasks += nstrip;
+        if (c->strip_debug & 4) { unsigned long long z[2]; CK(cudaMemcpy(z, cb + 220, 16, cudaMemcpyDeviceToHost)); c->strip_units += z[0]; c->strip_lane_iters += z[1]; CK(cudaMemset(cb + 220, 0, 16)); }
     }
     const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
     long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
@@ -371,6 +375,8 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }
+    if (!strcmp(key, "search_profile")) { c->search_prof = value; return BBM_OK; }
+    if (!strcmp(key, "search_blocks_per_sm")) { c->search_bps = value >= 16 ? 16 : (value >= 12 ? 12 : 8); return BBM_OK; }
     if (!strcmp(key, "strip_budget_mb")) { c->strip_budget = (size_t)value << 20; return BBM_OK; }
     return fail(BBM_E_ARG, "bbm_set_option: unknown key");
 }
@@ -382,6 +388,9 @@ extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
     if (!strcmp(key, "narrow_handed_over")) return c->narrow_handed_over;
     if (!strcmp(key, "tasks_total")) return c->tasks_total;
     if (!strcmp(key, "strip_tasks")) return c->strip_tasks;
+    if (!strcmp(key, "strip_units")) return (int64_t)c->strip_units;            // rows of 8 cells evaluated (with strip_debug bit 2)
+    if (!strcmp(key, "strip_lane_iters")) return (int64_t)c->strip_lane_iters;  // lane-iterations of the evaluation phase: units/iters = lane utilisation
+    if (!strncmp(key, "search_cycles_", 14) && key[14] >= '0' && key[14] <= '4') return (int64_t)c->search_cycles[key[14] - '0'];   // thread-cycles: total, filter, prescan, walk, extend
     if (!strcmp(key, "index_build_us")) return c->index_build_us;        // host wall time of the last bbm_index_build (reference already resident)
     return -1;
 }
@@ -1035,23 +1044,26 @@ static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int
     if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
     if ((int)c->iblocks.size() > 64) return fail(BBM_E_SHAPE, "bbm_search: more than 64 index blocks");
     const int T = bbm_search_threads();
-    int blocks = c->sms * 8;
+    const int bps = c->search_bps;
+    int blocks = c->sms * bps;
     const long long need = (nreads + T - 1) / T;
     if (need < blocks) blocks = (int)need;
     (void)maxReadLen;     // reserved: lets a later kernel size its per-read working set to the batch
-    if (c->searchCtx.ensure((size_t)c->sms * 8 * T * bbm_search_ctx_bytes()) || c->searchRev.ensure((size_t)c->sms * 8 * T * 2 * 608))
+    if (c->searchCtx.ensure((size_t)c->sms * bps * T * bbm_search_ctx_bytes()) || c->searchRev.ensure((size_t)c->sms * bps * T * 2 * 608))
         return fail(BBM_E_CUDA, "cudaMalloc search scratch");
     unsigned int* cb = (unsigned int*)c->counters.p;
     CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+    if (c->search_prof) CK(cudaMemsetAsync(cb + 208, 0, 40, st));
     CK(cudaEventRecord(c->ev0, st));
     int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, (int)c->iblocks.size(), (int)c->chrom_off.size() - 1, c->d_counts, c->d_ihist,
                               c->d_chroms, c->d_chrom_off, db, dbs, (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites,
-                              c->searchCtx.p, (int8_t*)c->searchRev.p, cb + 202, blocks, st);
+                              c->searchCtx.p, (int8_t*)c->searchRev.p, cb + 202, c->search_prof ? (unsigned long long*)(cb + 208) : nullptr, blocks, bps, st);
     if (e) return fail(BBM_E_CUDA, "search_kernel launch", (cudaError_t)e);
     c->launches++;
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaStreamSynchronize(st));
     if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    if (c->search_prof) CK(cudaMemcpy(c->search_cycles, cb + 208, 40, cudaMemcpyDeviceToHost));
     return BBM_OK;
 }
 

@@ -26,7 +26,7 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
             k = (useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T);
             atomicAdd(&local[k], 1u);
             if (k == CLASS_STRIP) atomicAdd(&localBytes, strip_task_bytes(T.rows, T.cols));
-            if (useNarrow && narrow_eligible(T)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
+            if (useNarrow && narrow_eligible(T, useNarrow > 1 ? useNarrow : 0)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
             else if (k == CLASS_STRIP) atomicAdd(&localSb[strip_bucket(T)], 1u);
         } else { bbm_msa_out o = {}; o.status = BBM_E_ARG; o.match_len = -1; P.outs[i] = o; }
         cls[i] = (unsigned char)k;

@@ -26,9 +26,12 @@ constexpr int NARROW_THREADS = 128;
 
 typedef CellTables NarrowShared;
 
-__device__ __forceinline__ bool narrow_eligible(const TaskCtx& T) {
+// maxSlack: alignments whose minScore leaves more than this many points below the best possible score almost always wander out
+// of the 16-diagonal window (an indel read scored against a ratio-based limit): they skip the attempt (0 = try everything)
+__device__ __forceinline__ bool narrow_eligible(const TaskCtx& T, int maxSlack) {
     const int D = T.cols - T.rows;
-    return T.limited && T.halfband < 1 && D >= NDLO + 1 && D <= NDLO + NDW - 2 && T.rows <= MAXR - 2 && T.rows >= 2;
+    if (!(T.limited && T.halfband < 1 && D >= NDLO + 1 && D <= NDLO + NDW - 2 && T.rows <= MAXR - 2 && T.rows >= 2)) return false;
+    return maxSlack <= 0 || ((T.rows - 1) * 100 + 70 - T.minScore) <= maxSlack;
 }
 
 // map a reference byte for comparison with a call: 'N' never matches (jni/...JNI.c:468-469)

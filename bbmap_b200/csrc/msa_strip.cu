@@ -44,7 +44,8 @@ struct StripParams {
     // per-task block in the pool:  int2 A[rows+2] {vertLimit[row], (minGood<<16|maxGood) of the row};  int hl[ns*SW] (hl[c-1] = horizLimit[c]);
     //                              unsigned tb[ns][rows+2]  4-bit predecessor codes, SW cells per word
     unsigned int* counter;
-    int debug;                                // bit 0: never skip a row, bit 1: never jump over rows (A/B and bisecting)
+    int debug;                                // bit 0: never skip a row, bit 1: never jump over rows (A/B and bisecting), bit 2: count work
+    unsigned long long* stats;                // [2] with debug bit 2: row-units evaluated, 32 x warp iterations of the evaluation phase
 };
 
 struct StripBlock { int2* A; int* hl; unsigned int* tb; int rs; };
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
     int mmRow = MM_NONE, call1 = 0, call0 = 0; // (minGood,maxGood) of row r so far; read[r-1], read[r-2]
     int loP = 1, hiP = 0, loC = INT_MAX, hiC = -1;
     int bestScore = INT_MIN, bestCol = -1, bestState = -1, bestPacked = 0;
+    unsigned long long nUnits = 0, nIters = 0;
 
     for (;;) {
         // ---- phase A: every lane advances to its next row that needs evaluation (cheap, divergent) ----
@@ -214,7 +216,9 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
             }
         }
         if (__all_sync(FULL, done)) break;
-        if (!pending) continue;          // (done lanes idle here until the warp has drained)
+        nIters++;
+        if (!pending) continue;
+        nUnits++;          // (done lanes idle here until the warp has drained)
 
         // ---- phase B: one row of W cells (convergent) ----
         {
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripP
             else newStrip = true;
         }
     }
+    if (S.debug & 4) { atomicAdd(S.stats, nUnits); atomicAdd(S.stats + 1, nIters); }
 }
 
 // ---------------- K2: per-row control flow of the reference, result, score2 + traceback2 ----------------
@@ -412,8 +417,8 @@ extern "C" size_t bbm_msa_strip_fixed_bytes(int chunkCount, int maxRows, int blo
 }
 extern "C" int bbm_launch_msa_strip(const MsaParams* P, const int* list, const unsigned int* endPtr, unsigned int base, int chunkStart, int chunkCount,
                                     int maxRows, void* scratch, size_t scratchBytes, unsigned int* counter, unsigned long long* poolCursor,
-                                    int blocks, int debug, cudaStream_t st) {
-    StripParams S;
+                                    int blocks, int debug, unsigned long long* stats, cudaStream_t st) {
+    StripParams S; S.stats = stats;
     S.P = *P; S.list = list; S.endPtr = endPtr; S.base = base; S.chunkStart = chunkStart; S.chunkCount = chunkCount;
     S.rowStride = maxRows + 2;
     char* p = (char*)scratch;

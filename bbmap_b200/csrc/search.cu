@@ -42,6 +42,7 @@ struct ctx_t {
     int values[MAXK], sizes[MAXK], rows[MAXK], stopsA[MAXK], active[MAXK];
     int locArray[SEARCH_MAX_READ];
     int status;
+    long long tExtend, tPrescan, tWalk, tFilter;      // clock64 per phase (only summed when SearchParams.prof is set)
 };
 
 __device__ __forceinline__ int rcomp_fast_dev(int kmer, int k) {     // AminoAcid.reverseComplementBinaryFast (dna/AminoAcid.java:258-271)
@@ -326,7 +327,7 @@ __device__ void find_max_qscore2(ctx_t* c, const int* starts, const int* stops, 
     int topQscore = -999999999, maxHits = 0, approxHitsCutoff, indelCutoff;
     if (perfectOnly) { approxHitsCutoff = numHits; indelCutoff = 0; }
     else { approxHitsCutoff = imax(prevMaxHits, imin(1, numHits - 1)); indelCutoff = MAX_INDEL2; }
-    int t;
+    int t, nActive = numHits;
     while ((t = heap_peek(c, numHits)) >= 0) {
         const int site = c->values[t], centerIndex = t;
         int approxHits = 0;
@@ -347,16 +348,19 @@ __device__ void find_max_qscore2(ctx_t* c, const int* starts, const int* stops, 
                 if (qscore >= maxQuickScore && earlyExit) { *outScore = topQscore; *outHits = maxHits; return; }
             }
         }
-        int t2;
-        while ((t2 = heap_peek(c, numHits)) >= 0 && c->values[t2] == site) {
-            const int row = c->rows[t2] + 1, col = t2;
-            if (row < c->stopsA[col]) {
-                c->rows[col] = row;
-                c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
-            } else {
-                c->active[col] = 0;
-                /* NOTE: values[col] keeps its last site, exactly like the reference's valueArray */
-                if (earlyExit && (perfectOnly || heap_size(c, numHits) < approxHitsCutoff)) { *outScore = topQscore; *outHits = maxHits; return; }
+        // pop every heap entry that sits on `site`.  The heap order is (site, column), so they come out in ascending column order, and a
+        // column whose next site is again `site` (clamped at the chromosome start) is popped again at once: one pass over the columns.
+        for (int col = 0; col < numHits; col++) {
+            while (c->active[col] && c->values[col] == site) {
+                const int row = c->rows[col] + 1;
+                if (row < c->stopsA[col]) {
+                    c->rows[col] = row;
+                    c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
+                } else {
+                    c->active[col] = 0; nActive--;
+                    /* NOTE: values[col] keeps its last site, exactly like the reference's valueArray */
+                    if (earlyExit && (perfectOnly || nActive < approxHitsCutoff)) { *outScore = topQscore; *outHits = maxHits; return; }
+                }
             }
         }
     }
@@ -389,7 +393,7 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
     }
     int* locArray = c->locArray;
     int prev = -1;       /* index of prevSS in R->sites (a site made during THIS walk), -1 = null */
-    int t, quit = 0;
+    int t, quit = 0, nActive = numHits;
     while (!quit && (t = heap_peek(c, numHits)) >= 0) {
         const int site = c->values[t], centerIndex = t;
         int maxNearbySite = site, approxHits = 0;
@@ -411,7 +415,9 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
                 const int chrom = number_to_chrom(c, site, baseChrom);
                 if (shortCircuit && qscore == maxQuickScore) score = maxScore;
                 else {
+                    const long long tx0 = clock64();
                     score = extend_score(c, bases, baseScores, len, offsets, c->values, chrom, centerIndex, locArray, numHits);
+                    c->tExtend += clock64() - tx0;
                     locArrayValid = 1;
                     int mn = 0x7fffffff, mx = (-0x7fffffff-1);
                     for (int i = 0; i < len; i++) { const int x = locArray[i]; if (x > -1) { if (x < mn) mn = x; if (x > mx) mx = x; } }
@@ -498,15 +504,17 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
             }
         }
         if (quit) break;
-        int t2, ret = 0;
-        while ((t2 = heap_peek(c, numHits)) >= 0 && c->values[t2] == site) {
-            const int row = c->rows[t2] + 1, col = t2;
-            if (row < c->stopsA[col]) {
-                c->rows[col] = row;
-                c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
-            } else {
-                c->active[col] = 0;
-                if (heap_size(c, numHits) < approxHitsCutoff) { ret = 1; break; }
+        int ret = 0;
+        for (int col = 0; col < numHits && !ret; col++) {          // same (site, column) pop order as the heap, see findMaxQscore2
+            while (c->active[col] && c->values[col] == site) {
+                const int row = c->rows[col] + 1;
+                if (row < c->stopsA[col]) {
+                    c->rows[col] = row;
+                    c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
+                } else {
+                    c->active[col] = 0; nActive--;
+                    if (nActive < approxHitsCutoff) { ret = 1; break; }
+                }
             }
         }
         if (ret) break;
@@ -639,6 +647,7 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
     }
     const int numKeysOriginal = n;
     const int maxLen = g->max_usable_length;
+    const long long tf0 = clock64();
     int numHits = count_hits(c, keysP, n, maxLen);
     if (numHits > 0) {
         const int trigger = (3 * n) / 4;
@@ -652,6 +661,7 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
         const int maxLists = imax((int)(HIT_FRACTION_TO_RETAIN * n), MIN_HIT_LISTS_TO_RETAIN);
         numHits = trim_by_greedy(c, offsetsP, keyScoresP, n, maxLists, keysP);
     }
+    c->tFilter += clock64() - tf0;
     H->num_hits = numHits;
     if (numHits < 1) { H->status = c->status; return; }
     if (numHits < n) n = shrink2(offsetsP, keysP, keyScoresP, n);
@@ -685,7 +695,9 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
                 else {
                     if (nh < n) nh = shrink_hits(st, sp, of, ks, n);
                     int ts, th;
+                    const long long tp0 = clock64();
                     find_max_qscore2(c, st, sp, of, ks, nh, chrom, minHitsToScore, 1, bestqscore >= maxQuickScore && pretend, &ts, &th);
+                    c->tPrescan += clock64() - tp0;
                     prescores[cycle] = ts; precounts[cycle] = th;
                     bestqscore = imax(ts, bestqscore); maxHits = imax(maxHits, th);
                     if (bestqscore >= maxQuickScore && pretend) { minHitsToScore = imax(minHitsToScore, maxHits); early = true; }
@@ -714,9 +726,11 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
                 const int* keys = strand == 0 ? keysP : keysM;
                 for (int i = 0; i < n; i++) { of[i] = strand == 0 ? offsetsP[i] : offsetsM[i]; ks[i] = strand == 0 ? keyScoresP[i] : keyScoresM[i]; }
                 const int nh = get_hits(c, keys, n, chrom, st, sp);
+                const long long tw0 = clock64();
                 if (nh >= 1)
                     slow_walk3(c, st, sp, strand == 0 ? basesP : basesM, strand == 0 ? baseScoresP : baseScoresM, len, ks, of, n, chrom, strand,
                                obeyLimits, R, bestScores, allBasesCovered, maxScore, fullyDefined, quitAfterTwoPerfects, 0);
+                c->tWalk += clock64() - tw0;
             }
             cycle++;
             if (quitAfterTwoPerfects && bestScores[5] >= 2) done = true;
@@ -732,15 +746,20 @@ struct SearchParams {
     const int* nkeys; const int* offsets; const int* keyScores; int maxKeys; int quitAfterTwoPerfects;
     bbm_search_head* heads; bbm_site* sites; int maxSites;
     ctx_t* ctxPool; int8_t* revPool; unsigned int* counter;
+    unsigned long long* prof;     // optional: 5 cycle counters {total, filter, prescan, walk (incl. extend), extend}
 };
 
 constexpr int SEARCH_THREADS = 64;
 
-__global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(SearchParams P) {
+
+template <int BPS>
+__global__ void __launch_bounds__(SEARCH_THREADS, BPS) search_kernel(SearchParams P) {
     const long long slot = (long long)blockIdx.x * SEARCH_THREADS + threadIdx.x;
     ctx_t* c = P.ctxPool + slot;
     int8_t* basesM = P.revPool + slot * 2 * SEARCH_MAX_READ;
     int8_t* baseScoresM = basesM + SEARCH_MAX_READ;
+    c->tExtend = 0; c->tPrescan = 0; c->tWalk = 0; c->tFilter = 0;
+    const long long tk0 = clock64();
     for (;;) {
         const unsigned r = atomicAdd(P.counter, 1u);
         if ((long long)r >= P.nreads) break;
@@ -752,6 +771,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(SearchParams P) 
             search_read(&P.X, P.bases + o, len, P.baseScores + o, P.offsets + (long long)r * P.maxKeys, P.keyScores + (long long)r * P.maxKeys,
                         P.nkeys[r], P.quitAfterTwoPerfects, H, &R, c, basesM, baseScoresM);
         H->nsites = R.nsites;
+    }
+    if (P.prof) {
+        atomicAdd(P.prof + 0, (unsigned long long)(clock64() - tk0)); atomicAdd(P.prof + 1, (unsigned long long)c->tFilter);
+        atomicAdd(P.prof + 2, (unsigned long long)c->tPrescan); atomicAdd(P.prof + 3, (unsigned long long)c->tWalk); atomicAdd(P.prof + 4, (unsigned long long)c->tExtend);
     }
 }
 
@@ -765,13 +788,15 @@ extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_block
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
                                  int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* ctxPool, int8_t* revPool,
-                                 unsigned int* counter, int blocks, cudaStream_t st) {
-    SearchParams P;
+                                 unsigned int* counter, unsigned long long* prof, int blocks, int blocksPerSm, cudaStream_t st) {
+    SearchParams P; P.prof = prof;
     P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts; P.X.hist = d_hist;
     P.X.chroms = d_chroms; P.X.chrom_off = d_chrom_off;
     P.bases = bases; P.baseScores = baseScores; P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.offsets = offsets; P.keyScores = keyScores;
     P.maxKeys = maxKeys; P.quitAfterTwoPerfects = quitAfterTwoPerfects; P.heads = heads; P.sites = sites; P.maxSites = maxSites;
     P.ctxPool = (ctx_t*)ctxPool; P.revPool = revPool; P.counter = counter;
-    search_kernel<<<blocks, SEARCH_THREADS, 0, st>>>(P);
+    if (blocksPerSm >= 16) search_kernel<16><<<blocks, SEARCH_THREADS, 0, st>>>(P);
+    else if (blocksPerSm >= 12) search_kernel<12><<<blocks, SEARCH_THREADS, 0, st>>>(P);
+    else search_kernel<8><<<blocks, SEARCH_THREADS, 0, st>>>(P);
     return (int)cudaGetLastError();
 }

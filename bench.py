@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-narrow", action="store_true", help="disable the thread-per-alignment narrow kernel (A/B)")
     ap.add_argument("--no-strip", action="store_true", help="route limited fills through the register-tiled kernel instead of the strip kernel (A/B)")
     ap.add_argument("--strip-budget-mb", type=int, default=0)
+    ap.add_argument("--narrow-slack", type=int, default=-1, help="narrow kernel only for alignments with maxQ-minScore <= this (points)")
     ap.add_argument("--strip-buckets", type=int, default=-1, help="work buckets (of 4096 cells) routed to the strip kernel; larger alignments use the tiled kernel")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-stage timings (ingest/seed/index/search/scoreNoIndels) of bench/stages.py")
     ap.add_argument("--stage-pairs", type=int, default=200_000)
@@ -181,8 +182,12 @@ def main():
         msa.set_option("narrow", 0)
     if args.no_strip:
         msa.set_option("strip", 0)
+    if args.narrow_slack >= 0:
+        msa.set_option("narrow", args.narrow_slack)
     if args.strip_buckets >= 0:
         msa.set_option("strip", args.strip_buckets)
+    if os.environ.get("BBM_STRIP_STATS"):
+        msa.set_option("strip_debug", 4)
     if args.strip_budget_mb:
         msa.set_option("strip_budget_mb", args.strip_budget_mb)
     dev = torch.device("cuda", local)
@@ -271,7 +276,7 @@ def main():
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
             "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
-                           "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "band_misses": msa.stat("band_misses")},
+                           "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "strip_units": msa.stat("strip_units"), "strip_lane_iters": msa.stat("strip_lane_iters"), "band_misses": msa.stat("band_misses")},
             "clocks": clocks,
             "int_peaks_glops": int_peaks,
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],

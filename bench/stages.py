@@ -49,7 +49,7 @@ def cpu_side(R, cb, co, n_cpu=20000):
     return out
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False, cpu=True):
+def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False, cpu=True, search_bps=0):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
@@ -98,6 +98,10 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     out["seed"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
                    "bytes_per_read": alg / n, "mean_keys": float(nk.mean())}
     # ---- a6-a9 search ----
+    if os.environ.get("BBM_SEARCH_PROFILE"):
+        _lib.check(L.bbm_set_option(h, b"search_profile", 1), "set_option")
+    if search_bps:
+        _lib.check(L.bbm_set_option(h, b"search_blocks_per_sm", search_bps), "set_option")
     d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_sites = torch.zeros(n * MAX_SITES * SITE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     t = timed(lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 1 if quit2 else 0,
@@ -118,6 +122,10 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     out["search"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
                      "bytes_per_read": alg / n, "mean_sites": float(ns.mean()), "reads_with_site": float((ns > 0).mean()), "top_site_is_origin": float(correct.mean()),
                      "status_nonzero": int((heads["status"] != 0).sum())}
+    if os.environ.get("BBM_SEARCH_PROFILE"):
+        L.bbm_get_stat.restype = C.c_int64
+        cyc = [L.bbm_get_stat(h, ("search_cycles_%d" % i).encode()) for i in range(5)]
+        out["search"]["thread_cycle_shares"] = dict(zip(["filter", "prescan", "walk_incl_extend", "extend"], [round(x / max(cyc[0], 1), 3) for x in cyc[1:]]))
     # ---- a10 scoreNoIndels over every emitted site ----
     rid, sj = np.nonzero(np.arange(MAX_SITES)[None, :] < ns[:, None])
     S = sites[rid, sj]
@@ -162,10 +170,12 @@ def main():
     ap.add_argument("--pairs", type=int, default=200_000)
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--search-bps", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
-    print(json.dumps(run(a.pairs, a.genome, a.reps, hbm_peak=hbm)))
+    print(json.dumps(run(a.pairs, a.genome, a.reps, hbm_peak=hbm, search_bps=a.search_bps, cpu=not a.no_cpu)))
 
 
 if __name__ == "__main__":

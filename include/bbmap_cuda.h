@@ -111,9 +111,14 @@ int  bbm_msa_gapped_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_
                                const bbm_gapped_task* tasks, const int32_t* gaps, int64_t ngap_ints, bbm_msa_out* outs,
                                int64_t ntasks, int8_t* match_buf, const int64_t* match_off);
 
-/* Tuning / introspection.  bbm_set_option keys: "narrow" (1 = route near-diagonal limited fills through the
- * thread-per-alignment kernel first; 0 = register-tiled kernel only).  bbm_get_stat keys: "launches", "band_misses"
- * (banded alignments re-run by the row-sequential kernel). */
+/* Tuning / introspection.  bbm_set_option keys:
+ *   "narrow"  0 = off, 1 = every shape-eligible limited fill first tries the 16-diagonal thread-per-alignment kernel, n>1 = only those
+ *             whose minScore lies within n points of the best possible score (default 1000; the others go straight to the strip kernel);
+ *   "strip"   0 = limited un-banded fills use the warp-per-alignment tiled kernel, n>0 = work-estimate buckets (of 4096 cells) below n use
+ *             the thread-per-alignment strip kernel (default 16 = all);  "strip_budget_mb" = device scratch the strip kernel may use;
+ *   "search_blocks_per_sm" 8/12/16;  "search_profile", "strip_debug" (diagnostics).
+ * Results are bit-identical for every setting.  bbm_get_stat keys: "launches", "band_misses" (banded alignments re-run by the
+ * row-sequential kernel), "tasks_total", "narrow_tried", "narrow_handed_over", "strip_tasks", "index_build_us". */
 int     bbm_set_option(bbm_ctx* ctx, const char* key, int value);
 int64_t bbm_get_stat(const bbm_ctx* ctx, const char* key);
 
