@@ -18,6 +18,7 @@ using namespace bbm;
 DECL_W(4) DECL_W(5) DECL_W(6) DECL_W(8) DECL_W(9) DECL_W(12) DECL_W(16)
 extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, cudaStream_t stream);
 extern "C" int bbm_msa_class_strip();
+extern "C" int bbm_msa_strip_blocks_per_sm();
 extern "C" int bbm_msa_strip_max_cols();
 extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols);
 extern "C" size_t bbm_msa_strip_fixed_bytes(int chunkCount, int maxRows, int blocks);
@@ -303,7 +304,7 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
         unsigned long long totalBytes = 0; memcpy(&totalBytes, &h[184], 8);
         const unsigned long long perMax = bbm_msa_strip_task_bytes(sRows, sCols);
         if (totalBytes > (unsigned long long)nstrip * perMax) totalBytes = (unsigned long long)nstrip * perMax;
-        const int blocksMax = c->sms * 4;
+        const int blocksMax = c->sms * bbm_msa_strip_blocks_per_sm();
         long long chunk = nstrip;
         if (totalBytes > c->strip_budget) { chunk = (long long)(c->strip_budget / perMax); if (chunk < 1024) chunk = 1024; if (chunk > nstrip) chunk = nstrip; }
         const unsigned long long poolBytes = (chunk == nstrip) ? totalBytes : (unsigned long long)chunk * perMax;

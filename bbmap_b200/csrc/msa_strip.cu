@@ -30,6 +30,9 @@
 namespace bbm {
 
 constexpr int STRIP_THREADS = 128;
+#ifndef STRIP_BLOCKS_PER_SM
+#define STRIP_BLOCKS_PER_SM 4
+#endif
 
 struct StripParams {
     MsaParams P;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(128) msa_strip_prep_kernel(StripParams S) {
 
 // ---------------- K1: the fill ----------------
 template <int W>
-__global__ void __launch_bounds__(STRIP_THREADS, 4) msa_strip_fill_kernel(StripParams S) {
+__global__ void __launch_bounds__(STRIP_THREADS, STRIP_BLOCKS_PER_SM) msa_strip_fill_kernel(StripParams S) {
     __shared__ CellTables tab;
     cell_tables_init(tab);
     __syncthreads();
@@ -409,6 +412,7 @@ __global__ void __launch_bounds__(128) msa_strip_finish_kernel(StripParams S) {
 using namespace bbm;
 
 extern "C" int bbm_msa_strip_width() { return SW; }
+extern "C" int bbm_msa_strip_blocks_per_sm() { return STRIP_BLOCKS_PER_SM; }
 extern "C" int bbm_msa_strip_max_cols() { return STRIP_MAX_COLS; }
 extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols) { return strip_task_bytes(rows, cols); }
 // fixed part of the scratch: per-slot header + final-row candidates, lane-private record arrays
