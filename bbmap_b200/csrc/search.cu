@@ -35,15 +35,25 @@ struct SearchIndex {
 struct ReadState {           // where this read's sites go
     bbm_site* sites; int maxSites; int nsites;
 };
+// Per-read working arrays of the heap walks, one slot per hit list: current (site - offset) value, current / end index into the
+// block's sites array (a list is exhausted when row == stop), key offset and key score.  For batches with at most 32 keys per read
+// they live in shared memory, laid out [slot][thread] (bank = thread: conflict-free whatever slot each lane touches); otherwise in a
+// per-thread global pool.  `S` is the slot stride in elements.
 struct ctx_t {
     const SearchIndex* X;
     int K, baseKeyHitScore, indelPenalty, maxPenaltyMisaligned, scoreZ1Key;
     int siteMask, shift, lowMask, highMask, cpb;
-    int values[MAXK], sizes[MAXK], rows[MAXK], stopsA[MAXK], active[MAXK];
-    int locArray[SEARCH_MAX_READ];
+    int S;
+    int* values; int* rows; int* stops; short* of; short* ks;
+    int* locArray;
     int status;
     long long tExtend, tPrescan, tWalk, tFilter;      // clock64 per phase (only summed when SearchParams.prof is set)
 };
+#define VAL(i)  c->values[(i) * c->S]
+#define ROW(i)  c->rows[(i) * c->S]
+#define STOP(i) c->stops[(i) * c->S]
+#define OFS(i)  ((int)c->of[(i) * c->S])
+#define KSC(i)  ((int)c->ks[(i) * c->S])
 
 __device__ __forceinline__ int rcomp_fast_dev(int kmer, int k) {     // AminoAcid.reverseComplementBinaryFast (dna/AminoAcid.java:258-271)
     int out = 0;
@@ -101,57 +111,66 @@ __device__ int max_quick_score(const ctx_t* c, const int* offsets, const int* ke
     return x + y;
 }
 
-__device__ int score_right(const ctx_t* c, const int* locs, const int* keyScores, int centerIndex, int numHits) {
-    int score = 0, prev, loc = locs[centerIndex];
+__device__ int score_right(const ctx_t* c, int centerIndex, int numHits) {
+    int score = 0, prev, loc = VAL(centerIndex);
     for (int i = centerIndex + 1; i < numHits; i++) {
-        if (locs[i] >= 0) {
-            prev = loc; loc = locs[i];
+        const int v = VAL(i);
+        if (v >= 0) {
+            prev = loc; loc = v;
             const int offset = absdif(loc, prev);
             if (offset <= MAX_INDEL) {
-                score += keyScores[i];
+                score += KSC(i);
                 if (offset != 0) score -= imin(c->indelPenalty + INDEL_PENALTY_MULT * offset, c->maxPenaltyMisaligned);
             } else loc = prev;
         }
     }
     return score;
 }
-__device__ int score_left(const ctx_t* c, const int* locs, const int* keyScores, int centerIndex) {
-    int score = 0, prev, loc = locs[centerIndex];
+__device__ int score_left(const ctx_t* c, int centerIndex) {
+    int score = 0, prev, loc = VAL(centerIndex);
     for (int i = centerIndex - 1; i >= 0; i--) {
-        if (locs[i] >= 0) {
-            prev = loc; loc = locs[i];
+        const int v = VAL(i);
+        if (v >= 0) {
+            prev = loc; loc = v;
             const int offset = absdif(loc, prev);
             if (offset <= MAX_INDEL) {
-                score += keyScores[i];
+                score += KSC(i);
                 if (offset != 0) score -= imin(c->indelPenalty + INDEL_PENALTY_MULT * offset, c->maxPenaltyMisaligned);
             } else loc = prev;
         }
     }
     return score;
 }
-__device__ int score_y(const int* locs, int centerIndex, const int* offsets, int n) {
-    const int center = locs[centerIndex];
+__device__ int score_y(const ctx_t* c, int centerIndex, int n) {
+    const int center = VAL(centerIndex);
     int rightIndex = -1;
-    for (int i = n - 1; rightIndex < centerIndex; i--) if (locs[i] == center) rightIndex = i;
-    return offsets[rightIndex] - offsets[centerIndex];
+    for (int i = n - 1; rightIndex < centerIndex; i--) if (VAL(i) == center) rightIndex = i;
+    return OFS(rightIndex) - OFS(centerIndex);
 }
-__device__ int quick_score(const ctx_t* c, const int* locs, const int* keyScores, int centerIndex, const int* offsets, int numApproxHits, int numHits) {
-    if (numApproxHits == 1) return keyScores[centerIndex];
-    const int x = keyScores[centerIndex] + score_left(c, locs, keyScores, centerIndex) + score_right(c, locs, keyScores, centerIndex, numHits) - centerIndex;
-    const int y = Y_SCORE_MULT * score_y(locs, centerIndex, offsets, numHits);
+__device__ int quick_score(const ctx_t* c, int centerIndex, int numApproxHits, int numHits) {
+    if (numApproxHits == 1) return KSC(centerIndex);
+    const int x = KSC(centerIndex) + score_left(c, centerIndex) + score_right(c, centerIndex, numHits) - centerIndex;
+    const int y = Y_SCORE_MULT * score_y(c, centerIndex, numHits);
     return x + y;
 }
-__device__ int score_z2(const ctx_t* c, const int* locs, int centerIndex, const int* offsets, int numApproxHits, int numHits) {
+__device__ int score_z2(const ctx_t* c, int centerIndex, int numApproxHits, int numHits) {
     if (numApproxHits == 1) return c->scoreZ1Key;
-    const int center = locs[centerIndex];
+    const int center = VAL(centerIndex);
     const int maxLoc = center + MAX_INDEL2, minLoc = imax(0, center - MAX_INDEL);
     int score = 0, a0 = -1, b0 = -1;
     for (int i = 0; i < numHits; i++) {
-        const int loc = locs[i];
-        if (loc >= minLoc && loc <= maxLoc) { const int a = offsets[i]; if (b0 < a) { score += b0 - a0; a0 = a; } b0 = a + c->K; }
+        const int loc = VAL(i);
+        if (loc >= minLoc && loc <= maxLoc) { const int a = OFS(i); if (b0 < a) { score += b0 - a0; a0 = a; } b0 = a + c->K; }
     }
     score += b0 - a0;
     return score * Z_SCORE_MULT;
+}
+// maxQuickScore over the ctx arrays (offsets / key scores of the current strand, before shrinking)
+__device__ int max_quick_score_ctx(const ctx_t* c, int n) {
+    int x = 0, score = 0, a0 = -1, b0 = -1;
+    for (int i = 0; i < n; i++) { x += KSC(i); const int a = OFS(i); if (b0 < a) { score += b0 - a0; a0 = a; } b0 = a + c->K; }
+    score += b0 - a0;
+    return x + score * Z_SCORE_MULT + Y_SCORE_MULT * (OFS(n - 1) - OFS(0));
 }
 
 /* ---------------- MSA.calcAffineScore(locArray, baseScores, bases) ---------------- */
@@ -188,20 +207,20 @@ __device__ int calc_affine_score(const int* locArray, const int8_t* baseScores, 
 }
 
 /* ---------------- extendScore (BBIndex.java:2558-2757, USE_AFFINE_SCORE, KFILTER<2) ---------------- */
-__device__ int extend_score(ctx_t* c, const int8_t* bases, const int8_t* baseScores, int len, const int* offsets, const int* values,
+__device__ int extend_score(ctx_t* c, const int8_t* bases, const int8_t* baseScores, int len,
                         int chrom, int centerIndex, int* locArray, int numHits) {
-    const int centerVal = values[centerIndex], centerLoc = number_to_site(c, centerVal);
+    const int centerVal = VAL(centerIndex), centerLoc = number_to_site(c, centerVal);
     const int minVal = centerVal - MAX_INDEL, maxVal = centerVal + MAX_INDEL2;
     const int8_t* ref = c->X->chroms + c->X->chrom_off[chrom - 1];
     const int refLen = (int)(c->X->chrom_off[chrom] - c->X->chrom_off[chrom - 1]);
     const int K = c->K;
     for (int i = 0; i < len; i++) locArray[i] = -1;
     for (int i = 0, keynum = 0; i < numHits; i++) {
-        const int value = values[i];
+        const int value = VAL(i);
         if (value >= minVal && value <= maxVal) {
             const int refbase = number_to_site(c, value);
             keynum++;
-            const int callbase = offsets[i];
+            const int callbase = OFS(i);
             int misses = 0;
             for (int cloc = callbase + K - 1, rloc = refbase + cloc; cloc >= 0 && rloc >= 0 && rloc < refLen; cloc--, rloc--) {
                 const int old = locArray[cloc];
@@ -213,10 +232,10 @@ __device__ int extend_score(ctx_t* c, const int8_t* bases, const int8_t* baseSco
         }
     }
     for (int i = 0; i < numHits; i++) {
-        const int value = values[i];
+        const int value = VAL(i);
         if (value >= minVal && value <= maxVal) {
             const int refbase = number_to_site(c, value);
-            const int callbase = offsets[i];
+            const int callbase = OFS(i);
             int misses = 0;
             for (int cloc = callbase + K, rloc = refbase + cloc; cloc < len && rloc < refLen; cloc++, rloc++) {
                 const int old = locArray[cloc];
@@ -275,25 +294,29 @@ __device__ void set_perfect(const ctx_t* c, bbm_site* s, const int8_t* bases, in
 }
 
 /* ---------------- getHits / shrink ---------------- */
-__device__ int get_hits(const ctx_t* c, const int* keys, int n, int chrom, int* starts, int* stops) {
+// getHits (BBIndex.java:353-373) straight into the ctx arrays: ROW/STOP = start/stop of the key's list in this block (-1 = none),
+// OFS/KSC = the strand's offsets and key scores.
+__device__ int get_hits(ctx_t* c, const int* keys, const int* offsets, const int* keyScores, int n, int chrom) {
     int numHits = 0;
     const SearchBlock* b = block_of(c, chrom);
     for (int i = 0; i < n; i++) {
         const int key = keys[i];
-        starts[i] = -1; stops[i] = -1;
+        int st = -1, sp = -1;
         if (key >= 0) {
             const int len = count_key(c, key);
             if (len > 0) {                                 /* maxLen = Integer.MAX_VALUE */
                 const int len2 = block_length(b, key);
-                if (len2 > 0) { starts[i] = b->starts[key]; stops[i] = starts[i] + len2; numHits++; }
+                if (len2 > 0) { st = b->starts[key]; sp = st + len2; numHits++; }
             }
         }
+        ROW(i) = st; STOP(i) = sp;
+        c->of[i * c->S] = (short)offsets[i]; c->ks[i * c->S] = (short)keyScores[i];
     }
     return numHits;
 }
-__device__ int shrink_hits(int* starts, int* stops, int* offsets, int* keyScores, int n) {
+__device__ int shrink_hits(ctx_t* c, int n) {
     int j = 0;
-    for (int i = 0; i < n; i++) if (starts[i] >= 0) { starts[j] = starts[i]; stops[j] = stops[i]; offsets[j] = offsets[i]; keyScores[j] = keyScores[i]; j++; }
+    for (int i = 0; i < n; i++) if (ROW(i) >= 0) { if (j != i) { ROW(j) = ROW(i); STOP(j) = STOP(i); c->of[j * c->S] = c->of[i * c->S]; c->ks[j * c->S] = c->ks[i * c->S]; } j++; }
     return j;
 }
 
@@ -304,43 +327,39 @@ __device__ __forceinline__ int site_minus_offset(const ctx_t* c, int a, int offs
     return to_number(c, imax(st - offset, 0), ch);
 }
 
-/* The heap (QuadHeap ordered by (site, column), Quad.java:18-22) is replaced by an arg-min over the active columns: the
+/* The heap (QuadHeap ordered by (site, column), Quad.java:18-22) is replaced by an arg-min over the live columns (row < stop): the
  * order is total, so the sequence of (site, column) visited is identical. */
 __device__ int heap_peek(const ctx_t* c, int numHits) {
-    int best = -1;
-    for (int i = 0; i < numHits; i++) if (c->active[i] && (best < 0 || c->values[i] < c->values[best])) best = i;
+    int best = -1, bestVal = 0;
+    for (int i = 0; i < numHits; i++) {
+        if (ROW(i) < STOP(i)) { const int v = VAL(i); if (best < 0 || v < bestVal) { best = i; bestVal = v; } }
+    }
     return best;
 }
-__device__ int heap_size(const ctx_t* c, int numHits) { int n = 0; for (int i = 0; i < numHits; i++) n += c->active[i]; return n; }
 
 /* ---------------- findMaxQscore2 ---------------- */
-__device__ void find_max_qscore2(ctx_t* c, const int* starts, const int* stops, const int* offsets, const int* keyScores, int numHits,
-                             int baseChrom_, int prevMaxHits, int earlyExit, int perfectOnly, int* outScore, int* outHits) {
+__device__ void find_max_qscore2(ctx_t* c, int numHits, int baseChrom_, int prevMaxHits, int earlyExit, int perfectOnly, int* outScore, int* outHits) {
     const int baseChrom = base_chrom(c, baseChrom_);
     const SearchBlock* b = block_of(c, baseChrom_);
-    for (int i = 0; i < numHits; i++) {
-        c->sizes[i] = stops[i] - starts[i];
-        c->rows[i] = starts[i]; c->stopsA[i] = stops[i]; c->active[i] = 1;
-        c->values[i] = site_minus_offset(c, b->sites[starts[i]], offsets[i], baseChrom);
-    }
-    const int maxQuickScore = max_quick_score(c, offsets, keyScores, numHits);
+    for (int i = 0; i < numHits; i++) VAL(i) = site_minus_offset(c, b->sites[ROW(i)], OFS(i), baseChrom);
+    const int maxQuickScore = max_quick_score_ctx(c, numHits);
     int topQscore = -999999999, maxHits = 0, approxHitsCutoff, indelCutoff;
     if (perfectOnly) { approxHitsCutoff = numHits; indelCutoff = 0; }
     else { approxHitsCutoff = imax(prevMaxHits, imin(1, numHits - 1)); indelCutoff = MAX_INDEL2; }
     int t, nActive = numHits;
     while ((t = heap_peek(c, numHits)) >= 0) {
-        const int site = c->values[t], centerIndex = t;
+        const int site = VAL(t), centerIndex = t;
         int approxHits = 0;
         {
             const int minsite = site - imin(MAX_INDEL, indelCutoff), maxsite = site + MAX_INDEL2;
             for (int column = 0, chances = numHits - approxHitsCutoff; column < numHits && chances >= 0; column++) {
-                const int x = c->values[column];
+                const int x = VAL(column);
                 if (x >= minsite && x <= maxsite) approxHits++; else chances--;
             }
         }
         if (approxHits >= approxHitsCutoff) {
-            int qscore = quick_score(c, c->values, keyScores, centerIndex, offsets, approxHits, numHits);
-            qscore += score_z2(c, c->values, centerIndex, offsets, approxHits, numHits);
+            int qscore = quick_score(c, centerIndex, approxHits, numHits);
+            qscore += score_z2(c, centerIndex, approxHits, numHits);
             if (qscore > topQscore) {
                 maxHits = imax(approxHits, maxHits);
                 approxHitsCutoff = imax(approxHitsCutoff, approxHits - 1);
@@ -351,14 +370,12 @@ __device__ void find_max_qscore2(ctx_t* c, const int* starts, const int* stops, 
         // pop every heap entry that sits on `site`.  The heap order is (site, column), so they come out in ascending column order, and a
         // column whose next site is again `site` (clamped at the chromosome start) is popped again at once: one pass over the columns.
         for (int col = 0; col < numHits; col++) {
-            while (c->active[col] && c->values[col] == site) {
-                const int row = c->rows[col] + 1;
-                if (row < c->stopsA[col]) {
-                    c->rows[col] = row;
-                    c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
-                } else {
-                    c->active[col] = 0; nActive--;
-                    /* NOTE: values[col] keeps its last site, exactly like the reference's valueArray */
+            while (ROW(col) < STOP(col) && VAL(col) == site) {
+                const int row = ROW(col) + 1;
+                ROW(col) = row;
+                if (row < STOP(col)) VAL(col) = site_minus_offset(c, b->sites[row], OFS(col), baseChrom);
+                else {
+                    nActive--;          /* VAL(col) keeps its last site, exactly like the reference's valueArray */
                     if (earlyExit && (perfectOnly || nActive < approxHitsCutoff)) { *outScore = topQscore; *outHits = maxHits; return; }
                 }
             }
@@ -368,11 +385,11 @@ __device__ void find_max_qscore2(ctx_t* c, const int* starts, const int* stops, 
 }
 
 /* ---------------- slowWalk3 ---------------- */
-__device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* bases, const int8_t* baseScores, int len, int* keyScores, int* offsets,
+__device__ void slow_walk3(ctx_t* c, const int8_t* bases, const int8_t* baseScores, int len,
                        int numKeys, int baseChrom_, int strand, int obeyLimits, ReadState* R, int* bestScores, int allBasesCovered,
-                       int maxScore, int fullyDefined, int quitAfterTwoPerfects, int* prevIdx) {
-    const int maxQuickScore = max_quick_score(c, offsets, keyScores, numKeys);
-    const int numHits = shrink_hits(starts, stops, offsets, keyScores, numKeys);
+                       int maxScore, int fullyDefined, int quitAfterTwoPerfects) {
+    const int maxQuickScore = max_quick_score_ctx(c, numKeys);
+    const int numHits = shrink_hits(c, numKeys);
     const int filter_by_qscore = (numKeys >= 5);
     const int minScore = obeyLimits ? (int)(MIN_SCORE_MULT * maxScore) : (int)(MIN_SCORE_MULT * 1.25f * maxScore);
     const int minQuickScore = (int)(MIN_QSCORE_MULT * maxQuickScore);
@@ -386,28 +403,24 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
     if (approxHitsCutoff > numHits) return;
     const int shortCircuit = (allBasesCovered && numKeys == numHits && filter_by_qscore);
     if (currentTopScore >= maxScore) qcutoff = imax(qcutoff, (int)(maxQuickScore * DYNAMIC_QSCORE_THRESH_PERFECT));
-    for (int i = 0; i < numHits; i++) {
-        c->sizes[i] = stops[i] - starts[i];
-        c->rows[i] = starts[i]; c->stopsA[i] = stops[i]; c->active[i] = 1;
-        c->values[i] = site_minus_offset(c, b->sites[starts[i]], offsets[i], baseChrom);
-    }
+    for (int i = 0; i < numHits; i++) VAL(i) = site_minus_offset(c, b->sites[ROW(i)], OFS(i), baseChrom);
     int* locArray = c->locArray;
     int prev = -1;       /* index of prevSS in R->sites (a site made during THIS walk), -1 = null */
     int t, quit = 0, nActive = numHits;
     while (!quit && (t = heap_peek(c, numHits)) >= 0) {
-        const int site = c->values[t], centerIndex = t;
+        const int site = VAL(t), centerIndex = t;
         int maxNearbySite = site, approxHits = 0;
         {
             const int minsite = site - MAX_INDEL, maxsite = site + MAX_INDEL2;
             for (int column = 0, chances = numHits - approxHitsCutoff; column < numHits && chances >= 0; column++) {
-                const int x = c->values[column];
+                const int x = VAL(column);
                 if (x >= minsite && x <= maxsite) { maxNearbySite = (x > maxNearbySite ? x : maxNearbySite); approxHits++; } else chances--;
             }
         }
         if (approxHits >= approxHitsCutoff) {
             int score;
-            int qscore = filter_by_qscore ? quick_score(c, c->values, keyScores, centerIndex, offsets, approxHits, numHits) : qcutoff;
-            qscore += score_z2(c, c->values, centerIndex, offsets, approxHits, numHits);
+            int qscore = filter_by_qscore ? quick_score(c, centerIndex, approxHits, numHits) : qcutoff;
+            qscore += score_z2(c, centerIndex, approxHits, numHits);
             int mapStart = site, mapStop = maxNearbySite;
             int locArrayValid = 0;
             if (qscore < qcutoff) score = -1;
@@ -416,7 +429,7 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
                 if (shortCircuit && qscore == maxQuickScore) score = maxScore;
                 else {
                     const long long tx0 = clock64();
-                    score = extend_score(c, bases, baseScores, len, offsets, c->values, chrom, centerIndex, locArray, numHits);
+                    score = extend_score(c, bases, baseScores, len, chrom, centerIndex, locArray, numHits);
                     c->tExtend += clock64() - tx0;
                     locArrayValid = 1;
                     int mn = 0x7fffffff, mx = (-0x7fffffff-1);
@@ -506,13 +519,12 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
         if (quit) break;
         int ret = 0;
         for (int col = 0; col < numHits && !ret; col++) {          // same (site, column) pop order as the heap, see findMaxQscore2
-            while (c->active[col] && c->values[col] == site) {
-                const int row = c->rows[col] + 1;
-                if (row < c->stopsA[col]) {
-                    c->rows[col] = row;
-                    c->values[col] = site_minus_offset(c, b->sites[row], offsets[col], baseChrom);
-                } else {
-                    c->active[col] = 0; nActive--;
+            while (ROW(col) < STOP(col) && VAL(col) == site) {
+                const int row = ROW(col) + 1;
+                ROW(col) = row;
+                if (row < STOP(col)) VAL(col) = site_minus_offset(c, b->sites[row], OFS(col), baseChrom);
+                else {
+                    nActive--;
                     if (nActive < approxHitsCutoff) { ret = 1; break; }
                 }
             }
@@ -525,7 +537,6 @@ __device__ void slow_walk3(ctx_t* c, int* starts, int* stops, const int8_t* base
     bestScores[3] = imax(bestScores[3], bestqscore);
     bestScores[4] = maxQuickScore;
     bestScores[5] = perfectsFound;
-    (void)prevIdx;
 }
 
 /* ---------------- Solver (greedy removal of the least useful hit list) ---------------- */
@@ -680,7 +691,6 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
     else for (int i = 1; i < n; i++) if (offsetsP[i] > offsetsP[i - 1] + K) { allBasesCovered = false; break; }
     const bool pretend = (allBasesCovered || n >= numKeysOriginal - 4 || (n >= 9 && (offsetsP[n - 1] - offsetsP[0] + K) > imax(40, (int)(len * .75f))));
     const int minChrom = 1, maxChrom = X->nchroms;
-    int st[MAXK], sp[MAXK], of[MAXK], ks[MAXK];
     if (prescan_qscore) {
         int bestqscore = 0, maxHits = 0, minHitsToScore = 1, cycle = 0; bool early = false;
         const int ncyc = 2 * X->nblocks;
@@ -688,15 +698,13 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
         havePre = true;
         for (int chrom = minChrom; chrom <= maxChrom && !early; chrom = ((chrom & c->highMask) + c->cpb)) {
             for (int pmi = 0; pmi < 2 && !early; pmi++, cycle++) {
-                const int* keys = pmi == 0 ? keysP : keysM;
-                for (int i = 0; i < n; i++) { of[i] = pmi == 0 ? offsetsP[i] : offsetsM[i]; ks[i] = pmi == 0 ? keyScoresP[i] : keyScoresM[i]; }
-                int nh = get_hits(c, keys, n, chrom, st, sp);
+                int nh = get_hits(c, pmi == 0 ? keysP : keysM, pmi == 0 ? offsetsP : offsetsM, pmi == 0 ? keyScoresP : keyScoresM, n, chrom);
                 if (nh < minHitsToScore) { prescores[cycle] = -9999; precounts[cycle] = 0; }
                 else {
-                    if (nh < n) nh = shrink_hits(st, sp, of, ks, n);
+                    if (nh < n) nh = shrink_hits(c, n);
                     int ts, th;
                     const long long tp0 = clock64();
-                    find_max_qscore2(c, st, sp, of, ks, nh, chrom, minHitsToScore, 1, bestqscore >= maxQuickScore && pretend, &ts, &th);
+                    find_max_qscore2(c, nh, chrom, minHitsToScore, 1, bestqscore >= maxQuickScore && pretend, &ts, &th);
                     c->tPrescan += clock64() - tp0;
                     prescores[cycle] = ts; precounts[cycle] = th;
                     bestqscore = imax(ts, bestqscore); maxHits = imax(maxHits, th);
@@ -723,13 +731,11 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
     for (int chrom = minChrom; chrom <= maxChrom && !done; chrom = ((chrom & c->highMask) + c->cpb)) {
         for (int strand = 0; strand < 2 && !done; strand++) {
             if (!havePre || precounts[cycle] >= hitsCutoff || prescores[cycle] >= qscoreCutoff) {
-                const int* keys = strand == 0 ? keysP : keysM;
-                for (int i = 0; i < n; i++) { of[i] = strand == 0 ? offsetsP[i] : offsetsM[i]; ks[i] = strand == 0 ? keyScoresP[i] : keyScoresM[i]; }
-                const int nh = get_hits(c, keys, n, chrom, st, sp);
+                const int nh = get_hits(c, strand == 0 ? keysP : keysM, strand == 0 ? offsetsP : offsetsM, strand == 0 ? keyScoresP : keyScoresM, n, chrom);
                 const long long tw0 = clock64();
                 if (nh >= 1)
-                    slow_walk3(c, st, sp, strand == 0 ? basesP : basesM, strand == 0 ? baseScoresP : baseScoresM, len, ks, of, n, chrom, strand,
-                               obeyLimits, R, bestScores, allBasesCovered, maxScore, fullyDefined, quitAfterTwoPerfects, 0);
+                    slow_walk3(c, strand == 0 ? basesP : basesM, strand == 0 ? baseScoresP : baseScoresM, len, n, chrom, strand,
+                               obeyLimits, R, bestScores, allBasesCovered, maxScore, fullyDefined, quitAfterTwoPerfects);
                 c->tWalk += clock64() - tw0;
             }
             cycle++;
@@ -745,19 +751,35 @@ struct SearchParams {
     const int8_t* bases; const int8_t* baseScores; const long long* read_off; long long nreads;
     const int* nkeys; const int* offsets; const int* keyScores; int maxKeys; int quitAfterTwoPerfects;
     bbm_search_head* heads; bbm_site* sites; int maxSites;
-    ctx_t* ctxPool; int8_t* revPool; unsigned int* counter;
+    char* pool; unsigned int* counter;
     unsigned long long* prof;     // optional: 5 cycle counters {total, filter, prescan, walk (incl. extend), extend}
 };
 
 constexpr int SEARCH_THREADS = 64;
+constexpr int SEARCH_FAST_KEYS = 32;           // batches with at most this many keys per read keep the walk arrays in shared memory
+// per-thread block in the global pool: locArray[608] int, basesM[608], baseScoresM[608], then (slow path only) the walk arrays for 96 keys
+constexpr size_t SEARCH_POOL_FIXED = (size_t)SEARCH_MAX_READ * 4 + 2 * SEARCH_MAX_READ;
+constexpr size_t SEARCH_POOL_BYTES = SEARCH_POOL_FIXED + (size_t)MAXK * (3 * 4 + 2 * 2);
 
-
-template <int BPS>
-__global__ void __launch_bounds__(SEARCH_THREADS, BPS) search_kernel(SearchParams P) {
+template <bool SHARED>
+__global__ void __launch_bounds__(SEARCH_THREADS, SHARED ? 7 : 8) search_kernel(SearchParams P) {
+    __shared__ int sVal[SHARED ? SEARCH_FAST_KEYS * SEARCH_THREADS : 1], sRow[SHARED ? SEARCH_FAST_KEYS * SEARCH_THREADS : 1],
+                   sStop[SHARED ? SEARCH_FAST_KEYS * SEARCH_THREADS : 1];
+    __shared__ short sOf[SHARED ? SEARCH_FAST_KEYS * SEARCH_THREADS : 1], sKs[SHARED ? SEARCH_FAST_KEYS * SEARCH_THREADS : 1];
     const long long slot = (long long)blockIdx.x * SEARCH_THREADS + threadIdx.x;
-    ctx_t* c = P.ctxPool + slot;
-    int8_t* basesM = P.revPool + slot * 2 * SEARCH_MAX_READ;
+    char* mine = P.pool + slot * SEARCH_POOL_BYTES;
+    ctx_t ctx; ctx_t* c = &ctx;
+    c->locArray = (int*)mine;
+    int8_t* basesM = (int8_t*)(mine + (size_t)SEARCH_MAX_READ * 4);
     int8_t* baseScoresM = basesM + SEARCH_MAX_READ;
+    if (SHARED) {
+        c->S = SEARCH_THREADS;
+        c->values = sVal + threadIdx.x; c->rows = sRow + threadIdx.x; c->stops = sStop + threadIdx.x; c->of = sOf + threadIdx.x; c->ks = sKs + threadIdx.x;
+    } else {
+        c->S = 1;
+        int* w = (int*)(mine + SEARCH_POOL_FIXED);
+        c->values = w; c->rows = w + MAXK; c->stops = w + 2 * MAXK; c->of = (short*)(w + 3 * MAXK); c->ks = c->of + MAXK;
+    }
     c->tExtend = 0; c->tPrescan = 0; c->tWalk = 0; c->tFilter = 0;
     const long long tk0 = clock64();
     for (;;) {
@@ -767,9 +789,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, BPS) search_kernel(SearchParam
         bbm_search_head z = {}; *H = z;
         ReadState R; R.sites = P.sites + (long long)r * P.maxSites; R.maxSites = P.maxSites; R.nsites = 0;
         const long long o = P.read_off[r]; const int len = (int)(P.read_off[r + 1] - o);
-        if (P.nkeys[r] > 0)
+        const int nk = P.nkeys[r];
+        if (SHARED && nk > SEARCH_FAST_KEYS) H->status = BBM_ST_BADARG;       // cannot happen: the host picks this kernel from maxKeys
+        else if (nk > 0)
             search_read(&P.X, P.bases + o, len, P.baseScores + o, P.offsets + (long long)r * P.maxKeys, P.keyScores + (long long)r * P.maxKeys,
-                        P.nkeys[r], P.quitAfterTwoPerfects, H, &R, c, basesM, baseScoresM);
+                        nk, P.quitAfterTwoPerfects, H, &R, c, basesM, baseScoresM);
         H->nsites = R.nsites;
     }
     if (P.prof) {
@@ -782,21 +806,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, BPS) search_kernel(SearchParam
 
 using namespace bbm;
 
-extern "C" size_t bbm_search_ctx_bytes() { return sizeof(ctx_t); }
+extern "C" size_t bbm_search_pool_bytes() { return SEARCH_POOL_BYTES; }
 extern "C" int bbm_search_threads() { return SEARCH_THREADS; }
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
-                                 int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* ctxPool, int8_t* revPool,
-                                 unsigned int* counter, unsigned long long* prof, int blocks, int blocksPerSm, cudaStream_t st) {
+                                 int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* pool,
+                                 unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, cudaStream_t st) {
     SearchParams P; P.prof = prof;
     P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts; P.X.hist = d_hist;
     P.X.chroms = d_chroms; P.X.chrom_off = d_chrom_off;
     P.bases = bases; P.baseScores = baseScores; P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.offsets = offsets; P.keyScores = keyScores;
     P.maxKeys = maxKeys; P.quitAfterTwoPerfects = quitAfterTwoPerfects; P.heads = heads; P.sites = sites; P.maxSites = maxSites;
-    P.ctxPool = (ctx_t*)ctxPool; P.revPool = revPool; P.counter = counter;
-    if (blocksPerSm >= 16) search_kernel<16><<<blocks, SEARCH_THREADS, 0, st>>>(P);
-    else if (blocksPerSm >= 12) search_kernel<12><<<blocks, SEARCH_THREADS, 0, st>>>(P);
-    else search_kernel<8><<<blocks, SEARCH_THREADS, 0, st>>>(P);
+    P.pool = (char*)pool; P.counter = counter;
+    if (maxKeys <= SEARCH_FAST_KEYS && !forcePool) search_kernel<true><<<blocks, SEARCH_THREADS, 0, st>>>(P);
+    else search_kernel<false><<<blocks, SEARCH_THREADS, 0, st>>>(P);
     return (int)cudaGetLastError();
 }

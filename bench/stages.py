@@ -101,7 +101,7 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     if os.environ.get("BBM_SEARCH_PROFILE"):
         _lib.check(L.bbm_set_option(h, b"search_profile", 1), "set_option")
     if search_bps:
-        _lib.check(L.bbm_set_option(h, b"search_blocks_per_sm", search_bps), "set_option")
+        _lib.check(L.bbm_set_option(h, b"search_shared", search_bps), "set_option")
     d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_sites = torch.zeros(n * MAX_SITES * SITE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     t = timed(lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 1 if quit2 else 0,

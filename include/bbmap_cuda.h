@@ -116,7 +116,9 @@ int  bbm_msa_gapped_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_
  *             whose minScore lies within n points of the best possible score (default 1000; the others go straight to the strip kernel);
  *   "strip"   0 = limited un-banded fills use the warp-per-alignment tiled kernel, n>0 = work-estimate buckets (of 4096 cells) below n use
  *             the thread-per-alignment strip kernel (default 16 = all);  "strip_budget_mb" = device scratch the strip kernel may use;
- *   "search_blocks_per_sm" 8/12/16;  "search_profile", "strip_debug" (diagnostics).
+ *   "search_shared" 1 = the index-search kernel keeps its per-read walk arrays in shared memory when a batch has <= 32 keys per read
+ *             (A/B; measured slower than the per-thread global pool on B200, so off by default);
+ *   "search_profile", "strip_debug" (diagnostics).
  * Results are bit-identical for every setting.  bbm_get_stat keys: "launches", "band_misses" (banded alignments re-run by the
  * row-sequential kernel), "tasks_total", "narrow_tried", "narrow_handed_over", "strip_tasks", "index_build_us". */
 int     bbm_set_option(bbm_ctx* ctx, const char* key, int value);

@@ -68,6 +68,11 @@ def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
         for key in ("nkeys", "offsets", "keyScores", "baseScores"):
             assert np.array_equal(seeds[key], eseeds[key])
         heads, sites = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2)
+        # the same batch with 32 key slots per read through the shared-memory variant of the kernel
+        s32 = {k: (np.ascontiguousarray(v[:, :32]) if getattr(v, "ndim", 1) == 2 else v) for k, v in seeds.items()}
+        if int(seeds["nkeys"].max()) <= 32:
+            h2, t2 = search.search_batch(idx, bases, seeds["baseScores"], off, s32, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, shared=True)
+            assert h2.tobytes() == heads.tobytes() and t2.tobytes() == sites.tobytes()
     finally:
         idx.close()
     for f in ("nsites", "status", "num_hits", "max_score", "max_quick_score", "best_scores"):
