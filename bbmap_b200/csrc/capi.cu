@@ -324,7 +324,12 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
             c->launches += 3;
         }
         c->strip_tasks += nstrip;
-        if (c->strip_debug & 4) { unsigned long long z[2]; CK(cudaMemcpy(z, cb + 220, 16, cudaMemcpyDeviceToHost)); c->strip_units += z[0]; c->strip_lane_iters += z[1]; CK(cudaMemset(cb + 220, 0, 16)); }
+        if (c->strip_debug & 4) {
+            unsigned long long z[2];
+            CK(cudaMemcpyAsync(z, cb + 220, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            c->strip_units += z[0]; c->strip_lane_iters += z[1];
+            CK(cudaMemsetAsync(cb + 220, 0, 16, st));
+        }
     }
     const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
     long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time

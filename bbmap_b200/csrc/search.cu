@@ -39,6 +39,9 @@ struct ReadState {           // where this read's sites go
 // block's sites array (a list is exhausted when row == stop), key offset and key score.  For batches with at most 32 keys per read
 // they live in shared memory, laid out [slot][thread] (bank = thread: conflict-free whatever slot each lane touches); otherwise in a
 // per-thread global pool.  `S` is the slot stride in elements.
+// (a ring in shared memory was measured slower: this kernel lives on L1 hits of its thread-local arrays, and every KB of shared memory
+// is taken from the L1 carve-out)
+constexpr int RING_KEYS = 32, RING_CAP = 2 * RING_KEYS, RING_STRIDE = 1;
 struct ctx_t {
     const SearchIndex* X;
     int K, baseKeyHitScore, indelPenalty, maxPenaltyMisaligned, scoreZ1Key;
@@ -46,6 +49,7 @@ struct ctx_t {
     int S;
     int* values; int* rows; int* stops; short* of; short* ks;
     int* locArray;
+    int* ringV; signed char* ringC;           // [RING_CAP] in the thread's pool block: sorted (value, column) view of the live heads (singleton fast path)
     int status;
     long long tExtend, tPrescan, tWalk, tFilter;      // clock64 per phase (only summed when SearchParams.prof is set)
 };
@@ -54,6 +58,8 @@ struct ctx_t {
 #define STOP(i) c->stops[(i) * c->S]
 #define OFS(i)  ((int)c->of[(i) * c->S])
 #define KSC(i)  ((int)c->ks[(i) * c->S])
+#define RV(p)   c->ringV[(p) * RING_STRIDE]
+#define RC(p)   c->ringC[(p) * RING_STRIDE]
 
 __device__ __forceinline__ int rcomp_fast_dev(int kmer, int k) {     // AminoAcid.reverseComplementBinaryFast (dna/AminoAcid.java:258-271)
     int out = 0;
@@ -337,6 +343,71 @@ __device__ int heap_peek(const ctx_t* c, int numHits) {
     return best;
 }
 
+/* ---------------- exact skip-ahead for long hit lists ----------------
+ * Both walks pop the globally smallest (site, column) one at a time and first count how many list heads lie in
+ * [site - MAX_INDEL, site + MAX_INDEL2]; a site with fewer than approxHitsCutoff such heads changes nothing but the heap
+ * (BBIndex.java:1340-1365, 2352-2376).  All live heads are >= site, heads only grow, and an exhausted list keeps its last value, which
+ * only falls out of range as the walk moves on.  So if no exhausted list is in range now and h_k is the k-th smallest live head, every
+ * site below T = h_k - MAX_INDEL2 sees fewer than k heads in range: with k = approxHitsCutoff those sites are no-ops and the lists can be
+ * advanced to T by binary search instead of one pop at a time.  On a human-sized index (hit lists ~46 long, 18 keys, 2 blocks) this
+ * removes ~99 % of the heap steps of slowWalk3.  In the prescan the cutoff starts at 1; there k = 2 is used: the skipped sites are then
+ * singletons, whose only effect is topQscore = max(topQscore, keyScore + scoreZ1Key) (quickScore/scoreZ2 with one hit, :2490-2492,
+ * 2883), which the caller applies for the one list that moved.  Exhaustion during the skip triggers the same exits as a pop would.
+ * Returns a bit mask: bit 0 = the caller's exhaustion rule fired, bit 1 = at least one list moved; *movedCol = a list that moved. */
+__device__ int skip_ahead(ctx_t* c, const SearchBlock* b, int baseChrom, int numHits, int k, int exitBelow, bool exitOnAnyExhaust,
+                          int* nActive, int* movedCol) {
+    if (k < 2 || *nActive < k) return 0;
+    // smallest live head, and the exhausted lists' stale values
+    int s = 0x7fffffff, staleMax = -0x7fffffff - 1;
+    for (int i = 0; i < numHits; i++) { const int v = VAL(i); if (ROW(i) < STOP(i)) s = imin(s, v); else staleMax = imax(staleMax, v); }
+    if (staleMax >= s - MAX_INDEL) return 0;
+    // k-th smallest live head in (value, column) order: k selection passes from below, or nActive-k+1 passes from above if that is fewer
+    int hk, hkCol;
+    if (k <= *nActive - k + 1) {
+        hk = -0x7fffffff - 1; hkCol = -1;
+        for (int pass = 0; pass < k; pass++) {
+            int best = 0x7fffffff, bestCol = -1;
+            for (int i = 0; i < numHits; i++) {
+                if (ROW(i) >= STOP(i)) continue;
+                const int v = VAL(i);
+                if ((v > hk || (v == hk && i > hkCol)) && (v < best || bestCol < 0)) { best = v; bestCol = i; }
+            }
+            hk = best; hkCol = bestCol;
+        }
+    } else {
+        hk = 0x7fffffff; hkCol = 0x7fffffff;
+        for (int pass = 0; pass < *nActive - k + 1; pass++) {
+            int best = -0x7fffffff - 1, bestCol = -1;
+            for (int i = 0; i < numHits; i++) {
+                if (ROW(i) >= STOP(i)) continue;
+                const int v = VAL(i);
+                if ((v < hk || (v == hk && i < hkCol)) && (v > best || (v == best && i > bestCol) || bestCol < 0)) { best = v; bestCol = i; }
+            }
+            hk = best; hkCol = bestCol;
+        }
+    }
+    if (hk < -0x40000000 + MAX_INDEL2) return 0;
+    const int T = hk - MAX_INDEL2;
+    if (T <= s) return 0;
+    int flags = 0;
+    for (int col = 0; col < numHits; col++) {
+        if (ROW(col) >= STOP(col) || VAL(col) >= T) continue;
+        // first element of the list whose translated value is >= T (the translation is monotone in the raw site)
+        const int ofs = OFS(col);
+        int lo = ROW(col) + 1, hi = STOP(col);
+        while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (site_minus_offset(c, b->sites[mid], ofs, baseChrom) >= T) hi = mid; else lo = mid + 1; }
+        flags |= 2; *movedCol = col;
+        if (lo < STOP(col)) { ROW(col) = lo; VAL(col) = site_minus_offset(c, b->sites[lo], ofs, baseChrom); }
+        else {
+            VAL(col) = site_minus_offset(c, b->sites[STOP(col) - 1], ofs, baseChrom);      // the list keeps its last site
+            ROW(col) = STOP(col);
+            (*nActive)--;
+            if (exitOnAnyExhaust || *nActive < exitBelow) return flags | 1;
+        }
+    }
+    return flags;
+}
+
 /* ---------------- findMaxQscore2 ---------------- */
 __device__ void find_max_qscore2(ctx_t* c, int numHits, int baseChrom_, int prevMaxHits, int earlyExit, int perfectOnly, int* outScore, int* outHits) {
     const int baseChrom = base_chrom(c, baseChrom_);
@@ -347,7 +418,49 @@ __device__ void find_max_qscore2(ctx_t* c, int numHits, int baseChrom_, int prev
     if (perfectOnly) { approxHitsCutoff = numHits; indelCutoff = 0; }
     else { approxHitsCutoff = imax(prevMaxHits, imin(1, numHits - 1)); indelCutoff = MAX_INDEL2; }
     int t, nActive = numHits;
-    while ((t = heap_peek(c, numHits)) >= 0) {
+    long long total = 0;
+    for (int i = 0; i < numHits; i++) total += STOP(i) - ROW(i);
+    const bool longLists = total >= 4LL * numHits;        // skip-ahead only pays when the lists are long
+    int staleMax = -0x7fffffff - 1;          // largest last-site of an exhausted list (it still counts as a hit within MAX_INDEL above it)
+    while (true) {
+        if (longLists && numHits >= 2 && approxHitsCutoff >= 2) {
+            int moved = -1;
+            const int f = skip_ahead(c, b, baseChrom, numHits, approxHitsCutoff, approxHitsCutoff, earlyExit && perfectOnly, &nActive, &moved);
+            if ((f & 1) && earlyExit) { *outScore = topQscore; *outHits = maxHits; return; }
+        } else if (longLists && c->ringV && numHits >= 2 && numHits <= RING_KEYS && nActive >= 2) {
+            // Singleton fast path (cutoff 1: every site is scored).  While the two smallest live heads are more than MAX_INDEL2 apart and
+            // no exhausted list is in range, the smallest head is a site with exactly one hit: quickScore = its key score, scoreZ2 =
+            // scoreZ1Key (BBIndex.java:2490-2492, 2883), approxHits-1 = 0 leaves the cutoff alone.  The live heads are kept sorted in a
+            // small ring (insertion from the back).
+            int front = 0, back = 0;
+            for (int i = 0; i < numHits; i++) {
+                if (ROW(i) >= STOP(i)) { staleMax = imax(staleMax, VAL(i)); continue; }
+                const int v = VAL(i);
+                int p = back++;
+                while (p > front && (RV(p - 1) > v || (RV(p - 1) == v && RC(p - 1) > i))) { RV(p) = RV(p - 1); RC(p) = RC(p - 1); p--; }
+                RV(p) = v; RC(p) = (signed char)i;
+            }
+            while (back - front >= 2 && RV(front) <= 0x7fffffff - MAX_INDEL2 && RV(front + 1) > RV(front) + MAX_INDEL2 && (long long)RV(front) - MAX_INDEL > staleMax) {
+                const int col = RC(front), s0 = RV(front);
+                front++;
+                const int q = KSC(col) + c->scoreZ1Key;
+                if (q > topQscore) { maxHits = imax(1, maxHits); topQscore = q; }
+                const int row = ROW(col) + 1;
+                ROW(col) = row;
+                if (row < STOP(col)) {
+                    const int v = site_minus_offset(c, b->sites[row], OFS(col), baseChrom);
+                    VAL(col) = v;
+                    if (back == RING_CAP) { const int n = back - front; for (int i = 0; i < n; i++) { RV(i) = RV(front + i); RC(i) = RC(front + i); } front = 0; back = n; }
+                    int p = back++;
+                    while (p > front && (RV(p - 1) > v || (RV(p - 1) == v && RC(p - 1) > col))) { RV(p) = RV(p - 1); RC(p) = RC(p - 1); p--; }
+                    RV(p) = v; RC(p) = (signed char)col;
+                } else {
+                    nActive--; staleMax = imax(staleMax, s0);          /* VAL(col) keeps its last site */
+                    if (earlyExit && nActive < approxHitsCutoff) { *outScore = topQscore; *outHits = maxHits; return; }
+                }
+            }
+        }
+        if ((t = heap_peek(c, numHits)) < 0) break;
         const int site = VAL(t), centerIndex = t;
         int approxHits = 0;
         {
@@ -407,7 +520,15 @@ __device__ void slow_walk3(ctx_t* c, const int8_t* bases, const int8_t* baseScor
     int* locArray = c->locArray;
     int prev = -1;       /* index of prevSS in R->sites (a site made during THIS walk), -1 = null */
     int t, quit = 0, nActive = numHits;
-    while (!quit && (t = heap_peek(c, numHits)) >= 0) {
+    long long total = 0;
+    for (int i = 0; i < numHits; i++) total += STOP(i) - ROW(i);
+    const bool longLists = total >= 4LL * numHits;
+    while (!quit) {
+        if (longLists) {
+            int moved = -1;
+            if (skip_ahead(c, b, baseChrom, numHits, approxHitsCutoff, approxHitsCutoff, false, &nActive, &moved) & 1) break;
+        }
+        if ((t = heap_peek(c, numHits)) < 0) break;
         const int site = VAL(t), centerIndex = t;
         int maxNearbySite = site, approxHits = 0;
         {
@@ -757,8 +878,8 @@ struct SearchParams {
 
 constexpr int SEARCH_THREADS = 64;
 constexpr int SEARCH_FAST_KEYS = 32;           // batches with at most this many keys per read keep the walk arrays in shared memory
-// per-thread block in the global pool: locArray[608] int, basesM[608], baseScoresM[608], then (slow path only) the walk arrays for 96 keys
-constexpr size_t SEARCH_POOL_FIXED = (size_t)SEARCH_MAX_READ * 4 + 2 * SEARCH_MAX_READ;
+// per-thread block in the global pool: locArray[608] int, basesM[608], baseScoresM[608], then (pool variant only) the walk arrays for 96 keys
+constexpr size_t SEARCH_POOL_FIXED = (size_t)SEARCH_MAX_READ * 4 + 2 * SEARCH_MAX_READ + (size_t)RING_CAP * 4 + RING_CAP;
 constexpr size_t SEARCH_POOL_BYTES = SEARCH_POOL_FIXED + (size_t)MAXK * (3 * 4 + 2 * 2);
 
 template <bool SHARED>
@@ -772,6 +893,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SHARED ? 7 : 8) search_kernel(
     c->locArray = (int*)mine;
     int8_t* basesM = (int8_t*)(mine + (size_t)SEARCH_MAX_READ * 4);
     int8_t* baseScoresM = basesM + SEARCH_MAX_READ;
+    c->ringV = (int*)(baseScoresM + SEARCH_MAX_READ); c->ringC = (signed char*)(c->ringV + RING_CAP);
     if (SHARED) {
         c->S = SEARCH_THREADS;
         c->values = sVal + threadIdx.x; c->rows = sRow + threadIdx.x; c->stops = sStop + threadIdx.x; c->of = sOf + threadIdx.x; c->ks = sKs + threadIdx.x;

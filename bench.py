@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 from bbmap_b200 import workloads as wl  # noqa: E402
 
 GENOME_LEN = 4_600_000      # "E. coli-sized" resident reference the windows point into
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (msa_strip_fill_kernel) per launch, from the committed ncu captures
+# (profiles/): keyed by alignments per step
+TRAFFIC_NCU = {800_000: 22.84e9, 1_600_000: 48.97e9}
 METRIC = "MSA fill GCUPS (MultiStateAligner11ts fillLimited+score+traceback, reference cell count / s)"
 
 
@@ -218,6 +221,15 @@ def main():
         step_dev()
     outs = np.frombuffer(d_outs.cpu().numpy().tobytes(), dtype=wl.OUT_DTYPE)
     cells_per_step = int(outs["iterations"].sum())
+    # one untimed step with the kernels' own work counters on: cells actually evaluated (strip kernel: rows of 8 cells; narrow kernel: 16
+    # diagonals per row of every alignment that tried it), for the integer-issue roofline below
+    msa.set_option("strip_debug", 4)
+    u0, n0 = msa.stat("strip_units"), msa.stat("narrow_tried")
+    step_dev()
+    tried = msa.stat("narrow_tried") - n0
+    evaluated_cells = 8 * (msa.stat("strip_units") - u0) + 16 * int(tasks["read_len"].mean()) * tried
+    strip_lane_util = (msa.stat("strip_units") - u0) / max(1, msa.stat("strip_lane_iters"))
+    msa.set_option("strip_debug", 0)
     assert (outs["status"] == 0).all(), "bench: some alignments returned an error status"
     sampler = ClockSampler(local)
     sampler.start()
@@ -279,8 +291,16 @@ def main():
                            "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "strip_units": msa.stat("strip_units"), "strip_lane_iters": msa.stat("strip_lane_iters"), "band_misses": msa.stat("band_misses")},
             "clocks": clocks,
             "int_peaks_glops": int_peaks,
+            "roofline_int": {"bound": "integer ALU issue (compare/select/min-max/logic; 64 lanes/clk/SM)",
+                             "evaluated_cells_per_s": evaluated_cells * world / step_s,
+                             "floor_lane_ops_per_cell": 45, "achieved": evaluated_cells * world / step_s * 45 / 1e9,
+                             "peak": 2 * int_peaks.get("cmp_select", 0.0) * world, "unit": "G lane-ops/s",
+                             "frac": (evaluated_cells / step_s * 45 / 1e9) / max(1e-9, 2 * int_peaks.get("cmp_select", 0.0)),
+                             "strip_lane_utilisation": strip_lane_util,
+                             "note": "achieved = cells the kernels evaluate x the 45-op floor of the 3-state recurrence (SURVEY 8d); peak = measured "
+                                     "compare+select issue rate of this GPU (bbm_int_peak); the kernels spend ~150 instructions per cell today"},
             "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
-                         "traffic": None, "peak_kind": pk_kind,
+                         "traffic": TRAFFIC_NCU.get(args.tasks), "peak_kind": pk_kind,
                          "note": "integer-issue-bound DP: algorithmic bytes/cell ~0.1; see DESIGN.md for the issue-slot roofline"}}
     if not args.no_stages:
         # the other kernels of the path on configs[1]-shaped input, each against the HBM roofline

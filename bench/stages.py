@@ -26,6 +26,12 @@ MAXK = 32          # slots per read for offsets/keys/keyScores (18 keys at 150 b
 MAX_SITES = 16
 
 
+def _nsites(L, h, block):
+    n = C.c_int64(0)
+    _lib.check(L.bbm_index_block_sites(h, block, C.byref(n)), "bbm_index_block_sites")
+    return n.value
+
+
 def cpu_side(R, cb, co, n_cpu=20000):
     """The same stages through the CPU oracle (C restatements, one host thread) on the first n_cpu reads — a reported baseline."""
     from oracle import oracle as orc
@@ -49,23 +55,37 @@ def cpu_side(R, cb, co, n_cpu=20000):
     return out
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False, cpu=True, search_bps=0):
+def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_peak=6549.4, quit2=False, cpu=True, search_bps=0, scaffolds=1):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
     torch.cuda.set_device(device)
-    genome = wl.random_genome(genome_len, seed=1)
-    cb, co, table = pack_chromosomes([genome])
+    if scaffolds <= 1:
+        scafs = [wl.random_genome(genome_len, seed=1)]
+    else:
+        # G3: `scaffolds` random scaffolds of unequal size + 1 % of the bases in planted 300-bp repeat families of 100 copies
+        rng = np.random.Generator(np.random.PCG64(3))
+        w = rng.uniform(0.4, 2.0, size=scaffolds); sizes = np.maximum(1000, (w / w.sum() * genome_len).astype(np.int64))
+        scafs = [wl.ACGT[rng.integers(0, 4, size=int(z), dtype=np.uint8)] for z in sizes]
+        fam = max(1, int(genome_len * 0.01 / 300 / 100))
+        for _ in range(fam):
+            unit = wl.ACGT[rng.integers(0, 4, size=300, dtype=np.uint8)]
+            for _c in range(100):
+                sc = scafs[int(rng.integers(0, scaffolds))]
+                p = int(rng.integers(0, len(sc) - 300)); sc[p:p + 300] = unit
+    cb, co, table = pack_chromosomes(scafs)
+    del scafs
     R = wl.make_mapping_reads(cb, co, table, pairs, seed=2)
     n = 2 * pairs
     nb = len(R["bases"])
-    out = {"workload": "configs[1]-shaped: %d bp random reference (1 scaffold), %d pairs 2x150, 1%% subs, 1-3 bp indel in ~50%% of reads, Q30" % (genome_len, pairs),
+    out = {"workload": "%d bp random reference (%d scaffold(s), %d chromosome array(s)%s), %d pairs 2x150, 1%% subs, 1-3 bp indel in ~50%% of reads, Q30"
+                       % (genome_len, scaffolds, len(co) - 1, ", 1% planted repeats" if scaffolds > 1 else "", pairs),
            "reads": n}
     t0 = time.perf_counter()
     idx = BBIndexCUDA(cb, co, keylen=13, device=device)
     torch.cuda.synchronize()
     L.bbm_get_stat.restype = C.c_int64
-    out["index_build"] = {"ms": L.bbm_get_stat(idx.h, b"index_build_us") / 1e3, "ms_with_upload_and_context": 1e3 * (time.perf_counter() - t0), "sites": int(idx.download(0)[1].size),
+    out["index_build"] = {"ms": L.bbm_get_stat(idx.h, b"index_build_us") / 1e3, "ms_with_upload_and_context": 1e3 * (time.perf_counter() - t0), "sites": int(sum(_nsites(L, idx.h, b) for b in range(idx.nblocks))), "blocks": idx.nblocks, "chrombits": int(idx.cfg["chrombits"][0]),
                           "note": "bbm_index_build with the reference resident: emit + radix sort + scan + analyzeIndex (COUNTS, clumpy keys, lengthHistogram), host-timed around a stream sync"}
     h = idx.h
     pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
@@ -114,9 +134,12 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     bi = sc.argmax(axis=1); best = sites[np.arange(n), bi]
     correct = (ns > 0) & (best["chrom"] == tr[:, 0]) & (best["strand"] == tr[:, 1]) & ((np.abs(best["start"] - tr[:, 2]) <= 8) | (np.abs(best["stop"] - tr[:, 3]) <= 8))
     # algorithmic bytes: COUNTS gathers 4/key + per strand (starts pair 8 + list 4*len) for prescan and walk + ~2*(L+k) reference bytes per extended key
-    counts = idx.download(0)[2]
+    counts = idx.download(0)[2] if idx.nblocks == 1 else None
     keys = d_keys.cpu().numpy().reshape(n, MAXK)
     valid = np.arange(MAXK)[None, :] < np.maximum(nk, 0)[:, None]
+    if counts is None:       # several blocks: COUNTS is global, fetch it without the block's sites
+        counts = np.zeros(1 << 26, np.int32)
+        _lib.check(L.bbm_index_download(h, 0, None, None, counts.ctypes.data_as(C.c_void_p), None), "bbm_index_download")
     listlen = np.where(valid & (keys >= 0), counts[np.maximum(keys, 0)], 0).astype(np.int64)
     alg = int(valid.sum()) * 4 + 2 * (int(valid.sum()) * 2 * 8 + int(listlen.sum()) * 4) + int(valid.sum()) * (150 + 13) + n * (300 + 48) + int(ns.sum()) * 64
     out["search"] = {"ms": t, "reads_per_s": n / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak,
@@ -170,12 +193,13 @@ def main():
     ap.add_argument("--pairs", type=int, default=200_000)
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--scaffolds", type=int, default=1)
     ap.add_argument("--search-bps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
-    print(json.dumps(run(a.pairs, a.genome, a.reps, hbm_peak=hbm, search_bps=a.search_bps, cpu=not a.no_cpu)))
+    print(json.dumps(run(a.pairs, a.genome, a.reps, hbm_peak=hbm, search_bps=a.search_bps, cpu=not a.no_cpu, scaffolds=a.scaffolds)))
 
 
 if __name__ == "__main__":

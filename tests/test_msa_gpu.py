@@ -239,3 +239,35 @@ def test_gapped_reference_parity(oracle):
             ngapped_ok += 1
             assert (match == ord("D")).sum() >= 128          # an intron went through '-' symbols
     assert ngapped_ok >= 100
+
+
+def test_large_batch_routings_agree(oracle):
+    """200 k alignments of the bench workload (G4): the strip routing, the tiled routing and the mixed one are three different
+    decompositions of the same fill — all results and match strings must be byte-identical; a 10 k sample is also checked against
+    the oracle.  Covers multi-task-per-thread refill and the longest-first ordering, which small batches do not exercise."""
+    from bbmap_b200.msa import MultiStateAligner11tsCUDA
+    genome = wl.random_genome(300000, seed=77)
+    reads, tasks = wl.make_msa_tasks(genome, 200000, seed=78, flags=wl.TF_SCORE | wl.TF_TRACEBACK)
+    moff = wl.match_offsets(tasks)
+    res = []
+    for strip, narrow in ((16, 1000), (0, 1), (3, 1), (16, 0)):
+        m = MultiStateAligner11tsCUDA()
+        try:
+            m.set_option("strip", strip); m.set_option("narrow", narrow)
+            d_ref = m.load_reference(genome)
+            outs, mb = m.align_batch(reads, d_ref, tasks, match_off=moff)
+            res.append((outs.tobytes(), mb.tobytes(), m.stat("strip_tasks")))
+        finally:
+            m.close()
+    assert res[0][2] > 50000 and res[1][2] == 0 and res[3][2] > 150000
+    for r in res[1:]:
+        assert r[0] == res[0][0] and r[1] == res[0][1]
+    n = 10000
+    exp, emb, _ = oracle.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], threads=8)
+    got = np.frombuffer(res[0][0], dtype=wl.OUT_DTYPE)[:n]
+    assert got.tobytes() == exp.tobytes()
+    gm = np.frombuffer(res[0][1], dtype=np.int8)
+    for i in range(n):
+        k = exp[i]["match_len"]
+        if k > 0:
+            assert gm[moff[i]:moff[i] + k].tobytes() == emb[moff[i]:moff[i] + k].tobytes()

@@ -50,7 +50,9 @@ def _make(seed, sizes, n, L, k, paired=False, repeats=True, chrombits=-1, max_le
     return cb, co, bases, qual, off, truth
 
 
-@pytest.mark.parametrize("sizes,k,L,chrombits,maxlen", [((150000, 40000), 13, 150, -1, None), ((60000,) * 4, 11, 100, 1, 90000), ((30000,), 10, 250, 0, None)])
+# the last two have hit lists of ~6 and ~2 sites per key: they exercise the exact skip-ahead of the walks (long lists), one of them with two index blocks
+@pytest.mark.parametrize("sizes,k,L,chrombits,maxlen", [((150000, 40000), 13, 150, -1, None), ((60000,) * 4, 11, 100, 1, 90000), ((30000,), 10, 250, 0, None),
+                                                        ((1500000,), 9, 150, -1, None), ((700000,) * 3, 10, 100, 1, 1000000)])
 @pytest.mark.parametrize("quit2", [True, False])
 def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
     from bbmap_b200.index import BBIndexCUDA
