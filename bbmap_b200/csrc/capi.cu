@@ -57,6 +57,10 @@ extern "C" int bbm_launch_gref_translate(const bbm_gapped_task* gt, long long n,
 extern "C" int bbm_ingest_threads();
 extern "C" int bbm_launch_ingest(int8_t* bases, int8_t* quality, const long long* read_off, long long nreads, int8_t* basesM, int* readFlags,
                                  int flags, int readsPerBlock, int stageBytes, int blocks, cudaStream_t st);
+extern "C" int bbm_sam_upload_table(const float* log2tab);
+extern "C" int bbm_sam_log2_tab();
+extern "C" int bbm_launch_sam(const bbm_sam_task* tasks, long long n, const int8_t* match_buf, const int* scaf_off, const int* scaf_loc, const int* scaf_len,
+                              int nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* outs, int8_t* cigar_buf, const long long* cigar_off, cudaStream_t st);
 extern "C" int bbm_search_threads();
 extern "C" size_t bbm_search_pool_bytes();
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
@@ -127,6 +131,7 @@ struct bbm_ctx {
     const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;
     void* d_icfg = nullptr; void* d_iblocks = nullptr; int* d_ihist = nullptr; long long* d_chrom_off = nullptr;
     DevBuf searchCtx, searchRev, d_srch[8];
+    DevBuf d_sam[8]; bool sam_table = false;   // staging for bbm_sam_batch_host
     DevBuf d_ing[5];   // staging for bbm_ingest_batch_host
     DevBuf grefPool, grefInfo, grefTasks, d_gtasks, d_gaps;   // gapped references (a15)   // staging for the host-buffer entry point
     PinBuf h_stage;
@@ -175,7 +180,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); for (auto& b : c->d_sam) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1039,6 +1044,76 @@ extern "C" int bbm_ingest_batch_host(bbm_ctx* c, int8_t* bases, int8_t* quality,
     if (quality) CK(cudaMemcpyAsync(quality, B[1].p, nb, cudaMemcpyDeviceToHost, st));
     if (basesM) CK(cudaMemcpyAsync(basesM, B[3].p, nb, cudaMemcpyDeviceToHost, st));
     if (read_flags) CK(cudaMemcpyAsync(read_flags, B[4].p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+
+// =====================  SAM record fields (SamLine)  =====================
+static int run_sam(bbm_ctx* c, const bbm_sam_task* dt, int64_t n, const int8_t* dm, const int* dso, const int* dsl, const int* dsn, int nchroms,
+                   const bbm_sam_cfg* cfg, bbm_sam_out* dout, int8_t* dcb, const int64_t* dco, cudaStream_t st, float* ms_out) {
+    if (n <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (!c->sam_table) {
+        // (float)Tools.log2(length) of SamLine.toMapq, computed with the host libm (the same call the oracle makes)
+        std::vector<float> tab(bbm_sam_log2_tab());
+        for (size_t i = 0; i < tab.size(); ++i) tab[i] = i == 0 ? 0.f : (float)(log((double)i) * (1 / log(2.0)));
+        int e0 = bbm_sam_upload_table(tab.data());
+        if (e0) return fail(BBM_E_CUDA, "sam log2 table", (cudaError_t)e0);
+        c->sam_table = true;
+    }
+    CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_sam(dt, n, dm, dso, dsl, dsn, nchroms, cfg, dout, dcb, (const long long*)dco, st);
+    if (e) return fail(BBM_E_CUDA, "sam_kernel launch", (cudaError_t)e);
+    c->launches++;
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+
+extern "C" int bbm_sam_batch_dev(bbm_ctx* c, const bbm_sam_task* d_tasks, int64_t n, const int8_t* d_match_buf, const int32_t* d_scaf_off,
+                                 const int32_t* d_scaf_loc, const int32_t* d_scaf_len, int32_t nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* d_outs,
+                                 int8_t* d_cigar_buf, const int64_t* d_cigar_off, void* stream, float* kernel_ms_out) {
+    if (!c || !d_tasks || !d_match_buf || !d_scaf_off || !d_scaf_loc || !d_scaf_len || !cfg || !d_outs || !d_cigar_buf || !d_cigar_off || nchroms < 1)
+        return fail(BBM_E_ARG, "bbm_sam_batch_dev: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_sam(c, d_tasks, n, d_match_buf, d_scaf_off, d_scaf_loc, d_scaf_len, nchroms, cfg, d_outs, d_cigar_buf, d_cigar_off,
+                   stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+
+extern "C" int bbm_sam_batch_host(bbm_ctx* c, const bbm_sam_task* tasks, int64_t n, const int8_t* match_buf, int64_t match_bytes, const int32_t* scaf_off,
+                                  const int32_t* scaf_loc, const int32_t* scaf_len, int32_t nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* outs,
+                                  int8_t* cigar_buf, const int64_t* cigar_off) {
+    if (!c || !tasks || !match_buf || !scaf_off || !scaf_loc || !scaf_len || !cfg || !outs || !cigar_buf || !cigar_off || nchroms < 1 || match_bytes < 0)
+        return fail(BBM_E_ARG, "bbm_sam_batch_host: bad argument");
+    if (n <= 0) return BBM_OK;
+    for (int64_t i = 0; i < n; ++i) {
+        const bbm_sam_task& t = tasks[i];
+        if (t.mate >= n || t.match_len < 0 || t.match_off < 0 || t.match_off + t.match_len > match_bytes) return fail(BBM_E_ARG, "bbm_sam_batch_host: record outside the buffers");
+        if ((t.flags & BBM_RF_MAPPED) && (t.chrom < 1 || t.chrom > nchroms)) return fail(BBM_E_ARG, "bbm_sam_batch_host: chromosome out of range");
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int nscaf = scaf_off[nchroms];
+    const size_t cb = (size_t)cigar_off[n];
+    DevBuf* B = c->d_sam;   // 0 tasks, 1 match, 2 scaf_off, 3 scaf_loc, 4 scaf_len, 5 outs, 6 cigar, 7 cigar_off
+    if (B[0].ensure((size_t)n * sizeof(bbm_sam_task)) || B[1].ensure((size_t)match_bytes + 16) || B[2].ensure((size_t)(nchroms + 1) * 4) ||
+        B[3].ensure((size_t)nscaf * 4 + 16) || B[4].ensure((size_t)nscaf * 4 + 16) || B[5].ensure((size_t)n * sizeof(bbm_sam_out)) || B[6].ensure(cb + 16) ||
+        B[7].ensure((size_t)(n + 1) * 8))
+        return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(B[0].p, tasks, (size_t)n * sizeof(bbm_sam_task), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[1].p, match_buf, (size_t)match_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[2].p, scaf_off, (size_t)(nchroms + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[3].p, scaf_loc, (size_t)nscaf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[4].p, scaf_len, (size_t)nscaf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[7].p, cigar_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(B[6].p, 0, cb, st));
+    int rc = run_sam(c, (const bbm_sam_task*)B[0].p, n, (const int8_t*)B[1].p, (const int*)B[2].p, (const int*)B[3].p, (const int*)B[4].p, nchroms, cfg,
+                     (bbm_sam_out*)B[5].p, (int8_t*)B[6].p, (const int64_t*)B[7].p, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outs, B[5].p, (size_t)n * sizeof(bbm_sam_out), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cigar_buf, B[6].p, cb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return BBM_OK;
 }

@@ -244,6 +244,48 @@ int  bbm_banded_batch_dev(bbm_ctx* ctx, const int8_t* d_queries, const int8_t* d
 int  bbm_banded_batch_host(bbm_ctx* ctx, const int8_t* queries, int64_t query_bytes, const int8_t* refs, int64_t ref_bytes,
                            const bbm_band_task* tasks, bbm_band_out* outs, int64_t ntasks);
 
+/* ---- SAM record fields of mapped reads: SamLine(Read,int) (current/stream/SamLine.java:82-330) with toCigar13/toCigar14 (:600-750),
+ * makeFlag (:2134-2151), toMapq (:1709-1723) and the scaffold lookups of dna/Data.java:1089-1140.  One record per read as the mapper
+ * leaves it; mates point at each other through `mate`.  Match strings are long-format (m S N I D X Y C B s), in reference order. ---- */
+#define BBM_RF_MAPPED     1
+#define BBM_RF_MINUS      2    /* r.strand()==Gene.MINUS */
+#define BBM_RF_PERFECT    4
+#define BBM_RF_AMBIGUOUS  8
+#define BBM_RF_SECONDARY  16
+#define BBM_RF_DISCARDED  32
+#define BBM_RF_PAIRED     64   /* r.paired(): the pairing logic accepted the pair */
+#define BBM_RF_PAIRNUM1   128  /* r.pairnum()==1 (second fragment) */
+typedef struct {                /* 48 bytes */
+    int64_t match_off;          /* byte offset of the match string in the match buffer */
+    int32_t match_len;          /* 0 = r.match==null */
+    int32_t chrom, start, stop; /* chromosome-array coordinates, chrom 1-based (r.chrom, r.start, r.stop) */
+    int32_t read_len;           /* r.length() */
+    int32_t score;              /* r.mapScore */
+    int32_t mate;               /* index of the mate's record in this batch, -1 = r.mate==null */
+    int32_t flags;              /* BBM_RF_* */
+    int32_t pad_;
+} bbm_sam_task;
+typedef struct {                /* 32 bytes */
+    int32_t flag, pos, mapq;    /* FLAG, POS (1-based, scaffold-relative), MAPQ */
+    int32_t scaffold;           /* RNAME as an index into the scaffold table, -1 = '*' */
+    int32_t rnext;              /* -1 = '*', -2 = '=', else scaffold index */
+    int32_t pnext, tlen;
+    int32_t cigar_len;          /* -1 = '*' (null cigar), -2 = invalid match character (the reference throws) */
+} bbm_sam_out;
+typedef struct {                /* 32 bytes; defaults: SamLine.VERSION=1.4, SOFT_CLIP=true, INTRON_LIMIT=Integer.MAX_VALUE, PENALIZE_AMBIG=true (:2424-2434);
+                                   inter_scaffold_padding = Data.interScaffoldPadding = FastaToChromArrays2.MID_PADDING = 300 */
+    int32_t version14, soft_clip, intron_limit, penalize_ambig, inter_scaffold_padding, pad_[3];
+} bbm_sam_cfg;
+/* Scaffold table (dna/Data.scaffoldLocs / scaffoldLengths): scaffolds of chromosome c (1-based) are entries scaf_off[c-1] .. scaf_off[c]-1 of
+ * scaf_loc (start inside the chromosome array, ascending) and scaf_len.  cigar i is written at cigar_buf + cigar_off[i] (capacity
+ * 2*match_len+12 is always enough). */
+int  bbm_sam_batch_dev(bbm_ctx* ctx, const bbm_sam_task* d_tasks, int64_t n, const int8_t* d_match_buf, const int32_t* d_scaf_off,
+                       const int32_t* d_scaf_loc, const int32_t* d_scaf_len, int32_t nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* d_outs,
+                       int8_t* d_cigar_buf, const int64_t* d_cigar_off, void* stream, float* kernel_ms_out);
+int  bbm_sam_batch_host(bbm_ctx* ctx, const bbm_sam_task* tasks, int64_t n, const int8_t* match_buf, int64_t match_bytes, const int32_t* scaf_off,
+                        const int32_t* scaf_loc, const int32_t* scaf_len, int32_t nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* outs,
+                        int8_t* cigar_buf, const int64_t* cigar_off);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

@@ -205,6 +205,17 @@ class Oracle:
         finally:
             L.orc_msa_free(m)
 
+    # ---------------- SAM record fields (SamLine) ----------------
+    def sam_batch(self, tasks, match_buf, scaf, cfg):
+        from bbmap_b200.sam import SAM_OUT_DTYPE, SAM_TASK_DTYPE, cigar_offsets
+        tasks = np.ascontiguousarray(tasks, SAM_TASK_DTYPE); mb = np.ascontiguousarray(match_buf).view(np.int8)
+        so, sl, sn = (np.ascontiguousarray(x, np.int32) for x in scaf)
+        coff = cigar_offsets(tasks)
+        outs = np.zeros(len(tasks), SAM_OUT_DTYPE); cbuf = np.zeros(max(int(coff[-1]), 1), np.int8)
+        self.lib.orc_sam_batch.restype = None
+        self.lib.orc_sam_batch(_p(tasks), C.c_int64(len(tasks)), _p(mb), _p(so), _p(sl), _p(sn), C.c_int32(len(so) - 1), _p(cfg), _p(outs), _p(cbuf), _p(coff))
+        return outs, cbuf, coff
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
