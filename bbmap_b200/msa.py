@@ -85,7 +85,7 @@ class MultiStateAligner11tsCUDA:
         return int(self.L.bbm_launch_count(self.h))
 
     # -- the batched plug-in call (host buffers in, host buffers out) --
-    def align_batch(self, reads, d_ref, tasks, match_off=None, outs=None, mbuf=None):
+    def align_batch(self, reads, d_ref, tasks, match_off=None, outs=None, mbuf=None, account=True):
         """Runs every task (see include/bbmap_cuda.h: bbm_msa_task) and returns (outs, match_buf).
         tasks['flags'] selects fillLimited (Java rule), raw fillLimitedX or raw fillUnlimited, and whether
         score2 / traceback2 follow."""
@@ -101,9 +101,10 @@ class MultiStateAligner11tsCUDA:
         moff = np.ascontiguousarray(match_off, np.int64) if want_tb else None
         _lib.check(self.L.bbm_msa_batch_host(self.h, _p(reads), reads.size, d_ref, _p(tasks), _p(outs), len(tasks),
                                             _p(mbuf) if want_tb else None, _p(moff) if want_tb else None), "bbm_msa_batch_host")
-        lim = outs["path"] == 0
-        self.iterationsLimited += int(outs["iterations"][lim].sum())
-        self.iterationsUnlimited += int(outs["iterations"][~lim].sum())
+        if account:           # the reference's iterationsLimited / iterationsUnlimited counters (MSA.java:866-867)
+            lim = outs["path"] == 0
+            self.iterationsLimited += int(outs["iterations"][lim].sum())
+            self.iterationsUnlimited += int(outs["iterations"][~lim].sum())
         return outs, mbuf
 
     def align_batch_gapped(self, reads, d_ref, gtasks, gaps, match_off):

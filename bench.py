@@ -251,24 +251,29 @@ def main():
     reads_p = pin(reads); tasks_p = pin(tasks.view(np.uint8)).view(wl.TASK_DTYPE); moff_p = pin(moff)
     outs_p = pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE)
     mbuf_p = pin(np.zeros(int(moff[-1]), np.int8))
-    # Two batches in flight, the way the reference keeps one MSA per mapping thread (AbstractMapThread.java:133-136): two host threads, each
-    # with its own context, staging buffers and pinned result buffers, alternate over the steps, so the copies of one batch overlap the
-    # kernels of the other.  Every step still pays its own H2D of tasks+reads and D2H of results+match strings inside the timed region.
+    # Several batches in flight (default 3), the way the reference keeps one MSA per mapping thread (AbstractMapThread.java:133-136): one
+    # host thread per batch, each with its own context, staging buffers and pinned result buffers, so the copies of one batch overlap
+    # the kernels of the others.  Every step still pays its own H2D of tasks+reads and D2H of results+match strings inside the timed region.
     msa_b = MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio)
     outs_q = pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE)
     mbuf_q = pin(np.zeros(int(moff[-1]), np.int8))
     lanes = [(msa, outs_p, mbuf_p), (msa_b, outs_q, mbuf_q)]
+    nfl = int(os.environ.get("BBM_E2E_IN_FLIGHT", "3"))
+    extra = []
+    for _k in range(nfl - 2):
+        extra.append(MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio))
+        lanes.append((extra[-1], pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE), pin(np.zeros(int(moff[-1]), np.int8))))
     for m_, o_, b_ in lanes:
         m_.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=o_, mbuf=b_)
     barrier()
-    e2e_steps = 2 * max(1, min(args.steps, 4) // 2)
+    e2e_steps = nfl * max(1, min(args.steps, 6) // nfl)
 
     def e2e_worker(k):
         m_, o_, b_ = lanes[k]
-        for _ in range(e2e_steps // 2):
-            m_.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=o_, mbuf=b_)
+        for _ in range(e2e_steps // nfl):
+            m_.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=o_, mbuf=b_, account=False)
 
-    workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(2)]
+    workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(nfl)]
     t0 = time.perf_counter()
     for w_ in workers:
         w_.start()
@@ -279,6 +284,8 @@ def main():
     h_outs = outs_p
     assert outs_q.tobytes() == outs.tobytes(), "second in-flight batch disagrees with the resident path"
     msa_b.close()
+    for m_ in extra:
+        m_.close()
     clocks = sampler.finish()
     assert h_outs.tobytes() == outs.tobytes(), "host-buffer path and resident path disagree"
 
@@ -305,7 +312,7 @@ def main():
             "alignments_per_s": len(tasks) * world / step_s,
             "computed_cells_gcups": float((tasks["read_len"].astype(np.int64) * cols).sum()) * world / step_s / 1e9,
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_step, "batches_in_flight": 2},
+                    "ms_per_step": e2e_ms_step, "batches_in_flight": nfl},
             "gpu_launches": int(launches),
             "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
                            "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "strip_units": msa.stat("strip_units"), "strip_lane_iters": msa.stat("strip_lane_iters"), "band_misses": msa.stat("band_misses")},
