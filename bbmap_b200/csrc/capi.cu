@@ -63,11 +63,13 @@ extern "C" int bbm_launch_sam(const bbm_sam_task* tasks, long long n, const int8
                               int nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* outs, int8_t* cigar_buf, const long long* cigar_off, cudaStream_t st);
 extern "C" int bbm_search_threads();
 extern "C" size_t bbm_search_pool_bytes();
+extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks);
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
                                  int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* pool,
-                                 unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, cudaStream_t st);
+                                 unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, int phases, int* mid, int midStride,
+                                 cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
 extern "C" int bbm_msa_warps_per_block();
@@ -116,7 +118,7 @@ struct bbm_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0;
+    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 0;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
@@ -386,6 +388,7 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }
+    if (!strcmp(key, "search_split")) { c->search_split = value; return BBM_OK; }
     if (!strcmp(key, "search_profile")) { c->search_prof = value; return BBM_OK; }
     if (!strcmp(key, "search_shared")) { c->search_shared = value; return BBM_OK; }     // 1 = walk arrays in shared memory when a batch has <=32 keys per read (A/B: measured slower)
     if (!strcmp(key, "strip_budget_mb")) { c->strip_budget = (size_t)value << 20; return BBM_OK; }
@@ -1131,14 +1134,30 @@ static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int
     (void)maxReadLen;     // reserved: lets a later kernel size its per-read working set to the batch
     if (c->searchCtx.ensure((size_t)c->sms * 8 * T * bbm_search_pool_bytes())) return fail(BBM_E_CUDA, "cudaMalloc search scratch");
     unsigned int* cb = (unsigned int*)c->counters.p;
-    CK(cudaMemsetAsync(cb + 202, 0, 4, st));
     if (c->search_prof) CK(cudaMemsetAsync(cb + 208, 0, 40, st));
+    unsigned long long* prof = c->search_prof ? (unsigned long long*)(cb + 208) : nullptr;
+    const int nblk = (int)c->iblocks.size(), nchr = (int)c->chrom_off.size() - 1;
     CK(cudaEventRecord(c->ev0, st));
-    int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, (int)c->iblocks.size(), (int)c->chrom_off.size() - 1, c->d_counts, c->d_ihist,
-                              c->d_chroms, c->d_chrom_off, db, dbs, (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites,
-                              c->searchCtx.p, cb + 202, c->search_prof ? (unsigned long long*)(cb + 208) : nullptr, blocks, c->search_shared ? 0 : 1, st);
-    if (e) return fail(BBM_E_CUDA, "search_kernel launch", (cudaError_t)e);
-    c->launches++;
+    if (c->search_split) {
+        // one phase of BBIndex.find per launch (key filtering, prescan, walk): all lanes of a warp run the same phase
+        const int stride = bbm_search_mid_stride(maxKeys, nblk);
+        if (c->searchRev.ensure((size_t)nreads * stride * 4)) return fail(BBM_E_CUDA, "cudaMalloc search phase state");
+        for (int ph = 1; ph <= 4; ph <<= 1) {
+            CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+            int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, c->d_ihist, c->d_chroms, c->d_chrom_off, db, dbs,
+                                      (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites, c->searchCtx.p, cb + 202, prof, blocks,
+                                      c->search_shared ? 0 : 1, ph, (int*)c->searchRev.p, stride, st);
+            if (e) return fail(BBM_E_CUDA, "search_kernel launch", (cudaError_t)e);
+            c->launches++;
+        }
+    } else {
+        CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+        int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, c->d_ihist, c->d_chroms, c->d_chrom_off, db, dbs,
+                                  (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites, c->searchCtx.p, cb + 202, prof, blocks,
+                                  c->search_shared ? 0 : 1, 7, nullptr, 0, st);
+        if (e) return fail(BBM_E_CUDA, "search_kernel launch", (cudaError_t)e);
+        c->launches++;
+    }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaStreamSynchronize(st));
     if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }

@@ -750,9 +750,13 @@ __device__ int8_t comp_base(int8_t b) {     /* baseToComplementExtended for the 
 
 
 // ---------------- BBIndex.find for one read (current/align2/BBIndex.java:403-639) ----------------
+// `phases`: 1 = key filtering, 2 = prescan, 4 = walk.  7 runs BBIndex.find in one go; the split launches run one phase per kernel and carry
+// the state between them in `mid` (int[midStride] per read: header, the filtered key arrays of both strands, the per-cycle prescan
+// results), so that all lanes of a warp execute the same phase.
+constexpr int MID_HDR = 24;
 __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len, const int8_t* baseScoresP, const int* offsetsIn,
                             const int* keyScoresIn, int nkeys, int quitAfterTwoPerfects, bbm_search_head* H, ReadState* R, ctx_t* c,
-                            int8_t* basesM, int8_t* baseScoresM) {
+                            int8_t* basesM, int8_t* baseScoresM, int phases, int* mid, int MK) {
     const bbm_index_cfg* g = X->cfg;
     c->X = X; c->K = g->keylen; c->baseKeyHitScore = BASE_HIT_SCORE * c->K;
     c->indelPenalty = (c->baseKeyHitScore / 2) - 1;
@@ -762,45 +766,59 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
     c->siteMask = (int)(0xFFFFFFFFu >> (g->chrombits + 1));
     c->status = 0;
     const int K = c->K, obeyLimits = 1;
-    int offsetsP[MAXK], keysP[MAXK], keyScoresP[MAXK], keysOriginal[MAXK];
-    if (nkeys < 1 || nkeys > MAXK || len > SEARCH_MAX_READ) { H->status = BBM_ST_BADARG; return; }
-    int n = nkeys;
-    for (int i = 0; i < n; i++) {
-        offsetsP[i] = offsetsIn[i]; keyScoresP[i] = keyScoresIn[i];
-        int key = 0; bool bad = false;
-        for (int p = offsetsIn[i]; p < offsetsIn[i] + K; p++) {        // KeyRing.makeKeys / ChromosomeArray.toNumber
-            const int ch = basesP[p];
-            const int u = ch & 0xDF;
-            const int x = (ch & 0x80) ? -1 : (u == 'A' ? 0 : (u == 'C' ? 1 : (u == 'G' ? 2 : ((u == 'T' || u == 'U') ? 3 : -1))));
-            if (x < 0) { bad = true; break; }
-            key = (key << 2) | x;
-        }
-        keysOriginal[i] = bad ? -1 : key; keysP[i] = keysOriginal[i];
-    }
-    const int numKeysOriginal = n;
-    const int maxLen = g->max_usable_length;
-    const long long tf0 = clock64();
-    int numHits = count_hits(c, keysP, n, maxLen);
-    if (numHits > 0) {
-        const int trigger = (3 * n) / 4;
-        if (numHits < 4 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, (maxLen * 3) / 2); }
-        if (numHits < 3 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 2); }
-        if (numHits < 3 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 3); }
-        if (numHits < 2 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 5); }
-    }
-    if (numHits < n) n = shrink2(offsetsP, keysP, keyScoresP, n);
-    if (n > 0) {     // TRIM_BY_GREEDY && obeyLimits
-        const int maxLists = imax((int)(HIT_FRACTION_TO_RETAIN * n), MIN_HIT_LISTS_TO_RETAIN);
-        numHits = trim_by_greedy(c, offsetsP, keyScoresP, n, maxLists, keysP);
-    }
-    c->tFilter += clock64() - tf0;
-    H->num_hits = numHits;
-    if (numHits < 1) { H->status = c->status; return; }
-    if (numHits < n) n = shrink2(offsetsP, keysP, keyScoresP, n);
-    // minus strand: KeyRing.reverseOffsets / reverseComplementKeys, Tools.reverseAndCopy, AminoAcid.reverseComplementBases
+    int offsetsP[MAXK], keysP[MAXK], keyScoresP[MAXK];
     int offsetsM[MAXK], keysM[MAXK], keyScoresM[MAXK];
-    for (int i = 0; i < n; i++) { offsetsM[i] = len - (offsetsP[n - 1 - i] + K); keysM[i] = rcomp_fast_dev(keysP[n - 1 - i], K); keyScoresM[i] = keyScoresP[n - 1 - i]; }
-    for (int i = 0; i < len; i++) { basesM[i] = comp_base(basesP[len - 1 - i]); baseScoresM[i] = baseScoresP[len - 1 - i]; }
+    if (nkeys < 1 || nkeys > MAXK || len > SEARCH_MAX_READ) { H->status = BBM_ST_BADARG; if (mid) mid[0] = 0; return; }
+    int n = nkeys, numHits = 0, numKeysOriginal = nkeys;
+    if (phases & 1) {
+        int keysOriginal[MAXK];
+        for (int i = 0; i < n; i++) {
+            offsetsP[i] = offsetsIn[i]; keyScoresP[i] = keyScoresIn[i];
+            int key = 0; bool bad = false;
+            for (int p = offsetsIn[i]; p < offsetsIn[i] + K; p++) {        // KeyRing.makeKeys / ChromosomeArray.toNumber
+                const int ch = basesP[p];
+                const int u = ch & 0xDF;
+                const int x = (ch & 0x80) ? -1 : (u == 'A' ? 0 : (u == 'C' ? 1 : (u == 'G' ? 2 : ((u == 'T' || u == 'U') ? 3 : -1))));
+                if (x < 0) { bad = true; break; }
+                key = (key << 2) | x;
+            }
+            keysOriginal[i] = bad ? -1 : key; keysP[i] = keysOriginal[i];
+        }
+        const int maxLen = g->max_usable_length;
+        const long long tf0 = clock64();
+        numHits = count_hits(c, keysP, n, maxLen);
+        if (numHits > 0) {
+            const int trigger = (3 * n) / 4;
+            if (numHits < 4 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, (maxLen * 3) / 2); }
+            if (numHits < 3 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 2); }
+            if (numHits < 3 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 3); }
+            if (numHits < 2 && numHits < trigger) { for (int i = 0; i < n; i++) keysP[i] = keysOriginal[i]; numHits = count_hits(c, keysP, n, maxLen * 5); }
+        }
+        if (numHits < n) n = shrink2(offsetsP, keysP, keyScoresP, n);
+        if (n > 0) {     // TRIM_BY_GREEDY && obeyLimits
+            const int maxLists = imax((int)(HIT_FRACTION_TO_RETAIN * n), MIN_HIT_LISTS_TO_RETAIN);
+            numHits = trim_by_greedy(c, offsetsP, keyScoresP, n, maxLists, keysP);
+        }
+        c->tFilter += clock64() - tf0;
+        H->num_hits = numHits;
+        if (numHits < 1) { H->status = c->status; if (mid) mid[0] = 0; return; }
+        if (numHits < n) n = shrink2(offsetsP, keysP, keyScoresP, n);
+        // minus strand: KeyRing.reverseOffsets / reverseComplementKeys
+        for (int i = 0; i < n; i++) { offsetsM[i] = len - (offsetsP[n - 1 - i] + K); keysM[i] = rcomp_fast_dev(keysP[n - 1 - i], K); keyScoresM[i] = keyScoresP[n - 1 - i]; }
+        if (mid) {
+            mid[0] = n; mid[1] = numHits; mid[2] = c->status;
+            int* a = mid + MID_HDR;
+            for (int i = 0; i < n; i++) { a[i] = keysP[i]; a[MK + i] = keysM[i]; a[2 * MK + i] = offsetsP[i]; a[3 * MK + i] = offsetsM[i]; a[4 * MK + i] = keyScoresP[i]; a[5 * MK + i] = keyScoresM[i]; }
+        }
+        if (!(phases & 6)) return;
+    } else {
+        n = mid[0]; numHits = mid[1]; c->status = mid[2];
+        if (n < 1) return;
+        const int* a = mid + MID_HDR;
+        for (int i = 0; i < n; i++) { keysP[i] = a[i]; keysM[i] = a[MK + i]; offsetsP[i] = a[2 * MK + i]; offsetsM[i] = a[3 * MK + i]; keyScoresP[i] = a[4 * MK + i]; keyScoresM[i] = a[5 * MK + i]; }
+    }
+    // Tools.reverseAndCopy / AminoAcid.reverseComplementBases: the walk scores minus-strand sites against the reverse complement
+    if (phases & 4) for (int i = 0; i < len; i++) { basesM[i] = comp_base(basesP[len - 1 - i]); baseScoresM[i] = baseScoresP[len - 1 - i]; }
     const int maxQuickScore = max_quick_score(c, offsetsP, keyScoresP, n);
     int bestScores[6] = {0, 0, 0, 0, 0, 0};
     const bool prescan_qscore = (numHits >= 5);
@@ -812,7 +830,13 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
     else for (int i = 1; i < n; i++) if (offsetsP[i] > offsetsP[i - 1] + K) { allBasesCovered = false; break; }
     const bool pretend = (allBasesCovered || n >= numKeysOriginal - 4 || (n >= 9 && (offsetsP[n - 1] - offsetsP[0] + K) > imax(40, (int)(len * .75f))));
     const int minChrom = 1, maxChrom = X->nchroms;
-    if (prescan_qscore) {
+    int* midPre = mid ? mid + MID_HDR + 6 * MK : nullptr;
+    if (!(phases & 2)) {
+        // prescan results of the earlier launch
+        if (mid[9]) { H->status = c->status; return; }
+        bestScores[1] = mid[4]; bestScores[3] = mid[5]; hitsCutoff = mid[6]; qscoreCutoff = mid[7]; havePre = mid[8] != 0;
+        if (havePre) { const int ncyc = 2 * X->nblocks; for (int i = 0; i < ncyc; i++) { precounts[i] = midPre[i]; prescores[i] = midPre[ncyc + i]; } }
+    } else if (prescan_qscore) {
         int bestqscore = 0, maxHits = 0, minHitsToScore = 1, cycle = 0; bool early = false;
         const int ncyc = 2 * X->nblocks;
         for (int i = 0; i < ncyc; i++) { precounts[i] = n; prescores[i] = maxQuickScore; }
@@ -834,8 +858,10 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
             }
         }
         bestScores[1] = imax(bestScores[1], maxHits); bestScores[3] = imax(bestScores[3], bestqscore);
-        if (bestScores[1] < 1) { H->status = c->status; return; }
-        if ((float)bestScores[3] < __fmul_rn((float)maxQuickScore, MIN_QSCORE_MULT2)) { H->status = c->status; return; }
+        bool dead = false;
+        if (bestScores[1] < 1) dead = true;
+        else if ((float)bestScores[3] < __fmul_rn((float)maxQuickScore, MIN_QSCORE_MULT2)) dead = true;
+        if (dead) { H->status = c->status; if (mid) mid[9] = 1; return; }
         if (bestScores[3] >= maxQuickScore && pretend) {
             hitsCutoff = approx_hits_cutoff(c, n, bestScores[1], 1, 1);
             qscoreCutoff = imax(qscoreCutoff, (int)(bestScores[3] * DYNAMIC_QSCORE_THRESH_PERFECT));
@@ -844,6 +870,11 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
             qscoreCutoff = imax(qscoreCutoff, (int)(bestScores[3] * PRESCAN_QSCORE_THRESH));
         }
     }
+    if ((phases & 2) && mid) {
+        mid[2] = c->status; mid[4] = bestScores[1]; mid[5] = bestScores[3]; mid[6] = hitsCutoff; mid[7] = qscoreCutoff; mid[8] = havePre ? 1 : 0; mid[9] = 0;
+        if (havePre) { const int ncyc = 2 * X->nblocks; for (int i = 0; i < ncyc; i++) { midPre[i] = precounts[i]; midPre[ncyc + i] = prescores[i]; } }
+    }
+    if (!(phases & 4)) return;
     int maxScore = 70 + (len - 1) * 100;                        // msa.maxQuality(baseScores)
     bool fullyDefined = true;
     for (int i = 0; i < len; i++) { maxScore += baseScoresP[i]; fullyDefined = fullyDefined && base_defined(basesP[i]); }
@@ -873,6 +904,7 @@ struct SearchParams {
     const int* nkeys; const int* offsets; const int* keyScores; int maxKeys; int quitAfterTwoPerfects;
     bbm_search_head* heads; bbm_site* sites; int maxSites;
     char* pool; unsigned int* counter;
+    int phases; int* mid; int midStride;      // split launches: one phase of BBIndex.find per kernel, state carried in mid[read][midStride]
     unsigned long long* prof;     // optional: 5 cycle counters {total, filter, prescan, walk (incl. extend), extend}
 };
 
@@ -908,15 +940,16 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SHARED ? 7 : 8) search_kernel(
         const unsigned r = atomicAdd(P.counter, 1u);
         if ((long long)r >= P.nreads) break;
         bbm_search_head* H = P.heads + r;
-        bbm_search_head z = {}; *H = z;
+        if (P.phases & 1) { bbm_search_head z = {}; *H = z; }
         ReadState R; R.sites = P.sites + (long long)r * P.maxSites; R.maxSites = P.maxSites; R.nsites = 0;
         const long long o = P.read_off[r]; const int len = (int)(P.read_off[r + 1] - o);
         const int nk = P.nkeys[r];
         if (SHARED && nk > SEARCH_FAST_KEYS) H->status = BBM_ST_BADARG;       // cannot happen: the host picks this kernel from maxKeys
         else if (nk > 0)
             search_read(&P.X, P.bases + o, len, P.baseScores + o, P.offsets + (long long)r * P.maxKeys, P.keyScores + (long long)r * P.maxKeys,
-                        nk, P.quitAfterTwoPerfects, H, &R, c, basesM, baseScoresM);
-        H->nsites = R.nsites;
+                        nk, P.quitAfterTwoPerfects, H, &R, c, basesM, baseScoresM, P.phases, P.mid ? P.mid + (long long)r * P.midStride : nullptr, P.maxKeys);
+        else if (P.mid && (P.phases & 1)) P.mid[(long long)r * P.midStride] = 0;
+        if (P.phases & 4) H->nsites = R.nsites;
     }
     if (P.prof) {
         atomicAdd(P.prof + 0, (unsigned long long)(clock64() - tk0)); atomicAdd(P.prof + 1, (unsigned long long)c->tFilter);
@@ -930,12 +963,14 @@ using namespace bbm;
 
 extern "C" size_t bbm_search_pool_bytes() { return SEARCH_POOL_BYTES; }
 extern "C" int bbm_search_threads() { return SEARCH_THREADS; }
+extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks) { return MID_HDR + 6 * maxKeys + 4 * nblocks; }
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
                                  int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* pool,
-                                 unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, cudaStream_t st) {
-    SearchParams P; P.prof = prof;
+                                 unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, int phases, int* mid, int midStride,
+                                 cudaStream_t st) {
+    SearchParams P; P.prof = prof; P.phases = phases; P.mid = mid; P.midStride = midStride;
     P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts; P.X.hist = d_hist;
     P.X.chroms = d_chroms; P.X.chrom_off = d_chrom_off;
     P.bases = bases; P.baseScores = baseScores; P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.offsets = offsets; P.keyScores = keyScores;

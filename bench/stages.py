@@ -120,6 +120,8 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     # ---- a6-a9 search ----
     if os.environ.get("BBM_SEARCH_PROFILE"):
         _lib.check(L.bbm_set_option(h, b"search_profile", 1), "set_option")
+    if os.environ.get("BBM_SEARCH_SPLIT"):
+        _lib.check(L.bbm_set_option(h, b"search_split", int(os.environ["BBM_SEARCH_SPLIT"])), "set_option")
     if search_bps:
         _lib.check(L.bbm_set_option(h, b"search_shared", search_bps), "set_option")
     d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)

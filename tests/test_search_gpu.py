@@ -70,6 +70,9 @@ def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
         for key in ("nkeys", "offsets", "keyScores", "baseScores"):
             assert np.array_equal(seeds[key], eseeds[key])
         heads, sites = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2)
+        # the same batch with one phase of BBIndex.find per kernel launch (key filtering / prescan / walk)
+        h3, t3 = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=True)
+        assert h3.tobytes() == heads.tobytes() and t3.tobytes() == sites.tobytes()
         # the same batch with 32 key slots per read through the shared-memory variant of the kernel
         s32 = {k: (np.ascontiguousarray(v[:, :32]) if getattr(v, "ndim", 1) == 2 else v) for k, v in seeds.items()}
         if int(seeds["nkeys"].max()) <= 32:
