@@ -64,6 +64,9 @@ extern "C" int bbm_launch_sam(const bbm_sam_task* tasks, long long n, const int8
 extern "C" int bbm_search_threads();
 extern "C" size_t bbm_search_pool_bytes();
 extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks);
+extern "C" int bbm_launch_search_prescan_warp(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts,
+                                              const long long* read_off, long long nreads, const int* nkeys, int maxKeys, bbm_search_head* heads,
+                                              unsigned int* counter, int blocks, int* mid, int midStride, cudaStream_t st);
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,
                                  const long long* read_off, long long nreads, const int* nkeys, const int* offsets, const int* keyScores, int maxKeys,
@@ -118,7 +121,7 @@ struct bbm_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 0;
+    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
@@ -1143,6 +1146,16 @@ static int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int
         const int stride = bbm_search_mid_stride(maxKeys, nblk);
         if (c->searchRev.ensure((size_t)nreads * stride * 4)) return fail(BBM_E_CUDA, "cudaMalloc search phase state");
         for (int ph = 1; ph <= 4; ph <<= 1) {
+            if (ph == 2 && c->search_split >= 2) {
+                // prescan with one warp per read; reads with more than 32 keys are left to the thread-per-read launch that follows
+                CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+                int wblocks = c->sms * 8; const long long wneed = (nreads + 3) / 4; if (wneed < wblocks) wblocks = (int)wneed;
+                int e = bbm_launch_search_prescan_warp((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, (const long long*)doff, nreads, dn,
+                                                       maxKeys, dh, cb + 202, wblocks, (int*)c->searchRev.p, stride, st);
+                if (e) return fail(BBM_E_CUDA, "prescan_warp_kernel launch", (cudaError_t)e);
+                c->launches++;
+                if (maxKeys <= 32) continue;
+            }
             CK(cudaMemsetAsync(cb + 202, 0, 4, st));
             int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, c->d_ihist, c->d_chroms, c->d_chrom_off, db, dbs,
                                       (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites, c->searchCtx.p, cb + 202, prof, blocks,

@@ -15,6 +15,7 @@
 // (site, column) sequence.  Index (starts/sites/COUNTS) and chromosome bytes are gathered straight from HBM/L2.
 // Unsupported corner (flagged in `status`, never silently wrong): subsumption into a previous site that carries a gap
 // array (needs GapTools.fixGaps).
+#include <cstring>
 #include <cuda_runtime.h>
 #include "msa_common.cuh"
 
@@ -806,7 +807,7 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
         // minus strand: KeyRing.reverseOffsets / reverseComplementKeys
         for (int i = 0; i < n; i++) { offsetsM[i] = len - (offsetsP[n - 1 - i] + K); keysM[i] = rcomp_fast_dev(keysP[n - 1 - i], K); keyScoresM[i] = keyScoresP[n - 1 - i]; }
         if (mid) {
-            mid[0] = n; mid[1] = numHits; mid[2] = c->status;
+            mid[0] = n; mid[1] = numHits; mid[2] = c->status; mid[10] = 0; mid[11] = 0;
             int* a = mid + MID_HDR;
             for (int i = 0; i < n; i++) { a[i] = keysP[i]; a[MK + i] = keysM[i]; a[2 * MK + i] = offsetsP[i]; a[3 * MK + i] = offsetsM[i]; a[4 * MK + i] = keyScoresP[i]; a[5 * MK + i] = keyScoresM[i]; }
         }
@@ -836,6 +837,8 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
         if (mid[9]) { H->status = c->status; return; }
         bestScores[1] = mid[4]; bestScores[3] = mid[5]; hitsCutoff = mid[6]; qscoreCutoff = mid[7]; havePre = mid[8] != 0;
         if (havePre) { const int ncyc = 2 * X->nblocks; for (int i = 0; i < ncyc; i++) { precounts[i] = midPre[i]; prescores[i] = midPre[ncyc + i]; } }
+    } else if (mid && phases == 2 && mid[10] == 0 && mid[11] == 1) {
+        return;                                   // the warp-per-read prescan already filled mid for this read
     } else if (prescan_qscore) {
         int bestqscore = 0, maxHits = 0, minHitsToScore = 1, cycle = 0; bool early = false;
         const int ncyc = 2 * X->nblocks;
@@ -957,12 +960,297 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SHARED ? 7 : 8) search_kernel(
     }
 }
 
+
+// =====================  warp-per-read prescan (phase 2 of the split launches)  =====================
+// prescanAllBlocks / findMaxQscore2 (BBIndex.java:642-741, 2294-2450) with one WARP per read: lane c owns hit list c of the current
+// (block, strand) — its cursor, head value and prefetched next value live in registers, the index gathers of a read are issued by all
+// lanes at once.  The reference pops the merged lists one site at a time; here every iteration first retires, in one go, the longest
+// prefix of the merged order that consists of *isolated* sites: sites whose window [site-MAX_INDEL, site+MAX_INDEL2] contains no other
+// list head at the time they are popped (decided from the heads and next values of all lists, ranked through shared memory) and no
+// last value of an exhausted list.  Such a site has exactly one hit: it is scored keyScore + scoreZ1Key if the cutoff is 1 and ignored
+// otherwise (:2352-2376, 2490-2492, 2883), so a whole run of them only raises topQscore to the largest of their scores.  Any other site
+// goes through the reference's own step (count, quickScore, scoreZ2, pops), evaluated redundantly by all lanes from shuffled values.
+// Reads with more than 32 keys are left to the thread-per-read kernel (mid[10] = 1).
+constexpr int PW_WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+struct PwSlot { int val, nx, flags; };     // flags: bit0 hasNx, bit1 retire
+
+__device__ __forceinline__ int jadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }   // Java int arithmetic (wraps)
+
+__global__ void __launch_bounds__(PW_WARPS * 32) prescan_warp_kernel(SearchParams P) {
+    __shared__ PwSlot slots[PW_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const SearchIndex* X = &P.X;
+    const bbm_index_cfg* g = X->cfg;
+    ctx_t cc; ctx_t* c = &cc;
+    c->X = X; c->K = g->keylen; c->baseKeyHitScore = BASE_HIT_SCORE * c->K;
+    c->indelPenalty = (c->baseKeyHitScore / 2) - 1;
+    c->maxPenaltyMisaligned = c->baseKeyHitScore - (1 + c->baseKeyHitScore / 8);
+    c->scoreZ1Key = Z_SCORE_MULT * c->K;
+    c->shift = g->shift_length; c->cpb = g->chroms_per_block; c->lowMask = c->cpb - 1; c->highMask = ~c->lowMask;
+    c->siteMask = (int)(0xFFFFFFFFu >> (g->chrombits + 1));
+    const int K = c->K, MK = P.maxKeys;
+    for (;;) {
+        unsigned r = 0;
+        if (lane == 0) r = atomicAdd(P.counter, 1u);
+        r = __shfl_sync(FULL, r, 0);
+        if ((long long)r >= P.nreads) break;
+        int* mid = P.mid + (long long)r * P.midStride;
+        const int n = mid[0];
+        if (n < 1) continue;
+        if (n > 32) { if (lane == 0) { mid[10] = 1; mid[11] = 1; } continue; }
+        const int numHitsRead = mid[1], status0 = mid[2];
+        const int len = (int)(P.read_off[r + 1] - P.read_off[r]), numKeysOriginal = P.nkeys[r];
+        const int* a = mid + MID_HDR;
+        int keyP = -1, keyM = -1, ofsP = 0, ofsM = 0, kscP = 0, kscM = 0;
+        if (lane < n) { keyP = a[lane]; keyM = a[MK + lane]; ofsP = a[2 * MK + lane]; ofsM = a[3 * MK + lane]; kscP = a[4 * MK + lane]; kscM = a[5 * MK + lane]; }
+        // maxQuickScore of the read (plus-strand arrays), allBasesCovered, pretend (BBIndex.java:470-486)
+        int maxQuickScore;
+        {
+            int x = lane < n ? kscP : 0;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            int score = 0, a0 = -1, b0 = -1;
+            for (int i = 0; i < n; i++) { const int av = __shfl_sync(FULL, ofsP, i); if (b0 < av) { score += b0 - a0; a0 = av; } b0 = av + K; }
+            score += b0 - a0;
+            maxQuickScore = x + score * Z_SCORE_MULT + Y_SCORE_MULT * (__shfl_sync(FULL, ofsP, n - 1) - __shfl_sync(FULL, ofsP, 0));
+        }
+        const int ofsFirst = __shfl_sync(FULL, ofsP, 0), ofsLast = __shfl_sync(FULL, ofsP, n - 1);
+        const int ofsPrev = __shfl_up_sync(FULL, ofsP, 1);
+        const bool gapBad = __any_sync(FULL, lane >= 1 && lane < n && ofsP > ofsPrev + K);
+        const bool allBasesCovered = (ofsFirst == 0) && (ofsLast == (len - K)) && !gapBad;
+        const bool pretend = (allBasesCovered || n >= numKeysOriginal - 4 || (n >= 9 && (ofsLast - ofsFirst + K) > imax(40, (int)(len * .75f))));
+        int hitsCutoff = 0, qscoreCutoff = (int)(MIN_QSCORE_MULT * maxQuickScore);
+        int best1 = 0, best3 = 0; bool havePre = false, dead = false;
+        int* midPre = mid + MID_HDR + 6 * MK;
+        if (numHitsRead >= 5) {
+            int bestqscore = 0, maxHitsAll = 0, minHitsToScore = 1, cycle = 0; bool early = false;
+            const int ncyc = 2 * X->nblocks;
+            if (lane < ncyc) { midPre[lane] = n; midPre[ncyc + lane] = maxQuickScore; }
+            for (int i = 32 + lane; i < ncyc; i += 32) { midPre[i] = n; midPre[ncyc + i] = maxQuickScore; }
+            havePre = true;
+            for (int chrom = 1; chrom <= X->nchroms && !early; chrom = ((chrom & c->highMask) + c->cpb)) {
+                const int baseChrom = base_chrom(c, chrom);
+                const SearchBlock* b = block_of(c, chrom);
+                for (int pmi = 0; pmi < 2 && !early; pmi++, cycle++) {
+                    // ---- getHits (:353-373): all lists of the read at once ----
+                    const int key = pmi == 0 ? keyP : keyM;
+                    int st = -1, sp = -1;
+                    if (lane < n && key >= 0 && X->counts[key] > 0) {
+                        const int s0 = b->starts[key], x = b->starts[key + 1] - s0;
+                        if (x > 0 && b->sites[s0] != -1) { st = s0; sp = s0 + x; }
+                    }
+                    const unsigned vmask = __ballot_sync(FULL, st >= 0);
+                    const int nh = __popc(vmask);
+                    int ts = -9999, th = 0;
+                    if (nh >= minHitsToScore) {
+                        // ---- shrink (:783-813): lane col takes the col-th list that has hits ----
+                        const int src = lane < nh ? __fns(vmask, 0, lane + 1) : 0;
+                        int row = __shfl_sync(FULL, st, src), stop = __shfl_sync(FULL, sp, src);
+                        const int ofs = __shfl_sync(FULL, pmi == 0 ? ofsP : ofsM, src), ksc = __shfl_sync(FULL, pmi == 0 ? kscP : kscM, src);
+                        const bool isCol = lane < nh;
+                        bool live = isCol;
+                        int val = 0, nx = 0; bool hasNx = false;
+                        if (isCol) {
+                            val = site_minus_offset(c, b->sites[row], ofs, baseChrom);
+                            hasNx = row + 1 < stop;
+                            if (hasNx) nx = site_minus_offset(c, b->sites[row + 1], ofs, baseChrom);
+                        }
+                        // maxQuickScore of these columns (:2316)
+                        int mqs;
+                        {
+                            int x = isCol ? ksc : 0;
+#pragma unroll
+                            for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+                            int score = 0, a0 = -1, b0 = -1;
+                            for (int i = 0; i < nh; i++) { const int av = __shfl_sync(FULL, ofs, i); if (b0 < av) { score += b0 - a0; a0 = av; } b0 = av + K; }
+                            score += b0 - a0;
+                            mqs = x + score * Z_SCORE_MULT + Y_SCORE_MULT * (__shfl_sync(FULL, ofs, nh - 1) - __shfl_sync(FULL, ofs, 0));
+                        }
+                        int topQscore = -999999999, maxHits = 0;
+                        int cutoff = imax(minHitsToScore, imin(1, nh - 1));
+                        int nActive = nh, staleMax = -0x7fffffff - 1;
+                        bool done = false;
+                        while (!done) {
+                            const unsigned liveMask = __ballot_sync(FULL, live);
+                            if (!liveMask) break;
+                            const int nLive = __popc(liveMask);
+                            // ---- rank the live heads by (value, column), move them to rank order through shared memory ----
+                            int rank = 0;
+                            for (int j = 0; j < nh; j++) {
+                                const int vj = __shfl_sync(FULL, val, j);
+                                if (((liveMask >> j) & 1u) && (vj < val || (vj == val && j < lane))) rank++;
+                            }
+                            if (live) { PwSlot q; q.val = val; q.nx = nx; q.flags = hasNx ? 1 : 0; slots[wib][rank] = q; }
+                            __syncwarp();
+                            bool iso = false;
+                            {
+                                const int big = 0x7fffffff, small = -0x7fffffff - 1;
+                                const bool pos = lane < nLive;                                     // this lane now stands for rank `lane`
+                                PwSlot me; me.val = 0; me.nx = 0; me.flags = 0;
+                                if (pos) me = slots[wib][lane];
+                                const int pv = me.val;
+                                int pmin = (pos && (me.flags & 1)) ? me.nx : big;                  // next values of the lists ranked at or below me
+                                int pmax = (pos && !(me.flags & 1)) ? me.val : small;              // lists without one leave their value behind when popped
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) {                                 // inclusive scans in rank order
+                                    const int tmin = __shfl_up_sync(FULL, pmin, o), tmax = __shfl_up_sync(FULL, pmax, o);
+                                    if (lane >= o) { pmin = imin(pmin, tmin); pmax = imax(pmax, tmax); }
+                                }
+                                int exMin = __shfl_up_sync(FULL, pmin, 1), exMax = __shfl_up_sync(FULL, pmax, 1);
+                                if (lane == 0) { exMin = big; exMax = small; }
+                                const int nextVal = (pos && lane + 1 < nLive) ? slots[wib][lane + 1].val : big;
+                                const bool room = pv <= 0x7fffffff - MAX_INDEL2;
+                                const long long hi = (long long)pv + MAX_INDEL2, lo = (long long)pv - MAX_INDEL;
+                                iso = pos && room && (lane + 1 >= nLive || (long long)nextVal > hi) && (exMin == big || (long long)exMin > hi) &&
+                                      ((long long)exMax < lo) && ((long long)staleMax < lo);
+                            }
+                            const unsigned nonIso = __ballot_sync(FULL, lane < nLive && !iso);
+                            const int firstNonIso = nonIso ? __ffs(nonIso) - 1 : nLive;
+                            if (lane < nLive) slots[wib][lane].flags |= (lane < firstNonIso) ? 2 : 0;
+                            __syncwarp();
+                            if (firstNonIso > 0) {
+                                // ---- retire the run of isolated sites ----
+                                const bool retire = live && (slots[wib][rank].flags & 2);
+                                int q = retire ? ksc + c->scoreZ1Key : -0x7fffffff - 1;
+#pragma unroll
+                                for (int o = 16; o >= 1; o >>= 1) q = imax(q, __shfl_xor_sync(FULL, q, o));
+                                if (cutoff <= 1 && q > topQscore) { maxHits = imax(1, maxHits); topQscore = q; }
+                                bool exhausted = false;
+                                if (retire) {
+                                    row++;
+                                    if (hasNx) { val = nx; hasNx = row + 1 < stop; if (hasNx) nx = site_minus_offset(c, b->sites[row + 1], ofs, baseChrom); }
+                                    else { live = false; exhausted = true; }
+                                }
+                                const unsigned exMask = __ballot_sync(FULL, exhausted);
+                                if (exMask) {
+                                    int sv = exhausted ? val : -0x7fffffff - 1;
+#pragma unroll
+                                    for (int o = 16; o >= 1; o >>= 1) sv = imax(sv, __shfl_xor_sync(FULL, sv, o));
+                                    staleMax = imax(staleMax, sv);
+                                    nActive -= __popc(exMask);
+                                    if (nActive < cutoff) done = true;
+                                }
+                                __syncwarp();
+                                continue;
+                            }
+                            __syncwarp();
+                            // ---- the reference's own step for the smallest head (:2340-2440) ----
+                            const int centerIndex = __ffs(__ballot_sync(FULL, live && rank == 0)) - 1;
+                            const int site = __shfl_sync(FULL, val, centerIndex);
+                            const int minsite = jadd(site, -MAX_INDEL), maxsite = jadd(site, MAX_INDEL2);
+                            const int approxHits = __popc(__ballot_sync(FULL, isCol && val >= minsite && val <= maxsite));
+                            if (approxHits >= cutoff) {
+                                int qscore;
+                                if (approxHits == 1) qscore = __shfl_sync(FULL, ksc, centerIndex) + c->scoreZ1Key;
+                                else {
+                                    // quickScore (:2490-2511) = key score + scoreLeft + scoreRight - centerIndex + Y * scoreY; scoreZ2 (:2882-2914)
+                                    int sc = __shfl_sync(FULL, ksc, centerIndex);
+                                    int loc = site, prev;
+                                    for (int i = centerIndex - 1; i >= 0; i--) {
+                                        const int v = __shfl_sync(FULL, val, i), ks = __shfl_sync(FULL, ksc, i);
+                                        if (v >= 0) {
+                                            prev = loc; loc = v;
+                                            const int offset = absdif(loc, prev);
+                                            if (offset <= MAX_INDEL) { sc += ks; if (offset != 0) sc -= imin(c->indelPenalty + INDEL_PENALTY_MULT * offset, c->maxPenaltyMisaligned); }
+                                            else loc = prev;
+                                        }
+                                    }
+                                    loc = site;
+                                    for (int i = centerIndex + 1; i < nh; i++) {
+                                        const int v = __shfl_sync(FULL, val, i), ks = __shfl_sync(FULL, ksc, i);
+                                        if (v >= 0) {
+                                            prev = loc; loc = v;
+                                            const int offset = absdif(loc, prev);
+                                            if (offset <= MAX_INDEL) { sc += ks; if (offset != 0) sc -= imin(c->indelPenalty + INDEL_PENALTY_MULT * offset, c->maxPenaltyMisaligned); }
+                                            else loc = prev;
+                                        }
+                                    }
+                                    sc -= centerIndex;
+                                    const unsigned eq = __ballot_sync(FULL, isCol && val == site);
+                                    const int rightIndex = 31 - __clz(eq);
+                                    sc += Y_SCORE_MULT * (__shfl_sync(FULL, ofs, rightIndex) - __shfl_sync(FULL, ofs, centerIndex));
+                                    const int maxLoc = jadd(site, MAX_INDEL2), minLoc = imax(0, jadd(site, -MAX_INDEL));
+                                    int z = 0, a0 = -1, b0 = -1;
+                                    for (int i = 0; i < nh; i++) {
+                                        const int v = __shfl_sync(FULL, val, i), av = __shfl_sync(FULL, ofs, i);
+                                        if (v >= minLoc && v <= maxLoc) { if (b0 < av) { z += b0 - a0; a0 = av; } b0 = av + K; }
+                                    }
+                                    z += b0 - a0;
+                                    qscore = sc + z * Z_SCORE_MULT;
+                                }
+                                if (qscore > topQscore) {
+                                    maxHits = imax(approxHits, maxHits);
+                                    cutoff = imax(cutoff, approxHits - 1);
+                                    topQscore = qscore;
+                                    if (qscore >= mqs) { done = true; continue; }
+                                }
+                            }
+                            // pops: every live list sitting on `site` advances (again if its next site is `site` too)
+                            for (;;) {
+                                const bool hit = live && val == site;
+                                if (!__any_sync(FULL, hit)) break;
+                                bool exhausted = false;
+                                if (hit) {
+                                    row++;
+                                    if (hasNx) { val = nx; hasNx = row + 1 < stop; if (hasNx) nx = site_minus_offset(c, b->sites[row + 1], ofs, baseChrom); }
+                                    else { live = false; exhausted = true; }
+                                }
+                                const unsigned exMask = __ballot_sync(FULL, exhausted);
+                                if (exMask) {
+                                    int sv = exhausted ? val : -0x7fffffff - 1;
+#pragma unroll
+                                    for (int o = 16; o >= 1; o >>= 1) sv = imax(sv, __shfl_xor_sync(FULL, sv, o));
+                                    staleMax = imax(staleMax, sv);
+                                    nActive -= __popc(exMask);
+                                    if (nActive < cutoff) { done = true; break; }
+                                }
+                            }
+                        }
+                        ts = topQscore; th = maxHits;
+                        bestqscore = imax(ts, bestqscore); maxHitsAll = imax(maxHitsAll, th);
+                        if (bestqscore >= maxQuickScore && pretend) { minHitsToScore = imax(minHitsToScore, maxHitsAll); early = true; }
+                    } else { ts = -9999; th = 0; }
+                    if (lane == 0) { midPre[cycle] = th; midPre[ncyc + cycle] = ts; }
+                }
+            }
+            best1 = maxHitsAll; best3 = bestqscore;
+            if (best1 < 1) dead = true;
+            else if ((float)best3 < __fmul_rn((float)maxQuickScore, MIN_QSCORE_MULT2)) dead = true;
+            if (!dead) {
+                if (best3 >= maxQuickScore && pretend) {
+                    hitsCutoff = approx_hits_cutoff(c, n, best1, 1, 1);
+                    qscoreCutoff = imax(qscoreCutoff, (int)(best3 * DYNAMIC_QSCORE_THRESH_PERFECT));
+                } else {
+                    hitsCutoff = approx_hits_cutoff(c, n, best1, 1, 0);
+                    qscoreCutoff = imax(qscoreCutoff, (int)(best3 * PRESCAN_QSCORE_THRESH));
+                }
+            }
+        }
+        if (lane == 0) {
+            mid[2] = status0; mid[4] = best1; mid[5] = best3; mid[6] = hitsCutoff; mid[7] = qscoreCutoff; mid[8] = havePre ? 1 : 0; mid[9] = dead ? 1 : 0; mid[10] = 0; mid[11] = 1;
+            if (dead) P.heads[r].status = status0;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace bbm
 
 using namespace bbm;
 
 extern "C" size_t bbm_search_pool_bytes() { return SEARCH_POOL_BYTES; }
 extern "C" int bbm_search_threads() { return SEARCH_THREADS; }
+extern "C" int bbm_launch_search_prescan_warp(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts,
+                                              const long long* read_off, long long nreads, const int* nkeys, int maxKeys, bbm_search_head* heads,
+                                              unsigned int* counter, int blocks, int* mid, int midStride, cudaStream_t st) {
+    SearchParams P; memset(&P, 0, sizeof(P));
+    P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts;
+    P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.maxKeys = maxKeys; P.heads = heads; P.counter = counter; P.mid = mid; P.midStride = midStride;
+    prescan_warp_kernel<<<blocks, PW_WARPS * 32, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
 extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks) { return MID_HDR + 6 * maxKeys + 4 * nblocks; }
 extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int* d_hist,
                                  const int8_t* d_chroms, const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores,

@@ -118,6 +118,8 @@ int  bbm_msa_gapped_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_
  *             the thread-per-alignment strip kernel (default 16 = all);  "strip_budget_mb" = device scratch the strip kernel may use;
  *   "search_shared" 1 = the index-search kernel keeps its per-read walk arrays in shared memory when a batch has <= 32 keys per read
  *             (A/B; measured slower than the per-thread global pool on B200, so off by default);
+ *   "search_split" 0 = BBIndex.find in one thread-per-read launch, 1 = key filtering / prescan / walk as three thread-per-read launches,
+ *             2 (default) = the prescan with one warp per read (reads with more than 32 keys fall back to the thread-per-read prescan);
  *   "search_profile", "strip_debug" (diagnostics).
  * Results are bit-identical for every setting.  bbm_get_stat keys: "launches", "band_misses" (banded alignments re-run by the
  * row-sequential kernel), "tasks_total", "narrow_tried", "narrow_handed_over", "strip_tasks", "index_build_us". */

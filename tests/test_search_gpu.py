@@ -73,6 +73,10 @@ def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
         # the same batch with one phase of BBIndex.find per kernel launch (key filtering / prescan / walk)
         h3, t3 = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=True)
         assert h3.tobytes() == heads.tobytes() and t3.tobytes() == sites.tobytes()
+        # ... and as a single thread-per-read launch (the default above is the split with the warp-per-read prescan; reads with more than
+        # 32 keys fall back to the thread-per-read prescan)
+        h4, t4 = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=0)
+        assert h4.tobytes() == heads.tobytes() and t4.tobytes() == sites.tobytes()
         # the same batch with 32 key slots per read through the shared-memory variant of the kernel
         s32 = {k: (np.ascontiguousarray(v[:, :32]) if getattr(v, "ndim", 1) == 2 else v) for k, v in seeds.items()}
         if int(seeds["nkeys"].max()) <= 32:
