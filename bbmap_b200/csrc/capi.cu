@@ -830,6 +830,69 @@ extern "C" int bbm_noindel_batch_host(bbm_ctx* c, const int8_t* reads, int64_t r
     return BBM_OK;
 }
 
+// =====================  tip-deletion search and mate rescue scans (rescue.cu)  =====================
+extern "C" int bbm_launch_tipdel(const int8_t* reads, const int8_t* refs, const bbm_tipdel_task* tasks, long long n, const bbm_tipdel_cfg* cfg,
+                                 bbm_tipdel_out* outs, cudaStream_t st);
+extern "C" int bbm_launch_rescue(const int8_t* reads, const int8_t* refs, const bbm_rescue_task* tasks, long long n, const bbm_rescue_cfg* cfg,
+                                 bbm_rescue_out* outs, cudaStream_t st);
+template <class Task, class Cfg, class Out, class Launch>
+static int run_scan(bbm_ctx* c, const char* what, Launch launch, const int8_t* dr, const int8_t* dref, const Task* dt, int64_t n, const Cfg* cfg,
+                    Out* dout, cudaStream_t st, float* ms_out) {
+    if (n <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    if (ms_out) CK(cudaEventRecord(c->ev0, st));
+    int e = launch(dr, dref, dt, (long long)n, cfg, dout, st);
+    if (e) return fail(BBM_E_CUDA, what, (cudaError_t)e);
+    c->launches += 1;
+    if (ms_out) { CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1)); float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    return BBM_OK;
+}
+template <class Task, class Cfg, class Out, class Launch>
+static int run_scan_host(bbm_ctx* c, const char* what, Launch launch, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const Task* tasks,
+                         int64_t n, const Cfg* cfg, Out* outs) {
+    if (n <= 0) return BBM_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (tasks[i].read_len < 0 || tasks[i].read_off < 0 || tasks[i].read_off + tasks[i].read_len > reads_bytes || tasks[i].ref_off < 0 || tasks[i].ref_len < 0)
+            return fail(BBM_E_ARG, "scan task outside the read buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t tb = (size_t)n * sizeof(Task), ob = (size_t)n * sizeof(Out);
+    if (c->d_reads.ensure((size_t)reads_bytes + 16) || c->d_tasks.ensure(tb) || c->d_outs.ensure(ob)) return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(c->d_reads.p, reads, (size_t)reads_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, tasks, tb, cudaMemcpyHostToDevice, st));
+    int rc = run_scan(c, what, launch, (const int8_t*)c->d_reads.p, d_refs, (const Task*)c->d_tasks.p, n, cfg, (Out*)c->d_outs.p, st, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(outs, c->d_outs.p, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BBM_OK;
+}
+extern "C" int bbm_tipdel_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_tipdel_task* d_tasks, int64_t n,
+                                    const bbm_tipdel_cfg* cfg, bbm_tipdel_out* d_outs, void* stream, float* kernel_ms_out) {
+    if (!c || !d_reads || !d_refs || !d_tasks || !cfg || !d_outs) return fail(BBM_E_ARG, "bbm_tipdel_batch_dev: null pointer");
+    if (cfg->max_tiplen < 3 || cfg->max_tiplen > 32) return fail(BBM_E_ARG, "bbm_tipdel: max_tiplen must be in 3..32");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_scan(c, "tipdel_kernel launch", bbm_launch_tipdel, d_reads, d_refs, d_tasks, n, cfg, d_outs, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+extern "C" int bbm_tipdel_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_tipdel_task* tasks, int64_t n,
+                                     const bbm_tipdel_cfg* cfg, bbm_tipdel_out* outs) {
+    if (!c || !reads || !d_refs || !tasks || !cfg || !outs) return fail(BBM_E_ARG, "bbm_tipdel_batch_host: null pointer");
+    if (cfg->max_tiplen < 3 || cfg->max_tiplen > 32) return fail(BBM_E_ARG, "bbm_tipdel: max_tiplen must be in 3..32");
+    return run_scan_host(c, "tipdel_kernel launch", bbm_launch_tipdel, reads, reads_bytes, d_refs, tasks, n, cfg, outs);
+}
+extern "C" int bbm_rescue_batch_dev(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_rescue_task* d_tasks, int64_t n,
+                                    const bbm_rescue_cfg* cfg, bbm_rescue_out* d_outs, void* stream, float* kernel_ms_out) {
+    if (!c || !d_reads || !d_refs || !d_tasks || !cfg || !d_outs) return fail(BBM_E_ARG, "bbm_rescue_batch_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return run_scan(c, "rescue_kernel launch", bbm_launch_rescue, d_reads, d_refs, d_tasks, n, cfg, d_outs, stream ? (cudaStream_t)stream : c->stream, kernel_ms_out);
+}
+extern "C" int bbm_rescue_batch_host(bbm_ctx* c, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_rescue_task* tasks, int64_t n,
+                                     const bbm_rescue_cfg* cfg, bbm_rescue_out* outs) {
+    if (!c || !reads || !d_refs || !tasks || !cfg || !outs) return fail(BBM_E_ARG, "bbm_rescue_batch_host: null pointer");
+    return run_scan_host(c, "rescue_kernel launch", bbm_launch_rescue, reads, reads_bytes, d_refs, tasks, n, cfg, outs);
+}
+
 // =====================  k-mer index build + analysis  =====================
 static void index_free(bbm_ctx* c) {
     for (auto& b : c->iblocks) { if (b.starts) cudaFree(b.starts); if (b.sites) cudaFree(b.sites); }

@@ -288,6 +288,47 @@ int  bbm_sam_batch_host(bbm_ctx* ctx, const bbm_sam_task* tasks, int64_t n, cons
                         const int32_t* scaf_loc, const int32_t* scaf_len, int32_t nchroms, const bbm_sam_cfg* cfg, bbm_sam_out* outs,
                         int8_t* cigar_buf, const int64_t* cigar_off);
 
+/* ---- ungapped scans around candidate sites: tip-deletion search and mate rescue ----
+ * bbm_tipdel_*: AbstractMapThread.findTipDeletions(SiteScore ss, bases, maxImperfectScore, lookRight, lookLeft)
+ *   (current/align2/AbstractMapThread.java:1107-1141) with findTipDeletionsRight/Left (:2178-2294): per site, how far stop may move
+ *   right / start may move left so that slow alignment sees a deletion near the read tip.  The caller then rescoring the site with
+ *   scoreNoIndels (bbm_noindel_*) is AbstractMapThread.findTipDeletions(Read,...) :1073-1104.
+ * bbm_rescue_*: AbstractMapThread.quickRescue (:2303-2405): best ungapped placement of the loose mate within searchDist of loc,
+ *   plus SiteScore.setPerfect / isInBounds of the site it returns (stream/SiteScore.java:239-291, 425-428). */
+typedef struct {                /* 48 bytes */
+    int64_t read_off, ref_off;  /* bases on the site's strand; chromosome array (ChromosomeArray.array) */
+    int32_t read_len, ref_len;  /* ref_len = array.length */
+    int32_t min_index;          /* ChromosomeArray.minIndex */
+    int32_t start, stop;        /* SiteScore.start / stop */
+    int32_t slow_score, max_imperfect;   /* nothing is searched when slowScore >= maxImperfectScore */
+    int32_t flags;              /* bit0 lookRight, bit1 lookLeft */
+} bbm_tipdel_task;
+typedef struct { int32_t start, stop, right, left; } bbm_tipdel_out;      /* new start/stop; right = x, left = y (0 = unchanged) */
+typedef struct {                /* defaults: TIP_SEARCH_DIST=100 (BBMap.java:59), TIP_DELETION_MAX_TIPLEN=8 (AbstractMapThread.java:2989),
+                                   ALIGN_COLUMNS=3000, SLOW_RESCUE_PADDING=8 (BBMap.java:57-58) */
+    int32_t search_range, max_tiplen, align_columns, slow_rescue_padding;
+} bbm_tipdel_cfg;
+typedef struct {                /* 56 bytes */
+    int64_t read_off, ref_off;
+    int32_t read_len, ref_len, min_index, max_index;   /* max_index = ChromosomeArray.maxIndex (isInBounds) */
+    int32_t loc, search_dist, ideal_start, max_mismatches;
+    int32_t flags, pad_;        /* bit0 searchRight */
+} bbm_rescue_task;
+typedef struct {                /* 32 bytes; start = -1: quickRescue returned null */
+    int32_t start, stop, mismatches /* SiteScore.slowScore as left by quickRescue */, max_contig, score;
+    int32_t perfect;            /* bit0 perfect, bit1 semiperfect */
+    int32_t in_bounds, pad_;
+} bbm_rescue_out;
+typedef struct { int32_t points_match /*70*/, points_match2 /*100*/, use_affine /*1*/, base_hit_score /*100*/; } bbm_rescue_cfg;
+int  bbm_tipdel_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_refs, const bbm_tipdel_task* d_tasks, int64_t n,
+                          const bbm_tipdel_cfg* cfg, bbm_tipdel_out* d_outs, void* stream, float* kernel_ms_out);
+int  bbm_tipdel_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_tipdel_task* tasks, int64_t n,
+                           const bbm_tipdel_cfg* cfg, bbm_tipdel_out* outs);
+int  bbm_rescue_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_refs, const bbm_rescue_task* d_tasks, int64_t n,
+                          const bbm_rescue_cfg* cfg, bbm_rescue_out* d_outs, void* stream, float* kernel_ms_out);
+int  bbm_rescue_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_rescue_task* tasks, int64_t n,
+                           const bbm_rescue_cfg* cfg, bbm_rescue_out* outs);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

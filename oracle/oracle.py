@@ -216,6 +216,35 @@ class Oracle:
         self.lib.orc_sam_batch(_p(tasks), C.c_int64(len(tasks)), _p(mb), _p(so), _p(sl), _p(sn), C.c_int32(len(so) - 1), _p(cfg), _p(outs), _p(cbuf), _p(coff))
         return outs, cbuf, coff
 
+    # ---------------- tip-deletion search / mate rescue scans ----------------
+    def tipdel_batch(self, reads, refs, tasks, cfg):
+        from bbmap_b200.rescue import TIPDEL_OUT_DTYPE, TIPDEL_TASK_DTYPE
+        reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
+        tasks = np.ascontiguousarray(tasks, TIPDEL_TASK_DTYPE); outs = np.zeros(len(tasks), TIPDEL_OUT_DTYPE)
+        self.lib.orc_tipdel_batch.restype = None
+        self.lib.orc_tipdel_batch(_p(reads), _p(refs), _p(tasks), C.c_int64(len(tasks)), _p(cfg), _p(outs))
+        return outs
+
+    def rescue_batch(self, reads, refs, tasks, cfg):
+        from bbmap_b200.rescue import RESCUE_OUT_DTYPE, RESCUE_TASK_DTYPE
+        reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
+        tasks = np.ascontiguousarray(tasks, RESCUE_TASK_DTYPE); outs = np.zeros(len(tasks), RESCUE_OUT_DTYPE)
+        self.lib.orc_rescue_batch.restype = None
+        self.lib.orc_rescue_batch(_p(reads), _p(refs), _p(tasks), C.c_int64(len(tasks)), _p(cfg), _p(outs))
+        return outs
+
+    def find_tip_deletions_right(self, bases, ref, min_index, original_stop, search_dist, tiplen):
+        b = np.ascontiguousarray(bases).view(np.int8); r = np.ascontiguousarray(ref).view(np.int8)
+        self.lib.orc_find_tip_deletions_right.restype = C.c_int
+        return self.lib.orc_find_tip_deletions_right(_p(b), C.c_int(len(b)), _p(r), C.c_int(len(r)), C.c_int(min_index), C.c_int(original_stop),
+                                                     C.c_int(search_dist), C.c_int(tiplen))
+
+    def find_tip_deletions_left(self, bases, ref, min_index, original_start, search_dist, tiplen):
+        b = np.ascontiguousarray(bases).view(np.int8); r = np.ascontiguousarray(ref).view(np.int8)
+        self.lib.orc_find_tip_deletions_left.restype = C.c_int
+        return self.lib.orc_find_tip_deletions_left(_p(b), C.c_int(len(b)), _p(r), C.c_int(len(r)), C.c_int(min_index), C.c_int(original_start),
+                                                    C.c_int(search_dist), C.c_int(tiplen))
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
