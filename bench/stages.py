@@ -52,6 +52,17 @@ def cpu_side(R, cb, co, n_cpu=20000):
     tasks["read_off"] = off[rid]; tasks["ref_off"] = co[S["chrom"] - 1]; tasks["read_len"] = 150
     tasks["ref_len"] = (co[S["chrom"]] - co[S["chrom"] - 1]); tasks["ref_start"] = S["start"]
     t0 = time.perf_counter(); o.noindel_batch(bases, cb, tasks); out["noindel_sites_per_s"] = len(S) / (time.perf_counter() - t0)
+    # quickRescue / findTipDeletions on the plus-strand sites (rescue searched with the read's own bases around its site: same scan cost)
+    from bbmap_b200 import rescue as rs
+    rt = np.zeros(len(S), rs.RESCUE_TASK_DTYPE)
+    rt["read_off"] = tasks["read_off"]; rt["ref_off"] = tasks["ref_off"]; rt["read_len"] = 150; rt["ref_len"] = tasks["ref_len"]
+    rt["max_index"] = rt["ref_len"] - 1; rt["loc"] = S["start"] - 400; rt["ideal_start"] = S["start"]; rt["search_dist"] = 600 + 250
+    rt["max_mismatches"] = 32; rt["flags"] = 1
+    t0 = time.perf_counter(); o.rescue_batch(bases, cb, rt, rs.rescue_cfg()); out["rescue_tasks_per_s"] = len(S) / (time.perf_counter() - t0)
+    tt = np.zeros(len(S), rs.TIPDEL_TASK_DTYPE)
+    tt["read_off"] = tasks["read_off"]; tt["ref_off"] = tasks["ref_off"]; tt["read_len"] = 150; tt["ref_len"] = tasks["ref_len"]
+    tt["start"] = S["start"]; tt["stop"] = S["stop"]; tt["max_imperfect"] = 1; tt["flags"] = 3
+    t0 = time.perf_counter(); o.tipdel_batch(bases, cb, tt, rs.tipdel_cfg()); out["tipdel_sites_per_s"] = len(S) / (time.perf_counter() - t0)
     return out
 
 
@@ -170,6 +181,48 @@ def run(pairs=200_000, genome_len=4_600_000, reps=5, stage="all", device=0, hbm_
     t = t1 + t2
     alg = len(S) * (32 + 4 + 300)
     out["noindel"] = {"ms": t, "sites_per_s": len(S) / (t / 1e3), "alg_bytes": alg, "GBps": alg / (t / 1e3) / 1e9, "frac_hbm": alg / (t / 1e3) / 1e9 / hbm_peak}
+    # ---- f3 mate rescue (quickRescue) and tip-deletion search over the top site of every read ----
+    from bbmap_b200 import rescue as rs
+    has = ns > 0
+    anchors = np.nonzero(has)[0]
+    A = best[anchors]; mate = anchors ^ 1
+    rt = np.zeros(len(anchors), rs.RESCUE_TASK_DTYPE)
+    into = (A["stop"] - A["start"] - 1 + 150 * 11 // 16).astype(np.int64)          # searchIntoAnchor (AbstractMapThread.java:1187)
+    plusA = A["strand"] == 0
+    rt["read_off"] = R["off"][mate]; rt["ref_off"] = co[A["chrom"] - 1]; rt["read_len"] = 150
+    rt["ref_len"] = (co[A["chrom"]] - co[A["chrom"] - 1]); rt["min_index"] = 0; rt["max_index"] = rt["ref_len"] - 1
+    rt["loc"] = np.where(plusA, A["stop"] - into, A["start"] + into)
+    rt["ideal_start"] = np.where(plusA, A["stop"] + 100, A["start"] - 100)           # AVERAGE_PAIR_DIST=100
+    rt["search_dist"] = 600 + into; rt["max_mismatches"] = 32; rt["flags"] = plusA.astype(np.int32)
+    d_ro = torch.zeros(len(rt) * rs.RESCUE_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    rcfg = rs.rescue_cfg(); tot_ms = 0.0; found = 0; right_place = 0; starts_scanned = 0
+    for strandA, buf in ((0, d_basesM), (1, d_bases)):                                # the loose mate is searched on the strand opposite to the anchor
+        sel = np.nonzero(A["strand"] == strandA)[0]
+        if not len(sel):
+            continue
+        tsel = np.ascontiguousarray(rt[sel]); d_rt = torch.from_numpy(tsel.view(np.uint8)).to(dev)
+        tot_ms += timed(lambda: _lib.check(L.bbm_rescue_batch_dev(h, p(buf), d_chroms, p(d_rt), len(tsel), rcfg.ctypes.data_as(C.c_void_p), p(d_ro), None, C.byref(ms)), "rescue"))
+        ro = np.frombuffer(d_ro[: len(tsel) * rs.RESCUE_OUT_DTYPE.itemsize].cpu().numpy().tobytes(), rs.RESCUE_OUT_DTYPE)
+        found += int((ro["start"] >= 0).sum()); right_place += int((np.abs(ro["start"] - tr[mate[sel], 2]) <= 8).sum())
+        starts_scanned += int((tsel["search_dist"].astype(np.int64) + 1).sum())
+    alg = len(rt) * (56 + 32 + 150) + starts_scanned + len(rt) * 150
+    out["rescue"] = {"ms": tot_ms, "tasks_per_s": len(rt) / (tot_ms / 1e3), "starts_per_s": starts_scanned / (tot_ms / 1e3), "found": found / max(1, len(rt)),
+                     "found_at_mate_origin": right_place / max(1, len(rt)), "alg_bytes": alg, "GBps": alg / (tot_ms / 1e3) / 1e9,
+                     "frac_hbm": alg / (tot_ms / 1e3) / 1e9 / hbm_peak,
+                     "note": "quickRescue of each read's mate from the read's top site: searchDist 600+searchIntoAnchor, maxMismatches 32; algorithmic bytes = one pass over the search window + read + task/out records"}
+    tt = np.zeros(len(S), rs.TIPDEL_TASK_DTYPE)
+    tt["read_off"] = tasks["read_off"]; tt["ref_off"] = tasks["ref_off"]; tt["read_len"] = 150; tt["ref_len"] = tasks["ref_len"]
+    tt["start"] = S["start"]; tt["stop"] = S["stop"]; tt["slow_score"] = 0; tt["max_imperfect"] = 1; tt["flags"] = 3
+    d_to = torch.zeros(len(tt) * rs.TIPDEL_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    tcfg = rs.tipdel_cfg(); tot_ms = 0.0
+    for sel, buf in ((ids, d_bases), (idm, d_basesM)):
+        if not len(sel):
+            continue
+        tsel = np.ascontiguousarray(tt[sel]); d_tt = torch.from_numpy(tsel.view(np.uint8)).to(dev)
+        tot_ms += timed(lambda: _lib.check(L.bbm_tipdel_batch_dev(h, p(buf), d_chroms, p(d_tt), len(tsel), tcfg.ctypes.data_as(C.c_void_p), p(d_to), None, C.byref(ms)), "tipdel"))
+    alg = len(tt) * (48 + 16 + 2 * 8 + 2 * 8)
+    out["tipdel"] = {"ms": tot_ms, "sites_per_s": len(tt) / (tot_ms / 1e3), "alg_bytes": alg, "GBps": alg / (tot_ms / 1e3) / 1e9, "frac_hbm": alg / (tot_ms / 1e3) / 1e9 / hbm_peak,
+                     "note": "findTipDeletions (both tips) over every emitted site; most sites stop after the 8-base tip check (<3 mismatches)"}
     idx.close()
     # ---- a16 BandedAligner on G6-shaped pairs ----
     q, rf, bt = wl.make_banded_tasks(20_000, seed=6)
