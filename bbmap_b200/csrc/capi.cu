@@ -893,6 +893,87 @@ extern "C" int bbm_rescue_batch_host(bbm_ctx* c, const int8_t* reads, int64_t re
     return run_scan_host(c, "rescue_kernel launch", bbm_launch_rescue, reads, reads_bytes, d_refs, tasks, n, cfg, outs);
 }
 
+// =====================  per-read site-list policies (sitelist.cu)  =====================
+extern "C" int bbm_sitelist_max_cap();
+extern "C" int bbm_launch_sitelist(int op, bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int8_t* basesP,
+                                   const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const bbm_policy_cfg* cfg, bbm_read_out* out,
+                                   cudaStream_t st);
+extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, const bbm_site* sites, long long nreads, int maxSites, bbm_ss* lists,
+                                               int* nss, int cap, cudaStream_t st);
+static int sitelist_args(int op, int cap, const bbm_policy_cfg* cfg) {
+    if (op != BBM_SL_TRIM && op != BBM_SL_NOINDEL && op != BBM_SL_FINAL) return fail(BBM_E_ARG, "bbm_sitelist: unknown op");
+    if (cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_sitelist: cap must be in 1..64");
+    if (!cfg || cfg->min_trim_sites_to_retain < 1 || cfg->max_trim_sites_to_retain <= cfg->min_trim_sites_to_retain) return fail(BBM_E_ARG, "bbm_sitelist: bad policy cfg");
+    return BBM_OK;
+}
+extern "C" int bbm_sitelist_from_search_dev(bbm_ctx* c, const bbm_search_head* d_heads, const bbm_site* d_sites, int64_t nreads, int32_t max_sites,
+                                            bbm_ss* d_lists, int32_t* d_nss, int32_t cap, void* stream) {
+    if (!c || !d_heads || !d_sites || !d_lists || !d_nss || max_sites < 1 || cap < 1) return fail(BBM_E_ARG, "bbm_sitelist_from_search_dev: bad argument");
+    if (nreads <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int e = bbm_launch_sitelist_from_search(d_heads, d_sites, nreads, max_sites, d_lists, d_nss, cap, stream ? (cudaStream_t)stream : c->stream);
+    if (e) return fail(BBM_E_CUDA, "sitelist_from_search_kernel launch", (cudaError_t)e);
+    c->launches++;
+    return BBM_OK;
+}
+extern "C" int bbm_sitelist_batch_dev(bbm_ctx* c, int32_t op, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                      const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off,
+                                      const bbm_policy_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out) {
+    if (!c || !d_lists || !d_nss || !d_read_off || !d_out) return fail(BBM_E_ARG, "bbm_sitelist_batch_dev: null pointer");
+    if (int rc = sitelist_args(op, cap, cfg)) return rc;
+    if (op == BBM_SL_NOINDEL && (!d_basesP || !d_basesM || !d_refs || !d_chrom_off)) return fail(BBM_E_ARG, "bbm_sitelist_batch_dev: BBM_SL_NOINDEL needs reads and reference");
+    if (nreads <= 0) { if (kernel_ms_out) *kernel_ms_out = 0.f; return BBM_OK; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (kernel_ms_out) CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_sitelist(op, d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_basesP, d_basesM, d_refs, (const long long*)d_chrom_off, cfg, d_out, st);
+    if (e) return fail(BBM_E_CUDA, "sitelist_kernel launch", (cudaError_t)e);
+    c->launches++;
+    if (kernel_ms_out) { CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1)); float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *kernel_ms_out = ms; }
+    return BBM_OK;
+}
+extern "C" int bbm_sitelist_batch_host(bbm_ctx* c, int32_t op, bbm_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off,
+                                       const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
+                                       const bbm_policy_cfg* cfg, bbm_read_out* out) {
+    if (!c || !lists || !nss || !read_off || !out) return fail(BBM_E_ARG, "bbm_sitelist_batch_host: null pointer");
+    if (int rc = sitelist_args(op, cap, cfg)) return rc;
+    if (op == BBM_SL_NOINDEL && (!basesP || !basesM || !d_refs || !chrom_off || nchroms < 1)) return fail(BBM_E_ARG, "bbm_sitelist_batch_host: BBM_SL_NOINDEL needs reads and reference");
+    if (nreads <= 0) return BBM_OK;
+    for (int64_t r = 0; r < nreads; ++r) {
+        if (nss[r] < 0 || nss[r] > cap || read_off[r + 1] < read_off[r]) return fail(BBM_E_ARG, "bbm_sitelist_batch_host: list length outside 0..cap");
+        if (op == BBM_SL_NOINDEL) for (int i = 0; i < nss[r]; ++i) { const bbm_ss& s = lists[r * cap + i]; if (s.chrom < 1 || s.chrom > nchroms) return fail(BBM_E_ARG, "bbm_sitelist_batch_host: chromosome out of range"); }
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t lb = (size_t)nreads * cap * sizeof(bbm_ss), nb = (size_t)nreads * 4, ob = (size_t)nreads * sizeof(bbm_read_out), fb = (size_t)(nreads + 1) * 8;
+    const size_t rb = (size_t)read_off[nreads], cb = (size_t)(nchroms + 1) * 8;
+    DevBuf L_, N_, O_, F_, P_, M_, C_;
+    const bool need = op == BBM_SL_NOINDEL;
+    if (L_.ensure(lb) || N_.ensure(nb) || O_.ensure(ob) || F_.ensure(fb) || (need && (P_.ensure(rb + 16) || M_.ensure(rb + 16) || C_.ensure(cb)))) return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(L_.p, lists, lb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(N_.p, nss, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(F_.p, read_off, fb, cudaMemcpyHostToDevice, st));
+    if (need) {
+        CK(cudaMemcpyAsync(P_.p, basesP, rb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(M_.p, basesM, rb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(C_.p, chrom_off, cb, cudaMemcpyHostToDevice, st));
+    }
+    int e = bbm_launch_sitelist(op, (bbm_ss*)L_.p, (int*)N_.p, nreads, cap, (const long long*)F_.p, (const int8_t*)P_.p, (const int8_t*)M_.p, d_refs, (const long long*)C_.p, cfg, (bbm_read_out*)O_.p, st);
+    int rc = BBM_OK;
+    if (e) rc = fail(BBM_E_CUDA, "sitelist_kernel launch", (cudaError_t)e);
+    else {
+        c->launches++;
+        cudaError_t ce = cudaMemcpyAsync(lists, L_.p, lb, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(nss, N_.p, nb, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, O_.p, ob, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) rc = fail(BBM_E_CUDA, "sitelist copy back", ce);
+    }
+    L_.release(); N_.release(); O_.release(); F_.release(); P_.release(); M_.release(); C_.release();
+    return rc;
+}
+
 // =====================  k-mer index build + analysis  =====================
 static void index_free(bbm_ctx* c) {
     for (auto& b : c->iblocks) { if (b.starts) cudaFree(b.starts); if (b.sites) cudaFree(b.sites); }

@@ -1,0 +1,322 @@
+// sitelist.cu — the per-read site-list policies of the unpaired mapping loop, on the device (part of SURVEY.md §8 f1).
+//   BBMapThread.processRead list handling     current/align2/BBMapThread.java:420-431, 440-443, 478-553
+//   BBMapThread.trimList (affine branch)      :140-249
+//   Tools.trimSiteList / trimSitesBelowCutoff / mergeDuplicateSites / countTopScores / removeLowQualitySitesUnpaired
+//                                             current/align2/Tools.java:654-673, 1106-1160, 697-760, 913-931, 986-1003
+//   SiteScore.compareTo / PCOMP / positionalMatch / setPerfect   current/stream/SiteScore.java:55-76, 379-395, 353-365, 239-291
+//   AbstractMapThread.scoreNoIndels(Read,...) current/align2/AbstractMapThread.java:762-855
+//
+// One thread per read: the lists are a handful of 80-byte records (a read keeps 1-3 sites after trimming), every policy is a short
+// sequential pass whose outcome depends on the order of the elements, and the reads of a batch are independent.  Removals are kept as a
+// bit mask and applied by one compaction, which is what the reference's "set to null, then condenseStrict" does.  Java's float
+// arithmetic (int -> float conversions, one rounding per operation, truncation by the (int) cast) is spelled out with __fmul_rn /
+// __fadd_rn / __fdiv_rn so that no multiply-add is contracted.
+#include <cuda_runtime.h>
+#include "msa_common.cuh"
+
+namespace bbm {
+
+constexpr int SL_MAX_CAP = 64;
+
+__device__ __forceinline__ int ss_compare(const bbm_ss& a, const bbm_ss& o) {      // SiteScore.compareTo
+    int x = o.score - a.score; if (x) return x;
+    x = o.slow_score - a.slow_score; if (x) return x;
+    x = o.paired_score - a.paired_score; if (x) return x;
+    x = o.quick_score - a.quick_score; if (x) return x;
+    x = a.chrom - o.chrom; if (x) return x;
+    return a.start - o.start;
+}
+__device__ __forceinline__ int ss_pcomp(const bbm_ss& a, const bbm_ss& b) {        // SiteScore.PCOMP
+    if (a.chrom != b.chrom) return a.chrom - b.chrom;
+    if (a.start != b.start) return a.start - b.start;
+    if (a.stop != b.stop) return a.stop - b.stop;
+    if (a.strand != b.strand) return a.strand - b.strand;
+    if (a.score != b.score) return b.score - a.score;
+    if (a.slow_score != b.slow_score) return b.slow_score - a.slow_score;
+    if (a.quick_score != b.quick_score) return b.quick_score - a.quick_score;
+    if (a.perfect != b.perfect) return a.perfect ? -1 : 1;
+    if (a.rescued != b.rescued) return a.rescued ? 1 : -1;
+    return 0;
+}
+template <bool POSITIONAL>
+__device__ void stable_sort(bbm_ss* v, int n) {        // Collections.sort is stable; so is insertion sort
+    for (int i = 1; i < n; i++) {
+        const bbm_ss x = v[i]; int j = i - 1;
+        while (j >= 0 && (POSITIONAL ? ss_pcomp(v[j], x) : ss_compare(v[j], x)) > 0) { v[j + 1] = v[j]; j--; }
+        if (j + 1 != i) v[j + 1] = x;
+    }
+}
+__device__ int compact(bbm_ss* v, int n, unsigned long long dead) {
+    if (!dead) return n;
+    int k = 0;
+    for (int i = 0; i < n; i++) if (!((dead >> i) & 1ull)) { if (k != i) v[k] = v[i]; k++; }
+    return k;
+}
+
+// Tools.trimSiteList + trimSitesBelowCutoff (retainSemiperfect = true)
+__device__ int trim_site_list(bbm_ss* v, int& n, float frac, bool retainPaired, int minS, int maxS) {
+    if (n == 0) return -999999;
+    if (n == 1) return v[0].score;
+    int maxScore = -999999;
+    if (minS > 1 && minS < n) maxScore = v[0].score;
+    else for (int i = 0; i < n; i++) maxScore = imax(maxScore, v[i].score);
+    const int cutoff = (int)__fmul_rn((float)maxScore, frac);
+    if (n <= minS) return maxScore;
+    while (n > maxS) n--;
+    int removed = 0; const int maxToRemove = n - minS;
+    unsigned long long dead = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        if (!v[i].semiperfect && v[i].score < cutoff && (!retainPaired || v[i].paired_score <= 0)) {
+            dead |= 1ull << i; removed++;
+            if (removed >= maxToRemove) break;
+        }
+    }
+    n = compact(v, n, dead);
+    return maxScore;
+}
+__device__ int trim_list(bbm_ss* v, int& n, bool retainPaired, int maxScore, bool specialCasePerfect, int minS, int maxS) {
+    if (n == 0) return -99999;
+    if (n == 1) return v[0].score;
+    const int highest = trim_site_list(v, n, .6f, retainPaired, minS, maxS);
+    if (highest == maxScore && specialCasePerfect) {
+        trim_site_list(v, n, .94f, retainPaired, minS, maxS);
+        if (n > 8) trim_site_list(v, n, .99f, retainPaired, minS, maxS);
+        return highest;
+    }
+    const int mstr2 = (minS <= 1 ? 1 : minS + 1);
+    if (n > 4) trim_site_list(v, n, .65f, retainPaired, minS, maxS);
+    if (n > 8) trim_site_list(v, n, .7f, retainPaired, minS, maxS);
+    if (n > 12) trim_site_list(v, n, .75f, retainPaired, minS, maxS);
+    if (n > 16) trim_site_list(v, n, .8f, retainPaired, minS, maxS);
+    if (n > 20) trim_site_list(v, n, .85f, retainPaired, minS, maxS);
+    if (n > 24) trim_site_list(v, n, .9f, retainPaired, minS, maxS);
+    if (n > 32) trim_site_list(v, n, .95f, retainPaired, minS, maxS);
+    if (n > 40) trim_site_list(v, n, .97f, retainPaired, mstr2, maxS);
+    if (n > 48) trim_site_list(v, n, .99f, retainPaired, mstr2, maxS);
+    return highest;
+}
+
+__device__ __forceinline__ int max_quality(int len) { return 70 + (len - 1) * 100; }                    // …JNI.java:1321-1323
+__device__ __forceinline__ int max_imperfect(int len) { return max_quality(len) + imin(-472, -395 - 100); }   // :1331-1336
+
+// MSA.scoreNoIndels (…JNI.java:1033-1089), score only (the kernel in noindel.cu also writes match strings)
+__device__ int score_no_indels(const int8_t* __restrict__ read, int len, const int8_t* __restrict__ ref, int refLen, int refStart) {
+    int readStart = 0, readStop = len;
+    const long long refStop = (long long)refStart + len;
+    if (refStart < 0) readStart = -refStart;
+    if (refStop > refLen) readStop -= (int)(refStop - refLen);
+    int score = 0, mode = -1, timeInMode = 0;
+    for (int k = readStart; k < readStop; ++k) {
+        const int c = read[k], r = ref[refStart + k];
+        if (c == r && c != 'N') { if (mode == 0) { timeInMode++; score += 100; } else { timeInMode = 0; score += 70; } mode = 0; }
+        else if (c < 0 || c == 'N') {}
+        else if (r < 0 || r == 'N') {}
+        else { if (mode == 3) timeInMode++; else timeInMode = 0; score += timeInMode == 0 ? -127 : (timeInMode < 5 ? -51 : -25); mode = 3; }
+    }
+    return score;
+}
+
+// SiteScore.setPerfect(bases) (stream/SiteScore.java:239-291)
+__device__ void ss_set_perfect(bbm_ss& s, const int8_t* __restrict__ bases, int len, const int8_t* __restrict__ ref, int refLen) {
+    if (len != s.stop - s.start + 1) { s.perfect = 0; s.semiperfect = 0; return; }
+    bool perfect = true, semiperfect = true;
+    int refloc = s.start, readloc = 0, N = 0;
+    const int mx = imin(s.stop, refLen - 1), nlimit = len / 2;
+    if (s.start < 0) { N -= s.start; readloc -= s.start; refloc -= s.start; perfect = false; }
+    if (s.stop >= refLen) { N += (s.stop - refLen + 1); perfect = false; }
+    if (N > nlimit) { s.perfect = 0; s.semiperfect = 0; return; }
+    for (; refloc <= mx; refloc++, readloc++) {
+        const int8_t c = bases[readloc], r = ref[refloc];
+        if (c != r || c == 'N') {
+            perfect = false;
+            if (c == 'N') semiperfect = false;
+            if (r != 'N' || (N = N + 1) > nlimit) { s.perfect = 0; s.semiperfect = 0; return; }
+        }
+    }
+    semiperfect = (semiperfect && (N <= nlimit));
+    perfect = (perfect && semiperfect && (N == 0));
+    s.perfect = perfect ? 1 : 0; s.semiperfect = semiperfect ? 1 : 0;
+}
+
+__device__ bool positional_match(const bbm_ss& a, const bbm_ss& b, bool testGaps) {
+    if (a.chrom != b.chrom || a.strand != b.strand || a.start != b.start || a.stop != b.stop) return false;
+    if (!testGaps || (a.ngaps == 0 && b.ngaps == 0)) return true;
+    if (a.ngaps != b.ngaps) return false;            // covers "one is null" as well
+    for (int i = 0; i < a.ngaps; i++) if (a.gaps[i] != b.gaps[i]) return false;
+    return true;
+}
+
+// Tools.mergeDuplicateSites(list, true, true)
+__device__ int merge_duplicate_sites(bbm_ss* v, int n) {
+    if (n < 2) return n;
+    stable_sort<true>(v, n);
+    unsigned long long dead = 0;
+    int ai = 0;
+    for (int i = 1; i < n; i++) {
+        bbm_ss& a = v[ai]; const bbm_ss& b = v[i];
+        const bool same = positional_match(a, b, true);
+        if (same || positional_match(a, b, false)) {
+            if (!same) {    // same outermost boundaries, different gaps: keep the gaps of the better one (decided before the scores are merged)
+                bool takeB;
+                if (a.score != b.score) takeB = b.score > a.score;
+                else if (a.slow_score != b.slow_score) takeB = b.slow_score > a.slow_score;
+                else if (a.paired_score != b.paired_score) takeB = b.paired_score > a.paired_score;
+                else takeB = false;
+                if (takeB) { a.ngaps = b.ngaps; for (int g = 0; g < BBM_MAX_GAPS - 1; g++) a.gaps[g] = b.gaps[g]; }
+            }
+            a.slow_score = imax(a.slow_score, b.slow_score);
+            a.paired_score = (a.paired_score <= a.slow_score && b.paired_score <= a.slow_score) ? 0 : imax(0, imax(a.paired_score, b.paired_score));
+            a.score = imax(a.score, b.score);
+            a.perfect = (a.perfect || b.perfect) ? 1 : 0; a.semiperfect = (a.semiperfect || b.semiperfect) ? 1 : 0;
+            dead |= 1ull << i;
+        } else ai = i;
+    }
+    return compact(v, n, dead);
+}
+
+__device__ int count_top_scores(const bbm_ss* v, int n, int thresh) {
+    if (n == 0) return 0;
+    int count = 1; const int limit = v[0].score - thresh;
+    for (int i = 1; i < n; i++) {
+        if (v[i].score < limit) break;
+        if (v[0].start != v[i].start && v[0].stop != v[i].stop) count++;
+    }
+    return count;
+}
+
+struct SitelistParams {
+    int op; bbm_ss* lists; int* nss; long long nreads; int cap; const long long* read_off;
+    const int8_t* basesP; const int8_t* basesM; const int8_t* refs; const long long* chrom_off;
+    bbm_policy_cfg cfg; bbm_read_out* out;
+};
+
+__global__ void __launch_bounds__(128) sitelist_kernel(SitelistParams P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    bbm_ss* v = P.lists + r * P.cap;
+    int n = P.nss[r];
+    const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
+    const bbm_policy_cfg& cfg = P.cfg;
+    bbm_read_out o; o.near_perfect = 0; o.flags = 0; o.clearzone = 0; o.best_sites = 0;
+    if (P.op == BBM_SL_TRIM) {
+        if (cfg.trim_list && n > 1) {
+            if (cfg.min_trim_sites_to_retain > 1) stable_sort<false>(v, n);
+            o.best_sites = trim_list(v, n, false, max_quality(len), true, cfg.min_trim_sites_to_retain, cfg.max_trim_sites_to_retain);
+        }
+    } else if (P.op == BBM_SL_NOINDEL) {
+        const int maxSw = max_quality(len), maxImp = max_imperfect(len);
+        int numNear = 0, best = -0x7fffffff - 1; bool forceSlow = false;
+        for (int j = 0; j < n; j++) {
+            bbm_ss ss = v[j];
+            const int oldScore = ss.score, sslen = ss.stop - ss.start + 1;
+            const int8_t* bases = (ss.strand == 0 ? P.basesP : P.basesM) + P.read_off[r];
+            const int8_t* ref = P.refs + P.chrom_off[ss.chrom - 1];
+            const int refLen = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
+            if (ss.perfect) {
+                numNear++;
+                ss.slow_score = maxSw; ss.score = maxSw; ss.ngaps = 0;
+            } else {
+                int sni = score_no_indels(bases, len, ref, refLen, ss.start);
+                if (sni < oldScore && oldScore >= maxImp && sslen != len) {
+                    const int s2 = score_no_indels(bases, len, ref, refLen, ss.stop - len + 1);
+                    if (s2 >= maxImp) { sni = s2; ss.start = ss.stop - len + 1; ss_set_perfect(ss, bases, len, ref, refLen); }
+                }
+                ss.slow_score = sni; ss.score = sni;
+                if (sni >= maxImp) {
+                    numNear++;
+                    ss.stop = ss.start + len - 1; ss.ngaps = 0;
+                    if (sni >= maxSw) { ss.perfect = 1; ss.semiperfect = 1; }
+                    else ss_set_perfect(ss, bases, len, ref, refLen);
+                    if (cfg.quick_match_strings && !ss.perfect && (cfg.print_secondary || sni >= best)) ss.has_match = 1;
+                } else if (oldScore >= maxImp) forceSlow = true;
+                else if (cfg.print_secondary) forceSlow = true;
+            }
+            best = imax(ss.slow_score, best);
+            v[j] = ss;
+        }
+        o.near_perfect = n == 0 ? 0 : (forceSlow ? -numNear : numNear);
+        stable_sort<false>(v, n);
+    } else {
+        const int maxSw = max_quality(len);
+        int flags = 0, clearzone = 0, numBest = 0;
+        if (n > 0) { n = merge_duplicate_sites(v, n); stable_sort<false>(v, n); }
+        const bool perfect = n > 0 && (v[0].slow_score == maxSw || v[0].perfect);
+        if (n > 1) {
+            const int score = v[0].score;
+            if (perfect) clearzone = cfg.clearzonep;
+            else {
+                const float fmax = (float)maxSw, fs = (float)score;
+                const float cz1blimit = __fsub_rn(__fmul_rn(fmax, cfg.cz1b_scale), cfg.cz1b_flat);
+                const float cz1climit = __fsub_rn(__fmul_rn(fmax, cfg.cz1c_scale), cfg.cz1c_flat);
+                if (fs > cz1blimit) {
+                    const float t1 = (float)((maxSw - score) * cfg.clearzone1b);                       // int product first, as in Java
+                    const float t2 = __fmul_rn(__fsub_rn(fs, cz1blimit), (float)cfg.clearzone1);
+                    clearzone = (int)__fdiv_rn(__fadd_rn(t1, t2), __fsub_rn(fmax, cz1blimit));
+                } else if (fs > cz1climit) {
+                    const float t1 = __fmul_rn(__fsub_rn(cz1blimit, fs), (float)cfg.clearzone1c);
+                    const float t2 = __fmul_rn(__fsub_rn(fs, cz1climit), (float)cfg.clearzone1b);
+                    clearzone = (int)__fdiv_rn(__fadd_rn(t1, t2), __fsub_rn(cz1blimit, cz1climit));
+                } else clearzone = cfg.clearzone1c;
+            }
+            numBest = count_top_scores(v, n, clearzone);
+            if (numBest > 1) flags |= 4;
+            else {
+                const int lim = (perfect ? (int)__fmul_rn(4.f, (float)cfg.clearzone_limit1e)
+                                         : (score + cfg.clearzone1e >= maxSw ? 2 * cfg.clearzone_limit1e : cfg.clearzone_limit1e)) + 1;
+                if (n > lim && clearzone < cfg.clearzone1e) {
+                    numBest = count_top_scores(v, n, cfg.clearzone1e);
+                    if (numBest > lim) flags |= 4;
+                }
+            }
+        }
+        if (n > 0) {
+            const int lim = (int)__fmul_rn((float)maxSw, cfg.min_align_ratio);
+            if (v[0].score < lim) n = 0;
+            else {
+                const int thresh = imin(lim, imax(1, lim - cfg.clearzone3));      // Tools.removeLowQualitySitesUnpaired(list, thresh)
+                unsigned long long dead = 0;
+                for (int i = n - 1; i > 1; i--) if (v[i].slow_score < thresh) dead |= 1ull << i;
+                n = compact(v, n, dead);
+            }
+        }
+        if (n > 0) flags |= 1;
+        if (perfect && n > 0) flags |= 2;
+        o.flags = flags; o.clearzone = clearzone; o.best_sites = numBest;
+    }
+    P.nss[r] = n;
+    P.out[r] = o;
+}
+
+__global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_search_head* __restrict__ heads, const bbm_site* __restrict__ sites, long long nreads,
+                                                                   int maxSites, bbm_ss* __restrict__ lists, int* __restrict__ nss, int cap) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    const int n = imin(imin(heads[r].nsites, maxSites), cap);
+    for (int i = 0; i < n; i++) {
+        const bbm_site s = sites[r * maxSites + i];
+        bbm_ss q = {};
+        q.chrom = s.chrom; q.start = s.start; q.stop = s.stop; q.hits = s.hits; q.score = s.score; q.quick_score = s.score;
+        q.strand = s.strand; q.perfect = s.perfect; q.semiperfect = s.semiperfect; q.ngaps = s.ngaps;
+        for (int g = 0; g < BBM_MAX_GAPS - 1; g++) q.gaps[g] = s.gaps[g];
+        lists[r * cap + i] = q;
+    }
+    nss[r] = n;
+}
+
+}  // namespace bbm
+
+extern "C" int bbm_sitelist_max_cap() { return bbm::SL_MAX_CAP; }
+extern "C" int bbm_launch_sitelist(int op, bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int8_t* basesP,
+                                   const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const bbm_policy_cfg* cfg, bbm_read_out* out,
+                                   cudaStream_t st) {
+    bbm::SitelistParams P;
+    P.op = op; P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP; P.basesM = basesM;
+    P.refs = refs; P.chrom_off = chrom_off; P.cfg = *cfg; P.out = out;
+    bbm::sitelist_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, const bbm_site* sites, long long nreads, int maxSites, bbm_ss* lists,
+                                               int* nss, int cap, cudaStream_t st) {
+    bbm::sitelist_from_search_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(heads, sites, nreads, maxSites, lists, nss, cap);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,59 @@
+"""Host-side mirror of the per-read site-list policies of the unpaired mapping loop (part of SURVEY 8f.1), batched for the CUDA path:
+Collections.sort + BBMapThread.trimList (current/align2/BBMapThread.java:428-431, 140-249), AbstractMapThread.scoreNoIndels(Read, ...)
+(current/align2/AbstractMapThread.java:762-855) and the post-alignment list handling (mergeDuplicateSites, Read.setPerfectFlag, clearzone /
+ambiguity, removeLowQualitySitesUnpaired; BBMapThread.java:478-553)."""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+SS_DTYPE = np.dtype([("chrom", "<i4"), ("start", "<i4"), ("stop", "<i4"), ("hits", "<i4"), ("score", "<i4"), ("quick_score", "<i4"),
+                     ("slow_score", "<i4"), ("paired_score", "<i4"), ("strand", "i1"), ("perfect", "i1"), ("semiperfect", "i1"), ("rescued", "i1"),
+                     ("ngaps", "<i4"), ("gaps", "<i4", (9,)), ("has_match", "<i4")], align=True)
+POLICY_CFG_DTYPE = np.dtype([("trim_list", "<i4"), ("min_trim_sites_to_retain", "<i4"), ("max_trim_sites_to_retain", "<i4"), ("quick_match_strings", "<i4"),
+                             ("clearzone1", "<i4"), ("clearzone1b", "<i4"), ("clearzone1c", "<i4"), ("clearzonep", "<i4"), ("clearzone3", "<i4"),
+                             ("clearzone1e", "<i4"), ("clearzone_limit1e", "<i4"), ("print_secondary", "<i4"), ("min_align_ratio", "<f4"),
+                             ("cz1b_scale", "<f4"), ("cz1b_flat", "<f4"), ("cz1c_scale", "<f4"), ("cz1c_flat", "<f4"), ("pad_", "<i4", (3,))], align=True)
+READ_OUT_DTYPE = np.dtype([("near_perfect", "<i4"), ("flags", "<i4"), ("clearzone", "<i4"), ("best_sites", "<i4")], align=True)
+assert SS_DTYPE.itemsize == 80 and POLICY_CFG_DTYPE.itemsize == 80 and READ_OUT_DTYPE.itemsize == 16
+SL_TRIM, SL_NOINDEL, SL_FINAL = 1, 2, 3
+F_MAPPED, F_PERFECT, F_AMBIGUOUS = 1, 2, 4
+
+
+def policy_cfg(**kw):
+    """BBMap defaults: TRIM_LIST=true (AbstractMapper.java:2678), MIN_TRIM_SITES_TO_RETAIN_SINGLE=3 (BBMapThread.java:62),
+    MAX_TRIM_SITES_TO_RETAIN=800 (AbstractMapThread.java:3004), CLEARZONE1/1b/1c/P/3 = (2.0, 2.6, 4.6, 1.6, 8.0) x POINTS_MATCH2
+    (BBMapThread.java:38-42,114-118), CLEARZONE1e = 2*100-70+127+1 = 258 (AbstractMapThread.java:142), CLEARZONE_LIMIT1e=40,
+    cutoffs 0.97/12x100 and 0.92/26x100 (BBMapThread.java:52-57), MINIMUM_ALIGNMENT_SCORE_RATIO=0.56 (BBMap.java:50)."""
+    c = np.zeros(1, POLICY_CFG_DTYPE)
+    d = dict(trim_list=1, min_trim_sites_to_retain=3, max_trim_sites_to_retain=800, quick_match_strings=1, clearzone1=200, clearzone1b=260,
+             clearzone1c=460, clearzonep=160, clearzone3=800, clearzone1e=258, clearzone_limit1e=40, print_secondary=0, min_align_ratio=0.56,
+             cz1b_scale=0.97, cz1b_flat=1200.0, cz1c_scale=0.92, cz1c_flat=2600.0)
+    d.update(kw)
+    for k, v in d.items():
+        c[k] = v
+    return c
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def site_lists(ctx, op, lists, nss, read_off, cfg=None, basesP=None, basesM=None, d_ref=None, chrom_off=None):
+    """Apply one policy to every read's list.  lists: SS_DTYPE[nreads, cap]; nss: int32[nreads].  Returns (lists, nss, READ_OUT_DTYPE[nreads])
+    (copies; the inputs are not modified)."""
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: site_lists has no CPU fallback")
+    cfg = policy_cfg() if cfg is None else cfg
+    lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+    n, cap = lists.shape
+    ro = np.ascontiguousarray(read_off, np.int64)
+    out = np.zeros(n, READ_OUT_DTYPE)
+    bp = None if basesP is None else np.ascontiguousarray(basesP).view(np.int8)
+    bm = None if basesM is None else np.ascontiguousarray(basesM).view(np.int8)
+    co = None if chrom_off is None else np.ascontiguousarray(chrom_off, np.int64)
+    _lib.check(L.bbm_sitelist_batch_host(ctx, op, _p(lists), _p(nss), n, cap, _p(ro), _p(bp), _p(bm), d_ref, _p(co), 0 if co is None else len(co) - 1,
+                                         _p(cfg), _p(out)), "bbm_sitelist_batch_host")
+    return lists, nss, out

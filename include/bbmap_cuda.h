@@ -329,6 +329,42 @@ int  bbm_rescue_batch_dev(bbm_ctx* ctx, const int8_t* d_reads, const int8_t* d_r
 int  bbm_rescue_batch_host(bbm_ctx* ctx, const int8_t* reads, int64_t reads_bytes, const int8_t* d_refs, const bbm_rescue_task* tasks, int64_t n,
                            const bbm_rescue_cfg* cfg, bbm_rescue_out* outs);
 
+/* ---- per-read site-list policies of the unpaired mapping loop (part of SURVEY 8f.1) ----
+ * The list handling BBMapThread.processRead does around the alignment stages (current/align2/BBMapThread.java:420-553), on the device
+ * so that search -> scoreNoIndels -> slow alignment can be chained without a host round trip:
+ *   BBM_SL_TRIM     Collections.sort + trimList (:428-431; trimList :140-249; Tools.trimSiteList / trimSitesBelowCutoff, Tools.java:654-673,1106-1160)
+ *   BBM_SL_NOINDEL  AbstractMapThread.scoreNoIndels(Read,...) (AbstractMapThread.java:762-855) + Collections.sort (:442)
+ *   BBM_SL_FINAL    mergeDuplicateSites + sort, Read.setPerfectFlag, clearzone / ambiguity, removeLowQualitySitesUnpaired (:478-553)
+ * One list of `cap` bbm_ss slots per read; nss[r] live entries. */
+typedef struct {                /* 80 bytes: the SiteScore fields the policies read and write (stream/SiteScore.java) */
+    int32_t chrom, start, stop, hits, score, quick_score, slow_score, paired_score;
+    int8_t strand, perfect, semiperfect, rescued;
+    int32_t ngaps;              /* 0 = gaps == null */
+    int32_t gaps[BBM_MAX_GAPS - 1];
+    int32_t has_match;          /* set where the reference attaches genMatchNoIndels (text: bbm_noindel_* with flag bit0) */
+} bbm_ss;
+typedef struct {                /* 80 bytes; defaults in bbmap_b200/sitelist.py (BBMapThread.java:38-62,114-118; AbstractMapThread.java:142,3004) */
+    int32_t trim_list, min_trim_sites_to_retain, max_trim_sites_to_retain, quick_match_strings;
+    int32_t clearzone1, clearzone1b, clearzone1c, clearzonep, clearzone3, clearzone1e, clearzone_limit1e, print_secondary;
+    float min_align_ratio, cz1b_scale, cz1b_flat, cz1c_scale;
+    float cz1c_flat; int32_t pad_[3];
+} bbm_policy_cfg;
+typedef struct { int32_t near_perfect /* scoreNoIndels' return value */, flags /* bit0 mapped, bit1 perfect, bit2 ambiguous */, clearzone, best_sites; } bbm_read_out;
+#define BBM_SL_TRIM 1
+#define BBM_SL_NOINDEL 2
+#define BBM_SL_FINAL 3
+/* sites as BBIndex.find emits them -> SiteScore(chrom, strand, start, stop, hits, quickScore): score = quickScore (SiteScore.java:40-52) */
+int  bbm_sitelist_from_search_dev(bbm_ctx* ctx, const bbm_search_head* d_heads, const bbm_site* d_sites, int64_t nreads, int32_t max_sites,
+                                  bbm_ss* d_lists, int32_t* d_nss, int32_t cap, void* stream);
+/* d_read_off has nreads+1 entries (read r is bases[read_off[r] .. read_off[r+1])); d_basesP/d_basesM/d_refs/d_chrom_off are only read by
+ * BBM_SL_NOINDEL (chrom_off as in bbm_index_build: chromosome c occupies refs[chrom_off[c-1] .. chrom_off[c])). */
+int  bbm_sitelist_batch_dev(bbm_ctx* ctx, int32_t op, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                            const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off,
+                            const bbm_policy_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out);
+int  bbm_sitelist_batch_host(bbm_ctx* ctx, int32_t op, bbm_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off,
+                             const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
+                             const bbm_policy_cfg* cfg, bbm_read_out* out);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

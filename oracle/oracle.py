@@ -245,6 +245,27 @@ class Oracle:
         return self.lib.orc_find_tip_deletions_left(_p(b), C.c_int(len(b)), _p(r), C.c_int(len(r)), C.c_int(min_index), C.c_int(original_start),
                                                     C.c_int(search_dist), C.c_int(tiplen))
 
+    # ---------------- per-read site-list policies ----------------
+    def sitelist(self, op, lists, nss, read_off, cfg, basesP=None, basesM=None, refs=None, chrom_off=None):
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SL_FINAL, SL_NOINDEL, SL_TRIM, SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); rl = np.ascontiguousarray(np.diff(ro), np.int32)
+        out = np.zeros(n, READ_OUT_DTYPE)
+        if op == SL_TRIM:
+            self.lib.orc_sitelist_trim.restype = None
+            self.lib.orc_sitelist_trim(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(cfg), _p(out))
+        elif op == SL_NOINDEL:
+            bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8)
+            rf = np.ascontiguousarray(refs).view(np.int8); co = np.ascontiguousarray(chrom_off, np.int64)
+            self.lib.orc_sitelist_noindel.restype = None
+            self.lib.orc_sitelist_noindel(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), _p(ro), _p(rf), _p(co), _p(cfg), _p(out))
+        else:
+            assert op == SL_FINAL
+            self.lib.orc_sitelist_final.restype = None
+            self.lib.orc_sitelist_final(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(cfg), _p(out))
+        return lists, nss, out
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)

@@ -1,0 +1,281 @@
+/* TEST INFRASTRUCTURE ONLY — see sitelist_oracle.h.  Restates, statement for statement, on an array that plays the ArrayList:
+ *   BBMapThread.processRead, the list handling around the alignment stages      current/align2/BBMapThread.java:420-431, 440-443, 478-553
+ *   BBMapThread.trimList (affine branch)                                        :140-249
+ *   Tools.trimSiteList / trimSitesBelowCutoff / condenseStrict                  current/align2/Tools.java:654-673, 1106-1160, 542-566
+ *   Tools.mergeDuplicateSites / countTopScores / removeLowQualitySitesUnpaired  :697-760, 913-931, 986-1003
+ *   SiteScore.compareTo, PositionComparator, positionalMatch, setPerfect        current/stream/SiteScore.java:55-76, 379-395, 353-365, 239-291
+ *   AbstractMapThread.scoreNoIndels(Read, ...)                                  current/align2/AbstractMapThread.java:762-855
+ *   Read.setPerfectFlag (match == null at this point)                           current/stream/Read.java:2494-2512
+ *   MSA.maxQuality / maxImperfectScore                                          current/align2/MultiStateAligner11tsJNI.java:1321-1336
+ */
+#include "sitelist_oracle.h"
+#include "host_oracle.h"
+#include <string.h>
+
+static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* SiteScore.compareTo: higher scores first */
+static int ss_compare(const orc_ss* a, const orc_ss* o) {
+    int x = o->score - a->score; if (x) return x;
+    x = o->slow_score - a->slow_score; if (x) return x;
+    x = o->paired_score - a->paired_score; if (x) return x;
+    x = o->quick_score - a->quick_score; if (x) return x;
+    x = a->chrom - o->chrom; if (x) return x;
+    return a->start - o->start;
+}
+/* SiteScore.PCOMP */
+static int ss_pcomp(const orc_ss* a, const orc_ss* b) {
+    if (a->chrom != b->chrom) return a->chrom - b->chrom;
+    if (a->start != b->start) return a->start - b->start;
+    if (a->stop != b->stop) return a->stop - b->stop;
+    if (a->strand != b->strand) return a->strand - b->strand;
+    if (a->score != b->score) return b->score - a->score;
+    if (a->slow_score != b->slow_score) return b->slow_score - a->slow_score;
+    if (a->quick_score != b->quick_score) return b->quick_score - a->quick_score;
+    if (a->perfect != b->perfect) return a->perfect ? -1 : 1;
+    if (a->rescued != b->rescued) return a->rescued ? 1 : -1;
+    return 0;
+}
+/* Collections.sort is stable: insertion sort keeps equal elements in order */
+static void stable_sort(orc_ss* v, int n, int (*cmp)(const orc_ss*, const orc_ss*)) {
+    for (int i = 1; i < n; i++) {
+        orc_ss x = v[i]; int j = i - 1;
+        while (j >= 0 && cmp(&v[j], &x) > 0) { v[j + 1] = v[j]; j--; }
+        v[j + 1] = x;
+    }
+}
+
+/* Tools.trimSitesBelowCutoff with retainSemiperfect = true */
+static int trim_below_cutoff(orc_ss* v, int n, int cutoff, int retainPaired, int minS, int maxS) {
+    if (n <= minS) return n;
+    while (n > maxS) n--;
+    int removed = 0; const int maxToRemove = n - minS;
+    char dead[4096]; memset(dead, 0, (size_t)n);
+    for (int i = n - 1; i >= 0; i--) {
+        const orc_ss* ss = &v[i];
+        if (!ss->semiperfect) {
+            if (ss->score < cutoff && (!retainPaired || ss->paired_score <= 0)) {
+                dead[i] = 1; removed++;
+                if (removed >= maxToRemove) break;
+            }
+        }
+    }
+    if (removed > 0) { int k = 0; for (int i = 0; i < n; i++) if (!dead[i]) v[k++] = v[i]; n = k; }
+    return n;
+}
+/* Tools.trimSiteList; *n is updated, returns maxScore */
+static int trim_site_list(orc_ss* v, int* n, float frac, int retainPaired, int minS, int maxS) {
+    if (*n == 0) return -999999;
+    if (*n == 1) return v[0].score;
+    int maxScore = -999999;
+    if (minS > 1 && minS < *n) maxScore = v[0].score;
+    else for (int i = 0; i < *n; i++) maxScore = imax(maxScore, v[i].score);
+    const int cutoff = (int)((float)maxScore * frac);
+    *n = trim_below_cutoff(v, *n, cutoff, retainPaired, minS, maxS);
+    return maxScore;
+}
+/* BBMapThread.trimList, USE_AFFINE_SCORE branch */
+static int trim_list(orc_ss* v, int* n, int retainPaired, int maxScore, int specialCasePerfect, int minS, int maxS) {
+    if (*n == 0) return -99999;
+    if (*n == 1) return v[0].score;
+    const int highest = trim_site_list(v, n, .6f, retainPaired, minS, maxS);
+    if (highest == maxScore && specialCasePerfect) {
+        trim_site_list(v, n, .94f, retainPaired, minS, maxS);
+        if (*n > 8) trim_site_list(v, n, .99f, retainPaired, minS, maxS);
+        return highest;
+    }
+    const int mstr2 = (minS <= 1 ? 1 : minS + 1);
+    if (*n > 4) trim_site_list(v, n, .65f, retainPaired, minS, maxS);
+    if (*n > 8) trim_site_list(v, n, .7f, retainPaired, minS, maxS);
+    if (*n > 12) trim_site_list(v, n, .75f, retainPaired, minS, maxS);
+    if (*n > 16) trim_site_list(v, n, .8f, retainPaired, minS, maxS);
+    if (*n > 20) trim_site_list(v, n, .85f, retainPaired, minS, maxS);
+    if (*n > 24) trim_site_list(v, n, .9f, retainPaired, minS, maxS);
+    if (*n > 32) trim_site_list(v, n, .95f, retainPaired, minS, maxS);
+    if (*n > 40) trim_site_list(v, n, .97f, retainPaired, mstr2, maxS);
+    if (*n > 48) trim_site_list(v, n, .99f, retainPaired, mstr2, maxS);
+    return highest;
+}
+
+static int max_quality(int len) { return 70 + (len - 1) * 100; }
+static int max_imperfect(int len) { return max_quality(len) + imin(-472, -395 - 100); }
+
+void orc_sitelist_trim(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; int n = nss[r];
+        out[r].near_perfect = 0; out[r].flags = 0; out[r].clearzone = 0; out[r].best_sites = 0;
+        if (cfg->trim_list && n > 1) {
+            if (cfg->min_trim_sites_to_retain > 1) stable_sort(v, n, ss_compare);
+            out[r].best_sites = trim_list(v, &n, 0, max_quality(read_len[r]), 1, cfg->min_trim_sites_to_retain, cfg->max_trim_sites_to_retain);
+        }
+        nss[r] = n;
+    }
+}
+
+/* SiteScore.setPerfect(bases) in full (sites of any length, possibly hanging over the array) */
+static void ss_set_perfect(orc_ss* s, const int8_t* bases, int len, const int8_t* ref, int refLen)
+{
+    if (len != s->stop - s->start + 1) { s->perfect = 0; s->semiperfect = 0; return; }
+    int perfect = 1, semiperfect = 1;
+    int refloc = s->start, readloc = 0, N = 0;
+    const int max = imin(s->stop, refLen - 1), nlimit = len / 2;
+    if (s->start < 0) { N -= s->start; readloc -= s->start; refloc -= s->start; perfect = 0; }
+    if (s->stop >= refLen) { N += (s->stop - refLen + 1); perfect = 0; }
+    if (N > nlimit) { s->perfect = 0; s->semiperfect = 0; return; }
+    for (; refloc <= max; refloc++, readloc++) {
+        const int8_t c = bases[readloc], r = ref[refloc];
+        if (c != r || c == 'N') {
+            perfect = 0;
+            if (c == 'N') semiperfect = 0;
+            if (r != 'N' || (N = N + 1) > nlimit) { s->perfect = 0; s->semiperfect = 0; return; }
+        }
+    }
+    semiperfect = (semiperfect && (N <= nlimit));
+    perfect = (perfect && semiperfect && (N == 0));
+    s->perfect = (int8_t)perfect; s->semiperfect = (int8_t)semiperfect;
+}
+
+void orc_sitelist_noindel(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
+                          const int8_t* refs, const int64_t* chrom_off, const orc_policy_cfg* cfg, orc_read_out* out)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; const int n = nss[r];
+        const int len = (int)(read_off[r + 1] - read_off[r]);
+        const int maxSw = max_quality(len), maxImp = max_imperfect(len);
+        int numPerfect = 0, numNear = 0, best = (-2147483647 - 1), forceSlow = 0;
+        for (int j = 0; j < n; j++) {
+            orc_ss* ss = &v[j];
+            const int oldScore = ss->score, sslen = ss->stop - ss->start + 1;
+            const int8_t* bases = (ss->strand == 0 ? basesP : basesM) + read_off[r];
+            const int8_t* ref = refs + chrom_off[ss->chrom - 1]; const int refLen = (int)(chrom_off[ss->chrom] - chrom_off[ss->chrom - 1]);
+            int sni;
+            if (ss->perfect) {
+                numNear++;
+                sni = maxSw; ss->slow_score = sni; ss->score = sni; ss->ngaps = 0;
+            } else {
+                sni = orc_score_no_indels(bases, len, ref, refLen, ss->start, 0);
+                if (sni < oldScore && oldScore >= maxImp && sslen != len) {
+                    const int s2 = orc_score_no_indels(bases, len, ref, refLen, ss->stop - len + 1, 0);
+                    if (s2 >= maxImp) { sni = s2; ss->start = ss->stop - len + 1; ss_set_perfect(ss, bases, len, ref, refLen); }
+                }
+                ss->slow_score = sni; ss->score = sni;
+                if (sni >= maxImp) {
+                    numNear++;
+                    ss->stop = ss->start + len - 1; ss->ngaps = 0;
+                    if (sni >= maxSw) { numPerfect++; ss->perfect = ss->semiperfect = 1; }
+                    else ss_set_perfect(ss, bases, len, ref, refLen);
+                    if (cfg->quick_match_strings && !ss->perfect && (cfg->print_secondary || sni >= best)) ss->has_match = 1;
+                } else if (oldScore >= maxImp) forceSlow = 1;
+                else if (cfg->print_secondary) forceSlow = 1;
+            }
+            best = imax(ss->slow_score, best);
+        }
+        out[r].near_perfect = n == 0 ? 0 : (forceSlow ? -numNear : numNear);
+        (void)numPerfect;
+        stable_sort(v, n, ss_compare);           /* BBMapThread.java:442 */
+    }
+}
+
+static int positional_match(const orc_ss* a, const orc_ss* b, int testGaps) {
+    if (a->chrom != b->chrom || a->strand != b->strand || a->start != b->start || a->stop != b->stop) return 0;
+    if (!testGaps || (a->ngaps == 0 && b->ngaps == 0)) return 1;
+    if ((a->ngaps == 0) != (b->ngaps == 0)) return 0;
+    if (a->ngaps != b->ngaps) return 0;
+    for (int i = 0; i < a->ngaps; i++) if (a->gaps[i] != b->gaps[i]) return 0;
+    return 1;
+}
+static int max3i(int a, int b, int c) { return imax(a, imax(b, c)); }
+
+/* Tools.mergeDuplicateSites(list, true, true); returns the new size (the assertion of doAssertions is not restated) */
+static int merge_duplicate_sites(orc_ss* v, int n) {
+    if (n < 2) return n;
+    stable_sort(v, n, ss_pcomp);
+    char dead[4096]; memset(dead, 0, (size_t)n);
+    int removed = 0, ai = 0;
+    for (int i = 1; i < n; i++) {
+        orc_ss* a = &v[ai]; orc_ss* b = &v[i];
+        if (positional_match(a, b, 1)) {
+            a->slow_score = imax(a->slow_score, b->slow_score);
+            a->paired_score = (a->paired_score <= a->slow_score && b->paired_score <= a->slow_score) ? 0 : max3i(0, a->paired_score, b->paired_score);
+            a->score = imax(a->score, b->score);
+            a->perfect = (a->perfect || b->perfect); a->semiperfect = (a->semiperfect || b->semiperfect);
+            removed++; dead[i] = 1;
+        } else if (positional_match(a, b, 0)) {
+            const orc_ss* better;
+            if (a->score != b->score) better = (a->score > b->score ? a : b);
+            else if (a->slow_score != b->slow_score) better = (a->slow_score > b->slow_score ? a : b);
+            else if (a->paired_score != b->paired_score) better = (a->paired_score > b->paired_score ? a : b);
+            else better = a;
+            const int bg = better->ngaps; int g[ORC_MAX_GAPS]; memcpy(g, better->gaps, sizeof(better->gaps));
+            a->slow_score = imax(a->slow_score, b->slow_score);
+            a->paired_score = (a->paired_score <= a->slow_score && b->paired_score <= a->slow_score) ? 0 : max3i(0, a->paired_score, b->paired_score);
+            a->score = imax(a->score, b->score);
+            a->perfect = (a->perfect || b->perfect); a->semiperfect = (a->semiperfect || b->semiperfect);
+            a->ngaps = bg; memcpy(a->gaps, g, sizeof(a->gaps));
+            removed++; dead[i] = 1;
+        } else ai = i;
+    }
+    if (removed > 0) { int k = 0; for (int i = 0; i < n; i++) if (!dead[i]) v[k++] = v[i]; n = k; }
+    return n;
+}
+static int count_top_scores(const orc_ss* v, int n, int thresh) {
+    if (n == 0) return 0;
+    int count = 1; const int limit = v[0].score - thresh;
+    for (int i = 1; i < n; i++) {
+        if (v[i].score < limit) break;
+        if (v[0].start != v[i].start && v[0].stop != v[i].stop) count++;
+    }
+    return count;
+}
+static int remove_low_quality_unpaired(orc_ss* v, int n, int thresh) {
+    if (n == 0) return 0;
+    if (v[0].score < thresh) return 0;
+    for (int i = n - 1; i > 1; i--)
+        if (v[i].slow_score < thresh) { for (int k = i; k + 1 < n; k++) v[k] = v[k + 1]; n--; }
+    return n;
+}
+
+/* BBMapThread.processRead :478-553 */
+void orc_sitelist_final(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; int n = nss[r];
+        const int maxSw = max_quality(read_len[r]);
+        int flags = 0, clearzone = 0, numBest = 0;
+        if (n > 0) { n = merge_duplicate_sites(v, n); stable_sort(v, n, ss_compare); }
+        const int perfect = n > 0 && (v[0].slow_score == maxSw || v[0].perfect);           /* Read.setPerfectFlag, match == null */
+        if (n > 1) {
+            const int score = v[0].score;
+            if (perfect) clearzone = cfg->clearzonep;
+            else {
+                const float cz1blimit = ((float)maxSw * cfg->cz1b_scale - cfg->cz1b_flat);
+                const float cz1climit = ((float)maxSw * cfg->cz1c_scale - cfg->cz1c_flat);
+                if ((float)score > cz1blimit)
+                    clearzone = (int)(((float)((maxSw - score) * cfg->clearzone1b) + ((float)score - cz1blimit) * (float)cfg->clearzone1) / ((float)maxSw - cz1blimit));   /* int product first, as in Java */
+                else if ((float)score > cz1climit)
+                    clearzone = (int)(((cz1blimit - (float)score) * (float)cfg->clearzone1c + ((float)score - cz1climit) * (float)cfg->clearzone1b) / (cz1blimit - cz1climit));
+                else clearzone = cfg->clearzone1c;
+            }
+            numBest = count_top_scores(v, n, clearzone);
+            if (numBest > 1) flags |= 4;
+            else {
+                const int lim = (perfect ? (int)(4.f * (float)cfg->clearzone_limit1e) : score + cfg->clearzone1e >= maxSw ? 2 * cfg->clearzone_limit1e : cfg->clearzone_limit1e) + 1;
+                if (n > lim && clearzone < cfg->clearzone1e) {
+                    numBest = count_top_scores(v, n, cfg->clearzone1e);
+                    if (numBest > lim) flags |= 4;
+                }
+            }
+        }
+        if (n > 0) {
+            const int lim = (int)((float)maxSw * cfg->min_align_ratio);
+            if (v[0].score < lim) n = 0;
+            else n = remove_low_quality_unpaired(v, n, imin(lim, imax(1, lim - cfg->clearzone3)));
+        }
+        if (n > 0) flags |= 1;
+        if (perfect && n > 0) flags |= 2;
+        nss[r] = n;
+        out[r].near_perfect = 0; out[r].flags = flags; out[r].clearzone = clearzone; out[r].best_sites = numBest;
+    }
+}

@@ -1,0 +1,99 @@
+"""GPU parity (part of SURVEY §8 f1): the per-read site-list policies on the device vs the C restatement — every field of every surviving
+site, list lengths and per-read outputs bit-exact — for trimList, scoreNoIndels(Read) and the post-alignment list handling, plus the
+conversion of BBIndex.find's sites into SiteScore records."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bbmap_b200 import lib as _lib
+from bbmap_b200 import sitelist as sl
+from sitelist_cases import noindel_lists, random_lists
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def msa():
+    from bbmap_b200.msa import MultiStateAligner11tsCUDA
+    m = MultiStateAligner11tsCUDA(device=0)
+    yield m
+    m.close()
+
+
+def _same(got, exp):
+    gl, gn, go = got; el, en, eo = exp
+    assert np.array_equal(gn, en)
+    for f in eo.dtype.names:
+        assert np.array_equal(go[f], eo[f]), f
+    live = np.arange(el.shape[1])[None, :] < en[:, None]
+    assert gl[live].tobytes() == el[live].tobytes()
+
+
+@pytest.mark.parametrize("seed,cap", [(51, 40), (52, 64), (53, 5)])
+def test_trim_parity(oracle, msa, seed, cap):
+    lists, nss, ro = random_lists(nreads=4000, cap=cap, seed=seed)
+    for cfg in (sl.policy_cfg(), sl.policy_cfg(min_trim_sites_to_retain=1), sl.policy_cfg(trim_list=0)):
+        _same(sl.site_lists(msa.h, sl.SL_TRIM, lists, nss, ro, cfg), oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg))
+
+
+@pytest.mark.parametrize("seed", [61, 62])
+def test_noindel_policy_parity(oracle, msa, seed):
+    refs, co, P, M, ro, lists, nss = noindel_lists(nreads=3000, seed=seed)
+    d_ref = msa.load_reference(refs)
+    try:
+        for cfg in (sl.policy_cfg(), sl.policy_cfg(print_secondary=1), sl.policy_cfg(quick_match_strings=0)):
+            exp = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, cfg, P, M, refs, co)
+            _same(sl.site_lists(msa.h, sl.SL_NOINDEL, lists, nss, ro, cfg, P, M, d_ref, co), exp)
+    finally:
+        msa.free(d_ref)
+    assert (exp[2]["near_perfect"] < 0).any() and (exp[2]["near_perfect"] > 0).any()
+
+
+@pytest.mark.parametrize("seed", [71, 72])
+def test_final_policy_parity(oracle, msa, seed):
+    lists, nss, ro = random_lists(nreads=5000, cap=24, seed=seed, after_alignment=True)
+    for cfg in (sl.policy_cfg(), sl.policy_cfg(clearzone3=0), sl.policy_cfg(clearzone_limit1e=2, clearzone1e=300)):
+        exp = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+        _same(sl.site_lists(msa.h, sl.SL_FINAL, lists, nss, ro, cfg), exp)
+    assert (exp[2]["flags"] & sl.F_AMBIGUOUS).any()
+
+
+def test_bad_arguments(msa):
+    lists, nss, ro = random_lists(nreads=4, cap=5, seed=1)
+    L = _lib.load()
+    out = np.zeros(4, sl.READ_OUT_DTYPE); cfg = sl.policy_cfg()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.bbm_sitelist_batch_host(msa.h, 9, p(lists), p(nss), 4, 5, p(ro), None, None, None, None, 0, p(cfg), p(out)) == _lib.BBM_E_ARG
+    assert L.bbm_sitelist_batch_host(msa.h, sl.SL_NOINDEL, p(lists), p(nss), 4, 5, p(ro), None, None, None, None, 0, p(cfg), p(out)) == _lib.BBM_E_ARG
+    big = np.zeros((4, 65), sl.SS_DTYPE)
+    assert L.bbm_sitelist_batch_host(msa.h, sl.SL_TRIM, p(big), p(nss), 4, 65, p(ro), None, None, None, None, 0, p(cfg), p(out)) == _lib.BBM_E_ARG
+
+
+def test_from_search(msa):
+    import torch
+    from bbmap_b200.search import HEAD_DTYPE, SITE_DTYPE
+    rng = np.random.default_rng(3)
+    n, ms, cap = 500, 6, 4
+    heads = np.zeros(n, HEAD_DTYPE); sites = np.zeros((n, ms), SITE_DTYPE)
+    heads["nsites"] = rng.integers(0, ms + 1, size=n)
+    for f in ("chrom", "start", "stop", "hits", "score", "ngaps"):
+        sites[f] = rng.integers(0, 9, size=(n, ms)) if f == "ngaps" else rng.integers(1, 100000, size=(n, ms))
+    sites["strand"] = rng.integers(0, 2, size=(n, ms)); sites["perfect"] = rng.integers(0, 2, size=(n, ms)); sites["semiperfect"] = sites["perfect"]
+    sites["gaps"] = rng.integers(0, 1000, size=sites["gaps"].shape)
+    dev = torch.device("cuda", 0)
+    d_h = torch.from_numpy(heads.view(np.uint8)).to(dev); d_s = torch.from_numpy(sites.view(np.uint8).reshape(-1)).to(dev)
+    d_l = torch.zeros(n * cap * sl.SS_DTYPE.itemsize, dtype=torch.uint8, device=dev); d_n = torch.zeros(n, dtype=torch.int32, device=dev)
+    L = _lib.load()
+    q = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(L.bbm_sitelist_from_search_dev(msa.h, q(d_h), q(d_s), n, ms, q(d_l), q(d_n), cap, None), "from_search")
+    torch.cuda.synchronize()
+    got = np.frombuffer(d_l.cpu().numpy().tobytes(), sl.SS_DTYPE).reshape(n, cap); gn = d_n.cpu().numpy()
+    assert np.array_equal(gn, np.minimum(heads["nsites"], cap))
+    for r in range(n):
+        for i in range(gn[r]):
+            a, b = got[r, i], sites[r, i]
+            assert (a["chrom"], a["start"], a["stop"], a["hits"], a["score"], a["quick_score"], a["slow_score"], a["paired_score"]) == \
+                   (b["chrom"], b["start"], b["stop"], b["hits"], b["score"], b["score"], 0, 0)
+            assert (a["strand"], a["perfect"], a["semiperfect"], a["rescued"], a["ngaps"]) == (b["strand"], b["perfect"], b["semiperfect"], 0, b["ngaps"])
+            assert np.array_equal(a["gaps"], b["gaps"])

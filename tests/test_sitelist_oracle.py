@@ -1,0 +1,102 @@
+"""The C restatement of the per-read site-list policies (oracle/sitelist_oracle.c) against lists whose outcome is worked out by hand from
+the reference's text (BBMapThread.java:140-249, 478-553; Tools.java:654-760, 913-1003).  Parity unpinned against Java (no JVM)."""
+import numpy as np
+
+from bbmap_b200 import sitelist as sl
+from sitelist_cases import noindel_lists, random_lists
+
+
+def _mk(rows, L=100, cap=8):
+    """rows: list of dicts of SS fields."""
+    lists = np.zeros((1, cap), sl.SS_DTYPE)
+    for i, d in enumerate(rows):
+        for k, v in d.items():
+            lists[0, i][k] = v
+        if "quick_score" not in d:
+            lists[0, i]["quick_score"] = d.get("score", 0)
+        if "stop" not in d:
+            lists[0, i]["stop"] = lists[0, i]["start"] + L - 1
+    return lists, np.array([len(rows)], np.int32), np.array([0, L], np.int64)
+
+
+def test_trim_list_by_hand(oracle):
+    cfg = sl.policy_cfg()
+    # perfect top score: cutoff (int)(9970*.6f)=5982; at most size-3 = 1 removal, from the end; then the .94 pass cannot shrink 3 sites
+    lists, nss, ro = _mk([dict(chrom=1, start=10, score=5000), dict(chrom=1, start=20, score=9970, perfect=1, semiperfect=1),
+                          dict(chrom=1, start=30, score=4000), dict(chrom=1, start=40, score=9000)])
+    L2, n2, out = oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)
+    assert n2[0] == 3 and list(L2[0, :3]["score"]) == [9970, 9000, 5000] and out["best_sites"][0] == 9970
+    # imperfect top: .6 -> cutoff 4800 removes 2000, 3000, 4000 (maxToRemove = 3); the list is then too short for the later passes
+    lists, nss, ro = _mk([dict(chrom=1, start=10 * i, score=s) for i, s in enumerate([3000, 8000, 2000, 7000, 5000, 4000])])
+    L2, n2, out = oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)
+    assert n2[0] == 3 and list(L2[0, :3]["score"]) == [8000, 7000, 5000] and out["best_sites"][0] == 8000
+    # semiperfect sites survive any cutoff; a single site and an empty list are untouched
+    lists, nss, ro = _mk([dict(chrom=1, start=10 * i, score=s, semiperfect=sp) for i, (s, sp) in enumerate([(9000, 0), (100, 1), (90, 1), (80, 1), (70, 0)])])
+    L2, n2, _ = oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)
+    assert n2[0] == 4 and list(L2[0, :4]["score"]) == [9000, 100, 90, 80]
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=5)])
+    assert oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)[1][0] == 1
+
+
+def test_final_policy_by_hand(oracle):
+    cfg = sl.policy_cfg()
+    f32 = np.float32
+    # perfect read, second site inside CLEARZONEP=160: ambiguous
+    lists, nss, ro = _mk([dict(chrom=1, start=100, score=9900, slow_score=9900), dict(chrom=1, start=5, score=9970, slow_score=9970, perfect=1, semiperfect=1)])
+    L2, n2, out = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    assert n2[0] == 2 and out["flags"][0] == sl.F_MAPPED | sl.F_PERFECT | sl.F_AMBIGUOUS and out["clearzone"][0] == 160 and out["best_sites"][0] == 2
+    assert L2[0, 0]["score"] == 9970
+    # imperfect: clearzone interpolated between CLEARZONE1b and CLEARZONE1 -> 210; the runner-up at 9400 is outside it
+    lists, nss, ro = _mk([dict(chrom=1, start=100, score=9400, slow_score=9400), dict(chrom=1, start=5, score=9700, slow_score=9700)])
+    L2, n2, out = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    lim = f32(9970) * f32(0.97) - f32(1200)
+    cz = int((f32((9970 - 9700) * 260) + (f32(9700) - lim) * f32(200)) / (f32(9970) - lim))
+    assert cz == 210 and out["clearzone"][0] == 210 and out["flags"][0] == sl.F_MAPPED and out["best_sites"][0] == 1 and n2[0] == 2
+    # ... and at 9500 inside it
+    lists[0, 0]["score"] = lists[0, 0]["slow_score"] = 9500
+    assert oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)[2]["flags"][0] == sl.F_MAPPED | sl.F_AMBIGUOUS
+    # same place twice: merged (scores maxed), then a lone site is never ambiguous
+    lists, nss, ro = _mk([dict(chrom=2, start=50, strand=1, score=9000, slow_score=9000), dict(chrom=2, start=50, strand=1, score=8000, slow_score=8500)])
+    L2, n2, out = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    assert n2[0] == 1 and L2[0, 0]["score"] == 9000 and L2[0, 0]["slow_score"] == 9000 and out["flags"][0] == sl.F_MAPPED
+    # below (int)(9970*.56f)=5583: unmapped; low third site (< 5583-800) dropped, the second is always kept (loop stops at index 2)
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=5500, slow_score=5500)])
+    assert oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)[1][0] == 0
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=9000, slow_score=9000), dict(chrom=1, start=300, score=4000, slow_score=4000),
+                          dict(chrom=1, start=600, score=3000, slow_score=3000)])
+    L2, n2, out = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    assert n2[0] == 2 and list(L2[0, :2]["score"]) == [9000, 4000]
+
+
+def test_noindel_policy_properties(oracle):
+    refs, co, P, M, ro, lists, nss = noindel_lists(nreads=800, seed=7)
+    cfg = sl.policy_cfg()
+    L2, n2, out = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, cfg, P, M, refs, co)
+    assert np.array_equal(n2, nss)
+    seen_shift = seen_match = 0
+    for r in range(len(nss)):
+        L = int(ro[r + 1] - ro[r]); maxq = 70 + 100 * (L - 1); v = L2[r, :n2[r]]
+        assert all(v["score"][i] >= v["score"][i + 1] for i in range(len(v) - 1))              # sorted by compareTo
+        assert (v["score"] == v["slow_score"]).all() and (v["score"] <= maxq).all()
+        near = (v["slow_score"] >= maxq - 495).sum()
+        assert abs(out["near_perfect"][r]) == near
+        for s in v[v["slow_score"] >= maxq - 495]:
+            assert s["stop"] - s["start"] + 1 == L and s["ngaps"] == 0
+            assert bool(s["perfect"]) == (s["slow_score"] == maxq)
+        seen_match += int(v["has_match"].sum())
+    # the stop-anchored rescoring moved some long sites onto the read
+    before = {(r, int(s["stop"])) for r in range(len(nss)) for s in lists[r, :nss[r]] if s["stop"] - s["start"] + 1 != ro[r + 1] - ro[r]}
+    after = {(r, int(s["stop"])) for r in range(len(nss)) for s in L2[r, :n2[r]] if s["slow_score"] >= 70 + 100 * (ro[r + 1] - ro[r] - 1) - 495}
+    assert len(before & after) > 20 and seen_match > 50
+
+
+def test_random_lists_invariants(oracle):
+    lists, nss, ro = random_lists(nreads=1500, seed=9)
+    cfg = sl.policy_cfg()
+    L2, n2, out = oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)
+    assert (n2 <= nss).all() and (n2[nss >= 3] >= 3).all() and (n2[nss < 3] == nss[nss < 3]).all() and (n2 < nss).sum() > 300
+    for r in np.nonzero(nss > 1)[0][:300]:
+        assert out["best_sites"][r] == lists[r, :nss[r]]["score"].max() == L2[r, 0]["score"]
+    lists, nss, ro = random_lists(nreads=1500, seed=10, after_alignment=True)
+    L3, n3, out3 = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    assert ((out3["flags"] & sl.F_MAPPED) != 0).sum() > 300 and ((out3["flags"] & sl.F_AMBIGUOUS) != 0).sum() > 50 and (n3 == 0).sum() > 100
