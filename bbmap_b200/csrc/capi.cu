@@ -974,6 +974,115 @@ extern "C" int bbm_sitelist_batch_host(bbm_ctx* c, int32_t op, bbm_ss* lists, in
     return rc;
 }
 
+// =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
+extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
+                                    const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
+                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, int* counters, cudaStream_t st);
+extern "C" int bbm_scoreslow_state_ints();
+static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                            const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
+                            const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, cudaStream_t st, int64_t* alignments_out, float* ms_out) {
+    const int SI = bbm_scoreslow_state_ints();
+    DevBuf state, tasks, outs, counters;
+    if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(16))
+        return fail(BBM_E_CUDA, "cudaMalloc scoreSlow scratch");
+    int rc = BBM_OK; int64_t aligned = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    auto launch = [&](int phase, int k) -> int {
+        int e = bbm_launch_scoreslow(phase, k, d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_basesP, d_basesM, d_refs, (const long long*)d_chrom_off,
+                                     d_run, cfg, (int*)state.p, (bbm_msa_task*)tasks.p, (const bbm_msa_out*)outs.p, (int*)counters.p, st);
+        if (e) return fail(BBM_E_CUDA, "scoreslow_kernel launch", (cudaError_t)e);
+        c->launches++;
+        return BBM_OK;
+    };
+    auto counts = [&](int* h) -> int {
+        cudaError_t ce = cudaMemcpyAsync(h, counters.p, 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        return ce == cudaSuccess ? BBM_OK : fail(BBM_E_CUDA, "scoreSlow counters", ce);
+    };
+    for (int k = 0; k < cap && rc == BBM_OK; ++k) {
+        int h[2] = {0, 0};
+        if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        if ((rc = launch(0, k)) || (rc = counts(h))) break;
+        if (h[0] == 0) break;                                   // no read has a k-th site
+        if (h[1] > 0) {
+            aligned += h[1];
+            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, nreads, nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
+        }
+        if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        if ((rc = launch(1, k)) || (rc = counts(h))) break;
+        if (h[1] > 0) {
+            aligned += h[1];
+            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, nreads, nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
+        }
+        if ((rc = launch(2, k))) break;
+    }
+    if (rc == BBM_OK && d_status) {
+        cudaError_t ce = cudaMemcpy2DAsync(d_status, 4, (const int*)state.p + 14, (size_t)SI * 4, 4, (size_t)nreads, cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) rc = fail(BBM_E_CUDA, "scoreSlow status", ce);
+    }
+    if (ms_out) {
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1); float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_out = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } else cudaStreamSynchronize(st);
+    if (alignments_out) *alignments_out = aligned;
+    state.release(); tasks.release(); outs.release(); counters.release();
+    return rc;
+}
+static int scoreslow_args(const bbm_slow_cfg* cfg, int cap) {
+    if (!cfg || cfg->slow_align_padding < 0 || cfg->extra_padding < 0 || cfg->expected_len_limit < 1) return fail(BBM_E_ARG, "bbm_scoreslow: bad cfg");
+    if (cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_scoreslow: cap must be in 1..64");
+    return BBM_OK;
+}
+extern "C" int bbm_scoreslow_dev(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                 const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
+                                 const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, void* stream, int64_t* alignments_out, float* ms_out) {
+    if (!c || !d_lists || !d_nss || !d_read_off || !d_basesP || !d_basesM || !d_refs || !d_chrom_off || !d_run) return fail(BBM_E_ARG, "bbm_scoreslow_dev: null pointer");
+    if (int rc = scoreslow_args(cfg, cap)) return rc;
+    if (alignments_out) *alignments_out = 0;
+    if (nreads <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return scoreslow_locked(c, d_lists, d_nss, nreads, cap, d_read_off, d_basesP, d_basesM, d_refs, d_chrom_off, d_run, cfg, d_status, max_read_len,
+                            stream ? (cudaStream_t)stream : c->stream, alignments_out, ms_out);
+}
+extern "C" int bbm_scoreslow_host(bbm_ctx* c, bbm_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off,
+                                  const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
+                                  const int32_t* run, const bbm_slow_cfg* cfg, int32_t* status, int64_t* alignments_out) {
+    if (!c || !lists || !nss || !read_off || !basesP || !basesM || !d_refs || !chrom_off || !run || nchroms < 1) return fail(BBM_E_ARG, "bbm_scoreslow_host: bad argument");
+    if (int rc = scoreslow_args(cfg, cap)) return rc;
+    if (alignments_out) *alignments_out = 0;
+    if (nreads <= 0) return BBM_OK;
+    int maxLen = 1;
+    for (int64_t r = 0; r < nreads; ++r) {
+        if (nss[r] < 0 || nss[r] > cap || read_off[r + 1] < read_off[r]) return fail(BBM_E_ARG, "bbm_scoreslow_host: list length outside 0..cap");
+        for (int i = 0; i < nss[r]; ++i) { const bbm_ss& s = lists[r * cap + i]; if (s.chrom < 1 || s.chrom > nchroms) return fail(BBM_E_ARG, "bbm_scoreslow_host: chromosome out of range"); }
+        if (read_off[r + 1] - read_off[r] > maxLen) maxLen = (int)(read_off[r + 1] - read_off[r]);
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t lb = (size_t)nreads * cap * sizeof(bbm_ss), nb = (size_t)nreads * 4, fb = (size_t)(nreads + 1) * 8, rb = (size_t)read_off[nreads], cb = (size_t)(nchroms + 1) * 8;
+    DevBuf L_, N_, F_, PM_, C_, R_, S_;
+    const size_t half = (rb + 31) & ~(size_t)15;            // both strands in one allocation: the aligner addresses the minus strand as an offset from the plus strand
+    if (L_.ensure(lb) || N_.ensure(nb) || F_.ensure(fb) || PM_.ensure(2 * half + 16) || C_.ensure(cb) || R_.ensure(nb) || S_.ensure(nb)) return fail(BBM_E_CUDA, "cudaMalloc staging");
+    CK(cudaMemcpyAsync(L_.p, lists, lb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(N_.p, nss, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(F_.p, read_off, fb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(PM_.p, basesP, rb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((char*)PM_.p + half, basesM, rb, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(C_.p, chrom_off, cb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R_.p, run, nb, cudaMemcpyHostToDevice, st));
+    int rc = scoreslow_locked(c, (bbm_ss*)L_.p, (const int32_t*)N_.p, nreads, cap, (const int64_t*)F_.p, (const int8_t*)PM_.p, (const int8_t*)PM_.p + half, d_refs,
+                              (const int64_t*)C_.p, (const int32_t*)R_.p, cfg, (int32_t*)S_.p, maxLen, st, alignments_out, nullptr);
+    if (rc == BBM_OK) {
+        cudaError_t ce = cudaMemcpyAsync(lists, L_.p, lb, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && status) ce = cudaMemcpyAsync(status, S_.p, nb, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) rc = fail(BBM_E_CUDA, "scoreSlow copy back", ce);
+    }
+    L_.release(); N_.release(); F_.release(); PM_.release(); C_.release(); R_.release(); S_.release();
+    return rc;
+}
+
 // =====================  k-mer index build + analysis  =====================
 static void index_free(bbm_ctx* c) {
     for (auto& b : c->iblocks) { if (b.starts) cudaFree(b.starts); if (b.sites) cudaFree(b.sites); }

@@ -303,6 +303,115 @@ __global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_sea
     nss[r] = n;
 }
 
+
+// =====================  scoreSlow in rounds (BBMapThread.scoreSlow, current/align2/BBMapThread.java:252-386)  =====================
+// scoreSlow walks the sites of one read in order because its limit ratchets: minMsaLimit = max(minMsaLimit, slowScore - CLEARZONE3)
+// after every site (:375-376).  Reads are independent, so the batched form is rounds: round k handles the k-th site of every read —
+//   SLOW_PREP   the per-site preamble (:270-300) and the fillAndScoreLimited request (MSA.java:136-143: window = site +- pad, clamped)
+//   [one bbm_msa batch over all reads of the round]
+//   SLOW_RETRY  "more padding needed" (:303-326): score array of length 8 -> widen the site by the suggested pads, ask again with
+//               SLOW_ALIGN_PADDING+EXTRA_PADDING;  [second batch, only if some read asked]
+//   SLOW_APPLY  keep the better array, setSlowScore/setLimits, ratchet, perfect/semiperfect flags (:327-385)
+// Default flags only: QUICK_MATCH_STRINGS=false (no traceback / fixXY / clipTipIndels inside scoreSlow).  Sites that carry gaps need the
+// gapped aligner and GapTools.fixGaps in setLimits: they are left as scoreNoIndels scored them and the read is flagged BBM_SLOW_GAPPED.
+struct SlowParams {
+    int phase, round; bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off;
+    const int8_t* basesP; const int8_t* basesM; const int8_t* refs; const long long* chrom_off; const int* run;
+    bbm_slow_cfg cfg; int* state;       // [nreads][16]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status
+    bbm_msa_task* tasks; const bbm_msa_out* outs; int* counters;   // counters[0] reads active in this round, [1] tasks emitted
+};
+constexpr int SLOW_PREP = 0, SLOW_RETRY = 1, SLOW_APPLY = 2;
+constexpr int SLOW_STATE = 16;
+
+__global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    int* st = P.state + r * SLOW_STATE;
+    bbm_msa_task task = {};                       // read_len 0: the aligner rejects it without work
+    const int k = P.round;
+    const bool active = P.run[r] != 0 && k < P.nss[r];
+    const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
+    const bbm_slow_cfg& cfg = P.cfg;
+    if (P.phase == SLOW_PREP) {
+        if (k == 0) {
+            const int maxSw = max_quality(len);
+            const int lim = -cfg.clearzone1e + (int)__fmul_rn(cfg.paired ? cfg.min_ratio_pre_rescue : cfg.min_ratio, (float)maxSw);
+            st[0] = lim; st[1] = imax(-300, lim - cfg.clearzone3); st[14] = 0;
+        }
+        st[2] = 0;
+        if (active) {
+            atomicAdd(P.counters, 1);
+            bbm_ss ss = P.lists[r * P.cap + k];
+            if (ss.stop - ss.start != len - 1) { ss.slow_score = 0; ss.semiperfect = 0; ss.perfect = 0; }
+            const int sw = ss.slow_score;
+            if (sw < max_imperfect(len) && !ss.semiperfect) {
+                if (ss.ngaps > 0) st[14] |= BBM_SLOW_GAPPED;
+                else {
+                    const int expectedLen = ss.stop - ss.start + 1;                      // GapTools.calcGrefLen without gaps
+                    if (expectedLen >= cfg.expected_len_limit) ss.stop = ss.start + imin(len + 40, cfg.expected_len_limit);
+                    const int minscore = imax(sw, st[0]);
+                    task.read_off = ((ss.strand == 0 ? P.basesP : P.basesM) - P.basesP) + P.read_off[r];
+                    task.ref_off = P.chrom_off[ss.chrom - 1]; task.read_len = len;
+                    task.ref_len = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
+                    task.ref_start = ss.start - cfg.slow_align_padding; task.ref_end = ss.stop + cfg.slow_align_padding;
+                    task.min_score = minscore; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
+                    st[2] = 1; st[3] = expectedLen; st[4] = minscore;
+                    atomicAdd(P.counters + 1, 1);
+                }
+            }
+            P.lists[r * P.cap + k] = ss;
+        }
+        P.tasks[r] = task;
+    } else if (P.phase == SLOW_RETRY) {
+        if (active && st[2] == 1) {
+            const bbm_msa_out o = P.outs[r];
+            if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
+            const int n = (o.status == 0) ? o.score_len : 0;
+            st[5] = n;
+#pragma unroll
+            for (int q = 0; q < 8; q++) st[6 + q] = o.score[q];
+            if (n > 6 && (o.score[3] + o.score[4] + st[3] < cfg.expected_len_limit)) {
+                bbm_ss ss = P.lists[r * P.cap + k];
+                ss.start -= o.score[6]; ss.stop += o.score[7];                           // setLimits (gaps == null)
+                const int pad = cfg.slow_align_padding + cfg.extra_padding;
+                task.read_off = ((ss.strand == 0 ? P.basesP : P.basesM) - P.basesP) + P.read_off[r];
+                task.ref_off = P.chrom_off[ss.chrom - 1]; task.read_len = len;
+                task.ref_len = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
+                task.ref_start = ss.start - pad; task.ref_end = ss.stop + pad;
+                task.min_score = st[4]; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
+                st[2] = 2;
+                atomicAdd(P.counters + 1, 1);
+                P.lists[r * P.cap + k] = ss;
+            }
+        }
+        P.tasks[r] = task;
+    } else {
+        if (active) {
+            bbm_ss ss = P.lists[r * P.cap + k];
+            int n = 0, a0 = 0, a1 = 0, a2 = 0;
+            if (st[2] >= 1) { n = st[5]; a0 = st[6]; a1 = st[7]; a2 = st[8]; }
+            if (st[2] == 2) {
+                const bbm_msa_out o = P.outs[r];
+                if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
+                const int n2 = (o.status == 0) ? o.score_len : 0;
+                if (!(n2 == 0 || o.score[0] < a0)) { n = n2; a0 = o.score[0]; a1 = o.score[1]; a2 = o.score[2]; }
+            }
+            if (n > 0) { ss.slow_score = a0; ss.start = a1; ss.stop = a2; }
+            ss.score = ss.slow_score;
+            st[1] = imax(st[1], ss.slow_score);
+            st[0] = imax(st[0], ss.slow_score - cfg.clearzone3);
+            const int maxSw = max_quality(len);
+            ss.perfect = (ss.slow_score == maxSw) ? 1 : 0;
+            if (ss.perfect) ss.semiperfect = 1;
+            else if (!ss.semiperfect) {
+                const int8_t* bases = (ss.strand == 0 ? P.basesP : P.basesM) + P.read_off[r];
+                ss_set_perfect(ss, bases, len, P.refs + P.chrom_off[ss.chrom - 1], (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]));
+            }
+            P.lists[r * P.cap + k] = ss;
+        }
+    }
+}
+
 }  // namespace bbm
 
 extern "C" int bbm_sitelist_max_cap() { return bbm::SL_MAX_CAP; }
@@ -320,3 +429,15 @@ extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, con
     bbm::sitelist_from_search_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(heads, sites, nreads, maxSites, lists, nss, cap);
     return (int)cudaGetLastError();
 }
+
+extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
+                                    const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
+                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, int* counters, cudaStream_t st) {
+    bbm::SlowParams P;
+    P.phase = phase; P.round = round; P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP;
+    P.basesM = basesM; P.refs = refs; P.chrom_off = chrom_off; P.run = run; P.cfg = *cfg; P.state = state; P.tasks = tasks; P.outs = outs;
+    P.counters = counters;
+    bbm::scoreslow_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_scoreslow_state_ints() { return bbm::SLOW_STATE; }

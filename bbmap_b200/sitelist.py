@@ -25,9 +25,10 @@ def policy_cfg(**kw):
     """BBMap defaults: TRIM_LIST=true (AbstractMapper.java:2678), MIN_TRIM_SITES_TO_RETAIN_SINGLE=3 (BBMapThread.java:62),
     MAX_TRIM_SITES_TO_RETAIN=800 (AbstractMapThread.java:3004), CLEARZONE1/1b/1c/P/3 = (2.0, 2.6, 4.6, 1.6, 8.0) x POINTS_MATCH2
     (BBMapThread.java:38-42,114-118), CLEARZONE1e = 2*100-70+127+1 = 258 (AbstractMapThread.java:142), CLEARZONE_LIMIT1e=40,
-    cutoffs 0.97/12x100 and 0.92/26x100 (BBMapThread.java:52-57), MINIMUM_ALIGNMENT_SCORE_RATIO=0.56 (BBMap.java:50)."""
+    cutoffs 0.97/12x100 and 0.92/26x100 (BBMapThread.java:52-57), MINIMUM_ALIGNMENT_SCORE_RATIO=0.56 (BBMap.java:50),
+    QUICK_MATCH_STRINGS=false (AbstractMapper.java:2731)."""
     c = np.zeros(1, POLICY_CFG_DTYPE)
-    d = dict(trim_list=1, min_trim_sites_to_retain=3, max_trim_sites_to_retain=800, quick_match_strings=1, clearzone1=200, clearzone1b=260,
+    d = dict(trim_list=1, min_trim_sites_to_retain=3, max_trim_sites_to_retain=800, quick_match_strings=0, clearzone1=200, clearzone1b=260,
              clearzone1c=460, clearzonep=160, clearzone3=800, clearzone1e=258, clearzone_limit1e=40, print_secondary=0, min_align_ratio=0.56,
              cz1b_scale=0.97, cz1b_flat=1200.0, cz1c_scale=0.92, cz1c_flat=2600.0)
     d.update(kw)
@@ -57,3 +58,37 @@ def site_lists(ctx, op, lists, nss, read_off, cfg=None, basesP=None, basesM=None
     _lib.check(L.bbm_sitelist_batch_host(ctx, op, _p(lists), _p(nss), n, cap, _p(ro), _p(bp), _p(bm), d_ref, _p(co), 0 if co is None else len(co) - 1,
                                          _p(cfg), _p(out)), "bbm_sitelist_batch_host")
     return lists, nss, out
+
+
+SLOW_CFG_DTYPE = np.dtype([("paired", "<i4"), ("min_ratio", "<f4"), ("min_ratio_pre_rescue", "<f4"), ("clearzone1e", "<i4"), ("clearzone3", "<i4"),
+                           ("slow_align_padding", "<i4"), ("extra_padding", "<i4"), ("expected_len_limit", "<i4")], align=True)
+assert SLOW_CFG_DTYPE.itemsize == 32
+SLOW_GAPPED, SLOW_ALIGNER_ERROR = 1, 2
+
+
+def slow_cfg(**kw):
+    """scoreSlow constants: MINIMUM_ALIGNMENT_SCORE_RATIO 0.56 (BBMap.java:50; the pre-rescue ratio only matters for pairs), CLEARZONE1e 258,
+    CLEARZONE3 800, SLOW_ALIGN_PADDING 4 (BBMap.java:57), EXTRA_PADDING 10 (AbstractMapThread.java:2953), EXPECTED_LEN_LIMIT =
+    (ALIGN_COLUMNS*17)/20-2*(SLOW_ALIGN_PADDING+10) = 2522 (AbstractMapThread.java:92)."""
+    c = np.zeros(1, SLOW_CFG_DTYPE)
+    d = dict(paired=0, min_ratio=0.56, min_ratio_pre_rescue=0.56, clearzone1e=258, clearzone3=800, slow_align_padding=4, extra_padding=10, expected_len_limit=2522)
+    d.update(kw)
+    for k, v in d.items():
+        c[k] = v
+    return c
+
+
+def scoreSlow(ctx, lists, nss, read_off, basesP, basesM, d_ref, chrom_off, run, cfg=None):
+    """BBMapThread.scoreSlow for every read with run[r] != 0, in rounds over the device aligner.  Returns (lists, status, alignments)."""
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: scoreSlow has no CPU fallback")
+    cfg = slow_cfg() if cfg is None else cfg
+    lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)
+    n, cap = lists.shape
+    ro = np.ascontiguousarray(read_off, np.int64); co = np.ascontiguousarray(chrom_off, np.int64)
+    bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8)
+    rn = np.ascontiguousarray(run, np.int32); status = np.zeros(n, np.int32); na = C.c_int64(0)
+    _lib.check(L.bbm_scoreslow_host(ctx, _p(lists), _p(nss), n, cap, _p(ro), _p(bp), _p(bm), d_ref, _p(co), len(co) - 1, _p(rn), _p(cfg), _p(status),
+                                    C.byref(na)), "bbm_scoreslow_host")
+    return lists, status, na.value

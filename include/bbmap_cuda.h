@@ -365,6 +365,25 @@ int  bbm_sitelist_batch_host(bbm_ctx* ctx, int32_t op, bbm_ss* lists, int32_t* n
                              const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
                              const bbm_policy_cfg* cfg, bbm_read_out* out);
 
+/* ---- BBMapThread.scoreSlow over a batch of reads, in rounds (current/align2/BBMapThread.java:252-386; part of SURVEY 8f.1) ----
+ * Round k slow-aligns the k-th site of every read whose run[r] != 0 (processRead calls scoreSlow when scoreNoIndels found no
+ * near-perfect site, :463-465): preamble, MSA.fillAndScoreLimited(bases, ss, SLOW_ALIGN_PADDING, max(slowScore, minMsaLimit)), the
+ * "more padding" retry with EXTRA_PADDING, setSlowScore/setLimits, the minMsaLimit ratchet and the perfect/semiperfect flags.  Default
+ * flags (QUICK_MATCH_STRINGS=false).  status[r] (may be NULL): BBM_SLOW_* bits. */
+typedef struct {                /* 32 bytes; defaults: MINIMUM_ALIGNMENT_SCORE_RATIO 0.56, ..._PRE_RESCUE (paired only), CLEARZONE1e 258, CLEARZONE3 800,
+                                   SLOW_ALIGN_PADDING 4, EXTRA_PADDING 10, EXPECTED_LEN_LIMIT (3000*17)/20-2*(4+10) = 2522 */
+    int32_t paired; float min_ratio, min_ratio_pre_rescue;
+    int32_t clearzone1e, clearzone3, slow_align_padding, extra_padding, expected_len_limit;
+} bbm_slow_cfg;
+#define BBM_SLOW_GAPPED         1   /* a site with a gap array was left as scoreNoIndels scored it (gapped fill + GapTools.fixGaps not chained yet) */
+#define BBM_SLOW_ALIGNER_ERROR  2   /* the aligner reported a per-task error (shape outside 601 x 3000) */
+int  bbm_scoreslow_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                       const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
+                       const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, void* stream, int64_t* alignments_out, float* ms_out);
+int  bbm_scoreslow_host(bbm_ctx* ctx, bbm_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off,
+                        const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
+                        const int32_t* run, const bbm_slow_cfg* cfg, int32_t* status, int64_t* alignments_out);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

@@ -266,6 +266,17 @@ class Oracle:
             self.lib.orc_sitelist_final(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(cfg), _p(out))
         return lists, nss, out
 
+    def score_slow(self, lists, nss, read_off, basesP, basesM, refs, chrom_off, run, cfg):
+        from bbmap_b200.sitelist import SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); co = np.ascontiguousarray(chrom_off, np.int64)
+        bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8); rf = np.ascontiguousarray(refs).view(np.int8)
+        rn = np.ascontiguousarray(run, np.int32); status = np.zeros(n, np.int32)
+        self.lib.orc_score_slow.restype = C.c_int64
+        na = self.lib.orc_score_slow(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), _p(ro), _p(rf), _p(co), _p(rn), _p(cfg), _p(status))
+        return lists, status, na
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)

@@ -94,3 +94,58 @@ def noindel_lists(nreads=3000, cap=8, seed=61):
                 s["ngaps"] = 2; s["gaps"][:2] = (s["start"], s["stop"])
         nss[r] = n
     return refs, chrom_off, P, M, read_off, lists, nss
+
+
+def slow_cases(nreads=1500, cap=4, seed=81):
+    """Lists as they stand when processRead calls scoreSlow: every site scored by scoreNoIndels (slow_score = score), sorted.  Reads carry
+    substitutions and one indel of 1-60 bp, some of them within 12 bases of a tip (the aligner then asks for more padding); decoy sites,
+    sites longer than the read, sites at the ends of the array, a few gapped sites, and reads for which scoreSlow is not called."""
+    rng = np.random.default_rng(seed)
+    g = wl.random_genome(40000, seed=seed).copy()
+    g[:200] = ord("N"); g[-200:] = ord("N")
+    refs = g; chrom_off = np.array([0, len(g)], np.int64)
+    lens = rng.choice([60, 100, 150, 250], size=nreads)
+    read_off = np.zeros(nreads + 1, np.int64); np.cumsum(lens, out=read_off[1:])
+    P = np.zeros(int(read_off[-1]), np.int8); M = np.zeros_like(P)
+    lists = np.zeros((nreads, cap), sl.SS_DTYPE); nss = np.zeros(nreads, np.int32); run = np.ones(nreads, np.int32)
+    for r in range(nreads):
+        L = int(lens[r])
+        p = int(rng.integers(260, len(g) - 260 - L - 70)) if rng.random() < 0.93 else int(rng.choice([198, 203, len(g) - 200 - L - 3, len(g) - 200 - L + 2]))
+        kind = int(rng.integers(0, 6)); d = int(rng.integers(1, 61))
+        q = int(rng.integers(3, 13)) if rng.random() < 0.35 else int(rng.integers(13, L - 13))
+        if rng.random() < 0.5:
+            q = L - q
+        if kind in (0, 1):          # deletion of d bases after read position q
+            src = np.concatenate([g[p:p + q], g[p + q + d:p + L + d]])
+        elif kind == 2:             # insertion of min(d, 20) random bases at q
+            d2 = min(d, 20, L - q - 1)
+            src = np.concatenate([g[p:p + q], wl.ACGT[rng.integers(0, 4, size=d2, dtype=np.uint8)].view(np.int8), g[p + q:p + L - d2]])
+        else:
+            src = g[p:p + L]
+        read = np.where(src == ord("N"), ord("A"), src).astype(np.int8)[:L]
+        for _ in range(int(rng.choice([0, 1, 2, 4]))):
+            k = int(rng.integers(0, L)); read[k] = ord("ACGT"[("ACGT".index(chr(read[k])) + int(rng.integers(1, 4))) % 4])
+        strand = int(rng.integers(0, 2))
+        plus = read if strand == 0 else wl.revcomp(read.view(np.uint8)).view(np.int8)
+        P[read_off[r]:read_off[r + 1]] = plus; M[read_off[r]:read_off[r + 1]] = wl.revcomp(plus.view(np.uint8)).view(np.int8)
+        n = int(rng.integers(1, cap + 1))
+        for i in range(n):
+            s = lists[r, i]
+            s["chrom"] = 1; s["strand"] = strand; s["start"] = p; s["stop"] = p + L - 1; s["hits"] = 4
+            if i > 0:
+                w = int(rng.integers(0, 5))
+                if w == 0:
+                    s["start"] = int(rng.integers(220, len(g) - 300 - L)); s["stop"] = s["start"] + L - 1          # decoy
+                elif w == 1:
+                    s["stop"] = s["start"] + L - 1 + d                                                               # site spanning the deletion
+                elif w == 2:
+                    s["strand"] = 1 - strand
+                elif w == 3:
+                    s["start"] += int(rng.integers(-6, 7)); s["stop"] = s["start"] + L - 1
+                else:
+                    s["ngaps"] = 4; s["stop"] = s["start"] + L + 300; s["gaps"][:4] = (s["start"], s["start"] + 40, s["start"] + 340, s["stop"])
+            s["quick_score"] = int((70 + 100 * (L - 1)) * rng.uniform(0.4, 1.0)); s["score"] = s["quick_score"]
+        nss[r] = n
+        if rng.random() < 0.1:
+            run[r] = 0
+    return refs, chrom_off, P, M, read_off, lists, nss, run
