@@ -41,6 +41,6 @@ def test_score_slow_properties(oracle):
                 assert a.tobytes() == b.tobytes(); continue
             assert b["score"] == b["slow_score"] <= maxq and bool(b["perfect"]) == (b["slow_score"] == maxq)
             if a["stop"] - a["start"] == Lr - 1:
-                assert b["slow_score"] >= a["slow_score"]           # the aligner is only trusted when it reaches max(noIndel score, limit)
+                assert b["slow_score"] >= a["slow_score"] - 120     # fillLimited runs with minScore-MIN_SCORE_ADJUST (MSA.java:868)
             improved += b["slow_score"] > a["slow_score"]; moved += (b["stop"] - b["start"]) != (a["stop"] - a["start"])
     assert improved > 100 and moved > 60
