@@ -1008,13 +1008,13 @@ static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, i
         if (h[0] == 0) break;                                   // no read has a k-th site
         if (h[1] > 0) {
             aligned += h[1];
-            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, nreads, nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
+            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
         if ((rc = launch(1, k)) || (rc = counts(h))) break;
         if (h[1] > 0) {
             aligned += h[1];
-            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, nreads, nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
+            if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if ((rc = launch(2, k))) break;
     }

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_sea
 struct SlowParams {
     int phase, round; bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off;
     const int8_t* basesP; const int8_t* basesM; const int8_t* refs; const long long* chrom_off; const int* run;
-    bbm_slow_cfg cfg; int* state;       // [nreads][16]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status
+    bbm_slow_cfg cfg; int* state;       // [nreads][16]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status, 15 task slot
     bbm_msa_task* tasks; const bbm_msa_out* outs; int* counters;   // counters[0] reads active in this round, [1] tasks emitted
 };
 constexpr int SLOW_PREP = 0, SLOW_RETRY = 1, SLOW_APPLY = 2;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.nreads) return;
     int* st = P.state + r * SLOW_STATE;
-    bbm_msa_task task = {};                       // read_len 0: the aligner rejects it without work
+    bbm_msa_task task = {};
     const int k = P.round;
     const bool active = P.run[r] != 0 && k < P.nss[r];
     const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
@@ -356,15 +356,15 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
                     task.ref_start = ss.start - cfg.slow_align_padding; task.ref_end = ss.stop + cfg.slow_align_padding;
                     task.min_score = minscore; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
                     st[2] = 1; st[3] = expectedLen; st[4] = minscore;
-                    atomicAdd(P.counters + 1, 1);
+                    const int slot = atomicAdd(P.counters + 1, 1);             // requests are packed: the aligner sees only real tasks
+                    st[15] = slot; P.tasks[slot] = task;
                 }
             }
             P.lists[r * P.cap + k] = ss;
         }
-        P.tasks[r] = task;
     } else if (P.phase == SLOW_RETRY) {
         if (active && st[2] == 1) {
-            const bbm_msa_out o = P.outs[r];
+            const bbm_msa_out o = P.outs[st[15]];
             if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
             const int n = (o.status == 0) ? o.score_len : 0;
             st[5] = n;
@@ -380,18 +380,18 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
                 task.ref_start = ss.start - pad; task.ref_end = ss.stop + pad;
                 task.min_score = st[4]; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
                 st[2] = 2;
-                atomicAdd(P.counters + 1, 1);
+                const int slot = atomicAdd(P.counters + 1, 1);
+                st[15] = slot; P.tasks[slot] = task;
                 P.lists[r * P.cap + k] = ss;
             }
         }
-        P.tasks[r] = task;
     } else {
         if (active) {
             bbm_ss ss = P.lists[r * P.cap + k];
             int n = 0, a0 = 0, a1 = 0, a2 = 0;
             if (st[2] >= 1) { n = st[5]; a0 = st[6]; a1 = st[7]; a2 = st[8]; }
             if (st[2] == 2) {
-                const bbm_msa_out o = P.outs[r];
+                const bbm_msa_out o = P.outs[st[15]];
                 if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
                 const int n2 = (o.status == 0) ? o.score_len : 0;
                 if (!(n2 == 0 || o.score[0] < a0)) { n = n2; a0 = o.score[0]; a1 = o.score[1]; a2 = o.score[2]; }

@@ -335,6 +335,9 @@ def main():
         import stages
         msa.close()
         line["stages"] = stages.run(pairs=args.stage_pairs, device=local, hbm_peak=pk["hbm_gbs"])
+        # the same stages chained on the device up to the final site decision (mapped reads/s of the built part of the mapper)
+        import pipeline
+        line["pipeline"] = pipeline.run(pairs=args.stage_pairs, device=local)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_run(reads, genome, tasks, moff, args.bandwidth, args.ratio)
     print(json.dumps(line))

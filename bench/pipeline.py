@@ -1,0 +1,136 @@
+"""The device stages of the unpaired mapping loop chained with everything resident in HBM (no host round trip between stages):
+
+    Read.validate -> KeyRing seeds -> BBIndex.find -> SiteScore lists -> trimList -> scoreNoIndels(Read) -> scoreSlow (rounds over the
+    MultiStateAligner11ts kernels, padding retry included) -> mergeDuplicateSites / clearzone / removeLowQualitySitesUnpaired
+
+on BASELINE configs[1]-shaped input (E. coli-sized random reference, 2x150 bp reads mapped as single reads, ~1 % substitutions, 1-3 bp
+indels, Q30).  What the reference's processRead (current/align2/BBMapThread.java:389-733) does in addition and is NOT in this chain yet:
+findTipDeletions' rescoring of changed sites, genMatchString/realign_new, applyClearzone3, the tip-score penalty, pairing and rescue, SAM
+text.  The reads/s printed here is therefore the throughput of the built device stages up to the final site decision (strand, POS, score,
+ambiguity), not yet a whole-mapper number.
+
+    python bench/pipeline.py [--pairs 200000] [--genome 4600000] [--reps 3]
+
+Prints one JSON object; bench.py embeds it as `pipeline`."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bbmap_b200 import lib as _lib, sitelist as sl, workloads as wl  # noqa: E402
+from bbmap_b200.index import BBIndexCUDA, pack_chromosomes  # noqa: E402
+from bbmap_b200.keyring import default_cfg  # noqa: E402
+from bbmap_b200.search import HEAD_DTYPE, SITE_DTYPE  # noqa: E402
+
+MAXK, MAX_SITES, CAP = 32, 16, 16
+
+
+def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0):
+    import torch
+    L = _lib.load()
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(device)
+    cb, co, table = pack_chromosomes([wl.random_genome(genome_len, seed=1)])
+    R = wl.make_mapping_reads(cb, co, table, pairs, seed=2)
+    n = 2 * pairs; nb = len(R["bases"])
+    idx = BBIndexCUDA(cb, co, keylen=13, device=device)
+    h = idx.h
+    p = lambda t: C.c_void_p(t.data_ptr())
+    pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
+    d_bases0 = pad(R["bases"]); d_qual0 = pad(R["qual"]); d_off = torch.from_numpy(R["off"]).to(dev)
+    d_bases = torch.empty_like(d_bases0); d_qual = torch.empty_like(d_qual0)
+    d_basesM = torch.zeros(nb + 64, dtype=torch.uint8, device=dev); d_flags = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_nkeys = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_offsets = torch.zeros(n * MAXK, dtype=torch.int32, device=dev); d_keys = torch.zeros_like(d_offsets); d_ks = torch.zeros_like(d_offsets)
+    d_offM = torch.zeros_like(d_offsets); d_keysM = torch.zeros_like(d_offsets)
+    d_bs = torch.zeros(nb + 64, dtype=torch.int8, device=dev)
+    d_heads = torch.zeros(n * HEAD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_sites = torch.zeros(n * MAX_SITES * SITE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_lists = torch.zeros(n * CAP * sl.SS_DTYPE.itemsize, dtype=torch.uint8, device=dev); d_nss = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_out = torch.zeros(n * sl.READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_co = torch.from_numpy(np.ascontiguousarray(co, np.int64)).to(dev)
+    d_chroms = C.c_void_p(idx.d_chroms.value)
+    scfg = default_cfg(); pcfg = sl.policy_cfg(); wcfg = sl.slow_cfg()
+    cp = lambda a: a.ctypes.data_as(C.c_void_p)
+    ms = C.c_float(0); na = C.c_int64(0)
+    t = {}
+
+    def step(name, fn):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+        t[name] = t.get(name, []) + [1e3 * (time.perf_counter() - t0)]
+
+    def sitelist(op):
+        _lib.check(L.bbm_sitelist_batch_dev(h, op, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_bases), p(d_basesM), d_chroms, p(d_co), cp(pcfg), p(d_out), None, None),
+                   "bbm_sitelist_batch_dev")
+
+    run_flags = [None]
+
+    def chain():
+        d_bases.copy_(d_bases0); d_qual.copy_(d_qual0)            # Read.validate works in place
+        step("ingest", lambda: _lib.check(L.bbm_ingest_batch_dev(h, p(d_bases), p(d_qual), p(d_off), n, 150, 0, p(d_basesM), p(d_flags), None, C.byref(ms)), "ingest"))
+        step("seed", lambda: _lib.check(L.bbm_seed_batch_dev(h, p(d_bases), p(d_qual), p(d_off), n, 150, cp(scfg), MAXK, p(d_nkeys), p(d_offsets), p(d_keys), p(d_ks),
+                                                             p(d_bs), p(d_offM), p(d_keysM), None, C.byref(ms)), "seed"))
+        step("search", lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 0, p(d_heads), p(d_sites),
+                                                                 MAX_SITES, 150, None, C.byref(ms)), "search"))
+        step("lists", lambda: _lib.check(L.bbm_sitelist_from_search_dev(h, p(d_heads), p(d_sites), n, MAX_SITES, p(d_lists), p(d_nss), CAP, None), "from_search"))
+        step("trimList", lambda: sitelist(sl.SL_TRIM))
+        step("scoreNoIndels", lambda: sitelist(sl.SL_NOINDEL))
+
+        def slow():
+            near = d_out.view(torch.int32).view(n, 4)[:, 0]
+            run_flags[0] = (near < 1).to(torch.int32).contiguous()            # processRead :463-465: scoreSlow only without a near-perfect site
+            _lib.check(L.bbm_scoreslow_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_bases), p(d_basesM), d_chroms, p(d_co), p(run_flags[0]), cp(wcfg), p(d_status),
+                                           150, None, C.byref(na), None), "bbm_scoreslow_dev")
+        step("scoreSlow", slow)
+        step("final", lambda: sitelist(sl.SL_FINAL))
+
+    L.bbm_launch_count.restype = C.c_int64
+    totals = []
+    for rep in range(reps + 1):
+        l0 = L.bbm_launch_count(h)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        chain()
+        torch.cuda.synchronize(); totals.append(1e3 * (time.perf_counter() - t0))
+        launches = L.bbm_launch_count(h) - l0
+        if rep == 0:
+            t.clear(); totals.clear()                                         # first pass is warm-up (allocations inside the library)
+    lists = np.frombuffer(d_lists.cpu().numpy().tobytes(), sl.SS_DTYPE).reshape(n, CAP)
+    nss = d_nss.cpu().numpy(); out = np.frombuffer(d_out.cpu().numpy().tobytes(), sl.READ_OUT_DTYPE); status = d_status.cpu().numpy()
+    tr = R["truth"]; top = lists[:, 0]
+    mapped = (out["flags"] & sl.F_MAPPED) != 0
+    correct = mapped & (top["chrom"] == tr[:, 0]) & (top["strand"] == tr[:, 1]) & ((np.abs(top["start"] - tr[:, 2]) <= 8) | (np.abs(top["stop"] - tr[:, 3]) <= 8))
+    exact = mapped & (top["start"] == tr[:, 2]) & (top["stop"] == tr[:, 3])
+    med = float(np.median(totals))
+    res = {"workload": "%d bp random reference, %d reads of 150 bp (the mates of %d pairs mapped as single reads), ~1%% subs, 1-3 bp indel in ~50%% of reads, Q30" % (genome_len, n, pairs),
+           "reads": n, "ms": med, "reads_per_s": n / (med / 1e3), "launches_per_pass": int(launches),
+           "stage_ms": {k: float(np.median(v)) for k, v in t.items()},
+           "slow_alignments": int(na.value), "reads_slow_aligned": float(run_flags[0].float().mean().item()),
+           "mapped": float(mapped.mean()), "top_site_is_origin": float(correct.mean()), "top_site_exact_start_and_stop": float(exact.mean()),
+           "ambiguous": float(((out["flags"] & sl.F_AMBIGUOUS) != 0).mean()), "status_nonzero": int((status != 0).sum()), "status_gapped_site": int(((status & sl.SLOW_GAPPED) != 0).sum()),
+           "status_aligner_error": int(((status & sl.SLOW_ALIGNER_ERROR) != 0).sum()),
+           "mean_sites_after_final": float(nss.mean()),
+           "not_chained_yet": "findTipDeletions rescoring, genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
+           "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
+    idx.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=200_000)
+    ap.add_argument("--genome", type=int, default=4_600_000)
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    print(json.dumps(run(a.pairs, a.genome, a.reps)))
+
+
+if __name__ == "__main__":
+    main()
