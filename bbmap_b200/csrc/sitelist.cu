@@ -96,6 +96,13 @@ __device__ int trim_list(bbm_ss* v, int& n, bool retainPaired, int maxScore, boo
     return highest;
 }
 
+// SiteScore.setSlowScore (stream/SiteScore.java:962-983): also moves pairedScore
+__device__ __forceinline__ void set_slow_score(bbm_ss& s, int x) {
+    if (x <= 0) { s.paired_score = x; }
+    else if (s.paired_score > 0) s.paired_score = (s.slow_score > 0) ? x + (s.paired_score - s.slow_score) : x + 1;
+    s.slow_score = x;
+}
+
 __device__ __forceinline__ int max_quality(int len) { return 70 + (len - 1) * 100; }                    // …JNI.java:1321-1323
 __device__ __forceinline__ int max_imperfect(int len) { return max_quality(len) + imin(-472, -395 - 100); }   // :1331-1336
 
@@ -214,14 +221,14 @@ __global__ void __launch_bounds__(128) sitelist_kernel(SitelistParams P) {
             const int refLen = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
             if (ss.perfect) {
                 numNear++;
-                ss.slow_score = maxSw; ss.score = maxSw; ss.ngaps = 0;
+                set_slow_score(ss, maxSw); ss.score = maxSw; ss.ngaps = 0;
             } else {
                 int sni = score_no_indels(bases, len, ref, refLen, ss.start);
                 if (sni < oldScore && oldScore >= maxImp && sslen != len) {
                     const int s2 = score_no_indels(bases, len, ref, refLen, ss.stop - len + 1);
                     if (s2 >= maxImp) { sni = s2; ss.start = ss.stop - len + 1; ss_set_perfect(ss, bases, len, ref, refLen); }
                 }
-                ss.slow_score = sni; ss.score = sni;
+                set_slow_score(ss, sni); ss.score = sni;
                 if (sni >= maxImp) {
                     numNear++;
                     ss.stop = ss.start + len - 1; ss.ngaps = 0;
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
         if (active) {
             atomicAdd(P.counters, 1);
             bbm_ss ss = P.lists[r * P.cap + k];
-            if (ss.stop - ss.start != len - 1) { ss.slow_score = 0; ss.semiperfect = 0; ss.perfect = 0; }
+            if (ss.stop - ss.start != len - 1) { set_slow_score(ss, 0); ss.semiperfect = 0; ss.perfect = 0; }
             const int sw = ss.slow_score;
             if (sw < max_imperfect(len) && !ss.semiperfect) {
                 if (ss.ngaps > 0) st[14] |= BBM_SLOW_GAPPED;
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
                 const int n2 = (o.status == 0) ? o.score_len : 0;
                 if (!(n2 == 0 || o.score[0] < a0)) { n = n2; a0 = o.score[0]; a1 = o.score[1]; a2 = o.score[2]; }
             }
-            if (n > 0) { ss.slow_score = a0; ss.start = a1; ss.stop = a2; }
+            if (n > 0) { set_slow_score(ss, a0); ss.start = a1; ss.stop = a2; }
             ss.score = ss.slow_score;
             st[1] = imax(st[1], ss.slow_score);
             st[0] = imax(st[0], ss.slow_score - cfg.clearzone3);

@@ -32,7 +32,33 @@ from bbmap_b200.search import HEAD_DTYPE, SITE_DTYPE  # noqa: E402
 MAXK, MAX_SITES, CAP = 32, 16, 16
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0):
+def cpu_side(R, cb, co, n_cpu=20000):
+    """The same chain through the CPU oracle (C restatements, one host thread) on the first n_cpu reads — a reported baseline."""
+    from oracle import oracle as orc
+    o = orc.get()
+    m = min(n_cpu, len(R["off"]) - 1)
+    off = R["off"][:m + 1]; nb = int(off[-1])
+    idx = o.index_build(cb, co, 13, -1)                       # not timed: the index is built once per genome
+    t0 = time.perf_counter()
+    bases, qual, basesM, _ = o.ingest_batch(R["bases"][:nb], R["qual"][:nb], off, 0)
+    seeds = o.seed_batch(bases, qual, off, default_cfg(), MAXK)
+    res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=False)
+    ns = np.minimum(res["nsites"], CAP).astype(np.int32)
+    lists = np.zeros((m, CAP), sl.SS_DTYPE); S = res["sites"][:, :CAP]
+    for f in ("chrom", "start", "stop", "hits", "score", "strand", "perfect", "semiperfect", "ngaps", "gaps"):
+        lists[f] = S[f]
+    lists["quick_score"] = S["score"]
+    pcfg = sl.policy_cfg()
+    lists, ns, _ = o.sitelist(sl.SL_TRIM, lists, ns, off, pcfg)
+    lists, ns, out = o.sitelist(sl.SL_NOINDEL, lists, ns, off, pcfg, bases, basesM, cb, co)
+    lists, _, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, (out["near_perfect"] < 1).astype(np.int32), sl.slow_cfg())
+    lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
+    dt = time.perf_counter() - t0
+    return {"reads": m, "cores": 1, "kind": "port", "seconds": dt, "reads_per_s": m / dt, "slow_alignments": int(na),
+            "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy()}
+
+
+def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
@@ -119,6 +145,13 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0):
            "mean_sites_after_final": float(nss.mean()),
            "not_chained_yet": "findTipDeletions rescoring, genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
            "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
+    if cpu:
+        cs = cpu_side(R, cb, co)
+        m = cs["reads"]; cl = cs.pop("lists"); cn = cs.pop("nss"); cf = cs.pop("flags")
+        live = np.arange(CAP)[None, :] < cn[:, None]
+        same = bool(np.array_equal(cn, nss[:m]) and np.array_equal(cf, out["flags"][:m]) and all(np.array_equal(cl[f][live], lists[:m][f][live]) for f in cl.dtype.names))
+        cs["device_chain_identical_on_sample"] = same          # every field of every final site + the read flags, device chain vs CPU chain
+        res["cpu_baseline"] = cs
     idx.close()
     return res
 
@@ -128,8 +161,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=200_000)
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
-    print(json.dumps(run(a.pairs, a.genome, a.reps)))
+    print(json.dumps(run(a.pairs, a.genome, a.reps, cpu=not a.no_cpu)))
 
 
 if __name__ == "__main__":

@@ -49,7 +49,7 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
             orc_ss* ss = &lists[r * cap + i];
             const int8_t* bases = (ss->strand == 0 ? basesP : basesM) + read_off[r];
             const int8_t* ref = refs + chrom_off[ss->chrom - 1]; const int refLen = (int)(chrom_off[ss->chrom] - chrom_off[ss->chrom - 1]);
-            if (ss->stop - ss->start != len - 1) { ss->slow_score = 0; ss->semiperfect = 0; ss->perfect = 0; }
+            if (ss->stop - ss->start != len - 1) { orc_ss_set_slow_score(ss, 0); ss->semiperfect = 0; ss->perfect = 0; }
             const int swscoreNoIndel = ss->slow_score;
             int32_t arr[8], old[8], max4[4]; int n = 0;
             if (swscoreNoIndel < maxImperfectSwScore && !ss->semiperfect) {
@@ -71,7 +71,7 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
                     }
                 }
             }
-            if (n > 0) { ss->slow_score = arr[0]; ss->start = arr[1]; ss->stop = arr[2]; }
+            if (n > 0) { orc_ss_set_slow_score(ss, arr[0]); ss->start = arr[1]; ss->stop = arr[2]; }
             ss->score = ss->slow_score;
             minMatch = imax2(minMatch, ss->slow_score);
             minMsaLimit = imax2(minMsaLimit, ss->slow_score - cfg->clearzone3);

@@ -10,6 +10,7 @@
  */
 #include "sitelist_oracle.h"
 #include "host_oracle.h"
+#include "rescue_oracle.h"
 #include <string.h>
 
 static int imax(int a, int b) { return a > b ? a : b; }
@@ -98,6 +99,14 @@ static int trim_list(orc_ss* v, int* n, int retainPaired, int maxScore, int spec
     return highest;
 }
 
+/* SiteScore.setSlowScore (stream/SiteScore.java:962-983): also moves pairedScore */
+void orc_ss_set_slow_score(orc_ss* s, int x) {
+    if (x <= 0) { s->paired_score = s->slow_score = x; }
+    else if (s->paired_score <= 0) { s->slow_score = x; }
+    else { if (s->slow_score > 0) s->paired_score = x + (s->paired_score - s->slow_score); else s->paired_score = x + 1; }
+    s->slow_score = x;
+}
+
 static int max_quality(int len) { return 70 + (len - 1) * 100; }
 static int max_imperfect(int len) { return max_quality(len) + imin(-472, -395 - 100); }
 
@@ -153,14 +162,14 @@ void orc_sitelist_noindel(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t c
             int sni;
             if (ss->perfect) {
                 numNear++;
-                sni = maxSw; ss->slow_score = sni; ss->score = sni; ss->ngaps = 0;
+                sni = maxSw; orc_ss_set_slow_score(ss, sni); ss->score = sni; ss->ngaps = 0;
             } else {
                 sni = orc_score_no_indels(bases, len, ref, refLen, ss->start, 0);
                 if (sni < oldScore && oldScore >= maxImp && sslen != len) {
                     const int s2 = orc_score_no_indels(bases, len, ref, refLen, ss->stop - len + 1, 0);
                     if (s2 >= maxImp) { sni = s2; ss->start = ss->stop - len + 1; ss_set_perfect(ss, bases, len, ref, refLen); }
                 }
-                ss->slow_score = sni; ss->score = sni;
+                orc_ss_set_slow_score(ss, sni); ss->score = sni;
                 if (sni >= maxImp) {
                     numNear++;
                     ss->stop = ss->start + len - 1; ss->ngaps = 0;
@@ -277,5 +286,72 @@ void orc_sitelist_final(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap
         if (perfect && n > 0) flags |= 2;
         nss[r] = n;
         out[r].near_perfect = 0; out[r].flags = flags; out[r].clearzone = clearzone; out[r].best_sites = numBest;
+    }
+}
+
+/* AbstractMapThread.findTipDeletions(Read r, basesP, basesM, maxSwScore, maxImperfectScore) (current/align2/AbstractMapThread.java:1073-1104) with the
+ * quality gate of Read.min/avgQuality{First,Last}NBases (current/stream/Read.java:1760-1815; quality == NULL: the FASTA path).  out[r].best_sites
+ * counts the sites that changed.  Sites with gaps would go through setStart/setStop -> GapTools.fixGaps: skipped and flagged (flags bit 3). */
+void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
+                         const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* chrom_min_index, const orc_tipdel_cfg* tc, orc_read_out* out)
+{
+    const int TIPLEN = tc->max_tiplen;
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; const int n = nss[r];
+        const int len = (int)(read_off[r + 1] - read_off[r]);
+        out[r].near_perfect = 0; out[r].flags = 0; out[r].clearzone = 0; out[r].best_sites = 0;
+        if (len == 0) continue;
+        int findRight = 1, findLeft = 1;
+        if (quality) {
+            const int8_t* q = quality + read_off[r];
+            int minL = 0, avgL = 0, minF = 0, avgF = 0;
+            if (TIPLEN <= len) {
+                int x = 0; minL = q[len - TIPLEN];
+                for (int i = len - TIPLEN; i < len; i++) { const int b = q[i]; x += (b < 0 ? 0 : b); if (b < minL) minL = b; }
+                avgL = x / TIPLEN;
+                x = 0; minF = q[0];
+                for (int i = 0; i < TIPLEN; i++) { const int b = q[i]; x += (b < 0 ? 0 : b); if (i >= 1 && b < minF) minF = b; }
+                avgF = x / TIPLEN;
+            }
+            findRight = (minL >= 6 && avgL >= 14); findLeft = (minF >= 6 && avgF >= 14);
+        }
+        if (!findRight && !findLeft) continue;
+        const int maxSw = max_quality(len), maxImp = max_imperfect(len);
+        for (int j = 0; j < n; j++) {
+            orc_ss* ss = &v[j];
+            if (ss->semiperfect || ss->slow_score >= maxImp) continue;
+            if (ss->ngaps > 0) { out[r].flags |= 8; continue; }
+            const int8_t* bases = (ss->strand == 0 ? basesP : basesM) + read_off[r];
+            const int8_t* ref = refs + chrom_off[ss->chrom - 1]; const int refLen = (int)(chrom_off[ss->chrom] - chrom_off[ss->chrom - 1]);
+            const int minIndex = chrom_min_index ? chrom_min_index[ss->chrom - 1] : 0;
+            /* findTipDeletions(ss, bases, maxImperfectScore, lookRight, lookLeft) :1107-1141 */
+            int changed = 0;
+            if (len > 2 * TIPLEN) {
+                int maxSearch = tc->search_range;
+                maxSearch = imin(maxSearch, tc->align_columns - (tc->slow_rescue_padding + 8 + imax(len, ss->stop - ss->start)));
+                if (maxSearch >= 1) {
+                    int go = 1;
+                    if (findRight) {
+                        const int x = orc_find_tip_deletions_right(bases, len, ref, refLen, minIndex, ss->stop, maxSearch, TIPLEN);
+                        if (x > 0) {
+                            ss->stop += x; changed = 1;
+                            maxSearch = imin(maxSearch, tc->align_columns - (tc->slow_rescue_padding + 8 + imax(len, ss->stop - ss->start)));
+                            if (maxSearch < 1) go = 0;
+                        }
+                    }
+                    if (go && findLeft) {
+                        const int y = orc_find_tip_deletions_left(bases, len, ref, refLen, minIndex, ss->start, maxSearch, TIPLEN);
+                        if (y > 0) { ss->start -= y; changed = 1; }
+                    }
+                }
+            }
+            if (changed) {
+                out[r].best_sites++;
+                ss->has_match = 0;
+                orc_ss_set_slow_score(ss, orc_score_no_indels(bases, len, ref, refLen, ss->start, 0));
+                if (ss->slow_score == maxSw) { ss->stop = ss->start + len - 1; ss->perfect = ss->semiperfect = 1; }
+                else { ss->perfect = 0; ss_set_perfect(ss, bases, len, ref, refLen); }
+            }
+        }
     }
 }

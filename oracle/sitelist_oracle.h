@@ -3,6 +3,7 @@
  * pinned by hand-built lists in tests/test_sitelist_oracle.py. */
 #pragma once
 #include <stdint.h>
+#include "rescue_oracle.h"
 
 #define ORC_MAX_GAPS 10
 typedef struct {            /* == bbm_ss (include/bbmap_cuda.h), 80 bytes */
@@ -20,7 +21,10 @@ typedef struct {            /* == bbm_policy_cfg, 80 bytes */
 } orc_policy_cfg;
 typedef struct { int32_t near_perfect, flags, clearzone, best_sites; } orc_read_out;   /* flags: bit0 mapped, bit1 perfect, bit2 ambiguous */
 
+void orc_ss_set_slow_score(orc_ss* s, int x);
 void orc_sitelist_trim(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out);
 void orc_sitelist_noindel(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
                           const int8_t* refs, const int64_t* chrom_off, const orc_policy_cfg* cfg, orc_read_out* out);
 void orc_sitelist_final(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out);
+void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
+                         const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* chrom_min_index, const orc_tipdel_cfg* tc, orc_read_out* out);

@@ -70,7 +70,7 @@ def test_final_policy_by_hand(oracle):
 
 def test_noindel_policy_properties(oracle):
     refs, co, P, M, ro, lists, nss = noindel_lists(nreads=800, seed=7)
-    cfg = sl.policy_cfg()
+    cfg = sl.policy_cfg(quick_match_strings=1)
     L2, n2, out = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, cfg, P, M, refs, co)
     assert np.array_equal(n2, nss)
     seen_shift = seen_match = 0
