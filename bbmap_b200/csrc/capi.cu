@@ -122,6 +122,7 @@ struct bbm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
+    long long strip_min_tasks = 8192;
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
@@ -239,7 +240,10 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     // 0 = off, 1 = try every shape-eligible alignment, n>1 = only those with (best possible score - minScore) <= n points
     const int useNarrow = (c->use_narrow && d_dump == nullptr) ? c->use_narrow : 0;
     // 0 = off; n>0: limited un-banded fills whose work estimate falls in buckets < n go to the strip kernel, larger ones to the tiled kernel
-    const int useStrip = (c->use_strip && d_dump == nullptr) ? c->use_strip : 0;
+    // The strip kernel is thread-per-alignment: it needs tens of thousands of alignments to fill 148 SMs, and a batch of a few dozen wide
+    // alignments would run as a few dozen single threads (measured: 14 alignments = 48 ms).  Small batches (scoreSlow's later rounds and
+    // padding retries) go to the warp-per-alignment tiled kernel instead; results are identical by construction and by test.
+    const int useStrip = (c->use_strip && d_dump == nullptr && ntasks >= c->strip_min_tasks) ? c->use_strip : 0;
     const int CS = bbm_msa_class_strip();
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
     if (useNarrow && c->nscratch.ensure((size_t)narrowWarps * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc narrow traceback scratch");
@@ -389,6 +393,7 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
 extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(BBM_E_ARG, "bbm_set_option: null");
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
+    if (!strcmp(key, "strip_min_tasks")) { c->strip_min_tasks = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }
     if (!strcmp(key, "search_split")) { c->search_split = value; return BBM_OK; }
@@ -974,6 +979,27 @@ extern "C" int bbm_sitelist_batch_host(bbm_ctx* c, int32_t op, bbm_ss* lists, in
     return rc;
 }
 
+extern "C" int bbm_launch_sitelist_tipdel(bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const int8_t* basesP,
+                                          const int8_t* basesM, const int8_t* quality, const int8_t* refs, const long long* chrom_off,
+                                          const int* chrom_min_index, const bbm_tipdel_cfg* tc, bbm_read_out* out, cudaStream_t st);
+extern "C" int bbm_sitelist_tipdel_dev(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                       const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_quality, const int8_t* d_refs, const int64_t* d_chrom_off,
+                                       const int32_t* d_chrom_min_index, const bbm_tipdel_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out) {
+    if (!c || !d_lists || !d_nss || !d_read_off || !d_basesP || !d_basesM || !d_refs || !d_chrom_off || !cfg || !d_out) return fail(BBM_E_ARG, "bbm_sitelist_tipdel_dev: null pointer");
+    if (cfg->max_tiplen < 3 || cfg->max_tiplen > 32 || cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_sitelist_tipdel_dev: bad cfg or cap");
+    if (nreads <= 0) { if (kernel_ms_out) *kernel_ms_out = 0.f; return BBM_OK; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (kernel_ms_out) CK(cudaEventRecord(c->ev0, st));
+    int e = bbm_launch_sitelist_tipdel(d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_basesP, d_basesM, d_quality, d_refs, (const long long*)d_chrom_off,
+                                       d_chrom_min_index, cfg, d_out, st);
+    if (e) return fail(BBM_E_CUDA, "sitelist_tipdel_kernel launch", (cudaError_t)e);
+    c->launches++;
+    if (kernel_ms_out) { CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1)); float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *kernel_ms_out = ms; }
+    return BBM_OK;
+}
+
 // =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
@@ -1001,22 +1027,29 @@ static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, i
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         return ce == cudaSuccess ? BBM_OK : fail(BBM_E_CUDA, "scoreSlow counters", ce);
     };
+    const bool trace = getenv("BBM_SLOW_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int k = 0; k < cap && rc == BBM_OK; ++k) {
         int h[2] = {0, 0};
+        const double t0 = now();
         if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
         if ((rc = launch(0, k)) || (rc = counts(h))) break;
+        if (trace) fprintf(stderr, "[scoreSlow] round %d: %d reads active, %d alignments requested (prep %.2f ms)\n", k, h[0], h[1], now() - t0);
         if (h[0] == 0) break;                                   // no read has a k-th site
         if (h[1] > 0) {
             aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[scoreSlow]   first pass done at %.2f ms\n", now() - t0); }
         if ((rc = launch(1, k)) || (rc = counts(h))) break;
+        if (trace) fprintf(stderr, "[scoreSlow]   %d padding retries\n", h[1]);
         if (h[1] > 0) {
             aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if ((rc = launch(2, k))) break;
+        if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[scoreSlow]   round done at %.2f ms\n", now() - t0); }
     }
     if (rc == BBM_OK && d_status) {
         cudaError_t ce = cudaMemcpy2DAsync(d_status, 4, (const int*)state.p + 14, (size_t)SI * 4, 4, (size_t)nreads, cudaMemcpyDeviceToDevice, st);

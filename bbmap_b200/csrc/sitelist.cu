@@ -311,6 +311,119 @@ __global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_sea
 }
 
 
+// =====================  findTipDeletions(Read, ...) (AbstractMapThread.java:1073-1104)  =====================
+// Scalar forms of findTipDeletionsRight/Left (:2178-2294; the warp-per-task forms live in rescue.cu): here the unit is the read, the
+// scans are short (<= 100 starts x 8 bases) and most sites stop after the 8-base tip check.
+__device__ int tip_right(const int8_t* __restrict__ bases, int len, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStop, int searchDist, int tiplen) {
+    if (originalStop < minIndex + tiplen - 1 || originalStop >= refLen) return 0;
+    const int tipCoord = len - 1;
+    int lastMismatch = 0, originalMismatches = 0, contig = 0;
+    for (int i = 0; i < tiplen && contig < 5; i++) {
+        if (bases[tipCoord - i] != ref[originalStop - i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
+    }
+    if (originalMismatches < 3) return 0;
+    int minMismatches = originalMismatches, bestStart = originalStop;
+    tiplen = lastMismatch + 1;
+    if (tiplen < 4) return 0;
+    searchDist = imin(searchDist, 30 * originalMismatches);
+    const int last = imin(refLen - 1, originalStop + searchDist);
+    for (int start = originalStop + 1; start <= last && minMismatches > 0; start++) {
+        int m = 0;
+        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[tipCoord - j] != ref[start - j]) ? 1 : 0;
+        if (m < minMismatches) { bestStart = start; minMismatches = m; }
+    }
+    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
+    return bestStart - originalStop;
+}
+__device__ int tip_left(const int8_t* __restrict__ bases, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStart, int searchDist, int tiplen) {
+    if (originalStart + tiplen >= refLen || minIndex >= originalStart) return 0;
+    int lastMismatch = 0, originalMismatches = 0, contig = 0;
+    for (int i = 0; i < tiplen && contig < 5; i++) {
+        if (bases[i] != ref[originalStart + i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
+    }
+    if (originalMismatches < 3) return 0;
+    int minMismatches = originalMismatches, bestStart = originalStart;
+    tiplen = lastMismatch + 1;
+    if (tiplen < 4) return 0;
+    searchDist = imin(searchDist, 16 + 16 * originalMismatches + 8 * tiplen);
+    const int last = imax(minIndex, originalStart - searchDist);
+    for (int start = originalStart - 1; start >= last && minMismatches > 0; start--) {
+        int m = 0;
+        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[j] != ref[start + j]) ? 1 : 0;
+        if (m < minMismatches) { bestStart = start; minMismatches = m; }
+    }
+    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
+    return originalStart - bestStart;
+}
+
+struct TipParams {
+    bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off; const int8_t* basesP; const int8_t* basesM;
+    const int8_t* quality; const int8_t* refs; const long long* chrom_off; const int* chrom_min_index; bbm_tipdel_cfg tc; bbm_read_out* out;
+};
+
+__global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    bbm_ss* v = P.lists + r * P.cap;
+    const int n = P.nss[r], len = (int)(P.read_off[r + 1] - P.read_off[r]), TIPLEN = P.tc.max_tiplen;
+    bbm_read_out o; o.near_perfect = 0; o.flags = 0; o.clearzone = 0; o.best_sites = 0;
+    bool findRight = true, findLeft = true;
+    if (len == 0) { P.out[r] = o; return; }
+    if (P.quality) {                                   // Read.min/avgQuality{First,Last}NBases (stream/Read.java:1760-1815)
+        const int8_t* q = P.quality + P.read_off[r];
+        int minL = 0, avgL = 0, minF = 0, avgF = 0;
+        if (TIPLEN <= len) {
+            int x = 0; minL = q[len - TIPLEN];
+            for (int i = len - TIPLEN; i < len; i++) { const int b = q[i]; x += (b < 0 ? 0 : b); minL = imin(minL, b); }
+            avgL = x / TIPLEN;
+            x = 0; minF = q[0];
+            for (int i = 0; i < TIPLEN; i++) { const int b = q[i]; x += (b < 0 ? 0 : b); minF = imin(minF, b); }
+            avgF = x / TIPLEN;
+        }
+        findRight = (minL >= 6 && avgL >= 14); findLeft = (minF >= 6 && avgF >= 14);
+    }
+    if (findRight || findLeft) {
+        const int maxSw = max_quality(len), maxImp = max_imperfect(len);
+        for (int j = 0; j < n; j++) {
+            bbm_ss ss = v[j];
+            if (ss.semiperfect || ss.slow_score >= maxImp) continue;
+            if (ss.ngaps > 0) { o.flags |= 8; continue; }
+            const int8_t* bases = (ss.strand == 0 ? P.basesP : P.basesM) + P.read_off[r];
+            const int8_t* ref = P.refs + P.chrom_off[ss.chrom - 1];
+            const int refLen = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
+            const int minIndex = P.chrom_min_index ? P.chrom_min_index[ss.chrom - 1] : 0;
+            bool changed = false;
+            if (len > 2 * TIPLEN) {
+                int maxSearch = imin(P.tc.search_range, P.tc.align_columns - (P.tc.slow_rescue_padding + 8 + imax(len, ss.stop - ss.start)));
+                if (maxSearch >= 1) {
+                    bool go = true;
+                    if (findRight) {
+                        const int x = tip_right(bases, len, ref, refLen, minIndex, ss.stop, maxSearch, TIPLEN);
+                        if (x > 0) {
+                            ss.stop += x; changed = true;
+                            maxSearch = imin(maxSearch, P.tc.align_columns - (P.tc.slow_rescue_padding + 8 + imax(len, ss.stop - ss.start)));
+                            if (maxSearch < 1) go = false;
+                        }
+                    }
+                    if (go && findLeft) {
+                        const int y = tip_left(bases, ref, refLen, minIndex, ss.start, maxSearch, TIPLEN);
+                        if (y > 0) { ss.start -= y; changed = true; }
+                    }
+                }
+            }
+            if (changed) {
+                o.best_sites++;
+                ss.has_match = 0;
+                set_slow_score(ss, score_no_indels(bases, len, ref, refLen, ss.start));
+                if (ss.slow_score == maxSw) { ss.stop = ss.start + len - 1; ss.perfect = 1; ss.semiperfect = 1; }
+                else { ss.perfect = 0; ss_set_perfect(ss, bases, len, ref, refLen); }
+                v[j] = ss;
+            }
+        }
+    }
+    P.out[r] = o;
+}
+
 // =====================  scoreSlow in rounds (BBMapThread.scoreSlow, current/align2/BBMapThread.java:252-386)  =====================
 // scoreSlow walks the sites of one read in order because its limit ratchets: minMsaLimit = max(minMsaLimit, slowScore - CLEARZONE3)
 // after every site (:375-376).  Reads are independent, so the batched form is rounds: round k handles the k-th site of every read —
@@ -448,3 +561,13 @@ extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const i
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_scoreslow_state_ints() { return bbm::SLOW_STATE; }
+
+extern "C" int bbm_launch_sitelist_tipdel(bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const int8_t* basesP,
+                                          const int8_t* basesM, const int8_t* quality, const int8_t* refs, const long long* chrom_off,
+                                          const int* chrom_min_index, const bbm_tipdel_cfg* tc, bbm_read_out* out, cudaStream_t st) {
+    bbm::TipParams P;
+    P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP; P.basesM = basesM; P.quality = quality;
+    P.refs = refs; P.chrom_off = chrom_off; P.chrom_min_index = chrom_min_index; P.tc = *tc; P.out = out;
+    bbm::sitelist_tipdel_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}

@@ -92,3 +92,28 @@ def scoreSlow(ctx, lists, nss, read_off, basesP, basesM, d_ref, chrom_off, run, 
     _lib.check(L.bbm_scoreslow_host(ctx, _p(lists), _p(nss), n, cap, _p(ro), _p(bp), _p(bm), d_ref, _p(co), len(co) - 1, _p(rn), _p(cfg), _p(status),
                                     C.byref(na)), "bbm_scoreslow_host")
     return lists, status, na.value
+
+
+def findTipDeletions(ctx, lists, nss, read_off, basesP, basesM, quality, d_ref, chrom_off, cfg=None, chrom_min_index=None, device=0):
+    """AbstractMapThread.findTipDeletions(Read, ...) on every list (staged through torch tensors; the entry point itself is device-resident).
+    Returns (lists, READ_OUT_DTYPE[n])."""
+    import torch
+    from .rescue import tipdel_cfg
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: findTipDeletions has no CPU fallback")
+    cfg = tipdel_cfg() if cfg is None else cfg
+    lists = np.ascontiguousarray(lists, SS_DTYPE); n, cap = lists.shape
+    dev = torch.device("cuda", device)
+    up = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else np.asarray(a, dt)).view(np.uint8).reshape(-1).copy()).to(dev)
+    q = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    d_l = up(lists); d_n = up(nss, np.int32); d_o = up(read_off, np.int64); d_p = up(np.concatenate([np.ascontiguousarray(basesP).view(np.uint8), np.zeros(16, np.uint8)]))
+    d_m = up(np.concatenate([np.ascontiguousarray(basesM).view(np.uint8), np.zeros(16, np.uint8)]))
+    d_q = None if quality is None else up(np.concatenate([np.ascontiguousarray(quality).view(np.uint8), np.zeros(16, np.uint8)]))
+    d_c = up(chrom_off, np.int64); d_mi = None if chrom_min_index is None else up(chrom_min_index, np.int32)
+    d_out = torch.zeros(max(n, 1) * READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    _lib.check(L.bbm_sitelist_tipdel_dev(ctx, q(d_l), q(d_n), n, cap, q(d_o), q(d_p), q(d_m), q(d_q), d_ref, q(d_c), q(d_mi), _p(cfg), q(d_out), None, None),
+               "bbm_sitelist_tipdel_dev")
+    torch.cuda.synchronize()
+    return (np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(),
+            np.frombuffer(d_out.cpu().numpy().tobytes(), READ_OUT_DTYPE)[:n].copy())

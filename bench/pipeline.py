@@ -1,11 +1,11 @@
 """The device stages of the unpaired mapping loop chained with everything resident in HBM (no host round trip between stages):
 
     Read.validate -> KeyRing seeds -> BBIndex.find -> SiteScore lists -> trimList -> scoreNoIndels(Read) -> scoreSlow (rounds over the
-    MultiStateAligner11ts kernels, padding retry included) -> mergeDuplicateSites / clearzone / removeLowQualitySitesUnpaired
+    MultiStateAligner11ts kernels, padding retry included; findTipDeletions before it) -> mergeDuplicateSites / clearzone / removeLowQualitySitesUnpaired
 
 on BASELINE configs[1]-shaped input (E. coli-sized random reference, 2x150 bp reads mapped as single reads, ~1 % substitutions, 1-3 bp
 indels, Q30).  What the reference's processRead (current/align2/BBMapThread.java:389-733) does in addition and is NOT in this chain yet:
-findTipDeletions' rescoring of changed sites, genMatchString/realign_new, applyClearzone3, the tip-score penalty, pairing and rescue, SAM
+genMatchString/realign_new, applyClearzone3, the tip-score penalty, pairing and rescue, SAM
 text.  The reads/s printed here is therefore the throughput of the built device stages up to the final site decision (strand, POS, score,
 ambiguity), not yet a whole-mapper number.
 
@@ -51,7 +51,10 @@ def cpu_side(R, cb, co, n_cpu=20000):
     pcfg = sl.policy_cfg()
     lists, ns, _ = o.sitelist(sl.SL_TRIM, lists, ns, off, pcfg)
     lists, ns, out = o.sitelist(sl.SL_NOINDEL, lists, ns, off, pcfg, bases, basesM, cb, co)
-    lists, _, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, (out["near_perfect"] < 1).astype(np.int32), sl.slow_cfg())
+    runm = (out["near_perfect"] < 1).astype(np.int32)
+    from bbmap_b200.rescue import tipdel_cfg
+    lists, _ = o.sitelist_tipdel(lists, ns * runm, off, bases, basesM, qual, cb, co, tipdel_cfg())
+    lists, _, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, runm, sl.slow_cfg())
     lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
     dt = time.perf_counter() - t0
     return {"reads": m, "cores": 1, "kind": "port", "seconds": dt, "reads_per_s": m / dt, "slow_alignments": int(na),
@@ -84,7 +87,9 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
     d_co = torch.from_numpy(np.ascontiguousarray(co, np.int64)).to(dev)
     d_chroms = C.c_void_p(idx.d_chroms.value)
-    scfg = default_cfg(); pcfg = sl.policy_cfg(); wcfg = sl.slow_cfg()
+    from bbmap_b200.rescue import tipdel_cfg
+    scfg = default_cfg(); pcfg = sl.policy_cfg(); wcfg = sl.slow_cfg(); tcfg = tipdel_cfg()
+    d_out2 = torch.zeros(n * sl.READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     cp = lambda a: a.ctypes.data_as(C.c_void_p)
     ms = C.c_float(0); na = C.c_int64(0)
     t = {}
@@ -97,7 +102,7 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
         _lib.check(L.bbm_sitelist_batch_dev(h, op, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_bases), p(d_basesM), d_chroms, p(d_co), cp(pcfg), p(d_out), None, None),
                    "bbm_sitelist_batch_dev")
 
-    run_flags = [None]
+    run_flags = [None]; masked = [None]
 
     def chain():
         d_bases.copy_(d_bases0); d_qual.copy_(d_qual0)            # Read.validate works in place
@@ -110,9 +115,13 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
         step("trimList", lambda: sitelist(sl.SL_TRIM))
         step("scoreNoIndels", lambda: sitelist(sl.SL_NOINDEL))
 
+        step("run_mask", lambda: run_flags.__setitem__(0, (d_out.view(torch.int32).view(n, 4)[:, 0] < 1).to(torch.int32).contiguous()))   # processRead :455-465
+        # findTipDeletions runs under the same condition; reads that skip it keep nss as is (the kernel sees 0 sites for them)
+        masked[0] = (d_nss * run_flags[0]).contiguous()
+        step("findTipDeletions", lambda: _lib.check(L.bbm_sitelist_tipdel_dev(h, p(d_lists), p(masked[0]), n, CAP, p(d_off), p(d_bases), p(d_basesM),
+                                                                             p(d_qual), d_chroms, p(d_co), None, cp(tcfg), p(d_out2), None, None), "tipdel"))
+
         def slow():
-            near = d_out.view(torch.int32).view(n, 4)[:, 0]
-            run_flags[0] = (near < 1).to(torch.int32).contiguous()            # processRead :463-465: scoreSlow only without a near-perfect site
             _lib.check(L.bbm_scoreslow_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_bases), p(d_basesM), d_chroms, p(d_co), p(run_flags[0]), cp(wcfg), p(d_status),
                                            150, None, C.byref(na), None), "bbm_scoreslow_dev")
         step("scoreSlow", slow)
@@ -143,7 +152,8 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
            "ambiguous": float(((out["flags"] & sl.F_AMBIGUOUS) != 0).mean()), "status_nonzero": int((status != 0).sum()), "status_gapped_site": int(((status & sl.SLOW_GAPPED) != 0).sum()),
            "status_aligner_error": int(((status & sl.SLOW_ALIGNER_ERROR) != 0).sum()),
            "mean_sites_after_final": float(nss.mean()),
-           "not_chained_yet": "findTipDeletions rescoring, genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
+           "tip_deletion_sites_changed": int(np.frombuffer(d_out2.cpu().numpy().tobytes(), sl.READ_OUT_DTYPE)["best_sites"].sum()),
+           "not_chained_yet": "genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
            "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
     if cpu:
         cs = cpu_side(R, cb, co)

@@ -365,6 +365,14 @@ int  bbm_sitelist_batch_host(bbm_ctx* ctx, int32_t op, bbm_ss* lists, int32_t* n
                              const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
                              const bbm_policy_cfg* cfg, bbm_read_out* out);
 
+/* AbstractMapThread.findTipDeletions(Read r, basesP, basesM, maxSwScore, maxImperfectScore) (current/align2/AbstractMapThread.java:1073-1104) on
+ * every read's list: quality gate (d_quality NULL = FASTA), findTipDeletions per eligible site, and for changed sites the rescoring with
+ * scoreNoIndels and the perfect/semiperfect update.  d_out[r].best_sites = sites changed; flags bit3 = a gapped site was skipped
+ * (setStart/setStop on gapped sites need GapTools.fixGaps).  d_chrom_min_index may be NULL (minIndex 0 everywhere). */
+int  bbm_sitelist_tipdel_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                             const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_quality, const int8_t* d_refs, const int64_t* d_chrom_off,
+                             const int32_t* d_chrom_min_index, const bbm_tipdel_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out);
+
 /* ---- BBMapThread.scoreSlow over a batch of reads, in rounds (current/align2/BBMapThread.java:252-386; part of SURVEY 8f.1) ----
  * Round k slow-aligns the k-th site of every read whose run[r] != 0 (processRead calls scoreSlow when scoreNoIndels found no
  * near-perfect site, :463-465): preamble, MSA.fillAndScoreLimited(bases, ss, SLOW_ALIGN_PADDING, max(slowScore, minMsaLimit)), the

@@ -266,6 +266,20 @@ class Oracle:
             self.lib.orc_sitelist_final(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(cfg), _p(out))
         return lists, nss, out
 
+    def sitelist_tipdel(self, lists, nss, read_off, basesP, basesM, quality, refs, chrom_off, cfg, chrom_min_index=None):
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); co = np.ascontiguousarray(chrom_off, np.int64)
+        bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8); rf = np.ascontiguousarray(refs).view(np.int8)
+        qq = None if quality is None else np.ascontiguousarray(quality).view(np.int8)
+        mi = None if chrom_min_index is None else np.ascontiguousarray(chrom_min_index, np.int32)
+        out = np.zeros(n, READ_OUT_DTYPE)
+        self.lib.orc_sitelist_tipdel.restype = None
+        self.lib.orc_sitelist_tipdel(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), None if qq is None else _p(qq), _p(ro), _p(rf), _p(co),
+                                     None if mi is None else _p(mi), _p(cfg), _p(out))
+        return lists, out
+
     def score_slow(self, lists, nss, read_off, basesP, basesM, refs, chrom_off, run, cfg):
         from bbmap_b200.sitelist import SS_DTYPE
         lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)

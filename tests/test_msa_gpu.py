@@ -15,6 +15,7 @@ def msa(request):
     from bbmap_b200.msa import MultiStateAligner11tsCUDA
     m = MultiStateAligner11tsCUDA()
     m.set_option("strip", {"strip": 16, "tiled": 0, "mixed": 3}[request.param])
+    m.set_option("strip_min_tasks", 0)     # the library keeps small batches away from the thread-per-alignment kernel; the tests want it exercised
     if request.param != "strip":
         m.set_option("narrow", 1)          # every shape-eligible alignment tries the narrow kernel first: exercises the hand-over path
     yield m

@@ -97,3 +97,34 @@ def test_from_search(msa):
                    (b["chrom"], b["start"], b["stop"], b["hits"], b["score"], b["score"], 0, 0)
             assert (a["strand"], a["perfect"], a["semiperfect"], a["rescued"], a["ngaps"]) == (b["strand"], b["perfect"], b["semiperfect"], 0, b["ngaps"])
             assert np.array_equal(a["gaps"], b["gaps"])
+
+
+@pytest.mark.parametrize("seed,with_quality", [(81, True), (86, False), (87, True)])
+def test_find_tip_deletions_read_parity(oracle, msa, seed, with_quality):
+    """findTipDeletions(Read, ...): quality gate, both tips, rescoring of the changed sites — on lists scored by scoreNoIndels."""
+    from bbmap_b200 import rescue as rs
+    from sitelist_cases import slow_cases
+    refs, co, P, M, ro, lists, nss, run = slow_cases(nreads=3000, seed=seed)
+    lists, _, _ = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, sl.policy_cfg(), P, M, refs, co)
+    rng = np.random.default_rng(seed)
+    quality = None
+    if with_quality:
+        quality = np.full(len(P), 30, np.int8)
+        for r in rng.choice(len(nss), size=600, replace=False):          # low-quality tips switch one or both searches off
+            a, b = int(ro[r]), int(ro[r + 1])
+            if rng.random() < 0.5:
+                quality[a:a + 8] = rng.integers(0, 16, size=8)
+            if rng.random() < 0.5:
+                quality[b - 8:b] = rng.integers(0, 16, size=8)
+    for cfg, mi in ((rs.tipdel_cfg(), None), (rs.tipdel_cfg(search_range=30), np.array([250], np.int32))):
+        exp, eo = oracle.sitelist_tipdel(lists, nss, ro, P, M, quality, refs, co, cfg, mi)
+        d_ref = msa.load_reference(refs)
+        try:
+            got, go = sl.findTipDeletions(msa.h, lists, nss, ro, P, M, quality, d_ref, co, cfg, mi)
+        finally:
+            msa.free(d_ref)
+        for f in eo.dtype.names:
+            assert np.array_equal(go[f], eo[f]), f
+        live = np.arange(exp.shape[1])[None, :] < nss[:, None]
+        assert got[live].tobytes() == exp[live].tobytes()
+    assert eo["best_sites"].sum() > 20 and (eo["flags"] & 8).any()
