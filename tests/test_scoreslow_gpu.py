@@ -23,6 +23,7 @@ def test_score_slow_parity(oracle, msa, seed, kw):
     lists, _, _ = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, sl.policy_cfg(), P, M, refs, co)
     cfg = sl.slow_cfg(**kw)
     exp, est, ena = oracle.score_slow(lists, nss, ro, P, M, refs, co, run, cfg)
+    msa.set_option("strip_min_tasks", 0 if seed % 2 == 0 else 8192)      # both routings of the aligner: thread-per-alignment strips and warp-per-alignment tiles
     d_ref = msa.load_reference(refs)
     try:
         got, gst, gna = sl.scoreSlow(msa.h, lists, nss, ro, P, M, d_ref, co, run, cfg)
