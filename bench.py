@@ -292,6 +292,18 @@ def main():
     from bbmap_b200 import shard
     ms_all, e2e_ms_step, kernel_ms_all = shard.max_over_ranks([ms, e2e_s * 1e3 / e2e_steps, kernel_ms], device=dev)
     total_cells_step, = shard.sum_over_ranks([float(cells_per_step)], device=dev)
+    pipe_multi = None
+    if world > 1 and not args.no_stages:
+        # reads/s of the chained device stages with the read batches sharded over the ranks (index and reference replicated, no collective):
+        # every rank maps its own shard (seed = rank) between two barriers; aggregate = reads of all ranks / slowest rank
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        import pipeline
+        barrier()
+        pr = pipeline.run(pairs=args.stage_pairs, device=local, cpu=False, seed=2 + rank)
+        pm, = shard.max_over_ranks([pr["ms"]], device=dev)
+        pn, = shard.sum_over_ranks([float(pr["reads"])], device=dev)
+        pipe_multi = {"n_gpus": world, "reads": int(pn), "ms_slowest_rank": pm, "reads_per_s": pn / (pm / 1e3), "scaling": "weak",
+                      "note": "bench/pipeline.py on every rank's own shard; see `pipeline` for the single-GPU stage split"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -334,6 +346,8 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "bench"))
         import stages
         msa.close()
+        if pipe_multi is not None:
+            line["pipeline_all_gpus"] = pipe_multi
         line["stages"] = stages.run(pairs=args.stage_pairs, device=local, hbm_peak=pk["hbm_gbs"])
         # the same stages chained on the device up to the final site decision (mapped reads/s of the built part of the mapper)
         import pipeline

@@ -61,13 +61,13 @@ def cpu_side(R, cb, co, n_cpu=20000):
             "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy()}
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True):
+def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
     torch.cuda.set_device(device)
     cb, co, table = pack_chromosomes([wl.random_genome(genome_len, seed=1)])
-    R = wl.make_mapping_reads(cb, co, table, pairs, seed=2)
+    R = wl.make_mapping_reads(cb, co, table, pairs, seed=seed)
     n = 2 * pairs; nb = len(R["bases"])
     idx = BBIndexCUDA(cb, co, keylen=13, device=device)
     h = idx.h
