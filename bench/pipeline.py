@@ -61,12 +61,31 @@ def cpu_side(R, cb, co, n_cpu=20000):
             "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy()}
 
 
-def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2):
+def make_reference(genome_len, scaffolds):
+    """One random scaffold (G2), or G3 of SURVEY 8d: `scaffolds` random scaffolds of unequal size + 1 % of the bases in planted 300-bp repeat
+    families of 100 copies (same generator as bench/stages.py)."""
+    if scaffolds <= 1:
+        return [wl.random_genome(genome_len, seed=1)]
+    rng = np.random.Generator(np.random.PCG64(3))
+    w = rng.uniform(0.4, 2.0, size=scaffolds); sizes = np.maximum(1000, (w / w.sum() * genome_len).astype(np.int64))
+    scafs = [wl.ACGT[rng.integers(0, 4, size=int(z), dtype=np.uint8)] for z in sizes]
+    fam = max(1, int(genome_len * 0.01 / 300 / 100))
+    for _ in range(fam):
+        unit = wl.ACGT[rng.integers(0, 4, size=300, dtype=np.uint8)]
+        for _c in range(100):
+            sc = scafs[int(rng.integers(0, scaffolds))]
+            q = int(rng.integers(0, len(sc) - 300)); sc[q:q + 300] = unit
+    return scafs
+
+
+def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2, scaffolds=1):
     import torch
     L = _lib.load()
     dev = torch.device("cuda", device)
     torch.cuda.set_device(device)
-    cb, co, table = pack_chromosomes([wl.random_genome(genome_len, seed=1)])
+    scafs = make_reference(genome_len, scaffolds)
+    cb, co, table = pack_chromosomes(scafs)
+    del scafs
     R = wl.make_mapping_reads(cb, co, table, pairs, seed=seed)
     n = 2 * pairs; nb = len(R["bases"])
     idx = BBIndexCUDA(cb, co, keylen=13, device=device)
@@ -144,7 +163,8 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2)
     correct = mapped & (top["chrom"] == tr[:, 0]) & (top["strand"] == tr[:, 1]) & ((np.abs(top["start"] - tr[:, 2]) <= 8) | (np.abs(top["stop"] - tr[:, 3]) <= 8))
     exact = mapped & (top["start"] == tr[:, 2]) & (top["stop"] == tr[:, 3])
     med = float(np.median(totals))
-    res = {"workload": "%d bp random reference, %d reads of 150 bp (the mates of %d pairs mapped as single reads), ~1%% subs, 1-3 bp indel in ~50%% of reads, Q30" % (genome_len, n, pairs),
+    res = {"reference": "%d scaffold(s), %d chromosome array(s), %d index block(s)" % (scaffolds, len(co) - 1, idx.nblocks),
+           "workload": "%d bp random reference, %d reads of 150 bp (the mates of %d pairs mapped as single reads), ~1%% subs, 1-3 bp indel in ~50%% of reads, Q30" % (genome_len, n, pairs),
            "reads": n, "ms": med, "reads_per_s": n / (med / 1e3), "launches_per_pass": int(launches),
            "stage_ms": {k: float(np.median(v)) for k, v in t.items()},
            "slow_alignments": int(na.value), "reads_slow_aligned": float(run_flags[0].float().mean().item()),
@@ -172,8 +192,9 @@ def main():
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaffolds", type=int, default=1)
     a = ap.parse_args()
-    print(json.dumps(run(a.pairs, a.genome, a.reps, cpu=not a.no_cpu)))
+    print(json.dumps(run(a.pairs, a.genome, a.reps, cpu=not a.no_cpu, scaffolds=a.scaffolds)))
 
 
 if __name__ == "__main__":
