@@ -74,7 +74,7 @@ extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_block
                                  unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, int phases, int* mid, int midStride,
                                  cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
-extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream);
+extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream, int max_rows, int max_cols);
 extern "C" int bbm_msa_warps_per_block();
 extern "C" int bbm_msa_num_wclass();
 extern "C" long long bbm_generic_scratch_ints(int rows, int cols);
@@ -120,6 +120,7 @@ struct bbm_ctx {
     int bandwidth = 0; float ratio = 0.f;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t gstream = nullptr; cudaEvent_t gev0 = nullptr, gev1 = nullptr;   // side stream for the row-sequential kernel (a few long alignments: pure latency)
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
     long long strip_min_tasks = 8192;
@@ -171,6 +172,9 @@ extern "C" int bbm_init(int device, bbm_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->gev0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->gev1, cudaEventDisableTiming));
     if (c->counters.ensure(256 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
     {   // strip-kernel scratch budget: a third of what is free now, at most 32 GB (B200: 180 GB of HBM3e)
         size_t freeB = 0, totalB = 0;
@@ -191,6 +195,9 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->gev0) cudaEventDestroy(c->gev0);
+    if (c->gev1) cudaEventDestroy(c->gev1);
+    if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -285,6 +292,21 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     e = bbm_launch_msa_scatter(&P, (const unsigned char*)c->cls.p, cb, (int*)c->lists.p, (int*)c->nlist.p, st);
     if (e) return fail(BBM_E_CUDA, "msa_scatter_kernel launch", (cudaError_t)e);
     c->launches++;
+    const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
+    long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
+    if (chunk < 1) chunk = 1;
+    auto run_generic = [&](const int* list, long long n, cudaStream_t gs) -> int {
+        if (n <= 0) return BBM_OK;
+        const long long ch = chunk > n ? n : chunk;
+        if (c->gscratch.ensure((size_t)ch * (size_t)gstride * 4)) return fail(BBM_E_CUDA, "cudaMalloc generic scratch");
+        for (long long done = 0; done < n; done += ch) {
+            const int m = (int)((n - done) < ch ? (n - done) : ch);
+            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, gs, max_rows, max_cols);
+            if (e2) return fail(BBM_E_CUDA, "msa_generic_kernel launch", (cudaError_t)e2);
+            c->launches++;
+        }
+        return BBM_OK;
+    };
     if (nacc > 0) {
         int blocks = narrowBlocks;
         const long long need = ((long long)nacc + bbm_msa_narrow_threads() - 1) / bbm_msa_narrow_threads();
@@ -345,28 +367,13 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
             CK(cudaMemsetAsync(cb + 220, 0, 16, st));
         }
     }
-    const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
-    long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
-    if (chunk < 1) chunk = 1;
-    auto run_generic = [&](const int* list, long long n) -> int {
-        if (n <= 0) return BBM_OK;
-        const long long ch = chunk > n ? n : chunk;
-        if (c->gscratch.ensure((size_t)ch * (size_t)gstride * 4)) return fail(BBM_E_CUDA, "cudaMalloc generic scratch");
-        for (long long done = 0; done < n; done += ch) {
-            const int m = (int)((n - done) < ch ? (n - done) : ch);
-            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, st);
-            if (e2) return fail(BBM_E_CUDA, "msa_generic_kernel launch", (cudaError_t)e2);
-            c->launches++;
-        }
-        return BBM_OK;
-    };
-    int rc = run_generic((const int*)c->lists.p + base[nw], h[nw]);       // shapes outside the tiled kernels
+    int rc = run_generic((const int*)c->lists.p + base[nw], h[nw], st);       // shapes outside the tiled kernels
     if (rc) return rc;
     if (c->bandwidth > 0 || c->ratio > 0.f) {
         unsigned int nover = 0;
         CK(cudaMemcpyAsync(&nover, cb + 48, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        rc = run_generic((const int*)c->overflow.p, nover);                   // banded right-edge misses
+        rc = run_generic((const int*)c->overflow.p, nover, st);                   // banded right-edge misses
         if (rc) return rc;
         c->band_misses += nover;
     }

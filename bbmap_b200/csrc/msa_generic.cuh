@@ -18,18 +18,23 @@ __host__ __device__ inline long long msa_generic_scratch_ints(int rows, int cols
     return rowbuf + lim + (tbBytes + 3) / 4 + 8;
 }
 
+// `fast` (optional): a buffer of msa_generic_fast_ints(rows, cols) ints for the rolling rows and the two limit vectors — the
+// shared-memory variant of the kernel passes dynamic shared memory here, which takes the ~10 dependent global round trips per cell
+// (one thread, L2 latency) out of the loop; the predecessor codes always live in `scratch`.
+__host__ __device__ inline long long msa_generic_fast_ints(int rows, int cols) { return 2LL * 3 * (cols + 2) + (rows + 2) + (cols + 2); }
+
 __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm_msa_task& task, long long taskId,
-                                 int* scratch, long long scratchInts, bbm_msa_out* out) {
+                                 int* scratch, long long scratchInts, bbm_msa_out* out, int* fast = nullptr) {
     const int rows = T.rows, cols = T.cols;
     const bool limited = T.limited != 0;
     const int8_t* __restrict__ read = P.reads + task.read_off;
     const int8_t* __restrict__ ref = P.refs + task.ref_off + T.a;
     if (msa_generic_scratch_ints(rows, cols) > scratchInts) { out->status = BBM_E_SHAPE; return; }
     const int stride = cols + 2;
-    int* rowbuf = scratch;                           // [2][3][stride]
+    int* rowbuf = fast ? fast : scratch;             // [2][3][stride]
     int* vl = rowbuf + 2 * 3 * stride;               // [rows+2]
     int* hl = vl + rows + 2;                         // [cols+2]
-    unsigned char* tb = reinterpret_cast<unsigned char*>(hl + cols + 2);   // [(rows+1)*(cols+1)]
+    unsigned char* tb = reinterpret_cast<unsigned char*>(scratch + 2 * 3 * stride + (rows + 2) + (cols + 2));   // [(rows+1)*(cols+1)]
     const int tbStride = cols + 1;
 
     const int maxGain = (rows - 1) * P_MATCH2 + P_MATCH;

@@ -69,6 +69,21 @@ __global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int*
     msa_generic_task(P, T, task, id, gscratch + (long long)i * gstride, gstride, P.outs + id);
 }
 
+// One alignment per block, rolling rows and limit vectors in dynamic shared memory.  The fill is a single dependent chain (the
+// reference's own row/column order), so one thread runs it; what this variant buys is latency: ~10 dependent accesses per cell hit
+// shared memory instead of L2 (measured on scoreSlow's wide windows: 41.6 ms -> see DESIGN.md §4 for the current figure).
+__global__ void __launch_bounds__(32) msa_generic_smem_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride, int smemInts) {
+    extern __shared__ int fastbuf[];
+    const int i = blockIdx.x;
+    if (i >= nlist || threadIdx.x != 0) return;
+    const int id = list[i];
+    const bbm_msa_task task = P.tasks[id];
+    TaskCtx T;
+    if (!resolve_task(task, P.bandwidth, P.ratio, T)) return;
+    const bool fits = msa_generic_fast_ints(T.rows, T.cols) <= smemInts;
+    msa_generic_task(P, T, task, id, gscratch + (long long)i * gstride, gstride, P.outs + id, fits ? fastbuf : nullptr);
+}
+
 }  // namespace bbm
 
 using namespace bbm;
@@ -90,7 +105,18 @@ extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n
 }
 extern "C" int bbm_msa_narrow_threads() { return NARROW_THREADS; }
 extern "C" int bbm_msa_narrow_buckets() { return NARROW_BUCKETS; }
-extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream) {
+extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream,
+                                      int max_rows, int max_cols) {
+    // few, long alignments (the usual case: a handful of wide windows per batch): one per block with its rows in shared memory;
+    // many alignments: the thread-per-alignment form keeps more of them in flight
+    const long long fastInts = msa_generic_fast_ints(max_rows, max_cols);
+    const size_t smem = (size_t)fastInts * 4;
+    if (nlist <= 4096 && smem <= 200 * 1024) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(msa_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        msa_generic_smem_kernel<<<nlist, 32, smem, stream>>>(*P, list, nlist, gscratch, gstride, (int)fastInts);
+        return (int)cudaGetLastError();
+    }
     const int threads = 64;
     msa_generic_kernel<<<(nlist + threads - 1) / threads, threads, 0, stream>>>(*P, list, nlist, gscratch, gstride);
     return (int)cudaGetLastError();
