@@ -24,7 +24,7 @@ __host__ __device__ inline long long msa_generic_scratch_ints(int rows, int cols
 __host__ __device__ inline long long msa_generic_fast_ints(int rows, int cols) { return 2LL * 3 * (cols + 2) + (rows + 2) + (cols + 2); }
 
 __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm_msa_task& task, long long taskId,
-                                 int* scratch, long long scratchInts, bbm_msa_out* out, int* fast = nullptr) {
+                                 int* scratch, long long scratchInts, bbm_msa_out* out, int* fast = nullptr, int lane = -1) {
     const int rows = T.rows, cols = T.cols;
     const bool limited = T.limited != 0;
     const int8_t* __restrict__ read = P.reads + task.read_off;
@@ -42,8 +42,14 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
     const int floor_ = limited ? minScore_off - maxGain : 0;
     const int subfloor = limited ? floor_ - 5 * P_MATCH2 : 0 - 2 * maxGain;
     const int hb = T.halfband;
+    // lane >= 0: called by all 32 lanes of a warp that share `fast`.  Un-banded limited fills are then evaluated 32 columns at a time
+    // (MS and INS of a row only depend on the previous row; DEL is a left-to-right chain resolved lane by lane with shuffles); every
+    // other case runs on lane 0 exactly as in the single-thread form.
+    const bool warpFill = lane >= 0 && fast != nullptr && limited && hb < 1 && P.dump == nullptr;
+    if (lane > 0 && !warpFill) return;
+    const bool lead = lane <= 0;
 
-    if (limited) {
+    if (limited && lead) {
         vl[rows] = minScore_off;
         bool pd = false;
         for (int i = rows - 1; i >= 0; --i) {
@@ -61,12 +67,152 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
         }
     }
     // row 0: all zero
-    for (int s = 0; s < 3; ++s) for (int c = 0; c <= cols + 1; ++c) rowbuf[s * stride + c] = 0;
+    if (warpFill) { for (int i = lane; i < 3 * stride; i += 32) rowbuf[i] = 0; __syncwarp(); }
+    else for (int s = 0; s < 3; ++s) for (int c = 0; c <= cols + 1; ++c) rowbuf[s * stride + c] = 0;
 
     int minGood = 1, maxGood = cols;
     long long iters = 0;
     bool broke = false;
     int lastRowLo = 1, lastRowHi = 0;       // visited interval of the final row (limited)
+    if (warpFill) {
+        constexpr unsigned WFULL = 0xffffffffu;
+        for (int row = 1; row <= rows; ++row) {
+            int* up = rowbuf + ((row - 1) & 1) * 3 * stride;
+            int* cur = rowbuf + (row & 1) * 3 * stride;
+            const int *uM = up, *uD = up + stride, *uI = up + 2 * stride;
+            int *cM = cur, *cD = cur + stride, *cI = cur + 2 * stride;
+            const int col0 = ins_score_offset(row);
+            const int colStart = minGood, colStop = maxGood;
+            minGood = -1; maxGood = -2;
+            if (colStart < 0 || colStop < colStart) { broke = true; break; }
+            __syncwarp();
+            if (lane == 0) {
+                cM[0] = col0; cD[0] = col0; cI[0] = col0;
+                if (colStart > 1) { cM[colStart - 1] = subfloor; cD[colStart - 1] = subfloor; cI[colStart - 1] = subfloor; }
+            }
+            __syncwarp();
+            const int vlimit = vl[row];
+            const int call1 = read[row - 1], call0 = row < 2 ? '?' : read[row - 2];
+            const bool delBar = (row < 3) || (row > rows - 3);
+            // the reference overwrites (row-1, col+1) with subfloor whenever it walks past colStop (jni/...JNI.c:662-667): beyond colStop the
+            // previous row reads as subfloor (row 1 sits on the all-zero row 0 and colStop == cols there)
+            const bool pastIsSub = row > 1;
+            int carryM = cM[colStart - 1], carryD = cD[colStart - 1];
+            int rowHi = colStart - 1;
+            bool stop = false;
+            for (int c0 = colStart; c0 <= cols && !stop; c0 += 32) {
+                const int col = c0 + lane;
+                const bool valid = col <= cols;
+                const int nIn = min(32, cols - c0 + 1);
+                int msv = subfloor, insv = subfloor, delv = subfloor;
+                unsigned code = 0; bool good = false;
+                int limit = 0, delNeeded = 0, insNeeded = 0, insPen = 0, r1 = 0; bool gap = false;
+                if (valid) {
+                    r1 = ref[col - 1];
+                    const int r0 = col < 2 ? '!' : ref[col - 2];
+                    gap = (r1 == '-');
+                    const bool match = (call1 == r1 && r1 != 'N'), prevMatch = (call0 == r0 && r0 != 'N');
+                    limit = max(vlimit, hl[col]);
+                    const int limit3 = max(floor_, match ? limit - P_MATCH2 : limit - P_SUB3);
+                    delNeeded = max(0, row - col - 1);
+                    insNeeded = max(0, (rows - row) - (cols - col) - 1);
+                    const int delPen = del_score_offset(delNeeded); insPen = ins_score_offset(insNeeded);
+                    const bool dSub = pastIsSub && (col - 1) > colStop, uSub = pastIsSub && col > colStop;
+                    {   // MS
+                        const int dm = dSub ? subfloor : uM[col - 1], dd = dSub ? subfloor : uD[col - 1], di = dSub ? subfloor : uI[col - 1];
+                        const int sM = dm & SMASK, sD = dd & SMASK, sI = di & SMASK, streak = dm & TMASK;
+                        if (gap || (sM <= limit3 && sD <= limit3 && sI <= limit3)) msv = subfloor;
+                        else {
+                            int a_, o;
+                            if (match) { a_ = sM + (prevMatch ? P_MATCH2 : P_MATCH); o = P_MATCH; }
+                            else {
+                                a_ = sM + ((r1 != 'N' && call1 != 'N') ? (prevMatch ? (streak <= 1 ? P_SUBR : P_SUB)
+                                           : (streak == 0 ? P_SUB : (streak < 5 ? P_SUB2 : P_SUB3))) : 0);
+                                o = P_SUB;
+                            }
+                            const int b_ = sD + o, c_ = sI + o;
+                            int score, time;
+                            if (a_ >= b_ && a_ >= c_) { score = a_; time = (match == prevMatch) ? streak + 1 : 1; }
+                            else if (b_ >= c_) { score = b_; time = 1; }
+                            else { score = c_; time = 1; }
+                            const int lim2 = delNeeded > 0 ? limit - delPen : (insNeeded > 0 ? limit - insPen : limit);
+                            if (score >= lim2) good = true; else score = subfloor;
+                            if (time > MAX_TIME) time = TIME_WRAP;
+                            msv = score | time;
+                            code |= (time > 1) ? 0u : ((sM >= sD && sM >= sI) ? 0u : (sD >= sI ? 1u : 2u));
+                        }
+                    }
+                    {   // INS
+                        const int um = uSub ? subfloor : uM[col], ui = uSub ? subfloor : uI[col];
+                        const int sM = um & SMASK, sI = ui & SMASK, streak = ui & TMASK;
+                        if (gap || (sM <= limit && sI <= limit) || (row < 2 && col > 1) || (row > rows - 2 && col < cols - 1)) insv = subfloor;
+                        else {
+                            const int a_ = sM + P_INS;
+                            const int b_ = sI + (streak == 0 ? P_INS : (streak < LIM3 ? P_INS2 : (streak < LIM4 ? P_INS3 : P_INS4)));
+                            int score, time;
+                            if (a_ >= b_) { score = a_; time = 1; } else { score = b_; time = streak + 1; }
+                            const int lim2 = delNeeded > 0 ? limit - delPen
+                                           : (insNeeded > 0 ? limit - ins_score_offset(time + insNeeded) + ins_score_offset(time) : limit);
+                            if (score >= lim2) good = true; else score = subfloor;
+                            if (time > MAX_TIME) time = TIME_WRAP;
+                            insv = score | time;
+                            code |= ((time > 1) ? 1u : (sM >= sI ? 0u : 1u)) << 3;
+                        }
+                    }
+                }
+                // DEL: (row, col) from (row, col-1) — MS of the left neighbour is known, DEL is the chain
+                int msLeft = __shfl_up_sync(WFULL, msv, 1);
+                if (lane == 0) msLeft = carryM;
+                // a DEL cell is subfloor outright when neither predecessor beats its limit; with a dead chain only the lanes whose left MS
+                // could open a deletion need a step, and a skipped lane leaves exactly `subfloor` (time 0) behind, as the reference writes it
+                const unsigned openMask = __ballot_sync(WFULL, valid && !delBar && (msLeft & SMASK) > limit);
+                for (int j = 0; j < nIn; ++j) {
+                    if ((carryD & SMASK) == subfloor && !((openMask >> j) & 1u)) {
+                        const unsigned m = openMask & (0xfffffffeu << j);
+                        if (!m) { carryD = subfloor; break; }
+                        j = __ffs(m) - 1;
+                        carryD = subfloor;
+                    }
+                    if (lane == j) {
+                        const int sM = msLeft & SMASK, sD = carryD & SMASK, streak = carryD & TMASK;
+                        if ((sM <= limit && sD <= limit) || delBar) delv = subfloor;
+                        else {
+                            int a_ = sM + P_DEL;
+                            int b_ = sD + (streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
+                                           (((streak & 3) == 0) ? P_DEL5 : 0)))));
+                            if (r1 == 'N') { a_ += P_DEL_REF_N; b_ += P_DEL_REF_N; } else if (gap) { a_ += P_GAP; b_ += P_GAP; }
+                            int score, time;
+                            if (a_ >= b_) { score = a_; time = 1; } else { score = b_; time = streak + 1; }
+                            const int lim2 = insNeeded > 0 ? limit - insPen
+                                           : (delNeeded > 0 ? limit - del_score_offset(time + delNeeded) + del_score_offset(time) : limit);
+                            if (score >= lim2) good = true; else score = subfloor;
+                            if (time > MAX_TIME) time = TIME_WRAP;
+                            delv = score | time;
+                            code |= ((time > 1) ? 1u : (sM >= sD ? 0u : 1u)) << 2;
+                        }
+                    }
+                    carryD = __shfl_sync(WFULL, delv, j);
+                }
+                carryM = __shfl_sync(WFULL, msv, 31);
+                // the reference leaves the row at the first cell past colStop that is not good (the cell itself is evaluated and stored)
+                const unsigned term = __ballot_sync(WFULL, valid && col > colStop && !good);
+                int lastLane = nIn - 1;
+                if (term) { lastLane = __ffs(term) - 1; stop = true; }
+                const bool visited = valid && lane <= lastLane;
+                if (visited) {
+                    cM[col] = msv; cD[col] = delv; cI[col] = insv;
+                    tb[(long long)row * tbStride + col] = (unsigned char)code;
+                }
+                const unsigned gm = __ballot_sync(WFULL, visited && good);
+                if (gm) { if (minGood < 0) minGood = c0 + __ffs(gm) - 1; maxGood = c0 + 31 - __clz(gm); }
+                iters += lastLane + 1;
+                rowHi = c0 + lastLane;
+            }
+            if (row == rows) { lastRowLo = colStart; lastRowHi = rowHi; }
+        }
+        __syncwarp();
+        if (lane != 0) return;
+    } else
     for (int row = 1; row <= rows; ++row) {
         int* up = rowbuf + ((row - 1) & 1) * 3 * stride;
         int* cur = rowbuf + (row & 1) * 3 * stride;

@@ -69,19 +69,19 @@ __global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int*
     msa_generic_task(P, T, task, id, gscratch + (long long)i * gstride, gstride, P.outs + id);
 }
 
-// One alignment per block, rolling rows and limit vectors in dynamic shared memory.  The fill is a single dependent chain (the
-// reference's own row/column order), so one thread runs it; what this variant buys is latency: ~10 dependent accesses per cell hit
-// shared memory instead of L2 (measured on scoreSlow's wide windows: 41.6 ms -> see DESIGN.md §4 for the current figure).
+// One alignment per block (one warp), rolling rows and limit vectors in dynamic shared memory.  Un-banded limited fills — the wide
+// windows scoreSlow sends — are evaluated 32 columns at a time (msa_generic.cuh); anything else runs on lane 0 in the reference's own
+// order, where shared memory still takes ~10 dependent L2 round trips per cell out of the chain.
 __global__ void __launch_bounds__(32) msa_generic_smem_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride, int smemInts) {
     extern __shared__ int fastbuf[];
     const int i = blockIdx.x;
-    if (i >= nlist || threadIdx.x != 0) return;
+    if (i >= nlist) return;
     const int id = list[i];
     const bbm_msa_task task = P.tasks[id];
     TaskCtx T;
     if (!resolve_task(task, P.bandwidth, P.ratio, T)) return;
     const bool fits = msa_generic_fast_ints(T.rows, T.cols) <= smemInts;
-    msa_generic_task(P, T, task, id, gscratch + (long long)i * gstride, gstride, P.outs + id, fits ? fastbuf : nullptr);
+    msa_generic_task(P, T, task, id, gscratch + (long long)i * gstride, gstride, P.outs + id, fits ? fastbuf : nullptr, (int)threadIdx.x);
 }
 
 }  // namespace bbm
