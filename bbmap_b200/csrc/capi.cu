@@ -74,7 +74,7 @@ extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_block
                                  unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, int phases, int* mid, int midStride,
                                  cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
-extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream, int max_rows, int max_cols);
+extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream, int max_rows, int max_cols, const unsigned int* endPtr, unsigned int base);
 extern "C" int bbm_msa_warps_per_block();
 extern "C" int bbm_msa_num_wclass();
 extern "C" long long bbm_generic_scratch_ints(int rows, int cols);
@@ -124,6 +124,7 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
     long long strip_min_tasks = 8192;
+    DevBuf slowBuf[4];                         // scoreSlow rounds: per-read state, packed requests, their results, counters
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
@@ -190,7 +191,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); for (auto& b : c->d_sam) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); for (auto& b : c->slowBuf) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); for (auto& b : c->d_sam) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -295,13 +296,13 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
     long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
     if (chunk < 1) chunk = 1;
-    auto run_generic = [&](const int* list, long long n, cudaStream_t gs) -> int {
+    auto run_generic = [&](const int* list, long long n, cudaStream_t gs, const unsigned int* endPtr, unsigned int lbase) -> int {
         if (n <= 0) return BBM_OK;
         const long long ch = chunk > n ? n : chunk;
         if (c->gscratch.ensure((size_t)ch * (size_t)gstride * 4)) return fail(BBM_E_CUDA, "cudaMalloc generic scratch");
         for (long long done = 0; done < n; done += ch) {
             const int m = (int)((n - done) < ch ? (n - done) : ch);
-            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, gs, max_rows, max_cols);
+            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, gs, max_rows, max_cols, endPtr, lbase + (unsigned int)done);
             if (e2) return fail(BBM_E_CUDA, "msa_generic_kernel launch", (cudaError_t)e2);
             c->launches++;
         }
@@ -314,6 +315,18 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
         e = bbm_launch_msa_narrow(&P, (const int*)c->nlist.p, (int)nacc, cb, (unsigned long long*)c->nscratch.p, words, (int*)c->lists.p, blocks, useStrip, st);
         if (e) return fail(BBM_E_CUDA, "msa_narrow_kernel launch", (cudaError_t)e);
         c->launches++;
+    }
+    // shapes outside the tiled kernels (windows wider than 512 columns, reads longer than 606): a handful of long fills, one warp each.  Their
+    // list is complete once the narrow kernel has handed its failures over, so they start here, on a side stream, beside the tiled and strip
+    // kernels of this batch; the main stream joins them before anything reads the results.
+    bool genericAside = false;
+    if (h[nw] > 0 && d_dump == nullptr) {
+        CK(cudaEventRecord(c->gev0, st));
+        CK(cudaStreamWaitEvent(c->gstream, c->gev0, 0));
+        int rcg = run_generic((const int*)c->lists.p + base[nw], h[nw], c->gstream, cb + 16 + nw, base[nw]);
+        if (rcg) return rcg;
+        CK(cudaEventRecord(c->gev1, c->gstream));
+        genericAside = true;
     }
     typedef int (*launch_fn)(const MsaParams*, const int*, int, const unsigned int*, unsigned int, unsigned int*, int, int, cudaStream_t);
     static const launch_fn fns[7] = { bbm_launch_msa_tiled_w4, bbm_launch_msa_tiled_w5, bbm_launch_msa_tiled_w6, bbm_launch_msa_tiled_w8,
@@ -367,13 +380,14 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
             CK(cudaMemsetAsync(cb + 220, 0, 16, st));
         }
     }
-    int rc = run_generic((const int*)c->lists.p + base[nw], h[nw], st);       // shapes outside the tiled kernels
-    if (rc) return rc;
+    int rc = BBM_OK;
+    if (genericAside) CK(cudaStreamWaitEvent(st, c->gev1, 0));
+    else { rc = run_generic((const int*)c->lists.p + base[nw], h[nw], st, cb + 16 + nw, base[nw]); if (rc) return rc; }
     if (c->bandwidth > 0 || c->ratio > 0.f) {
         unsigned int nover = 0;
         CK(cudaMemcpyAsync(&nover, cb + 48, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        rc = run_generic((const int*)c->overflow.p, nover, st);                   // banded right-edge misses
+        rc = run_generic((const int*)c->overflow.p, nover, st, nullptr, 0);                   // banded right-edge misses
         if (rc) return rc;
         c->band_misses += nover;
     }
@@ -1016,7 +1030,7 @@ static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, i
                             const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
                             const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, cudaStream_t st, int64_t* alignments_out, float* ms_out) {
     const int SI = bbm_scoreslow_state_ints();
-    DevBuf state, tasks, outs, counters;
+    DevBuf &state = c->slowBuf[0], &tasks = c->slowBuf[1], &outs = c->slowBuf[2], &counters = c->slowBuf[3];
     if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(16))
         return fail(BBM_E_CUDA, "cudaMalloc scoreSlow scratch");
     int rc = BBM_OK; int64_t aligned = 0;
@@ -1067,7 +1081,6 @@ static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, i
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     } else cudaStreamSynchronize(st);
     if (alignments_out) *alignments_out = aligned;
-    state.release(); tasks.release(); outs.release(); counters.release();
     return rc;
 }
 static int scoreslow_args(const bbm_slow_cfg* cfg, int cap) {

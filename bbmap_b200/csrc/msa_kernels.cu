@@ -59,8 +59,11 @@ __global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsign
     lists[pos] = (int)i;
 }
 
-__global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride) {
+// `endPtr` (optional): device cursor of the class list.  The narrow kernel hands alignments it cannot finish over to their class list on the
+// device, and a narrow candidate that it does finish leaves its reserved slot unused: the true length is cursor - base, never more than nlist.
+__global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride, const unsigned int* endPtr, unsigned int base) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (endPtr) nlist = min(nlist, (int)(*endPtr - base));
     if (i >= nlist) return;
     const int id = list[i];
     const bbm_msa_task task = P.tasks[id];
@@ -72,9 +75,11 @@ __global__ void msa_generic_kernel(MsaParams P, const int* list, int nlist, int*
 // One alignment per block (one warp), rolling rows and limit vectors in dynamic shared memory.  Un-banded limited fills — the wide
 // windows scoreSlow sends — are evaluated 32 columns at a time (msa_generic.cuh); anything else runs on lane 0 in the reference's own
 // order, where shared memory still takes ~10 dependent L2 round trips per cell out of the chain.
-__global__ void __launch_bounds__(32) msa_generic_smem_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride, int smemInts) {
+__global__ void __launch_bounds__(32) msa_generic_smem_kernel(MsaParams P, const int* list, int nlist, int* gscratch, long long gstride, int smemInts,
+                                                              const unsigned int* endPtr, unsigned int base) {
     extern __shared__ int fastbuf[];
     const int i = blockIdx.x;
+    if (endPtr) nlist = min(nlist, (int)(*endPtr - base));
     if (i >= nlist) return;
     const int id = list[i];
     const bbm_msa_task task = P.tasks[id];
@@ -106,7 +111,7 @@ extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n
 extern "C" int bbm_msa_narrow_threads() { return NARROW_THREADS; }
 extern "C" int bbm_msa_narrow_buckets() { return NARROW_BUCKETS; }
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream,
-                                      int max_rows, int max_cols) {
+                                      int max_rows, int max_cols, const unsigned int* endPtr, unsigned int base) {
     // few, long alignments (the usual case: a handful of wide windows per batch): one per block with its rows in shared memory;
     // many alignments: the thread-per-alignment form keeps more of them in flight
     const long long fastInts = msa_generic_fast_ints(max_rows, max_cols);
@@ -114,11 +119,11 @@ extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int n
     if (nlist <= 4096 && smem <= 200 * 1024) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(msa_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-        msa_generic_smem_kernel<<<nlist, 32, smem, stream>>>(*P, list, nlist, gscratch, gstride, (int)fastInts);
+        msa_generic_smem_kernel<<<nlist, 32, smem, stream>>>(*P, list, nlist, gscratch, gstride, (int)fastInts, endPtr, base);
         return (int)cudaGetLastError();
     }
     const int threads = 64;
-    msa_generic_kernel<<<(nlist + threads - 1) / threads, threads, 0, stream>>>(*P, list, nlist, gscratch, gstride);
+    msa_generic_kernel<<<(nlist + threads - 1) / threads, threads, 0, stream>>>(*P, list, nlist, gscratch, gstride, endPtr, base);
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_msa_warps_per_block() { return WARPS_PER_BLOCK; }

@@ -125,6 +125,29 @@ def test_odd_shapes(oracle, msa):
     _compare(oracle, msa, reads, genome, tasks, bw=20)
 
 
+def test_narrow_candidates_of_the_generic_class(oracle, msa):
+    """600-bp reads in 605-column windows are too wide for the tiled kernels (row-sequential class) yet narrow enough for the narrow kernel.
+    The ones it finishes leave their reserved slot in the class list unused: the row-sequential kernel must take the list length from the
+    device cursor, not from the classifier's count — checked with a small batch right after a large one (stale ids beyond the batch)."""
+    genome = wl.random_genome(60000, seed=41).copy()
+    big_reads, big_tasks = wl.make_msa_tasks(genome, 6000, seed=42, flags=wl.TF_SCORE | wl.TF_TRACEBACK)
+    _compare(oracle, msa, big_reads, genome, big_tasks)
+    rng = np.random.Generator(np.random.PCG64(43))
+    reads_l, tasks_l, off = [], [], 0
+    L = 600
+    for k in range(12):
+        pos = int(rng.integers(500, len(genome) - L - 500))
+        r = genome[pos:pos + L].copy()
+        if k % 3 == 1:
+            r[300] = wl.ACGT[(int(np.searchsorted(wl.ACGT, r[300])) + 1) % 4]            # one substitution: still a narrow success
+        if k % 3 == 2:
+            r = np.concatenate([r[:200], genome[pos + 230:pos + 230 + 400]])                # 30-base deletion: the narrow kernel hands it over
+        reads_l.append(r)
+        tasks_l.append((off, 0, L, len(genome), pos - 2, pos + L - 1 + 3, wl.max_quality(L) - (400 if k % 3 != 2 else 3000), wl.TF_SCORE | wl.TF_TRACEBACK))
+        off += L
+    _compare(oracle, msa, np.concatenate(reads_l), genome, np.array(tasks_l, dtype=wl.TASK_DTYPE))
+
+
 def test_reference_kind_agrees(oracle, msa):
     """Same comparison against the reference's own C (oracle/_ref), when it was built."""
     if not oracle.has_reference:
