@@ -117,8 +117,8 @@ extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int n
     const long long fastInts = msa_generic_fast_ints(max_rows, max_cols);
     const size_t smem = (size_t)fastInts * 4;
     if (nlist <= 4096 && smem <= 200 * 1024) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(msa_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        // per device, and cheap: set on every launch rather than once per process (one context per GPU may live in the same process)
+        cudaFuncSetAttribute(msa_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         msa_generic_smem_kernel<<<nlist, 32, smem, stream>>>(*P, list, nlist, gscratch, gstride, (int)fastInts, endPtr, base);
         return (int)cudaGetLastError();
     }
