@@ -1021,6 +1021,23 @@ extern "C" int bbm_sitelist_tipdel_dev(bbm_ctx* c, bbm_ss* d_lists, const int32_
     return BBM_OK;
 }
 
+extern "C" int bbm_launch_sitelist_bounds(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int* chrom_max_index,
+                                          const int* scaf_off, const int* scaf_loc, int pad, int sam_out, int expected_len_limit, bbm_read_out* out, cudaStream_t st);
+extern "C" int bbm_sitelist_bounds_dev(bbm_ctx* c, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                       const int32_t* d_chrom_max_index, const int32_t* d_scaf_off, const int32_t* d_scaf_loc, int32_t inter_scaffold_padding,
+                                       int32_t sam_out, int32_t expected_len_limit, bbm_read_out* d_out, void* stream) {
+    if (!c || !d_lists || !d_nss || !d_read_off || !d_chrom_max_index || !d_out) return fail(BBM_E_ARG, "bbm_sitelist_bounds_dev: null pointer");
+    if ((d_scaf_off == nullptr) != (d_scaf_loc == nullptr) || cap < 1 || cap > bbm_sitelist_max_cap() || expected_len_limit < 1) return fail(BBM_E_ARG, "bbm_sitelist_bounds_dev: bad argument");
+    if (nreads <= 0) return BBM_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int e = bbm_launch_sitelist_bounds(d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_chrom_max_index, d_scaf_off, d_scaf_loc, inter_scaffold_padding,
+                                       sam_out, expected_len_limit, d_out, stream ? (cudaStream_t)stream : c->stream);
+    if (e) return fail(BBM_E_CUDA, "sitelist_bounds_kernel launch", (cudaError_t)e);
+    c->launches++;
+    return BBM_OK;
+}
+
 // =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,

@@ -311,6 +311,52 @@ __global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_sea
 }
 
 
+// =====================  removeOutOfBounds (AbstractMapThread.java:2444-2479), quickMap's step right after the index search (:739)  =====================
+__device__ int sl_bsearch_java(const int* a, int n, int key) {       // Arrays.binarySearch
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) { const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1); const int v = a[mid]; if (v < key) lo = mid + 1; else if (v > key) hi = mid - 1; else return mid; }
+    return -(lo + 1);
+}
+__device__ bool sl_is_single_scaffold(const int* loc, int n, int pad, int loc1, int loc2) {      // Data.isSingleScaffold (dna/Data.java:1112-1140)
+    if (n < 2) return true;
+    const int idx = sl_bsearch_java(loc, n, loc1 + pad);
+    const int scaf = idx >= 0 ? idx : imax(0, (-1 - idx) - 1);
+    if (scaf == n - 1) return true;
+    const int lowerBound = loc[scaf] - pad, upperBound = loc[scaf + 1];
+    if (loc2 < lowerBound || loc1 > upperBound) return false;
+    return loc2 < upperBound;
+}
+struct BoundsParams {
+    bbm_ss* lists; int* nss; long long nreads; int cap; const long long* read_off; const int* chrom_max_index;
+    const int* scaf_off; const int* scaf_loc; int pad, sam_out, expected_len_limit; bbm_read_out* out;
+};
+__global__ void __launch_bounds__(128) sitelist_bounds_kernel(BoundsParams P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    bbm_ss* v = P.lists + r * P.cap;
+    const int n = P.nss[r], len = (int)(P.read_off[r + 1] - P.read_off[r]);
+    unsigned long long dead = 0; int flags = 0;
+    for (int i = 0; i < n; i++) {
+        bbm_ss& ss = v[i];
+        bool removed = false;
+        if (ss.start < 0 || ss.stop > P.chrom_max_index[ss.chrom - 1]) removed = true;
+        else if (P.sam_out && P.scaf_off) {
+            const int base = P.scaf_off[ss.chrom - 1], cnt = P.scaf_off[ss.chrom] - base;
+            if (!sl_is_single_scaffold(P.scaf_loc + base, cnt, P.pad, ss.start, ss.stop)) removed = true;
+        }
+        if (removed) { dead |= 1ull << i; continue; }
+        if (ss.ngaps > 0) {
+            int total = ss.stop - ss.start + 1;                             // GapTools.calcGrefLen / calcNumGapSymbols (GAPBUFFER2 = GAPLEN = 128)
+            for (int g = 2; g < ss.ngaps; g += 2) total -= imax(0, (ss.gaps[g] - ss.gaps[g - 1] - 128) / 128) * 127;
+            if (total >= P.expected_len_limit) flags |= 8;                  // would need setStop + GapTools.fixGaps
+        } else if (ss.stop - ss.start + 1 >= P.expected_len_limit) ss.stop = ss.start + imin(len + 40, P.expected_len_limit);
+    }
+    const int n2 = compact(v, n, dead);
+    P.nss[r] = n2;
+    bbm_read_out o; o.near_perfect = 0; o.flags = flags; o.clearzone = 0; o.best_sites = n - n2;
+    P.out[r] = o;
+}
+
 // =====================  findTipDeletions(Read, ...) (AbstractMapThread.java:1073-1104)  =====================
 // Scalar forms of findTipDeletionsRight/Left (:2178-2294; the warp-per-task forms live in rescue.cu): here the unit is the read, the
 // scans are short (<= 100 starts x 8 bases) and most sites stop after the 8-base tip check.
@@ -569,5 +615,14 @@ extern "C" int bbm_launch_sitelist_tipdel(bbm_ss* lists, const int* nss, long lo
     P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP; P.basesM = basesM; P.quality = quality;
     P.refs = refs; P.chrom_off = chrom_off; P.chrom_min_index = chrom_min_index; P.tc = *tc; P.out = out;
     bbm::sitelist_tipdel_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bbm_launch_sitelist_bounds(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int* chrom_max_index,
+                                          const int* scaf_off, const int* scaf_loc, int pad, int sam_out, int expected_len_limit, bbm_read_out* out, cudaStream_t st) {
+    bbm::BoundsParams P;
+    P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.chrom_max_index = chrom_max_index; P.scaf_off = scaf_off;
+    P.scaf_loc = scaf_loc; P.pad = pad; P.sam_out = sam_out; P.expected_len_limit = expected_len_limit; P.out = out;
+    bbm::sitelist_bounds_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
     return (int)cudaGetLastError();
 }

@@ -117,3 +117,24 @@ def findTipDeletions(ctx, lists, nss, read_off, basesP, basesM, quality, d_ref, 
     torch.cuda.synchronize()
     return (np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(),
             np.frombuffer(d_out.cpu().numpy().tobytes(), READ_OUT_DTYPE)[:n].copy())
+
+
+def removeOutOfBounds(ctx, lists, nss, read_off, chrom_max_index, scaf=None, inter_scaffold_padding=300, sam_out=1, expected_len_limit=2522, device=0):
+    """AbstractMapThread.removeOutOfBounds on every list (staged through torch tensors).  scaf = (scaf_off, scaf_loc, scaf_len) as for
+    bbmap_b200.sam.sam_batch, or None.  Returns (lists, nss, READ_OUT_DTYPE[n])."""
+    import torch
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: removeOutOfBounds has no CPU fallback")
+    lists = np.ascontiguousarray(lists, SS_DTYPE); n, cap = lists.shape
+    dev = torch.device("cuda", device)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dt)).view(np.uint8).reshape(-1).copy()).to(dev)
+    q = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    d_l = torch.from_numpy(lists.view(np.uint8).reshape(-1).copy()).to(dev); d_n = up(nss, np.int32); d_o = up(read_off, np.int64); d_m = up(chrom_max_index, np.int32)
+    d_so = None if scaf is None else up(scaf[0], np.int32); d_sl = None if scaf is None else up(scaf[1], np.int32)
+    d_out = torch.zeros(max(n, 1) * READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    _lib.check(L.bbm_sitelist_bounds_dev(ctx, q(d_l), q(d_n), n, cap, q(d_o), q(d_m), q(d_so), q(d_sl), inter_scaffold_padding, sam_out, expected_len_limit,
+                                         q(d_out), None), "bbm_sitelist_bounds_dev")
+    torch.cuda.synchronize()
+    return (np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(), np.frombuffer(d_n.cpu().numpy().tobytes(), np.int32)[:n].copy(),
+            np.frombuffer(d_out.cpu().numpy().tobytes(), READ_OUT_DTYPE)[:n].copy())

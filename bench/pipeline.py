@@ -1,6 +1,6 @@
 """The device stages of the unpaired mapping loop chained with everything resident in HBM (no host round trip between stages):
 
-    Read.validate -> KeyRing seeds -> BBIndex.find -> SiteScore lists -> trimList -> scoreNoIndels(Read) -> scoreSlow (rounds over the
+    Read.validate -> KeyRing seeds -> BBIndex.find -> SiteScore lists -> removeOutOfBounds -> trimList -> scoreNoIndels(Read) -> scoreSlow (rounds over the
     MultiStateAligner11ts kernels, padding retry included; findTipDeletions before it) -> mergeDuplicateSites / clearzone / removeLowQualitySitesUnpaired
 
 on BASELINE configs[1]-shaped input (E. coli-sized random reference, 2x150 bp reads mapped as single reads, ~1 % substitutions, 1-3 bp
@@ -32,7 +32,7 @@ from bbmap_b200.search import HEAD_DTYPE, SITE_DTYPE  # noqa: E402
 MAXK, MAX_SITES, CAP = 32, 16, 16
 
 
-def cpu_side(R, cb, co, n_cpu=20000):
+def cpu_side(R, cb, co, table, n_cpu=20000):
     """The same chain through the CPU oracle (C restatements, one host thread) on the first n_cpu reads — a reported baseline."""
     from oracle import oracle as orc
     o = orc.get()
@@ -49,6 +49,8 @@ def cpu_side(R, cb, co, n_cpu=20000):
         lists[f] = S[f]
     lists["quick_score"] = S["score"]
     pcfg = sl.policy_cfg()
+    from bbmap_b200.sam import scaffold_table
+    lists, ns, _ = o.sitelist_bounds(lists, ns, off, (np.diff(np.asarray(co, np.int64)) - 1).astype(np.int32), scaffold_table(table, len(co) - 1))
     lists, ns, _ = o.sitelist(sl.SL_TRIM, lists, ns, off, pcfg)
     lists, ns, out = o.sitelist(sl.SL_NOINDEL, lists, ns, off, pcfg, bases, basesM, cb, co)
     runm = (out["near_perfect"] < 1).astype(np.int32)
@@ -106,6 +108,10 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
     d_co = torch.from_numpy(np.ascontiguousarray(co, np.int64)).to(dev)
     d_chroms = C.c_void_p(idx.d_chroms.value)
+    from bbmap_b200.sam import scaffold_table
+    so_, sl_, _sn = scaffold_table(table, len(co) - 1)
+    d_scaf_off = torch.from_numpy(np.ascontiguousarray(so_, np.int32)).to(dev); d_scaf_loc = torch.from_numpy(np.ascontiguousarray(sl_, np.int32)).to(dev)
+    d_maxidx = torch.from_numpy((np.diff(np.asarray(co, np.int64)) - 1).astype(np.int32)).to(dev)       # ChromosomeArray.maxIndex of the packed arrays
     from bbmap_b200.rescue import tipdel_cfg
     scfg = default_cfg(); pcfg = sl.policy_cfg(); wcfg = sl.slow_cfg(); tcfg = tipdel_cfg()
     d_out2 = torch.zeros(n * sl.READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -131,6 +137,8 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
         step("search", lambda: _lib.check(L.bbm_search_batch_dev(h, p(d_bases), p(d_bs), p(d_off), n, p(d_nkeys), p(d_offsets), p(d_ks), MAXK, 0, p(d_heads), p(d_sites),
                                                                  MAX_SITES, 150, None, C.byref(ms)), "search"))
         step("lists", lambda: _lib.check(L.bbm_sitelist_from_search_dev(h, p(d_heads), p(d_sites), n, MAX_SITES, p(d_lists), p(d_nss), CAP, None), "from_search"))
+        step("removeOutOfBounds", lambda: _lib.check(L.bbm_sitelist_bounds_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_maxidx), p(d_scaf_off), p(d_scaf_loc), 300, 1,
+                                                                              2522, p(d_out2), None), "bounds"))
         step("trimList", lambda: sitelist(sl.SL_TRIM))
         step("scoreNoIndels", lambda: sitelist(sl.SL_NOINDEL))
 
@@ -176,7 +184,7 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
            "not_chained_yet": "genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
            "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
     if cpu:
-        cs = cpu_side(R, cb, co)
+        cs = cpu_side(R, cb, co, table)
         m = cs["reads"]; cl = cs.pop("lists"); cn = cs.pop("nss"); cf = cs.pop("flags")
         live = np.arange(CAP)[None, :] < cn[:, None]
         same = bool(np.array_equal(cn, nss[:m]) and np.array_equal(cf, out["flags"][:m]) and all(np.array_equal(cl[f][live], lists[:m][f][live]) for f in cl.dtype.names))

@@ -365,6 +365,14 @@ int  bbm_sitelist_batch_host(bbm_ctx* ctx, int32_t op, bbm_ss* lists, int32_t* n
                              const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
                              const bbm_policy_cfg* cfg, bbm_read_out* out);
 
+/* AbstractMapThread.removeOutOfBounds (current/align2/AbstractMapThread.java:2444-2479), quickMap's step right after the index search: sites hanging over
+ * the chromosome array (start < 0 or stop > ChromosomeArray.maxIndex) are removed; with SAM output (sam_out != 0) so are sites that span two scaffolds
+ * (Data.isSingleScaffold; d_scaf_off/d_scaf_loc as in bbm_sam_batch_*, NULL = no scaffold table); over-long ungapped sites are cut to read length + 40.
+ * d_out[r].best_sites = sites removed; flags bit3 = an over-long gapped site was left alone (needs GapTools.fixGaps). */
+int  bbm_sitelist_bounds_dev(bbm_ctx* ctx, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                             const int32_t* d_chrom_max_index, const int32_t* d_scaf_off, const int32_t* d_scaf_loc, int32_t inter_scaffold_padding,
+                             int32_t sam_out, int32_t expected_len_limit, bbm_read_out* d_out, void* stream);
+
 /* AbstractMapThread.findTipDeletions(Read r, basesP, basesM, maxSwScore, maxImperfectScore) (current/align2/AbstractMapThread.java:1073-1104) on
  * every read's list: quality gate (d_quality NULL = FASTA), findTipDeletions per eligible site, and for changed sites the rescoring with
  * scoreNoIndels and the perfect/semiperfect update.  d_out[r].best_sites = sites changed; flags bit3 = a gapped site was skipped

@@ -280,6 +280,19 @@ class Oracle:
                                      None if mi is None else _p(mi), _p(cfg), _p(out))
         return lists, out
 
+    def sitelist_bounds(self, lists, nss, read_off, chrom_max_index, scaf=None, inter_scaffold_padding=300, sam_out=1, expected_len_limit=2522):
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+        n, cap = lists.shape
+        rl = np.ascontiguousarray(np.diff(np.ascontiguousarray(read_off, np.int64)), np.int32)
+        mi = np.ascontiguousarray(chrom_max_index, np.int32)
+        so = None if scaf is None else np.ascontiguousarray(scaf[0], np.int32); sl_ = None if scaf is None else np.ascontiguousarray(scaf[1], np.int32)
+        out = np.zeros(n, READ_OUT_DTYPE)
+        self.lib.orc_sitelist_bounds.restype = None
+        self.lib.orc_sitelist_bounds(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(mi), None if so is None else _p(so), None if sl_ is None else _p(sl_),
+                                     C.c_int32(inter_scaffold_padding), C.c_int32(sam_out), C.c_int32(expected_len_limit), _p(out))
+        return lists, nss, out
+
     def score_slow(self, lists, nss, read_off, basesP, basesM, refs, chrom_off, run, cfg):
         from bbmap_b200.sitelist import SS_DTYPE
         lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)

@@ -355,3 +355,48 @@ void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int3
         }
     }
 }
+
+/* AbstractMapThread.removeOutOfBounds(r, ..., SAM_OUT, EXPECTED_LEN_LIMIT) (current/align2/AbstractMapThread.java:2444-2479), called by quickMap right
+ * after the index search (:739): sites hanging over the chromosome array go, with SAM output so do sites that span two scaffolds
+ * (Data.isSingleScaffold, current/dna/Data.java:1112-1140), and over-long sites are cut to read length + 40.  scaf_off == NULL: no scaffold table
+ * (Data.scaffoldLocs == null).  A gapped site that needs cutting would go through fixGaps: left alone and flagged (flags bit 3). */
+static int bsearch_java(const int32_t* a, int n, int key) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) { const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1); const int v = a[mid]; if (v < key) lo = mid + 1; else if (v > key) hi = mid - 1; else return mid; }
+    return -(lo + 1);
+}
+static int is_single_scaffold(const int32_t* loc, int n, int pad, int loc1, int loc2) {
+    if (n < 2) return 1;
+    const int idx = bsearch_java(loc, n, loc1 + pad);
+    const int scaf = idx >= 0 ? idx : imax(0, (-1 - idx) - 1);
+    if (scaf == n - 1) return 1;
+    const int lowerBound = loc[scaf] - pad, upperBound = loc[scaf + 1];
+    if (loc2 < lowerBound || loc1 > upperBound) return 0;
+    return loc2 < upperBound;
+}
+void orc_sitelist_bounds(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const int32_t* chrom_max_index,
+                         const int32_t* scaf_off, const int32_t* scaf_loc, int32_t inter_scaffold_padding, int32_t sam_out, int32_t expected_len_limit,
+                         orc_read_out* out)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; int n = nss[r];
+        const int initial = n; int flags = 0;
+        for (int i = 0; i < n; i++) {
+            orc_ss* ss = &v[i];
+            int removed = 0;
+            if (ss->start < 0 || ss->stop > chrom_max_index[ss->chrom - 1]) removed = 1;
+            else if (sam_out && scaf_off) {
+                const int base = scaf_off[ss->chrom - 1], cnt = scaf_off[ss->chrom] - base;
+                if (!is_single_scaffold(scaf_loc + base, cnt, inter_scaffold_padding, ss->start, ss->stop)) removed = 1;
+            }
+            if (removed) { for (int k = i; k + 1 < n; k++) v[k] = v[k + 1]; n--; i--; continue; }
+            if (ss->ngaps > 0) {
+                int total = ss->stop - ss->start + 1;                       /* GapTools.calcGrefLen */
+                for (int g = 2; g < ss->ngaps; g += 2) { const int gap = ss->gaps[g] - ss->gaps[g - 1] - 128; total -= imax(0, gap / 128) * 127;   /* calcNumGapSymbols: GAPBUFFER2 = GAPLEN = 128 (Shared.java:20-23) */ }
+                if (total >= expected_len_limit) flags |= 8;
+            } else if (ss->stop - ss->start + 1 >= expected_len_limit) ss->stop = ss->start + imin(read_len[r] + 40, expected_len_limit);
+        }
+        nss[r] = n;
+        out[r].near_perfect = 0; out[r].flags = flags; out[r].clearzone = 0; out[r].best_sites = initial - n;
+    }
+}

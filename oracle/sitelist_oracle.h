@@ -28,3 +28,6 @@ void orc_sitelist_noindel(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t c
 void orc_sitelist_final(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out);
 void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
                          const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* chrom_min_index, const orc_tipdel_cfg* tc, orc_read_out* out);
+void orc_sitelist_bounds(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const int32_t* chrom_max_index,
+                         const int32_t* scaf_off, const int32_t* scaf_loc, int32_t inter_scaffold_padding, int32_t sam_out, int32_t expected_len_limit,
+                         orc_read_out* out);

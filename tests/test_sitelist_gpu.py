@@ -128,3 +128,31 @@ def test_find_tip_deletions_read_parity(oracle, msa, seed, with_quality):
         live = np.arange(exp.shape[1])[None, :] < nss[:, None]
         assert got[live].tobytes() == exp[live].tobytes()
     assert eo["best_sites"].sum() > 20 and (eo["flags"] & 8).any()
+
+
+@pytest.mark.parametrize("seed,sam_out,with_scaf", [(91, 1, True), (92, 0, True), (93, 1, False)])
+def test_remove_out_of_bounds_parity(oracle, msa, seed, sam_out, with_scaf):
+    rng = np.random.default_rng(seed)
+    n, cap = 4000, 12
+    lists, nss, ro = random_lists(nreads=n, cap=cap, seed=seed)
+    maxidx = np.array([5200, 4900, 5600], np.int32)
+    scaf_loc = [np.array([100, 1800, 3700]), np.array([50]), np.array([0, 900, 1700, 2500, 4000])]
+    scaf = (np.cumsum([0] + [len(x) for x in scaf_loc]).astype(np.int32), np.concatenate(scaf_loc).astype(np.int32), None) if with_scaf else None
+    for r in range(n):                      # sites hanging over the arrays, over-long sites, gapped over-long sites
+        for i in range(nss[r]):
+            u = rng.random()
+            if u < 0.05:
+                lists[r, i]["start"] = -int(rng.integers(1, 50)); lists[r, i]["stop"] = lists[r, i]["start"] + 120
+            elif u < 0.10:
+                lists[r, i]["stop"] = int(maxidx[lists[r, i]["chrom"] - 1]) + int(rng.integers(0, 3))
+            elif u < 0.14:
+                lists[r, i]["stop"] = lists[r, i]["start"] + int(rng.integers(2500, 2600))
+    for cfg_limit in (2522, 180):
+        exp = oracle.sitelist_bounds(lists, nss, ro, maxidx, scaf, sam_out=sam_out, expected_len_limit=cfg_limit)
+        got = sl.removeOutOfBounds(msa.h, lists, nss, ro, maxidx, scaf, sam_out=sam_out, expected_len_limit=cfg_limit)
+        assert np.array_equal(got[1], exp[1])
+        for f in exp[2].dtype.names:
+            assert np.array_equal(got[2][f], exp[2][f]), f
+        live = np.arange(cap)[None, :] < exp[1][:, None]
+        assert got[0][live].tobytes() == exp[0][live].tobytes()
+    assert exp[2]["best_sites"].sum() > 500

@@ -100,3 +100,22 @@ def test_random_lists_invariants(oracle):
     lists, nss, ro = random_lists(nreads=1500, seed=10, after_alignment=True)
     L3, n3, out3 = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
     assert ((out3["flags"] & sl.F_MAPPED) != 0).sum() > 300 and ((out3["flags"] & sl.F_AMBIGUOUS) != 0).sum() > 50 and (n3 == 0).sum() > 100
+
+
+def test_remove_out_of_bounds_by_hand(oracle):
+    """chromosome 1: maxIndex 9999, scaffolds at 1000 (len 3000) and 4300 (len 5000), 300 N between them (Data.interScaffoldPadding)."""
+    L = 100
+    rows = [dict(chrom=1, start=-3, stop=96, score=1),            # hangs over the start: removed
+            dict(chrom=1, start=9950, stop=10049, score=2),       # hangs over maxIndex: removed
+            dict(chrom=1, start=1500, stop=1599, score=3),        # inside scaffold 0
+            dict(chrom=1, start=3950, stop=4349, score=4),        # runs from scaffold 0 into scaffold 1: removed with SAM output
+            dict(chrom=1, start=5000, stop=5000 + 2600, score=5), # over-long: cut to start + read length + 40
+            dict(chrom=1, start=4300, stop=4399, score=6)]        # first base of scaffold 1
+    lists, nss, ro = _mk(rows, L=L, cap=8)
+    scaf = (np.array([0, 2], np.int32), np.array([1000, 4300], np.int32), np.array([3000, 5000], np.int32))
+    L2, n2, out = oracle.sitelist_bounds(lists, nss, ro, [9999], scaf)
+    assert n2[0] == 3 and out["best_sites"][0] == 3
+    assert [(int(s["start"]), int(s["stop"])) for s in L2[0, :3]] == [(1500, 1599), (5000, 5140), (4300, 4399)]
+    # without SAM output the scaffold test is skipped
+    L3, n3, _ = oracle.sitelist_bounds(lists, nss, ro, [9999], scaf, sam_out=0)
+    assert n3[0] == 4 and int(L3[0, 1]["start"]) == 3950
