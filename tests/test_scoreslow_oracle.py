@@ -31,7 +31,12 @@ def test_score_slow_properties(oracle):
     cfg = sl.policy_cfg()
     lists, _, _ = oracle.sitelist(sl.SL_NOINDEL, lists, nss, ro, cfg, P, M, refs, co)
     L2, status, na = oracle.score_slow(lists, nss, ro, P, M, refs, co, run, sl.slow_cfg())
-    assert na > 300 and (status & sl.SLOW_GAPPED).any()
+    assert na > 300 and not (status & sl.SLOW_GAPPED).any()
+    gapped = [(r, i) for r in range(len(nss)) for i in range(nss[r]) if lists[r, i]["ngaps"] > 0 and run[r]]
+    assert len(gapped) > 20
+    for r, i in gapped:                                   # gapped sites go through the gapped reference; their gap array follows start/stop
+        b = L2[r, i]
+        assert b["ngaps"] == 0 or (b["gaps"][0] == b["start"] and b["gaps"][b["ngaps"] - 1] == b["stop"] and b["ngaps"] % 2 == 0)
     improved = moved = 0
     for r in range(len(nss)):
         Lr = int(ro[r + 1] - ro[r]); maxq = 70 + 100 * (Lr - 1)
