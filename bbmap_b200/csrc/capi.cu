@@ -124,7 +124,7 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
     long long strip_min_tasks = 8192;
-    DevBuf slowBuf[4];                         // scoreSlow rounds: per-read state, packed requests, their results, counters
+    DevBuf slowBuf[7];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;
@@ -1041,50 +1041,64 @@ extern "C" int bbm_sitelist_bounds_dev(bbm_ctx* c, bbm_ss* d_lists, int32_t* d_n
 // =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
-                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, int* counters, cudaStream_t st);
+                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, bbm_gapped_task* gtasks, int* gaps,
+                                    const bbm_msa_out* gouts, int* counters, cudaStream_t st);
+static int run_msa_gapped(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_gapped_task* d_gt, const int32_t* d_gaps,
+                          bbm_msa_out* d_outs, int64_t ntasks, int8_t* d_match, const int64_t* d_moff, cudaStream_t st, float* ms_out);
 extern "C" int bbm_scoreslow_state_ints();
 static int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
                             const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
                             const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, cudaStream_t st, int64_t* alignments_out, float* ms_out) {
     const int SI = bbm_scoreslow_state_ints();
     DevBuf &state = c->slowBuf[0], &tasks = c->slowBuf[1], &outs = c->slowBuf[2], &counters = c->slowBuf[3];
-    if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(16))
+    DevBuf &gtasks = c->slowBuf[4], &gaps = c->slowBuf[5], &gouts = c->slowBuf[6];
+    if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(16) ||
+        gtasks.ensure((size_t)nreads * sizeof(bbm_gapped_task)) || gaps.ensure((size_t)nreads * BBM_MAX_GAPS * 4) || gouts.ensure((size_t)nreads * sizeof(bbm_msa_out)))
         return fail(BBM_E_CUDA, "cudaMalloc scoreSlow scratch");
     int rc = BBM_OK; int64_t aligned = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     auto launch = [&](int phase, int k) -> int {
         int e = bbm_launch_scoreslow(phase, k, d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_basesP, d_basesM, d_refs, (const long long*)d_chrom_off,
-                                     d_run, cfg, (int*)state.p, (bbm_msa_task*)tasks.p, (const bbm_msa_out*)outs.p, (int*)counters.p, st);
+                                     d_run, cfg, (int*)state.p, (bbm_msa_task*)tasks.p, (const bbm_msa_out*)outs.p, (bbm_gapped_task*)gtasks.p, (int*)gaps.p,
+                                     (const bbm_msa_out*)gouts.p, (int*)counters.p, st);
         if (e) return fail(BBM_E_CUDA, "scoreslow_kernel launch", (cudaError_t)e);
         c->launches++;
         return BBM_OK;
     };
     auto counts = [&](int* h) -> int {
-        cudaError_t ce = cudaMemcpyAsync(h, counters.p, 8, cudaMemcpyDeviceToHost, st);
+        cudaError_t ce = cudaMemcpyAsync(h, counters.p, 12, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         return ce == cudaSuccess ? BBM_OK : fail(BBM_E_CUDA, "scoreSlow counters", ce);
     };
     const bool trace = getenv("BBM_SLOW_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int k = 0; k < cap && rc == BBM_OK; ++k) {
-        int h[2] = {0, 0};
+        int h[3] = {0, 0, 0};
         const double t0 = now();
-        if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        if (cudaMemsetAsync(counters.p, 0, 12, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
         if ((rc = launch(0, k)) || (rc = counts(h))) break;
-        if (trace) fprintf(stderr, "[scoreSlow] round %d: %d reads active, %d alignments requested (prep %.2f ms)\n", k, h[0], h[1], now() - t0);
+        if (trace) fprintf(stderr, "[scoreSlow] round %d: %d reads active, %d + %d (gapped) alignments requested (prep %.2f ms)\n", k, h[0], h[1], h[2], now() - t0);
         if (h[0] == 0) break;                                   // no read has a k-th site
         if (h[1] > 0) {
             aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
-        if (cudaMemsetAsync(counters.p, 0, 8, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        if (h[2] > 0) {
+            aligned += h[2];
+            if ((rc = run_msa_gapped(c, d_basesP, d_refs, (const bbm_gapped_task*)gtasks.p, (const int32_t*)gaps.p, (bbm_msa_out*)gouts.p, h[2], nullptr, nullptr, st, nullptr))) break;
+        }
+        if (cudaMemsetAsync(counters.p, 0, 12, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
         if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[scoreSlow]   first pass done at %.2f ms\n", now() - t0); }
         if ((rc = launch(1, k)) || (rc = counts(h))) break;
-        if (trace) fprintf(stderr, "[scoreSlow]   %d padding retries\n", h[1]);
+        if (trace) fprintf(stderr, "[scoreSlow]   %d + %d (gapped) padding retries\n", h[1], h[2]);
         if (h[1] > 0) {
             aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
+        }
+        if (h[2] > 0) {
+            aligned += h[2];
+            if ((rc = run_msa_gapped(c, d_basesP, d_refs, (const bbm_gapped_task*)gtasks.p, (const int32_t*)gaps.p, (bbm_msa_out*)gouts.p, h[2], nullptr, nullptr, st, nullptr))) break;
         }
         if ((rc = launch(2, k))) break;
         if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[scoreSlow]   round done at %.2f ms\n", now() - t0); }

@@ -311,6 +311,62 @@ __global__ void __launch_bounds__(128) sitelist_from_search_kernel(const bbm_sea
 }
 
 
+// ---- gap arrays: GapTools.fixGaps and the SiteScore setters that call it ----
+constexpr int SL_MINGAP = 256;                 // Shared.MINGAP = GAPBUFFER2 + GAPLEN (align2/Shared.java:20-24)
+
+// GapTools.fixGaps(a, b, gaps, minGap) + fixGaps2, in place; returns the new number of ints (0 = null)
+__device__ int fix_gaps(int a, int b, int* gaps, int n, int minGap) {
+    if (n == 0) return 0;
+    if (!(gaps[0] <= b && gaps[n - 1] >= a)) return 0;
+    int changed = 0;
+    if (gaps[0] != a) { gaps[0] = a; changed++; }
+    if (gaps[n - 1] != b) { gaps[n - 1] = b; changed++; }
+    for (int i = 0; i < n; i++) { if (gaps[i] < a) { gaps[i] = a; changed++; } else if (gaps[i] > b) { gaps[i] = b; changed++; } }
+    for (int i = 1; i < n; i++) if (gaps[i - 1] > gaps[i]) { gaps[i] = gaps[i - 1]; changed++; }
+    if (changed == 0) return n;
+    gaps[0] = a; gaps[n - 1] = b;
+    int remove = 0;
+    for (int i = 0; i < n; i += 2) {
+        gaps[i] = imin(imax(gaps[i], a), b); gaps[i + 1] = imin(imax(gaps[i + 1], a), b);
+        if (gaps[i] == gaps[i + 1]) remove++;
+    }
+    if (remove == 0) return n;
+    const int m = n / 2; unsigned dead = 0;
+    for (int i = 1; i < m; i++) {
+        if (gaps[2 * i] - gaps[2 * i - 1] <= minGap) {
+            gaps[2 * i] = imin(gaps[2 * i - 2], gaps[2 * i]); gaps[2 * i + 1] = imax(gaps[2 * i - 1], gaps[2 * i + 1]);
+            dead |= 1u << (i - 1);
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < m; i++) if (!((dead >> i) & 1u)) { gaps[2 * k] = gaps[2 * i]; gaps[2 * k + 1] = gaps[2 * i + 1]; k++; }
+    return k < 2 ? 0 : 2 * k;
+}
+__device__ bool check_gaps(const bbm_ss& s) {                                   // SiteScore.CHECKGAPS
+    if (s.ngaps == 0) return true;
+    if (s.ngaps & 1) return false;
+    for (int i = 1; i < s.ngaps; i++) if (s.gaps[i - 1] > s.gaps[i]) return false;
+    return s.gaps[0] == s.start && s.gaps[s.ngaps - 1] == s.stop;
+}
+__device__ void ss_set_limits(bbm_ss& s, int a, int b) {                        // SiteScore.setLimits
+    s.start = a; s.stop = b;
+    if (s.ngaps > 0) { s.gaps[0] = a; s.gaps[s.ngaps - 1] = b; if (!check_gaps(s)) s.ngaps = fix_gaps(a, b, s.gaps, s.ngaps, SL_MINGAP); }
+}
+__device__ void ss_set_stop(bbm_ss& s, int b) {                                 // SiteScore.setStop
+    s.stop = b;
+    if (s.ngaps > 0) { s.gaps[s.ngaps - 1] = b; s.ngaps = fix_gaps(s.start, b, s.gaps, s.ngaps, SL_MINGAP); }
+}
+__device__ int calc_gref_len(const bbm_ss& s) {                                 // GapTools.calcGrefLen (GAPBUFFER2 = GAPLEN = 128)
+    int total = s.stop - s.start + 1;
+    for (int i = 2; i < s.ngaps; i += 2) total -= imax(0, (s.gaps[i] - s.gaps[i - 1] - 128) / 128) * 127;
+    return total;
+}
+
+__device__ void ss_set_start(bbm_ss& s, int a) {                                // SiteScore.setStart (stream/SiteScore.java:933-942)
+    s.start = a;
+    if (s.ngaps > 0) { s.gaps[0] = a; if (s.gaps[0] > s.gaps[1]) s.ngaps = fix_gaps(a, s.stop, s.gaps, s.ngaps, SL_MINGAP); }
+}
+
 // =====================  removeOutOfBounds (AbstractMapThread.java:2444-2479), quickMap's step right after the index search (:739)  =====================
 __device__ int sl_bsearch_java(const int* a, int n, int key) {       // Arrays.binarySearch
     int lo = 0, hi = n - 1;
@@ -345,11 +401,10 @@ __global__ void __launch_bounds__(128) sitelist_bounds_kernel(BoundsParams P) {
             if (!sl_is_single_scaffold(P.scaf_loc + base, cnt, P.pad, ss.start, ss.stop)) removed = true;
         }
         if (removed) { dead |= 1ull << i; continue; }
-        if (ss.ngaps > 0) {
-            int total = ss.stop - ss.start + 1;                             // GapTools.calcGrefLen / calcNumGapSymbols (GAPBUFFER2 = GAPLEN = 128)
-            for (int g = 2; g < ss.ngaps; g += 2) total -= imax(0, (ss.gaps[g] - ss.gaps[g - 1] - 128) / 128) * 127;
-            if (total >= P.expected_len_limit) flags |= 8;                  // would need setStop + GapTools.fixGaps
-        } else if (ss.stop - ss.start + 1 >= P.expected_len_limit) ss.stop = ss.start + imin(len + 40, P.expected_len_limit);
+        if (calc_gref_len(ss) >= P.expected_len_limit) {
+            ss_set_stop(ss, ss.start + imin(len + 40, P.expected_len_limit));
+            if (ss.ngaps > 0) ss.ngaps = fix_gaps(ss.start, ss.stop, ss.gaps, ss.ngaps, SL_MINGAP);      // :2470 calls fixGaps once more
+        }
     }
     const int n2 = compact(v, n, dead);
     P.nss[r] = n2;
@@ -433,7 +488,6 @@ __global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
         for (int j = 0; j < n; j++) {
             bbm_ss ss = v[j];
             if (ss.semiperfect || ss.slow_score >= maxImp) continue;
-            if (ss.ngaps > 0) { o.flags |= 8; continue; }
             const int8_t* bases = (ss.strand == 0 ? P.basesP : P.basesM) + P.read_off[r];
             const int8_t* ref = P.refs + P.chrom_off[ss.chrom - 1];
             const int refLen = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
@@ -446,14 +500,14 @@ __global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
                     if (findRight) {
                         const int x = tip_right(bases, len, ref, refLen, minIndex, ss.stop, maxSearch, TIPLEN);
                         if (x > 0) {
-                            ss.stop += x; changed = true;
+                            ss_set_stop(ss, ss.stop + x); changed = true;
                             maxSearch = imin(maxSearch, P.tc.align_columns - (P.tc.slow_rescue_padding + 8 + imax(len, ss.stop - ss.start)));
                             if (maxSearch < 1) go = false;
                         }
                     }
                     if (go && findLeft) {
                         const int y = tip_left(bases, ref, refLen, minIndex, ss.start, maxSearch, TIPLEN);
-                        if (y > 0) { ss.start -= y; changed = true; }
+                        if (y > 0) { ss_set_start(ss, ss.start - y); changed = true; }
                     }
                 }
             }
@@ -461,7 +515,7 @@ __global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
                 o.best_sites++;
                 ss.has_match = 0;
                 set_slow_score(ss, score_no_indels(bases, len, ref, refLen, ss.start));
-                if (ss.slow_score == maxSw) { ss.stop = ss.start + len - 1; ss.perfect = 1; ss.semiperfect = 1; }
+                if (ss.slow_score == maxSw) { ss_set_stop(ss, ss.start + len - 1); ss.perfect = 1; ss.semiperfect = 1; }
                 else { ss.perfect = 0; ss_set_perfect(ss, bases, len, ref, refLen); }
                 v[j] = ss;
             }
@@ -478,22 +532,44 @@ __global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
 //   SLOW_RETRY  "more padding needed" (:303-326): score array of length 8 -> widen the site by the suggested pads, ask again with
 //               SLOW_ALIGN_PADDING+EXTRA_PADDING;  [second batch, only if some read asked]
 //   SLOW_APPLY  keep the better array, setSlowScore/setLimits, ratchet, perfect/semiperfect flags (:327-385)
-// Default flags only: QUICK_MATCH_STRINGS=false (no traceback / fixXY / clipTipIndels inside scoreSlow).  Sites that carry gaps need the
-// gapped aligner and GapTools.fixGaps in setLimits: they are left as scoreNoIndels scored them and the read is flagged BBM_SLOW_GAPPED.
+// Default flags only: QUICK_MATCH_STRINGS=false (no traceback / fixXY / clipTipIndels inside scoreSlow).  Sites that carry a gap array go to
+// the gapped aligner (bbm_msa_gapped: makeGref on the device) as a second packed request list; SiteScore.setLimits / setStop keep the gap
+// array consistent through GapTools.fixGaps (GapTools.java:26-72,126-175; stream/SiteScore.java:905-914,943-958).
 struct SlowParams {
     int phase, round; bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off;
     const int8_t* basesP; const int8_t* basesM; const int8_t* refs; const long long* chrom_off; const int* run;
-    bbm_slow_cfg cfg; int* state;       // [nreads][16]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status, 15 task slot
-    bbm_msa_task* tasks; const bbm_msa_out* outs; int* counters;   // counters[0] reads active in this round, [1] tasks emitted
+    bbm_slow_cfg cfg; int* state;       // [nreads][20]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status, 15 slot, 16 gapped request
+    bbm_msa_task* tasks; const bbm_msa_out* outs;                  // plain requests, packed
+    bbm_gapped_task* gtasks; int* gaps; const bbm_msa_out* gouts;  // gapped requests, packed; gap arrays at gaps[slot * BBM_MAX_GAPS]
+    int* counters;                                                 // [0] reads active in this round, [1] plain requests, [2] gapped requests
 };
 constexpr int SLOW_PREP = 0, SLOW_RETRY = 1, SLOW_APPLY = 2;
-constexpr int SLOW_STATE = 16;
+constexpr int SLOW_STATE = 20;
+// one fillAndScoreLimited(bases, ss, pad, minscore) request: plain or gapped list, slot remembered in the read's state
+__device__ void slow_request(const SlowParams& P, long long r, int len, const bbm_ss& ss, int pad, int minscore, int* st) {
+    bbm_msa_task task = {};
+    task.read_off = ((ss.strand == 0 ? P.basesP : P.basesM) - P.basesP) + P.read_off[r];
+    task.ref_off = P.chrom_off[ss.chrom - 1]; task.read_len = len;
+    task.ref_len = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
+    task.ref_start = ss.start - pad; task.ref_end = ss.stop + pad;
+    task.min_score = minscore;
+    if (ss.ngaps > 0) {
+        const int slot = atomicAdd(P.counters + 2, 1);
+        task.flags = BBM_TF_SCORE;                                   // the gapped path clamps the window itself (MSA.java:104-105)
+        bbm_gapped_task g; g.t = task; g.gaps_off = slot * BBM_MAX_GAPS; g.ngaps = ss.ngaps;
+        for (int i = 0; i < ss.ngaps; i++) P.gaps[slot * BBM_MAX_GAPS + i] = ss.gaps[i];
+        P.gtasks[slot] = g; st[15] = slot; st[16] = 1;
+    } else {
+        const int slot = atomicAdd(P.counters + 1, 1);
+        task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
+        P.tasks[slot] = task; st[15] = slot; st[16] = 0;
+    }
+}
 
 __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.nreads) return;
     int* st = P.state + r * SLOW_STATE;
-    bbm_msa_task task = {};
     const int k = P.round;
     const bool active = P.run[r] != 0 && k < P.nss[r];
     const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
@@ -511,26 +587,17 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
             if (ss.stop - ss.start != len - 1) { set_slow_score(ss, 0); ss.semiperfect = 0; ss.perfect = 0; }
             const int sw = ss.slow_score;
             if (sw < max_imperfect(len) && !ss.semiperfect) {
-                if (ss.ngaps > 0) st[14] |= BBM_SLOW_GAPPED;
-                else {
-                    const int expectedLen = ss.stop - ss.start + 1;                      // GapTools.calcGrefLen without gaps
-                    if (expectedLen >= cfg.expected_len_limit) ss.stop = ss.start + imin(len + 40, cfg.expected_len_limit);
-                    const int minscore = imax(sw, st[0]);
-                    task.read_off = ((ss.strand == 0 ? P.basesP : P.basesM) - P.basesP) + P.read_off[r];
-                    task.ref_off = P.chrom_off[ss.chrom - 1]; task.read_len = len;
-                    task.ref_len = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
-                    task.ref_start = ss.start - cfg.slow_align_padding; task.ref_end = ss.stop + cfg.slow_align_padding;
-                    task.min_score = minscore; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
-                    st[2] = 1; st[3] = expectedLen; st[4] = minscore;
-                    const int slot = atomicAdd(P.counters + 1, 1);             // requests are packed: the aligner sees only real tasks
-                    st[15] = slot; P.tasks[slot] = task;
-                }
+                const int expectedLen = calc_gref_len(ss);
+                if (expectedLen >= cfg.expected_len_limit) ss_set_stop(ss, ss.start + imin(len + 40, cfg.expected_len_limit));
+                const int minscore = imax(sw, st[0]);
+                st[2] = 1; st[3] = expectedLen; st[4] = minscore;
+                slow_request(P, r, len, ss, cfg.slow_align_padding, minscore, st);
             }
             P.lists[r * P.cap + k] = ss;
         }
     } else if (P.phase == SLOW_RETRY) {
         if (active && st[2] == 1) {
-            const bbm_msa_out o = P.outs[st[15]];
+            const bbm_msa_out o = st[16] ? P.gouts[st[15]] : P.outs[st[15]];
             if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
             const int n = (o.status == 0) ? o.score_len : 0;
             st[5] = n;
@@ -538,16 +605,9 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
             for (int q = 0; q < 8; q++) st[6 + q] = o.score[q];
             if (n > 6 && (o.score[3] + o.score[4] + st[3] < cfg.expected_len_limit)) {
                 bbm_ss ss = P.lists[r * P.cap + k];
-                ss.start -= o.score[6]; ss.stop += o.score[7];                           // setLimits (gaps == null)
-                const int pad = cfg.slow_align_padding + cfg.extra_padding;
-                task.read_off = ((ss.strand == 0 ? P.basesP : P.basesM) - P.basesP) + P.read_off[r];
-                task.ref_off = P.chrom_off[ss.chrom - 1]; task.read_len = len;
-                task.ref_len = (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]);
-                task.ref_start = ss.start - pad; task.ref_end = ss.stop + pad;
-                task.min_score = st[4]; task.flags = BBM_TF_CLAMP | BBM_TF_SCORE;
+                ss_set_limits(ss, ss.start - o.score[6], ss.stop + o.score[7]);
                 st[2] = 2;
-                const int slot = atomicAdd(P.counters + 1, 1);
-                st[15] = slot; P.tasks[slot] = task;
+                slow_request(P, r, len, ss, cfg.slow_align_padding + cfg.extra_padding, st[4], st);
                 P.lists[r * P.cap + k] = ss;
             }
         }
@@ -557,12 +617,12 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
             int n = 0, a0 = 0, a1 = 0, a2 = 0;
             if (st[2] >= 1) { n = st[5]; a0 = st[6]; a1 = st[7]; a2 = st[8]; }
             if (st[2] == 2) {
-                const bbm_msa_out o = P.outs[st[15]];
+                const bbm_msa_out o = st[16] ? P.gouts[st[15]] : P.outs[st[15]];
                 if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
                 const int n2 = (o.status == 0) ? o.score_len : 0;
                 if (!(n2 == 0 || o.score[0] < a0)) { n = n2; a0 = o.score[0]; a1 = o.score[1]; a2 = o.score[2]; }
             }
-            if (n > 0) { set_slow_score(ss, a0); ss.start = a1; ss.stop = a2; }
+            if (n > 0) { set_slow_score(ss, a0); ss_set_limits(ss, a1, a2); }
             ss.score = ss.slow_score;
             st[1] = imax(st[1], ss.slow_score);
             st[0] = imax(st[0], ss.slow_score - cfg.clearzone3);
@@ -598,10 +658,11 @@ extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, con
 
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
-                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, int* counters, cudaStream_t st) {
+                                    const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, bbm_gapped_task* gtasks, int* gaps,
+                                    const bbm_msa_out* gouts, int* counters, cudaStream_t st) {
     bbm::SlowParams P;
     P.phase = phase; P.round = round; P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP;
-    P.basesM = basesM; P.refs = refs; P.chrom_off = chrom_off; P.run = run; P.cfg = *cfg; P.state = state; P.tasks = tasks; P.outs = outs;
+    P.basesM = basesM; P.refs = refs; P.chrom_off = chrom_off; P.run = run; P.cfg = *cfg; P.state = state; P.tasks = tasks; P.outs = outs; P.gtasks = gtasks; P.gaps = gaps; P.gouts = gouts;
     P.counters = counters;
     bbm::scoreslow_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
     return (int)cudaGetLastError();

@@ -385,13 +385,14 @@ int  bbm_sitelist_tipdel_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss
  * Round k slow-aligns the k-th site of every read whose run[r] != 0 (processRead calls scoreSlow when scoreNoIndels found no
  * near-perfect site, :463-465): preamble, MSA.fillAndScoreLimited(bases, ss, SLOW_ALIGN_PADDING, max(slowScore, minMsaLimit)), the
  * "more padding" retry with EXTRA_PADDING, setSlowScore/setLimits, the minMsaLimit ratchet and the perfect/semiperfect flags.  Default
- * flags (QUICK_MATCH_STRINGS=false).  status[r] (may be NULL): BBM_SLOW_* bits. */
+ * flags (QUICK_MATCH_STRINGS=false).  Sites with a gap array are aligned against the gapped reference (bbm_msa_gapped semantics) and keep their
+ * gap array consistent through SiteScore.setLimits/setStop + GapTools.fixGaps.  status[r] (may be NULL): BBM_SLOW_* bits. */
 typedef struct {                /* 32 bytes; defaults: MINIMUM_ALIGNMENT_SCORE_RATIO 0.56, ..._PRE_RESCUE (paired only), CLEARZONE1e 258, CLEARZONE3 800,
                                    SLOW_ALIGN_PADDING 4, EXTRA_PADDING 10, EXPECTED_LEN_LIMIT (3000*17)/20-2*(4+10) = 2522 */
     int32_t paired; float min_ratio, min_ratio_pre_rescue;
     int32_t clearzone1e, clearzone3, slow_align_padding, extra_padding, expected_len_limit;
 } bbm_slow_cfg;
-#define BBM_SLOW_GAPPED         1   /* a site with a gap array was left as scoreNoIndels scored it (gapped fill + GapTools.fixGaps not chained yet) */
+#define BBM_SLOW_GAPPED         1   /* reserved (round 1 left gapped sites unaligned; they now go through the gapped aligner and GapTools.fixGaps) */
 #define BBM_SLOW_ALIGNER_ERROR  2   /* the aligner reported a per-task error (shape outside 601 x 3000) */
 int  bbm_scoreslow_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
                        const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,

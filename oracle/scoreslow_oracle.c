@@ -33,70 +33,6 @@ static void set_perfect(orc_ss* s, const int8_t* bases, int len, const int8_t* r
     s->perfect = (int8_t)perfect; s->semiperfect = (int8_t)semiperfect;
 }
 
-/* GapTools.fixGaps(a, b, gaps, minGap) + fixGaps2 (current/align2/GapTools.java:26-72, 126-175).  Works in place on gaps[0..n); returns the new number of
- * ints, 0 = null. */
-static int fix_gaps(int a, int b, int32_t* gaps, int n, int minGap)
-{
-    if (n == 0) return 0;
-    if (!(gaps[0] <= b && gaps[n - 1] >= a)) return 0;                 /* Tools.overlap(a, b, g0, gN) */
-    int changed = 0;
-    if (gaps[0] != a) { gaps[0] = a; changed++; }
-    if (gaps[n - 1] != b) { gaps[n - 1] = b; changed++; }
-    for (int i = 0; i < n; i++) { if (gaps[i] < a) { gaps[i] = a; changed++; } else if (gaps[i] > b) { gaps[i] = b; changed++; } }
-    for (int i = 1; i < n; i++) if (gaps[i - 1] > gaps[i]) { gaps[i] = gaps[i - 1]; changed++; }
-    if (changed == 0) return n;
-    gaps[0] = a; gaps[n - 1] = b;
-    int remove = 0;
-    for (int i = 0; i < n; i += 2) {
-        gaps[i] = gaps[i] < a ? a : (gaps[i] > b ? b : gaps[i]);
-        gaps[i + 1] = gaps[i + 1] < a ? a : (gaps[i + 1] > b ? b : gaps[i + 1]);
-        if (gaps[i] == gaps[i + 1]) remove++;
-    }
-    if (remove == 0) return n;
-    /* fixGaps2: merge ranges closer than minGap, left to right */
-    int dead[ORC_MAX_GAPS]; const int m = n / 2;
-    for (int i = 0; i < m; i++) dead[i] = 0;
-    for (int i = 1; i < m; i++) {
-        if (!dead[i - 1]) {
-            if (gaps[2 * i] - gaps[2 * i - 1] <= minGap) {
-                gaps[2 * i] = imin2(gaps[2 * i - 2], gaps[2 * i]);
-                gaps[2 * i + 1] = imax2(gaps[2 * i - 1], gaps[2 * i + 1]);
-                dead[i - 1] = 1;
-            }
-        }
-    }
-    int k = 0;
-    for (int i = 0; i < m; i++) if (!dead[i]) { gaps[2 * k] = gaps[2 * i]; gaps[2 * k + 1] = gaps[2 * i + 1]; k++; }
-    if (k < 2) return 0;
-    return 2 * k;
-}
-/* SiteScore.CHECKGAPS (stream/SiteScore.java:951-958) */
-static int check_gaps(const orc_ss* s)
-{
-    if (s->ngaps == 0) return 1;
-    if (s->ngaps & 1) return 0;
-    for (int i = 1; i < s->ngaps; i++) if (s->gaps[i - 1] > s->gaps[i]) return 0;
-    return s->gaps[0] == s->start && s->gaps[s->ngaps - 1] == s->stop;
-}
-/* SiteScore.setLimits / setStop (stream/SiteScore.java:905-914, 943-950); MINGAP = 256 (Shared.java:24) */
-static void ss_set_limits(orc_ss* s, int a, int b)
-{
-    s->start = a; s->stop = b;
-    if (s->ngaps > 0) { s->gaps[0] = a; s->gaps[s->ngaps - 1] = b; if (!check_gaps(s)) s->ngaps = fix_gaps(s->start, s->stop, s->gaps, s->ngaps, 256); }
-}
-static void ss_set_stop(orc_ss* s, int b)
-{
-    s->stop = b;
-    if (s->ngaps > 0) { s->gaps[s->ngaps - 1] = b; s->ngaps = fix_gaps(s->start, s->stop, s->gaps, s->ngaps, 256); }
-}
-/* GapTools.calcGrefLen (:75-91) */
-static int calc_gref_len(const orc_ss* s)
-{
-    int total = s->stop - s->start + 1;
-    for (int i = 2; i < s->ngaps; i += 2) total -= imax2(0, (s->gaps[i] - s->gaps[i - 1] - 128) / 128) * 127;
-    return total;
-}
-
 int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
                        const int8_t* refs, const int64_t* chrom_off, const int32_t* run, const orc_slow_cfg* cfg, int32_t* status)
 {
@@ -117,8 +53,8 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
             const int swscoreNoIndel = ss->slow_score;
             int32_t arr[8], old[8], max4[4]; int n = 0;
             if (swscoreNoIndel < maxImperfectSwScore && !ss->semiperfect) {
-                const int expectedLen = calc_gref_len(ss);
-                if (expectedLen >= cfg->expected_len_limit) ss_set_stop(ss, ss->start + imin2(len + 40, cfg->expected_len_limit));
+                const int expectedLen = orc_calc_gref_len(ss);
+                if (expectedLen >= cfg->expected_len_limit) orc_ss_set_stop(ss, ss->start + imin2(len + 40, cfg->expected_len_limit));
                 int pad = cfg->slow_align_padding;
                 const int minscore = imax2(swscoreNoIndel, minMsaLimit);
                 int32_t g[ORC_MAX_GAPS];
@@ -127,7 +63,7 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
                 alignments++;
                 if (n > 6 && (arr[3] + arr[4] + expectedLen < cfg->expected_len_limit)) {
                     const int oldn = n; memcpy(old, arr, sizeof(arr));
-                    ss_set_limits(ss, ss->start - arr[6], ss->stop + arr[7]);
+                    orc_ss_set_limits(ss, ss->start - arr[6], ss->stop + arr[7]);
                     pad = cfg->slow_align_padding + cfg->extra_padding;
                     memcpy(g, ss->gaps, sizeof(ss->gaps));
                     n = orc_msa_fillAndScoreLimited(msa, bases, len, ref, refLen, ss->start - pad, ss->stop + pad, minscore, ss->ngaps ? g : 0, ss->ngaps, max4, arr);
@@ -135,7 +71,7 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
                     if (n == 0 || arr[0] < old[0]) { n = oldn; memcpy(arr, old, sizeof(arr)); }
                 }
             }
-            if (n > 0) { orc_ss_set_slow_score(ss, arr[0]); ss_set_limits(ss, arr[1], arr[2]); }
+            if (n > 0) { orc_ss_set_slow_score(ss, arr[0]); orc_ss_set_limits(ss, arr[1], arr[2]); }
             ss->score = ss->slow_score;
             minMatch = imax2(minMatch, ss->slow_score);
             minMsaLimit = imax2(minMsaLimit, ss->slow_score - cfg->clearzone3);

@@ -99,6 +99,77 @@ static int trim_list(orc_ss* v, int* n, int retainPaired, int maxScore, int spec
     return highest;
 }
 
+/* GapTools.fixGaps(a, b, gaps, minGap) + fixGaps2 (current/align2/GapTools.java:26-72, 126-175).  Works in place on gaps[0..n); returns the new number of
+ * ints, 0 = null. */
+int orc_fix_gaps(int a, int b, int32_t* gaps, int n, int minGap)
+{
+    if (n == 0) return 0;
+    if (!(gaps[0] <= b && gaps[n - 1] >= a)) return 0;                 /* Tools.overlap(a, b, g0, gN) */
+    int changed = 0;
+    if (gaps[0] != a) { gaps[0] = a; changed++; }
+    if (gaps[n - 1] != b) { gaps[n - 1] = b; changed++; }
+    for (int i = 0; i < n; i++) { if (gaps[i] < a) { gaps[i] = a; changed++; } else if (gaps[i] > b) { gaps[i] = b; changed++; } }
+    for (int i = 1; i < n; i++) if (gaps[i - 1] > gaps[i]) { gaps[i] = gaps[i - 1]; changed++; }
+    if (changed == 0) return n;
+    gaps[0] = a; gaps[n - 1] = b;
+    int remove = 0;
+    for (int i = 0; i < n; i += 2) {
+        gaps[i] = gaps[i] < a ? a : (gaps[i] > b ? b : gaps[i]);
+        gaps[i + 1] = gaps[i + 1] < a ? a : (gaps[i + 1] > b ? b : gaps[i + 1]);
+        if (gaps[i] == gaps[i + 1]) remove++;
+    }
+    if (remove == 0) return n;
+    /* fixGaps2: merge ranges closer than minGap, left to right */
+    int dead[ORC_MAX_GAPS]; const int m = n / 2;
+    for (int i = 0; i < m; i++) dead[i] = 0;
+    for (int i = 1; i < m; i++) {
+        if (!dead[i - 1]) {
+            if (gaps[2 * i] - gaps[2 * i - 1] <= minGap) {
+                gaps[2 * i] = imin(gaps[2 * i - 2], gaps[2 * i]);
+                gaps[2 * i + 1] = imax(gaps[2 * i - 1], gaps[2 * i + 1]);
+                dead[i - 1] = 1;
+            }
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < m; i++) if (!dead[i]) { gaps[2 * k] = gaps[2 * i]; gaps[2 * k + 1] = gaps[2 * i + 1]; k++; }
+    if (k < 2) return 0;
+    return 2 * k;
+}
+/* SiteScore.CHECKGAPS (stream/SiteScore.java:951-958) */
+static int check_gaps(const orc_ss* s)
+{
+    if (s->ngaps == 0) return 1;
+    if (s->ngaps & 1) return 0;
+    for (int i = 1; i < s->ngaps; i++) if (s->gaps[i - 1] > s->gaps[i]) return 0;
+    return s->gaps[0] == s->start && s->gaps[s->ngaps - 1] == s->stop;
+}
+/* SiteScore.setLimits / setStop (stream/SiteScore.java:905-914, 943-950); MINGAP = 256 (Shared.java:24) */
+void orc_ss_set_limits(orc_ss* s, int a, int b)
+{
+    s->start = a; s->stop = b;
+    if (s->ngaps > 0) { s->gaps[0] = a; s->gaps[s->ngaps - 1] = b; if (!check_gaps(s)) s->ngaps = orc_fix_gaps(s->start, s->stop, s->gaps, s->ngaps, 256); }
+}
+void orc_ss_set_stop(orc_ss* s, int b)
+{
+    s->stop = b;
+    if (s->ngaps > 0) { s->gaps[s->ngaps - 1] = b; s->ngaps = orc_fix_gaps(s->start, s->stop, s->gaps, s->ngaps, 256); }
+}
+/* GapTools.calcGrefLen (:75-91) */
+int orc_calc_gref_len(const orc_ss* s)
+{
+    int total = s->stop - s->start + 1;
+    for (int i = 2; i < s->ngaps; i += 2) total -= imax(0, (s->gaps[i] - s->gaps[i - 1] - 128) / 128) * 127;
+    return total;
+}
+
+/* SiteScore.setStart (stream/SiteScore.java:933-942) */
+void orc_ss_set_start(orc_ss* s, int a)
+{
+    s->start = a;
+    if (s->ngaps > 0) { s->gaps[0] = a; if (s->gaps[0] > s->gaps[1]) s->ngaps = orc_fix_gaps(a, s->stop, s->gaps, s->ngaps, 256); }
+}
+
 /* SiteScore.setSlowScore (stream/SiteScore.java:962-983): also moves pairedScore */
 void orc_ss_set_slow_score(orc_ss* s, int x) {
     if (x <= 0) { s->paired_score = s->slow_score = x; }
@@ -320,7 +391,6 @@ void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int3
         for (int j = 0; j < n; j++) {
             orc_ss* ss = &v[j];
             if (ss->semiperfect || ss->slow_score >= maxImp) continue;
-            if (ss->ngaps > 0) { out[r].flags |= 8; continue; }
             const int8_t* bases = (ss->strand == 0 ? basesP : basesM) + read_off[r];
             const int8_t* ref = refs + chrom_off[ss->chrom - 1]; const int refLen = (int)(chrom_off[ss->chrom] - chrom_off[ss->chrom - 1]);
             const int minIndex = chrom_min_index ? chrom_min_index[ss->chrom - 1] : 0;
@@ -334,14 +404,14 @@ void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int3
                     if (findRight) {
                         const int x = orc_find_tip_deletions_right(bases, len, ref, refLen, minIndex, ss->stop, maxSearch, TIPLEN);
                         if (x > 0) {
-                            ss->stop += x; changed = 1;
+                            orc_ss_set_stop(ss, ss->stop + x); changed = 1;
                             maxSearch = imin(maxSearch, tc->align_columns - (tc->slow_rescue_padding + 8 + imax(len, ss->stop - ss->start)));
                             if (maxSearch < 1) go = 0;
                         }
                     }
                     if (go && findLeft) {
                         const int y = orc_find_tip_deletions_left(bases, len, ref, refLen, minIndex, ss->start, maxSearch, TIPLEN);
-                        if (y > 0) { ss->start -= y; changed = 1; }
+                        if (y > 0) { orc_ss_set_start(ss, ss->start - y); changed = 1; }
                     }
                 }
             }
@@ -349,7 +419,7 @@ void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int3
                 out[r].best_sites++;
                 ss->has_match = 0;
                 orc_ss_set_slow_score(ss, orc_score_no_indels(bases, len, ref, refLen, ss->start, 0));
-                if (ss->slow_score == maxSw) { ss->stop = ss->start + len - 1; ss->perfect = ss->semiperfect = 1; }
+                if (ss->slow_score == maxSw) { orc_ss_set_stop(ss, ss->start + len - 1); ss->perfect = ss->semiperfect = 1; }
                 else { ss->perfect = 0; ss_set_perfect(ss, bases, len, ref, refLen); }
             }
         }
@@ -390,11 +460,10 @@ void orc_sitelist_bounds(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t ca
                 if (!is_single_scaffold(scaf_loc + base, cnt, inter_scaffold_padding, ss->start, ss->stop)) removed = 1;
             }
             if (removed) { for (int k = i; k + 1 < n; k++) v[k] = v[k + 1]; n--; i--; continue; }
-            if (ss->ngaps > 0) {
-                int total = ss->stop - ss->start + 1;                       /* GapTools.calcGrefLen */
-                for (int g = 2; g < ss->ngaps; g += 2) { const int gap = ss->gaps[g] - ss->gaps[g - 1] - 128; total -= imax(0, gap / 128) * 127;   /* calcNumGapSymbols: GAPBUFFER2 = GAPLEN = 128 (Shared.java:20-23) */ }
-                if (total >= expected_len_limit) flags |= 8;
-            } else if (ss->stop - ss->start + 1 >= expected_len_limit) ss->stop = ss->start + imin(read_len[r] + 40, expected_len_limit);
+            if (orc_calc_gref_len(ss) >= expected_len_limit) {
+                orc_ss_set_stop(ss, ss->start + imin(read_len[r] + 40, expected_len_limit));
+                if (ss->ngaps > 0) ss->ngaps = orc_fix_gaps(ss->start, ss->stop, ss->gaps, ss->ngaps, 256);
+            }
         }
         nss[r] = n;
         out[r].near_perfect = 0; out[r].flags = flags; out[r].clearzone = 0; out[r].best_sites = initial - n;

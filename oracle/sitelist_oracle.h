@@ -22,6 +22,11 @@ typedef struct {            /* == bbm_policy_cfg, 80 bytes */
 typedef struct { int32_t near_perfect, flags, clearzone, best_sites; } orc_read_out;   /* flags: bit0 mapped, bit1 perfect, bit2 ambiguous */
 
 void orc_ss_set_slow_score(orc_ss* s, int x);
+int orc_fix_gaps(int a, int b, int32_t* gaps, int n, int minGap);
+void orc_ss_set_limits(orc_ss* s, int a, int b);
+void orc_ss_set_stop(orc_ss* s, int b);
+void orc_ss_set_start(orc_ss* s, int a);
+int orc_calc_gref_len(const orc_ss* s);
 void orc_sitelist_trim(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg, orc_read_out* out);
 void orc_sitelist_noindel(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
                           const int8_t* refs, const int64_t* chrom_off, const orc_policy_cfg* cfg, orc_read_out* out);
