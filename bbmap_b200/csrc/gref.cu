@@ -47,11 +47,11 @@ __global__ void __launch_bounds__(128) gref_build_kernel(const int8_t* __restric
             const int rem = gap % GAPLEN, div = (gap - GAPBUFFER2) / GAPLEN;
             const int n1 = GAPBUFFER + rem;
             if (gpos + n1 + div + GAPBUFFER > greflen) { over = true; break; }
-            for (int j = lane; j < n1; j += 32) gref[gpos + j] = ref[y + 1 + j];
+            for (int j = lane; j < n1; j += 32) { const int r = y + 1 + j; gref[gpos + j] = (r >= 0 && r < t.ref_len) ? ref[r] : (int8_t)'N'; }   // a gap array hanging over the array would make the reference throw; never read outside
             gpos += n1;
             for (int j = lane; j < div; j += 32) gref[gpos + j] = (int8_t)'-';
             gpos += div;
-            for (int j = lane; j < GAPBUFFER; j += 32) gref[gpos + j] = ref[z - GAPBUFFER + j];
+            for (int j = lane; j < GAPBUFFER; j += 32) { const int r = z - GAPBUFFER + j; gref[gpos + j] = (r >= 0 && r < t.ref_len) ? ref[r] : (int8_t)'N'; }
             gpos += GAPBUFFER;
         }
     }

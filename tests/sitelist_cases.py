@@ -142,7 +142,7 @@ def slow_cases(nreads=1500, cap=4, seed=81):
                     s["strand"] = 1 - strand
                 elif w == 3:
                     s["start"] += int(rng.integers(-6, 7)); s["stop"] = s["start"] + L - 1
-                else:
+                elif s["start"] + L + 300 < len(g) - 210:      # gapped site (kept inside the array: quickMap's removeOutOfBounds guarantees that)
                     s["ngaps"] = 4; s["stop"] = s["start"] + L + 300; s["gaps"][:4] = (s["start"], s["start"] + 40, s["start"] + 340, s["stop"])
             s["quick_score"] = int((70 + 100 * (L - 1)) * rng.uniform(0.4, 1.0)); s["score"] = s["quick_score"]
         nss[r] = n
