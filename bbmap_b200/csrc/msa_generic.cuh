@@ -45,7 +45,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
     // lane >= 0: called by all 32 lanes of a warp that share `fast`.  Un-banded limited fills are then evaluated 32 columns at a time
     // (MS and INS of a row only depend on the previous row; DEL is a left-to-right chain resolved lane by lane with shuffles); every
     // other case runs on lane 0 exactly as in the single-thread form.
-    const bool warpFill = lane >= 0 && fast != nullptr && limited && hb < 1 && P.dump == nullptr;
+    const bool warpFill = lane >= 0 && fast != nullptr && (!limited || hb < 1) && P.dump == nullptr;
     if (lane > 0 && !warpFill) return;
     const bool lead = lane <= 0;
 
@@ -82,7 +82,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
             const int *uM = up, *uD = up + stride, *uI = up + 2 * stride;
             int *cM = cur, *cD = cur + stride, *cI = cur + 2 * stride;
             const int col0 = ins_score_offset(row);
-            const int colStart = minGood, colStop = maxGood;
+            const int colStart = limited ? minGood : 1, colStop = limited ? maxGood : cols;      // an unlimited fill visits every cell (jni/...JNI.c:134-290)
             minGood = -1; maxGood = -2;
             if (colStart < 0 || colStop < colStart) { broke = true; break; }
             __syncwarp();
@@ -96,7 +96,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
             const bool delBar = (row < 3) || (row > rows - 3);
             // the reference overwrites (row-1, col+1) with subfloor whenever it walks past colStop (jni/...JNI.c:662-667): beyond colStop the
             // previous row reads as subfloor (row 1 sits on the all-zero row 0 and colStop == cols there)
-            const bool pastIsSub = row > 1;
+            const bool pastIsSub = limited && row > 1;
             int carryM = cM[colStart - 1], carryD = cD[colStart - 1];
             int rowHi = colStart - 1;
             bool stop = false;
@@ -112,16 +112,19 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                     const int r0 = col < 2 ? '!' : ref[col - 2];
                     gap = (r1 == '-');
                     const bool match = (call1 == r1 && r1 != 'N'), prevMatch = (call0 == r0 && r0 != 'N');
-                    limit = max(vlimit, hl[col]);
-                    const int limit3 = max(floor_, match ? limit - P_MATCH2 : limit - P_SUB3);
-                    delNeeded = max(0, row - col - 1);
-                    insNeeded = max(0, (rows - row) - (cols - col) - 1);
-                    const int delPen = del_score_offset(delNeeded); insPen = ins_score_offset(insNeeded);
+                    int limit3 = 0, delPen = 0;
+                    if (limited) {
+                        limit = max(vlimit, hl[col]);
+                        limit3 = max(floor_, match ? limit - P_MATCH2 : limit - P_SUB3);
+                        delNeeded = max(0, row - col - 1);
+                        insNeeded = max(0, (rows - row) - (cols - col) - 1);
+                        delPen = del_score_offset(delNeeded); insPen = ins_score_offset(insNeeded);
+                    }
                     const bool dSub = pastIsSub && (col - 1) > colStop, uSub = pastIsSub && col > colStop;
                     {   // MS
                         const int dm = dSub ? subfloor : uM[col - 1], dd = dSub ? subfloor : uD[col - 1], di = dSub ? subfloor : uI[col - 1];
                         const int sM = dm & SMASK, sD = dd & SMASK, sI = di & SMASK, streak = dm & TMASK;
-                        if (gap || (sM <= limit3 && sD <= limit3 && sI <= limit3)) msv = subfloor;
+                        if (gap || (limited && sM <= limit3 && sD <= limit3 && sI <= limit3)) msv = subfloor;
                         else {
                             int a_, o;
                             if (match) { a_ = sM + (prevMatch ? P_MATCH2 : P_MATCH); o = P_MATCH; }
@@ -135,8 +138,10 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                             if (a_ >= b_ && a_ >= c_) { score = a_; time = (match == prevMatch) ? streak + 1 : 1; }
                             else if (b_ >= c_) { score = b_; time = 1; }
                             else { score = c_; time = 1; }
-                            const int lim2 = delNeeded > 0 ? limit - delPen : (insNeeded > 0 ? limit - insPen : limit);
-                            if (score >= lim2) good = true; else score = subfloor;
+                            if (limited) {
+                                const int lim2 = delNeeded > 0 ? limit - delPen : (insNeeded > 0 ? limit - insPen : limit);
+                                if (score >= lim2) good = true; else score = subfloor;
+                            }
                             if (time > MAX_TIME) time = TIME_WRAP;
                             msv = score | time;
                             code |= (time > 1) ? 0u : ((sM >= sD && sM >= sI) ? 0u : (sD >= sI ? 1u : 2u));
@@ -145,15 +150,17 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                     {   // INS
                         const int um = uSub ? subfloor : uM[col], ui = uSub ? subfloor : uI[col];
                         const int sM = um & SMASK, sI = ui & SMASK, streak = ui & TMASK;
-                        if (gap || (sM <= limit && sI <= limit) || (row < 2 && col > 1) || (row > rows - 2 && col < cols - 1)) insv = subfloor;
+                        if (gap || (limited && sM <= limit && sI <= limit) || (row < 2 && col > 1) || (row > rows - 2 && col < cols - 1)) insv = subfloor;
                         else {
                             const int a_ = sM + P_INS;
                             const int b_ = sI + (streak == 0 ? P_INS : (streak < LIM3 ? P_INS2 : (streak < LIM4 ? P_INS3 : P_INS4)));
                             int score, time;
                             if (a_ >= b_) { score = a_; time = 1; } else { score = b_; time = streak + 1; }
-                            const int lim2 = delNeeded > 0 ? limit - delPen
-                                           : (insNeeded > 0 ? limit - ins_score_offset(time + insNeeded) + ins_score_offset(time) : limit);
-                            if (score >= lim2) good = true; else score = subfloor;
+                            if (limited) {
+                                const int lim2 = delNeeded > 0 ? limit - delPen
+                                               : (insNeeded > 0 ? limit - ins_score_offset(time + insNeeded) + ins_score_offset(time) : limit);
+                                if (score >= lim2) good = true; else score = subfloor;
+                            }
                             if (time > MAX_TIME) time = TIME_WRAP;
                             insv = score | time;
                             code |= ((time > 1) ? 1u : (sM >= sI ? 0u : 1u)) << 3;
@@ -165,8 +172,30 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                 if (lane == 0) msLeft = carryM;
                 // a DEL cell is subfloor outright when neither predecessor beats its limit; with a dead chain only the lanes whose left MS
                 // could open a deletion need a step, and a skipped lane leaves exactly `subfloor` (time 0) behind, as the reference writes it
-                const unsigned openMask = __ballot_sync(WFULL, valid && !delBar && (msLeft & SMASK) > limit);
-                for (int j = 0; j < nIn; ++j) {
+                if (!limited) {
+                    // unlimited fill: no limit tests, so the chain step is the same few instructions for every column — run it uniformly
+                    // (lane j's inputs broadcast, every lane follows the carry) instead of one divergent lane at a time
+                    const int adjv = (r1 == 'N') ? P_DEL_REF_N : (gap ? P_GAP : 0);
+                    const int aOpen = (msLeft & SMASK) + P_DEL + adjv;
+                    for (int j = 0; j < nIn; ++j) {
+                        const int aj = __shfl_sync(WFULL, aOpen, j), adjj = __shfl_sync(WFULL, adjv, j);
+                        int nv = subfloor; unsigned cbit = 0;
+                        if (!delBar) {
+                            const int sD = carryD & SMASK, streak = carryD & TMASK;
+                            const int b_ = sD + adjj + (streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
+                                                       (((streak & 3) == 0) ? P_DEL5 : 0)))));
+                            const bool msw = aj >= b_;
+                            int time = msw ? 1 : streak + 1;
+                            if (time > MAX_TIME) time = TIME_WRAP;
+                            nv = (msw ? aj : b_) | time;
+                            cbit = ((time > 1) ? 1u : ((aj - P_DEL - adjj) >= sD ? 0u : 1u)) << 2;
+                        }
+                        if (lane == j) { delv = nv; code |= cbit; }
+                        carryD = nv;
+                    }
+                }
+                const unsigned openMask = limited ? __ballot_sync(WFULL, valid && !delBar && (msLeft & SMASK) > limit) : 0u;
+                for (int j = 0; limited && j < nIn; ++j) {
                     if ((carryD & SMASK) == subfloor && !((openMask >> j) & 1u)) {
                         const unsigned m = openMask & (0xfffffffeu << j);
                         if (!m) { carryD = subfloor; break; }
@@ -175,7 +204,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                     }
                     if (lane == j) {
                         const int sM = msLeft & SMASK, sD = carryD & SMASK, streak = carryD & TMASK;
-                        if ((sM <= limit && sD <= limit) || delBar) delv = subfloor;
+                        if ((limited && sM <= limit && sD <= limit) || delBar) delv = subfloor;
                         else {
                             int a_ = sM + P_DEL;
                             int b_ = sD + (streak == 0 ? P_DEL : (streak < LIM3 ? P_DEL2 : (streak < LIM4 ? P_DEL3 : (streak < LIM5 ? P_DEL4 :
@@ -183,9 +212,11 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                             if (r1 == 'N') { a_ += P_DEL_REF_N; b_ += P_DEL_REF_N; } else if (gap) { a_ += P_GAP; b_ += P_GAP; }
                             int score, time;
                             if (a_ >= b_) { score = a_; time = 1; } else { score = b_; time = streak + 1; }
-                            const int lim2 = insNeeded > 0 ? limit - insPen
-                                           : (delNeeded > 0 ? limit - del_score_offset(time + delNeeded) + del_score_offset(time) : limit);
-                            if (score >= lim2) good = true; else score = subfloor;
+                            if (limited) {
+                                const int lim2 = insNeeded > 0 ? limit - insPen
+                                               : (delNeeded > 0 ? limit - del_score_offset(time + delNeeded) + del_score_offset(time) : limit);
+                                if (score >= lim2) good = true; else score = subfloor;
+                            }
                             if (time > MAX_TIME) time = TIME_WRAP;
                             delv = score | time;
                             code |= ((time > 1) ? 1u : (sM >= sD ? 0u : 1u)) << 2;
@@ -195,7 +226,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                 }
                 carryM = __shfl_sync(WFULL, msv, 31);
                 // the reference leaves the row at the first cell past colStop that is not good (the cell itself is evaluated and stored)
-                const unsigned term = __ballot_sync(WFULL, valid && col > colStop && !good);
+                const unsigned term = __ballot_sync(WFULL, limited && valid && col > colStop && !good);
                 int lastLane = nIn - 1;
                 if (term) { lastLane = __ffs(term) - 1; stop = true; }
                 const bool visited = valid && lane <= lastLane;
