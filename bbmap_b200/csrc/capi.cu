@@ -293,16 +293,21 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     e = bbm_launch_msa_scatter(&P, (const unsigned char*)c->cls.p, cb, (int*)c->lists.p, (int*)c->nlist.p, st);
     if (e) return fail(BBM_E_CUDA, "msa_scatter_kernel launch", (cudaError_t)e);
     c->launches++;
-    const long long gstride = bbm_generic_scratch_ints(max_rows, max_cols);
+    const int gRows0 = (h[51] && h[52] && !(c->bandwidth > 0 || c->ratio > 0.f)) ? (int)h[52] : max_rows, gCols0 = (h[51] && h[52] && !(c->bandwidth > 0 || c->ratio > 0.f)) ? (int)h[51] : max_cols;
+    const long long gstride = bbm_generic_scratch_ints(gRows0, gCols0);       // per-task scratch (predecessor codes) from the class's own largest shape when no banded re-runs can follow
     long long chunk = (long long)((1ULL << 31) / ((size_t)gstride * 4));     // <= 2 GiB of row scratch at a time
     if (chunk < 1) chunk = 1;
+    // shared-memory rows of the row-sequential kernel are sized from the largest shape actually in the class (the classifier tracks it):
+    // a gapped reference is 500-700 columns, the upper bound 3002, and the difference is 2 versus 13 alignments resident per SM
+    const int gRows = (h[51] && h[52]) ? (int)h[52] : max_rows, gCols = (h[51] && h[52]) ? (int)h[51] : max_cols;
     auto run_generic = [&](const int* list, long long n, cudaStream_t gs, const unsigned int* endPtr, unsigned int lbase) -> int {
         if (n <= 0) return BBM_OK;
+        const bool classList = endPtr != nullptr;
         const long long ch = chunk > n ? n : chunk;
         if (c->gscratch.ensure((size_t)ch * (size_t)gstride * 4)) return fail(BBM_E_CUDA, "cudaMalloc generic scratch");
         for (long long done = 0; done < n; done += ch) {
             const int m = (int)((n - done) < ch ? (n - done) : ch);
-            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, gs, max_rows, max_cols, endPtr, lbase + (unsigned int)done);
+            int e2 = bbm_launch_msa_generic(&P, list + done, m, (int*)c->gscratch.p, gstride, gs, classList ? gRows : max_rows, classList ? gCols : max_cols, endPtr, lbase + (unsigned int)done);
             if (e2) return fail(BBM_E_CUDA, "msa_generic_kernel launch", (cudaError_t)e2);
             c->launches++;
         }

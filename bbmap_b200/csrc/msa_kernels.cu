@@ -25,6 +25,7 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
         if (resolve_task(task, P.bandwidth, P.ratio, T)) {
             k = (useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T);
             atomicAdd(&local[k], 1u);
+            if (k == CLASS_GENERIC) { atomicMax(&cb[CB_GENERIC_MAXCOLS], (unsigned)T.cols); atomicMax(&cb[CB_GENERIC_MAXROWS], (unsigned)T.rows); }
             if (k == CLASS_STRIP) atomicAdd(&localBytes, strip_task_bytes(T.rows, T.cols));
             if (useNarrow && narrow_eligible(T, useNarrow > 1 ? useNarrow : 0)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
             else if (k == CLASS_STRIP) atomicAdd(&localSb[strip_bucket(T)], 1u);

@@ -46,6 +46,7 @@ constexpr int STRIP_MAX_COLS = 512;            // CellTables cover DEL/INS runs 
 constexpr int CLS_NARROW_BIT = 0x80;           // class byte flag: first try the thread-per-alignment narrow kernel
 // counter block (32-bit words)
 constexpr int CB_COUNTS = 0, CB_CURSORS = 16, CB_WORK = 32, CB_OVERFLOW = 48, CB_NARROW_WORK = 49;
+constexpr int CB_GENERIC_MAXCOLS = 51, CB_GENERIC_MAXROWS = 52;   // largest shape in the row-sequential class: sizes its shared-memory rows
 constexpr int CB_NB_COUNTS = 64, CB_NB_CURSORS = 128, CB_WORDS = 192;
 constexpr int STRIP_BUCKETS = 16;              // strip list is ordered by estimated work, largest first (longest-processing-time-first)
 constexpr int CB_SB_COUNTS = 104, CB_SB_CURSORS = 168, CB_STRIP_BYTES = 184 /* 64-bit */, CB_STRIP_WORK = 50, CB_STRIP_POOL = 186 /* 64-bit */;
