@@ -246,7 +246,7 @@ static int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, cons
     const int narrowBlocks = c->sms * 4;
     const int narrowWarps = narrowBlocks * (bbm_msa_narrow_threads() / 32);
     // 0 = off, 1 = try every shape-eligible alignment, n>1 = only those with (best possible score - minScore) <= n points
-    const int useNarrow = (c->use_narrow && d_dump == nullptr) ? c->use_narrow : 0;
+    const int useNarrow = (c->use_narrow && d_dump == nullptr && ntasks >= c->strip_min_tasks) ? c->use_narrow : 0;   // thread-per-alignment as well: not for small batches (see useStrip)
     // 0 = off; n>0: limited un-banded fills whose work estimate falls in buckets < n go to the strip kernel, larger ones to the tiled kernel
     // The strip kernel is thread-per-alignment: it needs tens of thousands of alignments to fill 148 SMs, and a batch of a few dozen wide
     // alignments would run as a few dozen single threads (measured: 14 alignments = 48 ms).  Small batches (scoreSlow's later rounds and
