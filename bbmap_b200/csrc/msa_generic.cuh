@@ -177,7 +177,7 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                     // (lane j's inputs broadcast, every lane follows the carry) instead of one divergent lane at a time
                     const int adjv = (r1 == 'N') ? P_DEL_REF_N : (gap ? P_GAP : 0);
                     const int aOpen = (msLeft & SMASK) + P_DEL + adjv;
-                    for (int j = 0; j < nIn; ++j) {
+                    auto step = [&](int j) {
                         const int aj = __shfl_sync(WFULL, aOpen, j), adjj = __shfl_sync(WFULL, adjv, j);
                         int nv = subfloor; unsigned cbit = 0;
                         if (!delBar) {
@@ -192,7 +192,11 @@ __device__ void msa_generic_task(const MsaParams& P, const TaskCtx& T, const bbm
                         }
                         if (lane == j) { delv = nv; code |= cbit; }
                         carryD = nv;
-                    }
+                                        };
+                    if (nIn == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) step(j);     // full chunk: unrolled, so the two broadcasts of a step issue ahead of the chain
+                    } else for (int j = 0; j < nIn; ++j) step(j);
                 }
                 const unsigned openMask = limited ? __ballot_sync(WFULL, valid && !delBar && (msLeft & SMASK) > limit) : 0u;
                 for (int j = 0; limited && j < nIn; ++j) {
