@@ -1043,6 +1043,40 @@ extern "C" int bbm_sitelist_bounds_dev(bbm_ctx* c, bbm_ss* d_lists, int32_t* d_n
     return BBM_OK;
 }
 
+extern "C" int bbm_launch_sitelist_cz3(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const bbm_policy_cfg* cfg,
+                                       int ambiguous_toss, bbm_read_out* io, cudaStream_t st);
+extern "C" int bbm_launch_sitelist_tip_penalty(bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const int8_t* bases,
+                                               const int8_t* match, const long long* match_off, const bbm_read_out* flags, int tiplen, int* penalty,
+                                               int* status, cudaStream_t st);
+extern "C" int bbm_sitelist_clearzone3_dev(bbm_ctx* c, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                           const bbm_policy_cfg* cfg, int32_t ambiguous_toss, bbm_read_out* d_io, void* stream) {
+    if (!c || !cfg) return fail(BBM_E_ARG, "bbm_sitelist_clearzone3_dev: null pointer");
+    if (cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_sitelist_clearzone3_dev: cap must be in 1..64");
+    if (nreads <= 0) return BBM_OK;                                                  // an empty batch carries no buffers
+    if (!d_lists || !d_nss || !d_read_off || !d_io) return fail(BBM_E_ARG, "bbm_sitelist_clearzone3_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int e = bbm_launch_sitelist_cz3(d_lists, d_nss, nreads, cap, (const long long*)d_read_off, cfg, ambiguous_toss, d_io, stream ? (cudaStream_t)stream : c->stream);
+    if (e) return fail(BBM_E_CUDA, "sitelist_cz3_kernel launch", (cudaError_t)e);
+    c->launches++;
+    return BBM_OK;
+}
+extern "C" int bbm_sitelist_tip_penalty_dev(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                            const int8_t* d_bases, const int8_t* d_match, const int64_t* d_match_off, const bbm_read_out* d_flags,
+                                            int32_t tiplen, int32_t* d_penalty, int32_t* d_status, void* stream) {
+    if (!c) return fail(BBM_E_ARG, "bbm_sitelist_tip_penalty_dev: null pointer");
+    if (cap < 1 || cap > bbm_sitelist_max_cap() || tiplen < 1 || tiplen > 64) return fail(BBM_E_ARG, "bbm_sitelist_tip_penalty_dev: bad cap or tiplen");
+    if (nreads <= 0) return BBM_OK;
+    if (!d_lists || !d_nss || !d_read_off || !d_bases || !d_match || !d_match_off || !d_flags || !d_penalty) return fail(BBM_E_ARG, "bbm_sitelist_tip_penalty_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int e = bbm_launch_sitelist_tip_penalty(d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_bases, d_match, (const long long*)d_match_off, d_flags,
+                                            tiplen, d_penalty, d_status, stream ? (cudaStream_t)stream : c->stream);
+    if (e) return fail(BBM_E_CUDA, "sitelist_tip_penalty_kernel launch", (cudaError_t)e);
+    c->launches++;
+    return BBM_OK;
+}
+
 // =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,

@@ -638,7 +638,146 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
     }
 }
 
+// =====================  after the primary site's match string: clearzone 3, final score gate, tip penalty  =====================
+// BBMapThread.processRead :667-684, 698-700, 706-709; AbstractMapThread.applyClearzone3 :1820-1870, calcCZ3_fraction :1893-1911,
+// calcTipScorePenalty :2499-2567, applyScorePenalty :2601-2609.  Java float arithmetic: one rounding per operation, no contraction.
+__device__ __forceinline__ float cz3_mult(int i) { return i == 1 ? 1.f : i == 2 ? .75f : i == 3 ? .5f : i == 4 ? .25f : i == 5 ? .125f : .0625f; }   // CZ3_MULTS :2809
+__device__ __forceinline__ float calc_cz3_fraction(int score1, int score2, int cz3, float inv) {
+    const int dif = score1 - score2;
+    if (dif >= cz3) return 0.f;
+    const float f = __fmul_rn((float)(cz3 - dif), inv);
+    const float a = __fmul_rn(2.f, __fmul_rn(f, f));
+    return __fadd_rn(__fadd_rn(f, a), __fmul_rn(a, f));
+}
+struct Cz3Params { bbm_ss* lists; int* nss; long long nreads; int cap; const long long* read_off; bbm_policy_cfg cfg; int ambiguous_toss; bbm_read_out* io; };
+__global__ void __launch_bounds__(128) sitelist_cz3_kernel(Cz3Params P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    bbm_ss* v = P.lists + r * P.cap;
+    int n = P.nss[r];
+    const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
+    const int maxSw = max_quality(len);
+    const bbm_policy_cfg& cfg = P.cfg;
+    int flags = P.io[r].flags, subi = 0;
+    if (n == 0) flags &= ~1;
+    int mapScore = n > 0 ? v[0].slow_score : 0;
+    if ((cfg.clearzone3 > cfg.clearzone1 || cfg.clearzone3 > cfg.clearzonep) && n > 0 && !(flags & 4) && mapScore > 0) {
+        const float q = __fdiv_rn((float)maxSw, (float)mapScore);
+        const float cz3v2 = __fmul_rn((float)cfg.clearzone3, 1.25f < q ? 1.25f : q);
+        const int cz3 = (int)cz3v2; const float inv = __fdiv_rn(1.f, cz3v2);
+        if ((flags & 1) && n >= 2) {                                     // applyClearzone3
+            const int score1 = mapScore;
+            float sub = 0.f;
+            const int mx = imin(7, n);
+            int prevScore = v[0].slow_score;
+            for (int i = 1; i < mx; i++) {
+                const int s2 = v[i].slow_score;
+                if (i > 2 && s2 < prevScore) break;
+                const float f = calc_cz3_fraction(score1, s2, cz3, inv);
+                if (f <= 0.f) break;
+                sub = __fadd_rn(sub, __fmul_rn(f, cz3_mult(i)));
+                prevScore = s2;
+            }
+            if (sub > 0.f) {
+                const float asym = __fadd_rn(4.f, __fmul_rn(0.03f, (float)len));
+                sub = __fmul_rn(sub, 1.8f);
+                const float sub2 = __fmul_rn((float)cz3, __fdiv_rn(__fmul_rn(asym, sub), __fadd_rn(sub, asym)));
+                subi = (int)__fadd_rn(sub2, 0.5f);
+                if (subi >= mapScore - 300) subi = mapScore - 300;
+                if (subi <= 0) subi = 0;
+                else for (int i = 0; i < n; i++) { bbm_ss ss = v[i]; set_slow_score(ss, ss.slow_score - subi); ss.score -= subi; v[i] = ss; }
+            }
+        }
+        if (subi > 0) {
+            mapScore -= subi;
+            if (mapScore < (int)__fmul_rn((float)maxSw, cfg.min_align_ratio)) flags |= 4;
+        }
+    }
+    if ((flags & 4) && P.ambiguous_toss) { n = 0; flags &= ~1; mapScore = 0; }
+    if (n == 0 || (!(flags & 4) && (float)mapScore < __fmul_rn((float)maxSw, cfg.min_align_ratio))) { n = 0; flags &= ~1; mapScore = 0; }   // r.clearMapping()
+    P.nss[r] = n;
+    bbm_read_out o = P.io[r];
+    o.flags = flags; o.near_perfect = mapScore; o.best_sites = subi;
+    P.io[r] = o;
+}
+
+struct TipPenParams {
+    bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off; const int8_t* bases; const int8_t* match; const long long* match_off;
+    const bbm_read_out* flags; int tiplen; int* penalty; int* status;
+};
+__device__ __forceinline__ int tip_points(int8_t b, int8_t prev, int tiplen, int& cpos) {      // one match symbol of either tip loop (:2507-2525 / :2529-2542)
+    if (b == 'm') { cpos++; return 0; }
+    if (b == 'D') return prev != 'D' ? 2 * (tiplen + 2 - cpos) : 0;
+    const int w = (b == 'N' || b == 'C') ? 1 : 2;
+    const int p = w * (tiplen + 2 - cpos);
+    cpos++;
+    return p;
+}
+__global__ void __launch_bounds__(128) sitelist_tip_penalty_kernel(TipPenParams P) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nreads) return;
+    bbm_ss* v = P.lists + r * P.cap;
+    const int n = P.nss[r], tiplen = P.tiplen;
+    const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
+    const int mlen = (int)(P.match_off[r + 1] - P.match_off[r]);
+    const int8_t* match = P.match + P.match_off[r];
+    const int8_t* bases = P.bases + P.read_off[r];
+    int st = 0, pen = 0;
+    if ((P.flags[r].flags & 1) && n > 0 && mlen > 0 && len >= 2 * tiplen) {
+        const int maxScore = max_quality(len), mapScore = v[0].slow_score;
+        int points = 0;
+        int8_t prev = 'm';
+        for (int i = 0, cpos = 0; cpos <= tiplen; i++) {
+            if (i >= mlen) { st |= 1; break; }
+            const int8_t b = match[i];
+            if (b >= '0' && b <= '9') { st |= 2; break; }
+            points += tip_points(b, prev, tiplen, cpos);
+            prev = b;
+        }
+        prev = 'm';
+        if (!st) for (int i = mlen - 1, cpos = 0; cpos <= tiplen; i--) {
+            if (i < 0) { st |= 1; break; }
+            const int8_t b = match[i];
+            points += tip_points(b, prev, tiplen, cpos);
+            prev = b;
+        }
+        if (!st) {
+            const int last = len - 1;
+            int8_t b = bases[0];
+            if (b != 'N' && b == bases[1]) for (int i = 2; i <= tiplen && bases[i] == b; i++) points++;
+            b = bases[last];
+            if (b != 'N' && b == bases[last - 1]) for (int i = last - 2; i >= (last - tiplen) && bases[i] == b; i--) points++;
+            if (points >= 1) {
+                const float f = __fdiv_rn(__fmul_rn(80.f, (float)points), __fadd_rn((float)points, 80.f));
+                const int penalty = (int)__fmul_rn(__fmul_rn(f, .0022f), (float)maxScore);
+                const int maxPenalty = mapScore - maxScore / 10;
+                if (maxPenalty > 0) pen = imin(penalty, maxPenalty);
+            }
+        }
+        if (pen > 0) for (int i = 0; i < n; i++) { bbm_ss ss = v[i]; set_slow_score(ss, ss.slow_score - pen); ss.score -= pen; v[i] = ss; }   // applyScorePenalty
+    }
+    P.penalty[r] = pen;
+    if (P.status) P.status[r] = st;
+}
+
 }  // namespace bbm
+
+extern "C" int bbm_launch_sitelist_cz3(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const bbm_policy_cfg* cfg,
+                                       int ambiguous_toss, bbm_read_out* io, cudaStream_t st) {
+    bbm::Cz3Params P;
+    P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.cfg = *cfg; P.ambiguous_toss = ambiguous_toss; P.io = io;
+    bbm::sitelist_cz3_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_launch_sitelist_tip_penalty(bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const int8_t* bases,
+                                               const int8_t* match, const long long* match_off, const bbm_read_out* flags, int tiplen, int* penalty,
+                                               int* status, cudaStream_t st) {
+    bbm::TipPenParams P;
+    P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.bases = bases; P.match = match; P.match_off = match_off;
+    P.flags = flags; P.tiplen = tiplen; P.penalty = penalty; P.status = status;
+    bbm::sitelist_tip_penalty_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int bbm_sitelist_max_cap() { return bbm::SL_MAX_CAP; }
 extern "C" int bbm_launch_sitelist(int op, bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int8_t* basesP,

@@ -138,3 +138,48 @@ def removeOutOfBounds(ctx, lists, nss, read_off, chrom_max_index, scaf=None, int
     torch.cuda.synchronize()
     return (np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(), np.frombuffer(d_n.cpu().numpy().tobytes(), np.int32)[:n].copy(),
             np.frombuffer(d_out.cpu().numpy().tobytes(), READ_OUT_DTYPE)[:n].copy())
+
+
+def _staged(device):
+    import torch
+    dev = torch.device("cuda", device)
+    up = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else np.asarray(a, dt)).view(np.uint8).reshape(-1).copy()).to(dev)
+    q = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    return torch, dev, up, q
+
+
+def applyClearzone3(ctx, lists, nss, read_off, flags, cfg=None, ambiguous_toss=False, device=0):
+    """The clearzone-3 block and the final score gate of processRead (BBMapThread.java:667-684, 698-700; AbstractMapThread.applyClearzone3
+    :1820-1870) on every list (staged through torch tensors).  flags: READ_OUT_DTYPE[n] as SL_FINAL returned it.  Returns (lists, nss,
+    READ_OUT_DTYPE[n]) with flags updated, near_perfect = r.mapScore and best_sites = the amount subtracted."""
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: applyClearzone3 has no CPU fallback")
+    torch, dev, up, q = _staged(device)
+    cfg = policy_cfg() if cfg is None else cfg
+    lists = np.ascontiguousarray(lists, SS_DTYPE); n, cap = lists.shape
+    d_l = up(lists); d_n = up(nss, np.int32); d_o = up(read_off, np.int64)
+    d_io = up(np.ascontiguousarray(flags, READ_OUT_DTYPE)) if n else torch.zeros(16, dtype=torch.uint8, device=dev)
+    _lib.check(L.bbm_sitelist_clearzone3_dev(ctx, q(d_l), q(d_n), n, cap, q(d_o), _p(cfg), int(bool(ambiguous_toss)), q(d_io), None), "bbm_sitelist_clearzone3_dev")
+    torch.cuda.synchronize()
+    return (np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(), np.frombuffer(d_n.cpu().numpy().tobytes(), np.int32)[:n].copy(),
+            np.frombuffer(d_io.cpu().numpy().tobytes(), READ_OUT_DTYPE)[:n].copy())
+
+
+def tipScorePenalty(ctx, lists, nss, read_off, bases, match, match_off, flags, tiplen=7, device=0):
+    """calcTipScorePenalty(r, maxSwScore, 7) + applyScorePenalty (BBMapThread.java:706-709; AbstractMapThread.java:2499-2567, 2601-2609) on every
+    read (staged through torch tensors).  Returns (lists, penalty int32[n], status int32[n])."""
+    L = _lib.load()
+    if L.bbm_device_count() <= 0:
+        raise _lib.BbmError("no CUDA device visible: tipScorePenalty has no CPU fallback")
+    torch, dev, up, q = _staged(device)
+    lists = np.ascontiguousarray(lists, SS_DTYPE); n, cap = lists.shape
+    d_l = up(lists); d_n = up(nss, np.int32); d_o = up(read_off, np.int64); d_mo = up(match_off, np.int64)
+    d_b = up(np.concatenate([np.ascontiguousarray(bases).view(np.uint8), np.zeros(16, np.uint8)]))
+    d_m = up(np.concatenate([np.ascontiguousarray(match).view(np.uint8), np.zeros(16, np.uint8)]))
+    d_f = up(np.ascontiguousarray(flags, READ_OUT_DTYPE)) if n else torch.zeros(16, dtype=torch.uint8, device=dev)
+    d_p = torch.zeros(max(n, 1), dtype=torch.int32, device=dev); d_s = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    _lib.check(L.bbm_sitelist_tip_penalty_dev(ctx, q(d_l), q(d_n), n, cap, q(d_o), q(d_b), q(d_m), q(d_mo), q(d_f), tiplen, q(d_p), q(d_s), None),
+               "bbm_sitelist_tip_penalty_dev")
+    torch.cuda.synchronize()
+    return np.frombuffer(d_l.cpu().numpy().tobytes(), SS_DTYPE).reshape(n, cap).copy(), d_p.cpu().numpy()[:n].copy(), d_s.cpu().numpy()[:n].copy()

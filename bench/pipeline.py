@@ -58,6 +58,7 @@ def cpu_side(R, cb, co, table, n_cpu=20000):
     lists, _ = o.sitelist_tipdel(lists, ns * runm, off, bases, basesM, qual, cb, co, tipdel_cfg())
     lists, _, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, runm, sl.slow_cfg())
     lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
+    lists, ns, out = o.sitelist_clearzone3(lists, ns, off, out, pcfg)
     dt = time.perf_counter() - t0
     return {"reads": m, "cores": 1, "kind": "port", "seconds": dt, "reads_per_s": m / dt, "slow_alignments": int(na),
             "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy()}
@@ -153,6 +154,8 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
                                            150, None, C.byref(na), None), "bbm_scoreslow_dev")
         step("scoreSlow", slow)
         step("final", lambda: sitelist(sl.SL_FINAL))
+        # processRead :667-700 (in the reference the primary site's match string is generated in between; it is not chained yet)
+        step("applyClearzone3", lambda: _lib.check(L.bbm_sitelist_clearzone3_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), cp(pcfg), 0, p(d_out), None), "clearzone3"))
 
     L.bbm_launch_count.restype = C.c_int64
     totals = []
@@ -179,9 +182,9 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
            "mapped": float(mapped.mean()), "top_site_is_origin": float(correct.mean()), "top_site_exact_start_and_stop": float(exact.mean()),
            "ambiguous": float(((out["flags"] & sl.F_AMBIGUOUS) != 0).mean()), "status_nonzero": int((status != 0).sum()), "status_gapped_site": int(((status & sl.SLOW_GAPPED) != 0).sum()),
            "status_aligner_error": int(((status & sl.SLOW_ALIGNER_ERROR) != 0).sum()),
-           "mean_sites_after_final": float(nss.mean()),
+           "mean_sites_after_final": float(nss.mean()), "reads_lowered_by_clearzone3": float((out["best_sites"] > 0).mean()),
            "tip_deletion_sites_changed": int(np.frombuffer(d_out2.cpu().numpy().tobytes(), sl.READ_OUT_DTYPE)["best_sites"].sum()),
-           "not_chained_yet": "genMatchString/realign_new, applyClearzone3, tip-score penalty, pairing/rescue, SAM text",
+           "not_chained_yet": "genMatchString/realign_new (and the tip-score penalty that reads its match string), pairing/rescue, SAM text",
            "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
     if cpu:
         cs = cpu_side(R, cb, co, table)

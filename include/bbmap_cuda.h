@@ -381,6 +381,21 @@ int  bbm_sitelist_tipdel_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss
                              const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_quality, const int8_t* d_refs, const int64_t* d_chrom_off,
                              const int32_t* d_chrom_min_index, const bbm_tipdel_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out);
 
+/* The clearzone-3 block and the final score gate of processRead, after the primary site's match string exists (current/align2/BBMapThread.java:667-684,
+ * 698-700; AbstractMapThread.applyClearzone3 :1820-1870, calcCZ3_fraction :1893-1911): the near-ties behind the top site lower every score of the list,
+ * a read pushed under MINIMUM_ALIGNMENT_SCORE_RATIO becomes ambiguous, AMBIGUOUS_TOSS (ambiguous_toss != 0) and the ratio gate clear the mapping.
+ * d_io is in/out: flags as BBM_SL_FINAL left them; afterwards flags updated, near_perfect = r.mapScore (= the top site's slowScore, Read.java:1178),
+ * best_sites = the amount subtracted (0: applyClearzone3 returned false). */
+int  bbm_sitelist_clearzone3_dev(bbm_ctx* ctx, bbm_ss* d_lists, int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                 const bbm_policy_cfg* cfg, int32_t ambiguous_toss, bbm_read_out* d_io, void* stream);
+/* PENALIZE_AMBIG block of processRead (BBMapThread.java:706-709): AbstractMapThread.calcTipScorePenalty(r, maxSwScore, tiplen) (:2499-2567; tiplen 7)
+ * on the long-format match string of the primary site, then applyScorePenalty (:2601-2609).  Read r: bases d_bases[read_off[r]..) as sequenced (r.bases),
+ * match d_match[match_off[r] .. match_off[r+1]) (empty = r.match == null), mapped = d_flags[r].flags bit0.  d_penalty[r] = the penalty applied;
+ * d_status[r] (may be NULL): bit0 the string ended inside a tip (the reference would throw), bit1 short-format digits (not supported). */
+int  bbm_sitelist_tip_penalty_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                  const int8_t* d_bases, const int8_t* d_match, const int64_t* d_match_off, const bbm_read_out* d_flags,
+                                  int32_t tiplen, int32_t* d_penalty, int32_t* d_status, void* stream);
+
 /* ---- BBMapThread.scoreSlow over a batch of reads, in rounds (current/align2/BBMapThread.java:252-386; part of SURVEY 8f.1) ----
  * Round k slow-aligns the k-th site of every read whose run[r] != 0 (processRead calls scoreSlow when scoreNoIndels found no
  * near-perfect site, :463-465): preamble, MSA.fillAndScoreLimited(bases, ss, SLOW_ALIGN_PADDING, max(slowScore, minMsaLimit)), the

@@ -293,6 +293,29 @@ class Oracle:
                                      C.c_int32(inter_scaffold_padding), C.c_int32(sam_out), C.c_int32(expected_len_limit), _p(out))
         return lists, nss, out
 
+    def sitelist_clearzone3(self, lists, nss, read_off, flags, cfg, ambiguous_toss=False):
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+        n, cap = lists.shape
+        rl = np.ascontiguousarray(np.diff(np.ascontiguousarray(read_off, np.int64)), np.int32)
+        io = np.ascontiguousarray(flags, READ_OUT_DTYPE).copy()
+        self.lib.orc_sitelist_clearzone3.restype = None
+        self.lib.orc_sitelist_clearzone3(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(rl), _p(cfg), C.c_int32(int(bool(ambiguous_toss))), _p(io))
+        return lists, nss, io
+
+    def sitelist_tip_penalty(self, lists, nss, read_off, bases, match, match_off, flags, tiplen=7):
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SS_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); mo = np.ascontiguousarray(match_off, np.int64)
+        bb = np.concatenate([np.ascontiguousarray(bases).view(np.int8), np.zeros(16, np.int8)])
+        mm = np.concatenate([np.ascontiguousarray(match).view(np.int8), np.zeros(16, np.int8)])
+        ff = np.ascontiguousarray(flags, READ_OUT_DTYPE)
+        pen = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+        self.lib.orc_sitelist_tip_penalty.restype = None
+        self.lib.orc_sitelist_tip_penalty(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(ro), _p(bb), _p(mm), _p(mo), _p(ff), C.c_int32(tiplen), _p(pen), _p(st))
+        return lists, pen, st
+
     def score_slow(self, lists, nss, read_off, basesP, basesM, refs, chrom_off, run, cfg):
         from bbmap_b200.sitelist import SS_DTYPE
         lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32)

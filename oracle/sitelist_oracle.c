@@ -469,3 +469,132 @@ void orc_sitelist_bounds(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t ca
         out[r].near_perfect = 0; out[r].flags = flags; out[r].clearzone = 0; out[r].best_sites = initial - n;
     }
 }
+
+/* ---- what processRead does to the list after the match string of the primary site exists (unpaired reads) ----
+ *   the clearzone-3 block and the final score gate          current/align2/BBMapThread.java:667-684, 698-700
+ *   AbstractMapThread.applyClearzone3 / calcCZ3_fraction    current/align2/AbstractMapThread.java:1820-1870, 1893-1911 (CZ3_MULTS :2809)
+ *   AbstractMapThread.calcTipScorePenalty / applyScorePenalty   :2499-2567, 2601-2609 (called with tiplen 7, BBMapThread.java:706-709)
+ * r.mapScore is the top site's slowScore (Read.setFromSite, current/stream/Read.java:1178; the reference asserts the equality, :1826).
+ * All float arithmetic is Java's: single precision, one rounding per operation. */
+static const float CZ3_MULTS[7] = { 0.f, 1.f, .75f, 0.5f, 0.25f, 0.125f, 0.0625f };
+
+static float calc_cz3_fraction(int score1, int score2, int cz3, float inv)
+{
+    const int dif = score1 - score2;
+    if (dif >= cz3) return 0.f;
+    const int dif2 = cz3 - dif;
+    const float f = (float)dif2 * inv;
+    const float f2 = f * f;
+    const float a = 2.f * f2;
+    return (f + a) + a * f;                     /* f+2f*f2+2f*f2*f, left to right */
+}
+
+/* returns the amount subtracted (0 = applyClearzone3 returned false) */
+static int apply_clearzone3(orc_ss* v, int n, int len, int flags, int cz3, float inv)
+{
+    if (!(flags & 1) || (flags & 4) || n < 2) return 0;
+    const int score1 = v[0].slow_score, mapScore = v[0].slow_score;
+    float sub = 0.f;
+    const int max = imin(7, n);
+    for (int i = 1; i < max; i++) {
+        if (i > 2 && v[i].slow_score < v[i - 1].slow_score) break;
+        const float f = calc_cz3_fraction(score1, v[i].slow_score, cz3, inv);
+        if (f <= 0.f) break;
+        sub += f * CZ3_MULTS[i];
+    }
+    if (sub <= 0.f) return 0;
+    const float asymptote = 4.f + 0.03f * (float)len;
+    sub = sub * 1.8f;
+    const float sub2 = (float)cz3 * ((asymptote * sub) / (sub + asymptote));
+    int subi = (int)(sub2 + 0.5f);
+    if (subi >= mapScore - 300) subi = mapScore - 300;
+    if (subi <= 0) return 0;
+    for (int i = 0; i < n; i++) { orc_ss_set_slow_score(&v[i], v[i].slow_score - subi); v[i].score -= subi; }
+    return subi;
+}
+
+/* out[r] is in/out: flags as the final policy left them; afterwards flags updated, near_perfect = r.mapScore, best_sites = the amount subtracted */
+void orc_sitelist_clearzone3(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg,
+                             int32_t ambiguous_toss, orc_read_out* out)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; int n = nss[r];
+        const int maxSw = max_quality(read_len[r]);
+        int flags = out[r].flags, subi = 0;
+        if (n == 0) flags &= ~1;
+        int mapScore = n > 0 ? v[0].slow_score : 0;
+        if ((cfg->clearzone3 > cfg->clearzone1 || cfg->clearzone3 > cfg->clearzonep) && n > 0 && !(flags & 4) && mapScore > 0) {
+            const float q = (float)maxSw / (float)mapScore;
+            const float cz3v2 = (float)cfg->clearzone3 * (1.25f < q ? 1.25f : q);
+            subi = apply_clearzone3(v, n, read_len[r], flags, (int)cz3v2, 1.f / cz3v2);
+            if (subi > 0) {
+                mapScore -= subi;
+                const int minScore = (int)((float)maxSw * cfg->min_align_ratio);
+                if (mapScore < minScore) flags |= 4;
+            }
+        }
+        if ((flags & 4) && ambiguous_toss) { n = 0; flags &= ~1; mapScore = 0; }
+        if (n == 0 || (!(flags & 4) && (float)mapScore < (float)maxSw * cfg->min_align_ratio)) { n = 0; flags &= ~1; mapScore = 0; }   /* r.clearMapping() */
+        nss[r] = n;
+        out[r].flags = flags; out[r].near_perfect = mapScore; out[r].best_sites = subi;
+    }
+}
+
+/* calcTipScorePenalty(r, maxScore, tiplen) on a long-format match string; status bit0: the string ended before tiplen+1 read positions
+ * were seen (the reference would throw), bit1: short-format digits (Read.toLongMatchString is not restated). */
+static int calc_tip_score_penalty(const int8_t* match, int mlen, const int8_t* bases, int len, int mapped, int mapScore, int maxScore, int tiplen, int* status)
+{
+    if (!mapped || mlen <= 0 || len < 2 * tiplen) return 0;
+    int points = 0;
+    int8_t prev = 'm';
+    for (int i = 0, cpos = 0; cpos <= tiplen; i++) {
+        if (i >= mlen) { *status |= 1; return 0; }
+        const int8_t b = match[i];
+        if (b == 'm') cpos++;
+        else if (b == 'D') { if (prev != 'D') points += 2 * (tiplen + 2 - cpos); }
+        else if (b == 'N' || b == 'C') { points += (tiplen + 2 - cpos); cpos++; }
+        else {
+            if (b >= '0' && b <= '9') { *status |= 2; return 0; }
+            points += 2 * (tiplen + 2 - cpos); cpos++;
+        }
+        prev = b;
+    }
+    prev = 'm';
+    for (int i = mlen - 1, cpos = 0; cpos <= tiplen; i--) {
+        if (i < 0) { *status |= 1; return 0; }
+        const int8_t b = match[i];
+        if (b == 'm') cpos++;
+        else if (b == 'D') { if (prev != 'D') points += 2 * (tiplen + 2 - cpos); }
+        else if (b == 'N' || b == 'C') { points += (tiplen + 2 - cpos); cpos++; }
+        else { points += 2 * (tiplen + 2 - cpos); cpos++; }
+        prev = b;
+    }
+    const int last = len - 1;
+    int8_t b = bases[0];
+    if (b != 'N' && b == bases[1]) for (int i = 2; i <= tiplen && bases[i] == b; i++) points++;
+    b = bases[last];
+    if (b != 'N' && b == bases[last - 1]) for (int i = last - 2; i >= (last - tiplen) && bases[i] == b; i--) points++;
+    if (points < 1) return 0;
+    const float asymptote = 80.f;
+    const float f = (asymptote * (float)points) / ((float)points + asymptote);
+    const int penalty = (int)((f * .0022f) * (float)maxScore);
+    const int maxPenalty = mapScore - maxScore / 10;
+    if (maxPenalty <= 0) return 0;
+    return imin(penalty, maxPenalty);
+}
+
+/* PENALIZE_AMBIG block of processRead: penalty[r] = calcTipScorePenalty(r, maxSwScore, tiplen), then applyScorePenalty.  flags[r] bit0 = r.mapped();
+ * match of read r = match[match_off[r] .. match_off[r+1]) (empty = r.match == null); bases = r.bases (the read as sequenced). */
+void orc_sitelist_tip_penalty(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off, const int8_t* bases,
+                              const int8_t* match, const int64_t* match_off, const orc_read_out* flags, int32_t tiplen, int32_t* penalty, int32_t* status)
+{
+    for (int64_t r = 0; r < nreads; r++) {
+        orc_ss* v = lists + r * cap; const int n = nss[r];
+        const int len = (int)(read_off[r + 1] - read_off[r]);
+        int st = 0;
+        const int p = calc_tip_score_penalty(match + match_off[r], (int)(match_off[r + 1] - match_off[r]), bases + read_off[r], len,
+                                             (flags[r].flags & 1) && n > 0, n > 0 ? v[0].slow_score : 0, max_quality(len), tiplen, &st);
+        if (p > 0) for (int i = 0; i < n; i++) { orc_ss_set_slow_score(&v[i], v[i].slow_score - p); v[i].score -= p; }
+        penalty[r] = p; status[r] = st;
+    }
+}

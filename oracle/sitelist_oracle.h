@@ -36,3 +36,7 @@ void orc_sitelist_tipdel(orc_ss* lists, const int32_t* nss, int64_t nreads, int3
 void orc_sitelist_bounds(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const int32_t* chrom_max_index,
                          const int32_t* scaf_off, const int32_t* scaf_loc, int32_t inter_scaffold_padding, int32_t sam_out, int32_t expected_len_limit,
                          orc_read_out* out);
+void orc_sitelist_clearzone3(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int32_t* read_len, const orc_policy_cfg* cfg,
+                             int32_t ambiguous_toss, orc_read_out* out);
+void orc_sitelist_tip_penalty(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off, const int8_t* bases,
+                              const int8_t* match, const int64_t* match_off, const orc_read_out* flags, int32_t tiplen, int32_t* penalty, int32_t* status);

@@ -149,3 +149,56 @@ def slow_cases(nreads=1500, cap=4, seed=81):
         if rng.random() < 0.1:
             run[r] = 0
     return refs, chrom_off, P, M, read_off, lists, nss, run
+
+
+def random_match_strings(read_off, seed=7):
+    """Long-format match strings ('m', 'S', 'N', 'I', 'D', 'C', rarely 'X'/'Y') consuming exactly each read, with events concentrated in the tips;
+    every 17th read has none (r.match == null), every 41st is cut short inside the tip, every 53rd is short format."""
+    rng = np.random.default_rng(seed)
+    n = len(read_off) - 1; parts = []; off = np.zeros(n + 1, np.int64)
+    for r in range(n):
+        L = int(read_off[r + 1] - read_off[r]); s = []
+        pos = 0
+        while pos < L:
+            tip = pos < 9 or pos >= L - 9
+            u = rng.random()
+            if u < (0.25 if tip else 0.02):
+                k = rng.random()
+                if k < 0.35:
+                    s.append("S"); pos += 1
+                elif k < 0.5:
+                    s.append("N"); pos += 1
+                elif k < 0.6:
+                    s.append("C"); pos += 1
+                elif k < 0.75:
+                    s.append("I"); pos += 1
+                elif k < 0.97:
+                    s.append("D" * int(rng.integers(1, 5)))
+                else:
+                    s.append("X" if pos < 9 else "Y"); pos += 1
+            else:
+                s.append("m"); pos += 1
+        t = "".join(s)
+        if r % 17 == 16:
+            t = ""
+        elif r % 41 == 40:
+            t = t[:5]
+        elif r % 53 == 52:
+            t = "m3S" + t[5:]
+        parts.append(t); off[r + 1] = off[r] + len(t)
+    return np.frombuffer("".join(parts).encode(), np.int8).copy(), off
+
+
+def homopolymer_reads(read_off, seed=9):
+    """Read bases (as sequenced) with homopolymer runs and Ns at the tips."""
+    rng = np.random.default_rng(seed)
+    b = np.frombuffer(b"ACGT", np.int8)[rng.integers(0, 4, size=int(read_off[-1]))].copy()
+    for r in range(len(read_off) - 1):
+        a, e = int(read_off[r]), int(read_off[r + 1])
+        if rng.random() < 0.4:
+            b[a:a + int(rng.integers(2, 10))] = b[a]
+        if rng.random() < 0.4:
+            b[e - int(rng.integers(2, 10)):e] = b[e - 1]
+        if rng.random() < 0.05:
+            b[a] = ord("N"); b[a + 1] = ord("N")
+    return b

@@ -156,3 +156,34 @@ def test_remove_out_of_bounds_parity(oracle, msa, seed, sam_out, with_scaf):
         live = np.arange(cap)[None, :] < exp[1][:, None]
         assert got[0][live].tobytes() == exp[0][live].tobytes()
     assert exp[2]["best_sites"].sum() > 500
+
+
+@pytest.mark.parametrize("seed", [77, 78])
+def test_clearzone3_parity(oracle, msa, seed):
+    """processRead's clearzone-3 block + score gate (BBMapThread.java:667-684, 698-700): lists, lengths, flags, mapScore, amount subtracted."""
+    lists, nss, ro = random_lists(nreads=6000, cap=16, seed=seed, after_alignment=True)
+    for cfg, toss in ((sl.policy_cfg(), False), (sl.policy_cfg(), True), (sl.policy_cfg(clearzone3=150), False), (sl.policy_cfg(min_align_ratio=0.7), False)):
+        l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+        exp = oracle.sitelist_clearzone3(l1, n1, ro, fl, cfg, ambiguous_toss=toss)
+        _same(sl.applyClearzone3(msa.h, l1, n1, ro, fl, cfg, ambiguous_toss=toss), exp)
+    l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, sl.policy_cfg())
+    exp = oracle.sitelist_clearzone3(l1, n1, ro, fl, sl.policy_cfg())
+    assert (exp[2]["best_sites"] > 0).sum() > 100 and ((exp[2]["flags"] & sl.F_AMBIGUOUS) > (fl["flags"] & sl.F_AMBIGUOUS)).any()
+    assert (oracle.sitelist_clearzone3(l1, n1, ro, fl, sl.policy_cfg(), ambiguous_toss=True)[1] < n1).any()
+    empty = sl.applyClearzone3(msa.h, l1[:0], n1[:0], ro[:1], fl[:0])
+    assert empty[0].shape[0] == 0
+
+
+@pytest.mark.parametrize("seed,tiplen", [(5, 7), (6, 7), (7, 4)])
+def test_tip_penalty_parity(oracle, msa, seed, tiplen):
+    """calcTipScorePenalty + applyScorePenalty (AbstractMapThread.java:2499-2567, 2601-2609): penalty, status and every score of the list."""
+    from sitelist_cases import homopolymer_reads, random_match_strings
+    lists, nss, ro = random_lists(nreads=6000, cap=8, seed=seed + 90, after_alignment=True)
+    l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, sl.policy_cfg())
+    bases = homopolymer_reads(ro, seed); match, mo = random_match_strings(ro, seed)
+    el, ep, es = oracle.sitelist_tip_penalty(l1, n1, ro, bases, match, mo, fl, tiplen)
+    gl, gp, gs = sl.tipScorePenalty(msa.h, l1, n1, ro, bases, match, mo, fl, tiplen)
+    assert np.array_equal(gp, ep) and np.array_equal(gs, es)
+    live = np.arange(el.shape[1])[None, :] < n1[:, None]
+    assert gl[live].tobytes() == el[live].tobytes()
+    assert (ep > 0).sum() > 1000 and (es == 1).any() and (es == 2).any()

@@ -119,3 +119,147 @@ def test_remove_out_of_bounds_by_hand(oracle):
     # without SAM output the scaffold test is skipped
     L3, n3, _ = oracle.sitelist_bounds(lists, nss, ro, [9999], scaf, sam_out=0)
     assert n3[0] == 4 and int(L3[0, 1]["start"]) == 3950
+
+
+# ---- clearzone 3 / tip penalty: a second, independent restatement in numpy float32, straight from the Java text ----
+_F = np.float32
+_CZ3_MULTS = [_F(x) for x in (0, 1, .75, .5, .25, .125, .0625)]           # AbstractMapThread.java:2809
+
+
+def _py_cz3_fraction(s1, s2, cz3, inv):                                    # :1893-1911
+    dif = s1 - s2
+    if dif >= cz3:
+        return _F(0)
+    f = _F(cz3 - dif) * inv
+    f2 = f * f
+    return f + _F(2) * f2 + _F(2) * f2 * f
+
+
+def _py_set_slow(s, x):                                                    # SiteScore.setSlowScore, stream/SiteScore.java:962-983
+    if x <= 0:
+        s["paired_score"] = x
+    elif s["paired_score"] > 0:
+        s["paired_score"] = x + (s["paired_score"] - s["slow_score"]) if s["slow_score"] > 0 else x + 1
+    s["slow_score"] = x
+
+
+def _py_clearzone3(v, n, L, flags, cfg, toss=False):
+    """BBMapThread.java:667-684, 698-700 + applyClearzone3 :1820-1870 for one read; returns (n, flags, mapScore, subi)."""
+    maxSw = 70 + 100 * (L - 1); ratio = _F(cfg["min_align_ratio"][0]); CZ3 = int(cfg["clearzone3"][0])
+    if n == 0:
+        flags &= ~1
+    mapScore = int(v[0]["slow_score"]) if n else 0
+    subi = 0
+    if (CZ3 > cfg["clearzone1"][0] or CZ3 > cfg["clearzonep"][0]) and n > 0 and not flags & 4 and mapScore > 0:
+        cz3v2 = _F(CZ3) * min(_F(1.25), _F(maxSw) / _F(mapScore))
+        cz3, inv = int(cz3v2), _F(1) / cz3v2
+        if flags & 1 and n >= 2:
+            sub = _F(0)
+            for i in range(1, min(7, n)):
+                if i > 2 and v[i]["slow_score"] < v[i - 1]["slow_score"]:
+                    break
+                f = _py_cz3_fraction(mapScore, int(v[i]["slow_score"]), cz3, inv)
+                if f <= 0:
+                    break
+                sub = sub + f * _CZ3_MULTS[i]
+            if sub > 0:
+                asym = _F(4) + _F(0.03) * _F(L)
+                sub = sub * _F(1.8)
+                sub2 = _F(cz3) * ((asym * sub) / (sub + asym))
+                subi = int(sub2 + _F(0.5))
+                if subi >= mapScore - 300:
+                    subi = mapScore - 300
+                if subi <= 0:
+                    subi = 0
+                else:
+                    for i in range(n):
+                        _py_set_slow(v[i], int(v[i]["slow_score"]) - subi); v[i]["score"] -= subi
+        if subi > 0:
+            mapScore -= subi
+            if mapScore < int(_F(maxSw) * ratio):
+                flags |= 4
+    if flags & 4 and toss:
+        n = 0; flags &= ~1; mapScore = 0
+    if n == 0 or (not flags & 4 and _F(mapScore) < _F(maxSw) * ratio):
+        n = 0; flags &= ~1; mapScore = 0
+    return n, flags, mapScore, subi
+
+
+def test_clearzone3_by_hand(oracle):
+    cfg = sl.policy_cfg()
+    fl = np.zeros(1, sl.READ_OUT_DTYPE); fl["flags"] = sl.F_MAPPED
+    # cz3v2 = 800*min(1.25, 9970/9000) = 886.22 -> CLEARZONE3 886; the runner-up 100 below gives f = 786/886.22, sub = 1.8*(f+2f^2+2f^3) = 6.94,
+    # sub2 = 886*(7*sub/(sub+7)) = 3087.6 -> every score drops by 3088; 5912 is still above (int)(9970*.56f) = 5583
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=9000, slow_score=9000), dict(chrom=1, start=500, score=8900, slow_score=8900, paired_score=9100)])
+    L2, n2, out = oracle.sitelist_clearzone3(lists, nss, ro, fl, cfg)
+    assert out["best_sites"][0] == 3088 and out["near_perfect"][0] == 5912 and out["flags"][0] == sl.F_MAPPED and n2[0] == 2
+    assert list(L2[0, :2]["slow_score"]) == [5912, 5812] and list(L2[0, :2]["score"]) == [5912, 5812] and L2[0, 1]["paired_score"] == 5812 + 200
+    # runner-up a full clearzone below, a single site, an ambiguous read: untouched
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=9000, slow_score=9000), dict(chrom=1, start=500, score=8100, slow_score=8100)])
+    assert oracle.sitelist_clearzone3(lists, nss, ro, fl, cfg)[2]["best_sites"][0] == 0
+    fa = fl.copy(); fa["flags"] = sl.F_MAPPED | sl.F_AMBIGUOUS
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=9000, slow_score=9000), dict(chrom=1, start=500, score=8990, slow_score=8990)])
+    L2, n2, out = oracle.sitelist_clearzone3(lists, nss, ro, fa, cfg)
+    assert out["best_sites"][0] == 0 and n2[0] == 2 and out["flags"][0] == sl.F_MAPPED | sl.F_AMBIGUOUS
+    assert oracle.sitelist_clearzone3(lists, nss, ro, fa, cfg, ambiguous_toss=True)[1][0] == 0
+    # a tie close to the ratio gate: the subtraction is capped at mapScore-300, the read turns ambiguous and stays mapped
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=5700, slow_score=5700), dict(chrom=1, start=500, score=5700, slow_score=5700),
+                          dict(chrom=1, start=900, score=5690, slow_score=5690)])
+    L2, n2, out = oracle.sitelist_clearzone3(lists, nss, ro, fl, cfg)
+    exp = _py_clearzone3(lists[0].copy(), 3, 100, sl.F_MAPPED, cfg)
+    assert (int(n2[0]), int(out["flags"][0]), int(out["near_perfect"][0]), int(out["best_sites"][0])) == exp
+    assert out["flags"][0] == sl.F_MAPPED | sl.F_AMBIGUOUS and out["best_sites"][0] > 0 and out["near_perfect"][0] >= 300
+    # CLEARZONE3 not above CLEARZONE1/P: only the ratio gate acts (5500 < 5583.2 -> unmapped)
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=5500, slow_score=5500)])
+    L2, n2, out = oracle.sitelist_clearzone3(lists, nss, ro, fl, sl.policy_cfg(clearzone3=100))
+    assert n2[0] == 0 and out["flags"][0] == 0 and out["near_perfect"][0] == 0
+
+
+def test_clearzone3_against_numpy_restatement(oracle):
+    cfg = sl.policy_cfg()
+    lists, nss, ro = random_lists(nreads=1500, cap=12, seed=77, after_alignment=True)
+    lists, nss, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    L2, n2, out = oracle.sitelist_clearzone3(lists, nss, ro, fl, cfg)
+    changed = 0
+    for r in range(len(nss)):
+        v = lists[r].copy()
+        exp = _py_clearzone3(v, int(nss[r]), int(ro[r + 1] - ro[r]), int(fl["flags"][r]), cfg)
+        assert (int(n2[r]), int(out["flags"][r]), int(out["near_perfect"][r]), int(out["best_sites"][r])) == exp, r
+        if exp[0]:
+            assert v[:exp[0]].tobytes() == L2[r, :exp[0]].tobytes(), r
+        changed += exp[3] > 0
+    assert changed > 50
+
+
+def test_tip_penalty_by_hand(oracle):
+    fl = np.zeros(1, sl.READ_OUT_DTYPE); fl["flags"] = sl.F_MAPPED
+    lists, nss, ro = _mk([dict(chrom=1, start=1, score=9000, slow_score=9000), dict(chrom=1, start=500, score=8000, slow_score=8000)])
+    bases = np.frombuffer((b"ACGT" * 25), np.int8)
+    enc = lambda s: (np.frombuffer(s.encode(), np.int8), np.array([0, len(s)], np.int64))
+    # one substitution at read position 3: 2*(7+2-3) = 12 points -> (int)((80*12/92)*.0022f*9970) = 228
+    m, mo = enc("mmmSmmmm" + "m" * 92)
+    L2, pen, st = oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, fl)
+    assert pen[0] == 228 and st[0] == 0 and list(L2[0, :2]["score"]) == [8772, 7772] and list(L2[0, :2]["slow_score"]) == [8772, 7772]
+    # all matches: nothing; a deletion run counts once (2*(9-2) = 14), an N costs half (9-0 = 9) at the far tip
+    m, mo = enc("m" * 100)
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, fl)[1][0] == 0
+    m, mo = enc("mmDDDmm" + "m" * 95 + "N")
+    pts = 14 + 9
+    exp = int((_F(80) * _F(pts)) / (_F(pts) + _F(80)) * _F(.0022) * _F(9970))
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, fl)[1][0] == exp
+    # homopolymer tips: AAAAAC... adds 3 points at the left, ...GTTT adds 1 at the right
+    hb = np.frombuffer(b"AAAAAC" + b"ACGT" * 22 + b"ACGTTT", np.int8)
+    m, mo = enc("m" * 100)
+    exp = int((_F(80) * _F(4)) / (_F(4) + _F(80)) * _F(.0022) * _F(9970))
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, hb, m, mo, fl)[1][0] == exp
+    # capped at mapScore - maxScore/10; unmapped, no match string, short format, truncated string
+    low, nl, _ = _mk([dict(chrom=1, start=1, score=1000, slow_score=1000)])
+    m, mo = enc("SSSSSSSS" + "m" * 92)
+    assert oracle.sitelist_tip_penalty(low, nl, ro, bases, m, mo, fl)[1][0] == 1000 - 997
+    f0 = fl.copy(); f0["flags"] = 0
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, f0)[1][0] == 0
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m[:0], np.array([0, 0], np.int64), fl)[1][0] == 0
+    m, mo = enc("m3S" + "m" * 90)
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, fl)[2][0] == 2
+    m, mo = enc("mmmm")
+    assert oracle.sitelist_tip_penalty(lists, nss, ro, bases, m, mo, fl)[2][0] == 1
