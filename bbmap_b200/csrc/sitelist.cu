@@ -659,6 +659,10 @@ __global__ void __launch_bounds__(128) sitelist_cz3_kernel(Cz3Params P) {
     const int maxSw = max_quality(len);
     const bbm_policy_cfg& cfg = P.cfg;
     int flags = P.io[r].flags, subi = 0;
+    if (n > 1) {                                                         // removeDuplicateBestSites (:1328-1349): copies of the top site at the end of the list
+        const bbm_ss t = v[0];
+        while (n > 1 && t.chrom == v[n - 1].chrom && t.strand == v[n - 1].strand && t.start == v[n - 1].start && t.stop == v[n - 1].stop) n--;
+    }
     if (n == 0) flags &= ~1;
     int mapScore = n > 0 ? v[0].slow_score : 0;
     if ((cfg.clearzone3 > cfg.clearzone1 || cfg.clearzone3 > cfg.clearzonep) && n > 0 && !(flags & 4) && mapScore > 0) {

@@ -381,8 +381,8 @@ int  bbm_sitelist_tipdel_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* d_nss
                              const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_quality, const int8_t* d_refs, const int64_t* d_chrom_off,
                              const int32_t* d_chrom_min_index, const bbm_tipdel_cfg* cfg, bbm_read_out* d_out, void* stream, float* kernel_ms_out);
 
-/* The clearzone-3 block and the final score gate of processRead, after the primary site's match string exists (current/align2/BBMapThread.java:667-684,
- * 698-700; AbstractMapThread.applyClearzone3 :1820-1870, calcCZ3_fraction :1893-1911): the near-ties behind the top site lower every score of the list,
+/* removeDuplicateBestSites (current/align2/AbstractMapThread.java:1328-1349; BBMapThread.java:624-628), then the clearzone-3 block and the final score gate of
+ * processRead, after the primary site's match string exists (BBMapThread.java:667-684, 698-700; AbstractMapThread.applyClearzone3 :1820-1870, calcCZ3_fraction :1893-1911): the near-ties behind the top site lower every score of the list,
  * a read pushed under MINIMUM_ALIGNMENT_SCORE_RATIO becomes ambiguous, AMBIGUOUS_TOSS (ambiguous_toss != 0) and the ratio gate clear the mapping.
  * d_io is in/out: flags as BBM_SL_FINAL left them; afterwards flags updated, near_perfect = r.mapScore (= the top site's slowScore, Read.java:1178),
  * best_sites = the amount subtracted (0: applyClearzone3 returned false). */

@@ -521,6 +521,8 @@ void orc_sitelist_clearzone3(orc_ss* lists, int32_t* nss, int64_t nreads, int32_
         orc_ss* v = lists + r * cap; int n = nss[r];
         const int maxSw = max_quality(read_len[r]);
         int flags = out[r].flags, subi = 0;
+        /* removeDuplicateBestSites (AbstractMapThread.java:1328-1349; processRead :624-628): copies of the top site at the end of the list */
+        while (n > 1 && v[0].chrom == v[n - 1].chrom && v[0].strand == v[n - 1].strand && v[0].start == v[n - 1].start && v[0].stop == v[n - 1].stop) n--;
         if (n == 0) flags &= ~1;
         int mapScore = n > 0 ? v[0].slow_score : 0;
         if ((cfg->clearzone3 > cfg->clearzone1 || cfg->clearzone3 > cfg->clearzonep) && n > 0 && !(flags & 4) && mapScore > 0) {

@@ -164,7 +164,12 @@ def test_clearzone3_parity(oracle, msa, seed):
     lists, nss, ro = random_lists(nreads=6000, cap=16, seed=seed, after_alignment=True)
     for cfg, toss in ((sl.policy_cfg(), False), (sl.policy_cfg(), True), (sl.policy_cfg(clearzone3=150), False), (sl.policy_cfg(min_align_ratio=0.7), False)):
         l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+        for r in range(0, len(n1), 9):                                     # copies of the top site at the tail (removeDuplicateBestSites)
+            k = int(n1[r])
+            if 2 <= k < l1.shape[1] - 1:
+                l1[r, k] = l1[r, 0]; l1[r, k + 1] = l1[r, 0]; l1[r, k + 1]["slow_score"] -= 7; n1[r] = k + 2
         exp = oracle.sitelist_clearzone3(l1, n1, ro, fl, cfg, ambiguous_toss=toss)
+        assert (exp[1] < n1).sum() > 20
         _same(sl.applyClearzone3(msa.h, l1, n1, ro, fl, cfg, ambiguous_toss=toss), exp)
     l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, sl.policy_cfg())
     exp = oracle.sitelist_clearzone3(l1, n1, ro, fl, sl.policy_cfg())
