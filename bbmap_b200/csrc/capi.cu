@@ -1077,6 +1077,23 @@ extern "C" int bbm_sitelist_tip_penalty_dev(bbm_ctx* c, bbm_ss* d_lists, const i
     return BBM_OK;
 }
 
+extern "C" int bbm_launch_sam_tasks_from_lists(const bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const bbm_read_out* flags,
+                                               const long long* match_off, bbm_sam_task* tasks, cudaStream_t st);
+extern "C" int bbm_sam_tasks_from_lists_dev(bbm_ctx* c, const bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                            const bbm_read_out* d_flags, const int64_t* d_match_off, bbm_sam_task* d_tasks, void* stream) {
+    if (!c) return fail(BBM_E_ARG, "bbm_sam_tasks_from_lists_dev: null pointer");
+    if (cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_sam_tasks_from_lists_dev: cap must be in 1..64");
+    if (nreads <= 0) return BBM_OK;
+    if (!d_lists || !d_nss || !d_read_off || !d_flags || !d_tasks) return fail(BBM_E_ARG, "bbm_sam_tasks_from_lists_dev: null pointer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int e = bbm_launch_sam_tasks_from_lists(d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_flags, (const long long*)d_match_off, d_tasks,
+                                            stream ? (cudaStream_t)stream : c->stream);
+    if (e) return fail(BBM_E_CUDA, "sam_tasks_from_lists_kernel launch", (cudaError_t)e);
+    c->launches++;
+    return BBM_OK;
+}
+
 // =====================  scoreSlow in rounds (sitelist.cu kernels + the aligner)  =====================
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,

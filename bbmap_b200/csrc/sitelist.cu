@@ -764,6 +764,30 @@ __global__ void __launch_bounds__(128) sitelist_tip_penalty_kernel(TipPenParams 
     if (P.status) P.status[r] = st;
 }
 
+// Read.setFromTopSite / setFromSite (stream/Read.java:1171-1190, 1213-1224) for an unpaired read, as the record SamLine(Read,int) reads: chrom, strand, start, stop,
+// mapScore = slowScore, perfect = ss.perfect; an empty list is Read.clearSite (:1278-1286).  Gapped top sites keep start/stop (fixGaps only touches the gap array).
+__global__ void __launch_bounds__(128) sam_tasks_from_lists_kernel(const bbm_ss* __restrict__ lists, const int* __restrict__ nss, long long nreads, int cap,
+                                                                   const long long* __restrict__ read_off, const bbm_read_out* __restrict__ flags,
+                                                                   const long long* __restrict__ match_off, bbm_sam_task* __restrict__ tasks) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    bbm_sam_task t;
+    t.match_off = match_off ? match_off[r] : 0;
+    t.match_len = match_off ? (int)(match_off[r + 1] - match_off[r]) : 0;
+    t.read_len = (int)(read_off[r + 1] - read_off[r]);
+    t.mate = -1; t.pad_ = 0;
+    const int f = flags[r].flags;
+    if (nss[r] > 0 && (f & 1)) {
+        const bbm_ss ss = lists[r * cap];
+        t.chrom = ss.chrom; t.start = ss.start; t.stop = ss.stop; t.score = ss.slow_score;
+        t.flags = BBM_RF_MAPPED | (ss.strand ? BBM_RF_MINUS : 0) | (ss.perfect ? BBM_RF_PERFECT : 0) | ((f & 4) ? BBM_RF_AMBIGUOUS : 0);
+    } else {
+        t.chrom = -1; t.start = -1; t.stop = -1; t.score = 0; t.match_len = 0;
+        t.flags = (f & 4) ? BBM_RF_AMBIGUOUS : 0;
+    }
+    tasks[r] = t;
+}
+
 }  // namespace bbm
 
 extern "C" int bbm_launch_sitelist_cz3(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const bbm_policy_cfg* cfg,
@@ -828,5 +852,10 @@ extern "C" int bbm_launch_sitelist_bounds(bbm_ss* lists, int* nss, long long nre
     P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.chrom_max_index = chrom_max_index; P.scaf_off = scaf_off;
     P.scaf_loc = scaf_loc; P.pad = pad; P.sam_out = sam_out; P.expected_len_limit = expected_len_limit; P.out = out;
     bbm::sitelist_bounds_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_launch_sam_tasks_from_lists(const bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off, const bbm_read_out* flags,
+                                               const long long* match_off, bbm_sam_task* tasks, cudaStream_t st) {
+    bbm::sam_tasks_from_lists_kernel<<<(unsigned)((nreads + 127) / 128), 128, 0, st>>>(lists, nss, nreads, cap, read_off, flags, match_off, tasks);
     return (int)cudaGetLastError();
 }

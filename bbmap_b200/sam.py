@@ -59,3 +59,20 @@ def sam_batch(ctx, tasks, match_buf, scaf, cfg=None):
     _lib.check(L.bbm_sam_batch_host(ctx, _p(tasks), len(tasks), _p(mb), mb.size, _p(so), _p(sl), _p(sn), len(so) - 1, _p(cfg), _p(outs), _p(cbuf), _p(coff)),
                "bbm_sam_batch_host")
     return outs, cbuf, coff
+
+
+def tasks_from_lists(lists, nss, read_off, flags, match_off=None):
+    """Read.setFromTopSite for unpaired reads (current/stream/Read.java:1171-1190, 1213-1224; clearSite :1278-1286) in numpy — what
+    bbm_sam_tasks_from_lists_dev builds on the device.  flags: sitelist.READ_OUT_DTYPE[n]."""
+    n = len(nss)
+    t = np.zeros(n, SAM_TASK_DTYPE)
+    top = lists[:, 0]; f = flags["flags"]
+    m = (np.asarray(nss) > 0) & ((f & 1) != 0)
+    t["read_len"] = np.diff(np.asarray(read_off, np.int64)); t["mate"] = -1
+    if match_off is not None:
+        t["match_off"] = np.asarray(match_off, np.int64)[:-1]; t["match_len"] = np.where(m, np.diff(np.asarray(match_off, np.int64)), 0)
+    for k in ("chrom", "start", "stop"):
+        t[k] = np.where(m, top[k], -1)
+    t["score"] = np.where(m, top["slow_score"], 0)
+    t["flags"] = np.where(m, RF_MAPPED | np.where(top["strand"] != 0, RF_MINUS, 0) | np.where(top["perfect"] != 0, RF_PERFECT, 0), 0) | np.where((f & 4) != 0, RF_AMBIGUOUS, 0)
+    return t

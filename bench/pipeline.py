@@ -59,9 +59,11 @@ def cpu_side(R, cb, co, table, n_cpu=20000):
     lists, _, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, runm, sl.slow_cfg())
     lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
     lists, ns, out = o.sitelist_clearzone3(lists, ns, off, out, pcfg)
+    from bbmap_b200 import sam as _sam
+    srec, _, _ = o.sam_batch(_sam.tasks_from_lists(lists, ns, off, out), np.zeros(1, np.int8), scaffold_table(table, len(co) - 1), _sam.default_cfg())
     dt = time.perf_counter() - t0
     return {"reads": m, "cores": 1, "kind": "port", "seconds": dt, "reads_per_s": m / dt, "slow_alignments": int(na),
-            "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy()}
+            "mapped": float(((out["flags"] & sl.F_MAPPED) != 0).mean()), "lists": lists, "nss": ns, "flags": out["flags"].copy(), "sam": srec}
 
 
 def make_reference(genome_len, scaffolds):
@@ -116,6 +118,12 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
     from bbmap_b200.rescue import tipdel_cfg
     scfg = default_cfg(); pcfg = sl.policy_cfg(); wcfg = sl.slow_cfg(); tcfg = tipdel_cfg()
     d_out2 = torch.zeros(n * sl.READ_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    from bbmap_b200 import sam as _sam
+    samcfg = _sam.default_cfg()
+    d_scaf_len = torch.from_numpy(np.ascontiguousarray(_sn, np.int32)).to(dev)
+    d_stasks = torch.zeros(n * _sam.SAM_TASK_DTYPE.itemsize, dtype=torch.uint8, device=dev); d_souts = torch.zeros(n * _sam.SAM_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_nomatch = torch.zeros(16, dtype=torch.int8, device=dev); d_coff = (torch.arange(n + 1, dtype=torch.int64, device=dev) * 12).contiguous()   # 2*match_len+12 per record
+    d_cigar = torch.zeros(12 * n + 16, dtype=torch.int8, device=dev)
     cp = lambda a: a.ctypes.data_as(C.c_void_p)
     ms = C.c_float(0); na = C.c_int64(0)
     t = {}
@@ -156,6 +164,10 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
         step("final", lambda: sitelist(sl.SL_FINAL))
         # processRead :667-700 (in the reference the primary site's match string is generated in between; it is not chained yet)
         step("applyClearzone3", lambda: _lib.check(L.bbm_sitelist_clearzone3_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), cp(pcfg), 0, p(d_out), None), "clearzone3"))
+        # Read.setFromTopSite + SamLine(Read,int): FLAG / POS / MAPQ / RNAME of every read (no match strings yet: CIGAR '*')
+        step("samFields", lambda: (_lib.check(L.bbm_sam_tasks_from_lists_dev(h, p(d_lists), p(d_nss), n, CAP, p(d_off), p(d_out), None, p(d_stasks), None), "sam tasks"),
+                                   _lib.check(L.bbm_sam_batch_dev(h, p(d_stasks), n, p(d_nomatch), p(d_scaf_off), p(d_scaf_loc), p(d_scaf_len), len(co) - 1, cp(samcfg),
+                                                                  p(d_souts), p(d_cigar), p(d_coff), None, None), "sam batch")))
 
     L.bbm_launch_count.restype = C.c_int64
     totals = []
@@ -169,6 +181,7 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
             t.clear(); totals.clear()                                         # first pass is warm-up (allocations inside the library)
     lists = np.frombuffer(d_lists.cpu().numpy().tobytes(), sl.SS_DTYPE).reshape(n, CAP)
     nss = d_nss.cpu().numpy(); out = np.frombuffer(d_out.cpu().numpy().tobytes(), sl.READ_OUT_DTYPE); status = d_status.cpu().numpy()
+    souts = np.frombuffer(d_souts.cpu().numpy().tobytes(), _sam.SAM_OUT_DTYPE)
     tr = R["truth"]; top = lists[:, 0]
     mapped = (out["flags"] & sl.F_MAPPED) != 0
     correct = mapped & (top["chrom"] == tr[:, 0]) & (top["strand"] == tr[:, 1]) & ((np.abs(top["start"] - tr[:, 2]) <= 8) | (np.abs(top["stop"] - tr[:, 3]) <= 8))
@@ -182,13 +195,15 @@ def run(pairs=200_000, genome_len=4_600_000, reps=3, device=0, cpu=True, seed=2,
            "mapped": float(mapped.mean()), "top_site_is_origin": float(correct.mean()), "top_site_exact_start_and_stop": float(exact.mean()),
            "ambiguous": float(((out["flags"] & sl.F_AMBIGUOUS) != 0).mean()), "status_nonzero": int((status != 0).sum()), "status_gapped_site": int(((status & sl.SLOW_GAPPED) != 0).sum()),
            "status_aligner_error": int(((status & sl.SLOW_ALIGNER_ERROR) != 0).sum()),
+           "mean_mapq": float(souts["mapq"][mapped].mean()) if mapped.any() else 0.0,
            "mean_sites_after_final": float(nss.mean()), "reads_lowered_by_clearzone3": float((out["best_sites"] > 0).mean()),
            "tip_deletion_sites_changed": int(np.frombuffer(d_out2.cpu().numpy().tobytes(), sl.READ_OUT_DTYPE)["best_sites"].sum()),
-           "not_chained_yet": "genMatchString/realign_new (and the tip-score penalty that reads its match string), pairing/rescue, SAM text",
+           "not_chained_yet": "genMatchString/realign_new (and the tip-score penalty and CIGAR that read its match string), pairing/rescue, SAM text",
            "timing": "host wall clock around device synchronisation, whole chain, median of %d passes after one warm-up pass" % reps}
     if cpu:
         cs = cpu_side(R, cb, co, table)
-        m = cs["reads"]; cl = cs.pop("lists"); cn = cs.pop("nss"); cf = cs.pop("flags")
+        m = cs["reads"]; cl = cs.pop("lists"); cn = cs.pop("nss"); cf = cs.pop("flags"); csam = cs.pop("sam")
+        cs["device_sam_fields_identical_on_sample"] = bool(souts[:m].tobytes() == csam.tobytes())     # FLAG, POS, MAPQ, RNAME, RNEXT, PNEXT, TLEN, cigar length
         live = np.arange(CAP)[None, :] < cn[:, None]
         same = bool(np.array_equal(cn, nss[:m]) and np.array_equal(cf, out["flags"][:m]) and all(np.array_equal(cl[f][live], lists[:m][f][live]) for f in cl.dtype.names))
         cs["device_chain_identical_on_sample"] = same          # every field of every final site + the read flags, device chain vs CPU chain

@@ -396,6 +396,12 @@ int  bbm_sitelist_tip_penalty_dev(bbm_ctx* ctx, bbm_ss* d_lists, const int32_t* 
                                   const int8_t* d_bases, const int8_t* d_match, const int64_t* d_match_off, const bbm_read_out* d_flags,
                                   int32_t tiplen, int32_t* d_penalty, int32_t* d_status, void* stream);
 
+/* Read.setFromTopSite / setFromSite (current/stream/Read.java:1171-1190, 1213-1224; processRead :557) for unpaired reads: the top site of every list becomes the
+ * record bbm_sam_batch_* reads (chrom, strand, start, stop, mapScore = slowScore, perfect = ss.perfect, ambiguous from d_flags); an empty list or a cleared
+ * mapping gives Read.clearSite (:1278-1286).  d_match_off (nreads+1 entries, may be NULL = no match strings yet, CIGAR '*') places read r's match string. */
+int  bbm_sam_tasks_from_lists_dev(bbm_ctx* ctx, const bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
+                                  const bbm_read_out* d_flags, const int64_t* d_match_off, bbm_sam_task* d_tasks, void* stream);
+
 /* ---- BBMapThread.scoreSlow over a batch of reads, in rounds (current/align2/BBMapThread.java:252-386; part of SURVEY 8f.1) ----
  * Round k slow-aligns the k-th site of every read whose run[r] != 0 (processRead calls scoreSlow when scoreNoIndels found no
  * near-perfect site, :463-465): preamble, MSA.fillAndScoreLimited(bases, ss, SLOW_ALIGN_PADDING, max(slowScore, minMsaLimit)), the

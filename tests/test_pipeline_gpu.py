@@ -17,6 +17,7 @@ def test_chain_identical_to_cpu_chain(genome_len, scaffolds, pairs, floor):
     import pipeline
     res = pipeline.run(pairs=pairs, genome_len=genome_len, reps=1, device=0, cpu=True, scaffolds=scaffolds)
     cs = res["cpu_baseline"]
-    assert cs["reads"] == 2 * pairs and cs["device_chain_identical_on_sample"]
+    assert cs["reads"] == 2 * pairs and cs["device_chain_identical_on_sample"] and cs["device_sam_fields_identical_on_sample"]
+    assert res["mean_mapq"] > 20
     assert res["mapped"] > floor and res["top_site_is_origin"] > floor - 0.03 and res["status_nonzero"] == 0
     assert res["slow_alignments"] == cs["slow_alignments"] > pairs
