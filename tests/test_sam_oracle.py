@@ -61,3 +61,26 @@ def test_invariants(oracle):
                 q, r = cigar_stats(_cig(cbuf, coff, outs, i))
                 assert q == t["read_len"], (i, _cig(cbuf, coff, outs, i))       # SamLine.java:744: cigarlen == bases.length
         assert ncig > 3000
+
+
+def test_tasks_from_lists_by_hand(oracle):
+    """Read.setFromTopSite / clearSite (stream/Read.java:1171-1190, 1213-1224, 1278-1286) as bbmap_b200.sam.tasks_from_lists states them, and the
+    records SamLine makes of them: a plus-strand read, a minus-strand perfect read, an ambiguous read, an empty list, a cleared mapping."""
+    from bbmap_b200 import sitelist as sl
+    lists = np.zeros((5, 3), sl.SS_DTYPE); nss = np.array([2, 1, 1, 0, 1], np.int32); ro = np.arange(6, dtype=np.int64) * 100
+    fl = np.zeros(5, sl.READ_OUT_DTYPE); fl["flags"] = [1, 1 | 2, 1 | 4, 0, 0]
+    for r, (st, strand, perfect, slow) in enumerate([(8100, 0, 0, 9000), (8200, 1, 1, 9970), (8300, 0, 0, 7000), (0, 0, 0, 0), (8400, 1, 0, 6000)]):
+        lists[r, 0]["chrom"] = 1; lists[r, 0]["start"] = st; lists[r, 0]["stop"] = st + 99; lists[r, 0]["strand"] = strand
+        lists[r, 0]["perfect"] = perfect; lists[r, 0]["slow_score"] = slow; lists[r, 0]["score"] = slow + 5       # mapScore is the slow score
+    lists[0, 1] = lists[0, 0]; lists[0, 1]["start"] = 20000                                                        # only the top site counts
+    t = sam.tasks_from_lists(lists, nss, ro, fl)
+    assert list(t["flags"]) == [sam.RF_MAPPED, sam.RF_MAPPED | sam.RF_MINUS | sam.RF_PERFECT, sam.RF_MAPPED | sam.RF_AMBIGUOUS, 0, 0]
+    assert list(t["chrom"]) == [1, 1, 1, -1, -1] and list(t["start"]) == [8100, 8200, 8300, -1, -1] and list(t["stop"]) == [8199, 8299, 8399, -1, -1]
+    assert list(t["score"]) == [9000, 9970, 7000, 0, 0] and (t["mate"] == -1).all() and (t["read_len"] == 100).all() and (t["match_len"] == 0).all()
+    mo = np.arange(6, dtype=np.int64) * 104
+    t2 = sam.tasks_from_lists(lists, nss, ro, fl, mo)
+    assert list(t2["match_len"]) == [104, 104, 104, 0, 0] and list(t2["match_off"]) == [0, 104, 208, 312, 416]
+    scaf = sam.scaffold_table([(1, 8000, 5000)], 1)
+    out, _, _ = oracle.sam_batch(t, np.zeros(1, np.int8), scaf, sam.default_cfg())
+    assert list(out["flag"]) == [0, 16, 0, 4, 4] and list(out["pos"][:3]) == [101, 201, 301] and (out["cigar_len"] == -1).all()
+    assert out["mapq"][1] > out["mapq"][0] > out["mapq"][2] and list(out["scaffold"]) == [0, 0, 0, -1, -1]
