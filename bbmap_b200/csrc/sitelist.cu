@@ -171,7 +171,7 @@ __device__ int merge_duplicate_sites(bbm_ss* v, int n) {
                 else takeB = false;
                 if (takeB) { a.ngaps = b.ngaps; for (int g = 0; g < BBM_MAX_GAPS - 1; g++) a.gaps[g] = b.gaps[g]; }
             }
-            a.slow_score = imax(a.slow_score, b.slow_score);
+            set_slow_score(a, imax(a.slow_score, b.slow_score));          // a.setSlowScore(max(...)) moves a positive pairedScore first (Tools.java:733)
             a.paired_score = (a.paired_score <= a.slow_score && b.paired_score <= a.slow_score) ? 0 : imax(0, imax(a.paired_score, b.paired_score));
             a.score = imax(a.score, b.score);
             a.perfect = (a.perfect || b.perfect) ? 1 : 0; a.semiperfect = (a.semiperfect || b.semiperfect) ? 1 : 0;

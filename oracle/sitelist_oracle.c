@@ -277,7 +277,7 @@ static int merge_duplicate_sites(orc_ss* v, int n) {
     for (int i = 1; i < n; i++) {
         orc_ss* a = &v[ai]; orc_ss* b = &v[i];
         if (positional_match(a, b, 1)) {
-            a->slow_score = imax(a->slow_score, b->slow_score);
+            orc_ss_set_slow_score(a, imax(a->slow_score, b->slow_score));
             a->paired_score = (a->paired_score <= a->slow_score && b->paired_score <= a->slow_score) ? 0 : max3i(0, a->paired_score, b->paired_score);
             a->score = imax(a->score, b->score);
             a->perfect = (a->perfect || b->perfect); a->semiperfect = (a->semiperfect || b->semiperfect);
@@ -289,7 +289,7 @@ static int merge_duplicate_sites(orc_ss* v, int n) {
             else if (a->paired_score != b->paired_score) better = (a->paired_score > b->paired_score ? a : b);
             else better = a;
             const int bg = better->ngaps; int g[ORC_MAX_GAPS]; memcpy(g, better->gaps, sizeof(better->gaps));
-            a->slow_score = imax(a->slow_score, b->slow_score);
+            orc_ss_set_slow_score(a, imax(a->slow_score, b->slow_score));
             a->paired_score = (a->paired_score <= a->slow_score && b->paired_score <= a->slow_score) ? 0 : max3i(0, a->paired_score, b->paired_score);
             a->score = imax(a->score, b->score);
             a->perfect = (a->perfect || b->perfect); a->semiperfect = (a->semiperfect || b->semiperfect);

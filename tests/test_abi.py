@@ -41,7 +41,7 @@ def test_exports(lib):
     for n in names + JNI_SYMBOLS:
         assert hasattr(lib, n), "libbbmapcuda.so does not export %s" % n
     from bbmap_b200 import lib as L
-    assert set(L.EXPORTS) <= set(names)
+    assert set(L.EXPORTS) == set(names), sorted(set(names) ^ set(L.EXPORTS))      # every declared entry point has ctypes argtypes
 
 
 def test_no_cpu_fallback(lib):
