@@ -142,6 +142,9 @@ struct bbm_ctx {
     DevBuf d_ing[5];   // staging for bbm_ingest_batch_host
     DevBuf grefPool, grefInfo, grefTasks, d_gtasks, d_gaps;   // gapped references (a15)   // staging for the host-buffer entry point
     PinBuf h_stage;
+    // the batched mapper (capi_mapper.cu): working buffers of the chain, scaffold table, staging of the host entry point
+    DevBuf mapBuf[48], mapScaf[6], mapHost[8];
+    int map_nchroms = 0, map_nscaf = 0, map_maxidx_for = -1; bool map_has_names = false; long long map_last_cs = 0, map_last_ms = 0;
     std::vector<void*> uploads;
     long long launches = 0;
     std::mutex mu;

@@ -422,6 +422,63 @@ int  bbm_scoreslow_host(bbm_ctx* ctx, bbm_ss* lists, const int32_t* nss, int64_t
                         const int8_t* basesP, const int8_t* basesM, const int8_t* d_refs, const int64_t* chrom_off, int32_t nchroms,
                         const int32_t* run, const bbm_slow_cfg* cfg, int32_t* status, int64_t* alignments_out);
 
+
+/* ---- the batched mapper: BBMapThread.processRead / processReadPair over a batch of reads, FASTQ-shaped bytes in, SAM records out ----
+ * (current/align2/BBMapThread.java:389-733, 943-1362; AbstractMapThread.quickMap :643-755; genMatchString :860-1068;
+ *  TranslateColorspaceRead.realign_new :229-660; SamLine(Read,int) stream/SamLine.java:82-410, toBytes :1925-1960).
+ * One call chains every device stage with all intermediates resident: Read.validate -> KeyRing seeds -> BBIndex.find -> removeOutOfBounds ->
+ * trimList -> scoreNoIndels -> findTipDeletions -> scoreSlow (rounds) -> final list policy -> genMatchString / realign_new (rounds) ->
+ * removeDuplicateBestSites, clearzone 3, toLocalAlignment for X/Y/C tips, score gates, tip-score penalty -> SamLine fields, CIGAR, SAM text.
+ * Needs the index (bbm_index_build) and the scaffold table (bbm_map_set_scaffolds) in the context. */
+#define BBM_MAP_ST_MATCH_OVERFLOW  1   /* a match string did not fit its slot */
+#define BBM_MAP_ST_TIP             2   /* calcTipScorePenalty ran off the match string (the reference would throw) */
+#define BBM_MAP_ST_SLOTS           4   /* more than 3 sites of one read needed a match string at the same time */
+#define BBM_MAP_ST_ALIGNER         8   /* the aligner reported a per-task error (shape outside 601 x 3000) */
+#define BBM_MAP_ST_SITE_OVERFLOW  16   /* BBIndex.find emitted more sites than the mapper's site slots (the reference keeps an unbounded list) */
+#define BBM_MAP_ST_SLOW           32   /* scoreSlow reported a status bit for this read */
+typedef struct {                /* 80 bytes; defaults in bbmap_b200/mapper.py */
+    int32_t paired;             /* reads 2i / 2i+1 are mates (processReadPair) */
+    float min_ratio, min_ratio_paired, min_ratio_pre_rescue, secondary_site_score_ratio;   /* MINIMUM_ALIGNMENT_SCORE_RATIO* (AbstractMapThread.java:104-107) */
+    int32_t slow_align_padding, max_indel, ambiguous_toss, penalize_ambig;
+    int32_t average_pair_dist, max_pair_dist, max_rescue_dist, max_rescue_mismatches;
+    int32_t do_rescue, kill_bad_pairs, require_correct_strands, same_strand_pairs;
+    int32_t pad_[3];
+} bbm_map_cfg;
+typedef struct {                /* 48 bytes: the Read fields SamLine(Read,int) reads, as the mapper leaves them */
+    int32_t chrom, start, stop, strand, map_score;
+    int32_t flags;              /* bit0 mapped, bit1 perfect, bit2 ambiguous, bit3 paired, bit4 rescued, bit5 discarded */
+    int32_t match_len, cz3_sub, tip_penalty;
+    int32_t status;             /* BBM_MAP_ST_* */
+    int32_t match_slot, pad_;
+} bbm_map_rec;
+typedef struct {                /* every switch of the chain in one record */
+    bbm_map_cfg map; bbm_seed_cfg seed; bbm_policy_cfg policy; bbm_slow_cfg slow; bbm_tipdel_cfg tip; bbm_sam_cfg sam;
+    int32_t ingest_flags;       /* BBM_ING_* */
+    int32_t max_keys;           /* seed slots per read (32) */
+    int32_t max_sites;          /* site slots per read for BBIndex.find = list capacity (16; raised automatically up to 64 when a read overflows) */
+    int32_t sam_text;           /* 1 = also format SAM lines */
+} bbm_mapper_cfg;
+typedef struct {                /* what a call did (host) */
+    int64_t reads, mapped, slow_alignments, realign_fills, site_overflow_reads, status_reads, sam_bytes;
+    int32_t max_sites_used, genmatch_rounds;
+    float ms_total, ms_seed_search, ms_lists, ms_slow, ms_genmatch, ms_sam;
+    int32_t pad_[2];
+} bbm_map_stats;
+/* Scaffold table (bbm_sam_batch_* layout, host arrays) + scaffold names for RNAME (names_buf/name_off with nscaffolds+1 offsets; may be NULL: "*"). */
+int  bbm_map_set_scaffolds(bbm_ctx* ctx, const int32_t* scaf_off, const int32_t* scaf_loc, const int32_t* scaf_len, int32_t nchroms,
+                           const int8_t* names_buf, const int64_t* name_off);
+/* Everything resident.  d_bases / d_quality are validated in place (Read.validate); d_quality may be NULL (FASTA).  Outputs: d_recs[nreads],
+ * d_sam[nreads], the primary match strings at d_match + r * match_stride (may be NULL).  Buffers must be readable 16 bytes past their end. */
+int  bbm_map_batch_dev(bbm_ctx* ctx, int8_t* d_bases, int8_t* d_quality, const int64_t* d_read_off, int64_t nreads, int32_t max_read_len,
+                       const bbm_mapper_cfg* cfg, bbm_map_rec* d_recs, bbm_sam_out* d_sam, int8_t* d_match, int64_t match_stride,
+                       void* stream, bbm_map_stats* stats);
+/* The reference-facing call: host buffers in (FASTQ-shaped: bases, phred qualities or NULL, offsets, read names or NULL), host buffers out
+ * (records, SamLine fields, primary match strings, and — with cfg->sam_text — the SAM lines: sam_text/sam_off[nreads+1], capacity sam_cap bytes;
+ * BBM_E_CAPACITY with *sam_bytes_needed set when too small).  bases/quality are not modified. */
+int  bbm_map_batch_host(bbm_ctx* ctx, const int8_t* bases, const int8_t* quality, const int64_t* read_off, int64_t nreads,
+                        const int8_t* names, const int64_t* name_off, const bbm_mapper_cfg* cfg, bbm_map_rec* recs, bbm_sam_out* sam,
+                        int8_t* match, int64_t match_stride, int8_t* sam_text, int64_t sam_cap, int64_t* sam_off, bbm_map_stats* stats);
+
 /* ---- 1:1 twins of the reference's plain C entry points (single alignment; latency path) ----
  * Same argument meaning as jni/MultiStateAligner11tsJNI.c:100-114 / :361-382.  `packed` (host, 3*(maxRows+1)*(maxColumns+1)
  * ints) receives exactly the cells the reference would have written (values included), so Java's score2/traceback2

@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY — the whole mapping chain through the CPU oracle (C restatements in liborc.so, the reference's own C for the fills
+when oracle/_ref exists is NOT used here: the chain calls the port, which tests/test_oracle_vs_reference.py pins to the reference's C).
+
+    Read.validate -> quickMap (KeyRing, BBIndex.find, removeOutOfBounds) -> trimList -> scoreNoIndels -> findTipDeletions -> scoreSlow ->
+    final list policy -> genMatchString / realign_new -> clearzone 3 / toLocalAlignment / score gates / tip penalty -> SamLine fields
+
+Used by tests/ (the checker of bbm_map_batch_*) and by bench.py's cpu_baseline / --impl reference legs."""
+import numpy as np
+
+from bbmap_b200 import mapper as mp, sitelist as sl
+from bbmap_b200.keyring import default_cfg
+from bbmap_b200.rescue import tipdel_cfg
+from bbmap_b200.sam import scaffold_table, default_cfg as sam_default_cfg, SAM_TASK_DTYPE
+
+MAXK = 32
+
+
+def match_stride(max_len):
+    return 2 * int(max_len) + 128
+
+
+def search_to_lists(res, cap):
+    m = len(res["nsites"])
+    ns = np.minimum(res["nsites"], cap).astype(np.int32)
+    lists = np.zeros((m, cap), sl.SS_DTYPE); S = res["sites"][:, :cap]
+    for f in ("chrom", "start", "stop", "hits", "score", "strand", "perfect", "semiperfect", "ngaps", "gaps"):
+        lists[f] = S[f]
+    lists["quick_score"] = S["score"]
+    return lists, ns
+
+
+def map_single(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=None, sam_cfg=None, ingest_flags=0):
+    """Unpaired reads.  idx = o.index_build(cb, co, 13, -1).  Returns a dict with the final lists, the read records, match strings, SAM
+    fields and CIGAR text."""
+    pcfg = sl.policy_cfg() if pcfg is None else pcfg
+    mcfg = mp.map_cfg() if mcfg is None else mcfg
+    scfg = sam_default_cfg() if sam_cfg is None else sam_cfg
+    off = np.ascontiguousarray(off, np.int64); n = len(off) - 1
+    nb = int(off[-1])
+    bases, qual, basesM, rflags = o.ingest_batch(bases[:nb], None if qual is None else qual[:nb], off, ingest_flags)
+    seeds = o.seed_batch(bases, qual, off, default_cfg(), MAXK)
+    res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=True)     # AbstractIndex.QUIT_AFTER_TWO_PERFECTS, single-ended
+    overflow = int(((res["status"] & 2) != 0).sum() + (res["nsites"] > cap).sum())
+    lists, ns = search_to_lists(res, cap)
+    scaf = scaffold_table(table, len(co) - 1)
+    maxidx = (np.diff(np.asarray(co, np.int64)) - 1).astype(np.int32)
+    lists, ns, _ = o.sitelist_bounds(lists, ns, off, maxidx, scaf)
+    lists, ns, _ = o.sitelist(sl.SL_TRIM, lists, ns, off, pcfg)
+    lists, ns, out = o.sitelist(sl.SL_NOINDEL, lists, ns, off, pcfg, bases, basesM, cb, co)
+    runm = (out["near_perfect"] < 1).astype(np.int32)
+    lists, _ = o.sitelist_tipdel(lists, ns * runm, off, bases, basesM, qual, cb, co, tipdel_cfg())
+    lists, slow_status, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, runm, sl.slow_cfg())
+    lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
+    ms = match_stride(int(np.diff(off).max()) if n else 1)
+    lists, ns, recs, match, fills = o.map_finish_single(lists, ns, off, bases, basesM, cb, co, out, pcfg, mcfg, ms)
+    recs["flags"] |= np.where(seeds["nkeys"] < 0, 32, 0).astype(np.int32)          # quickMap < 0: r.setDiscarded(true)
+    tasks = sam_tasks(recs, off, ms)
+    srec, cig, cig_off = o.sam_batch(tasks, match, scaf, scfg)
+    return {"lists": lists, "nss": ns, "recs": recs, "match": match, "match_stride": ms, "sam": srec, "cigar": cig, "cigar_off": cig_off,
+            "slow_alignments": int(na), "realign_fills": int(fills), "site_overflow": overflow, "discarded": (seeds["nkeys"] < 0), "bases": bases, "basesM": basesM,
+            "qual": qual}
+
+
+def sam_tasks(recs, off, ms, mate=None):
+    """Read fields -> the record SamLine(Read,int) reads (bbm_sam_task)."""
+    n = len(recs)
+    t = np.zeros(n, SAM_TASK_DTYPE)
+    t["match_off"] = np.arange(n, dtype=np.int64) * ms
+    t["match_len"] = recs["match_len"]
+    t["chrom"] = recs["chrom"]; t["start"] = recs["start"]; t["stop"] = recs["stop"]
+    t["read_len"] = np.diff(off).astype(np.int32)
+    t["score"] = recs["map_score"]
+    t["mate"] = -1 if mate is None else mate
+    f = recs["flags"]
+    t["flags"] = ((f & 1) * 1) | (np.where((recs["strand"] == 1) & ((f & 1) != 0), 2, 0)) | (np.where(f & 2, 4, 0)) | (np.where(f & 4, 8, 0)) | (np.where(f & 32, 32, 0)) | (np.where(f & 8, 64, 0))
+    return t

@@ -1,0 +1,24 @@
+/* TEST INFRASTRUCTURE ONLY — see mapper_oracle.c (the tail of BBMapThread.processRead / processReadPair, sequential restatement). */
+#ifndef MAPPER_ORACLE_H
+#define MAPPER_ORACLE_H
+#include <stdint.h>
+#include "sitelist_oracle.h"
+#define ORC_MAP_ST_MATCH_OVERFLOW 1   /* a match string did not fit the caller's slot */
+#define ORC_MAP_ST_TIP            2   /* calcTipScorePenalty ran off the match string (the reference would throw) */
+typedef struct {            /* == bbm_map_cfg (include/bbmap_cuda.h) */
+    int32_t paired;                     /* reads 2i / 2i+1 are mates */
+    float min_ratio, min_ratio_paired, min_ratio_pre_rescue, secondary_site_score_ratio;
+    int32_t slow_align_padding, max_indel, ambiguous_toss, penalize_ambig;
+    int32_t average_pair_dist, max_pair_dist, max_rescue_dist, max_rescue_mismatches;
+    int32_t do_rescue, kill_bad_pairs, require_correct_strands, same_strand_pairs;
+    int32_t pad_[3];
+} orc_map_cfg;
+typedef struct {            /* == bbm_map_rec: the Read fields SamLine(Read,int) reads, 48 bytes */
+    int32_t chrom, start, stop, strand, map_score, flags;     /* flags: bit0 mapped, bit1 perfect, bit2 ambiguous, bit3 paired, bit4 rescued, bit5 discarded */
+    int32_t match_len, cz3_sub, tip_penalty, status, pad_[2];
+} orc_map_rec;
+int orc_score_match(const int8_t* match, int n);
+int64_t orc_map_finish_single(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
+                              const int8_t* refs, const int64_t* chrom_off, const orc_policy_cfg* pc, const orc_map_cfg* cfg, const orc_read_out* flags_in,
+                              orc_map_rec* recs, int8_t* match_buf, int64_t match_stride);
+#endif

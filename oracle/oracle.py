@@ -327,6 +327,21 @@ class Oracle:
         na = self.lib.orc_score_slow(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), _p(ro), _p(rf), _p(co), _p(rn), _p(cfg), _p(status))
         return lists, status, na
 
+    def map_finish_single(self, lists, nss, read_off, basesP, basesM, refs, chrom_off, flags, pcfg, mcfg, match_stride):
+        """Tail of processRead (match string of the primary site ... tip penalty) for every read; see mapper_oracle.c."""
+        from bbmap_b200.sitelist import READ_OUT_DTYPE, SS_DTYPE
+        from bbmap_b200.mapper import MAP_REC_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); co = np.ascontiguousarray(chrom_off, np.int64)
+        bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8); rf = np.ascontiguousarray(refs).view(np.int8)
+        ff = np.ascontiguousarray(flags, READ_OUT_DTYPE)
+        recs = np.zeros(n, MAP_REC_DTYPE); match = np.zeros(n * match_stride + 16, np.int8)
+        self.lib.orc_map_finish_single.restype = C.c_int64
+        fills = self.lib.orc_map_finish_single(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), _p(ro), _p(rf), _p(co), _p(pcfg), _p(mcfg),
+                                               _p(ff), _p(recs), _p(match), C.c_int64(match_stride))
+        return lists, nss, recs, match, fills
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)
