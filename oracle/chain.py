@@ -74,3 +74,71 @@ def sam_tasks(recs, off, ms, mate=None):
     f = recs["flags"]
     t["flags"] = ((f & 1) * 1) | (np.where((recs["strand"] == 1) & ((f & 1) != 0), 2, 0)) | (np.where(f & 2, 4, 0)) | (np.where(f & 4, 8, 0)) | (np.where(f & 32, 32, 0)) | (np.where(f & 8, 64, 0))
     return t
+
+
+def sam_lines(res, off, names=None, scaf_names=None, paired=False, intron_limit=2 ** 31 - 1):
+    """SamLine.toBytes (current/stream/SamLine.java:1925-1960) + makeOptionalTags (:1481-1560, the default NM / AM tags and XT:A:R) for every read of a
+    chain result, in plain Python: QNAME rule of SamLine(Read,int) (:100-112), reverse-complemented SEQ and reversed QUAL for mapped minus-strand lines."""
+    recs, sam, ms = res["recs"], res["sam"], res["match_stride"]
+    bases, basesM, qual = res["bases"], res["basesM"], res["qual"]
+    lines = []
+    for r in range(len(recs)):
+        q, o = recs[r], sam[r]
+        a, b = int(off[r]), int(off[r + 1])
+        if names is None:
+            qname = b"*"
+        else:
+            qname = names[r].replace(b"\t", b"_")
+            if paired and len(qname) > 2 and qname[-1:] in (b"1", b"2") and qname[-2:-1] in (b" ", b"/"):
+                qname = qname[:-2]
+        def sname(i):
+            return b"*" if (i < 0 or scaf_names is None) else scaf_names[i]
+        cig = b"*" if o["cigar_len"] <= 0 else res["cigar"][int(res["cigar_off"][r]):int(res["cigar_off"][r]) + int(o["cigar_len"])].tobytes()
+        rnext = b"*" if o["rnext"] == -1 else (b"=" if o["rnext"] == -2 else sname(int(o["rnext"])))
+        mapped_line = (o["flag"] & 4) == 0; minus = (o["flag"] & 16) != 0
+        L = b - a
+        if L == 0:
+            seq = b"*"; ql = b"*"
+        else:
+            rc = mapped_line and minus
+            seq = (basesM if rc else bases)[a:b].tobytes()
+            if qual is None:
+                ql = b"*"
+            else:
+                qq = qual[a:b].astype(np.int16) + 33
+                ql = bytes((qq[::-1] if rc else qq).astype(np.uint8).tolist())
+        f = [qname, b"%d" % o["flag"], sname(int(o["scaffold"])), b"%d" % o["pos"], b"%d" % o["mapq"], cig, rnext, b"%d" % o["pnext"], b"%d" % o["tlen"], seq, ql]
+        if q["flags"] & 1:
+            if q["flags"] & 4:
+                f.append(b"XT:A:R")
+            if q["flags"] & 2:
+                f.append(b"NM:i:0")
+            elif q["match_len"] > 0:
+                m = res["match"][r * ms:r * ms + int(q["match_len"])].tobytes()
+                import re
+                c = cig.decode() if cig != b"*" else ""
+                lm = re.match(r"^(\d+)S", c); rm = re.search(r"(\d+)S$", c)
+                lo = int(lm.group(1)) if lm else 0; hi = L - (int(rm.group(1)) if rm else 0)
+                nm = 0; dels = 0; cpos = 0
+                for ch in m:
+                    if lo <= cpos < hi:
+                        if ch in b"ISNXY":
+                            nm += 1
+                        if ch == ord("D"):
+                            dels += 1
+                        else:
+                            if dels <= intron_limit:
+                                nm += dels
+                            dels = 0
+                    if ch != ord("D"):
+                        cpos += 1
+                if dels <= intron_limit:
+                    nm += dels
+                f.append(b"NM:i:%d" % nm)
+            am = int(o["mapq"])
+            if paired:
+                mt = recs[r ^ 1]; ml = int(off[(r ^ 1) + 1] - off[r ^ 1])
+                am = min(am, (max(1, int(mt["map_score"]) // ml) if (mt["flags"] & 1) else 0))
+            f.append(b"AM:i:%d" % am)
+        lines.append(b"\t".join(f) + b"\n")
+    return lines

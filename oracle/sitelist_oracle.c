@@ -600,3 +600,11 @@ void orc_sitelist_tip_penalty(orc_ss* lists, const int32_t* nss, int64_t nreads,
         penalty[r] = p; status[r] = st;
     }
 }
+
+/* ---- list primitives for the paired chain (mapper_oracle.c) ---- */
+void orc_sl_sort(orc_ss* v, int n, int positional) { stable_sort(v, n, positional ? ss_pcomp : ss_compare); }
+int orc_sl_trim_below_cutoff(orc_ss* v, int n, int cutoff, int retainPaired, int minS, int maxS) { return trim_below_cutoff(v, n, cutoff, retainPaired, minS, maxS); }
+int orc_sl_trim_list(orc_ss* v, int* n, int retainPaired, int maxScore, int specialCasePerfect, int minS, int maxS) { return trim_list(v, n, retainPaired, maxScore, specialCasePerfect, minS, maxS); }
+int orc_sl_merge_duplicates(orc_ss* v, int n) { return merge_duplicate_sites(v, n); }
+int orc_sl_count_top_scores(const orc_ss* v, int n, int thresh) { return count_top_scores(v, n, thresh); }
+void orc_sl_set_perfect(orc_ss* s, const int8_t* bases, int len, const int8_t* ref, int refLen) { ss_set_perfect(s, bases, len, ref, refLen); }

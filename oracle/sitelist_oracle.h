@@ -40,3 +40,9 @@ void orc_sitelist_clearzone3(orc_ss* lists, int32_t* nss, int64_t nreads, int32_
                              int32_t ambiguous_toss, orc_read_out* out);
 void orc_sitelist_tip_penalty(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int64_t* read_off, const int8_t* bases,
                               const int8_t* match, const int64_t* match_off, const orc_read_out* flags, int32_t tiplen, int32_t* penalty, int32_t* status);
+void orc_sl_sort(orc_ss* v, int n, int positional);
+int orc_sl_trim_below_cutoff(orc_ss* v, int n, int cutoff, int retainPaired, int minS, int maxS);
+int orc_sl_trim_list(orc_ss* v, int* n, int retainPaired, int maxScore, int specialCasePerfect, int minS, int maxS);
+int orc_sl_merge_duplicates(orc_ss* v, int n);
+int orc_sl_count_top_scores(const orc_ss* v, int n, int thresh);
+void orc_sl_set_perfect(orc_ss* s, const int8_t* bases, int len, const int8_t* ref, int refLen);

@@ -55,3 +55,36 @@ def test_map_batch_single_equals_cpu_chain(kind, seed, L):
         assert int(dev["stats"]["realign_fills"]) == ref["realign_fills"] and int(dev["stats"]["slow_alignments"]) == ref["slow_alignments"]
     finally:
         m.close()
+
+
+def test_map_batch_sam_text():
+    """SAM lines (SamLine.toBytes + default tags) of the device chain == the Python restatement over the CPU chain's records; multi-scaffold reference."""
+    from bbmap_b200.mapper import BBMapCUDA, mapper_cfg
+    from oracle import chain, oracle as orc
+    scafs = [wl.random_genome(120_000, seed=21), wl.random_genome(90_000, seed=22), wl.random_genome(60_000, seed=23)]
+    snames = ["chrA some description", "chrB", "scaffold_3"]
+    m = BBMapCUDA(scafs, names=snames)
+    try:
+        R = wl.make_mapping_reads(m.cb, m.co, m.table, 1200, L=150, seed=24, sub_rate=0.02, indel_rate=0.02 / 3)
+        n = len(R["off"]) - 1
+        rng = np.random.Generator(np.random.PCG64(5))
+        R["qual"] = rng.integers(2, 42, size=len(R["qual"])).astype(np.uint8)
+        junk = wl.ACGT[rng.integers(0, 4, size=150 * 40, dtype=np.uint8)]                    # 40 unmappable reads at the end
+        bases = np.concatenate([R["bases"], junk]); qual = np.concatenate([R["qual"], np.full(len(junk), 30, np.uint8)])
+        off = np.arange(n + 41, dtype=np.int64) * 150
+        names = [b"read_%d\tx/1" % i for i in range(n + 40)]
+        nbuf = np.frombuffer(b"".join(names), np.int8).copy(); noff = np.zeros(n + 41, np.int64); np.cumsum([len(x) for x in names], out=noff[1:])
+        o = orc.get()
+        idx = o.index_build(m.cb, m.co, 13, -1)
+        ref = chain.map_single(o, idx, m.cb, m.co, m.table, bases, qual, off)
+        order = sorted(range(len(m.table)), key=lambda i: m.table[i])
+        exp = chain.sam_lines(ref, off, names=names, scaf_names=[snames[i].encode() for i in order])
+        dev = m.map_batch(bases, qual, off, cfg=mapper_cfg(sam_text=True), names=nbuf, name_off=noff, match_stride=ref["match_stride"], sam_cap=sum(len(x) for x in exp) + 64)
+        _compare(dev, ref, n + 40)
+        to = dev["sam_off"]
+        assert int(to[-1]) == sum(len(x) for x in exp) == int(dev["stats"]["sam_bytes"])
+        got = dev["sam_text"][: int(to[-1])].tobytes()
+        assert got == b"".join(exp)
+        assert (ref["recs"]["flags"][n:] & 1).sum() == 0 and (ref["recs"]["flags"][:n] & 1).mean() > 0.97
+    finally:
+        m.close()
