@@ -61,6 +61,32 @@ def map_single(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=
             "qual": qual}
 
 
+def map_pairs(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=None, sam_cfg=None, ingest_flags=0):
+    """Paired reads (reads 2i / 2i+1 are mates): BBMapThread.processReadPair."""
+    pcfg = sl.policy_cfg() if pcfg is None else pcfg
+    mcfg = mp.map_cfg(paired=1) if mcfg is None else mcfg
+    scfg = sam_default_cfg() if sam_cfg is None else sam_cfg
+    off = np.ascontiguousarray(off, np.int64); n = len(off) - 1
+    nb = int(off[-1])
+    bases, qual, basesM, rflags = o.ingest_batch(bases[:nb], None if qual is None else qual[:nb], off, ingest_flags)
+    seeds = o.seed_batch(bases, qual, off, default_cfg(), MAXK)
+    res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=False)    # forced false in paired mode (BBMap.java:434)
+    overflow = int(((res["status"] & 2) != 0).sum() + (res["nsites"] > cap).sum())
+    lists, ns = search_to_lists(res, cap)
+    scaf = scaffold_table(table, len(co) - 1)
+    maxidx = (np.diff(np.asarray(co, np.int64)) - 1).astype(np.int32)
+    lists, ns, _ = o.sitelist_bounds(lists, ns, off, maxidx, scaf)
+    ms = match_stride(int(np.diff(off).max()) if n else 1)
+    wcfg = sl.slow_cfg(paired=1, min_ratio=mcfg["min_ratio"][0], min_ratio_pre_rescue=mcfg["min_ratio_pre_rescue"][0])
+    lists, ns, recs, match, stats = o.map_pairs(lists, ns, off, bases, basesM, qual, cb, co, seeds["nkeys"], pcfg, mcfg, wcfg, tipdel_cfg(), ms)
+    tasks = sam_tasks(recs, off, ms, mate=np.arange(n, dtype=np.int32) ^ 1)
+    tasks["flags"] |= np.where(np.arange(n) & 1, 128, 0).astype(np.int32)
+    srec, cig, cig_off = o.sam_batch(tasks, match, scaf, scfg)
+    return {"lists": lists, "nss": ns, "recs": recs, "match": match, "match_stride": ms, "sam": srec, "cigar": cig, "cigar_off": cig_off,
+            "slow_alignments": int(stats[0]), "realign_fills": int(stats[1]), "rescue_scans": int(stats[2]), "rescue_fills": int(stats[3]), "mated": int(stats[4]),
+            "inner_sum": int(stats[5]), "site_overflow": overflow, "bases": bases, "basesM": basesM, "qual": qual}
+
+
 def sam_tasks(recs, off, ms, mate=None):
     """Read fields -> the record SamLine(Read,int) reads (bbm_sam_task)."""
     n = len(recs)

@@ -756,3 +756,420 @@ int64_t orc_map_finish_single(orc_ss* lists, int32_t* nss, int64_t nreads, int32
     orc_msa_free(C.msa);
     return fills;
 }
+
+/* =====================  paired reads: BBMapThread.processReadPair (current/align2/BBMapThread.java:943-1362)  =====================
+ * pairSiteScoresInitial :736-940, the rescue block :1061-1100 with AbstractMapThread.rescue / slowRescue (:1144-1306), removeLowQualitySitesPaired
+ * (Tools.java:934-958), pairSiteScoresFinal / canPair (AbstractMapThread.java:1919-2170), the paired clearzone rule :1147-1176, Read.isBadPair
+ * (stream/Read.java:1305-1331), genMatchString per mate and the bookkeeping behind it (:1186-1352).  One pair after the other. */
+#include "rescue_oracle.h"
+typedef struct { int32_t paired; float min_ratio, min_ratio_pre_rescue; int32_t clearzone1e, clearzone3, slow_align_padding, extra_padding, expected_len_limit; } orc_slow_cfg2;
+int64_t orc_score_slow_with(orc_msa* msa, orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
+                            const int8_t* refs, const int64_t* chrom_off, const int32_t* run, const orc_slow_cfg2* cfg, int32_t* status);
+
+static int absdif_i(int a, int b) { return a > b ? a - b : b - a; }
+static void pair_dists(const orc_ss* ss1, const orc_ss* ss2, int requireCorrect, int* inner, int* outer) {
+    int plusFirst;
+    if (requireCorrect && ss1->strand != ss2->strand) plusFirst = (ss1->strand == 0);
+    else plusFirst = (ss1->start <= ss2->start);
+    if (plusFirst) { *inner = ss2->start - ss1->stop; *outer = ss2->stop - ss1->start; }
+    else { *inner = ss1->start - ss2->stop; *outer = ss1->stop - ss2->start; }
+}
+
+static int pair_site_scores_initial(orc_ss* a, int* na, int len1, orc_ss* b, int* nb, int len2, const orc_map_cfg* cfg, int maxTrim) {
+    if (*na < 1 || *nb < 1) return 0;
+    orc_sl_sort(a, *na, 1); orc_sl_sort(b, *nb, 1);
+    for (int i = 0; i < *na; i++) a[i].paired_score = 0;
+    for (int i = 0; i < *nb; i++) b[i].paired_score = 0;
+    int maxPaired1 = -1, maxPaired2 = -1, numPerfectPairs = 0;
+    const int ilimit = *na - 1, jlimit = *nb - 1, maxReadLen = imax2(len1, len2);
+    const int outerDistLimit = (maxReadLen * 14) / 32, innerDistLimit = cfg->max_pair_dist;
+    const int apd = cfg->average_pair_dist, expectedFragLength = apd + len1 + len2;
+    const int sameStrand = cfg->same_strand_pairs, requireCorrect = cfg->require_correct_strands;
+    for (int i = 0, j = 0; i <= ilimit && j <= jlimit; i++) {
+        orc_ss* ss1 = &a[i]; orc_ss* ss2 = &b[j];
+        while (j < jlimit && (ss2->chrom < ss1->chrom || (ss2->chrom == ss1->chrom && ss1->start - ss2->stop > innerDistLimit))) { j++; ss2 = &b[j]; }
+        for (int k = j; k <= jlimit; k++) {
+            ss2 = &b[k];
+            if (ss2->chrom > ss1->chrom) break;
+            if (ss2->start - ss1->stop > innerDistLimit) break;
+            int innerdist, outerdist;
+            pair_dists(ss1, ss2, requireCorrect, &innerdist, &outerdist);
+            if (outerdist >= outerDistLimit && innerdist <= innerDistLimit) {
+                const int strandOK = ((ss1->strand == ss2->strand) == (sameStrand != 0));
+                if (strandOK || !requireCorrect) {
+                    int paired1 = 0, paired2 = 0;
+                    const int deviation = absdif_i(apd, innerdist);
+                    int ps1, ps2;
+                    if (strandOK) {
+                        ps1 = ss1->score + 1 + imax2(1, ss2->score / 2 - ((deviation * ss2->score) / (32 * expectedFragLength + 100)));
+                        ps2 = ss2->score + 1 + imax2(1, ss1->score / 2 - ((deviation * ss1->score) / (32 * expectedFragLength + 100)));
+                    } else { ps1 = ss1->score + imax2(0, ss2->score / 16); ps2 = ss2->score + imax2(0, ss1->score / 16); }
+                    if (ps1 > ss1->paired_score) { paired1 = 1; ss1->paired_score = imax2(ss1->paired_score, ps1); maxPaired1 = imax2(ss1->score, maxPaired1); }
+                    if (ps2 > ss2->paired_score) { paired2 = 1; ss2->paired_score = imax2(ss2->paired_score, ps2); maxPaired2 = imax2(ss2->score, maxPaired2); }
+                    if (paired1 && paired2 && outerdist >= maxReadLen && deviation <= expectedFragLength && ss1->perfect && ss2->perfect) numPerfectPairs++;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < *na; i++) if (a[i].paired_score > a[i].score) a[i].score = a[i].paired_score;
+    for (int i = 0; i < *nb; i++) if (b[i].paired_score > b[i].score) b[i].score = b[i].paired_score;
+    if (numPerfectPairs > 0) {
+        *na = orc_sl_trim_below_cutoff(a, *na, (int)((float)maxPaired1 * .94f), 0, 1, maxTrim);
+        *nb = orc_sl_trim_below_cutoff(b, *nb, (int)((float)maxPaired2 * .94f), 0, 1, maxTrim);
+    } else {
+        if (*na > 4) *na = orc_sl_trim_below_cutoff(a, *na, (int)((float)maxPaired1 * .9f), 1, 1, maxTrim);
+        if (*nb > 4) *nb = orc_sl_trim_below_cutoff(b, *nb, (int)((float)maxPaired2 * .9f), 1, 1, maxTrim);
+    }
+    return numPerfectPairs;
+}
+
+static void pair_site_scores_final(orc_ss* a, int* na, int len1, orc_ss* b, int* nb, int len2, const orc_map_cfg* cfg, int maxTrim) {
+    for (int i = 0; i < *na; i++) a[i].paired_score = 0;
+    for (int i = 0; i < *nb; i++) b[i].paired_score = 0;
+    if (*na < 1 || *nb < 1) return;
+    orc_sl_sort(a, *na, 1); orc_sl_sort(b, *nb, 1);
+    int maxPaired1 = -1, maxPaired2 = -1;
+    const float q1 = (float)len1 / (4.f * (float)len2), q2 = (float)len2 / (4.f * (float)len1);
+    const float mult1 = (0.5f < ((0.25f > q1) ? 0.25f : q1)) ? 0.5f : ((0.25f > q1) ? 0.25f : q1);
+    const float mult2 = (0.5f < ((0.25f > q2) ? 0.25f : q2)) ? 0.5f : ((0.25f > q2) ? 0.25f : q2);
+    const int ilimit = *na - 1, jlimit = *nb - 1;
+    const int outerDistLimit = (imax2(len1, len2) * 14) / 32, MPD = cfg->max_pair_dist, apd = cfg->average_pair_dist;
+    const int expectedFragLength = apd + len1 + len2;
+    const int sameStrand = cfg->same_strand_pairs, requireCorrect = cfg->require_correct_strands;
+    for (int i = 0, j = 0; i <= ilimit && j <= jlimit; i++) {
+        orc_ss* ss1 = &a[i]; orc_ss* ss2 = &b[j];
+        while (j < jlimit && (ss2->chrom < ss1->chrom || (ss2->chrom == ss1->chrom && ss1->start - ss2->stop > MPD))) { j++; ss2 = &b[j]; }
+        for (int k = j; k <= jlimit; k++) {
+            ss2 = &b[k];
+            if (ss2->chrom > ss1->chrom) break;
+            if (ss2->start - ss1->stop > MPD) break;
+            int innerdist, outerdist;
+            pair_dists(ss1, ss2, requireCorrect, &innerdist, &outerdist);
+            if (outerdist >= outerDistLimit && innerdist <= MPD) {
+                const int strandOK = ((ss1->strand == ss2->strand) == (sameStrand != 0));
+                if (strandOK || !requireCorrect) {
+                    const int deviation = absdif_i(apd, innerdist);
+                    int ps1, ps2;
+                    if (strandOK) {
+                        const int den = imax2(100, 10 * expectedFragLength + 100);
+                        ps1 = ss1->score + 1 + imax2(1, (int)((float)ss2->score * mult1) - ((deviation * ss2->score) / den));
+                        ps2 = ss2->score + 1 + imax2(1, (int)((float)ss1->score * mult2) - ((deviation * ss1->score) / den));
+                    } else { ps1 = ss1->score + ss2->score / 16; ps2 = ss2->score + ss1->score / 16; }
+                    ss1->paired_score = imax2(ss1->paired_score, ps1);
+                    ss2->paired_score = imax2(ss2->paired_score, ps2);
+                    maxPaired1 = imax2(ss1->score, maxPaired1);
+                    maxPaired2 = imax2(ss2->score, maxPaired2);
+                }
+            }
+        }
+    }
+    for (int i = 0; i < *na; i++) if (a[i].paired_score > a[i].score) a[i].score = a[i].paired_score;
+    for (int i = 0; i < *nb; i++) if (b[i].paired_score > b[i].score) b[i].score = b[i].paired_score;
+    const float f = cfg->secondary_site_score_ratio < 0.95f ? cfg->secondary_site_score_ratio : 0.95f;
+    *na = orc_sl_trim_below_cutoff(a, *na, (int)((float)maxPaired1 * f), 0, 1, maxTrim);
+    *nb = orc_sl_trim_below_cutoff(b, *nb, (int)((float)maxPaired2 * f), 0, 1, maxTrim);
+}
+
+static int can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, const orc_map_cfg* cfg) {
+    if (ss1->chrom != ss2->chrom) return 0;
+    if (cfg->require_correct_strands) { const int strandOK = ((ss1->strand == ss2->strand) == (cfg->same_strand_pairs != 0)); if (!strandOK) return 0; }
+    const int outerDistLimit = (imax2(len1, len2) * 14) / 32;
+    int inner, outer;
+    pair_dists(ss1, ss2, cfg->require_correct_strands, &inner, &outer);
+    return outer >= outerDistLimit && inner <= cfg->max_pair_dist;
+}
+
+/* Tools.removeLowQualitySitesPaired */
+static int remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) {
+    if (n == 0) return 0;
+    const int th = (int)((float)maxSw * multSingle), thp = (int)((float)maxSw * multPaired);
+    if (v[0].score < thp) return 0;
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        const int dead = (v[i].paired_score > 0) ? (v[i].slow_score < thp) : (v[i].slow_score < th);
+        if (!dead) v[k++] = v[i];
+    }
+    return k;
+}
+
+typedef struct { int64_t rescue_scans, rescue_fills; } pstats;
+
+/* AbstractMapThread.rescue(anchor, loose, basesP, basesM, searchDist) */
+static void rescue_dir(mctx* C, orc_ss* A, int nA, int lenA, orc_ss* L, int* nL, int cap, const int8_t* basesP, const int8_t* basesM, const int8_t* qualL, int lenL,
+                       int searchDist, const orc_tipdel_cfg* tc, int clearzone1e, pstats* ps, int* status)
+{
+    const orc_map_cfg* cfg = C->cfg;
+    if (searchDist > cfg->max_rescue_dist) return;
+    if (nA == 0) return;
+    const int maxLooseSw = 70 + (lenL - 1) * 100, maxAnchorSw = 70 + (lenA - 1) * 100, maxImperfect = maxLooseSw + imin2(-472, -395 - 100);
+    const int bestLoose = (*nL == 0) ? 0 : L[0].slow_score, bestAnchor = A[0].slow_score;
+    if (bestLoose == maxLooseSw && bestAnchor == maxAnchorSw && A[0].paired_score > 0) return;
+    const int rescueScoreLimit = (int)(0.95f * (float)bestAnchor);
+    const int retainScoreLimit = imax2((int)(0.68f * (float)bestLoose), (int)(0.4f * (float)maxLooseSw));
+    const int retainScoreLimit2 = imax2((int)(0.95f * (float)bestLoose), (int)(0.55f * (float)maxLooseSw));
+    const int maxMismatches = (bestLoose > maxImperfect) ? 5 : imin2(cfg->max_rescue_mismatches, (int)(0.60f * (float)lenL - 1.f));
+    const int findTip = bestLoose < maxImperfect;
+    int findRight = findTip, findLeft = findTip;
+    if (findTip && qualL) {
+        const int T = tc->max_tiplen;
+        int minL = 0, avgL = 0, minF = 0, avgF = 0;
+        if (T <= lenL) {
+            int x = 0; minL = qualL[lenL - T];
+            for (int i = lenL - T; i < lenL; i++) { const int b = qualL[i]; x += (b < 0 ? 0 : b); if (b < minL) minL = b; }
+            avgL = x / T;
+            x = 0; minF = qualL[0];
+            for (int i = 0; i < T; i++) { const int b = qualL[i]; x += (b < 0 ? 0 : b); if (i >= 1 && b < minF) minF = b; }
+            avgF = x / T;
+        }
+        findRight = (minL >= 6 && avgL >= 14); findLeft = (minF >= 6 && avgF >= 14);
+    }
+    const orc_rescue_cfg rc = {70, 100, 1, 100};
+    const int n0 = nA;
+    for (int ia = 0; ia < n0; ia++) {
+        orc_ss* ssa = &A[ia];
+        if (ssa->slow_score < rescueScoreLimit) break;
+        if (!(ssa->paired_score == 0 && !ssa->rescued)) continue;
+        const int searchIntoAnchor = ssa->stop - ssa->start - 1 + (lenA * 11 / 16);
+        int loc, idealStart; const int8_t* bases;
+        const int8_t strand = (int8_t)(cfg->same_strand_pairs ? ssa->strand : (ssa->strand ^ 1));
+        const int searchRight = cfg->same_strand_pairs ? (strand == 0) : (strand == 1);
+        if (cfg->same_strand_pairs) {
+            if (ssa->strand == 1) { bases = basesM; loc = ssa->start + searchIntoAnchor; idealStart = ssa->start - cfg->average_pair_dist; }
+            else { bases = basesP; loc = ssa->stop - searchIntoAnchor; idealStart = ssa->stop + cfg->average_pair_dist; }
+        } else {
+            if (ssa->strand == 0) { bases = basesM; loc = ssa->stop - searchIntoAnchor; idealStart = ssa->stop + cfg->average_pair_dist; }
+            else { bases = basesP; loc = ssa->start + searchIntoAnchor; idealStart = ssa->start - cfg->average_pair_dist; }
+        }
+        int refLen; const int8_t* ref = chrom_ptr(C, ssa->chrom, &refLen);
+        orc_rescue_task T; memset(&T, 0, sizeof T);
+        T.read_off = 0; T.ref_off = 0; T.read_len = lenL; T.ref_len = refLen; T.min_index = 0; T.max_index = refLen - 1; T.loc = loc;
+        T.search_dist = searchDist + searchIntoAnchor; T.ideal_start = idealStart; T.max_mismatches = maxMismatches; T.flags = searchRight ? 1 : 0;
+        orc_rescue_out O;
+        orc_rescue_batch(bases, ref, &T, 1, &rc, &O);
+        ps->rescue_scans++;
+        if (O.start < 0 || !O.in_bounds) continue;
+        const int mismatches = O.mismatches;
+        if (mismatches > maxMismatches) continue;
+        orc_ss ss; memset(&ss, 0, sizeof ss);
+        ss.chrom = ssa->chrom; ss.strand = strand; ss.start = O.start; ss.stop = O.stop; ss.hits = 0; ss.quick_score = O.score; ss.score = O.score;
+        ss.perfect = (O.perfect & 1) ? 1 : 0; ss.semiperfect = (O.perfect & 2) ? 1 : 0; ss.rescued = 1;
+        ss.slow_score = 0; ss.paired_score = 0;           /* setSlowScore(minMismatches) then setSlowScore(0): pairedScore ends at 0 */
+        /* slowRescue(bases, ss, maxLooseSwScore, maxImperfectScore, findRight, findLeft) */
+        {
+            int sw = orc_score_no_indels(bases, lenL, ref, refLen, ss.start, 0);
+            const int oldStart = ss.start;
+            if (sw < maxImperfect && cfg->max_indel > 0) {
+                orc_ss_set_slow_score(&ss, sw);
+                if (findRight || findLeft) {
+                    orc_tipdel_task tt; memset(&tt, 0, sizeof tt);
+                    tt.read_len = lenL; tt.ref_len = refLen; tt.min_index = 0; tt.start = ss.start; tt.stop = ss.stop; tt.slow_score = ss.slow_score; tt.max_imperfect = maxImperfect;
+                    tt.flags = (findRight ? 1 : 0) | (findLeft ? 2 : 0);
+                    orc_tipdel_out to;
+                    orc_tipdel_batch(bases, ref, &tt, 1, tc, &to);
+                    if (to.right > 0 || to.left > 0) {
+                        if (to.right > 0) orc_ss_set_stop(&ss, to.stop);
+                        if (to.left > 0) orc_ss_set_start(&ss, to.start);
+                        sw = orc_score_no_indels(bases, lenL, ref, refLen, ss.start, 0);
+                    }
+                }
+                const int minMsaLimit = -clearzone1e + (int)(cfg->min_ratio_paired * (float)maxLooseSw);
+                const int minscore = imax2(sw, minMsaLimit);
+                int32_t max4[4], arr[8];
+                const int n8 = orc_msa_fillAndScoreLimited(C->msa, bases, lenL, ref, refLen, ss.start - tc->slow_rescue_padding, ss.stop + tc->slow_rescue_padding, minscore, 0, 0, max4, arr);
+                ps->rescue_fills++;
+                if (n8 > 0) { orc_ss_set_slow_score(&ss, arr[0]); ss.score = ss.slow_score; orc_ss_set_start(&ss, arr[1]); orc_ss_set_stop(&ss, arr[2]); }
+                else { orc_ss_set_slow_score(&ss, sw); ss.score = ss.slow_score; orc_ss_set_start(&ss, oldStart); orc_ss_set_stop(&ss, ss.start + lenL - 1); }
+            } else { orc_ss_set_slow_score(&ss, sw); ss.score = ss.slow_score; orc_ss_set_stop(&ss, ss.start + lenL - 1); }
+            ss.paired_score = ss.score + 1;
+            ss.perfect = (ss.slow_score == maxLooseSw);
+            if (ss.perfect) ss.semiperfect = 1; else orc_sl_set_perfect(&ss, bases, lenL, ref, refLen);
+        }
+        const int inb = (ss.start >= 0 && ss.stop <= refLen - 1);
+        if (ss.score > retainScoreLimit && inb) {
+            if (ss.score > retainScoreLimit2) {
+                ss.paired_score = imax2(ss.paired_score, ss.slow_score + ssa->slow_score / 4);
+                ssa->paired_score = imax2(ssa->paired_score, ssa->slow_score + ss.slow_score / 4);
+            }
+            if (*nL < cap) { L[*nL] = ss; (*nL)++; } else *status |= ORC_MAP_ST_LIST_OVERFLOW;
+        }
+    }
+}
+
+static int paired_clearzone(const orc_ss* top, int perfect, int maxSw, const orc_policy_cfg* pc) {
+    if (perfect) return pc->clearzonep;
+    if (top->score >= (int)((float)maxSw * pc->cz1b_scale - pc->cz1b_flat)) return pc->clearzone1;
+    if (top->score >= (int)((float)maxSw * pc->cz1c_scale - pc->cz1c_flat)) return pc->clearzone1b;
+    return pc->clearzone1c;
+}
+
+/* Read.isBadPair(requireCorrectStrands, sameStrandPairs, maxdist) */
+static int is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) {
+    if (r->flags & 8) return 0;
+    if (!(r->flags & 1) || !(m->flags & 1)) return 0;
+    if (r->chrom != m->chrom) return 1;
+    { const int inner = (r->start <= m->start) ? (m->start - r->stop) : (r->start - m->stop); if (inner > cfg->max_pair_dist) return 1; }
+    if (cfg->require_correct_strands && ((r->strand == m->strand) != (cfg->same_strand_pairs != 0))) return 1;
+    if (!cfg->same_strand_pairs) {
+        if (r->strand == 0 && m->strand == 1) { if (r->start >= m->stop) return 1; }
+        else if (r->strand == 1 && m->strand == 0) { if (m->start >= r->stop) return 1; }
+    }
+    return 0;
+}
+
+static void set_from_top(orc_map_rec* q, const orc_ss* v, int n) {       /* Read.setFromTopSite (ambig=best): clearSite / setFromSite */
+    if (n == 0) { q->chrom = -1; q->strand = 0; q->start = -1; q->stop = -1; q->map_score = 0; q->flags &= ~(1 | 16); return; }
+    q->flags |= 1;
+    q->chrom = v[0].chrom; q->strand = v[0].strand; q->start = v[0].start; q->stop = v[0].stop; q->map_score = v[0].slow_score;
+    q->flags = (q->flags & ~(2 | 16)) | (v[0].perfect ? 2 : 0) | (v[0].rescued ? 16 : 0);
+}
+static void clear_mapping(orc_map_rec* q, orc_map_rec* mate, int* n) {   /* Read.clearMapping */
+    q->chrom = -1; q->strand = 0; q->start = -1; q->stop = -1; q->map_score = 0; q->match_len = 0;
+    *n = 0; q->flags &= ~(1 | 8); mate->flags &= ~8;
+}
+
+int64_t orc_map_pairs(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
+                      const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* nkeys, const orc_policy_cfg* pc,
+                      const orc_map_cfg* cfg, const void* slow_cfg, const orc_tipdel_cfg* tc, orc_map_rec* recs, int8_t* match_buf, int64_t match_stride,
+                      int64_t* stats /* [8]: slow alignments, realign fills, rescue scans, rescue fills, mated pairs, inner length sum */)
+{
+    mctx C; memset(&C, 0, sizeof C);
+    C.msa = orc_msa_new(601, 3000); C.cfg = cfg; C.refs = refs; C.chrom_off = chrom_off;
+    const orc_slow_cfg2* sc = (const orc_slow_cfg2*)slow_cfg;
+    msite* mv = (msite*)calloc((size_t)cap, sizeof(msite));
+    pstats ps = {0, 0};
+    int64_t slowAl = 0, mated = 0, innerSum = 0;
+    const int maxTrim = pc->max_trim_sites_to_retain;
+    for (int64_t p = 0; p + 1 < nreads; p += 2) {
+        orc_ss* v[2] = { lists + p * cap, lists + (p + 1) * cap };
+        int n[2] = { nss[p], nss[p + 1] };
+        int len[2], maxSw[2], st[2] = {0, 0};
+        const int8_t* bP[2]; const int8_t* bM[2]; const int8_t* ql[2];
+        orc_map_rec* q[2] = { &recs[p], &recs[p + 1] };
+        for (int e = 0; e < 2; e++) {
+            len[e] = (int)(read_off[p + e + 1] - read_off[p + e]); maxSw[e] = 70 + (len[e] - 1) * 100;
+            bP[e] = basesP + read_off[p + e]; bM[e] = basesM + read_off[p + e]; ql[e] = quality ? quality + read_off[p + e] : 0;
+            memset(q[e], 0, sizeof(orc_map_rec)); q[e]->chrom = -1; q[e]->start = -1; q[e]->stop = -1;
+        }
+        if (nkeys[p] < 0 && nkeys[p + 1] < 0) { q[0]->flags |= 32; q[1]->flags |= 32; nss[p] = 0; nss[p + 1] = 0; continue; }
+        pair_site_scores_initial(v[0], &n[0], len[0], v[1], &n[1], len[1], cfg, maxTrim);
+        for (int e = 0; e < 2; e++) {
+            if (n[e] > 2) orc_sl_sort(v[e], n[e], 0);
+            orc_sl_trim_list(v[e], &n[e], 1, maxSw[e], 0, 2, maxTrim);
+        }
+        for (int e = 0; e < 2; e++) for (int i = 0; i < n[e]; i++) v[e][i].score = v[e][i].quick_score;
+        for (int e = 0; e < 2; e++) {
+            if (n[e] <= 0) continue;
+            orc_read_out ro; int32_t nn = n[e]; int32_t one = 1;
+            orc_sitelist_noindel(v[e], &nn, 1, cap, basesP, basesM, read_off + p + e, refs, chrom_off, pc, &ro);      /* scoreNoIndels + Collections.sort */
+            if (ro.near_perfect < 1) { orc_read_out r2; orc_sitelist_tipdel(v[e], &nn, 1, cap, basesP, basesM, quality, read_off + p + e, refs, chrom_off, 0, tc, &r2); }
+            int32_t sst = 0;
+            slowAl += orc_score_slow_with(C.msa, v[e], &nn, 1, cap, basesP, basesM, read_off + p + e, refs, chrom_off, &one, sc, &sst);
+            if (sst) st[e] |= ORC_MAP_ST_SLOW;
+            n[e] = orc_sl_merge_duplicates(v[e], nn);
+        }
+        if (cfg->do_rescue) {
+            int unpaired[2] = {0, 0};
+            for (int e = 0; e < 2; e++) for (int i = 0; i < n[e]; i++) if (v[e][i].paired_score == 0) unpaired[e]++;
+            const int searchDist = imin2(cfg->max_pair_dist, 2 * cfg->average_pair_dist + 100);
+            for (int e = 0; e < 2; e++) {
+                const int o = e ^ 1;
+                if (unpaired[e] > 0 && n[e] > 0) {
+                    orc_sl_sort(v[e], n[e], 0);
+                    n[e] = remove_low_quality_paired(v[e], n[e], maxSw[e], cfg->min_ratio_pre_rescue, cfg->min_ratio_pre_rescue);
+                    rescue_dir(&C, v[e], n[e], len[e], v[o], &n[o], cap, bP[o], bM[o], ql[o], len[o], searchDist, tc, sc->clearzone1e, &ps, &st[o]);
+                    n[o] = orc_sl_merge_duplicates(v[o], n[o]);
+                }
+            }
+        }
+        for (int e = 0; e < 2; e++) if (n[e] > 1) orc_sl_sort(v[e], n[e], 0);
+        for (int e = 0; e < 2; e++) n[e] = remove_low_quality_paired(v[e], n[e], maxSw[e], cfg->min_ratio, cfg->min_ratio_paired);
+        pair_site_scores_final(v[0], &n[0], len[0], v[1], &n[1], len[1], cfg, maxTrim);
+        for (int e = 0; e < 2; e++) if (n[e] > 0) orc_sl_sort(v[e], n[e], 0);
+        int perfect[2], ambiguous[2] = {0, 0};
+        for (int e = 0; e < 2; e++) {
+            perfect[e] = n[e] > 0 && (v[e][0].slow_score == maxSw[e] || v[e][0].perfect);       /* Read.setPerfectFlag, match == null */
+            if (n[e] > 1) {
+                const int cz = paired_clearzone(&v[e][0], perfect[e], maxSw[e], pc);
+                if (orc_sl_count_top_scores(v[e], n[e], cz) > 1) ambiguous[e] = 1;                 /* processAmbiguous(..., AMBIGUOUS_TOSS=false) keeps the list */
+            }
+        }
+        int paired = 0;
+        if (n[0] > 0 && n[1] > 0 && can_pair(&v[0][0], &v[1][0], len[0], len[1], cfg)) paired = 1;
+        for (int e = 0; e < 2; e++) {
+            q[e]->flags = (perfect[e] ? 2 : 0) | (ambiguous[e] ? 4 : 0) | (paired ? 8 : 0);
+            set_from_top(q[e], v[e], n[e]);
+        }
+        if (cfg->kill_bad_pairs && is_bad_pair(q[0], q[1], cfg)) {
+            const int x = q[0]->map_score / len[0], y = q[1]->map_score / len[1];
+            const int k = (x >= y) ? 1 : 0;                   /* clearAnswers(false) on the weaker mate */
+            q[k]->chrom = -1; q[k]->strand = 0; q[k]->start = -1; q[k]->stop = -1; q[k]->map_score = 0; q[k]->flags = 0; n[k] = 0;
+        }
+        /* genMatchString per mate (setSSScore = false) */
+        int slotlen[2] = {0, 0};
+        for (int e = 0; e < 2; e++) {
+            if (n[e] <= 0) continue;
+            for (int i = 0; i < n[e]; i++) { mv[i].s = v[e][i]; mv[i].match = NULL; mv[i].mlen = 0; mv[i].serial = i; mv[i].s.has_match = 0; }
+            int pflag = (q[e]->flags & 8) ? 1 : 0; const int pflag0 = pflag;
+            C.status = 0;
+            gen_match_string(&C, mv, &n[e], bP[e], bM[e], len[e], maxSw[e], 0, &pflag);
+            st[e] |= C.status;
+            if (pflag0 && !pflag) { q[0]->flags &= ~8; q[1]->flags &= ~8; }
+            /* r.start ... r.mapScore = top site (:944-953) */
+            q[e]->start = mv[0].s.start; q[e]->stop = mv[0].s.stop; q[e]->chrom = mv[0].s.chrom; q[e]->strand = mv[0].s.strand; q[e]->map_score = mv[0].s.slow_score;
+            q[e]->flags = (q[e]->flags & ~(2 | 16)) | (mv[0].s.perfect ? 2 : 0) | (mv[0].s.rescued ? 16 : 0);
+            int8_t* mo = match_buf + (p + e) * match_stride;
+            if (mv[0].match && mv[0].mlen <= match_stride) { memcpy(mo, mv[0].match, (size_t)mv[0].mlen); slotlen[e] = mv[0].mlen; }
+            else if (mv[0].match) st[e] |= ORC_MAP_ST_MATCH_OVERFLOW;
+            for (int i = 0; i < n[e]; i++) { v[e][i] = mv[i].s; v[e][i].has_match = mv[i].match ? 1 : 0; if (mv[i].match && i > 0) { free(mv[i].match); mv[i].match = NULL; } }
+            /* keep the top site's string in mv[0] for toLocalAlignment below: stash it per mate */
+            if (e == 0) { q[0]->pad_[0] = 0; }
+            q[e]->match_len = slotlen[e];
+            if (mv[0].match) { free(mv[0].match); mv[0].match = NULL; }
+        }
+        /* anomaly blocks (:1228-1253) */
+        for (int e = 0; e < 2; e++) {
+            const int o = e ^ 1;
+            if (q[e]->map_score > 0 && n[e] == 0) clear_mapping(q[e], q[o], &n[e]);
+            else if (q[e]->map_score <= 0 && n[e] > 0) clear_mapping(q[e], q[o], &n[e]);
+        }
+        for (int e = 0; e < 2; e++) if (n[e] > 1) {         /* removeDuplicateBestSites */
+            const orc_ss* t = &v[e][0];
+            while (n[e] > 1 && t->chrom == v[e][n[e] - 1].chrom && t->strand == v[e][n[e] - 1].strand && t->start == v[e][n[e] - 1].start && t->stop == v[e][n[e] - 1].stop) n[e]--;
+        }
+        for (int e = 0; e < 2; e++) if ((q[e]->flags & 4) && cfg->ambiguous_toss) {
+            n[e] = 0; q[e]->chrom = -1; q[e]->strand = 0; q[e]->start = -1; q[e]->stop = -1; q[e]->map_score = 0; q[e]->flags &= ~(1 | 8); q[e ^ 1]->flags &= ~8; q[e]->match_len = 0;
+        }
+        for (int e = 0; e < 2; e++) {                        /* toLocalAlignment for X/Y/C tips */
+            if (!(q[e]->flags & 1) || n[e] == 0 || q[e]->match_len < 1) continue;
+            int8_t* mo = match_buf + (p + e) * match_stride;
+            const int8_t a = mo[0], b = mo[q[e]->match_len - 1];
+            if (!(a == 'X' || b == 'Y' || a == 'C' || b == 'C')) continue;
+            msite top; top.s = v[e][0]; top.match = NULL; top.mlen = 0; top.serial = 0;
+            set_match(&top, mo, q[e]->match_len);
+            int f2 = q[e]->flags & 7, rs = q[e]->start, rp = q[e]->stop, msc = q[e]->map_score;
+            to_local_alignment(&C, &top, v[e][0].strand == 0 ? bP[e] : bM[e], len[e], 1, &rs, &rp, &msc, &f2, 0);
+            if (f2 & 256) clear_mapping(q[e], q[e ^ 1], &n[e]);
+            else {
+                v[e][0] = top.s; v[e][0].has_match = 1;
+                q[e]->start = rs; q[e]->stop = rp; q[e]->map_score = msc; q[e]->flags = (q[e]->flags & ~7) | (f2 & 7);
+                if (top.mlen <= match_stride) { memcpy(mo, top.match, (size_t)top.mlen); q[e]->match_len = top.mlen; } else { st[e] |= ORC_MAP_ST_MATCH_OVERFLOW; q[e]->match_len = 0; }
+            }
+            free(top.match);
+        }
+        for (int e = 0; e < 2; e++) {
+            if (!(q[e]->flags & 1) || n[e] == 0) { q[e]->chrom = -1; q[e]->strand = 0; q[e]->start = -1; q[e]->stop = -1; q[e]->match_len = 0; if (!(q[e]->flags & 1)) q[e]->map_score = 0; }
+            q[e]->status = st[e];
+            if (nkeys[p + e] < 0) q[e]->flags |= 32;
+            nss[p + e] = n[e];
+        }
+        if ((q[0]->flags & 8) && (q[0]->flags & 1)) {        /* calcStatistics1: numMated, innerLengthSum */
+            int inner = (q[0]->start <= q[1]->start) ? (q[1]->start - q[0]->stop) : (q[0]->start - q[1]->stop);
+            inner = imin2(cfg->max_pair_dist, inner); inner = imax2(-160, inner);
+            mated++; innerSum += inner;
+        }
+    }
+    free(mv);
+    if (stats) { stats[0] = slowAl; stats[1] = C.fills; stats[2] = ps.rescue_scans; stats[3] = ps.rescue_fills; stats[4] = mated; stats[5] = innerSum; }
+    orc_msa_free(C.msa);
+    return mated;
+}

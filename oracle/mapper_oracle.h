@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include "sitelist_oracle.h"
 #define ORC_MAP_ST_MATCH_OVERFLOW 1   /* a match string did not fit the caller's slot */
-#define ORC_MAP_ST_TIP            2   /* calcTipScorePenalty ran off the match string (the reference would throw) */
+#define ORC_MAP_ST_TIP            2
+#define ORC_MAP_ST_SLOW           32
+#define ORC_MAP_ST_LIST_OVERFLOW  64  /* a rescued site did not fit the list */   /* calcTipScorePenalty ran off the match string (the reference would throw) */
 typedef struct {            /* == bbm_map_cfg (include/bbmap_cuda.h) */
     int32_t paired;                     /* reads 2i / 2i+1 are mates */
     float min_ratio, min_ratio_paired, min_ratio_pre_rescue, secondary_site_score_ratio;
@@ -21,4 +23,8 @@ int orc_score_match(const int8_t* match, int n);
 int64_t orc_map_finish_single(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
                               const int8_t* refs, const int64_t* chrom_off, const orc_policy_cfg* pc, const orc_map_cfg* cfg, const orc_read_out* flags_in,
                               orc_map_rec* recs, int8_t* match_buf, int64_t match_stride);
+int64_t orc_map_pairs(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
+                      const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* nkeys, const orc_policy_cfg* pc,
+                      const orc_map_cfg* cfg, const void* slow_cfg, const orc_tipdel_cfg* tc, orc_map_rec* recs, int8_t* match_buf, int64_t match_stride,
+                      int64_t* stats);
 #endif

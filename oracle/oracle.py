@@ -342,6 +342,22 @@ class Oracle:
                                                _p(ff), _p(recs), _p(match), C.c_int64(match_stride))
         return lists, nss, recs, match, fills
 
+    def map_pairs(self, lists, nss, read_off, basesP, basesM, quality, refs, chrom_off, nkeys, pcfg, mcfg, scfg, tcfg, match_stride):
+        """processReadPair after quickMap for every pair (reads 2i / 2i+1); see mapper_oracle.c."""
+        from bbmap_b200.sitelist import SS_DTYPE
+        from bbmap_b200.mapper import MAP_REC_DTYPE
+        lists = np.ascontiguousarray(lists, SS_DTYPE).copy(); nss = np.ascontiguousarray(nss, np.int32).copy()
+        n, cap = lists.shape
+        ro = np.ascontiguousarray(read_off, np.int64); co = np.ascontiguousarray(chrom_off, np.int64)
+        bp = np.ascontiguousarray(basesP).view(np.int8); bm = np.ascontiguousarray(basesM).view(np.int8); rf = np.ascontiguousarray(refs).view(np.int8)
+        q = None if quality is None else np.ascontiguousarray(quality).view(np.int8)
+        nk = np.ascontiguousarray(nkeys, np.int32)
+        recs = np.zeros(n, MAP_REC_DTYPE); match = np.zeros(n * match_stride + 16, np.int8); stats = np.zeros(8, np.int64)
+        self.lib.orc_map_pairs.restype = C.c_int64
+        self.lib.orc_map_pairs(_p(lists), _p(nss), C.c_int64(n), C.c_int32(cap), _p(bp), _p(bm), None if q is None else _p(q), _p(ro), _p(rf), _p(co), _p(nk), _p(pcfg),
+                               _p(mcfg), _p(scfg), _p(tcfg), _p(recs), _p(match), C.c_int64(match_stride), _p(stats))
+        return lists, nss, recs, match, stats
+
     # ---------------- scoreNoIndels ----------------
     def noindel_batch(self, reads, refs, tasks, match_off=None):
         reads = np.ascontiguousarray(reads).view(np.int8); refs = np.ascontiguousarray(refs).view(np.int8)

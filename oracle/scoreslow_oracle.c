@@ -33,10 +33,9 @@ static void set_perfect(orc_ss* s, const int8_t* bases, int len, const int8_t* r
     s->perfect = (int8_t)perfect; s->semiperfect = (int8_t)semiperfect;
 }
 
-int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
-                       const int8_t* refs, const int64_t* chrom_off, const int32_t* run, const orc_slow_cfg* cfg, int32_t* status)
+int64_t orc_score_slow_with(orc_msa* msa, orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
+                            const int8_t* refs, const int64_t* chrom_off, const int32_t* run, const orc_slow_cfg* cfg, int32_t* status)
 {
-    orc_msa* msa = orc_msa_new(601, 3000);
     int64_t alignments = 0;
     for (int64_t r = 0; r < nreads; r++) {
         if (status) status[r] = 0;
@@ -81,6 +80,14 @@ int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_
         }
         (void)minMatch;
     }
-    orc_msa_free(msa);
     return alignments;
+}
+
+int64_t orc_score_slow(orc_ss* lists, const int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int64_t* read_off,
+                       const int8_t* refs, const int64_t* chrom_off, const int32_t* run, const orc_slow_cfg* cfg, int32_t* status)
+{
+    orc_msa* msa = orc_msa_new(601, 3000);
+    const int64_t a = orc_score_slow_with(msa, lists, nss, nreads, cap, basesP, basesM, read_off, refs, chrom_off, run, cfg, status);
+    orc_msa_free(msa);
+    return a;
 }
