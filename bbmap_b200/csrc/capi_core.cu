@@ -97,6 +97,7 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
     if (!strcmp(key, "strip_min_tasks")) { c->strip_min_tasks = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
+    if (!strcmp(key, "msa_count")) { c->msa_count = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }
     if (!strcmp(key, "search_split")) { c->search_split = value; return BBM_OK; }
     if (!strcmp(key, "search_profile")) { c->search_prof = value; return BBM_OK; }
@@ -112,6 +113,8 @@ extern "C" int64_t bbm_get_stat(const bbm_ctx* c, const char* key) {
     if (!strcmp(key, "narrow_handed_over")) return c->narrow_handed_over;
     if (!strcmp(key, "tasks_total")) return c->tasks_total;
     if (!strcmp(key, "strip_tasks")) return c->strip_tasks;
+    if (!strcmp(key, "msa_us")) return (int64_t)(c->msa_ms * 1000.0);          // device time of all aligner batches so far (CUDA events)
+    if (!strcmp(key, "msa_cells")) return c->msa_cells;                         // reference cell visits summed while "msa_count" is on
     if (!strcmp(key, "strip_units")) return (int64_t)c->strip_units;            // rows of 8 cells evaluated (with strip_debug bit 2)
     if (!strcmp(key, "strip_lane_iters")) return (int64_t)c->strip_lane_iters;  // lane-iterations of the evaluation phase: units/iters = lane utilisation
     if (!strncmp(key, "search_cycles_", 14) && key[14] >= '0' && key[14] <= '4') return (int64_t)c->search_cycles[key[14] - '0'];   // thread-cycles: total, filter, prescan, walk, extend

@@ -11,7 +11,7 @@ extern "C" int bbm_launch_sitelist(int op, bbm_ss* lists, int* nss, long long nr
 extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, const bbm_site* sites, long long nreads, int maxSites, bbm_ss* lists,
                                                int* nss, int cap, cudaStream_t st);
 static int sitelist_args(int op, int cap, const bbm_policy_cfg* cfg) {
-    if (op != BBM_SL_TRIM && op != BBM_SL_NOINDEL && op != BBM_SL_FINAL) return fail(BBM_E_ARG, "bbm_sitelist: unknown op");
+    if (op != BBM_SL_TRIM && op != BBM_SL_NOINDEL && op != BBM_SL_FINAL && op != BBM_SL_MERGE) return fail(BBM_E_ARG, "bbm_sitelist: unknown op");
     if (cap < 1 || cap > bbm_sitelist_max_cap()) return fail(BBM_E_ARG, "bbm_sitelist: cap must be in 1..64");
     if (!cfg || cfg->min_trim_sites_to_retain < 1 || cfg->max_trim_sites_to_retain <= cfg->min_trim_sites_to_retain) return fail(BBM_E_ARG, "bbm_sitelist: bad policy cfg");
     return BBM_OK;

@@ -17,6 +17,8 @@ extern "C" int bbm_launch_sitelist_tipdel(bbm_ss* lists, const int* nss, long lo
 extern "C" int bbm_launch_sitelist_bounds(bbm_ss* lists, int* nss, long long nreads, int cap, const long long* read_off, const int* chrom_max_index,
                                           const int* scaf_off, const int* scaf_loc, int pad, int sam_out, int expected_len_limit, bbm_read_out* out, cudaStream_t st);
 extern "C" int bbm_sitelist_max_cap();
+extern "C" int bbm_launch_rescue(const int8_t* reads, const int8_t* refs, const bbm_rescue_task* tasks, long long n, const bbm_rescue_cfg* cfg,
+                                 bbm_rescue_out* outs, cudaStream_t st);
 
 namespace {
 struct StageTimer {                 // host wall time per stage (every stage ends in a stream synchronisation or is followed by one)
@@ -25,8 +27,11 @@ struct StageTimer {                 // host wall time per stage (every stage end
 };
 enum { MB_BASESM = 0, MB_RFLAGS, MB_NKEYS, MB_OFFSETS, MB_KEYS, MB_KSCORES, MB_BSCORES, MB_OFFM, MB_KEYSM, MB_HEADS, MB_SITES, MB_LISTS, MB_NSS, MB_OUT, MB_OUT2,
        MB_RUN, MB_MASKED, MB_SLOWST, MB_GMSTATE, MB_MSLOTS, MB_MLEN, MB_TASKS, MB_OUTS, MB_RMATCH, MB_RMOFF, MB_GTASKS, MB_GAPS, MB_GOUTS, MB_GMATCH, MB_GMOFF,
-       MB_COUNTERS, MB_STASKS, MB_CIGAR, MB_CIGOFF, MB_RECS, MB_SAM, MB_TLENS, MB_TNM, MB_TLINEOFF, MB_TSCAN, MB_TEXT, MB_TEXTOFF, MB_COUNT };
+       MB_COUNTERS, MB_STASKS, MB_CIGAR, MB_CIGOFF, MB_RECS, MB_SAM, MB_TLENS, MB_TNM, MB_TLINEOFF, MB_TSCAN, MB_TEXT, MB_TEXTOFF,
+       MB_PSTATE, MB_RFLAGS2, MB_RTASKS, MB_ROUTS, MB_RAUX, MB_RSITES, MB_RTASKOF, MB_PSTATS, MB_COUNT };
 }
+
+static_assert(MB_COUNT <= 64, "bbm_ctx::mapBuf is too small");
 
 #define LAUNCH(call, what) do { int e_ = (call); if (e_) return fail(BBM_E_CUDA, what, (cudaError_t)e_); c->launches++; } while (0)
 
@@ -59,7 +64,6 @@ static int map_args(bbm_ctx* c, const bbm_mapper_cfg* cfg, int64_t nreads) {
     if (c->map_nchroms != (int)c->chrom_off.size() - 1) return fail(BBM_E_ARG, "bbm_map_batch: no scaffold table for this index (call bbm_map_set_scaffolds)");
     if (cfg->max_sites < 1 || cfg->max_sites > bbm_sitelist_max_cap() || cfg->max_keys < 1) return fail(BBM_E_ARG, "bbm_map_batch: max_sites must be in 1..64");
     if (cfg->map.paired && (nreads & 1)) return fail(BBM_E_ARG, "bbm_map_batch: paired input needs an even number of reads");
-    if (cfg->map.paired) return fail(BBM_E_ARG, "bbm_map_batch: paired mode is not built into this library version");
     if (nreads > 0x3fffffffLL) return fail(BBM_E_ARG, "bbm_map_batch: too many reads in one batch");
     return BBM_OK;
 }
@@ -122,7 +126,24 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     LAUNCH(bbm_launch_sitelist_from_search(heads, (const bbm_site*)B[MB_SITES].p, n, maxSites, lists, nss, cap, st), "sitelist_from_search_kernel launch");
     LAUNCH(bbm_launch_sitelist_bounds(lists, nss, n, cap, off, (const int*)c->mapScaf[5].p, (const int*)c->mapScaf[0].p, (const int*)c->mapScaf[1].p,
                                       cfg->sam.inter_scaffold_padding, 1, cfg->slow.expected_len_limit, out2, st), "sitelist_bounds_kernel launch");
-    LAUNCH(bbm_launch_sitelist(BBM_SL_TRIM, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
+    PairParams PP; memset(&PP, 0, sizeof PP);
+    const long long npairs = n / 2;
+    const int maxTasks = (int)std::min<long long>(0x3fffffffLL, 4 * n);
+    if (paired) {
+        if (B[MB_PSTATE].ensure((size_t)npairs * PAIR_STATE * 4) || B[MB_RFLAGS2].ensure(n * 4) || B[MB_RTASKS].ensure((size_t)maxTasks * sizeof(bbm_rescue_task)) ||
+            B[MB_ROUTS].ensure((size_t)maxTasks * sizeof(bbm_rescue_out)) || B[MB_RAUX].ensure((size_t)maxTasks * sizeof(RescueAux)) || B[MB_RSITES].ensure((size_t)maxTasks * sizeof(bbm_ss)) ||
+            B[MB_RTASKOF].ensure((size_t)n * cap * 4) || B[MB_PSTATS].ensure(64) || B[MB_TASKS].ensure((size_t)maxTasks * sizeof(bbm_msa_task)) ||
+            B[MB_OUTS].ensure((size_t)maxTasks * sizeof(bbm_msa_out))) return fail(BBM_E_CUDA, "cudaMalloc pairing buffers");
+        PP.lists = lists; PP.nss = nss; PP.npairs = npairs; PP.cap = cap; PP.read_off = off; PP.basesP = d_bases; PP.basesM = basesM; PP.quality = d_quality; PP.refs = refs;
+        PP.chrom_off = chrom_off; PP.nkeys = nkeys; PP.cfg = cfg->map; PP.pc = cfg->policy; PP.tc = cfg->tip; PP.clearzone1e = cfg->slow.clearzone1e;
+        PP.pstate = (int*)B[MB_PSTATE].p; PP.rflags = (int*)B[MB_RFLAGS2].p; PP.rtasks = (bbm_rescue_task*)B[MB_RTASKS].p; PP.routs = (const bbm_rescue_out*)B[MB_ROUTS].p;
+        PP.raux = (RescueAux*)B[MB_RAUX].p; PP.rsites = (bbm_ss*)B[MB_RSITES].p; PP.rtask_of = (int*)B[MB_RTASKOF].p; PP.maxTasks = maxTasks;
+        PP.mtasks = (bbm_msa_task*)B[MB_TASKS].p; PP.mouts = (const bbm_msa_out*)B[MB_OUTS].p; PP.counters = counters; PP.stats = (unsigned long long*)B[MB_PSTATS].p;
+        CK(cudaMemsetAsync(B[MB_PSTATS].p, 0, 64, st));
+        LAUNCH(bbm_launch_pair(&PP, PAIR_OP_INIT, st), "pair_kernel launch");           // pairSiteScoresInitial, paired trimList, score reset
+    } else {
+        LAUNCH(bbm_launch_sitelist(BBM_SL_TRIM, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
+    }
     LAUNCH(bbm_launch_sitelist(BBM_SL_NOINDEL, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
     LAUNCH(bbm_launch_map_runmask(out, nss, n, paired, (int*)B[MB_RUN].p, (int*)B[MB_MASKED].p, st), "map_runmask_kernel launch");
     LAUNCH(bbm_launch_sitelist_tipdel(lists, (const int*)B[MB_MASKED].p, n, cap, off, d_bases, basesM, d_quality, refs, chrom_off, nullptr, &cfg->tip, out2, st),
@@ -133,7 +154,29 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
                                   maxLen, st, &aligned, nullptr)) return rc;
     S.slow_alignments = aligned;
     S.ms_slow = T.lap(st);
-    LAUNCH(bbm_launch_sitelist(BBM_SL_FINAL, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
+    if (paired) {
+        LAUNCH(bbm_launch_sitelist(BBM_SL_MERGE, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
+        const bbm_rescue_cfg rcfg = {70, 100, 1, 100};           // POINTS_MATCH / POINTS_MATCH2, USE_AFFINE_SCORE, BASE_HIT_SCORE
+        for (int dir = 0; dir < 2; dir++) {                     // rescue(r, r2, ...) then rescue(r2, r, ...): the second sees what the first added
+            CK(cudaMemsetAsync(counters, 0, 32, st));
+            LAUNCH(bbm_launch_pair(&PP, dir == 0 ? PAIR_OP_RESCUE_PREP0 : PAIR_OP_RESCUE_PREP1, st), "pair_kernel launch");
+            int h[3];
+            CK(cudaMemcpyAsync(h, counters, 12, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            const int ntasks = std::min(h[1], maxTasks);
+            if (ntasks > 0) {
+                LAUNCH(bbm_launch_rescue(d_bases, refs, PP.rtasks, ntasks, &rcfg, (bbm_rescue_out*)B[MB_ROUTS].p, st), "rescue_kernel launch");
+                LAUNCH(bbm_launch_rescue_mid(&PP, ntasks, st), "rescue_mid_kernel launch");
+                CK(cudaMemcpyAsync(h, counters, 12, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+                S.rescue_scans += ntasks; S.rescue_fills += h[2];
+                if (h[2] > 0) if (int rc = run_msa(c, d_bases, refs, PP.mtasks, (bbm_msa_out*)B[MB_OUTS].p, h[2], nullptr, nullptr, maxLen, 0, st, nullptr, nullptr)) return rc;
+            }
+            LAUNCH(bbm_launch_pair(&PP, dir == 0 ? PAIR_OP_RESCUE_APPLY0 : PAIR_OP_RESCUE_APPLY1, st), "pair_kernel launch");
+        }
+        LAUNCH(bbm_launch_pair(&PP, PAIR_OP_FINAL, st), "pair_kernel launch");
+        S.ms_rescue = T.lap(st);
+    } else {
+        LAUNCH(bbm_launch_sitelist(BBM_SL_FINAL, lists, nss, n, cap, off, d_bases, basesM, refs, chrom_off, &cfg->policy, out, st), "sitelist_kernel launch");
+    }
 
     // ---- genMatchString in rounds ----
     long long ms = ((2ll * maxLen + 128 + 15) / 16) * 16;
@@ -182,7 +225,12 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     FinParams F; memset(&F, 0, sizeof F);
     F.lists = lists; F.nss = nss; F.nreads = n; F.cap = cap; F.read_off = off; F.basesP = d_bases; F.basesM = basesM; F.refs = refs; F.chrom_off = chrom_off;
     F.pc = cfg->policy; F.cfg = cfg->map; F.flags = out; F.state = G.state; F.mslots = G.mslots; F.ms = ms; F.mlen = G.mlen; F.recs = recs;
-    LAUNCH(bbm_launch_map_finish(&F, st), "map_finish_kernel launch");
+    if (paired) {
+        LAUNCH(bbm_launch_pair_finish(&PP, &F, st), "pair_finish_kernel launch");
+        unsigned long long ph[2];
+        CK(cudaMemcpyAsync(ph, B[MB_PSTATS].p, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        S.mated_pairs = (int64_t)ph[0]; S.inner_length_sum = (int64_t)ph[1];
+    } else LAUNCH(bbm_launch_map_finish(&F, st), "map_finish_kernel launch");
     CK(cudaMemsetAsync(counters, 0, 32, st));
     LAUNCH(bbm_launch_map_status(heads, maxSites, (const int*)B[MB_SLOWST].p, nkeys, recs, n, (unsigned long long*)counters, st), "map_status_kernel launch");
     S.ms_genmatch = T.lap(st);

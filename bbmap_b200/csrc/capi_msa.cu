@@ -173,7 +173,16 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
     unsigned int hend[16];
     CK(cudaMemcpyAsync(hend, cb + 16, 16 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }
+    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); if (ms_out) *ms_out = ms; c->msa_ms += ms; }
+    if (c->msa_count) {             // diagnostics ("msa_count" option): the reference's cell counter summed over the batch, for the roofline of a chained step
+        if (c->msaCells.ensure(8)) return fail(BBM_E_CUDA, "cudaMalloc cell counter");
+        CK(cudaMemsetAsync(c->msaCells.p, 0, 8, st));
+        int e3 = bbm_launch_msa_sum_iterations(d_outs, ntasks, (unsigned long long*)c->msaCells.p, st);
+        if (e3) return fail(BBM_E_CUDA, "msa_sum_iterations launch", (cudaError_t)e3);
+        unsigned long long cells = 0;
+        CK(cudaMemcpyAsync(&cells, c->msaCells.p, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        c->msa_cells += (long long)cells;
+    }
     {   // bookkeeping: how many alignments the narrow kernel tried / handed over to the tiled kernels
         long long tiledTotal = 0;
         for (int k = 0; k < nw; ++k) tiledTotal += (long long)hend[k] - base[k];

@@ -74,6 +74,7 @@ extern "C" int bbm_launch_search(const bbm_index_cfg* d_cfg, const void* d_block
                                  int quitAfterTwoPerfects, bbm_search_head* heads, bbm_site* sites, int maxSites, void* pool,
                                  unsigned int* counter, unsigned long long* prof, int blocks, int forcePool, int phases, int* mid, int midStride,
                                  cudaStream_t st);
+extern "C" int bbm_launch_msa_sum_iterations(const bbm_msa_out* outs, long long n, unsigned long long* sum, cudaStream_t st);
 extern "C" int bbm_launch_peak(int kind, int blocks, int iters, int* d_out, cudaStream_t st);
 extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int nlist, int* gscratch, long long gstride, cudaStream_t stream, int max_rows, int max_cols, const unsigned int* endPtr, unsigned int base);
 extern "C" int bbm_msa_warps_per_block();
@@ -143,10 +144,11 @@ struct bbm_ctx {
     DevBuf grefPool, grefInfo, grefTasks, d_gtasks, d_gaps;   // gapped references (a15)   // staging for the host-buffer entry point
     PinBuf h_stage;
     // the batched mapper (capi_mapper.cu): working buffers of the chain, scaffold table, staging of the host entry point
-    DevBuf mapBuf[48], mapScaf[6], mapHost[8];
+    DevBuf mapBuf[64], mapScaf[6], mapHost[8];
     int map_nchroms = 0, map_nscaf = 0, map_maxidx_for = -1; bool map_has_names = false; long long map_last_cs = 0, map_last_ms = 0;
     std::vector<void*> uploads;
     long long launches = 0;
+    double msa_ms = 0.0; long long msa_cells = 0; int msa_count = 0; DevBuf msaCells;     // device time of every run_msa so far; reference cells (with "msa_count")
     std::mutex mu;
 };
 

@@ -132,3 +132,17 @@ extern "C" int bbm_msa_num_wclass() { return NUM_WCLASS; }
 extern "C" int bbm_msa_class_strip() { return CLASS_STRIP; }
 extern "C" int bbm_msa_wclass_width(int k) { return wclass_width(k); }
 extern "C" long long bbm_generic_scratch_ints(int rows, int cols) { return msa_generic_scratch_ints(rows, cols); }
+
+// sum of the reference's cell counter over a batch (diagnostics for the roofline of a chained step)
+__global__ void __launch_bounds__(256) msa_sum_iterations_kernel(const bbm_msa_out* __restrict__ outs, long long n, unsigned long long* __restrict__ sum) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    for (; i < n; i += (long long)gridDim.x * blockDim.x) if (outs[i].status == 0) v += (unsigned long long)outs[i].iterations;
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, v);
+}
+extern "C" int bbm_launch_msa_sum_iterations(const bbm_msa_out* outs, long long n, unsigned long long* sum, cudaStream_t st) {
+    const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    msa_sum_iterations_kernel<<<blocks, 256, 0, st>>>(outs, n, sum);
+    return (int)cudaGetLastError();
+}

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(128) sitelist_kernel(SitelistParams P) {
             if (cfg.min_trim_sites_to_retain > 1) stable_sort<false>(v, n);
             o.best_sites = trim_list(v, n, false, max_quality(len), true, cfg.min_trim_sites_to_retain, cfg.max_trim_sites_to_retain);
         }
+    } else if (P.op == BBM_SL_MERGE) {
+        n = merge_duplicate_sites(v, n);                 // Tools.mergeDuplicateSites(r.sites, true, true) on its own (processReadPair :1043, :1059)
     } else if (P.op == BBM_SL_NOINDEL) {
         const int maxSw = max_quality(len), maxImp = max_imperfect(len);
         int numNear = 0, best = -0x7fffffff - 1; bool forceSlow = false;
@@ -186,48 +188,6 @@ __global__ void __launch_bounds__(128) sitelist_bounds_kernel(BoundsParams P) {
 // =====================  findTipDeletions(Read, ...) (AbstractMapThread.java:1073-1104)  =====================
 // Scalar forms of findTipDeletionsRight/Left (:2178-2294; the warp-per-task forms live in rescue.cu): here the unit is the read, the
 // scans are short (<= 100 starts x 8 bases) and most sites stop after the 8-base tip check.
-__device__ int tip_right(const int8_t* __restrict__ bases, int len, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStop, int searchDist, int tiplen) {
-    if (originalStop < minIndex + tiplen - 1 || originalStop >= refLen) return 0;
-    const int tipCoord = len - 1;
-    int lastMismatch = 0, originalMismatches = 0, contig = 0;
-    for (int i = 0; i < tiplen && contig < 5; i++) {
-        if (bases[tipCoord - i] != ref[originalStop - i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
-    }
-    if (originalMismatches < 3) return 0;
-    int minMismatches = originalMismatches, bestStart = originalStop;
-    tiplen = lastMismatch + 1;
-    if (tiplen < 4) return 0;
-    searchDist = imin(searchDist, 30 * originalMismatches);
-    const int last = imin(refLen - 1, originalStop + searchDist);
-    for (int start = originalStop + 1; start <= last && minMismatches > 0; start++) {
-        int m = 0;
-        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[tipCoord - j] != ref[start - j]) ? 1 : 0;
-        if (m < minMismatches) { bestStart = start; minMismatches = m; }
-    }
-    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
-    return bestStart - originalStop;
-}
-__device__ int tip_left(const int8_t* __restrict__ bases, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStart, int searchDist, int tiplen) {
-    if (originalStart + tiplen >= refLen || minIndex >= originalStart) return 0;
-    int lastMismatch = 0, originalMismatches = 0, contig = 0;
-    for (int i = 0; i < tiplen && contig < 5; i++) {
-        if (bases[i] != ref[originalStart + i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
-    }
-    if (originalMismatches < 3) return 0;
-    int minMismatches = originalMismatches, bestStart = originalStart;
-    tiplen = lastMismatch + 1;
-    if (tiplen < 4) return 0;
-    searchDist = imin(searchDist, 16 + 16 * originalMismatches + 8 * tiplen);
-    const int last = imax(minIndex, originalStart - searchDist);
-    for (int start = originalStart - 1; start >= last && minMismatches > 0; start--) {
-        int m = 0;
-        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[j] != ref[start + j]) ? 1 : 0;
-        if (m < minMismatches) { bestStart = start; minMismatches = m; }
-    }
-    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
-    return originalStart - bestStart;
-}
-
 struct TipParams {
     bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off; const int8_t* basesP; const int8_t* basesM;
     const int8_t* quality; const int8_t* refs; const long long* chrom_off; const int* chrom_min_index; bbm_tipdel_cfg tc; bbm_read_out* out;

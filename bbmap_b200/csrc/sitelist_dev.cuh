@@ -247,4 +247,47 @@ __device__ __forceinline__ float calc_cz3_fraction(int score1, int score2, int c
     return __fadd_rn(__fadd_rn(f, a), __fmul_rn(a, f));
 }
 
+// findTipDeletionsRight / findTipDeletionsLeft, scalar forms (AbstractMapThread.java:2178-2294)
+static __device__ int tip_right(const int8_t* __restrict__ bases, int len, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStop, int searchDist, int tiplen) {
+    if (originalStop < minIndex + tiplen - 1 || originalStop >= refLen) return 0;
+    const int tipCoord = len - 1;
+    int lastMismatch = 0, originalMismatches = 0, contig = 0;
+    for (int i = 0; i < tiplen && contig < 5; i++) {
+        if (bases[tipCoord - i] != ref[originalStop - i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
+    }
+    if (originalMismatches < 3) return 0;
+    int minMismatches = originalMismatches, bestStart = originalStop;
+    tiplen = lastMismatch + 1;
+    if (tiplen < 4) return 0;
+    searchDist = imin(searchDist, 30 * originalMismatches);
+    const int last = imin(refLen - 1, originalStop + searchDist);
+    for (int start = originalStop + 1; start <= last && minMismatches > 0; start++) {
+        int m = 0;
+        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[tipCoord - j] != ref[start - j]) ? 1 : 0;
+        if (m < minMismatches) { bestStart = start; minMismatches = m; }
+    }
+    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
+    return bestStart - originalStop;
+}
+static __device__ int tip_left(const int8_t* __restrict__ bases, const int8_t* __restrict__ ref, int refLen, int minIndex, int originalStart, int searchDist, int tiplen) {
+    if (originalStart + tiplen >= refLen || minIndex >= originalStart) return 0;
+    int lastMismatch = 0, originalMismatches = 0, contig = 0;
+    for (int i = 0; i < tiplen && contig < 5; i++) {
+        if (bases[i] != ref[originalStart + i]) { originalMismatches++; lastMismatch = i; contig = 0; } else contig++;
+    }
+    if (originalMismatches < 3) return 0;
+    int minMismatches = originalMismatches, bestStart = originalStart;
+    tiplen = lastMismatch + 1;
+    if (tiplen < 4) return 0;
+    searchDist = imin(searchDist, 16 + 16 * originalMismatches + 8 * tiplen);
+    const int last = imax(minIndex, originalStart - searchDist);
+    for (int start = originalStart - 1; start >= last && minMismatches > 0; start--) {
+        int m = 0;
+        for (int j = 0; j < tiplen && m < minMismatches; j++) m += (bases[j] != ref[start + j]) ? 1 : 0;
+        if (m < minMismatches) { bestStart = start; minMismatches = m; }
+    }
+    if (minMismatches > 2 || originalMismatches - minMismatches < 2) return 0;
+    return originalStart - bestStart;
+}
+
 }  // namespace bbm

@@ -49,8 +49,9 @@ MAPPER_CFG_DTYPE = np.dtype([("map", MAP_CFG_DTYPE), ("seed", SEED_CFG_DTYPE), (
                              ("sam", SAM_CFG_DTYPE), ("ingest_flags", "<i4"), ("max_keys", "<i4"), ("max_sites", "<i4"), ("sam_text", "<i4")], align=True)
 MAP_STATS_DTYPE = np.dtype([("reads", "<i8"), ("mapped", "<i8"), ("slow_alignments", "<i8"), ("realign_fills", "<i8"), ("site_overflow_reads", "<i8"),
                             ("status_reads", "<i8"), ("sam_bytes", "<i8"), ("max_sites_used", "<i4"), ("genmatch_rounds", "<i4"), ("ms_total", "<f4"),
-                            ("ms_seed_search", "<f4"), ("ms_lists", "<f4"), ("ms_slow", "<f4"), ("ms_genmatch", "<f4"), ("ms_sam", "<f4"), ("pad_", "<i4", (2,))], align=True)
-assert MAPPER_CFG_DTYPE.itemsize == 80 + 32 + 80 + 32 + 16 + 32 + 16 and MAP_STATS_DTYPE.itemsize == 96
+                            ("ms_seed_search", "<f4"), ("ms_lists", "<f4"), ("ms_slow", "<f4"), ("ms_genmatch", "<f4"), ("ms_sam", "<f4"), ("ms_rescue", "<f4"), ("pad_", "<i4"), ("rescue_scans", "<i8"),
+                            ("rescue_fills", "<i8"), ("mated_pairs", "<i8"), ("inner_length_sum", "<i8")], align=True)
+assert MAPPER_CFG_DTYPE.itemsize == 80 + 32 + 80 + 32 + 16 + 32 + 16 and MAP_STATS_DTYPE.itemsize == 128
 ST_MATCH_OVERFLOW, ST_TIP, ST_SLOTS, ST_ALIGNER, ST_SITE_OVERFLOW, ST_SLOW = 1, 2, 4, 8, 16, 32
 
 

@@ -1,36 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — MultiStateAligner11ts microbenchmark (BASELINE.json configs[2], SURVEY.md §8d workload G4).
+"""bench.py — mapped reads/s of the whole seed-and-extend chain on BASELINE.json configs[1]-shaped input, one B200 per rank.
 
-One "step" = one pass of the hot path (fillLimited rule -> fillLimitedX/fillUnlimited -> score2 -> traceback2) over one
-batch of synthetic (read, candidate window) tasks.  Metric: DP GCUPS = the reference's own cell counter
-(iterationsLimited+iterationsUnlimited, jni/MultiStateAligner11tsJNI.c:138,471) summed over the batch / seconds.
+One "step" = one call of the batched mapper over one batch of synthetic 2x150 bp pairs (E. coli-sized random reference, ~1 % substitutions,
+1-3 bp indels, Q30): Read.validate -> KeyRing -> BBIndex.find -> pairSiteScoresInitial -> scoreNoIndels -> findTipDeletions -> scoreSlow -> rescue
+-> pairSiteScoresFinal -> genMatchString / realign_new -> SamLine fields -> SAM text, i.e. BBMapThread.processReadPair for every pair.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--tasks T] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--genome G] [--scaffolds S] [--impl reference]
 
-Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer
-plug-in call (H2D of tasks+reads and D2H of results inside the timed region).  `--impl reference` times the
-reference's own C (oracle/_ref, all host threads) on a bounded sample of the same workload.
-"""
+`value`   reads/s with the reads resident in HBM (bbm_map_batch_dev), SAM text formatted on the device;
+`e2e`     reads/s through the reference-facing call bbm_map_batch_host: FASTQ-shaped pinned host buffers in, SAM text + records out, every
+          copy inside the timed region;
+`roofline` the dominant kernels of the step — the MultiStateAligner11ts fills — against the integer-issue roof measured in the same run;
+`msa`     the MultiStateAligner11ts microbenchmark (configs[2], GCUPS; bench/msa_bench.py), `banded` BandedAligner at G6 scale;
+`cpu_baseline` / `--impl reference`: the same chain through the sequential CPU restatement (oracle/), one process per host core.
+Prints ONE JSON line (rank 0)."""
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "bench"))
 
 from bbmap_b200 import workloads as wl  # noqa: E402
 
-GENOME_LEN = 4_600_000      # "E. coli-sized" resident reference the windows point into
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (msa_strip_fill_kernel) per launch, from the committed ncu captures
-# (profiles/): keyed by alignments per step
-TRAFFIC_NCU = {800_000: 22.84e9, 1_600_000: 48.97e9}
-METRIC = "MSA fill GCUPS (MultiStateAligner11ts fillLimited+score+traceback, reference cell count / s)"
+METRIC = "mapped reads/sec (2x150bp pairs, SAM text out)"
 
 
 def parse():
@@ -38,175 +36,134 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--tasks", type=int, default=1_600_000, help="alignments per step per GPU")
+    ap.add_argument("--pairs", type=int, default=200_000, help="pairs per step per GPU")
+    ap.add_argument("--genome", type=int, default=4_600_000)
+    ap.add_argument("--scaffolds", type=int, default=1)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--bandwidth", type=int, default=0)
-    ap.add_argument("--ratio", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lengths", default="100,150,250")
-    ap.add_argument("--no-narrow", action="store_true", help="disable the thread-per-alignment narrow kernel (A/B)")
-    ap.add_argument("--no-strip", action="store_true", help="route limited fills through the register-tiled kernel instead of the strip kernel (A/B)")
-    ap.add_argument("--strip-budget-mb", type=int, default=0)
-    ap.add_argument("--narrow-slack", type=int, default=-1, help="narrow kernel only for alignments with maxQ-minScore <= this (points)")
-    ap.add_argument("--strip-buckets", type=int, default=-1, help="work buckets (of 4096 cells) routed to the strip kernel; larger alignments use the tiled kernel")
-    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage timings (ingest/seed/index/search/scoreNoIndels) of bench/stages.py")
-    ap.add_argument("--stage-pairs", type=int, default=200_000)
+    ap.add_argument("--no-msa", action="store_true", help="skip the MSA microbenchmark (configs[2]) sub-measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the band sweep / BandedAligner / single-ended sub-measurements")
+    ap.add_argument("--msa-tasks", type=int, default=1_600_000)
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the CPU sample (0 = sized for ~20 s)")
+    ap.add_argument("--in-flight", type=int, default=2, help="mapper contexts of the end-to-end arm (batches in flight)")
     return ap.parse_args()
 
 
-def peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return json.load(open(p)), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+def make_reference(genome_len, scaffolds):
+    """G2: one random scaffold; G3: `scaffolds` random scaffolds of unequal size + 1 % of the bases in planted 300-bp repeat families of 100 copies."""
+    if scaffolds <= 1:
+        return [wl.random_genome(genome_len, seed=1)]
+    rng = np.random.Generator(np.random.PCG64(3))
+    w = rng.uniform(0.4, 2.0, size=scaffolds); sizes = np.maximum(1000, (w / w.sum() * genome_len).astype(np.int64))
+    scafs = [wl.ACGT[rng.integers(0, 4, size=int(z), dtype=np.uint8)] for z in sizes]
+    fam = max(1, int(genome_len * 0.01 / 300 / 100))
+    for _ in range(fam):
+        unit = wl.ACGT[rng.integers(0, 4, size=300, dtype=np.uint8)]
+        for _c in range(100):
+            sc = scafs[int(rng.integers(0, scaffolds))]
+            q = int(rng.integers(0, len(sc) - 300)); sc[q:q + 300] = unit
+    return scafs
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.stop_flag = False
-        self.proc = None
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
-
-    def finish(self):
-        self.stop_flag = True
-        if self.proc:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+def read_names(n):
+    """FASTQ-style names: pair index and /1 /2."""
+    names = [b"p%d/%d" % (i // 2, (i & 1) + 1) for i in range(n)]
+    off = np.zeros(n + 1, np.int64); np.cumsum([len(x) for x in names], out=off[1:])
+    return np.frombuffer(b"".join(names), np.int8).copy(), off, names
 
 
-def cpu_reference_run(reads, genome, tasks, moff, bw, ratio, budget_s=12.0, threads=None):
-    """Times the reference's own C (oracle/_ref) — or the port if it is absent — on a bounded sample: whole passes over
-    (a prefix of) the step batch until ~budget_s seconds of wall time have been spent."""
+# ---------------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the sequential restatement (oracle/chain.py), one worker process per host core, each mapping its own slice of the sample
+_W = {}
+
+
+def _cpu_worker(args):
+    lo, hi, paired = args
+    from oracle import chain, oracle as orc
+    o = orc.get()
+    R = _W["R"]; L = 150
+    a, b = 2 * lo * L, 2 * hi * L
+    off = np.arange(2 * (hi - lo) + 1, dtype=np.int64) * L
+    t0 = time.perf_counter()
+    fn = chain.map_pairs if paired else chain.map_single
+    res = fn(o, _W["idx"], _W["cb"], _W["co"], _W["table"], R["bases"][a:b], R["qual"][a:b], off)
+    lines = chain.sam_lines(res, off, names=_W["names"][2 * lo:2 * hi], scaf_names=_W["snames"], paired=paired)
+    return time.perf_counter() - t0, int((res["recs"]["flags"] & 1).sum()), sum(len(x) for x in lines)
+
+
+def cpu_chain(cb, co, table, R, names, snames, npairs, threads, paired=True):
+    """Maps the first `npairs` pairs with `threads` worker processes (fork: the index is built once and shared copy-on-write)."""
+    import multiprocessing as mp
     from oracle import oracle as orc
     o = orc.get()
-    kind = "reference" if o.has_reference else "port"
-    threads = threads or (os.cpu_count() or 1)
-    n = int(min(len(tasks), 100_000))
-    cells = 0; secs = 0.0; passes = 0
-    while secs < budget_s and passes < 64:
-        t0 = time.perf_counter()
-        _, _, c = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=bw, ratio=ratio, kind=kind, threads=threads)
-        secs += time.perf_counter() - t0
-        cells += c; passes += 1
-    return {"value": cells / secs / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
-            "sample": "%d passes over the first %d alignments of the step batch, %.1f s, %d threads, one private packed matrix per thread"
-                      % (passes, n, secs, threads),
-            "seconds": secs, "cells": cells, "tasks": n * passes}
+    _W.update(R=R, cb=cb, co=co, table=table, names=names, snames=snames, idx=o.index_build(cb, co, 13, -1))
+    threads = max(1, min(threads, npairs))
+    bounds = [(npairs * k // threads, npairs * (k + 1) // threads, paired) for k in range(threads)]
+    t0 = time.perf_counter()
+    if threads == 1:
+        outs = [_cpu_worker(bounds[0])]
+    else:
+        with mp.get_context("fork").Pool(threads) as pool:
+            outs = pool.map(_cpu_worker, bounds)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "reads": 2 * npairs, "reads_per_s": 2 * npairs / dt, "mapped": sum(x[1] for x in outs), "sam_bytes": sum(x[2] for x in outs), "threads": threads}
+
+
+def reference_arm(args, cb, co, table, R, names, snames):
+    threads = os.cpu_count() or 1
+    npairs = args.cpu_pairs or max(threads * 150, 600)
+    times, reads = [], 0
+    for it in range(args.warmup + args.steps):
+        r = cpu_chain(cb, co, table, R, names, snames, npairs, threads)
+        if it >= args.warmup:
+            times.append(r["seconds"]); reads += r["reads"]
+    v = reads / sum(times)
+    sample = "the first %d pairs of the step batch per step, %d worker processes, sequential C restatement of the chain (oracle/) incl. SAM text" % (npairs, threads)
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": config_of(args), "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "no JVM in the image: the reference's Java host cannot run; this is its restatement in C (the fills are pinned to the reference's own C by tests/test_oracle_vs_reference.py)"}
+
+
+def config_of(args):
+    return {"workload": "configs[1]: %d bp random reference (%d scaffold(s)), %d pairs of 2x150 bp per step per GPU, insert 200-500, ~1%% substitutions, 1-3 bp indel in ~50%% of the reads, "
+                        "Q30; BBMap default flags (k=13, ambig=best, rescue on), index and reference resident and replicated per GPU" % (args.genome, args.scaffolds, args.pairs),
+            "pairs_per_step_per_gpu": args.pairs, "genome_bp": args.genome, "scaffolds": args.scaffolds,
+            "l2": "inputs larger than L2 (%.0f MB of reads + %.0f MB of site lists per step)" % (args.pairs * 2 * 300 / 1e6, args.pairs * 2 * 16 * 80 / 1e6)}
 
 
 def main():
     args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    lengths = tuple(int(x) for x in args.lengths.split(","))
-    config = {"workload": "configs[2] MSA11ts microbenchmark G4: %d alignments/step/GPU, read length {%s}, window = locus +-4, "
-                          "70%% ~1%% subs / 20%% 1-40bp indel / 10%% unrelated, minScore=max(scoreNoIndels, 0.56*maxQ-258), "
-                          "fillLimited rule + score2 + traceback2; resident %d bp reference" % (args.tasks, args.lengths, GENOME_LEN),
-              "tasks_per_step_per_gpu": args.tasks, "bandwidth": args.bandwidth, "bandwidthRatio": args.ratio,
-              "l2": "inputs larger than L2 (tasks+reads+outs+match > 200 MB per step)"}
-
-    genome = wl.random_genome(GENOME_LEN, seed=1)
-    # the reference arm times a bounded sample (the first 20 k alignments of the step batch): generate only the first block
-    ngen = args.tasks if args.impl != "reference" else min(args.tasks, 100_000)
-    reads, tasks = wl.make_msa_tasks(genome, ngen, seed=2 + rank, lengths=lengths, flags=wl.TF_SCORE | wl.TF_TRACEBACK)
-    moff = wl.match_offsets(tasks)
-
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    scafs = make_reference(args.genome, args.scaffolds)
+    snames_all = ["scaffold_%d" % (i + 1) for i in range(len(scafs))]
+    from bbmap_b200.index import pack_chromosomes
     if args.impl == "reference":
         if rank != 0:
             return
-        # each step = a bounded sample sized so steps+warmup finish within minutes
-        from oracle import oracle as orc
-        o = orc.get()
-        kind = "reference" if o.has_reference else "port"
-        threads = os.cpu_count() or 1
-        n = min(len(tasks), 20000)
-        times, cells = [], 0
-        for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            _, _, c = o.run_batch(reads, genome, tasks[:n], match_off=moff[:n + 1], bandwidth=args.bandwidth, ratio=args.ratio,
-                                  kind=kind, threads=threads)
-            dt = time.perf_counter() - t0
-            if it >= args.warmup:
-                times.append(dt); cells += c
-        total = sum(times)
-        v = cells / total / 1e9
-        sample = "first %d alignments of the step batch per step, %d threads" % (n, threads)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
-                          "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        cb, co, table = pack_chromosomes(scafs)
+        npairs = args.cpu_pairs or max((os.cpu_count() or 1) * 150, 600)
+        R = wl.make_mapping_reads(cb, co, table, npairs, seed=2)
+        _, _, names = read_names(2 * npairs)
+        order = sorted(range(len(table)), key=lambda i: table[i])
+        print(json.dumps(reference_arm(args, cb, co, table, R, names, [snames_all[i].encode() for i in order])))
         return
 
     import torch
-    import ctypes as C
-    from bbmap_b200.msa import MultiStateAligner11tsCUDA
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (bbmap_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    msa = MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio)
-    if args.no_narrow:
-        msa.set_option("narrow", 0)
-    if args.no_strip:
-        msa.set_option("strip", 0)
-    if args.narrow_slack >= 0:
-        msa.set_option("narrow", args.narrow_slack)
-    if args.strip_buckets >= 0:
-        msa.set_option("strip", args.strip_buckets)
-    if os.environ.get("BBM_STRIP_STATS"):
-        msa.set_option("strip_debug", 4)
-    if args.strip_budget_mb:
-        msa.set_option("strip_budget_mb", args.strip_budget_mb)
+        dist.init_process_group("gloo")            # barrier + max-over-ranks only: the data path has no collective, so no NCCL
+    import ctypes as C
+    from bbmap_b200 import lib as _lib, shard
+    from bbmap_b200.mapper import BBMapCUDA, MAP_REC_DTYPE, MAP_STATS_DTYPE, mapper_cfg
+    from bbmap_b200.sam import SAM_OUT_DTYPE
+    from msa_bench import ClockSampler, peaks
     dev = torch.device("cuda", local)
-    # resident inputs (torch owns the device memory; the C ABI takes raw pointers)
-    d_genome = torch.from_numpy(np.concatenate([genome, np.full(256, ord("N"), np.uint8)])).to(dev)
-    d_reads = torch.from_numpy(reads).to(dev)
-    d_tasks = torch.from_numpy(tasks.view(np.uint8)).to(dev)
-    d_moff = torch.from_numpy(moff).to(dev)
-    d_outs = torch.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_match = torch.zeros(int(moff[-1]) + 16, dtype=torch.uint8, device=dev)
-    max_rows = int(tasks["read_len"].max()); max_cols = int((tasks["ref_end"] - tasks["ref_start"] + 1).max())
-    stream = torch.cuda.current_stream()
-
-    def step_dev():
-        return msa.align_batch_dev(d_reads.data_ptr(), d_genome.data_ptr(), d_tasks.data_ptr(), d_outs.data_ptr(), len(tasks),
-                                   d_match.data_ptr(), d_moff.data_ptr(), max_rows, max_cols, C.c_void_p(stream.cuda_stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,146 +171,170 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # integer / DPX pipe peaks of this very GPU (the DP kernels' roofline denominators; not in MEASURED_PEAKS.json)
-    kinds = ["iadd3", "lop3", "vimnmx3_dpx", "viaddmnmx_dpx", "imad", "half_imad_half_lop3", "cmp_select"]
-    int_peaks = {k: msa.int_peak(i) for i, k in enumerate(kinds)} if rank == 0 else {}
+    t_build = time.perf_counter()
+    m = BBMapCUDA(scafs, names=snames_all, device=local)
+    t_build = time.perf_counter() - t_build
+    del scafs
+    cb, co, table = m.cb, m.co, m.table
+    R = wl.make_mapping_reads(cb, co, table, args.pairs, seed=2 + rank)
+    n = 2 * args.pairs
+    nbuf, noff, names = read_names(n)
+    cfg = mapper_cfg(paired=True, sam_text=True)
+    L = m.L; h = m.h
+    L.bbm_set_option(h, b"msa_count", 0)
+
+    # ---- resident arm ----
+    pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
+    d_bases = pad(R["bases"]); d_qual = pad(R["qual"]); d_off = torch.from_numpy(R["off"]).to(dev)
+    d_recs = torch.zeros(n * MAP_REC_DTYPE.itemsize, dtype=torch.uint8, device=dev); d_sam = torch.zeros(n * SAM_OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    stats = np.zeros(1, MAP_STATS_DTYPE)
+    stream = torch.cuda.current_stream()
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_dev():
+        _lib.check(L.bbm_map_batch_dev(h, p(d_bases), p(d_qual), p(d_off), n, 150, cfg.ctypes.data_as(C.c_void_p), p(d_recs), p(d_sam), None, 0,
+                                       C.c_void_p(stream.cuda_stream), stats.ctypes.data_as(C.c_void_p)), "bbm_map_batch_dev")
+        return stats[0].copy()
+
     for _ in range(max(args.warmup, 3)):
-        step_dev()
-    outs = np.frombuffer(d_outs.cpu().numpy().tobytes(), dtype=wl.OUT_DTYPE)
-    cells_per_step = int(outs["iterations"].sum())
-    # one untimed step with the kernels' own work counters on: cells actually evaluated (strip kernel: rows of 8 cells; narrow kernel: 16
-    # diagonals per row of every alignment that tried it), for the integer-issue roofline below
-    msa.set_option("strip_debug", 4)
-    u0, n0 = msa.stat("strip_units"), msa.stat("narrow_tried")
+        st0 = step_dev()
+    # one untimed step with the aligner's cell counter on (roofline numerator) and the integer peaks of this very GPU (denominator)
+    L.bbm_set_option(h, b"msa_count", 1)
+    c0 = L.bbm_get_stat(h, b"msa_cells"); u0 = L.bbm_get_stat(h, b"msa_us")
     step_dev()
-    tried = msa.stat("narrow_tried") - n0
-    evaluated_cells = 8 * (msa.stat("strip_units") - u0) + 16 * int(tasks["read_len"].mean()) * tried
-    strip_lane_util = (msa.stat("strip_units") - u0) / max(1, msa.stat("strip_lane_iters"))
-    msa.set_option("strip_debug", 0)
-    assert (outs["status"] == 0).all(), "bench: some alignments returned an error status"
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    cells_step = L.bbm_get_stat(h, b"msa_cells") - c0
+    L.bbm_set_option(h, b"msa_count", 0)
+    kinds = ["iadd3", "lop3", "vimnmx3_dpx", "viaddmnmx_dpx", "imad", "half_imad_half_lop3", "cmp_select"]
+    int_peaks = {}
+    if rank == 0:
+        for i, k in enumerate(kinds):
+            g = C.c_double(0); _lib.check(L.bbm_int_peak(h, i, C.byref(g)), "bbm_int_peak"); int_peaks[k] = g.value
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
     barrier()
-    l0 = msa.launches
+    l0 = L.bbm_launch_count(h); u0 = L.bbm_get_stat(h, b"msa_us")
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    kernel_ms = 0.0
+    stage = np.zeros(7)
     for _ in range(args.steps):
-        kernel_ms += step_dev()
+        s_ = step_dev()
+        stage += [s_["ms_seed_search"], s_["ms_lists"], s_["ms_slow"], s_["ms_rescue"], s_["ms_genmatch"], s_["ms_sam"], s_["ms_total"]]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = msa.launches - l0
-    # e2e: host buffers through the plug-in call, copies inside the timed region
-    d_ref_ptr = C.c_void_p(d_genome.data_ptr())
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()           # pinned host buffers, as a production host would hold
-    reads_p = pin(reads); tasks_p = pin(tasks.view(np.uint8)).view(wl.TASK_DTYPE); moff_p = pin(moff)
-    outs_p = pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE)
-    mbuf_p = pin(np.zeros(int(moff[-1]), np.int8))
-    # Several batches in flight (default 3), the way the reference keeps one MSA per mapping thread (AbstractMapThread.java:133-136): one
-    # host thread per batch, each with its own context, staging buffers and pinned result buffers, so the copies of one batch overlap
-    # the kernels of the others.  Every step still pays its own H2D of tasks+reads and D2H of results+match strings inside the timed region.
-    msa_b = MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio)
-    outs_q = pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE)
-    mbuf_q = pin(np.zeros(int(moff[-1]), np.int8))
-    lanes = [(msa, outs_p, mbuf_p), (msa_b, outs_q, mbuf_q)]
-    nfl = int(os.environ.get("BBM_E2E_IN_FLIGHT", "3"))
-    extra = []
-    for _k in range(nfl - 2):
-        extra.append(MultiStateAligner11tsCUDA(device=local, bandwidth=args.bandwidth, bandwidthRatio=args.ratio))
-        lanes.append((extra[-1], pin(np.zeros(len(tasks) * wl.OUT_DTYPE.itemsize, np.uint8)).view(wl.OUT_DTYPE), pin(np.zeros(int(moff[-1]), np.int8))))
-    for m_, o_, b_ in lanes:
-        m_.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=o_, mbuf=b_)
+    launches = L.bbm_launch_count(h) - l0
+    msa_ms_step = (L.bbm_get_stat(h, b"msa_us") - u0) / 1e3 / args.steps
+    recs = np.frombuffer(d_recs.cpu().numpy().tobytes(), MAP_REC_DTYPE)
+    tr = R["truth"]
+    mapped = (recs["flags"] & 1) != 0
+    correct = mapped & (recs["chrom"] == tr[:, 0]) & (recs["strand"] == tr[:, 1]) & ((np.abs(recs["start"] - tr[:, 2]) <= 8) | (np.abs(recs["stop"] - tr[:, 3]) <= 8))
+    exact = mapped & (recs["start"] == tr[:, 2]) & (recs["stop"] == tr[:, 3])
+
+    # ---- end to end: host buffers through the reference-facing call, `in_flight` batches at a time on their own contexts / host threads ----
+    import threading
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hb = pin(R["bases"].view(np.int8)); hq = pin(R["qual"].view(np.int8)); ho = pin(R["off"]); hn = pin(nbuf); hno = pin(noff)
+    sam_cap = int(st0["sam_bytes"]) + (1 << 20)
+    nfl = max(1, args.in_flight)
+    ctxs = [m] + [BBMapCUDA([cb[co[i] + 8000:co[i + 1] - 8001] for i in range(0)] or None, device=local) if False else None for _ in range(nfl - 1)]
+    lanes = []
+    for k in range(nfl):
+        mk = m if k == 0 else BBMapCUDA.__new__(BBMapCUDA)
+        if k > 0:
+            mk.clone_from(m, device=local)
+        lanes.append({"m": mk, "recs": pin(np.zeros(n * MAP_REC_DTYPE.itemsize, np.int8)), "sam": pin(np.zeros(n * SAM_OUT_DTYPE.itemsize, np.int8)),
+                      "text": pin(np.zeros(sam_cap, np.int8)), "toff": pin(np.zeros(n + 1, np.int64)), "stats": np.zeros(1, MAP_STATS_DTYPE)})
+
+    def step_host(lane):
+        _lib.check(L.bbm_map_batch_host(lane["m"].h, hb.ctypes.data_as(C.c_void_p), hq.ctypes.data_as(C.c_void_p), ho.ctypes.data_as(C.c_void_p), n, hn.ctypes.data_as(C.c_void_p),
+                                        hno.ctypes.data_as(C.c_void_p), cfg.ctypes.data_as(C.c_void_p), lane["recs"].ctypes.data_as(C.c_void_p), lane["sam"].ctypes.data_as(C.c_void_p),
+                                        None, 0, lane["text"].ctypes.data_as(C.c_void_p), sam_cap, lane["toff"].ctypes.data_as(C.c_void_p), lane["stats"].ctypes.data_as(C.c_void_p)),
+                   "bbm_map_batch_host")
+
+    for lane in lanes:
+        step_host(lane)
     barrier()
-    e2e_steps = nfl * max(1, min(args.steps, 6) // nfl)
+    per_lane = max(1, args.steps // nfl)
+    e2e_steps = per_lane * nfl
 
-    def e2e_worker(k):
-        m_, o_, b_ = lanes[k]
-        for _ in range(e2e_steps // nfl):
-            m_.align_batch(reads_p, d_ref_ptr, tasks_p, match_off=moff_p, outs=o_, mbuf=b_, account=False)
+    def worker(lane):
+        for _ in range(per_lane):
+            step_host(lane)
 
-    workers = [threading.Thread(target=e2e_worker, args=(k,)) for k in range(nfl)]
+    ths = [threading.Thread(target=worker, args=(lane,)) for lane in lanes]
     t0 = time.perf_counter()
-    for w_ in workers:
-        w_.start()
-    for w_ in workers:
-        w_.join()
+    for t_ in ths:
+        t_.start()
+    for t_ in ths:
+        t_.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h_outs = outs_p
-    assert outs_q.tobytes() == outs.tobytes(), "second in-flight batch disagrees with the resident path"
-    msa_b.close()
-    for m_ in extra:
-        m_.close()
     clocks = sampler.finish()
-    assert h_outs.tobytes() == outs.tobytes(), "host-buffer path and resident path disagree"
+    sam_bytes = int(lanes[0]["stats"][0]["sam_bytes"])
+    assert lanes[0]["recs"].tobytes() == recs.tobytes(), "host-buffer path and resident path disagree"
+    for lane in lanes[1:]:
+        assert lane["recs"].tobytes() == recs.tobytes() and lane["text"][:sam_bytes].tobytes() == lanes[0]["text"][:sam_bytes].tobytes(), "in-flight contexts disagree"
+        lane["m"].close()
+    first_lines = lanes[0]["text"][: int(lanes[0]["toff"][2])].tobytes().decode()
 
-    from bbmap_b200 import shard
-    ms_all, e2e_ms_step, kernel_ms_all = shard.max_over_ranks([ms, e2e_s * 1e3 / e2e_steps, kernel_ms], device=dev)
-    total_cells_step, = shard.sum_over_ranks([float(cells_per_step)], device=dev)
-    pipe_multi = None
-    if world > 1 and not args.no_stages:
-        # reads/s of the chained device stages with the read batches sharded over the ranks (index and reference replicated, no collective):
-        # every rank maps its own shard (seed = rank) between two barriers; aggregate = reads of all ranks / slowest rank
-        sys.path.insert(0, os.path.join(ROOT, "bench"))
-        import pipeline
-        barrier()
-        pr = pipeline.run(pairs=args.stage_pairs, device=local, cpu=False, seed=2 + rank)
-        pm, = shard.max_over_ranks([pr["ms"]], device=dev)
-        pn, = shard.sum_over_ranks([float(pr["reads"])], device=dev)
-        pipe_multi = {"n_gpus": world, "reads": int(pn), "ms_slowest_rank": pm, "reads_per_s": pn / (pm / 1e3), "scaling": "weak",
-                      "note": "bench/pipeline.py on every rank's own shard; see `pipeline` for the single-GPU stage split"}
+    ms_all, e2e_ms_step, msa_ms_all = shard.max_over_ranks([ms, e2e_s * 1e3 / e2e_steps, msa_ms_step])
+    reads_all, mapped_all, cells_all = shard.sum_over_ranks([float(n), float(mapped.sum()), float(cells_step)])
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        m.close()
         return
-    value = total_cells_step * args.steps / (ms_all / 1e3) / 1e9
-    e2e_value = total_cells_step / (e2e_ms_step / 1e3) / 1e9
-    pk, pk_kind = peaks()
-    # algorithmic HBM bytes per step: task + read + window + result + match string
-    cols = (tasks["ref_end"] - tasks["ref_start"] + 1).astype(np.int64)
-    alg_bytes = int(len(tasks) * (40 + 80) + tasks["read_len"].sum() + cols.sum() + np.maximum(outs["match_len"], 0).sum())
     step_s = ms_all / 1e3 / args.steps
-    hbm_ach = alg_bytes / step_s / 1e9
-    h2d = int(tasks.nbytes + reads.nbytes + moff.nbytes)
-    d2h = int(outs.nbytes + moff[-1])
-    line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic", "config": config,
-            "alignments_per_s": len(tasks) * world / step_s,
-            "computed_cells_gcups": float((tasks["read_len"].astype(np.int64) * cols).sum()) * world / step_s / 1e9,
-            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_step, "batches_in_flight": nfl},
+    value = reads_all / step_s
+    e2e_value = reads_all / (e2e_ms_step / 1e3)
+    pk, pk_kind = peaks()
+    h2d = int(R["bases"].nbytes + R["qual"].nbytes + R["off"].nbytes + nbuf.nbytes + noff.nbytes)
+    d2h = int(n * (MAP_REC_DTYPE.itemsize + SAM_OUT_DTYPE.itemsize) + sam_bytes + (n + 1) * 8)
+    cmp_peak = 2 * int_peaks.get("cmp_select", 0.0)
+    dp_s = msa_ms_all / 1e3
+    line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config_of(args),
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step, "batches_in_flight": nfl,
+                    "sam_bytes_per_step": sam_bytes},
             "gpu_launches": int(launches),
-            "kernel_mix": {"tasks": msa.stat("tasks_total"), "narrow_tried": msa.stat("narrow_tried"),
-                           "narrow_handed_over": msa.stat("narrow_handed_over"), "strip_tasks": msa.stat("strip_tasks"), "strip_units": msa.stat("strip_units"), "strip_lane_iters": msa.stat("strip_lane_iters"), "band_misses": msa.stat("band_misses")},
             "clocks": clocks,
+            "roofline": {"bound": "int-issue", "kernel": "MultiStateAligner11ts fills of the step (scoreSlow + slowRescue + realign_new: classify, narrow, strip prep/fill/finish, tiled, generic)",
+                         "achieved": cells_all / max(dp_s, 1e-9) * 45 / 1e9 / world, "peak": cmp_peak, "unit": "G lane-ops/s",
+                         "frac": (cells_all / world / max(dp_s, 1e-9) * 45 / 1e9) / max(cmp_peak, 1e-9), "traffic": None,
+                         "dp_ms_per_step": msa_ms_all, "dp_share_of_step": msa_ms_all / (ms_all / args.steps), "reference_cells_per_step_per_gpu": cells_all / world,
+                         "dp_gcups": cells_all / world / max(dp_s, 1e-9) / 1e9,
+                         "note": "achieved = reference cell visits of every alignment of the step (the reference's iterations counter) x the 45-lane-op floor of the 3-state "
+                                 "recurrence / the device time of the aligner batches (CUDA events); peak = 2 x the compare+select issue rate measured by bbm_int_peak in this run",
+                         "hbm_peak_gbs": pk["hbm_gbs"], "hbm_peak_kind": pk_kind},
             "int_peaks_glops": int_peaks,
-            "roofline_int": {"bound": "integer ALU issue (compare/select/min-max/logic; 64 lanes/clk/SM)",
-                             "evaluated_cells_per_s": evaluated_cells * world / step_s,
-                             "floor_lane_ops_per_cell": 45, "achieved": evaluated_cells * world / step_s * 45 / 1e9,
-                             "peak": 2 * int_peaks.get("cmp_select", 0.0) * world, "unit": "G lane-ops/s",
-                             "frac": (evaluated_cells / step_s * 45 / 1e9) / max(1e-9, 2 * int_peaks.get("cmp_select", 0.0)),
-                             "strip_lane_utilisation": strip_lane_util,
-                             "note": "achieved = cells the kernels evaluate x the 45-op floor of the 3-state recurrence (SURVEY 8d); peak = measured "
-                                     "compare+select issue rate of this GPU (bbm_int_peak); the kernels spend ~150 instructions per cell today"},
-            "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
-                         "traffic": TRAFFIC_NCU.get(args.tasks), "peak_kind": pk_kind,
-                         "note": "integer-issue-bound DP: algorithmic bytes/cell ~0.1; see DESIGN.md for the issue-slot roofline"}}
-    if not args.no_stages:
-        # the other kernels of the path on configs[1]-shaped input, each against the HBM roofline
-        sys.path.insert(0, os.path.join(ROOT, "bench"))
-        import stages
-        msa.close()
-        if pipe_multi is not None:
-            line["pipeline_all_gpus"] = pipe_multi
-        line["stages"] = stages.run(pairs=args.stage_pairs, device=local, hbm_peak=pk["hbm_gbs"])
-        # the same stages chained on the device up to the final site decision (mapped reads/s of the built part of the mapper)
-        import pipeline
-        line["pipeline"] = pipeline.run(pairs=args.stage_pairs, device=local)
+            "stage_ms": dict(zip(["seed_search", "lists", "scoreSlow", "rescue_pairing", "genMatchString_finish", "sam", "total"], (stage / args.steps).tolist())),
+            "mapping": {"mapped": float(mapped_all / reads_all), "paired": float(((recs["flags"] & 8) != 0).mean()), "rescued": float(((recs["flags"] & 16) != 0).mean()),
+                        "ambiguous": float(((recs["flags"] & 4) != 0).mean()), "top_site_is_origin": float(correct.mean()), "exact_start_and_stop": float(exact.mean()),
+                        "status_reads": int(st0["status_reads"]), "site_overflow_reads": int(st0["site_overflow_reads"]), "max_sites_used": int(st0["max_sites_used"]),
+                        "slow_alignments": int(st0["slow_alignments"]), "rescue_scans": int(st0["rescue_scans"]), "rescue_fills": int(st0["rescue_fills"]),
+                        "realign_fills": int(st0["realign_fills"]), "genmatch_rounds": int(st0["genmatch_rounds"]), "mated_pairs": int(st0["mated_pairs"]),
+                        "mean_inner_length": float(st0["inner_length_sum"]) / max(1, int(st0["mated_pairs"])), "first_sam_lines": first_lines},
+            "index_build_s": t_build}
+    m.close()
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_run(reads, genome, tasks, moff, args.bandwidth, args.ratio)
+        threads = os.cpu_count() or 1
+        npairs = args.cpu_pairs or max(threads * 150, 600)
+        order = sorted(range(len(table)), key=lambda i: table[i])
+        cr = cpu_chain(cb, co, table, R, names, [snames_all[i].encode() for i in order], npairs, threads)
+        line["cpu_baseline"] = {"value": cr["reads_per_s"], "unit": "reads/s", "cores": cr["threads"], "kind": "port",
+                                "sample": "first %d pairs of the step batch, %d worker processes, sequential C restatement of the chain incl. SAM text, %.1f s" % (npairs, cr["threads"], cr["seconds"]),
+                                "mapped": cr["mapped"] / cr["reads"]}
+    if not args.no_msa:
+        import msa_bench
+        a2 = argparse.Namespace(gpus=args.gpus, steps=min(args.steps, 5), warmup=3, tasks=args.msa_tasks, impl="cuda", bandwidth=0, ratio=0.0, no_cpu_baseline=False,
+                                lengths="100,150,250", no_narrow=False, no_strip=False, strip_budget_mb=0, narrow_slack=-1, strip_buckets=-1, no_stages=True, stage_pairs=0)
+        if world == 1:
+            line["msa"] = msa_bench.measure(a2, 0, 1, local)
+            if not args.no_extras:
+                sweep = []
+                for bw, ratio in ((12, 0.0), (40, 0.0), (0, 0.18)):
+                    a3 = argparse.Namespace(**vars(a2)); a3.bandwidth = bw; a3.ratio = ratio; a3.no_cpu_baseline = True; a3.tasks = min(args.msa_tasks, 400_000); a3.steps = 3
+                    r3 = msa_bench.measure(a3, 0, 1, local)
+                    sweep.append({"bandwidth": bw, "bandwidthRatio": ratio, "gcups": r3["value"], "e2e_gcups": r3["e2e"]["value"], "ms_per_step": r3["ms_per_step"],
+                                  "alignments_per_s": r3["alignments_per_s"], "band_misses": r3["kernel_mix"]["band_misses"]})
+                line["msa_band_sweep"] = sweep
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -353,6 +353,7 @@ typedef struct { int32_t near_perfect /* scoreNoIndels' return value */, flags /
 #define BBM_SL_TRIM 1
 #define BBM_SL_NOINDEL 2
 #define BBM_SL_FINAL 3
+#define BBM_SL_MERGE 4                /* Tools.mergeDuplicateSites(list, true, true) only (processReadPair, BBMapThread.java:1043,1059) */
 /* sites as BBIndex.find emits them -> SiteScore(chrom, strand, start, stop, hits, quickScore): score = quickScore (SiteScore.java:40-52) */
 int  bbm_sitelist_from_search_dev(bbm_ctx* ctx, const bbm_search_head* d_heads, const bbm_site* d_sites, int64_t nreads, int32_t max_sites,
                                   bbm_ss* d_lists, int32_t* d_nss, int32_t cap, void* stream);
@@ -436,6 +437,7 @@ int  bbm_scoreslow_host(bbm_ctx* ctx, bbm_ss* lists, const int32_t* nss, int64_t
 #define BBM_MAP_ST_ALIGNER         8   /* the aligner reported a per-task error (shape outside 601 x 3000) */
 #define BBM_MAP_ST_SITE_OVERFLOW  16   /* BBIndex.find emitted more sites than the mapper's site slots (the reference keeps an unbounded list) */
 #define BBM_MAP_ST_SLOW           32   /* scoreSlow reported a status bit for this read */
+#define BBM_MAP_ST_LIST_OVERFLOW   64   /* a rescued site did not fit the read's list (or the batch's rescue task slots) */
 typedef struct {                /* 80 bytes; defaults in bbmap_b200/mapper.py */
     int32_t paired;             /* reads 2i / 2i+1 are mates (processReadPair) */
     float min_ratio, min_ratio_paired, min_ratio_pre_rescue, secondary_site_score_ratio;   /* MINIMUM_ALIGNMENT_SCORE_RATIO* (AbstractMapThread.java:104-107) */
@@ -462,7 +464,11 @@ typedef struct {                /* what a call did (host) */
     int64_t reads, mapped, slow_alignments, realign_fills, site_overflow_reads, status_reads, sam_bytes;
     int32_t max_sites_used, genmatch_rounds;
     float ms_total, ms_seed_search, ms_lists, ms_slow, ms_genmatch, ms_sam;
-    int32_t pad_[2];
+    float ms_rescue; int32_t pad_;
+    int64_t rescue_scans, rescue_fills;         /* quickRescue scans / slowRescue alignments (pairs) */
+    int64_t mated_pairs, inner_length_sum;      /* numMated / innerLengthSum of this batch (AbstractMapThread.java:1543-1557): the host keeps the running
+                                                   AVERAGE_PAIR_DIST = innerLengthSum / numMated once numMated > 1000 (BBMapThread.java:1307-1309) and passes it
+                                                   with the next batch (bbm_map_cfg.average_pair_dist) */
 } bbm_map_stats;
 /* Scaffold table (bbm_sam_batch_* layout, host arrays) + scaffold names for RNAME (names_buf/name_off with nscaffolds+1 offsets; may be NULL: "*"). */
 int  bbm_map_set_scaffolds(bbm_ctx* ctx, const int32_t* scaf_off, const int32_t* scaf_loc, const int32_t* scaf_len, int32_t nchroms,
