@@ -5,6 +5,10 @@
 
 // =====================  k-mer index build + analysis  =====================
 void index_free(bbm_ctx* c) {
+    if (c->index_shared) {          // borrowed from another context (bbm_index_share): nothing to free here
+        c->iblocks.clear(); c->d_counts = nullptr; c->has_index = false; c->d_icfg = c->d_iblocks = nullptr; c->d_ihist = nullptr; c->d_chrom_off = nullptr;
+        c->index_shared = false; return;
+    }
     for (auto& b : c->iblocks) { if (b.starts) cudaFree(b.starts); if (b.sites) cudaFree(b.sites); }
     c->iblocks.clear();
     if (c->d_counts) cudaFree(c->d_counts);
@@ -268,3 +272,18 @@ extern "C" int bbm_search_batch_host(bbm_ctx* c, const int8_t* bases, const int8
     return BBM_OK;
 }
 
+
+// A second context on the same device that maps against the SAME resident index and reference (no copy): the reference keeps one index per
+// process and one MSA per mapping thread (AbstractMapThread.java:133-136); here a context is the unit that owns scratch buffers and a stream, so
+// several batches can be in flight against one index.  `src` must outlive `dst`.
+extern "C" int bbm_index_share(bbm_ctx* dst, bbm_ctx* src) {
+    if (!dst || !src || dst == src) return fail(BBM_E_ARG, "bbm_index_share: bad argument");
+    if (!src->has_index) return fail(BBM_E_ARG, "bbm_index_share: the source context has no index");
+    if (dst->device != src->device) return fail(BBM_E_ARG, "bbm_index_share: contexts live on different devices");
+    std::lock_guard<std::mutex> lk(dst->mu);
+    index_free(dst);
+    dst->iblocks = src->iblocks; dst->d_counts = src->d_counts; memcpy(dst->ihist, src->ihist, sizeof(dst->ihist)); dst->icfg = src->icfg;
+    dst->d_chroms = src->d_chroms; dst->chrom_off = src->chrom_off; dst->d_icfg = src->d_icfg; dst->d_iblocks = src->d_iblocks; dst->d_ihist = src->d_ihist;
+    dst->d_chrom_off = src->d_chrom_off; dst->has_index = true; dst->index_shared = true;
+    return BBM_OK;
+}

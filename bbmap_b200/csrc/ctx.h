@@ -135,7 +135,7 @@ struct bbm_ctx {
     bool seed_tables = false;
     struct IndexBlock { int* starts = nullptr; int* sites = nullptr; long long nsites = 0; int minChrom = 0, maxChrom = 0; };
     std::vector<IndexBlock> iblocks;
-    int* d_counts = nullptr; int ihist[1001]; bbm_index_cfg icfg; bool has_index = false;
+    int* d_counts = nullptr; int ihist[1001]; bbm_index_cfg icfg; bool has_index = false; bool index_shared = false;
     const int8_t* d_chroms = nullptr; std::vector<long long> chrom_off;
     void* d_icfg = nullptr; void* d_iblocks = nullptr; int* d_ihist = nullptr; long long* d_chrom_off = nullptr;
     DevBuf searchCtx, searchRev, d_srch[8];

@@ -225,6 +225,13 @@ __global__ void __launch_bounds__(STRIP_THREADS, STRIP_BLOCKS_PER_SM) msa_strip_
 
         // ---- phase B: one row of W cells (convergent) ----
         {
+#ifdef STRIP_PREFETCH
+            // the next row's records are one dependent global round trip away when phase A asks for them: start the fetch now, without a register
+            if (r < rows) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(A + r + 1));
+                if (s > 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + r + 1));
+            }
+#endif
             CellRow R;
             R.call1 = call1;
             R.call0 = call0;

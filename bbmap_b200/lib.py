@@ -16,7 +16,7 @@ EXPORTS = [
     "bbm_init", "bbm_destroy", "bbm_set_band", "bbm_last_error", "bbm_device_count", "bbm_upload", "bbm_free_dev",
     "bbm_msa_batch_dev", "bbm_msa_batch_host", "bbm_launch_count", "bbm_set_option", "bbm_get_stat", "bbm_int_peak", "bbm_banded_batch_dev", "bbm_banded_batch_host", "bbm_seed_batch_dev", "bbm_seed_batch_host", "bbm_noindel_batch_dev", "bbm_noindel_batch_host", "bbm_index_build", "bbm_index_block_sites", "bbm_index_download", "bbm_search_batch_dev", "bbm_search_batch_host", "bbm_msa_gapped_batch_dev", "bbm_msa_gapped_batch_host", "bbm_ingest_batch_dev", "bbm_ingest_batch_host", "bbm_sam_batch_dev", "bbm_sam_batch_host", "bbm_tipdel_batch_dev", "bbm_tipdel_batch_host", "bbm_rescue_batch_dev", "bbm_rescue_batch_host", "bbm_sitelist_from_search_dev", "bbm_sitelist_batch_dev", "bbm_sitelist_batch_host", "bbm_scoreslow_dev", "bbm_scoreslow_host", "bbm_sitelist_tipdel_dev", "bbm_sitelist_bounds_dev",
     "bbm_sitelist_clearzone3_dev", "bbm_sitelist_tip_penalty_dev", "bbm_sam_tasks_from_lists_dev",
-    "bbm_map_set_scaffolds", "bbm_map_batch_dev", "bbm_map_batch_host",
+    "bbm_map_set_scaffolds", "bbm_map_batch_dev", "bbm_map_batch_host", "bbm_index_share",
     "bbm_fillUnlimited", "bbm_fillLimitedX",
 ]
 
@@ -85,6 +85,7 @@ def load():
     L.bbm_sitelist_clearzone3_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.bbm_sitelist_tip_penalty_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bbm_sam_tasks_from_lists_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 5
+    L.bbm_index_share.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -88,6 +88,7 @@ class BBMapCUDA:
             enc = [names[i].encode() for i in order]
             no = np.zeros(len(enc) + 1, np.int64); np.cumsum([len(e) for e in enc], out=no[1:])
             nb = np.frombuffer(b"".join(enc) + b"\0", np.int8).copy()
+        self._names = (nb, no); self._device = device
         self.L.bbm_map_set_scaffolds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib.check(self.L.bbm_map_set_scaffolds(self.h, _p(self.scaf[0]), _p(self.scaf[1]), _p(self.scaf[2]), len(self.co) - 1, _p(nb), _p(no)), "bbm_map_set_scaffolds")
         self.L.bbm_map_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -95,8 +96,24 @@ class BBMapCUDA:
         self.L.bbm_map_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.c_void_p, C.c_void_p]
 
+    def clone(self):
+        """Another context on the same device that shares this mapper's resident index and reference (bbm_index_share): one per batch in flight."""
+        o = BBMapCUDA.__new__(BBMapCUDA)
+        o.L = self.L; o.cb, o.co, o.table, o.scaf = self.cb, self.co, self.table, self.scaf; o.index = None; o._names = self._names; o._parent = self
+        h = C.c_void_p()
+        _lib.check(self.L.bbm_init(self._device, C.byref(h)), "bbm_init")
+        o.h = h; o._device = self._device
+        _lib.check(self.L.bbm_index_share(o.h, self.h), "bbm_index_share")
+        nb, no = self._names
+        _lib.check(self.L.bbm_map_set_scaffolds(o.h, _p(self.scaf[0]), _p(self.scaf[1]), _p(self.scaf[2]), len(self.co) - 1, _p(nb), _p(no)), "bbm_map_set_scaffolds")
+        return o
+
     def close(self):
-        self.index.close()
+        if self.index is not None:
+            self.index.close()
+        elif getattr(self, "h", None):
+            self.L.bbm_destroy(self.h)
+        self.h = None
 
     def map_batch(self, bases, quality, read_off, cfg=None, names=None, name_off=None, match_stride=None, sam_cap=0):
         """bases/quality: concatenated bytes (quality = phred values or None), read_off int64[n+1].  Returns dict(recs, sam, match, match_stride, stats

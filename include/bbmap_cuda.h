@@ -161,6 +161,10 @@ typedef struct {        /* 80 bytes: the BBIndex statics as they stand after BBM
  * chrombits<0 = automatic (BBMap.java:317-321).  The index stays resident in the context. */
 int  bbm_index_build(bbm_ctx* ctx, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
                      bbm_index_cfg* cfg_out, int32_t* nblocks_out);
+/* Lets `dst` (same device) search and map against the index and reference resident in `src`, without copying them: one index per process, one
+ * context (scratch buffers + stream) per batch in flight, the way the reference keeps one index and one MSA per mapping thread
+ * (AbstractMapThread.java:133-136).  `src` must outlive `dst`. */
+int  bbm_index_share(bbm_ctx* dst, bbm_ctx* src);
 /* Sizes / contents for inspection and parity tests: nsites of a block; copies of starts[4^k+1], sites[nsites] of one block;
  * COUNTS[4^k] and lengthHistogram[1001] (either may be NULL). */
 int  bbm_index_block_sites(bbm_ctx* ctx, int32_t block, int64_t* nsites_out);
