@@ -126,3 +126,51 @@ def test_map_batch_pairs_equals_cpu_chain(kind, seed, L, sub, indel):
         assert ((f & 8) != 0).mean() > 0.9 and ((f & 16) != 0).sum() > 10          # most pairs mate; rescue placed some mates
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_map_batch_phix_fixture(paired):
+    """configs[0]: the reference's own 100 shipped phiX pairs (tests/golden/phix.npz) through bbm_map_batch_host: device == CPU chain, and the mapping
+    agrees with the origin the read names carry (the checks of tests/test_mapper_oracle.py)."""
+    from bbmap_b200.mapper import BBMapCUDA, mapper_cfg
+    from oracle import chain, oracle as orc
+    from test_mapper_oracle import _phix_pairs, check_mapping_invariants
+    from test_search_oracle import phix
+    d, _, _, _ = phix()
+    cb, co, table, bases, qual, off, truth = _phix_pairs()
+    m = BBMapCUDA([d["genome"]], names=["phiX"])
+    try:
+        assert np.array_equal(m.cb, cb)
+        o = orc.get()
+        idx = o.index_build(cb, co, 13, -1)
+        ref = (chain.map_pairs if paired else chain.map_single)(o, idx, cb, co, table, bases, qual, off)
+        dev = m.map_batch(bases, qual, off, cfg=mapper_cfg(paired=paired), match_stride=ref["match_stride"])
+        _compare(dev, ref, len(off) - 1)
+        dev["cigar"], dev["cigar_off"] = ref["cigar"], ref["cigar_off"]           # CIGAR text is a function of the (identical) records and match strings
+        check_mapping_invariants(dev, off, truth)
+    finally:
+        m.close()
+
+
+def test_map_batch_rescue_and_missing_mates():
+    from bbmap_b200.mapper import BBMapCUDA, mapper_cfg
+    from oracle import chain, oracle as orc
+    g = wl.random_genome(200_000, seed=41)
+    m = BBMapCUDA([g])
+    try:
+        R = wl.make_mapping_reads(m.cb, m.co, m.table, 400, seed=42, sub_rate=0.01, indel_rate=0.0)
+        L = 150
+        rng = np.random.Generator(np.random.PCG64(43))
+        bases = R["bases"].copy()
+        for r in [2 * i + 1 for i in range(0, 60)]:
+            v = bases[r * L:(r + 1) * L]
+            v[4::8] = wl.ACGT[(np.searchsorted(wl.ACGT, v[4::8]) + 1) % 4]
+        for r in [2 * i + 1 for i in range(100, 120)]:
+            bases[r * L:(r + 1) * L] = wl.ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        o = orc.get()
+        ref = chain.map_pairs(o, o.index_build(m.cb, m.co, 13, -1), m.cb, m.co, m.table, bases, R["qual"], R["off"])
+        dev = m.map_batch(bases, R["qual"], R["off"], cfg=mapper_cfg(paired=True), match_stride=ref["match_stride"])
+        _compare(dev, ref, len(R["off"]) - 1)
+        assert ((ref["recs"]["flags"] & 16) != 0).sum() >= 40 and int(dev["stats"]["rescue_scans"]) == ref["rescue_scans"]
+    finally:
+        m.close()
