@@ -249,28 +249,19 @@ __global__ void __launch_bounds__(STRIP_THREADS, STRIP_BLOCKS_PER_SM) msa_strip_
                 const bool good = visit && o.good;
                 word |= o.code << (4 * j);
                 gCur |= (good ? 1u : 0u) << j;
+                if (r == rows && visit) {
+                    // candidates of the final scan (jni/...JNI.c:672-686): state-major, first max wins
+                    const int s0 = nM & SMASK, s1 = nD & SMASK, s2 = nI & SMASK;
+                    if (s0 > bestScore || (s0 == bestScore && 0 < bestState)) { bestScore = s0; bestCol = c; bestState = 0; bestPacked = nM; }
+                    if (s1 > bestScore || (s1 == bestScore && 1 < bestState)) { bestScore = s1; bestCol = c; bestState = 1; bestPacked = nD; }
+                    if (s2 > bestScore) { bestScore = s2; bestCol = c; bestState = 2; bestPacked = nI; }
+                }
                 xM = MS[j]; xD = DL[j]; xI = IN[j];
                 MS[j] = nM; DL[j] = nD; IN[j] = nI;
                 yM = nM; yD = nD;
                 ref0 = rf[j];
             }
             tbT[(long long)s * rs + r] = word;
-            if (r == rows) {
-                // candidates of the final scan (jni/...JNI.c:672-686): state-major, first max wins.  Only on an alignment's last row, so out of the cell
-                // loop: the lanes of a warp sit on different rows and a predicated copy inside the loop would issue for every cell of every row.  A cell
-                // that was not visited holds subfloor in all three states and cannot beat a real candidate; if nothing else exists the finish kernel's
-                // "every visited cell of the last row holds subfloor" rule applies either way.
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const int c = c0 + j;
-                    if (c <= cols) {
-                        const int s0 = MS[j] & SMASK, s1 = DL[j] & SMASK, s2 = IN[j] & SMASK;
-                        if (s0 > bestScore || (s0 == bestScore && 0 < bestState)) { bestScore = s0; bestCol = c; bestState = 0; bestPacked = MS[j]; }
-                        if (s1 > bestScore || (s1 == bestScore && 1 < bestState)) { bestScore = s1; bestCol = c; bestState = 1; bestPacked = DL[j]; }
-                        if (s2 > bestScore) { bestScore = s2; bestCol = c; bestState = 2; bestPacked = IN[j]; }
-                    }
-                }
-            }
             if (gCur) {
                 const int old = mmRow;
                 const int first = c0 + __ffs(gCur) - 1, lastc = c0 + 31 - __clz(gCur);
