@@ -39,27 +39,35 @@ static void index_cfg_init(bbm_index_cfg* c, int k, int chrombits, long long num
     c->chroms_per_block = 1 << chrombits;
 }
 
+static int index_finalize(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, cudaStream_t st);
+
+// chrombits (automatic rule BBMap.java:317-321), the BBIndex statics for this genome; leaves the context without blocks
+static int index_begin(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits, cudaStream_t st) {
+    index_free(c);
+    long long maxLen = 0, total = chrom_off[nchroms] - chrom_off[0];
+    for (int i = 0; i < nchroms; ++i) maxLen = std::max<long long>(maxLen, chrom_off[i + 1] - chrom_off[i]);
+    if (chrombits < 0) { int nlz = maxLen == 0 ? 32 : __builtin_clz((unsigned)maxLen); chrombits = std::min(nlz - 1, 16); }
+    if (maxLen - 1 > (long long)(~((-1) << (32 - 1 - chrombits)))) return fail(BBM_E_ARG, "bbm_index_build: chromosome longer than MAX_ALLOWED_CHROM_INDEX for these chrombits");
+    unsigned long long* d_def = nullptr; CK(cudaMalloc(&d_def, 8)); CK(cudaMemsetAsync(d_def, 0, 8, st));
+    int e = bbm_index_count_defined(d_chroms + chrom_off[0], total, d_def, st);
+    if (e) return fail(BBM_E_CUDA, "count_defined", (cudaError_t)e);
+    unsigned long long nDefined = 0; CK(cudaMemcpyAsync(&nDefined, d_def, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(d_def);
+    c->launches++;
+    index_cfg_init(&c->icfg, keylen, chrombits, (long long)nDefined);
+    return BBM_OK;
+}
+
 extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
                                bbm_index_cfg* cfg_out, int32_t* nblocks_out) {
     if (!c || !d_chroms || !chrom_off || nchroms < 1 || keylen < 8 || keylen > 15) return fail(BBM_E_ARG, "bbm_index_build: bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    index_free(c);
     const auto t_build0 = std::chrono::steady_clock::now();
+    if (int rc = index_begin(c, d_chroms, chrom_off, nchroms, keylen, chrombits, st)) return rc;
     const int k = keylen;
     const long long keyspace = 1LL << (2 * k);
-    long long maxLen = 0, total = chrom_off[nchroms] - chrom_off[0];
-    for (int i = 0; i < nchroms; ++i) maxLen = std::max<long long>(maxLen, chrom_off[i + 1] - chrom_off[i]);
-    if (chrombits < 0) { int nlz = maxLen == 0 ? 32 : __builtin_clz((unsigned)maxLen); chrombits = std::min(nlz - 1, 16); }
-    if (maxLen - 1 > (long long)(~((-1) << (32 - 1 - chrombits)))) return fail(BBM_E_ARG, "bbm_index_build: chromosome longer than MAX_ALLOWED_CHROM_INDEX for these chrombits");
-    // numDefinedBases
-    unsigned long long* d_def = nullptr; CK(cudaMalloc(&d_def, 8)); CK(cudaMemsetAsync(d_def, 0, 8, st));
-    int e = bbm_index_count_defined(d_chroms + chrom_off[0], total, d_def, st);
-    if (e) return fail(BBM_E_CUDA, "count_defined", (cudaError_t)e);
-    unsigned long long nDefined = 0; CK(cudaMemcpyAsync(&nDefined, d_def, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(d_def);
-    c->launches++;
-    index_cfg_init(&c->icfg, k, chrombits, (long long)nDefined);
+    int e = 0;
     const int cpb = c->icfg.chroms_per_block, low = cpb - 1, shift = c->icfg.shift_length;
     // blocks: chromosomes sharing (chrom & ~low); chrom numbers are 1-based (IndexMaker4.makeIndex :44-62)
     for (int chrom = 1; chrom <= nchroms;) {
@@ -100,6 +108,18 @@ extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t
         c->iblocks.push_back(B);
         chrom = b + 1;
     }
+    if (int rc = index_finalize(c, d_chroms, chrom_off, nchroms, st)) return rc;
+    c->index_build_us = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_build0).count();
+    if (cfg_out) *cfg_out = c->icfg;
+    if (nblocks_out) *nblocks_out = (int)c->iblocks.size();
+    return BBM_OK;
+}
+
+// BBIndex.analyzeIndex over the blocks now resident (COUNTS, clumpy keys, lengthHistogram, the derived limits) + the device-side descriptors
+static int index_finalize(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, cudaStream_t st) {
+    const int k = c->icfg.keylen;
+    const long long keyspace = 1LL << (2 * k);
+    int e = 0;
     // analyzeIndex
     unsigned long long* d_clump = nullptr; int* d_max = nullptr;
     CK(cudaMalloc(&c->d_counts, (size_t)keyspace * 4)); CK(cudaMemsetAsync(c->d_counts, 0, (size_t)keyspace * 4, st));
@@ -147,8 +167,62 @@ extern "C" int bbm_index_build(bbm_ctx* c, const int8_t* d_chroms, const int64_t
         CK(cudaMalloc(&c->d_chrom_off, rel.size() * 8)); CK(cudaMemcpy(c->d_chrom_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice));
     }
     CK(cudaStreamSynchronize(st));
-    c->index_build_us = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_build0).count();
     c->has_index = true;
+    return BBM_OK;
+}
+
+// ---- index persistence in the reference's own on-disk format (formats in wire.cpp) ----
+// IndexMaker4.makeIndex writes every block it builds with Block.write (IndexMaker4.java:197-200); BBIndex/IndexMaker4 load it back with
+// Block.read when both files exist (:135-139).  root_index is the reference's Data.ROOT_INDEX ("<path>/ref/index/"), `build` its genome build number.
+extern "C" int bbm_index_save(bbm_ctx* c, const char* root_index, int32_t build) {
+    if (!c || !c->has_index || !root_index) return fail(BBM_E_ARG, "bbm_index_save: no index in this context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const long long nstarts = (1LL << (2 * c->icfg.keylen)) + 1;
+    std::vector<int32_t> starts((size_t)nstarts), sites;
+    for (const auto& B : c->iblocks) {
+        char fname[4096];
+        if (bbm_wire_block_fname(fname, sizeof fname, root_index, B.minChrom, B.maxChrom, c->icfg.keylen, c->icfg.chrombits, build)) return fail(BBM_E_ARG, bbm_wire_last_error());
+        sites.resize((size_t)std::max<long long>(B.nsites, 1));
+        CK(cudaMemcpy(starts.data(), B.starts, (size_t)nstarts * 4, cudaMemcpyDeviceToHost));
+        if (B.nsites) CK(cudaMemcpy(sites.data(), B.sites, (size_t)B.nsites * 4, cudaMemcpyDeviceToHost));
+        if (bbm_wire_write_block(fname, sites.data(), B.nsites, starts.data(), nstarts)) return fail(BBM_E_ARG, bbm_wire_last_error());
+    }
+    return BBM_OK;
+}
+
+extern "C" int bbm_index_load(bbm_ctx* c, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
+                              const char* root_index, int32_t build, bbm_index_cfg* cfg_out, int32_t* nblocks_out) {
+    if (!c || !d_chroms || !chrom_off || nchroms < 1 || keylen < 8 || keylen > 15 || !root_index) return fail(BBM_E_ARG, "bbm_index_load: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (int rc = index_begin(c, d_chroms, chrom_off, nchroms, keylen, chrombits, st)) return rc;
+    const int cpb = c->icfg.chroms_per_block, low = cpb - 1;
+    const long long nstartsWant = (1LL << (2 * keylen)) + 1;
+    for (int chrom = 1; chrom <= nchroms;) {
+        const int a = std::max(1, chrom & ~low), b = std::min(nchroms, (chrom & ~low) + cpb - 1);
+        char fname[4096];
+        if (bbm_wire_block_fname(fname, sizeof fname, root_index, a, b, keylen, c->icfg.chrombits, build)) { index_free(c); return fail(BBM_E_ARG, bbm_wire_last_error()); }
+        int32_t *sites = nullptr, *starts = nullptr; int64_t nsites = 0, nstarts = 0;
+        if (bbm_wire_read_block(fname, &sites, &nsites, &starts, &nstarts)) { index_free(c); return fail(BBM_E_ARG, bbm_wire_last_error()); }
+        bbm_ctx::IndexBlock B; B.minChrom = a; B.maxChrom = b; B.nsites = nsites;
+        cudaError_t ce = cudaSuccess;
+        if (nstarts != nstartsWant) ce = cudaErrorInvalidValue;
+        if (ce == cudaSuccess) ce = cudaMalloc(&B.starts, (size_t)nstarts * 4);
+        if (ce == cudaSuccess) ce = cudaMalloc(&B.sites, (size_t)std::max<int64_t>(nsites, 1) * 4);
+        if (ce == cudaSuccess) ce = cudaMemcpy(B.starts, starts, (size_t)nstarts * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess && nsites) ce = cudaMemcpy(B.sites, sites, (size_t)nsites * 4, cudaMemcpyHostToDevice);
+        bbm_wire_free(sites); bbm_wire_free(starts);
+        if (ce != cudaSuccess) {
+            if (B.starts) cudaFree(B.starts); if (B.sites) cudaFree(B.sites);
+            index_free(c);
+            return nstarts != nstartsWant ? fail(BBM_E_ARG, "bbm_index_load: the block on disk was built with another key length") : fail(BBM_E_CUDA, "bbm_index_load: upload", ce);
+        }
+        c->iblocks.push_back(B);
+        chrom = b + 1;
+    }
+    if (int rc = index_finalize(c, d_chroms, chrom_off, nchroms, st)) return rc;
     if (cfg_out) *cfg_out = c->icfg;
     if (nblocks_out) *nblocks_out = (int)c->iblocks.size();
     return BBM_OK;

@@ -64,7 +64,9 @@ def _p(a):
 class BBIndexCUDA:
     """Device-resident index of one packed reference (replicated per GPU)."""
 
-    def __init__(self, chrom_bytes, chrom_off, keylen=13, chrombits=-1, device=0, ctx=None):
+    def __init__(self, chrom_bytes, chrom_off, keylen=13, chrombits=-1, device=0, ctx=None, load_from=None, build=1):
+        """load_from: the reference's Data.ROOT_INDEX ("<path>/ref/index/") — read the blocks IndexMaker4 / `save` wrote there instead of building
+        (IndexMaker4.java:135-139); the analysis is recomputed on the device either way."""
         self.L = _lib.load()
         if self.L.bbm_device_count() <= 0:
             raise _lib.BbmError("no CUDA device visible: BBIndexCUDA has no CPU fallback")
@@ -81,8 +83,13 @@ class BBIndexCUDA:
         self.d_chroms = d
         self.cfg = np.zeros(1, INDEX_CFG_DTYPE)
         nb = C.c_int32(0)
-        _lib.check(self.L.bbm_index_build(self.h, d, _p(self.chrom_off), len(self.chrom_off) - 1, keylen, chrombits, _p(self.cfg), C.byref(nb)),
-                   "bbm_index_build")
+        if load_from is None:
+            _lib.check(self.L.bbm_index_build(self.h, d, _p(self.chrom_off), len(self.chrom_off) - 1, keylen, chrombits, _p(self.cfg), C.byref(nb)),
+                       "bbm_index_build")
+        else:
+            import os
+            _lib.check(self.L.bbm_index_load(self.h, d, _p(self.chrom_off), len(self.chrom_off) - 1, keylen, chrombits, os.fsencode(load_from), build, _p(self.cfg),
+                                             C.byref(nb)), "bbm_index_load")
         self.nblocks = nb.value
         self.keylen = keylen
 
@@ -90,6 +97,12 @@ class BBIndexCUDA:
         if self._own and getattr(self, "h", None):
             self.L.bbm_destroy(self.h)
         self.h = None
+
+    def save(self, root_index, build=1):
+        """Block.write for every block (IndexMaker4.java:197-200): <root_index><build>/chr<a>[-<b>]_index_k<k>_c<chrombits>_b<build>.block + ...block2.gz"""
+        import os
+        os.makedirs(os.path.join(root_index, str(build)), exist_ok=True)
+        _lib.check(self.L.bbm_index_save(self.h, os.fsencode(root_index), build), "bbm_index_save")
 
     def download(self, block=0):
         n = C.c_int64(0)

@@ -170,6 +170,37 @@ int  bbm_index_share(bbm_ctx* dst, bbm_ctx* src);
 int  bbm_index_block_sites(bbm_ctx* ctx, int32_t block, int64_t* nsites_out);
 int  bbm_index_download(bbm_ctx* ctx, int32_t block, int32_t* starts, int32_t* sites, int32_t* counts, int32_t* hist1001);
 
+/* ---- index persistence: the reference's own on-disk formats, host side, no device needed for the bbm_wire_* calls ----
+ * Files are Java ObjectOutputStream streams (current/fileIO/ReadWrite.java:200-240, :739-757); a name ending in .gz is gzipped
+ * (ReadWrite.getOutputStream :349-392).  Arrays returned by the readers are malloc'ed: release with bbm_wire_free.
+ * All return 0 or a negative BBM_E_* code with the reason in bbm_wire_last_error() (thread-local). */
+typedef struct {        /* ref/genome/<build>/summary.txt (dna/FastaToChromArrays2.java:229-250) */
+    int64_t chroms, bases, defined, undefined, contigs, scaffolds, interpad;
+    int32_t version, pad_;
+    char name[256];
+} bbm_genome_summary;
+const char* bbm_wire_last_error(void);
+void bbm_wire_free(void* p);
+/* ReadWrite.write(int[] x, fname) / ReadWrite.read(int[].class, fname) */
+int  bbm_wire_write_int_array(const char* path, const int32_t* data, int64_t n);
+int  bbm_wire_read_int_array(const char* path, int32_t** data_out, int64_t* n_out);
+/* IndexMaker4.fname (current/align2/IndexMaker4.java:477-488): <root_index><build>/chr<a>[-<b>]_index_k<k>_c<chrombits>_b<build>.block */
+int  bbm_wire_block_fname(char* out, size_t cap, const char* root_index, int minChrom, int maxChrom, int k, int chrombits, int build);
+/* Block.write / Block.read (current/align2/Block.java:74-160): `fname` holds int[] sites, `fname`+"2.gz" the delta-coded int[] starts
+ * (nstarts = 4^k + 1 entries). */
+int  bbm_wire_write_block(const char* fname, const int32_t* sites, int64_t nsites, const int32_t* starts, int64_t nstarts);
+int  bbm_wire_read_block(const char* fname, int32_t** sites, int64_t* nsites, int32_t** starts, int64_t* nstarts);
+/* dna.ChromosomeArray as chrN.chrom.gz (current/dna/ChromosomeArray.java:14-22,63-71,415-419; written FastaToChromArrays2.java:347-353) */
+int  bbm_wire_write_chrom(const char* path, int32_t chromosome, const int8_t* array, int32_t len, int32_t minIndex, int32_t maxIndex, int8_t strand);
+int  bbm_wire_read_chrom(const char* path, int32_t* chromosome, int8_t** array, int32_t* len, int32_t* minIndex, int32_t* maxIndex, int8_t* strand);
+int  bbm_wire_write_summary(const char* path, const bbm_genome_summary* g);
+int  bbm_wire_read_summary(const char* path, bbm_genome_summary* g);
+/* Writes every block of the resident index the way IndexMaker4.makeIndex does (IndexMaker4.java:197-200) / loads them back instead of
+ * building (:135-139; the analysis — COUNTS, lengthHistogram, derived limits — is recomputed on the device exactly as after a build). */
+int  bbm_index_save(bbm_ctx* ctx, const char* root_index, int32_t build);
+int  bbm_index_load(bbm_ctx* ctx, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
+                    const char* root_index, int32_t build, bbm_index_cfg* cfg_out, int32_t* nblocks_out);
+
 /* ---- index search: BBIndex.find (current/align2/BBIndex.java:403-639) — seeds -> candidate sites (SiteScore) ---- */
 #define BBM_MAX_GAPS 10
 #define BBM_ST_ANOMALY        1   /* extendScore located no base (the reference prints an anomaly and scores -99999) */

@@ -49,3 +49,46 @@ def test_index_build_parity(oracle, k, sizes, chrombits):
         assert (gc > 0).any()
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("k,sizes,chrombits", [(10, (60000, 5000, 80000), -1), (11, (30000,) * 5, 1)])
+def test_index_save_load_in_reference_format(oracle, tmp_path, k, sizes, chrombits):
+    """the resident index written the way IndexMaker4 writes it (Block.write) and loaded back instead of built; the files are checked
+    with the independent parser (tests/javaser.py) against the oracle's arrays, and the loaded index (+ its recomputed analysis) equals the built one."""
+    import os
+    import javaser
+    from bbmap_b200 import wire
+    from bbmap_b200.index import BBIndexCUDA, pack_chromosomes
+    scafs = _genome(100 + k, sizes)
+    bytes_, off, table = pack_chromosomes(scafs, max_length=120000)
+    ecfg, eblocks, ecounts, ehist = oracle.index_build(bytes_, off, k, chrombits)
+    root = str(tmp_path) + "/ref/index/"
+    idx = BBIndexCUDA(bytes_, off, keylen=k, chrombits=chrombits)
+    try:
+        idx.save(root, build=1)
+        cbits = int(idx.cfg[0]["chrombits"]); cpb = 1 << cbits; nch = len(off) - 1
+        names = sorted(os.listdir(root + "1"))
+        assert len(names) == 2 * idx.nblocks
+        b = 0; chrom = 1
+        while chrom <= nch:
+            lo = max(1, chrom & ~(cpb - 1)); hi = min(nch, (chrom & ~(cpb - 1)) + cpb - 1)
+            fname = wire.block_fname(root, lo, hi, k, cbits, 1)
+            es, et = eblocks[b]
+            assert javaser.parse_file(fname)["values"] == et.tolist()
+            delta = javaser.parse_file(fname + "2.gz")["values"]
+            assert delta[0] == int(es[0]) and delta[1:] == np.diff(es).tolist()
+            b += 1; chrom = hi + 1
+        assert b == idx.nblocks
+    finally:
+        idx.close()
+    idx2 = BBIndexCUDA(bytes_, off, keylen=k, chrombits=chrombits, load_from=root, build=1)
+    try:
+        assert idx2.cfg.tobytes() == ecfg.tobytes() and idx2.nblocks == len(eblocks)
+        for b, (es, et) in enumerate(eblocks):
+            gs, gt, gc, gh = idx2.download(b)
+            assert np.array_equal(gs, es) and np.array_equal(gt, et)
+        assert np.array_equal(gc, ecounts) and np.array_equal(gh, ehist)
+    finally:
+        idx2.close()
+    with pytest.raises(Exception, match="cannot open"):
+        BBIndexCUDA(bytes_, off, keylen=k, chrombits=chrombits, load_from=root, build=2)

@@ -22,7 +22,11 @@ def msa(request):
     m.close()
 
 
-def _compare(oracle, msa, reads, genome, tasks, bw=0, ratio=0.0, kind="port"):
+def _compare(oracle, msa, reads, genome, tasks, bw=0, ratio=0.0, kind=None):
+    """kind=None: the fills of the comparator are the reference's OWN C (oracle/_ref/libbbref.so, prebuilt, travels to the GPU box)
+    whenever it is there; the C restatement ("port") otherwise.  port == reference is a CPU test (tests/test_oracle_vs_reference.py)."""
+    if kind is None:
+        kind = "reference" if oracle.has_reference else "port"
     moff = wl.match_offsets(tasks)
     exp, emb, cells = oracle.run_batch(reads, genome, tasks, match_off=moff, bandwidth=bw, ratio=ratio, kind=kind, threads=8)
     msa.set_band(bw, ratio)
