@@ -5,6 +5,7 @@
 
 // =====================  k-mer index build + analysis  =====================
 void index_free(bbm_ctx* c) {
+    c->map_sites_hint = 0;
     if (c->index_shared) {          // borrowed from another context (bbm_index_share): nothing to free here
         c->iblocks.clear(); c->d_counts = nullptr; c->has_index = false; c->d_icfg = c->d_iblocks = nullptr; c->d_ihist = nullptr; c->d_chrom_off = nullptr;
         c->index_shared = false; return;

@@ -104,8 +104,11 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     if (int rc = run_ingest(c, d_bases, d_quality, d_off, n, maxLen, cfg->ingest_flags, basesM, (int*)B[MB_RFLAGS].p, st, nullptr)) return rc;
     if (int rc = run_seed(c, d_bases, d_quality, d_off, n, maxLen, &cfg->seed, maxK, nkeys, (int*)B[MB_OFFSETS].p, (int*)B[MB_KEYS].p, (int*)B[MB_KSCORES].p,
                           (int8_t*)B[MB_BSCORES].p, (int*)B[MB_OFFM].p, (int*)B[MB_KEYSM].p, st, nullptr)) return rc;
-    int maxSites = cfg->max_sites;
-    for (;;) {          // the reference keeps an unbounded ArrayList; here a read that overflows its slots sends the batch through the search again with more
+    // the reference keeps an unbounded ArrayList; here a read that overflows its slots sends the batch through the search again with more.  The size a
+    // batch ended up needing is remembered in the context, so the next batch against the same index starts there (human-scale repeats: 16 -> 64 slots
+    // meant three searches per batch, 465 of 746 ms).
+    int maxSites = std::max(cfg->max_sites, std::min(c->map_sites_hint, bbm_sitelist_max_cap()));
+    for (;;) {
         if (B[MB_SITES].ensure((size_t)n * maxSites * sizeof(bbm_site))) return fail(BBM_E_CUDA, "cudaMalloc site slots");
         if (int rc = run_search(c, d_bases, (const int8_t*)B[MB_BSCORES].p, d_off, n, nkeys, (const int*)B[MB_OFFSETS].p, (const int*)B[MB_KSCORES].p, maxK,
                                 paired ? 0 : 1, heads, (bbm_site*)B[MB_SITES].p, maxSites, maxLen, st, nullptr)) return rc;
@@ -118,6 +121,7 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     }
     const int cap = maxSites;
     S.max_sites_used = maxSites;
+    c->map_sites_hint = maxSites > cfg->max_sites ? maxSites : 0;
     S.ms_seed_search = T.lap(st);
 
     // ---- site lists up to the final policy ----

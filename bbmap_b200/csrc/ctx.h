@@ -145,7 +145,7 @@ struct bbm_ctx {
     PinBuf h_stage;
     // the batched mapper (capi_mapper.cu): working buffers of the chain, scaffold table, staging of the host entry point
     DevBuf mapBuf[64], mapScaf[6], mapHost[8];
-    int map_nchroms = 0, map_nscaf = 0, map_maxidx_for = -1; bool map_has_names = false; long long map_last_cs = 0, map_last_ms = 0;
+    int map_nchroms = 0, map_nscaf = 0, map_maxidx_for = -1; bool map_has_names = false; long long map_last_cs = 0, map_last_ms = 0; int map_sites_hint = 0;   // site slots per read the previous batch ended up needing
     std::vector<void*> uploads;
     long long launches = 0;
     double msa_ms = 0.0; long long msa_cells = 0; int msa_count = 0; DevBuf msaCells;     // device time of every run_msa so far; reference cells (with "msa_count")

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--msa-tasks", type=int, default=1_600_000)
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs of the CPU sample (0 = sized for ~20 s)")
     ap.add_argument("--in-flight", type=int, default=2, help="mapper contexts of the end-to-end arm (batches in flight)")
+    ap.add_argument("--opt", action="append", default=[], help="bbm_set_option key=value applied to every mapper context (A/B while tuning)")
     return ap.parse_args()
 
 
@@ -184,6 +185,9 @@ def main():
     cfg = mapper_cfg(paired=True, sam_text=True)
     L = m.L; h = m.h
     L.bbm_set_option(h, b"msa_count", 0)
+    opts = [(kv.split("=")[0].encode(), int(kv.split("=")[1])) for kv in args.opt]
+    for k_, v_ in opts:
+        _lib.check(L.bbm_set_option(h, k_, v_), "bbm_set_option")
 
     # ---- resident arm ----
     pad = lambda a, extra=64: torch.from_numpy(np.concatenate([a, np.zeros(extra, a.dtype)])).to(dev)
@@ -240,6 +244,8 @@ def main():
     lanes = []
     for k in range(nfl):
         mk = m if k == 0 else m.clone()
+        for k_, v_ in opts:
+            L.bbm_set_option(mk.h, k_, v_)
         lanes.append({"m": mk, "recs": pin(np.zeros(n * MAP_REC_DTYPE.itemsize, np.int8)), "sam": pin(np.zeros(n * SAM_OUT_DTYPE.itemsize, np.int8)),
                       "text": pin(np.zeros(sam_cap, np.int8)), "toff": pin(np.zeros(n + 1, np.int64)), "stats": np.zeros(1, MAP_STATS_DTYPE)})
 
