@@ -96,6 +96,7 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(BBM_E_ARG, "bbm_set_option: null");
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
     if (!strcmp(key, "strip_min_tasks")) { c->strip_min_tasks = value; return BBM_OK; }
+    if (!strcmp(key, "slow_lookahead")) { c->slow_lookahead = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "msa_count")) { c->msa_count = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }

@@ -177,24 +177,27 @@ extern "C" int bbm_sam_tasks_from_lists_dev(bbm_ctx* c, const bbm_ss* d_lists, c
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
                                     const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, bbm_gapped_task* gtasks, int* gaps,
-                                    const bbm_msa_out* gouts, int* counters, cudaStream_t st);
+                                    const bbm_msa_out* gouts, int* counters, int window, int* slots, bbm_ss* backup, cudaStream_t st);
 extern "C" int bbm_scoreslow_state_ints();
 int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t nreads, int32_t cap, const int64_t* d_read_off,
                             const int8_t* d_basesP, const int8_t* d_basesM, const int8_t* d_refs, const int64_t* d_chrom_off, const int32_t* d_run,
                             const bbm_slow_cfg* cfg, int32_t* d_status, int32_t max_read_len, cudaStream_t st, int64_t* alignments_out, float* ms_out) {
     const int SI = bbm_scoreslow_state_ints();
     DevBuf &state = c->slowBuf[0], &tasks = c->slowBuf[1], &outs = c->slowBuf[2], &counters = c->slowBuf[3];
-    DevBuf &gtasks = c->slowBuf[4], &gaps = c->slowBuf[5], &gouts = c->slowBuf[6];
-    if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(16) ||
+    DevBuf &gtasks = c->slowBuf[4], &gaps = c->slowBuf[5], &gouts = c->slowBuf[6], &slots = c->slowBuf[7], &backup = c->slowBuf[8];
+    // `nreads` sites can be in flight in one round (one per read in the first round, a window of several for the few reads still active later)
+    if (state.ensure((size_t)nreads * SI * 4) || tasks.ensure((size_t)nreads * sizeof(bbm_msa_task)) || outs.ensure((size_t)nreads * sizeof(bbm_msa_out)) || counters.ensure(32) ||
+        slots.ensure((size_t)nreads * SI * 4) || backup.ensure((size_t)nreads * sizeof(bbm_ss)) ||
         gtasks.ensure((size_t)nreads * sizeof(bbm_gapped_task)) || gaps.ensure((size_t)nreads * BBM_MAX_GAPS * 4) || gouts.ensure((size_t)nreads * sizeof(bbm_msa_out)))
         return fail(BBM_E_CUDA, "cudaMalloc scoreSlow scratch");
     int rc = BBM_OK; int64_t aligned = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    int window = 1;
     auto launch = [&](int phase, int k) -> int {
         int e = bbm_launch_scoreslow(phase, k, d_lists, d_nss, nreads, cap, (const long long*)d_read_off, d_basesP, d_basesM, d_refs, (const long long*)d_chrom_off,
                                      d_run, cfg, (int*)state.p, (bbm_msa_task*)tasks.p, (const bbm_msa_out*)outs.p, (bbm_gapped_task*)gtasks.p, (int*)gaps.p,
-                                     (const bbm_msa_out*)gouts.p, (int*)counters.p, st);
+                                     (const bbm_msa_out*)gouts.p, (int*)counters.p, window, (int*)slots.p, (bbm_ss*)backup.p, st);
         if (e) return fail(BBM_E_CUDA, "scoreslow_kernel launch", (cudaError_t)e);
         c->launches++;
         return BBM_OK;
@@ -206,19 +209,23 @@ int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t 
     };
     const bool trace = getenv("BBM_SLOW_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    for (int k = 0; k < cap && rc == BBM_OK; ++k) {
+    if (cudaMemsetAsync(counters.p, 0, 32, st) != cudaSuccess) return fail(BBM_E_CUDA, "memset");
+    const int lookahead = c->slow_lookahead > 0 ? (c->slow_lookahead > 64 ? 64 : c->slow_lookahead) : 1;
+    long long activePrev = nreads;
+    for (int k = 0; k <= cap && rc == BBM_OK; ++k) {
         int h[3] = {0, 0, 0};
         const double t0 = now();
-        if (cudaMemsetAsync(counters.p, 0, 12, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
+        // sites in flight <= reads still active x window <= nreads (the size of the slot pool and of the request lists)
+        window = (int)std::max<long long>(1, std::min<long long>(lookahead, nreads / std::max<long long>(1, activePrev)));
+        if (cudaMemsetAsync(counters.p, 0, 16, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
         if ((rc = launch(0, k)) || (rc = counts(h))) break;
-        if (trace) fprintf(stderr, "[scoreSlow] round %d: %d reads active, %d + %d (gapped) alignments requested (prep %.2f ms)\n", k, h[0], h[1], h[2], now() - t0);
-        if (h[0] == 0) break;                                   // no read has a k-th site
+        if (trace) fprintf(stderr, "[scoreSlow] round %d (window %d): %d reads active, %d + %d (gapped) alignments requested (prep %.2f ms)\n", k, window, h[0], h[1], h[2], now() - t0);
+        if (h[0] == 0) break;                                   // no read has a site left
+        activePrev = h[0];
         if (h[1] > 0) {
-            aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if (h[2] > 0) {
-            aligned += h[2];
             if ((rc = run_msa_gapped(c, d_basesP, d_refs, (const bbm_gapped_task*)gtasks.p, (const int32_t*)gaps.p, (bbm_msa_out*)gouts.p, h[2], nullptr, nullptr, st, nullptr))) break;
         }
         if (cudaMemsetAsync(counters.p, 0, 12, st) != cudaSuccess) { rc = fail(BBM_E_CUDA, "memset"); break; }
@@ -226,15 +233,20 @@ int scoreslow_locked(bbm_ctx* c, bbm_ss* d_lists, const int32_t* d_nss, int64_t 
         if ((rc = launch(1, k)) || (rc = counts(h))) break;
         if (trace) fprintf(stderr, "[scoreSlow]   %d + %d (gapped) padding retries\n", h[1], h[2]);
         if (h[1] > 0) {
-            aligned += h[1];
             if ((rc = run_msa(c, d_basesP, d_refs, (const bbm_msa_task*)tasks.p, (bbm_msa_out*)outs.p, h[1], nullptr, nullptr, max_read_len, 0, st, nullptr, nullptr))) break;
         }
         if (h[2] > 0) {
-            aligned += h[2];
             if ((rc = run_msa_gapped(c, d_basesP, d_refs, (const bbm_gapped_task*)gtasks.p, (const int32_t*)gaps.p, (bbm_msa_out*)gouts.p, h[2], nullptr, nullptr, st, nullptr))) break;
         }
         if ((rc = launch(2, k))) break;
         if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[scoreSlow]   round done at %.2f ms\n", now() - t0); }
+    }
+    if (rc == BBM_OK) {          // alignments behind the results that were applied (requests thrown away by the look-ahead are not the reference's work)
+        int na = 0;
+        cudaError_t ce = cudaMemcpyAsync(&na, (const int*)counters.p + 4, 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) rc = fail(BBM_E_CUDA, "scoreSlow counters", ce);
+        aligned = na;
     }
     if (rc == BBM_OK && d_status) {
         cudaError_t ce = cudaMemcpy2DAsync(d_status, 4, (const int*)state.p + 14, (size_t)SI * 4, 4, (size_t)nreads, cudaMemcpyDeviceToDevice, st);

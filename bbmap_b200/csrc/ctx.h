@@ -124,7 +124,8 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
     long long strip_min_tasks = 8192;
-    DevBuf slowBuf[7];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results
+    int slow_lookahead = 16;                   // scoreSlow: sites of one read taken per round after its first (1 = one site per round, the round-1 schedule)
+    DevBuf slowBuf[9];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")
     DevBuf stripScratch;
     long long strip_tasks = 0, index_build_us = 0;

@@ -266,13 +266,22 @@ __global__ void __launch_bounds__(128) sitelist_tipdel_kernel(TipParams P) {
 // Default flags only: QUICK_MATCH_STRINGS=false (no traceback / fixXY / clipTipIndels inside scoreSlow).  Sites that carry a gap array go to
 // the gapped aligner (bbm_msa_gapped: makeGref on the device) as a second packed request list; SiteScore.setLimits / setStop keep the gap
 // array consistent through GapTools.fixGaps (GapTools.java:26-72,126-175; stream/SiteScore.java:905-914,943-958).
+//
+// Look-ahead.  The ONLY state scoreSlow carries from one site of a read to the next is minMsaLimit (minMatch matters to QUICK_MATCH_STRINGS alone), and a
+// site sees it only through minscore = max(swscoreNoIndel, minMsaLimit).  So from a read's second site on, a round takes a WINDOW of its next sites at
+// once, each prepared with the limit as it stands, and SLOW_APPLY walks the window in list order: a site whose minscore would be different under the
+// limit as ratcheted by the sites before it is put back exactly as it was (a copy is kept) together with everything behind it, and waits for the next
+// round.  Every result that is applied was therefore computed with the very limit the reference would have used; sites are sorted best-first, so the
+// limit almost never moves after the first site and a read from a 64-copy repeat takes 5 rounds instead of 64 (human-scale scoreSlow 185 -> see DESIGN).
 struct SlowParams {
-    int phase, round; bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off;
+    int phase, round, window; bbm_ss* lists; const int* nss; long long nreads; int cap; const long long* read_off;
     const int8_t* basesP; const int8_t* basesM; const int8_t* refs; const long long* chrom_off; const int* run;
-    bbm_slow_cfg cfg; int* state;       // [nreads][20]: 0 minMsaLimit, 1 minMatch, 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 14 status, 15 slot, 16 gapped request
+    bbm_slow_cfg cfg; int* state;       // [nreads][20]: 0 minMsaLimit, 1 minMatch, 14 status, 17 cursor (next site), 18 first slot of this round's window, 19 window length
+    int* slots;                         // [pool][20] per site in flight: 2 aligned, 3 expectedLen, 4 minscore, 5 old_len, 6..13 old[8], 15 request slot, 16 gapped request, 17 swscoreNoIndel
+    bbm_ss* backup;                     // [pool] the site as it was before SLOW_PREP touched it
     bbm_msa_task* tasks; const bbm_msa_out* outs;                  // plain requests, packed
     bbm_gapped_task* gtasks; int* gaps; const bbm_msa_out* gouts;  // gapped requests, packed; gap arrays at gaps[slot * BBM_MAX_GAPS]
-    int* counters;                                                 // [0] reads active in this round, [1] plain requests, [2] gapped requests
+    int* counters;                                                 // [0] reads active in this round, [1] plain requests, [2] gapped requests, [3] slot pool cursor, [4] alignments applied (whole call)
 };
 constexpr int SLOW_PREP = 0, SLOW_RETRY = 1, SLOW_APPLY = 2;
 constexpr int SLOW_STATE = 20;
@@ -301,54 +310,74 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.nreads) return;
     int* st = P.state + r * SLOW_STATE;
-    const int k = P.round;
-    const bool active = P.run[r] != 0 && k < P.nss[r];
     const int len = (int)(P.read_off[r + 1] - P.read_off[r]);
     const bbm_slow_cfg& cfg = P.cfg;
     if (P.phase == SLOW_PREP) {
-        if (k == 0) {
+        if (P.round == 0) {
             const int maxSw = max_quality(len);
             const int lim = -cfg.clearzone1e + (int)__fmul_rn(cfg.paired ? cfg.min_ratio_pre_rescue : cfg.min_ratio, (float)maxSw);
-            st[0] = lim; st[1] = imax(-300, lim - cfg.clearzone3); st[14] = 0;
+            st[0] = lim; st[1] = imax(-300, lim - cfg.clearzone3); st[14] = 0; st[17] = 0;
         }
-        st[2] = 0;
-        if (active) {
+        const int cur = st[17], n = P.nss[r];
+        st[19] = 0;
+        if (P.run[r] != 0 && cur < n) {
             atomicAdd(P.counters, 1);
-            bbm_ss ss = P.lists[r * P.cap + k];
-            if (ss.stop - ss.start != len - 1) { set_slow_score(ss, 0); ss.semiperfect = 0; ss.perfect = 0; }
-            const int sw = ss.slow_score;
-            if (sw < max_imperfect(len) && !ss.semiperfect) {
-                const int expectedLen = calc_gref_len(ss);
-                if (expectedLen >= cfg.expected_len_limit) ss_set_stop(ss, ss.start + imin(len + 40, cfg.expected_len_limit));
-                const int minscore = imax(sw, st[0]);
-                st[2] = 1; st[3] = expectedLen; st[4] = minscore;
-                slow_request(P, r, len, ss, cfg.slow_align_padding, minscore, st);
+            const int w = (cur < 1) ? 1 : imin(P.window, n - cur);       // the first site sets the limit every later one is judged by
+            const int base = atomicAdd(P.counters + 3, w);
+            st[18] = base; st[19] = w;
+            for (int g = 0; g < w; g++) {
+                const int k = cur + g;
+                int* ps = P.slots + (long long)(base + g) * SLOW_STATE;
+                bbm_ss ss = P.lists[r * P.cap + k];
+                P.backup[base + g] = ss;
+                ps[2] = 0;
+                if (ss.stop - ss.start != len - 1) { set_slow_score(ss, 0); ss.semiperfect = 0; ss.perfect = 0; }
+                const int sw = ss.slow_score;
+                if (sw < max_imperfect(len) && !ss.semiperfect) {
+                    const int expectedLen = calc_gref_len(ss);
+                    if (expectedLen >= cfg.expected_len_limit) ss_set_stop(ss, ss.start + imin(len + 40, cfg.expected_len_limit));
+                    const int minscore = imax(sw, st[0]);
+                    ps[2] = 1; ps[3] = expectedLen; ps[4] = minscore; ps[17] = sw;
+                    slow_request(P, r, len, ss, cfg.slow_align_padding, minscore, ps);
+                }
+                P.lists[r * P.cap + k] = ss;
             }
-            P.lists[r * P.cap + k] = ss;
         }
     } else if (P.phase == SLOW_RETRY) {
-        if (active && st[2] == 1) {
-            const bbm_msa_out o = st[16] ? P.gouts[st[15]] : P.outs[st[15]];
-            if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
+        const int cur = st[17], w = st[19], base = st[18];
+        for (int g = 0; g < w; g++) {
+            int* ps = P.slots + (long long)(base + g) * SLOW_STATE;
+            if (ps[2] != 1) continue;
+            const int k = cur + g;
+            const bbm_msa_out o = ps[16] ? P.gouts[ps[15]] : P.outs[ps[15]];
+            if (o.status != 0) ps[18] = BBM_SLOW_ALIGNER_ERROR; else ps[18] = 0;
             const int n = (o.status == 0) ? o.score_len : 0;
-            st[5] = n;
+            ps[5] = n;
 #pragma unroll
-            for (int q = 0; q < 8; q++) st[6 + q] = o.score[q];
-            if (n > 6 && (o.score[3] + o.score[4] + st[3] < cfg.expected_len_limit)) {
+            for (int q = 0; q < 8; q++) ps[6 + q] = o.score[q];
+            if (n > 6 && (o.score[3] + o.score[4] + ps[3] < cfg.expected_len_limit)) {
                 bbm_ss ss = P.lists[r * P.cap + k];
                 ss_set_limits(ss, ss.start - o.score[6], ss.stop + o.score[7]);
-                st[2] = 2;
-                slow_request(P, r, len, ss, cfg.slow_align_padding + cfg.extra_padding, st[4], st);
+                ps[2] = 2;
+                slow_request(P, r, len, ss, cfg.slow_align_padding + cfg.extra_padding, ps[4], ps);
                 P.lists[r * P.cap + k] = ss;
             }
         }
     } else {
-        if (active) {
+        const int cur = st[17], w = st[19], base = st[18];
+        for (int g = 0; g < w; g++) {
+            const int k = cur + g;
+            const int* ps = P.slots + (long long)(base + g) * SLOW_STATE;
+            if (g > 0 && ps[2] >= 1 && imax(ps[17], st[0]) != ps[4]) {
+                // the limit moved under this request: the site and everything behind it go back to what they were and are asked again next round
+                for (int q = g; q < w; q++) P.lists[r * P.cap + cur + q] = P.backup[base + q];
+                break;
+            }
             bbm_ss ss = P.lists[r * P.cap + k];
             int n = 0, a0 = 0, a1 = 0, a2 = 0;
-            if (st[2] >= 1) { n = st[5]; a0 = st[6]; a1 = st[7]; a2 = st[8]; }
-            if (st[2] == 2) {
-                const bbm_msa_out o = st[16] ? P.gouts[st[15]] : P.outs[st[15]];
+            if (ps[2] >= 1) { n = ps[5]; a0 = ps[6]; a1 = ps[7]; a2 = ps[8]; st[14] |= ps[18]; atomicAdd(P.counters + 4, ps[2]); }
+            if (ps[2] == 2) {
+                const bbm_msa_out o = ps[16] ? P.gouts[ps[15]] : P.outs[ps[15]];
                 if (o.status != 0) st[14] |= BBM_SLOW_ALIGNER_ERROR;
                 const int n2 = (o.status == 0) ? o.score_len : 0;
                 if (!(n2 == 0 || o.score[0] < a0)) { n = n2; a0 = o.score[0]; a1 = o.score[1]; a2 = o.score[2]; }
@@ -365,7 +394,9 @@ __global__ void __launch_bounds__(128) scoreslow_kernel(SlowParams P) {
                 ss_set_perfect(ss, bases, len, P.refs + P.chrom_off[ss.chrom - 1], (int)(P.chrom_off[ss.chrom] - P.chrom_off[ss.chrom - 1]));
             }
             P.lists[r * P.cap + k] = ss;
+            st[17] = k + 1;
         }
+        st[19] = 0;
     }
 }
 
@@ -549,8 +580,9 @@ extern "C" int bbm_launch_sitelist_from_search(const bbm_search_head* heads, con
 extern "C" int bbm_launch_scoreslow(int phase, int round, bbm_ss* lists, const int* nss, long long nreads, int cap, const long long* read_off,
                                     const int8_t* basesP, const int8_t* basesM, const int8_t* refs, const long long* chrom_off, const int* run,
                                     const bbm_slow_cfg* cfg, int* state, bbm_msa_task* tasks, const bbm_msa_out* outs, bbm_gapped_task* gtasks, int* gaps,
-                                    const bbm_msa_out* gouts, int* counters, cudaStream_t st) {
+                                    const bbm_msa_out* gouts, int* counters, int window, int* slots, bbm_ss* backup, cudaStream_t st) {
     bbm::SlowParams P;
+    P.window = window; P.slots = slots; P.backup = backup;
     P.phase = phase; P.round = round; P.lists = lists; P.nss = nss; P.nreads = nreads; P.cap = cap; P.read_off = read_off; P.basesP = basesP;
     P.basesM = basesM; P.refs = refs; P.chrom_off = chrom_off; P.run = run; P.cfg = *cfg; P.state = state; P.tasks = tasks; P.outs = outs; P.gtasks = gtasks; P.gaps = gaps; P.gouts = gouts;
     P.counters = counters;
