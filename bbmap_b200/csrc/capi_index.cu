@@ -281,6 +281,16 @@ int run_search(bbm_ctx* c, const int8_t* db, const int8_t* dbs, const int64_t* d
                 c->launches++;
                 if (maxKeys <= 32) continue;
             }
+            if (ph == 4 && c->search_split >= 3) {
+                // slowWalk3 / extendScore with one warp per read; reads with more than 32 keys are left to the thread-per-read launch that follows
+                CK(cudaMemsetAsync(cb + 202, 0, 4, st));
+                int wblocks = c->sms * 8; const long long wneed = (nreads + 3) / 4; if (wneed < wblocks) wblocks = (int)wneed;
+                int e = bbm_launch_search_walk_warp((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, c->d_chroms, c->d_chrom_off, db, dbs,
+                                                    (const long long*)doff, nreads, dn, maxKeys, quit2, dh, ds, maxSites, cb + 202, wblocks, (int*)c->searchRev.p, stride, st);
+                if (e) return fail(BBM_E_CUDA, "walk_warp_kernel launch", (cudaError_t)e);
+                c->launches++;
+                if (maxKeys <= 32) continue;
+            }
             CK(cudaMemsetAsync(cb + 202, 0, 4, st));
             int e = bbm_launch_search((const bbm_index_cfg*)c->d_icfg, c->d_iblocks, nblk, nchr, c->d_counts, c->d_ihist, c->d_chroms, c->d_chrom_off, db, dbs,
                                       (const long long*)doff, nreads, dn, dof, dks, maxKeys, quit2, dh, ds, maxSites, c->searchCtx.p, cb + 202, prof, blocks,

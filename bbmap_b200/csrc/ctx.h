@@ -65,6 +65,10 @@ extern "C" int bbm_launch_sam(const bbm_sam_task* tasks, long long n, const int8
 extern "C" int bbm_search_threads();
 extern "C" size_t bbm_search_pool_bytes();
 extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks);
+extern "C" int bbm_launch_search_walk_warp(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int8_t* d_chroms,
+                                           const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores, const long long* read_off, long long nreads,
+                                           const int* nkeys, int maxKeys, int quit2, bbm_search_head* heads, bbm_site* sites, int maxSites, unsigned int* counter, int blocks,
+                                           int* mid, int midStride, cudaStream_t st);
 extern "C" int bbm_launch_search_prescan_warp(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts,
                                               const long long* read_off, long long nreads, const int* nkeys, int maxKeys, bbm_search_head* heads,
                                               unsigned int* counter, int blocks, int* mid, int midStride, cudaStream_t st);
@@ -122,7 +126,7 @@ struct bbm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t gstream = nullptr; cudaEvent_t gev0 = nullptr, gev1 = nullptr;   // side stream for the row-sequential kernel (a few long alignments: pure latency)
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
-    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 2;
+    int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 3;
     long long strip_min_tasks = 8192;
     int slow_lookahead = 16;                   // scoreSlow: sites of one read taken per round after its first (1 = one site per round, the round-1 schedule)
     DevBuf slowBuf[9];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results

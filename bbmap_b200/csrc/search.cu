@@ -807,7 +807,7 @@ __device__ void search_read(const SearchIndex* X, const int8_t* basesP, int len,
         // minus strand: KeyRing.reverseOffsets / reverseComplementKeys
         for (int i = 0; i < n; i++) { offsetsM[i] = len - (offsetsP[n - 1 - i] + K); keysM[i] = rcomp_fast_dev(keysP[n - 1 - i], K); keyScoresM[i] = keyScoresP[n - 1 - i]; }
         if (mid) {
-            mid[0] = n; mid[1] = numHits; mid[2] = c->status; mid[10] = 0; mid[11] = 0;
+            mid[0] = n; mid[1] = numHits; mid[2] = c->status; mid[10] = 0; mid[11] = 0; mid[12] = 0;
             int* a = mid + MID_HDR;
             for (int i = 0; i < n; i++) { a[i] = keysP[i]; a[MK + i] = keysM[i]; a[2 * MK + i] = offsetsP[i]; a[3 * MK + i] = offsetsM[i]; a[4 * MK + i] = keyScoresP[i]; a[5 * MK + i] = keyScoresM[i]; }
         }
@@ -944,6 +944,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SHARED ? 7 : 8) search_kernel(
         if ((long long)r >= P.nreads) break;
         bbm_search_head* H = P.heads + r;
         if (P.phases & 1) { bbm_search_head z = {}; *H = z; }
+        if (P.phases == 4 && P.mid) { const int* m = P.mid + (long long)r * P.midStride; if (m[0] >= 1 && m[0] <= 32 && m[12] == 1) continue; }   // walked by walk_warp_kernel
         ReadState R; R.sites = P.sites + (long long)r * P.maxSites; R.maxSites = P.maxSites; R.nsites = 0;
         const long long o = P.read_off[r]; const int len = (int)(P.read_off[r + 1] - o);
         const int nk = P.nkeys[r];
@@ -1236,6 +1237,8 @@ __global__ void __launch_bounds__(PW_WARPS * 32) prescan_warp_kernel(SearchParam
     }
 }
 
+#include "search_walk_warp.cuh"
+
 }  // namespace bbm
 
 using namespace bbm;
@@ -1249,6 +1252,19 @@ extern "C" int bbm_launch_search_prescan_warp(const bbm_index_cfg* d_cfg, const 
     P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts;
     P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.maxKeys = maxKeys; P.heads = heads; P.counter = counter; P.mid = mid; P.midStride = midStride;
     prescan_warp_kernel<<<blocks, PW_WARPS * 32, 0, st>>>(P);
+    return (int)cudaGetLastError();
+}
+extern "C" int bbm_launch_search_walk_warp(const bbm_index_cfg* d_cfg, const void* d_blocks, int nblocks, int nchroms, const int* d_counts, const int8_t* d_chroms,
+                                           const long long* d_chrom_off, const int8_t* bases, const int8_t* baseScores, const long long* read_off, long long nreads,
+                                           const int* nkeys, int maxKeys, int quit2, bbm_search_head* heads, bbm_site* sites, int maxSites, unsigned int* counter, int blocks,
+                                           int* mid, int midStride, cudaStream_t st) {
+    SearchParams P;
+    memset(&P, 0, sizeof P);
+    P.X.cfg = d_cfg; P.X.blocks = (const SearchBlock*)d_blocks; P.X.nblocks = nblocks; P.X.nchroms = nchroms; P.X.counts = d_counts;
+    P.X.chroms = d_chroms; P.X.chrom_off = d_chrom_off;
+    P.bases = bases; P.baseScores = baseScores; P.read_off = read_off; P.nreads = nreads; P.nkeys = nkeys; P.maxKeys = maxKeys; P.quitAfterTwoPerfects = quit2;
+    P.heads = heads; P.sites = sites; P.maxSites = maxSites; P.counter = counter; P.phases = 4; P.mid = mid; P.midStride = midStride;
+    walk_warp_kernel<<<blocks, WW_WARPS * 32, 0, st>>>(P);
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_search_mid_stride(int maxKeys, int nblocks) { return MID_HDR + 6 * maxKeys + 4 * nblocks; }

@@ -22,7 +22,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def search_batch(index, bases, baseScores, read_off, seeds, max_sites=MAX_SITES, quit_after_two_perfects=True, shared=False, split=2):
+def search_batch(index, bases, baseScores, read_off, seeds, max_sites=MAX_SITES, quit_after_two_perfects=True, shared=False, split=3):
     """BBIndex.find for a batch of reads against `index` (a bbmap_b200.index.BBIndexCUDA).  `seeds` is the dict returned by
     KeyRingCUDA.seed_batch (nkeys, offsets, keyScores).  Returns (heads HEAD_DTYPE[n], sites SITE_DTYPE[n, max_sites])."""
     L = index.L
@@ -33,7 +33,7 @@ def search_batch(index, bases, baseScores, read_off, seeds, max_sites=MAX_SITES,
     ks = np.ascontiguousarray(seeds["keyScores"], np.int32)
     heads = np.zeros(n, HEAD_DTYPE); sites = np.zeros((n, max_sites), SITE_DTYPE)
     _lib.check(L.bbm_set_option(index.h, b"search_shared", 1 if shared else 0), "bbm_set_option")
-    _lib.check(L.bbm_set_option(index.h, b"search_split", int(split)), "bbm_set_option")        # 0 one launch, 1 three thread-per-read phases, 2 warp-per-read prescan
+    _lib.check(L.bbm_set_option(index.h, b"search_split", int(split)), "bbm_set_option")        # 0 one launch, 1 three thread-per-read phases, 2 warp-per-read prescan, 3 (default) warp-per-read prescan and walk
     _lib.check(L.bbm_search_batch_host(index.h, _p(bases), _p(bs), _p(ro), n, _p(nk), _p(of), _p(ks), of.shape[1],
                                        1 if quit_after_two_perfects else 0, _p(heads), _p(sites), max_sites), "bbm_search_batch_host")
     return heads, sites

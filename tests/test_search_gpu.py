@@ -77,11 +77,17 @@ def test_search_parity(oracle, sizes, k, L, chrombits, maxlen, quit2):
         # 32 keys fall back to the thread-per-read prescan)
         h4, t4 = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=0)
         assert h4.tobytes() == heads.tobytes() and t4.tobytes() == sites.tobytes()
+        # ... and with the warp-per-read prescan but the thread-per-read walk (the default, split=3, walks with one warp per read as well)
+        h5, t5 = search.search_batch(idx, bases, seeds["baseScores"], off, seeds, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=2)
+        assert h5.tobytes() == heads.tobytes() and t5.tobytes() == sites.tobytes()
         # the same batch with 32 key slots per read through the shared-memory variant of the kernel
         s32 = {k: (np.ascontiguousarray(v[:, :32]) if getattr(v, "ndim", 1) == 2 else v) for k, v in seeds.items()}
         if int(seeds["nkeys"].max()) <= 32:
             h2, t2 = search.search_batch(idx, bases, seeds["baseScores"], off, s32, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, shared=True)
             assert h2.tobytes() == heads.tobytes() and t2.tobytes() == sites.tobytes()
+            # 32 key slots: no thread-per-read launch follows the warp-per-read walk at all
+            h6, t6 = search.search_batch(idx, bases, seeds["baseScores"], off, s32, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2)
+            assert h6.tobytes() == heads.tobytes() and t6.tobytes() == sites.tobytes()
     finally:
         idx.close()
     for f in ("nsites", "status", "num_hits", "max_score", "max_quick_score", "best_scores"):
