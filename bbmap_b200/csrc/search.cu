@@ -16,6 +16,7 @@
 // Unsupported corner (flagged in `status`, never silently wrong): subsumption into a previous site that carries a gap
 // array (needs GapTools.fixGaps).
 #include <cstring>
+#include <cstdio>
 #include <cuda_runtime.h>
 #include "msa_common.cuh"
 

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(WW_WARPS * 32) walk_warp_kernel(SearchParams P
                                                     if (lane < nproc && match && (old < 0 || refbase == centerLoc)) sh.loc[cloc] = refbase;
                                                     misses += __popc(mm & (nproc >= 32 ? FULL : ((1u << nproc) - 1u)));
                                                     __syncwarp();
-                                                    if (nproc < 32) break;
+                                                    if (pre | post) break;                                           // a stop anywhere in the chunk (also after its last position) ends this key's loop
                                                 }
                                             }
                                             for (int i = 0; i < numHits; i++) {                                  // rightwards from behind each key
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(WW_WARPS * 32) walk_warp_kernel(SearchParams P
                                                     if (lane < nproc && match && (old < 0 || refbase == centerLoc)) sh.loc[cloc] = refbase;
                                                     misses += __popc(mm & (nproc >= 32 ? FULL : ((1u << nproc) - 1u)));
                                                     __syncwarp();
-                                                    if (nproc < 32) break;
+                                                    if (pre | post) break;                                           // a stop anywhere in the chunk (also after its last position) ends this key's loop
                                                 }
                                             }
                                             int mn = 0x7fffffff, mx = (-0x7fffffff - 1);
@@ -401,6 +401,9 @@ __global__ void __launch_bounds__(WW_WARPS * 32) walk_warp_kernel(SearchParams P
                                         }
                                         if (score >= cutoff) { qcutoff = imax(qcutoff, (int)(qscore * DYNAMIC_QSCORE_THRESH)); bestqscore = imax(qscore, bestqscore); }
                                     }
+#ifdef WW_DEBUG_READ
+                                    if (r == WW_DEBUG_READ && lane == 0) printf("WW read %u strand %d site %d center %d approx %d cutoffHits %d qscore %d qcutoff %d score %d cutoff %d top %d\n", r, strand, site, centerIndex, approxHits, approxHitsCutoff, qscore, qcutoff, score, cutoff, currentTopScore);
+#endif
                                     if (score >= cutoff) {
                                         if (score > currentTopScore) {
                                             maxHits = imax(approxHits, maxHits);

@@ -137,3 +137,48 @@ def test_search_phix_fixture(oracle, tag):
             assert sum(top_site_correct(sites[i], heads["nsites"][i], truth[i]) for i in range(len(truth))) >= 95
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("L,seed", [(250, 14), (150, 31), (100, 32)])
+def test_search_parity_repeat_families(oracle, L, seed):
+    """Near-identical 400-bp repeat families (five copies each, 1 % apart) and reads with indels: extensions whose keys point at several copies,
+    so extendScore's per-key loops stop at every kind of cell — the case that caught a chunk-boundary slip in the warp-per-read walk (a stop
+    after the 32nd position of a chunk).  Every launch variant against the C restatement."""
+    from bbmap_b200.index import BBIndexCUDA, pack_chromosomes
+    from bbmap_b200.keyring import default_cfg
+    from bbmap_b200 import search
+    g = wl.random_genome(300_000, seed=seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 100))
+    starts = []
+    for _ in range(8):
+        unit = wl.ACGT[rng.integers(0, 4, size=400, dtype=np.uint8)]
+        for _c in range(5):
+            u = unit.copy()
+            m = rng.random(400) < 0.01
+            u[m] = wl.ACGT[rng.integers(0, 4, size=int(m.sum()), dtype=np.uint8)]
+            q = int(rng.integers(0, len(g) - 400)); g[q:q + 400] = u; starts.append(q)
+    cb, co, table = pack_chromosomes([g])
+    R = wl.make_mapping_reads(cb, co, table, 1500, L=L, seed=seed + 1, sub_rate=0.015, indel_rate=0.02 / 3)
+    bases, qual, off = R["bases"].copy(), R["qual"], R["off"]
+    for i in range(0, len(off) - 1, 2):                       # every second read from inside a repeat copy (clean), either strand
+        q = starts[int(rng.integers(0, len(starts)))] + int(rng.integers(-L // 2, 400 - L // 2))
+        q = min(max(q, 0), len(g) - L)
+        r = g[q:q + L]
+        bases[off[i]:off[i + 1]] = r if (i // 2) % 2 == 0 else wl.revcomp(r)
+    cfg = default_cfg()
+    eidx = oracle.index_build(cb, co, 13, -1)
+    es = oracle.seed_batch(bases, qual, off, cfg, 32)
+    idx = BBIndexCUDA(cb, co, keylen=13)
+    try:
+        for quit2 in (True, False):
+            exp = oracle.search_batch(eidx, cb, co, bases, es["baseScores"], off, es, quit_after_two_perfects=quit2)
+            for split in (3, 2):
+                h, t = search.search_batch(idx, bases, es["baseScores"], off, es, max_sites=search.MAX_SITES, quit_after_two_perfects=quit2, split=split)
+                for f in ("nsites", "status", "num_hits", "max_score", "max_quick_score", "best_scores"):
+                    assert np.array_equal(h[f], exp[f]), (f, split, quit2, np.nonzero((h[f] != exp[f]).reshape(len(h), -1).any(axis=1))[0][:5])
+                for i in range(len(h)):
+                    ns = exp["nsites"][i]
+                    assert t[i, :ns].tobytes() == exp["sites"][i, :ns].tobytes(), (i, split, quit2)
+            assert (exp["nsites"] > 2).sum() > 200
+    finally:
+        idx.close()
