@@ -36,8 +36,8 @@ extern "C" int bbm_init(int device, bbm_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->gev0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->gev1, cudaEventDisableTiming));
-    if (c->counters.ensure(256 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
-    CK(cudaMemset(c->counters.p, 0, 256 * 4));          // run_msa re-zeroes the first 192 words per batch; the debug counters behind them start at 0 too
+    if (c->counters.ensure(512 * 4)) return fail(BBM_E_CUDA, "cudaMalloc counters");
+    CK(cudaMemset(c->counters.p, 0, 512 * 4));          // run_msa re-zeroes the first 192 words per batch; the debug counters behind them start at 0 too
     {   // strip-kernel scratch budget: a third of what is free now, at most 32 GB (B200: 180 GB of HBM3e)
         size_t freeB = 0, totalB = 0;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && freeB / 3 < c->strip_budget) c->strip_budget = freeB / 3;
@@ -52,7 +52,7 @@ extern "C" void bbm_destroy(bbm_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->uploads) cudaFree(p);
     c->scratch.release(); c->counters.release(); c->overflow.release(); c->gscratch.release(); c->lists.release(); c->cls.release(); c->nscratch.release(); c->nlist.release();
-    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); for (auto& b : c->slowBuf) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); for (auto& b : c->d_sam) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
+    c->d_reads.release(); c->d_tasks.release(); c->d_outs.release(); c->d_match.release(); c->d_moff.release(); c->d_dump.release(); c->d_refs2.release(); c->seedScratch.release(); for (auto& b : c->d_seed) b.release(); c->stripScratch.release(); c->bandScratch.release(); for (auto& b : c->slowBuf) b.release(); c->searchCtx.release(); c->searchRev.release(); for (auto& b : c->d_ing) b.release(); for (auto& b : c->d_sam) b.release(); c->grefPool.release(); c->grefInfo.release(); c->grefTasks.release(); c->d_gtasks.release(); c->d_gaps.release(); for (auto& b : c->d_srch) b.release();
     c->h_stage.release();
     index_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -97,6 +97,7 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!strcmp(key, "narrow")) { c->use_narrow = value; return BBM_OK; }
     if (!strcmp(key, "strip_min_tasks")) { c->strip_min_tasks = value; return BBM_OK; }
     if (!strcmp(key, "slow_lookahead")) { c->slow_lookahead = value; return BBM_OK; }
+    if (!strcmp(key, "band")) { c->use_band = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "msa_count")) { c->msa_count = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }

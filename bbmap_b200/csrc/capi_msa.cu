@@ -25,7 +25,8 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
     // alignments would run as a few dozen single threads (measured: 14 alignments = 48 ms).  Small batches (scoreSlow's later rounds and
     // padding retries) go to the warp-per-alignment tiled kernel instead; results are identical by construction and by test.
     const int useStrip = (c->use_strip && d_dump == nullptr && ntasks >= c->strip_min_tasks) ? c->use_strip : 0;
-    const int CS = bbm_msa_class_strip();
+    const int CS = bbm_msa_class_strip(), CB = bbm_msa_class_band();
+    const int useBand = (c->use_band && d_dump == nullptr && (c->bandwidth > 0 || c->ratio > 0.f)) ? 1 : 0;
     if (c->scratch.ensure((size_t)c->blocks * wpb * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc traceback scratch");
     if (useNarrow && c->nscratch.ensure((size_t)narrowWarps * words * 8)) return fail(BBM_E_CUDA, "cudaMalloc narrow traceback scratch");
     if (c->overflow.ensure((size_t)ntasks * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc overflow list");
@@ -42,15 +43,16 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
     P.overflow_list = (int*)c->overflow.p;
     P.dump = d_dump;
     CK(cudaMemsetAsync(c->counters.p, 0, 192 * 4, st));
+    if (useBand) CK(cudaMemsetAsync(cb + 256, 0, 256 * 4, st));
     CK(cudaEventRecord(c->ev0, st));
-    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cb, useNarrow, useStrip, st);
+    int e = bbm_launch_msa_classify(&P, (unsigned char*)c->cls.p, cb, useNarrow, useStrip, useBand, st);
     if (e) return fail(BBM_E_CUDA, "msa_classify_kernel launch", (cudaError_t)e);
     c->launches++;
-    unsigned int h[192];
-    CK(cudaMemcpyAsync(h, cb, 192 * 4, cudaMemcpyDeviceToHost, st));
+    unsigned int h[512];
+    CK(cudaMemcpyAsync(h, cb, (useBand ? 512 : 192) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     unsigned int base[16]; unsigned int acc = 0;
-    for (int k = 0; k < 16; ++k) { base[k] = acc; if (k <= nw || k == CS) acc += h[k]; }
+    for (int k = 0; k < 16; ++k) { base[k] = acc; if (k <= nw || k == CS || k == CB) acc += h[k]; }
     unsigned int nbase[64]; unsigned int nacc = 0;
     for (int k = 0; k < 64; ++k) { nbase[k] = nacc; if (k < nb) nacc += h[64 + k]; }
     unsigned int curs[16]; memcpy(curs, base, sizeof(curs));
@@ -59,6 +61,12 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
         unsigned int cur = base[CS];
         for (int b = 15; b >= 0; --b) { sbBase[b] = cur; cur += h[104 + b]; }
         curs[CS] = cur;
+    }
+    unsigned int bdBase[120], bdClass[4] = {0, 0, 0, 0};
+    if (useBand && h[CB]) {       // band list: slot class, then read length (the 32 alignments of a warp then have the same shape)
+        unsigned int cur = base[CB];
+        for (int b = 0; b < 120; ++b) { bdBase[b] = cur; cur += h[256 + b]; bdClass[b / 40] += h[256 + b]; }
+        CK(cudaMemcpyAsync(cb + 384, bdBase, 120 * 4, cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemcpyAsync(cb + 16, curs, 16 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cb + 168, sbBase, 16 * 4, cudaMemcpyHostToDevice, st));
@@ -117,6 +125,28 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
         e = fns[k](&P, (const int*)c->lists.p + base[k], 0, cb + 16 + k, base[k], cb + 32 + k, blocks, d_dump != nullptr, st);
         if (e) return fail(BBM_E_CUDA, "msa_tiled_kernel launch", (cudaError_t)e);
         c->launches++;
+    }
+    if (useBand && h[CB]) {
+        // banded limited fills: one thread per alignment, the band by diagonal in shared memory (msa_band.cu); no right-edge assumption, no re-runs.
+        // One launch per slot class present (32 / 64 / 128 slots of shared memory per thread and state).
+        const int bRows = (int)h[53], bCols = (int)h[54];
+        const int BT = bbm_msa_band_threads();
+        unsigned int segBase = base[CB];
+        for (int cls = 0; cls < 3; ++cls) {
+            const unsigned int cnt = bdClass[cls];
+            if (!cnt) continue;
+            const int nd = 32 << cls;
+            const size_t smemPerBlock = (size_t)3 * nd * BT * 4 + 16 * 1024;
+            int perSm = (int)((220 * 1024) / smemPerBlock); if (perSm < 1) perSm = 1; if (perSm > 8) perSm = 8;
+            long long blocks = (long long)c->sms * perSm;
+            const long long needB = ((long long)cnt + BT - 1) / BT;
+            if (needB < blocks) blocks = needB;
+            if (c->bandScratch.ensure((size_t)blocks * BT * bbm_msa_band_thread_bytes(bRows, bCols, nd) + 256)) return fail(BBM_E_CUDA, "cudaMalloc band scratch");
+            e = bbm_launch_msa_band(&P, (const int*)c->lists.p + segBase, (int)cnt, nullptr, segBase, nd, bRows, bCols, c->bandScratch.p, cb + 56 + cls, (int)blocks, st);
+            if (e) return fail(BBM_E_CUDA, "msa_band_kernel launch", (cudaError_t)e);
+            c->launches++;
+            segBase += cnt;
+        }
     }
     if (useStrip && h[CS]) {
         // limited, un-banded fills (narrow-kernel hand-overs included): thread-per-alignment strip kernel.  Scratch = fixed part + one

@@ -17,8 +17,13 @@ using namespace bbm;
 
 #define DECL_W(W) extern "C" int bbm_launch_msa_tiled_w##W(const MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, unsigned int* counter, int blocks, int dump, cudaStream_t stream);
 DECL_W(4) DECL_W(5) DECL_W(6) DECL_W(8) DECL_W(9) DECL_W(12) DECL_W(16)
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, cudaStream_t stream);
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, int useBand, cudaStream_t stream);
 extern "C" int bbm_msa_class_strip();
+extern "C" int bbm_msa_class_band();
+extern "C" int bbm_msa_band_threads();
+extern "C" size_t bbm_msa_band_thread_bytes(int maxRows, int maxCols, int nd);
+extern "C" int bbm_launch_msa_band(const MsaParams* P, const int* list, int nlist, const unsigned int* endPtr, unsigned int base, int nd, int maxRows, int maxCols,
+                                   void* scratch, unsigned int* counter, int blocks, cudaStream_t st);
 extern "C" int bbm_msa_strip_blocks_per_sm();
 extern "C" int bbm_msa_strip_max_cols();
 extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols);
@@ -128,6 +133,8 @@ struct bbm_ctx {
     DevBuf scratch, nscratch, counters, overflow, gscratch, lists, nlist, cls;
     int use_narrow = 1000, use_strip = 16, strip_debug = 0, search_shared = 0, search_split = 3;
     long long strip_min_tasks = 8192;
+    int use_band = 1;                          // banded limited fills go to the thread-per-alignment band kernel (0: register-tiled kernel + row-sequential re-runs)
+    DevBuf bandScratch;
     int slow_lookahead = 16;                   // scoreSlow: sites of one read taken per round after its first (1 = one site per round, the round-1 schedule)
     DevBuf slowBuf[9];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")

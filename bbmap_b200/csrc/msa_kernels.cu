@@ -9,11 +9,13 @@
 namespace bbm {
 
 // pass 1: class of every task + per-class counts; pass 2: scatter ids into per-class lists
-__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip) {
+__global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, int useBand) {
     __shared__ unsigned int local[NUM_CLASS];
     __shared__ unsigned int localNb[NARROW_BUCKETS];
     __shared__ unsigned int localSb[STRIP_BUCKETS];
     __shared__ unsigned long long localBytes;
+    __shared__ unsigned int localBd[BAND_BUCKETS];
+    if (threadIdx.x < BAND_BUCKETS) localBd[threadIdx.x] = 0;
     if (threadIdx.x < STRIP_BUCKETS) localSb[threadIdx.x] = 0;
     if (threadIdx.x == 0) localBytes = 0;
     if (threadIdx.x < NUM_CLASS) local[threadIdx.x] = 0;
@@ -25,8 +27,9 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
         const bbm_msa_task task = P.tasks[i];
         int k = CLASS_BAD;
         if (resolve_task(task, P.bandwidth, P.ratio, T)) {
-            k = (useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T);
+            k = (useBand && band_eligible(T)) ? CLASS_BAND : ((useStrip && strip_eligible(T) && strip_bucket(T) < useStrip) ? CLASS_STRIP : classify(T));
             atomicAdd(&local[k], 1u);
+            if (k == CLASS_BAND) { atomicMax(&cb[CB_BAND_MAXROWS], (unsigned)T.rows); atomicMax(&cb[CB_BAND_MAXCOLS], (unsigned)T.cols); atomicMax(&cb[CB_BAND_MAXHB], (unsigned)T.halfband); atomicAdd(&localBd[band_bucket(T)], 1u); }
             if (k == CLASS_GENERIC) { atomicMax(&cb[CB_GENERIC_MAXCOLS], (unsigned)T.cols); atomicMax(&cb[CB_GENERIC_MAXROWS], (unsigned)T.rows); }
             if (k == CLASS_STRIP) atomicAdd(&localBytes, strip_task_bytes(T.rows, T.cols));
             if (useNarrow && narrow_eligible(T, useNarrow > 1 ? useNarrow : 0)) { atomicAdd(&localNb[narrow_bucket(T.rows)], 1u); k |= CLS_NARROW_BIT; }
@@ -39,6 +42,7 @@ __global__ void msa_classify_kernel(MsaParams P, unsigned char* cls, unsigned in
     if (threadIdx.x < NARROW_BUCKETS && localNb[threadIdx.x]) atomicAdd(&cb[CB_NB_COUNTS + threadIdx.x], localNb[threadIdx.x]);
     if (threadIdx.x < STRIP_BUCKETS && localSb[threadIdx.x]) atomicAdd(&cb[CB_SB_COUNTS + threadIdx.x], localSb[threadIdx.x]);
     if (threadIdx.x == 0 && localBytes) atomicAdd(reinterpret_cast<unsigned long long*>(cb + CB_STRIP_BYTES), localBytes);
+    if (threadIdx.x < BAND_BUCKETS && localBd[threadIdx.x]) atomicAdd(&cb[CB_BD_COUNTS + threadIdx.x], localBd[threadIdx.x]);
 }
 
 __global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist) {
@@ -55,6 +59,13 @@ __global__ void msa_scatter_kernel(MsaParams P, const unsigned char* cls, unsign
         TaskCtx T;
         resolve_task(P.tasks[i], P.bandwidth, P.ratio, T);
         const unsigned pos = atomicAdd(&cb[CB_SB_CURSORS + strip_bucket(T)], 1u);
+        lists[pos] = (int)i;
+        return;
+    }
+    if (k == CLASS_BAND) {
+        TaskCtx T;
+        resolve_task(P.tasks[i], P.bandwidth, P.ratio, T);
+        const unsigned pos = atomicAdd(&cb[CB_BD_CURSORS + band_bucket(T)], 1u);
         lists[pos] = (int)i;
         return;
     }
@@ -278,9 +289,9 @@ __global__ void __launch_bounds__(WIDE_THREADS) msa_wide_unlimited_kernel(MsaPar
 
 using namespace bbm;
 
-extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, cudaStream_t stream) {
+extern "C" int bbm_launch_msa_classify(const MsaParams* P, unsigned char* cls, unsigned int* cb, int useNarrow, int useStrip, int useBand, cudaStream_t stream) {
     const int threads = 256;
-    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, useNarrow, useStrip);
+    msa_classify_kernel<<<(unsigned)((P->ntasks + threads - 1) / threads), threads, 0, stream>>>(*P, cls, cb, useNarrow, useStrip, useBand);
     return (int)cudaGetLastError();
 }
 extern "C" int bbm_launch_msa_scatter(const MsaParams* P, const unsigned char* cls, unsigned int* cb, int* lists, int* nlist, cudaStream_t stream) {
@@ -323,6 +334,7 @@ extern "C" int bbm_launch_msa_generic(const MsaParams* P, const int* list, int n
 extern "C" int bbm_msa_warps_per_block() { return WARPS_PER_BLOCK; }
 extern "C" int bbm_msa_num_wclass() { return NUM_WCLASS; }
 extern "C" int bbm_msa_class_strip() { return CLASS_STRIP; }
+extern "C" int bbm_msa_class_band() { return CLASS_BAND; }
 extern "C" int bbm_msa_wclass_width(int k) { return wclass_width(k); }
 extern "C" long long bbm_generic_scratch_ints(int rows, int cols) { return msa_generic_scratch_ints(rows, cols); }
 

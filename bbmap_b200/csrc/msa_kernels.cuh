@@ -41,11 +41,16 @@ __host__ __device__ constexpr int wclass_width(int k) { return k == 0 ? 4 : k ==
 constexpr int CLASS_GENERIC = NUM_WCLASS;      // row-sequential kernel
 constexpr int CLASS_BAD = NUM_WCLASS + 1;      // invalid task
 constexpr int CLASS_STRIP = NUM_WCLASS + 2;    // limited, un-banded fills: thread-per-alignment strip kernel (msa_strip.cu)
-constexpr int NUM_CLASS = NUM_WCLASS + 3;
+constexpr int CLASS_BAND = NUM_WCLASS + 3;     // limited, banded fills: thread-per-alignment band kernel (msa_band.cu)
+constexpr int NUM_CLASS = NUM_WCLASS + 4;
 constexpr int STRIP_MAX_COLS = 512;            // CellTables cover DEL/INS runs up to this (msa_cell.cuh)
 constexpr int CLS_NARROW_BIT = 0x80;           // class byte flag: first try the thread-per-alignment narrow kernel
+constexpr int NARROW_BUCKETS_C = 40;
 // counter block (32-bit words)
 constexpr int CB_COUNTS = 0, CB_CURSORS = 16, CB_WORK = 32, CB_OVERFLOW = 48, CB_NARROW_WORK = 49;
+constexpr int CB_BAND_MAXROWS = 53, CB_BAND_MAXCOLS = 54, CB_BAND_MAXHB = 55, CB_BAND_WORK = 56;      // largest shape / halfband in the band class, its work counters (56, 57, 58: one per slot class)
+constexpr int BAND_ND_CLASSES = 3, BAND_BUCKETS = BAND_ND_CLASSES * NARROW_BUCKETS_C;                  // band list order: slot class (32 / 64 / 128 slots), then read length, so that the 32 alignments of a warp have the same shape
+constexpr int CB_BD_COUNTS = 256, CB_BD_CURSORS = 384, CB_WORDS_ALL = 512;
 constexpr int CB_GENERIC_MAXCOLS = 51, CB_GENERIC_MAXROWS = 52;   // largest shape in the row-sequential class: sizes its shared-memory rows
 constexpr int CB_NB_COUNTS = 64, CB_NB_CURSORS = 128, CB_WORDS = 192;
 constexpr int STRIP_BUCKETS = 16;              // strip list is ordered by estimated work, largest first (longest-processing-time-first)
@@ -61,6 +66,21 @@ __device__ __forceinline__ int classify(const TaskCtx& T) {
 
 __device__ __forceinline__ bool strip_eligible(const TaskCtx& T) {
     return T.limited && T.halfband < 1 && T.rows >= 2 && T.rows <= MAXR - 2 && T.cols <= STRIP_MAX_COLS;
+}
+
+// banded limited fills whose band (3*halfband+3 slots) fits the band kernel's shared-memory row (msa_band.cu); CellTables bound the columns as for the strips
+__device__ __forceinline__ bool band_eligible(const TaskCtx& T) {
+    return T.limited && T.halfband >= 1 && 3 * T.halfband + 3 <= 128 && T.rows >= 1 && T.rows <= MAXR - 2 && T.cols <= STRIP_MAX_COLS;
+}
+
+__device__ __forceinline__ int band_nd_class(int hb) { const int nd = 3 * hb + 3; return nd <= 32 ? 0 : (nd <= 64 ? 1 : 2); }
+// band list order within a slot class: estimated work (rows x cells a path may wander over given the slack between the best possible score and
+// minScore, at most the band), largest first — the 32 alignments a warp starts together should take about equally long
+__device__ __forceinline__ int band_bucket(const TaskCtx& T) {
+    const int maxQ = (T.rows - 1) * 100 + 70;
+    const int slack = imax(0, maxQ - T.minScore);
+    const int w = (T.rows * imin(3 * T.halfband + 2, slack / 64 + 5)) >> 8;         // buckets of 256 cells
+    return band_nd_class(T.halfband) * NARROW_BUCKETS_C + (NARROW_BUCKETS_C - 1 - imin(w, NARROW_BUCKETS_C - 1));
 }
 
 constexpr int SW = 8;                           // columns per strip (msa_strip.cu)

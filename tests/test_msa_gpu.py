@@ -18,6 +18,8 @@ def msa(request):
     m.set_option("strip_min_tasks", 0)     # the library keeps small batches away from the thread-per-alignment kernel; the tests want it exercised
     if request.param != "strip":
         m.set_option("narrow", 1)          # every shape-eligible alignment tries the narrow kernel first: exercises the hand-over path
+    if request.param == "tiled":
+        m.set_option("band", 0)            # banded fills through the register-tiled kernel + row-sequential re-runs (the other two routings use msa_band.cu)
     yield m
     m.close()
 
