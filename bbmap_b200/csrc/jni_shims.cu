@@ -6,25 +6,27 @@
 // current/align2/MultiStateAligner11tsJNI.java:11-14) — see INTEGRATION.md.  Built against include/bbm_jni_min.h (the three
 // JNIEnv slots the reference uses, at their specified indices); unverified against a live JVM (none in this image).
 //
-// One process-wide context on device $BBM_DEVICE (default 0); calls from concurrent Java threads serialise on it — this is
-// the compatibility path (one alignment per call); throughput callers use bbm_msa_batch_*.
+// One context PER CALLING THREAD on device $BBM_DEVICE (default 0), created at the thread's first call: the reference's entry points are re-entrant
+// and BBMap keeps one MSA per mapping thread (AbstractMapThread.java:133-136), so concurrent Java threads must not serialise on a shared context.
+// This is still the compatibility path (one alignment per call, ~150 us each); throughput callers use bbm_map_batch_* / bbm_msa_batch_*.
+// Contexts are not destroyed at thread exit (mapping threads live as long as the run; tearing CUDA objects down from a dying thread's TLS destructor
+// after the runtime has begun to unload is not safe).
 #include <cstdlib>
 #include <cstdio>
-#include <mutex>
 #include "../../include/bbm_jni_min.h"
 #include "../../include/bbmap_cuda.h"
 
-static bbm_ctx* g_ctx = nullptr;
-static std::once_flag g_once;
-static int g_init_rc = 0;
+static thread_local bbm_ctx* t_ctx = nullptr;
+static thread_local bool t_tried = false;
 
 static bbm_ctx* default_ctx() {
-    std::call_once(g_once, [] {
+    if (!t_tried) {
+        t_tried = true;
         const char* d = getenv("BBM_DEVICE");
-        g_init_rc = bbm_init(d ? atoi(d) : 0, &g_ctx);
-        if (g_init_rc) { fprintf(stderr, "libbbmapcuda: %s\n", bbm_last_error()); g_ctx = nullptr; }
-    });
-    return g_ctx;
+        const int rc = bbm_init(d ? atoi(d) : 0, &t_ctx);
+        if (rc) { fprintf(stderr, "libbbmapcuda: %s\n", bbm_last_error()); t_ctx = nullptr; }
+    }
+    return t_ctx;
 }
 
 extern "C" bbm_ctx* bbm_default_ctx(void) { return default_ctx(); }

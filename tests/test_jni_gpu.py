@@ -82,3 +82,51 @@ def test_banded_jni_symbols(oracle):
                                           C.c_ubyte(int(t["exact"])), int(t["max_width"]), _p(b2n), _p(comp), _p(rv))
         exp = oracle.banded(d, qq, rr, int(t["qstart"]), int(t["rstart"]), int(t["max_edits"]), bool(t["exact"]), int(t["max_width"]))
         assert (int(e), rv.tolist()) == exp
+
+
+def test_jni_concurrent_threads(oracle):
+    """Four host threads call Java_align2_MultiStateAligner11tsJNI_fillLimitedXJNI at the same time, each with its own arrays, the way BBMap's mapping
+    threads do (one MSA per thread): every thread's sequence of calls must leave its `packed`, result and counters as the reference's C does."""
+    import threading
+    from bbmap_b200 import lib as L
+    lib = L.load()
+    kind = "reference" if oracle.has_reference else "port"
+    orc = oracle.lib
+    fnL = C.cast(lib.Java_align2_MultiStateAligner11tsJNI_fillLimitedXJNI, C.c_void_p)
+    genome = wl.random_genome(30000, seed=71)
+    g8 = genome.view(np.int8)
+    reads, tasks = wl.make_msa_tasks(genome, 64, seed=72, flags=0)
+    errors = []
+
+    def worker(tid):
+        try:
+            pa = oracle.new_packed(MAXR, MAXC)
+            vla = np.zeros(MAXR + 1, np.int32); hla = np.zeros(MAXC + 1, np.int32); ita = np.zeros(1, np.int64)
+            out = []
+            for t in tasks[tid::4]:
+                r = np.ascontiguousarray(reads[t["read_off"]: t["read_off"] + t["read_len"]].view(np.int8))
+                res = np.zeros(5, np.int32)
+                orc.fake_call_fillLimitedXJNI(fnL, _p(r), len(r), _p(g8), len(g8), int(t["ref_start"]), int(t["ref_end"]), int(t["min_score"]) - 120, _p(res), _p(ita),
+                                              _p(pa), len(pa), _p(oracle.sub), _p(oracle.ins), 604, MAXR, MAXC, 0, C.c_float(0.0),
+                                              _p(vla), _p(hla), _p(oracle.b2n), _p(oracle.insC))
+                out.append(res.copy())
+            results[tid] = (out, pa, int(ita[0]))
+        except Exception as e:          # noqa: BLE001
+            errors.append(e)
+
+    results = {}
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t_ in ths:
+        t_.start()
+    for t_ in ths:
+        t_.join()
+    assert not errors, errors
+    for tid in range(4):
+        pb = oracle.new_packed(MAXR, MAXC); itb = 0
+        out, pa, ita = results[tid]
+        for j, t in enumerate(tasks[tid::4]):
+            r = np.ascontiguousarray(reads[t["read_off"]: t["read_off"] + t["read_len"]].view(np.int8))
+            exp, it = oracle.fill_limited(r, g8, int(t["ref_start"]), int(t["ref_end"]), int(t["min_score"]) - 120, pb, MAXR, MAXC, kind=kind)
+            assert out[j].tolist() == exp.tolist(), (tid, j)
+            itb += it
+        assert ita == itb and np.array_equal(pa, pb), tid
