@@ -76,7 +76,9 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     bbm_map_stats S; memset(&S, 0, sizeof S); S.reads = n;
     if (n <= 0) { if (stats) *stats = S; return BBM_OK; }
     StageTimer T; StageTimer Tall;
-    const int maxK = cfg->max_keys, paired = cfg->map.paired;
+    // key slots per read: the caller's figure (32 covers reads up to ~200 bp), raised for longer reads to 2 keys per k bases + 3 (the key density never
+    // exceeds 1.9, AbstractMapThread.java:663-676), at most 96 — a read must never lose its seeds to the size of a scratch array
+    const int maxK = std::max(cfg->max_keys, std::min(96, 2 * maxLen / std::max(1, (int)cfg->seed.keylen) + 3)), paired = cfg->map.paired;
     const long long* off = (const long long*)d_off;
     const int8_t* refs = c->d_chroms; const long long* chrom_off = c->d_chrom_off;
     const int nchroms = c->map_nchroms;
@@ -183,7 +185,7 @@ static int map_locked(bbm_ctx* c, int8_t* d_bases, int8_t* d_quality, const int6
     }
 
     // ---- genMatchString in rounds ----
-    long long ms = ((2ll * maxLen + 128 + 15) / 16) * 16;
+    long long ms = ((std::max<long long>(2ll * maxLen + 128, cfg->map.match_slot) + 15) / 16) * 16;
     if (B[MB_GMSTATE].ensure((size_t)n * GM_STATE * 4) || B[MB_MLEN].ensure((size_t)n * GM_SLOTS * 4) || B[MB_MSLOTS].ensure((size_t)n * GM_SLOTS * ms + 64) ||
         B[MB_TASKS].ensure((size_t)n * sizeof(bbm_msa_task)) || B[MB_OUTS].ensure((size_t)n * sizeof(bbm_msa_out)) || B[MB_GTASKS].ensure((size_t)n * sizeof(bbm_gapped_task)) ||
         B[MB_GAPS].ensure((size_t)n * BBM_MAX_GAPS * 4) || B[MB_GOUTS].ensure((size_t)n * sizeof(bbm_msa_out)) || B[MB_RECS].ensure((size_t)n * sizeof(bbm_map_rec)))

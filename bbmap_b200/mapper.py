@@ -7,7 +7,7 @@ MAP_CFG_DTYPE = np.dtype([("paired", "<i4"), ("min_ratio", "<f4"), ("min_ratio_p
                           ("secondary_site_score_ratio", "<f4"), ("slow_align_padding", "<i4"), ("max_indel", "<i4"), ("ambiguous_toss", "<i4"),
                           ("penalize_ambig", "<i4"), ("average_pair_dist", "<i4"), ("max_pair_dist", "<i4"), ("max_rescue_dist", "<i4"),
                           ("max_rescue_mismatches", "<i4"), ("do_rescue", "<i4"), ("kill_bad_pairs", "<i4"), ("require_correct_strands", "<i4"),
-                          ("same_strand_pairs", "<i4"), ("pad_", "<i4", (3,))], align=True)
+                          ("same_strand_pairs", "<i4"), ("match_slot", "<i4"), ("pad_", "<i4", (2,))], align=True)
 MAP_REC_DTYPE = np.dtype([("chrom", "<i4"), ("start", "<i4"), ("stop", "<i4"), ("strand", "<i4"), ("map_score", "<i4"), ("flags", "<i4"),
                           ("match_len", "<i4"), ("cz3_sub", "<i4"), ("tip_penalty", "<i4"), ("status", "<i4"), ("pad_", "<i4", (2,))], align=True)
 assert MAP_CFG_DTYPE.itemsize == 80 and MAP_REC_DTYPE.itemsize == 48
@@ -28,7 +28,7 @@ def map_cfg(**kw):
              min_ratio_pre_rescue=max(np.float32(r * np.float32(.60)), np.float32(one - np.float32(np.float32(one - r) * np.float32(1.8)))),
              secondary_site_score_ratio=.95, slow_align_padding=4, max_indel=16000, ambiguous_toss=0, penalize_ambig=1, average_pair_dist=100,
              max_pair_dist=32000, max_rescue_dist=1200, max_rescue_mismatches=32, do_rescue=1, kill_bad_pairs=0, require_correct_strands=1,
-             same_strand_pairs=0)
+             same_strand_pairs=0, match_slot=0)
     d.update(kw)
     for k, v in d.items():
         c[k] = v

@@ -479,7 +479,9 @@ typedef struct {                /* 80 bytes; defaults in bbmap_b200/mapper.py */
     int32_t slow_align_padding, max_indel, ambiguous_toss, penalize_ambig;
     int32_t average_pair_dist, max_pair_dist, max_rescue_dist, max_rescue_mismatches;
     int32_t do_rescue, kill_bad_pairs, require_correct_strands, same_strand_pairs;
-    int32_t pad_[3];
+    int32_t match_slot;         /* bytes a site's match string may take inside the mapper; 0 = 2 * longest read + 128 (enough for indels up to ~1 kbp).  Spliced
+                                   reads need read length + intron length: a longer string sets BBM_MAP_ST_MATCH_OVERFLOW and leaves the read without CIGAR */
+    int32_t pad_[2];
 } bbm_map_cfg;
 typedef struct {                /* 48 bytes: the Read fields SamLine(Read,int) reads, as the mapper leaves them */
     int32_t chrom, start, stop, strand, map_score;

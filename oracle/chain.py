@@ -15,8 +15,15 @@ from bbmap_b200.sam import scaffold_table, default_cfg as sam_default_cfg, SAM_T
 MAXK = 32
 
 
-def match_stride(max_len):
-    return 2 * int(max_len) + 128
+def max_keys_for(off):
+    """key slots per read: 32 covers reads up to ~200 bp; longer reads get 2 keys per k bases + 3 (the key density never exceeds 1.9, AbstractMapThread.java:663-676), at most 96"""
+    longest = int(np.diff(off).max()) if len(off) > 1 else 0
+    return max(MAXK, min(96, 2 * longest // 13 + 3))
+
+
+def match_stride(max_len, mcfg=None):
+    slot = int(mcfg["match_slot"][0]) if mcfg is not None and "match_slot" in mcfg.dtype.names else 0
+    return max(2 * int(max_len) + 128, slot)
 
 
 def search_to_lists(res, cap):
@@ -38,7 +45,7 @@ def map_single(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=
     off = np.ascontiguousarray(off, np.int64); n = len(off) - 1
     nb = int(off[-1])
     bases, qual, basesM, rflags = o.ingest_batch(bases[:nb], None if qual is None else qual[:nb], off, ingest_flags)
-    seeds = o.seed_batch(bases, qual, off, default_cfg(), MAXK)
+    seeds = o.seed_batch(bases, qual, off, default_cfg(), max_keys_for(off))
     res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=True)     # AbstractIndex.QUIT_AFTER_TWO_PERFECTS, single-ended
     overflow = int(((res["status"] & 2) != 0).sum() + (res["nsites"] > cap).sum())
     lists, ns = search_to_lists(res, cap)
@@ -51,7 +58,7 @@ def map_single(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=
     lists, _ = o.sitelist_tipdel(lists, ns * runm, off, bases, basesM, qual, cb, co, tipdel_cfg())
     lists, slow_status, na = o.score_slow(lists, ns, off, bases, basesM, cb, co, runm, sl.slow_cfg())
     lists, ns, out = o.sitelist(sl.SL_FINAL, lists, ns, off, pcfg)
-    ms = match_stride(int(np.diff(off).max()) if n else 1)
+    ms = match_stride(int(np.diff(off).max()) if n else 1, mcfg)
     lists, ns, recs, match, fills = o.map_finish_single(lists, ns, off, bases, basesM, cb, co, out, pcfg, mcfg, ms)
     recs["flags"] |= np.where(seeds["nkeys"] < 0, 32, 0).astype(np.int32)          # quickMap < 0: r.setDiscarded(true)
     tasks = sam_tasks(recs, off, ms)
@@ -69,14 +76,14 @@ def map_pairs(o, idx, cb, co, table, bases, qual, off, cap=16, pcfg=None, mcfg=N
     off = np.ascontiguousarray(off, np.int64); n = len(off) - 1
     nb = int(off[-1])
     bases, qual, basesM, rflags = o.ingest_batch(bases[:nb], None if qual is None else qual[:nb], off, ingest_flags)
-    seeds = o.seed_batch(bases, qual, off, default_cfg(), MAXK)
+    seeds = o.seed_batch(bases, qual, off, default_cfg(), max_keys_for(off))
     res = o.search_batch(idx, cb, co, bases, seeds["baseScores"], off, seeds, quit_after_two_perfects=False)    # forced false in paired mode (BBMap.java:434)
     overflow = int(((res["status"] & 2) != 0).sum() + (res["nsites"] > cap).sum())
     lists, ns = search_to_lists(res, cap)
     scaf = scaffold_table(table, len(co) - 1)
     maxidx = (np.diff(np.asarray(co, np.int64)) - 1).astype(np.int32)
     lists, ns, _ = o.sitelist_bounds(lists, ns, off, maxidx, scaf)
-    ms = match_stride(int(np.diff(off).max()) if n else 1)
+    ms = match_stride(int(np.diff(off).max()) if n else 1, mcfg)
     wcfg = sl.slow_cfg(paired=1, min_ratio=mcfg["min_ratio"][0], min_ratio_pre_rescue=mcfg["min_ratio_pre_rescue"][0])
     lists, ns, recs, match, stats = o.map_pairs(lists, ns, off, bases, basesM, qual, cb, co, seeds["nkeys"], pcfg, mcfg, wcfg, tipdel_cfg(), ms)
     tasks = sam_tasks(recs, off, ms, mate=np.arange(n, dtype=np.int32) ^ 1)
