@@ -310,3 +310,42 @@ def _reads_from_footprints(chrom_bytes, chrom, start, strand, L, rng, sub_rate, 
     truth = np.stack([chrom, strand, start, start + span - 1], axis=1).astype(np.int32)
     off = np.arange(n + 1, dtype=np.int64) * L
     return {"bases": reads.reshape(-1), "qual": np.full(n * L, qual, np.uint8), "off": off, "truth": truth}
+
+
+def make_spliced_reads(chrom_bytes, chrom_off, table, npairs, L=150, seed=7, intron=(300, 12000), frac=0.5, sub_rate=0.005, insert=(200, 500), qual=30):
+    """RNA-seq-style pairs (BASELINE configs[4] shape within the default maxindel of 16000): in a fraction `frac` of the pairs the left read of the
+    fragment is spliced over one intron of `intron` bp (its footprint on the reference is L + intron bases, the mate lies behind it).  Returns
+    dict(bases, qual, off, truth, spliced): reads 2i / 2i+1 are mates; truth[r] = (chrom, strand, start, stop) in chromosome coordinates."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tab = np.asarray(table, np.int64)
+    w = tab[:, 2].astype(np.float64); w /= w.sum()
+    sc = rng.choice(len(tab), size=npairs, p=w)
+    ins = rng.integers(insert[0], insert[1] + 1, size=npairs)
+    gap = np.where(rng.random(npairs) < frac, rng.integers(intron[0], intron[1] + 1, size=npairs), 0)
+    span = np.minimum(ins + gap, tab[sc, 2] - 8)
+    gap = np.where(span < ins + gap, 0, gap); span = ins + gap
+    fstart = tab[sc, 1] + (rng.random(npairs) * (tab[sc, 2] - span - 4)).astype(np.int64)
+    fstrand = rng.integers(0, 2, size=npairs)
+    q = rng.integers(40, L - 40, size=npairs)
+    j = np.arange(L, dtype=np.int64)[None, :]
+    base0 = np.asarray(chrom_off, np.int64)[tab[sc, 0] - 1]
+    left_idx = fstart[:, None] + j + np.where(j >= q[:, None], gap[:, None], 0)
+    right_start = fstart + span - L
+    right_idx = right_start[:, None] + j
+    left = chrom_bytes[np.minimum(left_idx + base0[:, None], len(chrom_bytes) - 1)]
+    right = chrom_bytes[np.minimum(right_idx + base0[:, None], len(chrom_bytes) - 1)]
+    for arr in (left, right):
+        sub = rng.random(arr.shape) < sub_rate
+        arr[sub] = ACGT[(np.searchsorted(ACGT, np.minimum(arr[sub], ord("T"))) + rng.integers(1, 4, size=int(sub.sum()))) % 4]
+    right = revcomp(right.reshape(-1)).reshape(-1, L)[::-1]            # the right read of a fragment is its minus-strand end
+    n = 2 * npairs
+    reads = np.empty((n, L), np.uint8); truth = np.empty((n, 4), np.int32)
+    plus = fstrand == 0
+    # fragment on the plus strand: read 1 = left (+), read 2 = right (-); on the minus strand the roles swap
+    reads[0::2] = np.where(plus[:, None], left, right); reads[1::2] = np.where(plus[:, None], right, left)
+    lt = np.stack([tab[sc, 0], np.zeros(npairs, np.int64), fstart, fstart + L + gap - 1], axis=1)
+    rt = np.stack([tab[sc, 0], np.ones(npairs, np.int64), right_start, right_start + L - 1], axis=1)
+    truth[0::2] = np.where(plus[:, None], lt, rt); truth[1::2] = np.where(plus[:, None], rt, lt)
+    spl = np.zeros(n, bool); spl[0::2] = plus & (gap > 0); spl[1::2] = ~plus & (gap > 0)
+    off = np.arange(n + 1, dtype=np.int64) * L
+    return {"bases": reads.reshape(-1), "qual": np.full(n * L, qual, np.uint8), "off": off, "truth": truth, "spliced": spl}

@@ -11,7 +11,9 @@ One "step" = one call of the batched mapper over one batch of synthetic 2x150 bp
 `e2e`     reads/s through the reference-facing call bbm_map_batch_host: FASTQ-shaped pinned host buffers in, SAM text + records out, every
           copy inside the timed region;
 `roofline` the dominant kernels of the step — the MultiStateAligner11ts fills — against the integer-issue roof measured in the same run;
-`msa`     the MultiStateAligner11ts microbenchmark (configs[2], GCUPS; bench/msa_bench.py), `banded` BandedAligner at G6 scale;
+`msa`     the MultiStateAligner11ts microbenchmark (configs[2], GCUPS; bench/msa_bench.py), `msa_band_sweep` its band sweep (bw 12 / 40, ratio 0.18),
+          `banded` BandedAligner at G6 scale, `spliced` RNA-seq-style pairs with 0.3-12 kbp introns through the same mapper call (configs[4] shape within the
+          default maxindel);
 `cpu_baseline` / `--impl reference`: the same chain through the sequential CPU restatement (oracle/), one process per host core.
 Prints ONE JSON line (rank 0)."""
 import argparse
@@ -317,8 +319,30 @@ def main():
                         "realign_fills": int(st0["realign_fills"]), "genmatch_rounds": int(st0["genmatch_rounds"]), "mated_pairs": int(st0["mated_pairs"]),
                         "mean_inner_length": float(st0["inner_length_sum"]) / max(1, int(st0["mated_pairs"])), "first_sam_lines": first_lines},
             "index_build_s": t_build}
+    if not args.no_extras and world == 1:
+        # configs[4] shape within the default maxindel (16000): RNA-seq-style pairs, half of them with one read spliced over a 0.3-12 kbp intron
+        # (gapped candidate sites from BBIndex, makeGref fills, match strings with the intron as a D run); through the host-buffer call
+        sp_pairs = min(args.pairs, 50_000)
+        RS = wl.make_spliced_reads(cb, co, table, sp_pairs, seed=7)
+        ns_ = 2 * sp_pairs
+        cfg_s = mapper_cfg(paired=True, sam_text=False, match_slot=12288 + 384)
+        ms_s = 12288 + 384
+        for _ in range(2):
+            dev_s = m.map_batch(RS["bases"], RS["qual"], RS["off"], cfg=cfg_s, match_stride=ms_s)
+        t0 = time.perf_counter(); reps_s = 3
+        for _ in range(reps_s):
+            dev_s = m.map_batch(RS["bases"], RS["qual"], RS["off"], cfg=cfg_s, match_stride=ms_s)
+        dt_s = (time.perf_counter() - t0) / reps_s
+        rs_, ts_ = dev_s["recs"], RS["truth"]
+        mp_ = (rs_["flags"] & 1) != 0
+        ok_ = mp_ & (rs_["chrom"] == ts_[:, 0]) & (rs_["strand"] == ts_[:, 1]) & (np.abs(rs_["start"] - ts_[:, 2]) <= 8) & (np.abs(rs_["stop"] - ts_[:, 3]) <= 8)
+        line["spliced"] = {"workload": "%d pairs of 2x150 bp on the same reference, one read of every second pair spliced over an intron of 300-12000 bp; default flags (maxindel 16000), "
+                                       "bbm_map_cfg.match_slot %d" % (sp_pairs, ms_s),
+                           "e2e_reads_per_s": ns_ / dt_s, "ms_per_batch": dt_s * 1e3, "mapped": float(mp_.mean()), "start_and_stop_within_8": float(ok_.mean()),
+                           "spliced_reads": int(RS["spliced"].sum()), "spliced_start_and_stop_within_8": float(ok_[RS["spliced"]].mean()),
+                           "status_reads": int((rs_["status"] != 0).sum()), "realign_fills": int(dev_s["stats"]["realign_fills"]), "slow_alignments": int(dev_s["stats"]["slow_alignments"])}
     m.close()
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU figure is reported at N=1 only
         threads = os.cpu_count() or 1
         npairs = args.cpu_pairs or min(args.pairs, threads * 6000)
         order = sorted(range(len(table)), key=lambda i: table[i])
