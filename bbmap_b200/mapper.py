@@ -123,7 +123,8 @@ class BBMapCUDA:
         b = np.ascontiguousarray(bases).view(np.int8); q = None if quality is None else np.ascontiguousarray(quality).view(np.int8)
         if match_stride is None:
             match_stride = 2 * int(np.diff(ro).max() if n else 1) + 128
-        recs = np.zeros(n, MAP_REC_DTYPE); sam = np.zeros(n, SAM_OUT_DTYPE); match = np.zeros(n * match_stride + 16, np.int8)
+        recs = np.zeros(n, MAP_REC_DTYPE); sam = np.zeros(n, SAM_OUT_DTYPE)
+        match = np.zeros(n * match_stride + 16, np.int8) if match_stride > 0 else None          # match_stride=0: records and SAM fields only
         stats = np.zeros(1, MAP_STATS_DTYPE)
         text = np.zeros(max(sam_cap, 1), np.int8) if cfg["sam_text"][0] else None
         toff = np.zeros(n + 1, np.int64) if cfg["sam_text"][0] else None
