@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — mapped reads/s of the whole seed-and-extend chain on BASELINE.json configs[1]-shaped input, one B200 per rank.
 
-One "step" = one call of the batched mapper over one batch of synthetic 2x150 bp pairs (E. coli-sized random reference, ~1 % substitutions,
+One "step" = one call of the batched mapper over one batch of synthetic 2x150 bp pairs — by default the 1 M pairs BASELINE configs[1] names, as ONE batch (E. coli-sized random reference, ~1 % substitutions,
 1-3 bp indels, Q30): Read.validate -> KeyRing -> BBIndex.find -> pairSiteScoresInitial -> scoreNoIndels -> findTipDeletions -> scoreSlow -> rescue
 -> pairSiteScoresFinal -> genMatchString / realign_new -> SamLine fields -> SAM text, i.e. BBMapThread.processReadPair for every pair.
 
@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=200_000, help="pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per step per GPU (configs[1] names 1 M pairs: one step maps all of them as one batch)")
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--scaffolds", type=int, default=1)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
