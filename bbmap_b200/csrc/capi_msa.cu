@@ -163,7 +163,19 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
         if (totalBytes > (unsigned long long)nstrip * perMax) totalBytes = (unsigned long long)nstrip * perMax;
         const int blocksMax = c->sms * bbm_msa_strip_blocks_per_sm();
         long long chunk = nstrip;
-        if (totalBytes > c->strip_budget) { chunk = (long long)(c->strip_budget / perMax); if (chunk < 1024) chunk = 1024; if (chunk > nstrip) chunk = nstrip; }
+        // the budget also follows what the device has left NOW (other contexts of the process hold their own scratch): what this context already owns
+        // plus 70 % of the free memory, so that a later context works in more, smaller chunks instead of failing its allocation
+        unsigned long long budget = c->strip_budget;
+        {
+            size_t freeB = 0, totalB = 0;
+            if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+                const unsigned long long avail = (unsigned long long)c->stripScratch.cap + (unsigned long long)(freeB * 0.7);
+                if (avail < budget) budget = avail;
+            }
+            const unsigned long long fixedMax = bbm_msa_strip_fixed_bytes((int)std::min<long long>(nstrip, 0x7fffffff), sRows, blocksMax) + 4096;
+            budget = budget > 2 * fixedMax ? budget - fixedMax : fixedMax;
+        }
+        if (totalBytes > budget) { chunk = (long long)(budget / perMax); if (chunk < 1024) chunk = 1024; if (chunk > nstrip) chunk = nstrip; }
         const unsigned long long poolBytes = (chunk == nstrip) ? totalBytes : (unsigned long long)chunk * perMax;
         for (long long start = 0; start < nstrip; start += chunk) {
             const int cnt = (int)((nstrip - start) < chunk ? (nstrip - start) : chunk);
