@@ -168,7 +168,10 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
         unsigned long long budget = c->strip_budget;
         {
             size_t freeB = 0, totalB = 0;
-            if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            static const bool noFollow = getenv("BBM_NO_ADAPTIVE_BUDGET") != nullptr;
+            // only when the scratch would have to grow: cudaMemGetInfo is a synchronous driver query, not something for every launch of a steady-state step
+            const bool wouldGrow = totalBytes + bbm_msa_strip_fixed_bytes((int)std::min<long long>(nstrip, 0x7fffffff), sRows, blocksMax) + 4096 > (unsigned long long)c->stripScratch.cap;
+            if (!noFollow && wouldGrow && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
                 const unsigned long long avail = (unsigned long long)c->stripScratch.cap + (unsigned long long)(freeB * 0.7);
                 if (avail < budget) budget = avail;
             }
