@@ -145,3 +145,62 @@ def test_rescue_restatement_properties(oracle):
         assert o["score"][i] == 70 + 100 * (L - 1 - mism)
         assert bool(o["perfect"][i] & 1) == (mism == 0)
     assert (tasks["read_len"][~found] < 10).any()
+
+
+def _rescue_all_starts(b, g, T):
+    """quickRescue stated over ALL candidate starts at once (numpy: full mismatch counts and the longest match run that a mismatch ends, for every
+    start), followed by the reference's selection rule; the early exits of the reference's loops only skip candidates this rule rejects anyway."""
+    L = len(b)
+    if L < 10:
+        return None
+    right = bool(T["flags"] & 1)
+    loc, dist, ideal = int(T["loc"]), int(T["search_dist"]), int(T["ideal_start"])
+    lo, hi = (max(int(T["min_index"]), loc), min(len(g) - L, loc + dist)) if right else (max(int(T["min_index"]), loc - dist), min(len(g) - L, loc))
+    if hi < lo:
+        return None
+    win = np.lib.stride_tricks.sliding_window_view(g[lo: hi + L], L)
+    eq = (win == b[None, :]) & (b != ord("N"))[None, :]
+    mism = L - eq.sum(axis=1)
+    cur = np.zeros(len(win), np.int64); contig = np.zeros(len(win), np.int64)
+    for j in range(L):
+        contig = np.where(eq[:, j], contig, np.maximum(contig, cur))
+        cur = np.where(eq[:, j], cur + 1, 0)
+    score = (L - mism) + contig
+    limit = int(T["max_mismatches"]) + 1
+    first = lo
+    best_start, best_m, best_c, best_score, best_ad = -1, 0, 0, 0, 1 << 40
+    s = lo if right else hi
+    while lo <= s <= hi:
+        k = s - first
+        m, sc, ad = int(mism[k]), int(score[k]), abs(s - ideal)
+        if m <= limit and (sc > best_score or (sc == best_score and ad < best_ad)):
+            best_start, best_m, best_c, best_score, best_ad = s, m, int(contig[k]), sc, ad
+            limit = m
+            if m == 0:
+                if right:
+                    hi = min(hi, ideal + ad)
+                else:
+                    lo = max(lo, ideal - ad)
+        s += 1 if right else -1
+    best = None if best_start < 0 else (best_start, best_m, best_c, best_score, best_ad)
+    return best
+
+
+def test_rescue_restatement_vs_all_starts_formulation(oracle):
+    g, reads, tasks = rescue_cases(n=1500, seed=44)
+    o = oracle.rescue_batch(reads, g, tasks, rs.rescue_cfg())
+    found = shrunk = 0
+    for i in range(len(tasks)):
+        T = tasks[i]; L = int(T["read_len"]); b = reads[T["read_off"]:T["read_off"] + L]
+        best = _rescue_all_starts(b, g, T)
+        if best is None:
+            assert o["start"][i] == -1, i
+            continue
+        found += 1
+        s, m, c, sc, ad = best
+        assert (o["start"][i], o["stop"][i], o["mismatches"][i], o["max_contig"][i]) == (s, s + L - 1, m, c), (i, best, o[i])
+        assert o["score"][i] == 70 + 100 * (L - 1 - m)
+        w = g[s:s + L]
+        perfect = bool((b == w).all() and not (b == ord("N")).any())
+        assert bool(o["perfect"][i] & 1) == perfect
+    assert found > 500
