@@ -151,89 +151,4 @@ __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R
     return o;
 }
 
-
-// ---- the same cell on UNPACKED values (msa_strip.cu, STRIP_SPLIT): scores carry no time bits and times are separate registers, so the ten
-// `& SCOREMASK` / `& TIMEMASK` of the inputs and the three `score | time` of the outputs disappear from the ALU pipe.  Only the streaks the
-// recurrence reads are passed: MS from the diagonal, DEL from the left, INS from above.  A skipped state is (subfloor, 0); a state that was
-// evaluated but failed its limit is (subfloor, time) — "score -> subfloor but time kept" — exactly as in the packed form.
-struct CellOutS {
-    int msS, msT, delS, delT, insS, insT;
-    unsigned code;
-    bool good;
-};
-__device__ __forceinline__ CellOutS msa_cell_split(const CellConst& K, const CellRow& R,
-                                                   int sMd, int streakM, int sDd, int sId,       // (row-1,col-1)
-                                                   int sMl, int sDl, int streakD,                // (row,  col-1)
-                                                   int sMu, int sIu, int streakI,                // (row-1,col)
-                                                   int ref1, int ref0, bool insBar, int hlimit, int delNeeded, int insNeeded, const CellTables& T) {
-    CellOutS o;
-    const bool match = (R.call1 == ref1);
-    const bool prevMatch = (R.call0 == ref0);
-    const bool refN = (ref1 == 0x100);
-    const bool gap = (ref1 == '-');
-    const int mxDI = imax(sDd, sId);
-    const int limit = imax(R.vlimit, hlimit);
-    const int limit3 = __viaddmax_s32(limit, match ? -P_MATCH2 : -P_SUB3, K.floor_);
-    const int delPen = T.delc[delNeeded];
-    const int insPen = T.insc[insNeeded];
-    const int lim2MS = limit - (delNeeded > 0 ? delPen : insPen);
-    const int lim2DEL = limit - insPen;
-    const int lim2INS = limit - delPen;
-    const bool skipMS = gap || (imax(sMd, mxDI) <= limit3);
-    const bool skipDEL = R.delBar || (imax(sMl, sDl) <= limit);
-    const bool skipINS = gap || insBar || (imax(sMu, sIu) <= limit);
-    bool good;
-    unsigned code;
-    {   // MS
-        const int addMatch = prevMatch ? P_MATCH2 : P_MATCH;
-        const int subPrev = streakM <= 1 ? P_SUBR : P_SUB;
-        int addSub = prevMatch ? subPrev : T.subExt[streakM];
-        addSub = (refN || R.callN) ? 0 : addSub;
-        const int a_ = sMd + (match ? addMatch : addSub);
-        const int mx = mxDI + (match ? P_MATCH : P_SUB);
-        const bool msWins = a_ >= mx;
-        const int score = imax(a_, mx);
-        const bool keep = msWins && (match == prevMatch);
-        const int time = keep ? streakM + 1 : 1;
-        const bool preMS = (keep && streakM >= 1) || (sMd >= mxDI);
-        code = preMS ? 0u : (sDd >= sId ? 1u : 2u);
-        const bool ok = score >= lim2MS;
-        good = ok && !skipMS;
-        o.msS = good ? score : K.subfloor;
-        o.msT = skipMS ? 0 : time;
-    }
-    {   // DEL
-        const int adj = refN ? P_DEL_REF_N : (gap ? P_GAP : 0);
-        const int a_ = sMl + P_DEL, b_ = sDl + T.delExt[streakD];
-        const bool msWins = a_ >= b_;
-        const int score = imax(a_, b_) + adj;
-        const int time = msWins ? 1 : streakD + 1;
-        int lim2 = lim2DEL;
-        if (delNeeded > 0 && insNeeded == 0 && !skipDEL) lim2 = limit - (T.delc[time + delNeeded] - T.delc[time]);
-        const bool ok = (score >= lim2) && !skipDEL;
-        good = good || ok;
-        const bool preDEL = (!msWins && streakD >= 1) || (sMl < sDl);
-        code |= preDEL ? 4u : 0u;
-        o.delS = ok ? score : K.subfloor;
-        o.delT = skipDEL ? 0 : time;
-    }
-    {   // INS
-        const int a_ = sMu + P_INS, b_ = sIu + T.insExt[streakI];
-        const bool msWins = a_ >= b_;
-        const int score = imax(a_, b_);
-        const int time = msWins ? 1 : streakI + 1;
-        int lim2 = lim2INS;
-        if (insNeeded > 0 && delNeeded == 0 && !skipINS) lim2 = limit - (T.insc[time + insNeeded] - T.insc[time]);
-        const bool ok = (score >= lim2) && !skipINS;
-        good = good || ok;
-        const bool preINS = (!msWins && streakI >= 1) || (sMu < sIu);
-        code |= preINS ? 8u : 0u;
-        o.insS = ok ? score : K.subfloor;
-        o.insT = skipINS ? 0 : time;
-    }
-    o.code = code;
-    o.good = good;
-    return o;
-}
-
 }  // namespace bbm
