@@ -50,7 +50,7 @@ __device__ __forceinline__ void cell_tables_init(CellTables& t) {
     for (int i = threadIdx.x; i < DELC_TAB; i += blockDim.x) t.delc[i] = del_score_offset(i);
 }
 
-// One cell.  Streaks never exceed PEN_TAB-1 here (rows <= 606, columns <= 512 in the kernels that use this function), so the
+// One cell.  Streaks never exceed PEN_TAB-1 here (rows <= 606, columns <= TAB_MAX_COLS = 768 in the kernels that use this function), so the
 // tables need no index clamp and `time` never reaches MAX_TIME (the generic kernel handles the wrap for wider windows).
 template <bool LIMITED>
 __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R,

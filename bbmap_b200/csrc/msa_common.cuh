@@ -32,8 +32,9 @@ constexpr int ST_MS = 0, ST_DEL = 1, ST_INS = 2;
 
 // Largest read the register-tiled kernels take (reference ALIGN_ROWS=601, BBMapThread.java:28)
 constexpr int MAXR = 608;
-constexpr int PEN_TAB = MAXR + 8;
-constexpr int DELC_TAB = MAXR + 512 + 32;   // DEL run length (<= columns of the tiled kernels) + delNeeded (<= rows)
+constexpr int TAB_MAX_COLS = 768;              // widest window of the kernels that read the penalty tables (strip / band kernels; the tiled ones stop at 512)
+constexpr int PEN_TAB = TAB_MAX_COLS + 8;      // streak-indexed tables: a DEL run is at most `columns` long, INS / SUB runs at most `rows` (<= MAXR)
+constexpr int DELC_TAB = MAXR + TAB_MAX_COLS + 32;   // DEL run length (<= columns) + delNeeded (<= rows)
 
 __device__ __forceinline__ int imax(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int imin(int a, int b) { return min(a, b); }

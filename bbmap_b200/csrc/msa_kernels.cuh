@@ -43,7 +43,7 @@ constexpr int CLASS_BAD = NUM_WCLASS + 1;      // invalid task
 constexpr int CLASS_STRIP = NUM_WCLASS + 2;    // limited, un-banded fills: thread-per-alignment strip kernel (msa_strip.cu)
 constexpr int CLASS_BAND = NUM_WCLASS + 3;     // limited, banded fills: thread-per-alignment band kernel (msa_band.cu)
 constexpr int NUM_CLASS = NUM_WCLASS + 4;
-constexpr int STRIP_MAX_COLS = 512;            // CellTables cover DEL/INS runs up to this (msa_cell.cuh)
+constexpr int STRIP_MAX_COLS = TAB_MAX_COLS;   // CellTables cover DEL/INS runs up to this (msa_cell.cuh): 600-row reads (configs[4]'s pieces, `maxlen=500`) in padded windows
 constexpr int CLS_NARROW_BIT = 0x80;           // class byte flag: first try the thread-per-alignment narrow kernel
 constexpr int NARROW_BUCKETS_C = 40;
 // counter block (32-bit words)

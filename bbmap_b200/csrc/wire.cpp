@@ -251,3 +251,44 @@ extern "C" int bbm_wire_read_summary(const char* path, bbm_genome_summary* g) {
     fclose(f);
     return BBM_OK;
 }
+
+// ---- ReformatReads.breakReads (current/jgi/ReformatReads.java:1179-1219) as AbstractMapThread.run applies it (AbstractMapThread.java:441-443) ----
+extern "C" int bbm_break_reads(const int8_t* bases, const int8_t* quality, const int64_t* read_off, int64_t nreads, const int8_t* names, const int64_t* name_off,
+                               int32_t paired, int32_t max_len, int32_t min_len, int64_t* n_out, int64_t* bases_out_len, int64_t* names_out_len,
+                               int8_t* out_bases, int8_t* out_quality, int64_t* out_read_off, int8_t* out_names, int64_t* out_name_off, int64_t* src,
+                               int32_t* piece_start) {
+    if (!bases || !read_off || !names || !name_off || nreads < 0 || !n_out || !bases_out_len || !names_out_len)
+        return wfail(BBM_E_ARG, "bbm_break_reads: bad argument");
+    if (max_len <= 0 && min_len <= 0) return wfail(BBM_E_ARG, "bbm_break_reads: min or max read length must be positive");
+    if (max_len > 0 && max_len < min_len) return wfail(BBM_E_ARG, "bbm_break_reads: max read length must be at least min read length");
+    const int64_t mn = min_len > 0 ? min_len : 0;
+    const bool fill = out_bases != nullptr;
+    if (fill && (!out_read_off || !out_names || !out_name_off || !src || !piece_start)) return wfail(BBM_E_ARG, "bbm_break_reads: output buffer missing");
+    int64_t n = 0, nb = 0, nn = 0;
+    auto emit = [&](int64_t r, int64_t start, int64_t stop, int num) {
+        const int64_t nlen = name_off[r + 1] - name_off[r];
+        char suffix[24]; int slen = 0;
+        if (num > 0) slen = snprintf(suffix, sizeof suffix, "_%d", num);
+        if (fill) {
+            out_read_off[n] = nb; out_name_off[n] = nn; src[n] = r; piece_start[n] = (int32_t)start;
+            memcpy(out_bases + nb, bases + read_off[r] + start, (size_t)(stop - start));
+            if (out_quality && quality) memcpy(out_quality + nb, quality + read_off[r] + start, (size_t)(stop - start));
+            memcpy(out_names + nn, names + name_off[r], (size_t)nlen);
+            memcpy(out_names + nn + nlen, suffix, (size_t)slen);
+        }
+        n++; nb += stop - start; nn += nlen + slen;
+    };
+    for (int64_t r = 0; r < nreads; ++r) {
+        const int64_t len = read_off[r + 1] - read_off[r];
+        if (len < mn) continue;                                         // dropped
+        if (max_len < 1 || len <= max_len) { emit(r, 0, len, 0); continue; }
+        if (paired) return wfail(BBM_E_ARG, "bbm_break_reads: paired input is incompatible with breaking reads (a read is longer than max_len)");
+        const int64_t limit = len - mn;
+        int num = 1;
+        for (int64_t start = 0, stop = max_len; start < limit; ++num, start += max_len, stop += max_len)
+            emit(r, start, stop < len ? stop : len, num);
+    }
+    if (fill) { out_read_off[n] = nb; out_name_off[n] = nn; }
+    *n_out = n; *bases_out_len = nb; *names_out_len = nn;
+    return BBM_OK;
+}

@@ -14,7 +14,7 @@ BBM_OK, BBM_E_NODEVICE, BBM_E_CUDA, BBM_E_ARG, BBM_E_SHAPE, BBM_E_CAPACITY = 0, 
 # every symbol include/bbmap_cuda.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "bbm_init", "bbm_destroy", "bbm_set_band", "bbm_last_error", "bbm_device_count", "bbm_upload", "bbm_free_dev",
-    "bbm_msa_batch_dev", "bbm_msa_batch_host", "bbm_launch_count", "bbm_set_option", "bbm_get_stat", "bbm_int_peak", "bbm_banded_batch_dev", "bbm_banded_batch_host", "bbm_seed_batch_dev", "bbm_seed_batch_host", "bbm_noindel_batch_dev", "bbm_noindel_batch_host", "bbm_index_build", "bbm_index_block_sites", "bbm_index_download", "bbm_index_save", "bbm_index_load", "bbm_wire_last_error", "bbm_wire_free", "bbm_wire_write_int_array", "bbm_wire_read_int_array", "bbm_wire_block_fname", "bbm_wire_write_block", "bbm_wire_read_block", "bbm_wire_write_chrom", "bbm_wire_read_chrom", "bbm_wire_write_summary", "bbm_wire_read_summary", "bbm_search_batch_dev", "bbm_search_batch_host", "bbm_msa_gapped_batch_dev", "bbm_msa_gapped_batch_host", "bbm_ingest_batch_dev", "bbm_ingest_batch_host", "bbm_sam_batch_dev", "bbm_sam_batch_host", "bbm_tipdel_batch_dev", "bbm_tipdel_batch_host", "bbm_rescue_batch_dev", "bbm_rescue_batch_host", "bbm_sitelist_from_search_dev", "bbm_sitelist_batch_dev", "bbm_sitelist_batch_host", "bbm_scoreslow_dev", "bbm_scoreslow_host", "bbm_sitelist_tipdel_dev", "bbm_sitelist_bounds_dev",
+    "bbm_msa_batch_dev", "bbm_msa_batch_host", "bbm_launch_count", "bbm_set_option", "bbm_get_stat", "bbm_int_peak", "bbm_banded_batch_dev", "bbm_banded_batch_host", "bbm_seed_batch_dev", "bbm_seed_batch_host", "bbm_noindel_batch_dev", "bbm_noindel_batch_host", "bbm_index_build", "bbm_index_block_sites", "bbm_index_download", "bbm_index_save", "bbm_index_load", "bbm_wire_last_error", "bbm_wire_free", "bbm_wire_write_int_array", "bbm_wire_read_int_array", "bbm_wire_block_fname", "bbm_wire_write_block", "bbm_wire_read_block", "bbm_wire_write_chrom", "bbm_wire_read_chrom", "bbm_wire_write_summary", "bbm_wire_read_summary", "bbm_break_reads", "bbm_search_batch_dev", "bbm_search_batch_host", "bbm_msa_gapped_batch_dev", "bbm_msa_gapped_batch_host", "bbm_ingest_batch_dev", "bbm_ingest_batch_host", "bbm_sam_batch_dev", "bbm_sam_batch_host", "bbm_tipdel_batch_dev", "bbm_tipdel_batch_host", "bbm_rescue_batch_dev", "bbm_rescue_batch_host", "bbm_sitelist_from_search_dev", "bbm_sitelist_batch_dev", "bbm_sitelist_batch_host", "bbm_scoreslow_dev", "bbm_scoreslow_host", "bbm_sitelist_tipdel_dev", "bbm_sitelist_bounds_dev",
     "bbm_sitelist_clearzone3_dev", "bbm_sitelist_tip_penalty_dev", "bbm_sam_tasks_from_lists_dev",
     "bbm_map_set_scaffolds", "bbm_map_batch_dev", "bbm_map_batch_host", "bbm_index_share",
     "bbm_fillUnlimited", "bbm_fillLimitedX",
@@ -75,6 +75,8 @@ def load():
     L.bbm_wire_read_chrom.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int8)]
     L.bbm_wire_write_summary.argtypes = [C.c_char_p, C.c_void_p]
     L.bbm_wire_read_summary.argtypes = [C.c_char_p, C.c_void_p]
+    L.bbm_break_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)] + [C.c_void_p] * 7
     L.bbm_search_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
     L.bbm_msa_gapped_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.bbm_ingest_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]

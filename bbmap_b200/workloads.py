@@ -349,3 +349,20 @@ def make_spliced_reads(chrom_bytes, chrom_off, table, npairs, L=150, seed=7, int
     spl = np.zeros(n, bool); spl[0::2] = plus & (gap > 0); spl[1::2] = ~plus & (gap > 0)
     off = np.arange(n + 1, dtype=np.int64) * L
     return {"bases": reads.reshape(-1), "qual": np.full(n * L, qual, np.uint8), "off": off, "truth": truth, "spliced": spl}
+
+
+def make_long_reads(chrom_bytes, chrom_off, table, nreads, L=1000, seed=8, sub_rate=0.01, indel_rate=0.0005, qual=30):
+    """Single-ended long reads (BASELINE configs[4]: "1 kbp long reads"): L bases from a random locus and strand, ~1 % substitutions, a 1-3 bp indel in
+    about half of them.  The mapper takes them after bbmap_b200.reads.break_reads(..., max_len=500) (`maxlen=500`, ReformatReads.breakReads).
+    Returns dict(bases, qual, off, truth, names, name_off)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tab = np.asarray(table, np.int64)
+    w = tab[:, 2].astype(np.float64); w /= w.sum()
+    sc = rng.choice(len(tab), size=nreads, p=w)
+    start = tab[sc, 1] + (rng.random(nreads) * np.maximum(tab[sc, 2] - L - 8, 1)).astype(np.int64)
+    strand = rng.integers(0, 2, size=nreads)
+    R = _reads_from_footprints(chrom_bytes, tab[sc, 0], start, strand, L, rng, sub_rate, indel_rate, qual, chrom_off)
+    names = [b"long_%d" % i for i in range(nreads)]
+    R["names"] = np.frombuffer(b"".join(names), np.int8).copy()
+    R["name_off"] = np.zeros(nreads + 1, np.int64); np.cumsum([len(x) for x in names], out=R["name_off"][1:])
+    return R

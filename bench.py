@@ -341,6 +341,32 @@ def main():
                            "e2e_reads_per_s": ns_ / dt_s, "ms_per_batch": dt_s * 1e3, "mapped": float(mp_.mean()), "start_and_stop_within_8": float(ok_.mean()),
                            "spliced_reads": int(RS["spliced"].sum()), "spliced_start_and_stop_within_8": float(ok_[RS["spliced"]].mean()),
                            "status_reads": int((rs_["status"] != 0).sum()), "realign_fills": int(dev_s["stats"]["realign_fills"]), "slow_alignments": int(dev_s["stats"]["slow_alignments"])}
+        # configs[4], second half: 1 kbp single-ended reads, cut into 500-base pieces by the host as `maxlen=500` does (ReformatReads.breakReads in
+        # AbstractMapThread.run), every piece mapped as a read of its own through the same host-buffer call
+        from bbmap_b200.reads import break_reads
+        nlong = min(args.pairs, 20_000)
+        RL = wl.make_long_reads(cb, co, table, nlong, L=1000, seed=8)
+        cfg_l = mapper_cfg(paired=False, sam_text=False)
+        t0 = time.perf_counter()
+        P = break_reads(RL["bases"], RL["qual"], RL["off"], RL["names"], RL["name_off"], 500, 0)
+        t_break = time.perf_counter() - t0
+        for _ in range(2):
+            dev_l = m.map_batch(P["bases"], P["quality"], P["read_off"], cfg=cfg_l, match_stride=0)
+        t0 = time.perf_counter(); reps_l = 3
+        for _ in range(reps_l):
+            dev_l = m.map_batch(P["bases"], P["quality"], P["read_off"], cfg=cfg_l, match_stride=0)
+        dt_l = (time.perf_counter() - t0) / reps_l
+        rl_, tl_ = dev_l["recs"], RL["truth"][P["src"]]
+        plen = np.diff(P["read_off"])
+        mp_l = (rl_["flags"] & 1) != 0
+        # a piece that starts at read offset o lies o bases into the footprint on the plus strand, o bases before its end on the minus strand (+- the indel)
+        exp_start = np.where(tl_[:, 1] == 0, tl_[:, 2] + P["piece_start"], tl_[:, 3] - P["piece_start"] - plen + 1)
+        ok_l = mp_l & (rl_["chrom"] == tl_[:, 0]) & (rl_["strand"] == tl_[:, 1]) & (np.abs(rl_["start"] - exp_start) <= 4) & (np.abs((rl_["stop"] - rl_["start"] + 1) - plen) <= 4)
+        line["long_reads"] = {"workload": "%d single-ended reads of 1000 bp on the same reference (~1%% substitutions, a 1-3 bp indel in half of them), cut into %d pieces of <= 500 bp "
+                                          "by bbm_break_reads (maxlen=500) and mapped through bbm_map_batch_host, default flags" % (nlong, len(plen)),
+                              "e2e_long_reads_per_s": nlong / (dt_l + t_break), "e2e_pieces_per_s": len(plen) / (dt_l + t_break), "ms_per_batch": dt_l * 1e3, "break_ms": t_break * 1e3,
+                              "mapped": float(mp_l.mean()), "piece_at_its_origin_within_4": float(ok_l.mean()), "status_reads": int((rl_["status"] != 0).sum()),
+                              "slow_alignments": int(dev_l["stats"]["slow_alignments"]), "realign_fills": int(dev_l["stats"]["realign_fills"])}
     m.close()
     if not args.no_cpu_baseline and world == 1:          # the CPU figure is reported at N=1 only
         threads = os.cpu_count() or 1

@@ -201,6 +201,18 @@ int  bbm_index_save(bbm_ctx* ctx, const char* root_index, int32_t build);
 int  bbm_index_load(bbm_ctx* ctx, const int8_t* d_chroms, const int64_t* chrom_off, int32_t nchroms, int32_t keylen, int32_t chrombits,
                     const char* root_index, int32_t build, bbm_index_cfg* cfg_out, int32_t* nblocks_out);
 
+/* ---- read batching in front of the mapper: ReformatReads.breakReads(list, max, min) as AbstractMapThread.run applies it to every list of reads when
+ * `maxlen` / `minlen` are set (current/jgi/ReformatReads.java:1179-1219, current/align2/AbstractMapThread.java:441-443; how configs[4]'s 1-kbp reads reach a
+ * 600-row aligner).  A read shorter than `min_len` is dropped; a read longer than `max_len` (> 0) is cut into pieces [0,max) [max,2max) ... while the piece
+ * start is < length - min_len, piece number n (1-based) named "<name>_<n>"; other reads pass through unchanged.  Host code, no device involved.
+ * Call once with out_* NULL to get the sizes (n_out, bases_out_len, names_out_len), then with buffers of at least those sizes.  src[i] = index of the input
+ * read piece i came from, piece_start[i] = its offset in that read.  Paired input with a read longer than max_len is BBM_E_ARG (the reference asserts). ---- */
+int bbm_break_reads(const int8_t* bases, const int8_t* quality /* may be NULL */, const int64_t* read_off, int64_t nreads,
+                    const int8_t* names, const int64_t* name_off, int32_t paired, int32_t max_len, int32_t min_len,
+                    int64_t* n_out, int64_t* bases_out_len, int64_t* names_out_len,
+                    int8_t* out_bases, int8_t* out_quality /* may be NULL */, int64_t* out_read_off /* n_out+1 */,
+                    int8_t* out_names, int64_t* out_name_off /* n_out+1 */, int64_t* src /* n_out */, int32_t* piece_start /* n_out */);
+
 /* ---- index search: BBIndex.find (current/align2/BBIndex.java:403-639) — seeds -> candidate sites (SiteScore) ---- */
 #define BBM_MAX_GAPS 10
 #define BBM_ST_ANOMALY        1   /* extendScore located no base (the reference prints an anomaly and scores -99999) */

@@ -65,6 +65,34 @@ def test_map_batch_single_equals_cpu_chain(kind, seed, L):
         m.close()
 
 
+def test_map_batch_long_reads_broken_at_500():
+    """configs[4]: 1-kbp single-ended reads cut by bbm_break_reads (`maxlen=500`, ReformatReads.breakReads) and mapped piece by piece: the device chain ==
+    the sequential CPU chain on 500-row alignments (39 seeds per piece), names carry the piece number into the SAM text."""
+    from bbmap_b200.mapper import BBMapCUDA, mapper_cfg
+    from bbmap_b200.reads import break_reads
+    from oracle import chain, oracle as orc
+    g = _genome("repeats", 31)
+    m = BBMapCUDA([g])
+    try:
+        RL = wl.make_long_reads(m.cb, m.co, m.table, 300, L=1000, seed=32, sub_rate=0.015, indel_rate=0.0008)
+        P = break_reads(RL["bases"], RL["qual"], RL["off"], RL["names"], RL["name_off"], 500, 0)
+        n = len(P["src"])
+        assert n == 600 and (np.diff(P["read_off"]) == 500).all()
+        o = orc.get()
+        idx = o.index_build(m.cb, m.co, 13, -1)
+        ref = chain.map_single(o, idx, m.cb, m.co, m.table, P["bases"], P["quality"], P["read_off"])
+        dev = m.map_batch(P["bases"], P["quality"], P["read_off"], cfg=mapper_cfg(sam_text=True), match_stride=ref["match_stride"], names=P["names"],
+                          name_off=P["name_off"], sam_cap=n * 1400)
+        assert ref["site_overflow"] == 0 and int(dev["stats"]["site_overflow_reads"]) == 0
+        _compare(dev, ref, n)
+        assert (ref["recs"]["flags"] & 1).mean() > 0.97
+        assert int(dev["stats"]["realign_fills"]) == ref["realign_fills"] and int(dev["stats"]["slow_alignments"]) == ref["slow_alignments"]
+        lines = bytes(dev["sam_text"][: int(dev["sam_off"][-1])]).split(b"\n")
+        assert lines[0].startswith(b"long_0_1\t") and lines[1].startswith(b"long_0_2\t") and len(lines) >= n
+    finally:
+        m.close()
+
+
 def test_map_batch_sam_text():
     """SAM lines (SamLine.toBytes + default tags) of the device chain == the Python restatement over the CPU chain's records; multi-scaffold reference."""
     from bbmap_b200.mapper import BBMapCUDA, mapper_cfg

@@ -131,6 +131,23 @@ def test_odd_shapes(oracle, msa):
     _compare(oracle, msa, reads, genome, tasks, bw=20)
 
 
+def test_long_reads_in_wide_windows(oracle, msa):
+    """configs[4]'s pieces (`maxlen=500`) and the longest reads the aligner takes: 450-600 rows in windows of 460-700 columns (indels up to 60) — wider than the
+    register-tiled kernels' 512 columns, so the limited fills run on the strip kernel up to 768 columns and on the row-sequential kernel beyond."""
+    genome = wl.random_genome(80000, seed=61)
+    for tight, ratio, n in ((True, 0.56, 500), (False, 0.336, 300)):
+        reads, tasks = wl.make_msa_tasks(genome, n, seed=62 + tight, lengths=(450, 500, 600), flags=wl.TF_SCORE | wl.TF_TRACEBACK, tight=tight, ratio=ratio,
+                                         max_indel=60, pad=8)
+        cols = tasks["ref_end"] - tasks["ref_start"] + 1
+        assert (cols > 512).mean() > 0.5 and cols.max() <= 768
+        exp = _compare(oracle, msa, reads, genome, tasks)
+        assert (exp["match_len"] > 0).sum() > 0.5 * n
+    # a few windows beyond 768 columns as well (row-sequential class)
+    reads, tasks = wl.make_msa_tasks(genome, 60, seed=64, lengths=(600,), flags=wl.TF_SCORE | wl.TF_TRACEBACK | wl.TF_RAW_LIMITED, tight=False, ratio=0.336, pad=130)
+    assert ((tasks["ref_end"] - tasks["ref_start"] + 1) > 768).all()
+    _compare(oracle, msa, reads, genome, tasks)
+
+
 def test_narrow_candidates_of_the_generic_class(oracle, msa):
     """600-bp reads in 605-column windows are too wide for the tiled kernels (row-sequential class) yet narrow enough for the narrow kernel.
     The ones it finishes leave their reserved slot in the class list unused: the row-sequential kernel must take the list length from the
