@@ -1,0 +1,228 @@
+"""TEST INFRASTRUCTURE — an independent restatement (Python objects in Python lists, written from the Java text alone) of the per-read site-list policies of
+the unpaired mapping loop:
+  the TRIM_LIST block of processRead          current/align2/BBMapThread.java:426-429  (Collections.sort + trimList :140-249)
+  Tools.trimSiteList / trimSitesBelowCutoff   current/align2/Tools.java:654-672, 1106-1160
+  the tail of processRead                     current/align2/BBMapThread.java:478-553  (mergeDuplicateSites, sort, setPerfectFlag, clearzone / ambiguity,
+                                              score gate, removeLowQualitySitesUnpaired)
+  Tools.mergeDuplicateSites / countTopScores / removeLowQualitySitesUnpaired / condenseStrict   Tools.java:542-568, 696-758, 911-927, 985-1003
+  SiteScore.compareTo / PCOMP / positionalMatch / setSlowScore / setPairedScore   current/stream/SiteScore.java:55-76, 353-395, 962-983
+  Read.setPerfectFlag                         current/stream/Read.java:2494-2513 (no match string exists yet at that point: testMatchPerfection(false) is false)
+Shares no code with oracle/sitelist_oracle.c.  Java float arithmetic is numpy float32, one rounding per operation."""
+import functools
+
+import numpy as np
+
+F = np.float32
+
+
+class Site:
+    def __init__(self, chrom, strand, start, stop, hits, score, quick, slow, paired, perfect, semiperfect, rescued, gaps, tag=None):
+        self.chrom, self.strand, self.start, self.stop, self.hits = chrom, strand, start, stop, hits
+        self.score, self.quickScore, self.slowScore, self.pairedScore = score, quick, slow, paired
+        self.perfect, self.semiperfect, self.rescued, self.gaps, self.tag = perfect, semiperfect, rescued, gaps, tag
+
+    def set_slow_score(self, x):
+        if x <= 0:
+            self.pairedScore = self.slowScore = x
+        elif self.pairedScore <= 0:
+            self.slowScore = x
+        elif self.pairedScore > 0:
+            self.pairedScore = x + (self.pairedScore - self.slowScore) if self.slowScore > 0 else x + 1
+        self.slowScore = x
+
+    def positional_match(self, b, test_gaps):
+        if (self.chrom, self.strand, self.start, self.stop) != (b.chrom, b.strand, b.start, b.stop):
+            return False
+        if not test_gaps or (self.gaps is None and b.gaps is None):
+            return True
+        if (self.gaps is None) != (b.gaps is None):
+            return False
+        return list(self.gaps) == list(b.gaps)
+
+
+def compare_to(a, b):
+    for x in (b.score - a.score, b.slowScore - a.slowScore, b.pairedScore - a.pairedScore, b.quickScore - a.quickScore, a.chrom - b.chrom):
+        if x != 0:
+            return x
+    return a.start - b.start
+
+
+def pcomp(a, b):
+    for x, y in ((a.chrom, b.chrom), (a.start, b.start), (a.stop, b.stop), (a.strand, b.strand)):
+        if x != y:
+            return x - y
+    for x, y in ((a.score, b.score), (a.slowScore, b.slowScore), (a.quickScore, b.quickScore)):
+        if x != y:
+            return y - x
+    if a.perfect != b.perfect:
+        return -1 if a.perfect else 1
+    if a.rescued != b.rescued:
+        return 1 if a.rescued else -1
+    return 0
+
+
+def sort_sites(lst, cmp=compare_to):
+    lst.sort(key=functools.cmp_to_key(cmp))          # list.sort is stable, like Collections.sort
+
+
+def trim_sites_below_cutoff(ssl, cutoff, retain_paired, retain_semiperfect, min_retain, max_retain):
+    if len(ssl) <= min_retain:
+        return
+    del ssl[max_retain:]
+    removed = 0
+    max_remove = len(ssl) - min_retain
+    for i in range(len(ssl) - 1, -1, -1):
+        ss = ssl[i]
+        if not retain_semiperfect or not ss.semiperfect:
+            if ss.score < cutoff and (not retain_paired or ss.pairedScore <= 0):
+                ssl[i] = None
+                removed += 1
+                if removed >= max_remove:
+                    break
+    if removed:
+        ssl[:] = [x for x in ssl if x is not None]
+
+
+def trim_site_list(ssl, fraction, retain_paired, retain_semiperfect, min_retain, max_retain):
+    if not ssl:
+        return -999999
+    if len(ssl) == 1:
+        return ssl[0].score
+    if 1 < min_retain < len(ssl):
+        mx = ssl[0].score
+    else:
+        mx = max(max(s.score for s in ssl), -999999)
+    cutoff = int(F(mx) * F(fraction))
+    trim_sites_below_cutoff(ssl, cutoff, retain_paired, retain_semiperfect, min_retain, max_retain)
+    return mx
+
+
+def trim_list(lst, retain_paired, max_score, special_case_perfect, min_retain, max_retain):
+    """BBMapThread.trimList with USE_AFFINE_SCORE."""
+    if not lst:
+        return -99999
+    if len(lst) == 1:
+        return lst[0].score
+    t = lambda f, mr=min_retain: trim_site_list(lst, f, retain_paired, True, mr, max_retain)
+    highest = t(.6)
+    if highest == max_score and special_case_perfect:
+        t(.94)
+        if len(lst) > 8:
+            t(.99)
+        return highest
+    mstr2 = 1 if min_retain <= 1 else min_retain + 1
+    for size, frac in ((4, .65), (8, .7), (12, .75), (16, .8), (20, .85), (24, .9), (32, .95)):
+        if len(lst) > size:
+            t(frac)
+    for size, frac in ((40, .97), (48, .99)):
+        if len(lst) > size:
+            t(frac, mstr2)
+    return highest
+
+
+def trim_policy(sites, read_len, cfg):
+    """The TRIM_LIST block of processRead.  Returns the highest quick score (or None when the block is skipped)."""
+    max_sw = 70 + (read_len - 1) * 100
+    if cfg["trim_list"] and len(sites) > 1:
+        if cfg["min_trim_sites_to_retain"] > 1:
+            sort_sites(sites)
+        return trim_list(sites, False, max_sw, True, int(cfg["min_trim_sites_to_retain"]), int(cfg["max_trim_sites_to_retain"]))
+    return None
+
+
+def merge_duplicate_sites(lst, merge_different_gaps=True):
+    if len(lst) < 2:
+        return 0
+    sort_sites(lst, pcomp)
+    removed = 0
+    a = lst[0]
+    for i in range(1, len(lst)):
+        b = lst[i]
+        exact = a.positional_match(b, True)
+        if exact or (merge_different_gaps and a.positional_match(b, False)):
+            better = a
+            if not exact:
+                if a.score != b.score:
+                    better = a if a.score > b.score else b
+                elif a.slowScore != b.slowScore:
+                    better = a if a.slowScore > b.slowScore else b
+                elif a.pairedScore != b.pairedScore:
+                    better = a if a.pairedScore > b.pairedScore else b
+            a.set_slow_score(max(a.slowScore, b.slowScore))
+            a.pairedScore = 0 if (a.pairedScore <= a.slowScore and b.pairedScore <= a.slowScore) else max(0, a.pairedScore, b.pairedScore)
+            a.score = max(a.score, b.score)
+            a.perfect = a.perfect or b.perfect
+            a.semiperfect = a.semiperfect or b.semiperfect
+            if not exact:
+                a.gaps = better.gaps
+            removed += 1
+            lst[i] = None
+        else:
+            a = b
+    if removed:
+        lst[:] = [x for x in lst if x is not None]
+    return removed
+
+
+def count_top_scores(lst, thresh):
+    if not lst:
+        return 0
+    top = lst[0]
+    limit = top.score - thresh
+    count = 1
+    for s in lst[1:]:
+        if s.score < limit:
+            break
+        if top.start != s.start and top.stop != s.stop:
+            count += 1
+    return count
+
+
+def final_policy(sites, read_len, cfg):
+    """The tail of processRead after scoreSlow.  Returns dict(mapped, perfect, ambiguous, clearzone, best_sites); `sites` is edited in place."""
+    max_sw = 70 + (read_len - 1) * 100
+    out = dict(mapped=False, perfect=False, ambiguous=False, clearzone=None, best_sites=None)
+    if sites:
+        merge_duplicate_sites(sites)
+        sort_sites(sites)
+    top = sites[0] if sites else None
+    out["perfect"] = bool(top is not None and (top.slowScore == max_sw or top.perfect))
+    if len(sites) > 1:
+        score = top.score
+        if out["perfect"]:
+            clearzone = int(cfg["clearzonep"])
+        else:
+            cz1b = F(max_sw) * F(cfg["cz1b_scale"]) - F(cfg["cz1b_flat"])
+            cz1c = F(max_sw) * F(cfg["cz1c_scale"]) - F(cfg["cz1c_flat"])
+            if F(score) > cz1b:
+                clearzone = int((F((max_sw - score) * int(cfg["clearzone1b"])) + (F(score) - cz1b) * F(int(cfg["clearzone1"]))) / (F(max_sw) - cz1b))
+            elif F(score) > cz1c:
+                clearzone = int(((cz1b - F(score)) * F(int(cfg["clearzone1c"])) + (F(score) - cz1c) * F(int(cfg["clearzone1b"]))) / (cz1b - cz1c))
+            else:
+                clearzone = int(cfg["clearzone1c"])
+        out["clearzone"] = clearzone
+        nbest = count_top_scores(sites, clearzone)
+        if nbest > 1:
+            out["ambiguous"] = True
+        else:
+            e, lim1e = int(cfg["clearzone1e"]), int(cfg["clearzone_limit1e"])
+            lim = (int(F(4) * F(lim1e)) if out["perfect"] else (2 * lim1e if score + e >= max_sw else lim1e)) + 1
+            if len(sites) > lim and clearzone < e:
+                nbest = count_top_scores(sites, e)
+                if nbest > lim:
+                    out["ambiguous"] = True
+        out["best_sites"] = nbest
+    if sites:
+        lim = int(F(max_sw) * F(cfg["min_align_ratio"]))
+        if sites[0].score < lim:
+            del sites[:]
+        else:
+            thresh = min(lim, max(1, lim - int(cfg["clearzone3"])))
+            if sites[0].score < thresh:
+                del sites[:]
+            else:
+                for i in range(len(sites) - 1, 1, -1):
+                    if sites[i].slowScore < thresh:
+                        del sites[i]
+    out["mapped"] = len(sites) > 0
+    return out

@@ -1,0 +1,76 @@
+"""CPU: the per-read site-list policies of the unpaired loop — the C restatement the CUDA kernels are checked against
+(oracle/sitelist_oracle.c) must equal a second restatement written from the Java text alone (tests/pysitelist.py: SiteScore objects in Python lists,
+Collections.sort as a stable comparator sort, numpy float32 for Java float) on every surviving site in order, and on the per-read outcome
+(mapped / perfect / ambiguous, clearzone, number of best sites, highest quick score)."""
+import numpy as np
+import pytest
+
+from bbmap_b200 import sitelist as sl
+from sitelist_cases import random_lists
+
+import pysitelist as ps
+
+
+def _to_sites(row, n):
+    out = []
+    for i in range(n):
+        s = row[i]
+        g = None if s["ngaps"] == 0 else [int(x) for x in s["gaps"][: s["ngaps"]]]
+        out.append(ps.Site(int(s["chrom"]), int(s["strand"]), int(s["start"]), int(s["stop"]), int(s["hits"]), int(s["score"]), int(s["quick_score"]),
+                           int(s["slow_score"]), int(s["paired_score"]), bool(s["perfect"]), bool(s["semiperfect"]), bool(s["rescued"]), g, tag=i))
+    return out
+
+
+def _same(sites, row, n, r):
+    assert len(sites) == n, (r, len(sites), n)
+    for i, s in enumerate(sites):
+        t = row[i]
+        got = (s.chrom, s.strand, s.start, s.stop, s.hits, s.score, s.quickScore, s.slowScore, s.pairedScore, int(s.perfect), int(s.semiperfect), int(s.rescued),
+               [] if s.gaps is None else list(s.gaps))
+        exp = (int(t["chrom"]), int(t["strand"]), int(t["start"]), int(t["stop"]), int(t["hits"]), int(t["score"]), int(t["quick_score"]), int(t["slow_score"]),
+               int(t["paired_score"]), int(t["perfect"]), int(t["semiperfect"]), int(t["rescued"]), t["gaps"][: t["ngaps"]].tolist())
+        assert got == exp, (r, i, got, exp)
+
+
+@pytest.mark.parametrize("seed,kw", [(109, {}), (110, dict(min_trim_sites_to_retain=1)), (111, dict(max_trim_sites_to_retain=20)), (112, dict(trim_list=0))])
+def test_trim_policy(oracle, seed, kw):
+    lists, nss, ro = random_lists(nreads=1200, seed=seed)
+    cfg = sl.policy_cfg(**kw)
+    L2, n2, out = oracle.sitelist(sl.SL_TRIM, lists, nss, ro, cfg)
+    trimmed = 0
+    for r in range(len(nss)):
+        sites = _to_sites(lists[r], int(nss[r]))
+        hi = ps.trim_policy(sites, int(ro[r + 1] - ro[r]), cfg[0])
+        _same(sites, L2[r], int(n2[r]), r)
+        if hi is not None:
+            assert hi == out["best_sites"][r], (r, hi, out[r])
+        trimmed += len(sites) < nss[r]
+    assert trimmed > 200 or kw.get("trim_list") == 0
+
+
+@pytest.mark.parametrize("seed,kw", [(120, {}), (121, dict(clearzone3=100)), (122, dict(min_align_ratio=0.3, clearzone_limit1e=2))])
+def test_final_policy(oracle, seed, kw):
+    lists, nss, ro = random_lists(nreads=1500, seed=seed, after_alignment=True)
+    # paired scores on some sites: mergeDuplicateSites' setSlowScore / setPairedScore interplay
+    rng = np.random.default_rng(seed)
+    for r in range(0, len(nss), 5):
+        for i in range(int(nss[r])):
+            if rng.random() < 0.5:
+                lists[r, i]["paired_score"] = int(lists[r, i]["slow_score"]) + int(rng.integers(-50, 400))
+    cfg = sl.policy_cfg(**kw)
+    L2, n2, out = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, cfg)
+    seen = dict(mapped=0, ambiguous=0, perfect=0, merged=0, dropped=0)
+    for r in range(len(nss)):
+        sites = _to_sites(lists[r], int(nss[r]))
+        res = ps.final_policy(sites, int(ro[r + 1] - ro[r]), cfg[0])
+        _same(sites, L2[r], int(n2[r]), r)
+        f = int(out["flags"][r])
+        assert (bool(f & sl.F_MAPPED), bool(f & sl.F_AMBIGUOUS)) == (res["mapped"], res["ambiguous"]), (r, f, res)
+        if res["mapped"]:
+            assert bool(f & sl.F_PERFECT) == res["perfect"], (r, f, res)
+        if res["clearzone"] is not None:
+            assert (int(out["clearzone"][r]), int(out["best_sites"][r])) == (res["clearzone"], res["best_sites"]), (r, out[r], res)
+        for k in ("mapped", "ambiguous", "perfect"):
+            seen[k] += res[k]
+        seen["dropped"] += nss[r] > 0 and not res["mapped"]
+    assert seen["mapped"] > 300 and seen["ambiguous"] > 50 and seen["perfect"] > 50 and (seen["dropped"] > 50 or "min_align_ratio" in kw), seen
