@@ -151,3 +151,68 @@ def fill_and_score_limited(oracle, packed, maxRows, maxColumns, read, ref, ref_s
         sv[2] = gref.from_gapped(sv[2])
         ms = pywalk.traceback2(M, bytes(read.view(np.uint8)), bytes(fill_ref.view(np.uint8)), columns, gstart, max4[0], max4[1], max4[2])
     return sv, ms, max4
+
+
+# ---------------- MSA.score(match) (current/align2/MSA.java:488-557, calc*Score :726-747, MultiStateAligner11tsJNI.java:1347-1425) ----------------
+def _del_score(n):
+    score = -472
+    if n > 256:                                   # approximateGaps: a run longer than MINGAP is costed like the gapped reference would be
+        rem, div = n % 128, (n - 128) // 128
+        score += div * -2                          # POINTS_GAP = -GAPCOST = -max(1, GAPLEN/64)
+        n = rem + 128
+    if n > 80:
+        score += ((n - 80 + 3) // 4) * -1
+        n = 80
+    if n > 20:
+        score += (n - 20) * -1
+        n = 20
+    if n > 5:
+        score += (n - 5) * -9
+        n = 5
+    if n > 1:
+        score += (n - 1) * -33
+    return score
+
+
+def _ins_score(n):
+    total = 0
+    for i in range(1, n + 1):                      # POINTS_INS_ARRAY_C: cumulative, clamped at MIN_SCORE
+        total = max(-1046575, total + (-8 if i > 20 else (-23 if i > 5 else (-39 if i > 1 else -395))))
+    return total
+
+
+def _sub_score(n):
+    score = -127
+    if n > 5:
+        score += (n - 5) * -25
+        n = 5
+    if n > 1:
+        score += (n - 1) * -51
+    return score
+
+
+def score_match(match):
+    """match: bytes in long format.  Runs come from itertools.groupby instead of the reference's mode / current bookkeeping."""
+    import itertools
+    score = 0
+    prev_mode, prev_len = "0", 0
+    for sym, grp in itertools.groupby(match):
+        c, n = chr(sym), len(list(grp))
+        if c == "m":
+            score += 70 + (n - 1) * 100
+        elif c == "S":
+            score += _sub_score(n)
+            if prev_mode in "NR":
+                score += -51 - -127
+            elif prev_mode == "m" and prev_len < 2:
+                score += -147 - -127
+        elif c == "D":
+            score += _del_score(n)
+        elif c in "IXY":
+            score += _ins_score(n)
+        elif c in "CNR":
+            pass                                   # POINTS_NOCALL = POINTS_NOREF = 0
+        else:
+            raise AssertionError("Unhandled symbol " + c)
+        prev_mode, prev_len = c, n
+    return score

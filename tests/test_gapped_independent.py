@@ -113,3 +113,25 @@ def test_gref_layout_by_hand():
     for p in (96, 150, 367, 1136, 1200, 1303):
         assert g.from_gapped(g.to_gapped(p)) == p
     assert g.to_gapped(1136) == 278 and g.from_gapped(272) == 368 and g.from_gapped(273) == 368 + 128
+
+
+def test_score_of_a_match_string_independent(oracle):
+    """MSA.score(match) (what realign_new and the tip-penalty code re-score match strings with): groupby formulation vs the C restatement."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    syms = np.frombuffer(b"mmmmmmmmmmmmSSNIDDXYCR", np.uint8)
+    cases = [b"m" * 100, b"m" * 40 + b"S" + b"m" * 59, b"mS" + b"m" * 98, b"N" + b"S" * 7 + b"m" * 20, b"m" * 30 + b"D" * 300 + b"m" * 70, b"m" * 30 + b"D" * 257 + b"m" * 70,
+             b"m" * 30 + b"D" * 256 + b"m" * 70, b"X" * 3 + b"m" * 50 + b"I" * 25 + b"m" * 50 + b"Y" * 2, b"C" * 5 + b"m" * 95, b"m", b"S", b"D" * 16000 + b"m"]
+    for _ in range(3000):
+        n = int(rng.integers(1, 300))
+        runs = []
+        while sum(len(x) for x in runs) < n:
+            s = syms[rng.integers(0, len(syms))]
+            runs.append(bytes([s]) * int(rng.choice([1, 1, 2, 3, 6, 21, 81, 90, 300]) if s in b"DIS" else rng.integers(1, 40)))
+        cases.append(b"".join(runs))
+    oracle.lib.orc_score_match.restype = C.c_int
+    for m in cases:
+        b = np.frombuffer(m, np.int8)
+        exp = oracle.lib.orc_score_match(b.ctypes.data_as(C.c_void_p), C.c_int(len(b)))
+        assert pygapped.score_match(m) == exp, (m[:80], pygapped.score_match(m), exp)
+    assert pygapped.score_match(b"m" * 100) == 9970 and pygapped.score_match(b"m" * 30 + b"DDD" + b"m" * 70) == 2970 + 6970 - 472 - 66
