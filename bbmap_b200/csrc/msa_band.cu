@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(BAND_THREADS) msa_band_kernel(BandParams S) {
         // (cheap, divergent), then evaluates ONE cell for every lane that has one (the expensive part, converged): a lane whose band is 4 cells wide
         // does not wait at the end of each row for a neighbour whose band is 25 cells wide, it simply gets through its rows sooner.
         int row = 0, col = 0, colStop = 0, off = 0, lM = 0, lD = 0, ref0 = 0;
+        int refCur = 0, hlCur = 0;                             // ref[col-1] and horizLimit[col] of the cell about to be evaluated: loaded one cell ahead
         bool inRow = false, fillDone = !active, insTop = false, insBot = false;
         CellRow R; R.call1 = 0; R.call0 = 0; R.callN = false; R.vlimit = 0; R.delBar = false;
         unsigned char* tbr = tb;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(BAND_THREADS) msa_band_kernel(BandParams S) {
                         tbr = tb + (long long)row * nd;
                         col = colStart;
                         ref0 = col < 2 ? '!' : (ref[col - 2] == 'N' ? 0x100 : (int)ref[col - 2]);
+                        refCur = ref[col - 1]; hlCur = hl[col];
                         if (row == rows) lastLo = colStart;
                         inRow = true;
                     }
@@ -133,14 +135,16 @@ __global__ void __launch_bounds__(BAND_THREADS) msa_band_kernel(BandParams S) {
             if (__all_sync(0xffffffffu, fillDone)) break;
             if (inRow) {
                 const int slot = col + off;
-                int ref1 = ref[col - 1]; if (ref1 == 'N') ref1 = 0x100;
+                int ref1 = refCur; if (ref1 == 'N') ref1 = 0x100;
+                const int hlim = hlCur;
+                if (col < cols) { refCur = ref[col]; hlCur = hl[col + 1]; }      // the next cell of the row: its loads overlap this cell's arithmetic
                 int dM, dD, dI;
                 if (col == 1) { dM = row == 1 ? 0 : tab.insc[row - 1]; dD = dM; dI = dM; }        // (row-1, 0)
                 else { dM = SLOT(bM, slot); dD = SLOT(bD, slot); dI = SLOT(bI, slot); }
                 const int uM = SLOT(bM, slot + 1), uI = SLOT(bI, slot + 1);
                 const int delNeeded = imax(0, row - col - 1), insNeeded = imax(0, (rows - row) - (cols - col) - 1);
                 const bool insBar = (insTop && col > 1) || (insBot && col < cols - 1);
-                const CellOut o = msa_cell<true>(K, R, dM, dD, dI, lM, lD, uM, uI, ref1, ref0, insBar, hl[col], delNeeded, insNeeded, tab);
+                const CellOut o = msa_cell<true>(K, R, dM, dD, dI, lM, lD, uM, uI, ref1, ref0, insBar, hlim, delNeeded, insNeeded, tab);
                 SLOT(bM, slot) = o.ms; SLOT(bD, slot) = o.del; SLOT(bI, slot) = o.ins;
                 tbr[slot] = (unsigned char)o.code;
                 iters++;
