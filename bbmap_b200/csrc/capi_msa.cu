@@ -136,8 +136,8 @@ int run_msa(bbm_ctx* c, const int8_t* d_reads, const int8_t* d_refs, const bbm_m
             const unsigned int cnt = bdClass[cls];
             if (!cnt) continue;
             const int nd = 32 << cls;
-            const size_t smemPerBlock = (size_t)3 * nd * BT * 4 + 16 * 1024;
-            int perSm = (int)((220 * 1024) / smemPerBlock); if (perSm < 1) perSm = 1; if (perSm > 8) perSm = 8;
+            const size_t smemPerBlock = bbm_msa_band_smem_bytes(bRows, bCols, nd) + 1024;       // + the per-block reservation of the runtime
+            int perSm = (int)((227 * 1024) / smemPerBlock); if (perSm < 1) perSm = 1; if (perSm > 12) perSm = 12;
             long long blocks = (long long)c->sms * perSm;
             const long long needB = ((long long)cnt + BT - 1) / BT;
             if (needB < blocks) blocks = needB;

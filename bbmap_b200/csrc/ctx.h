@@ -26,6 +26,7 @@ extern "C" int bbm_launch_msa_band(const MsaParams* P, const int* list, int nlis
                                    void* scratch, unsigned int* counter, int blocks, cudaStream_t st);
 extern "C" int bbm_msa_strip_blocks_per_sm();
 extern "C" int bbm_msa_strip_max_cols();
+extern "C" size_t bbm_msa_band_smem_bytes(int maxRows, int maxCols, int nd);
 extern "C" unsigned long long bbm_msa_strip_task_bytes(int rows, int cols);
 extern "C" size_t bbm_msa_strip_fixed_bytes(int chunkCount, int maxRows, int blocks);
 extern "C" int bbm_launch_msa_strip(const MsaParams* P, const int* list, const unsigned int* endPtr, unsigned int base, int chunkStart, int chunkCount,

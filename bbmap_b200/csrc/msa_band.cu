@@ -27,20 +27,21 @@ struct BandParams {
     MsaParams P;
     const int* list; const unsigned int* endPtr; unsigned int base; int nlist;
     int nd, maxRows, maxCols;                 // slots per row (>= 3*halfband+3 of every task), largest shape in the list
+    int pen, delcN;                           // sizes of the penalty tables in shared memory (cell_tables_init_dyn)
     int* lim;                                 // [threads][maxRows + maxCols + 8]  vertLimit / horizLimit of the thread's current alignment
     unsigned char* tb;                        // [threads][(maxRows + 1) * nd]     predecessor codes by (row, slot)
     unsigned int* counter;
 };
 
 __global__ void __launch_bounds__(BAND_THREADS) msa_band_kernel(BandParams S) {
-    extern __shared__ int bandBuf[];          // [3][nd][BAND_THREADS]
-    __shared__ CellTables tab;
-    cell_tables_init(tab);
+    extern __shared__ int bandBuf[];          // penalty tables sized for this launch's shapes, then [3][nd][BAND_THREADS]
+    CellTablesDyn tab;
+    cell_tables_init_dyn(bandBuf, S.pen, S.delcN, tab);
     __syncthreads();
     const MsaParams& P = S.P;
     const int tid = threadIdx.x, nd = S.nd;
     const long long gthread = (long long)blockIdx.x * BAND_THREADS + tid;
-    int* bM = bandBuf + tid; int* bD = bM + nd * BAND_THREADS; int* bI = bD + nd * BAND_THREADS;
+    int* bM = bandBuf + ((cell_tables_dyn_ints(S.pen, S.delcN) + 31) & ~31) + tid; int* bD = bM + nd * BAND_THREADS; int* bI = bD + nd * BAND_THREADS;
 #define SLOT(p, s) (p)[(s) * BAND_THREADS]
     int* vl = S.lim + gthread * (S.maxRows + S.maxCols + 8);
     int* hl = vl + S.maxRows + 4;
@@ -251,6 +252,13 @@ using namespace bbm;
 
 extern "C" int bbm_msa_band_threads() { return BAND_THREADS; }
 extern "C" int bbm_msa_band_max_nd() { return BAND_MAX_ND; }
+static inline int band_pen(int maxRows, int maxCols) { return (maxRows > maxCols ? maxRows : maxCols) + 8; }
+static inline int band_delc(int maxRows, int maxCols) { return maxRows + maxCols + 8; }
+// dynamic shared memory of one block: the penalty tables for shapes up to maxRows x maxCols + three band rows of nd slots per thread
+extern "C" size_t bbm_msa_band_smem_bytes(int maxRows, int maxCols, int nd) {
+    const int tab = (cell_tables_dyn_ints(band_pen(maxRows, maxCols), band_delc(maxRows, maxCols)) + 31) & ~31;
+    return ((size_t)tab + (size_t)3 * nd * BAND_THREADS) * sizeof(int);
+}
 extern "C" size_t bbm_msa_band_thread_bytes(int maxRows, int maxCols, int nd) {
     return (size_t)(maxRows + maxCols + 8) * 4 + (size_t)(maxRows + 1) * nd;
 }
@@ -261,9 +269,10 @@ extern "C" int bbm_launch_msa_band(const MsaParams* P, const int* list, int nlis
     const size_t threads = (size_t)blocks * BAND_THREADS;
     S.lim = (int*)scratch;
     S.tb = (unsigned char*)scratch + threads * (size_t)(maxRows + maxCols + 8) * 4;
-    const size_t smem = (size_t)3 * nd * BAND_THREADS * sizeof(int);
-    // static tables (14.5 KB) + the band rows: above the 48 KB default from 64 slots on; the opt-in is per device, so it is simply made on every launch
-    cudaError_t ea = cudaFuncSetAttribute(msa_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * BAND_MAX_ND * BAND_THREADS * sizeof(int)));
+    S.pen = band_pen(maxRows, maxCols); S.delcN = band_delc(maxRows, maxCols);
+    const size_t smem = bbm_msa_band_smem_bytes(maxRows, maxCols, nd);
+    // tables + band rows: above the 48 KB default from 64 slots on; the opt-in is per device, so it is simply made on every launch
+    cudaError_t ea = cudaFuncSetAttribute(msa_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbm_msa_band_smem_bytes(MAXR, STRIP_MAX_COLS, BAND_MAX_ND));
     if (ea != cudaSuccess) return (int)ea;
     msa_band_kernel<<<blocks, BAND_THREADS, smem, st>>>(S);
     return (int)cudaGetLastError();

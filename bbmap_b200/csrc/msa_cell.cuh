@@ -50,9 +50,27 @@ __device__ __forceinline__ void cell_tables_init(CellTables& t) {
     for (int i = threadIdx.x; i < DELC_TAB; i += blockDim.x) t.delc[i] = del_score_offset(i);
 }
 
+// The same tables behind pointers, sized for the shapes of one launch (msa_band.cu: the band kernel's occupancy is bound by shared memory, and the
+// fixed-size struct above costs it 18 KB per block of 64 threads).  pen > the longest streak (max(rows, columns)), delcN > rows + columns.
+struct CellTablesDyn {
+    const int* insc; const int* delc; const int* delExt; const int* insExt; const int* subExt;
+};
+__host__ __device__ inline int cell_tables_dyn_ints(int pen, int delcN) { return 4 * pen + delcN; }
+__device__ __forceinline__ void cell_tables_init_dyn(int* base, int pen, int delcN, CellTablesDyn& t) {
+    int* insc = base; int* delExt = base + pen; int* insExt = base + 2 * pen; int* subExt = base + 3 * pen; int* delc = base + 4 * pen;
+    for (int i = threadIdx.x; i < pen; i += blockDim.x) {
+        insc[i] = ins_score_offset(i);
+        delExt[i] = i == 0 ? P_DEL : (i < LIM3 ? P_DEL2 : (i < LIM4 ? P_DEL3 : (i < LIM5 ? P_DEL4 : (((i & 3) == 0) ? P_DEL5 : 0))));
+        insExt[i] = i == 0 ? P_INS : (i < LIM3 ? P_INS2 : (i < LIM4 ? P_INS3 : P_INS4));
+        subExt[i] = i == 0 ? P_SUB : (i < 5 ? P_SUB2 : P_SUB3);
+    }
+    for (int i = threadIdx.x; i < delcN; i += blockDim.x) delc[i] = del_score_offset(i);
+    t.insc = insc; t.delc = delc; t.delExt = delExt; t.insExt = insExt; t.subExt = subExt;
+}
+
 // One cell.  Streaks never exceed PEN_TAB-1 here (rows <= 606, columns <= TAB_MAX_COLS = 768 in the kernels that use this function), so the
 // tables need no index clamp and `time` never reaches MAX_TIME (the generic kernel handles the wrap for wider windows).
-template <bool LIMITED>
+template <bool LIMITED, class TT = CellTables>
 __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R,
                                             int dMS, int dDEL, int dINS,        // (row-1,col-1)
                                             int lMS, int lDEL,                  // (row,  col-1)
@@ -61,7 +79,7 @@ __device__ __forceinline__ CellOut msa_cell(const CellConst& K, const CellRow& R
                                             bool insBar,                        // INS state is barred at this cell
                                             int hlimit,                         // horizLimit[col]
                                             int delNeeded, int insNeeded,
-                                            const CellTables& T) {
+                                            const TT& T) {
     CellOut o;
     const bool match = (R.call1 == ref1);
     const bool prevMatch = (R.call0 == ref0);
