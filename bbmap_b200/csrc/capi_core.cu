@@ -98,6 +98,7 @@ extern "C" int bbm_set_option(bbm_ctx* c, const char* key, int value) {
     if (!strcmp(key, "strip_min_tasks")) { c->strip_min_tasks = value; return BBM_OK; }
     if (!strcmp(key, "slow_lookahead")) { c->slow_lookahead = value; return BBM_OK; }
     if (!strcmp(key, "band")) { c->use_band = value; return BBM_OK; }
+    if (!strcmp(key, "banded_thread")) { c->banded_thread = value; return BBM_OK; }
     if (!strcmp(key, "strip")) { c->use_strip = value; return BBM_OK; }
     if (!strcmp(key, "msa_count")) { c->msa_count = value; return BBM_OK; }
     if (!strcmp(key, "strip_debug")) { c->strip_debug = value; return BBM_OK; }

@@ -8,14 +8,39 @@ int run_banded(bbm_ctx* c, const int8_t* dq, const int8_t* dr, const bbm_band_ta
                       cudaStream_t st, float* ms_out) {
     if (n <= 0) { if (ms_out) *ms_out = 0.f; return BBM_OK; }
     unsigned int* cb = (unsigned int*)c->counters.p;
-    CK(cudaMemsetAsync(cb + 200, 0, 4, st));
+    CK(cudaMemsetAsync(cb + 200, 0, 16, st));          // [200] task counter, [201] wide-pair count, [202] widest band of the batch, [203] counter of the wide pass
     CK(cudaEventRecord(c->ev0, st));
-    int blocks = c->sms * 8;
-    const long long need = (n + 3) / 4;
-    if (need < blocks) blocks = (int)need;
-    int e = bbm_launch_banded(dq, dr, dt, dout, n, cb + 200, blocks, st);
-    if (e) return fail(BBM_E_CUDA, "banded_kernel launch", (cudaError_t)e);
-    c->launches++;
+    int e;
+    if (c->banded_thread) {
+        // narrow bands (Dedupe: 3-9 cells): one thread per pair (banded_thread_kernel); the widest band of the batch picks the instantiation and tells
+        // whether any pair needs the warp-per-pair kernel at all
+        int sb = c->sms * 4; if ((n + 255) / 256 < sb) sb = (int)((n + 255) / 256);
+        e = bbm_launch_banded_maxwidth(dt, n, cb + 202, sb, st);
+        if (e) return fail(BBM_E_CUDA, "banded_maxwidth_kernel launch", (cudaError_t)e);
+        unsigned int maxBand = 0;
+        CK(cudaMemcpyAsync(&maxBand, cb + 202, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const bool anyWide = maxBand > 15;
+        if (anyWide && c->bandedWide.ensure((size_t)n * 4 + 16)) return fail(BBM_E_CUDA, "cudaMalloc banded wide list");
+        int blocks = c->sms * 8;
+        const long long need = (n + 127) / 128;
+        if (need < blocks) blocks = (int)need;
+        e = bbm_launch_banded_thread(dq, dr, dt, dout, n, cb + 200, (int*)c->bandedWide.p, cb + 201, (int)maxBand, blocks, st);
+        if (e) return fail(BBM_E_CUDA, "banded_thread_kernel launch", (cudaError_t)e);
+        c->launches += 2;
+        if (anyWide) {
+            e = bbm_launch_banded(dq, dr, dt, dout, n, cb + 203, c->sms * 8, st, (const int*)c->bandedWide.p, cb + 201);
+            if (e) return fail(BBM_E_CUDA, "banded_kernel launch", (cudaError_t)e);
+            c->launches++;
+        }
+    } else {
+        int blocks = c->sms * 8;
+        const long long need = (n + 3) / 4;
+        if (need < blocks) blocks = (int)need;
+        e = bbm_launch_banded(dq, dr, dt, dout, n, cb + 200, blocks, st, nullptr, nullptr);
+        if (e) return fail(BBM_E_CUDA, "banded_kernel launch", (cudaError_t)e);
+        c->launches++;
+    }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaStreamSynchronize(st));
     if (ms_out) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); *ms_out = ms; }

@@ -38,7 +38,10 @@ extern "C" int bbm_launch_msa_narrow(const MsaParams* P, const int* nlist, int n
 extern "C" int bbm_msa_narrow_threads();
 extern "C" int bbm_msa_narrow_buckets();
 extern "C" int bbm_launch_banded(const int8_t* q, const int8_t* r, const bbm_band_task* t, bbm_band_out* o, long long n,
-                                 unsigned int* counter, int blocks, cudaStream_t st);
+                                 unsigned int* counter, int blocks, cudaStream_t st, const int* list, const unsigned int* listCount);
+extern "C" int bbm_launch_banded_maxwidth(const bbm_band_task* t, long long n, unsigned int* outMax, int blocks, cudaStream_t st);
+extern "C" int bbm_launch_banded_thread(const int8_t* q, const int8_t* r, const bbm_band_task* t, bbm_band_out* o, long long n,
+                                        unsigned int* counter, int* wideList, unsigned int* wideCount, int maxBand, int blocks, cudaStream_t st);
 extern "C" int bbm_seed_upload_tables(const float* pc, const float* pci);
 extern "C" int bbm_launch_seed(const int8_t* bases, const int8_t* quality, const long long* read_off, long long nreads, const bbm_seed_cfg* cfg,
                                int maxKeys, int* nkeys, int* offsets, int* keys, int* keyScores, int8_t* baseScores,
@@ -136,6 +139,8 @@ struct bbm_ctx {
     long long strip_min_tasks = 8192;
     int use_band = 1;                          // banded limited fills go to the thread-per-alignment band kernel (0: register-tiled kernel + row-sequential re-runs)
     DevBuf bandScratch;
+    DevBuf bandedWide;                         // BandedAligner: pairs whose band is too wide for the thread-per-pair kernel
+    int banded_thread = 1;                     // option "banded_thread": 0 = warp-per-pair kernel for every pair (A/B, tests)
     int slow_lookahead = 16;                   // scoreSlow: sites of one read taken per round after its first (1 = one site per round, the round-1 schedule)
     DevBuf slowBuf[9];                         // scoreSlow rounds: per-read state, packed requests, their results, counters, gapped requests / gap arrays / results
     size_t strip_budget = (size_t)32 << 30;    // device scratch the strip kernel may use per chunk (raised or lowered with "strip_budget_mb")

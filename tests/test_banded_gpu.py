@@ -8,15 +8,19 @@ from bbmap_b200 import workloads as wl
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def band():
+@pytest.fixture(scope="module", params=["thread", "warp"])
+def band(request):
+    """Both kernels: one thread per pair for bands of up to 15 cells with the wider pairs handed to the warp-per-pair kernel (default), and the
+    warp-per-pair kernel for every pair."""
     from bbmap_b200.banded import BandedAlignerCUDA
     b = BandedAlignerCUDA()
+    b.L.bbm_set_option(b.h, b"banded_thread", 1 if request.param == "thread" else 0)
     yield b
     b.close()
 
 
-@pytest.mark.parametrize("widths,maxlen", [(None, 1200), ((3, 5, 11, 21, 53, 64, 101, 127), 500), ((1, 2, 4, 31, 32, 33, 63), 300)])
+@pytest.mark.parametrize("widths,maxlen", [(None, 1200), ((3, 5, 11, 21, 53, 64, 101, 127), 500), ((1, 2, 4, 31, 32, 33, 63), 300), ((1, 2, 3, 4, 5, 6, 7, 8, 9), 400),
+                                           ((8, 9, 10, 11, 12, 13, 14, 15, 16, 17), 400)])
 def test_banded_random(oracle, band, widths, maxlen):
     q, r, tasks = wl.make_banded_tasks(3000, seed=18, min_len=10, max_len=maxlen, widths=widths,
                                        max_edits=(2, 5, 26) if widths is None else (0, 1, 2, 5, 16, 26, 40, 63))
