@@ -879,6 +879,15 @@ static int can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, co
     return outer >= outerDistLimit && inner <= cfg->max_pair_dist;
 }
 
+/* test entry points: the pairing helpers on their own, so that a second restatement can be compared with them (tests/test_pairing_independent.py) */
+int orc_test_pair_initial(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim) {
+    int x = *na, y = *nb; const int r = pair_site_scores_initial(a, &x, len1, b, &y, len2, cfg, maxTrim); *na = x; *nb = y; return r;
+}
+void orc_test_pair_final(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim) {
+    int x = *na, y = *nb; pair_site_scores_final(a, &x, len1, b, &y, len2, cfg, maxTrim); *na = x; *nb = y;
+}
+int orc_test_can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, const orc_map_cfg* cfg) { return can_pair(ss1, ss2, len1, len2, cfg); }
+
 /* Tools.removeLowQualitySitesPaired */
 static int remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) {
     if (n == 0) return 0;

@@ -27,4 +27,7 @@ int64_t orc_map_pairs(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, 
                       const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* nkeys, const orc_policy_cfg* pc,
                       const orc_map_cfg* cfg, const void* slow_cfg, const orc_tipdel_cfg* tc, orc_map_rec* recs, int8_t* match_buf, int64_t match_stride,
                       int64_t* stats);
+int orc_test_pair_initial(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim);
+void orc_test_pair_final(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim);
+int orc_test_can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, const orc_map_cfg* cfg);
 #endif
