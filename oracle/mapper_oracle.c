@@ -1036,6 +1036,9 @@ static void clear_mapping(orc_map_rec* q, orc_map_rec* mate, int* n) {   /* Read
     *n = 0; q->flags &= ~(1 | 8); mate->flags &= ~8;
 }
 
+int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) { return remove_low_quality_paired(v, n, maxSw, multSingle, multPaired); }
+int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) { return is_bad_pair(r, m, cfg); }
+
 int64_t orc_map_pairs(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, const int8_t* basesP, const int8_t* basesM, const int8_t* quality,
                       const int64_t* read_off, const int8_t* refs, const int64_t* chrom_off, const int32_t* nkeys, const orc_policy_cfg* pc,
                       const orc_map_cfg* cfg, const void* slow_cfg, const orc_tipdel_cfg* tc, orc_map_rec* recs, int8_t* match_buf, int64_t match_stride,

@@ -30,4 +30,6 @@ int64_t orc_map_pairs(orc_ss* lists, int32_t* nss, int64_t nreads, int32_t cap, 
 int orc_test_pair_initial(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim);
 void orc_test_pair_final(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* nb, int len2, const orc_map_cfg* cfg, int maxTrim);
 int orc_test_can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, const orc_map_cfg* cfg);
+int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired);
+int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg);
 #endif

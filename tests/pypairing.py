@@ -143,3 +143,43 @@ def can_pair(s1, s2, len1, len2, cfg):
         return False
     inner, outer = _dists(s1, s2, require)
     return outer >= (max(len1, len2) * OUTER_DIST_MULT) // OUTER_DIST_DIV and inner <= int(cfg["max_pair_dist"])
+
+
+def remove_low_quality_sites_paired(lst, max_sw, mult_single, mult_paired):
+    """Tools.removeLowQualitySitesPaired (current/align2/Tools.java:934-958).  The list is edited in place; returns the number removed."""
+    if not lst:
+        return 0
+    initial = len(lst)
+    thresh = int(F(max_sw) * F(mult_single))
+    thresh_paired = int(F(max_sw) * F(mult_paired))
+    if lst[0].score < thresh_paired:
+        del lst[:]
+        return initial
+    for i in range(len(lst) - 1, -1, -1):
+        s = lst[i]
+        if s.slowScore < (thresh_paired if s.pairedScore > 0 else thresh):
+            del lst[i]
+    return initial - len(lst)
+
+
+def is_bad_pair(r, m, require_correct_strands, same_strand_pairs, maxdist):
+    """Read.isBadPair (current/stream/Read.java:1305-1331); r, m: objects with mapped, paired, chrom, start, stop, strand (0 plus, 1 minus)."""
+    if m is None or r.paired:
+        return False
+    if not r.mapped or not m.mapped:
+        return False
+    if r.chrom != m.chrom:
+        return True
+    inner = m.start - r.stop if r.start <= m.start else r.start - m.stop
+    if inner > maxdist:
+        return True
+    if require_correct_strands and ((r.strand == m.strand) != same_strand_pairs):
+        return True
+    if not same_strand_pairs:
+        if r.strand == 0 and m.strand == 1:
+            if r.start >= m.stop:
+                return True
+        elif r.strand == 1 and m.strand == 0:
+            if m.start >= r.stop:
+                return True
+    return False

@@ -106,3 +106,59 @@ def test_can_pair(oracle):
                     assert bool(exp) == got, (p, i, j, kw)
                     yes += got; no += not got
     assert yes > 500 and no > 500
+
+
+def test_remove_low_quality_sites_paired(oracle):
+    rng = np.random.default_rng(320)
+    lib = oracle.lib
+    lib.orc_test_remove_low_quality_paired.restype = C.c_int
+    cleared = trimmed = 0
+    for _ in range(1500):
+        L = int(rng.choice([50, 100, 150, 250])); maxq = 70 + 100 * (L - 1)
+        n = int(rng.integers(1, 14))
+        v = np.zeros(n, sl.SS_DTYPE)
+        top = int(maxq * rng.uniform(0.2, 1.0))
+        sc = np.sort((top * rng.uniform(0.1, 1.0, size=n)).astype(np.int32))[::-1]
+        v["score"] = sc; v["slow_score"] = sc; v["chrom"] = 1; v["start"] = rng.integers(0, 9000, size=n); v["stop"] = v["start"] + L - 1
+        v["paired_score"] = np.where(rng.random(n) < 0.5, sc + rng.integers(1, 400, size=n), 0)
+        ms, mp = (0.56, 0.448) if rng.random() < 0.7 else (0.7, 0.3)
+        sites = _to_sites(v, n)
+        a = v.copy()
+        k = lib.orc_test_remove_low_quality_paired(_p(a), C.c_int(n), C.c_int(maxq), C.c_float(ms), C.c_float(mp))
+        removed = pp.remove_low_quality_sites_paired(sites, maxq, ms, mp)
+        # the C restatement signals "list cleared" by returning 0 survivors only when the top site fails; it returns the survivor count otherwise
+        if len(sites) == 0:
+            assert k == 0, (k, removed)
+            cleared += 1
+        else:
+            _same(sites, a, k, "rlqsp")
+            trimmed += removed > 0
+    assert cleared > 100 and trimmed > 300
+
+
+def test_is_bad_pair(oracle):
+    from bbmap_b200.mapper import MAP_REC_DTYPE
+    rng = np.random.default_rng(321)
+    lib = oracle.lib
+    lib.orc_test_is_bad_pair.restype = C.c_int
+
+    class R:
+        pass
+    bad = good = 0
+    for kw in ({}, dict(require_correct_strands=0), dict(same_strand_pairs=1), dict(max_pair_dist=400)):
+        cfg = map_cfg(paired=1, **kw)
+        for _ in range(1500):
+            recs = np.zeros(2, MAP_REC_DTYPE); objs = []
+            for i in range(2):
+                o = R()
+                o.chrom = int(rng.integers(1, 3)) if rng.random() < 0.2 else 1
+                o.start = int(rng.integers(0, 3000)) if rng.random() < 0.8 else int(rng.integers(0, 60000)); o.stop = o.start + int(rng.choice([49, 99, 149]))
+                o.strand = int(rng.integers(0, 2)); o.mapped = rng.random() < 0.9; o.paired = rng.random() < 0.2
+                recs[i]["chrom"] = o.chrom; recs[i]["start"] = o.start; recs[i]["stop"] = o.stop; recs[i]["strand"] = o.strand
+                recs[i]["flags"] = (1 if o.mapped else 0) | (8 if o.paired else 0)
+                objs.append(o)
+            exp = lib.orc_test_is_bad_pair(_p(recs[0:1]), _p(recs[1:2]), _p(cfg))
+            got = pp.is_bad_pair(objs[0], objs[1], bool(cfg["require_correct_strands"][0]), bool(cfg["same_strand_pairs"][0]), int(cfg["max_pair_dist"][0]))
+            assert bool(exp) == got, (kw, recs)
+            bad += got; good += not got
+    assert bad > 800 and good > 800
