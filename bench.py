@@ -13,7 +13,7 @@ One "step" = one call of the batched mapper over one batch of synthetic 2x150 bp
 `roofline` the dominant kernels of the step — the MultiStateAligner11ts fills — against the integer-issue roof measured in the same run;
 `msa`     the MultiStateAligner11ts microbenchmark (configs[2], GCUPS; bench/msa_bench.py), `msa_band_sweep` its band sweep (bw 12 / 40, ratio 0.18),
           `banded` BandedAligner at G6 scale, `spliced` RNA-seq-style pairs with 0.3-12 kbp introns through the same mapper call (configs[4] shape within the
-          default maxindel);
+          default maxindel, intronlen=10), `long_reads` 1-kbp single-ended reads cut at 500 by bbm_break_reads (maxlen=500) and mapped piece by piece;
 `cpu_baseline` / `--impl reference`: the same chain through the sequential CPU restatement (oracle/), one process per host core.
 Prints ONE JSON line (rank 0)."""
 import argparse
