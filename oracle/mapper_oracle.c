@@ -1036,6 +1036,25 @@ static void clear_mapping(orc_map_rec* q, orc_map_rec* mate, int* n) {   /* Read
     *n = 0; q->flags &= ~(1 | 8); mate->flags &= ~8;
 }
 
+/* test entry point: one SiteScore with its match string through a helper of realign_new / genMatchString (tests/test_clip_independent.py).
+ * op 0 leftPaddingNeeded, 1 rightPaddingNeeded, 2 clipTipIndels, 3 fixXY, 4 unclip, 5 setPerfect.  match is edited in place (capacity mcap). */
+int orc_test_site_op(int op, orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
+                     int tiplen, int maxIndel) {
+    mctx C; memset(&C, 0, sizeof C); C.refs = refs; C.chrom_off = chrom_off;
+    msite m; memset(&m, 0, sizeof m); m.s = *s; m.match = NULL; m.mlen = 0;
+    if (*mlen >= 0) set_match(&m, match, *mlen);
+    int refLen; const int8_t* ref = chrom_ptr(&C, m.s.chrom, &refLen);
+    int r = 0;
+    if (op == 0) r = left_padding_needed(&m, tiplen, maxIndel);
+    else if (op == 1) r = right_padding_needed(&m, tiplen, maxIndel);
+    else if (op == 2) r = clip_tip_indels(&C, &m, bases, len, tiplen, maxIndel);
+    else if (op == 3) r = fix_xy(&C, &m, bases, len);
+    else if (op == 4) r = unclip(&m, bases, ref, refLen);
+    else if (op == 5) { set_perfect(&m.s, bases, len, ref, refLen); r = m.s.perfect; }
+    *s = m.s;
+    if (m.match) { if (m.mlen <= mcap) memcpy(match, m.match, (size_t)m.mlen); *mlen = m.mlen; free(m.match); } else *mlen = -1;
+    return r;
+}
 int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) { return remove_low_quality_paired(v, n, maxSw, multSingle, multPaired); }
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) { return is_bad_pair(r, m, cfg); }
 

@@ -32,4 +32,6 @@ void orc_test_pair_final(orc_ss* a, int32_t* na, int len1, orc_ss* b, int32_t* n
 int orc_test_can_pair(const orc_ss* ss1, const orc_ss* ss2, int len1, int len2, const orc_map_cfg* cfg);
 int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired);
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg);
+int orc_test_site_op(int op, orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
+                     int tiplen, int maxIndel);
 #endif
