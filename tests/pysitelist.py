@@ -226,3 +226,72 @@ def final_policy(sites, read_len, cfg):
                         del sites[i]
     out["mapped"] = len(sites) > 0
     return out
+
+
+def calc_tip_score_penalty(mapped, match, bases, map_score, tiplen):
+    """AbstractMapThread.calcTipScorePenalty (current/align2/AbstractMapThread.java:2499-2567) on a long-format match string.  Returns (penalty, status):
+    status 1 = the string ends before tiplen+1 read symbols were seen (the Java would run off the array), 2 = short format (digits)."""
+    L = len(bases)
+    max_score = 70 + (L - 1) * 100
+    if not mapped or match is None or L < 2 * tiplen:
+        return 0, 0
+
+    def scan(order):
+        points, cpos, prev = 0, 0, "m"
+        it = iter(order)
+        while cpos <= tiplen:
+            try:
+                b = chr(match[next(it)])
+            except StopIteration:
+                return None
+            if b == "m":
+                cpos += 1
+            elif b == "D":
+                if prev != "D":
+                    points += 2 * (tiplen + 2 - cpos)
+            elif b in "NC":
+                points += tiplen + 2 - cpos
+                cpos += 1
+            elif b.isdigit():
+                return "short"
+            else:
+                points += 2 * (tiplen + 2 - cpos)
+                cpos += 1
+            prev = b
+        return points
+
+    left = scan(range(len(match)))
+    if left == "short":
+        return 0, 2
+    if left is None:
+        return 0, 1
+    right = scan(range(len(match) - 1, -1, -1))
+    if right is None:
+        return 0, 1
+    points = left + right
+    last = L - 1
+    b = bases[0]
+    if b != ord("N") and b == bases[1]:
+        i = 2
+        while i <= tiplen and bases[i] == b:
+            points += 1; i += 1
+    b = bases[last]
+    if b != ord("N") and b == bases[last - 1]:
+        i = last - 2
+        while i >= last - tiplen and bases[i] == b:
+            points += 1; i -= 1
+    if points < 1:
+        return 0, 0
+    f = (F(80) * F(points)) / (F(points) + F(80))
+    penalty = int(f * F(.0022) * F(max_score))
+    max_penalty = map_score - (abs(max_score) // 10 if max_score >= 0 else -(abs(max_score) // 10))
+    if max_penalty <= 0:
+        return 0, 0
+    return min(penalty, max_penalty), 0
+
+
+def apply_score_penalty(sites, penalty):
+    if penalty > 0:
+        for s in sites:
+            s.set_slow_score(s.slowScore - penalty)
+            s.score = s.score - penalty

@@ -74,3 +74,27 @@ def test_final_policy(oracle, seed, kw):
             seen[k] += res[k]
         seen["dropped"] += nss[r] > 0 and not res["mapped"]
     assert seen["mapped"] > 300 and seen["ambiguous"] > 50 and seen["perfect"] > 50 and (seen["dropped"] > 50 or "min_align_ratio" in kw), seen
+
+
+@pytest.mark.parametrize("seed,tiplen", [(3, 7), (4, 5)])
+def test_tip_penalty(oracle, seed, tiplen):
+    """calcTipScorePenalty + applyScorePenalty: the penalty of every read and every score of its list."""
+    from sitelist_cases import homopolymer_reads, random_match_strings
+    lists, nss, ro = random_lists(nreads=1500, cap=8, seed=seed + 90, after_alignment=True)
+    l1, n1, fl = oracle.sitelist(sl.SL_FINAL, lists, nss, ro, sl.policy_cfg())
+    bases = homopolymer_reads(ro, seed); match, mo = random_match_strings(ro, seed)
+    el, ep, es = oracle.sitelist_tip_penalty(l1, n1, ro, bases, match, mo, fl, tiplen)
+    b8 = np.ascontiguousarray(bases).view(np.int8); m8 = np.ascontiguousarray(match).view(np.uint8)
+    hit = 0
+    for r in range(len(n1)):
+        n = int(n1[r])
+        sites = _to_sites(l1[r], n)
+        mapped = bool(fl["flags"][r] & sl.F_MAPPED) and n > 0
+        ms = m8[int(mo[r]): int(mo[r + 1])]
+        mstr = bytes(ms) if len(ms) else None
+        pen, st = ps.calc_tip_score_penalty(mapped, mstr, b8[int(ro[r]): int(ro[r + 1])].tolist(), sites[0].score if n else 0, tiplen)
+        assert (pen, st) == (int(ep[r]), int(es[r])), (r, pen, st, ep[r], es[r], mstr)
+        ps.apply_score_penalty(sites, pen)
+        _same(sites, el[r], n, r)
+        hit += pen > 0
+    assert hit > 250
