@@ -295,3 +295,90 @@ def apply_score_penalty(sites, penalty):
         for s in sites:
             s.set_slow_score(s.slowScore - penalty)
             s.score = s.score - penalty
+
+
+# ---------------- GapTools (current/align2/GapTools.java:10-14, 26-91, 126-175) and removeOutOfBounds (AbstractMapThread.java:2444-2479) ----------------
+GAPBUFFER2, GAPLEN, MINGAP = 128, 128, 256
+
+
+def _jdiv(a, b):
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b > 0) else -q
+
+
+def calc_gref_len(a, b, gaps):
+    total = b - a + 1
+    if gaps is None:
+        return total
+    for i in range(2, len(gaps), 2):
+        total -= max(0, _jdiv(gaps[i] - gaps[i - 1] - GAPBUFFER2, GAPLEN)) * (GAPLEN - 1)
+    return total
+
+
+def fix_gaps(a, b, gaps, min_gap=MINGAP):
+    """Returns the gap array (the same list object, edited in place, where the reference keeps its array) or None."""
+    if gaps is None:
+        return None
+    if not (a <= gaps[-1] and b >= gaps[0]):               # Tools.overlap
+        return None
+    changed = 0
+    if gaps[0] != a:
+        gaps[0] = a; changed += 1
+    if gaps[-1] != b:
+        gaps[-1] = b; changed += 1
+    for i in range(len(gaps)):
+        if gaps[i] < a:
+            gaps[i] = a; changed += 1
+        elif gaps[i] > b:
+            gaps[i] = b; changed += 1
+    for i in range(1, len(gaps)):
+        if gaps[i - 1] > gaps[i]:
+            gaps[i] = gaps[i - 1]; changed += 1
+    if changed == 0:
+        return gaps
+    gaps[0], gaps[-1] = a, b
+    remove = 0
+    for i in range(0, len(gaps), 2):
+        gaps[i] = min(max(gaps[i], a), b); gaps[i + 1] = min(max(gaps[i + 1], a), b)
+        if gaps[i] == gaps[i + 1]:
+            remove += 1
+    if remove == 0:
+        return gaps
+    ranges = [[gaps[i], gaps[i + 1]] for i in range(0, len(gaps), 2)]       # fixGaps2
+    for i in range(1, len(ranges)):
+        r1, r2 = ranges[i - 1], ranges[i]
+        if r1 is not None and r2[0] - r1[1] <= min_gap:
+            r2[0] = min(r1[0], r2[0]); r2[1] = max(r1[1], r2[1])
+            ranges[i - 1] = None
+    ranges = [r for r in ranges if r is not None]
+    if len(ranges) < 2:
+        return None
+    return [x for r in ranges for x in r]
+
+
+def set_stop(site, b):
+    """SiteScore.setStop (stream/SiteScore.java:944-951): with a gap array the array is always re-fixed."""
+    site.stop = b
+    if site.gaps is not None:
+        site.gaps[-1] = b
+        site.gaps = fix_gaps(site.start, site.stop, site.gaps)
+
+
+def remove_out_of_bounds(sites, read_len, chrom_max_index, is_single_scaffold, sam_out, expected_len_limit):
+    """chrom_max_index: chrom -> ChromosomeArray.maxIndex; is_single_scaffold(chrom, start, stop) -> bool.  Returns the number of sites removed."""
+    initial = len(sites)
+    i = 0
+    while i < len(sites):
+        ss = sites[i]
+        if ss.start < 0 or ss.stop > chrom_max_index[ss.chrom]:
+            del sites[i]
+            continue
+        if sam_out and not is_single_scaffold(ss.chrom, ss.start, ss.stop):
+            del sites[i]
+            continue
+        if calc_gref_len(ss.start, ss.stop, ss.gaps) >= expected_len_limit:
+            set_stop(ss, ss.start + min(read_len + 40, expected_len_limit))
+            if ss.gaps is not None:
+                ss.gaps = fix_gaps(ss.start, ss.stop, ss.gaps)          # GapTools.fixGaps(ss) assigns its result to ss.gaps
+        i += 1
+    return initial - len(sites)

@@ -98,3 +98,43 @@ def test_tip_penalty(oracle, seed, tiplen):
         _same(sites, el[r], n, r)
         hit += pen > 0
     assert hit > 250
+
+
+@pytest.mark.parametrize("seed,sam_out,with_scaf", [(91, 1, True), (92, 0, True), (93, 1, False)])
+def test_remove_out_of_bounds(oracle, seed, sam_out, with_scaf):
+    """removeOutOfBounds with GapTools.calcGrefLen / fixGaps and Data.isSingleScaffold: surviving sites, their stops and gap arrays."""
+    import pysam_fields as psf
+    rng = np.random.default_rng(seed)
+    n, cap = 1500, 12
+    lists, nss, ro = random_lists(nreads=n, cap=cap, seed=seed)
+    maxidx = np.array([5200, 4900, 5600], np.int32)
+    scaf_loc = [np.array([100, 1800, 3700]), np.array([50]), np.array([0, 900, 1700, 2500, 4000])]
+    scaf = (np.cumsum([0] + [len(x) for x in scaf_loc]).astype(np.int32), np.concatenate(scaf_loc).astype(np.int32), None) if with_scaf else None
+    for r in range(n):
+        for i in range(nss[r]):
+            u = rng.random()
+            if u < 0.05:
+                lists[r, i]["start"] = -int(rng.integers(1, 50)); lists[r, i]["stop"] = lists[r, i]["start"] + 120
+            elif u < 0.10:
+                lists[r, i]["stop"] = int(maxidx[lists[r, i]["chrom"] - 1]) + int(rng.integers(0, 3))
+            elif u < 0.14:
+                lists[r, i]["stop"] = lists[r, i]["start"] + int(rng.integers(2500, 2600))
+    S = psf.Scaffolds([(ch + 1, int(x), 1) for ch, locs in enumerate(scaf_loc) for x in locs], 300) if with_scaf else None
+    single = (lambda c, a, b: S.is_single(c, a, b)) if with_scaf else (lambda c, a, b: True)
+    mi = {c + 1: int(maxidx[c]) for c in range(3)}
+    removed_total = cut = 0
+    for limit in (2522, 180):
+        L2, n2, out = oracle.sitelist_bounds(lists, nss, ro, maxidx, scaf, sam_out=sam_out, expected_len_limit=limit)
+        for r in range(n):
+            sites = _to_sites(lists[r], int(nss[r]))
+            before = [(s.start, s.stop) for s in sites]
+            removed = ps.remove_out_of_bounds(sites, int(ro[r + 1] - ro[r]), mi, single, bool(sam_out), limit)
+            for s in sites:
+                if s.gaps is None:
+                    s.gaps = None
+            # a gap array that fixGaps dissolved is None here and ngaps == 0 on the C side
+            _same(sites, L2[r], int(n2[r]), (r, limit))
+            assert removed == int(out["best_sites"][r]), (r, removed, out[r])
+            removed_total += removed
+            cut += sum(1 for s in sites if (s.start, s.stop) not in before)
+    assert removed_total > 300 and cut > 100, (removed_total, cut)
