@@ -1055,6 +1055,19 @@ int orc_test_site_op(int op, orc_ss* s, int8_t* match, int32_t* mlen, int32_t mc
     if (m.match) { if (m.mlen <= mcap) memcpy(match, m.match, (size_t)m.mlen); *mlen = m.mlen; free(m.match); } else *mlen = -1;
     return r;
 }
+/* test entry point: realign_new on one site (tests/test_realign_independent.py); returns the number of fills it asked for */
+int orc_test_realign_new(orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
+                         int padding, int recur, int minValidScore, int forbidIndels, int fixXY) {
+    static orc_msa* msa = NULL;
+    if (!msa) msa = orc_msa_new(601, MAXCOLS);
+    mctx C; memset(&C, 0, sizeof C); C.refs = refs; C.chrom_off = chrom_off; C.msa = msa;
+    msite m; memset(&m, 0, sizeof m); m.s = *s; m.match = NULL; m.mlen = 0;
+    if (*mlen >= 0) set_match(&m, match, *mlen);
+    realign_new(&C, &m, bases, len, padding, recur, minValidScore, forbidIndels, fixXY);
+    *s = m.s;
+    if (m.match) { if (m.mlen <= mcap) memcpy(match, m.match, (size_t)m.mlen); *mlen = m.mlen; free(m.match); } else *mlen = -1;
+    return (int)C.fills;
+}
 int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) { return remove_low_quality_paired(v, n, maxSw, multSingle, multPaired); }
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) { return is_bad_pair(r, m, cfg); }
 

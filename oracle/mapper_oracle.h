@@ -34,4 +34,6 @@ int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSi
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg);
 int orc_test_site_op(int op, orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
                      int tiplen, int maxIndel);
+int orc_test_realign_new(orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
+                         int padding, int recur, int minValidScore, int forbidIndels, int fixXY);
 #endif
