@@ -1068,6 +1068,19 @@ int orc_test_realign_new(orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, 
     if (m.match) { if (m.mlen <= mcap) memcpy(match, m.match, (size_t)m.mlen); *mlen = m.mlen; free(m.match); } else *mlen = -1;
     return (int)C.fills;
 }
+/* test entry point: AbstractMapThread.rescue(anchor, loose, ...) on one pair of lists (tests/test_rescue_independent.py); returns the status bits */
+int orc_test_rescue(orc_ss* A, int nA, int lenA, orc_ss* L, int32_t* nL, int cap, const int8_t* basesP, const int8_t* basesM, const int8_t* qualL, int lenL,
+                    int searchDist, const int8_t* refs, const int64_t* chrom_off, const orc_map_cfg* cfg, const orc_tipdel_cfg* tc, int clearzone1e, int64_t* counts) {
+    static orc_msa* msa = NULL;
+    if (!msa) msa = orc_msa_new(601, MAXCOLS);
+    mctx C; memset(&C, 0, sizeof C); C.refs = refs; C.chrom_off = chrom_off; C.msa = msa; C.cfg = cfg;
+    pstats ps; memset(&ps, 0, sizeof ps);
+    int status = 0, n = *nL;
+    rescue_dir(&C, A, nA, lenA, L, &n, cap, basesP, basesM, qualL, lenL, searchDist, tc, clearzone1e, &ps, &status);
+    *nL = n;
+    if (counts) { counts[0] = ps.rescue_scans; counts[1] = ps.rescue_fills; }
+    return status;
+}
 int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) { return remove_low_quality_paired(v, n, maxSw, multSingle, multPaired); }
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) { return is_bad_pair(r, m, cfg); }
 

@@ -36,4 +36,6 @@ int orc_test_site_op(int op, orc_ss* s, int8_t* match, int32_t* mlen, int32_t mc
                      int tiplen, int maxIndel);
 int orc_test_realign_new(orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, const int8_t* bases, int len, const int8_t* refs, const int64_t* chrom_off,
                          int padding, int recur, int minValidScore, int forbidIndels, int fixXY);
+int orc_test_rescue(orc_ss* A, int nA, int lenA, orc_ss* L, int32_t* nL, int cap, const int8_t* basesP, const int8_t* basesM, const int8_t* qualL, int lenL,
+                    int searchDist, const int8_t* refs, const int64_t* chrom_off, const orc_map_cfg* cfg, const orc_tipdel_cfg* tc, int clearzone1e, int64_t* counts);
 #endif
