@@ -1081,6 +1081,27 @@ int orc_test_rescue(orc_ss* A, int nA, int lenA, orc_ss* L, int32_t* nL, int cap
     if (counts) { counts[0] = ps.rescue_scans; counts[1] = ps.rescue_fills; }
     return status;
 }
+/* test entry point: AbstractMapThread.genMatchString on one read's list (tests/test_genmatch_independent.py); sites come in without match strings.
+ * Returns the number of fills; writes the surviving sites, the `paired` flag and the top site's match string. */
+int orc_test_gen_match_string(orc_ss* lists, int32_t* n, int cap, const int8_t* basesP, const int8_t* basesM, int len, const int8_t* refs, const int64_t* chrom_off,
+                              const orc_map_cfg* cfg, int maxSwScore, int setSSScore, int32_t* paired, int8_t* top_match, int32_t* top_mlen, int32_t mcap) {
+    static orc_msa* msa = NULL;
+    if (!msa) msa = orc_msa_new(601, MAXCOLS);
+    mctx C; memset(&C, 0, sizeof C); C.refs = refs; C.chrom_off = chrom_off; C.msa = msa; C.cfg = cfg;
+    msite* v = (msite*)calloc((size_t)(cap > 0 ? cap : 1), sizeof(msite));
+    int k = *n;
+    for (int i = 0; i < k; i++) { v[i].s = lists[i]; v[i].match = NULL; v[i].mlen = 0; v[i].serial = i; }
+    int pf = *paired;
+    gen_match_string(&C, v, &k, basesP, basesM, len, maxSwScore, setSSScore, &pf);
+    *paired = pf;
+    for (int i = 0; i < k; i++) lists[i] = v[i].s;
+    *top_mlen = -1;
+    if (k > 0 && v[0].match) { if (v[0].mlen <= mcap) memcpy(top_match, v[0].match, (size_t)v[0].mlen); *top_mlen = v[0].mlen; }
+    for (int i = 0; i < k; i++) if (v[i].match) free(v[i].match);          /* (removed sites were released by gen_match_string itself or leak here: test code) */
+    free(v);
+    *n = k;
+    return (int)C.fills;
+}
 int orc_test_remove_low_quality_paired(orc_ss* v, int n, int maxSw, float multSingle, float multPaired) { return remove_low_quality_paired(v, n, maxSw, multSingle, multPaired); }
 int orc_test_is_bad_pair(const orc_map_rec* r, const orc_map_rec* m, const orc_map_cfg* cfg) { return is_bad_pair(r, m, cfg); }
 

@@ -38,4 +38,6 @@ int orc_test_realign_new(orc_ss* s, int8_t* match, int32_t* mlen, int32_t mcap, 
                          int padding, int recur, int minValidScore, int forbidIndels, int fixXY);
 int orc_test_rescue(orc_ss* A, int nA, int lenA, orc_ss* L, int32_t* nL, int cap, const int8_t* basesP, const int8_t* basesM, const int8_t* qualL, int lenL,
                     int searchDist, const int8_t* refs, const int64_t* chrom_off, const orc_map_cfg* cfg, const orc_tipdel_cfg* tc, int clearzone1e, int64_t* counts);
+int orc_test_gen_match_string(orc_ss* lists, int32_t* n, int cap, const int8_t* basesP, const int8_t* basesM, int len, const int8_t* refs, const int64_t* chrom_off,
+                              const orc_map_cfg* cfg, int maxSwScore, int setSSScore, int32_t* paired, int8_t* top_match, int32_t* top_mlen, int32_t mcap);
 #endif
