@@ -1,11 +1,13 @@
 """TEST INFRASTRUCTURE — an independent restatement (Python, from the Java text alone) of the control flow of BBMapThread.scoreSlow for the default flag set
-(current/align2/BBMapThread.java:252-386; QUICK_MATCH_STRINGS off) on sites without a gap array: which sites are re-aligned, with which window and minScore, the
+(current/align2/BBMapThread.java:252-386; QUICK_MATCH_STRINGS off), gapped sites included (the fill then runs on makeGref's reference, tests/pygapped.py; setStop /
+setLimits re-fix the gap array, tests/pysitelist.py): which sites are re-aligned, with which window and minScore, the
 "more padding" retry, setSlowScore / setLimits, the minMsaLimit ratchet, the perfect / semiperfect bits.  Every alignment is MSA.fillAndScoreLimited restated in
 tests/pygapped.py (fill by the reference's own C, walk by tests/pywalk.py).  Shares no code with oracle/scoreslow_oracle.c."""
 import numpy as np
 
 import pyclip
 import pygapped
+import pysitelist as ps
 
 F = np.float32
 
@@ -26,7 +28,7 @@ def score_slow(oracle, packed, sites, basesP, basesM, ref8, cfg, maxR=601, maxC=
     def align(ss, bases, pad, minscore):
         nonlocal fills
         fills += 1
-        sv, _, _ = pygapped.fill_and_score_limited(oracle, packed, maxR, maxC, bases, ref8, ss.start - pad, ss.stop + pad, minscore, None)
+        sv, _, _ = pygapped.fill_and_score_limited(oracle, packed, maxR, maxC, bases, ref8, ss.start - pad, ss.stop + pad, minscore, ss.gaps)
         return sv
 
     for ss in sites:
@@ -37,20 +39,20 @@ def score_slow(oracle, packed, sites, basesP, basesM, ref8, cfg, maxR=601, maxC=
         no_indel = ss.slowScore
         arr = None
         if no_indel < max_imperfect and not ss.semiperfect:
-            expected_len = ss.stop - ss.start + 1
+            expected_len = ps.calc_gref_len(ss.start, ss.stop, ss.gaps)
             if expected_len >= limit:
-                ss.stop = ss.start + min(L + 40, limit)
+                ps.set_stop(ss, ss.start + min(L + 40, limit))
             minscore = max(no_indel, min_msa_limit)
             arr = align(ss, bases, pad0, minscore)
             if arr is not None and len(arr) > 6 and arr[3] + arr[4] + expected_len < limit:
                 old = list(arr)
-                ss.start -= arr[6]; ss.stop += arr[7]
+                ps.set_limits(ss, ss.start - arr[6], ss.stop + arr[7])
                 arr = align(ss, bases, pad0 + extra, minscore)
                 if arr is None or arr[0] < old[0]:
                     arr = old
         if arr is not None:
             ss.set_slow_score(arr[0])
-            ss.start, ss.stop = arr[1], arr[2]
+            ps.set_limits(ss, arr[1], arr[2])
         ss.score = ss.slowScore
         min_msa_limit = max(min_msa_limit, ss.slowScore - int(cfg["clearzone3"]))
         ss.perfect = ss.slowScore == max_sw

@@ -382,3 +382,25 @@ def remove_out_of_bounds(sites, read_len, chrom_max_index, is_single_scaffold, s
                 ss.gaps = fix_gaps(ss.start, ss.stop, ss.gaps)          # GapTools.fixGaps(ss) assigns its result to ss.gaps
         i += 1
     return initial - len(sites)
+
+
+def check_gaps(site):
+    """SiteScore.CHECKGAPS (stream/SiteScore.java:952-959)."""
+    g = site.gaps
+    if g is None:
+        return True
+    if len(g) == 0 or len(g) % 2 == 1:
+        return False
+    if any(g[i - 1] > g[i] for i in range(1, len(g))):
+        return False
+    return g[0] == site.start and g[-1] == site.stop
+
+
+def set_limits(site, a, b):
+    """SiteScore.setLimits (stream/SiteScore.java:905-914)."""
+    site.start, site.stop = a, b
+    if site.gaps is not None:
+        site.gaps[0] = a
+        site.gaps[-1] = b
+        if not check_gaps(site):
+            site.gaps = fix_gaps(site.start, site.stop, site.gaps)

@@ -1,6 +1,6 @@
 """CPU: the control flow of BBMapThread.scoreSlow — the sequential C restatement the CUDA rounds are checked against (oracle/scoreslow_oracle.c) must
 equal a second restatement written from the Java text alone (tests/pyscoreslow.py), whose alignments are MSA.fillAndScoreLimited restated in tests/pygapped.py with
-every fill done by the reference's own C: every site field after scoreSlow and the number of alignments requested, for reads whose sites carry no gap array."""
+every fill done by the reference's own C: every site field after scoreSlow (gap arrays included), gapped sites too."""
 import numpy as np
 import pytest
 
@@ -22,10 +22,10 @@ def test_score_slow_control_flow(oracle, seed, kw):
     L2, status, na = oracle.score_slow(lists, nss, ro, P, M, refs, co, run, scfg)
     packed = oracle.new_packed(601, 3000)
     P8 = np.ascontiguousarray(P).view(np.int8); M8 = np.ascontiguousarray(M).view(np.int8); R8 = np.ascontiguousarray(refs).view(np.int8)
-    checked = fills = retried = 0
+    checked = fills = retried = gapped = 0
     for r in range(len(nss)):
         n = int(nss[r])
-        if not run[r] or n == 0 or (lists[r, :n]["ngaps"] > 0).any() or status[r]:
+        if not run[r] or n == 0 or status[r]:
             continue
         sites = _to_sites(lists[r], n)
         chroms = {s.chrom for s in sites}
@@ -38,5 +38,5 @@ def test_score_slow_control_flow(oracle, seed, kw):
         fills += pyscoreslow.score_slow(oracle, packed, sites, P8[a:b], M8[a:b], ref8, scfg[0])
         _same(sites, L2[r], n, r)
         retried += sum(1 for s, (x, y) in zip(sites, before) if (s.stop - s.start) != (y - x))
-        checked += 1
-    assert checked > 120 and fills > 150 and retried > 30, (checked, fills, retried)
+        checked += 1; gapped += int((lists[r, :n]["ngaps"] > 0).any())
+    assert checked > 120 and fills > 150 and retried > 30 and gapped > 10, (checked, fills, retried, gapped)
