@@ -5,9 +5,10 @@
   setPerfect                                 :239-292
   ChromosomeArray.get                        current/dna/ChromosomeArray.java:232-234 (N at and beyond maxIndex)
   Read.calcMatchLength                       current/stream/Read.java:1419-1470 (long format: every symbol but I advances the reference)
-for sites without a gap array.  The match string is a Python list of characters; MSA.score(match) is tests/pygapped.score_match, setSlowScore the one of
+(incrementStart / incrementStop re-fix a gap array the way setStart / setStop do).  The match string is a Python list of characters; MSA.score(match) is tests/pygapped.score_match, setSlowScore the one of
 tests/pysitelist.Site.  Shares no code with oracle/mapper_oracle.c."""
 import pygapped
+import pysitelist as _ps
 
 N = ord("N")
 DEFINED = {ord(c) for c in "ACGT"}
@@ -95,7 +96,7 @@ class ClipSite:
         for i in range(neutral + ins):
             m[i] = ord("C")
         self.match = m
-        self.s.start -= ins - dele
+        _set_start(self.s, self.s.start - (ins - dele))
         return True
 
     def _clip_right(self, tiplen, max_indel):
@@ -128,7 +129,7 @@ class ClipSite:
         for i in range(limit, len(m)):
             m[i] = ord("C")
         self.match = m
-        self.s.stop += ins - dele
+        _ps.set_stop(self.s, self.s.stop + (ins - dele))
         return True
 
     def unclip(self, bases, ca):
@@ -200,7 +201,7 @@ class ClipSite:
                     if subs == 1:
                         first_sub = mloc
             if self.mapped_length() != self.match_length():
-                self.s.start -= lead
+                _set_start(self.s, self.s.start - lead)
             if subs > MAX_SUBS and subs > lead * MAX_RATE:
                 for i in range(first_sub + 1):
                     m[i] = ord("C")
@@ -227,7 +228,7 @@ class ClipSite:
                         rloc += 1; cloc += 1
                 if success:
                     if self.mapped_length() != self.match_length():
-                        self.s.stop += num_x
+                        _ps.set_stop(self.s, self.s.stop + num_x)
                     if subs > MAX_SUBS and subs > num_x * MAX_RATE:
                         for i in range(first_sub, len(m)):
                             m[i] = ord("C")
@@ -236,6 +237,15 @@ class ClipSite:
             self._rescore()
         set_perfect(self.s, bases, ref)
         return success
+
+
+def _set_start(site, a):
+    """SiteScore.setStart (stream/SiteScore.java:935-943)."""
+    site.start = a
+    if site.gaps is not None:
+        site.gaps[0] = a
+        if site.gaps[0] > site.gaps[1]:
+            site.gaps = _ps.fix_gaps(site.start, site.stop, site.gaps)
 
 
 def _getter(ref):

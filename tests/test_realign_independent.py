@@ -1,5 +1,5 @@
 """CPU: TranslateColorspaceRead.realign_new (the primary site's match string) — the C restatement inside oracle/mapper_oracle.c must equal a second
-restatement written from the Java text (tests/pyrealign.py; every fill by the reference's own C, every walk by tests/pywalk.py) on sites without a gap array:
+restatement written from the Java text (tests/pyrealign.py; every fill by the reference's own C, every walk by tests/pywalk.py) on plain and gapped sites:
 the new match string, start / stop, the three scores, the perfect bits and the number of fills requested."""
 import ctypes as C
 
@@ -30,13 +30,14 @@ def test_realign_new(oracle, seed, ratio, recur):
     lib.orc_test_realign_new.restype = C.c_int
     realigners = {}
     rng = np.random.default_rng(seed)
-    done = indel = refilled = 0
+    done = indel = refilled = gapped = 0
     for r in range(len(nss)):
         for i in range(min(int(nss[r]), 2)):
             rec = L2[r, i:i + 1].copy()
-            if rec["ngaps"][0] > 0 or status[r]:
+            if status[r]:
                 continue
-            if (r + i) % 2:                                   # a misplaced or shrunken site: the alignment runs into the window edge, which is what the
+            ng = int(rec["ngaps"][0])
+            if (r + i) % 2 and ng == 0:                                   # a misplaced or shrunken site: the alignment runs into the window edge, which is what the
                 d = int(rng.integers(-28, 29))                # padding suggestions, the wider re-fills and the recursion are for
                 rec["start"] += d; rec["stop"] += d - int(rng.integers(0, 12))
                 if rec["stop"][0] <= rec["start"][0]:
@@ -50,7 +51,7 @@ def test_realign_new(oracle, seed, ratio, recur):
             min_valid = int(np.float32(ratio) * np.float32(maxq)) - 258
             s = rec[0]
             site = ps.Site(ch, int(s["strand"]), int(s["start"]), int(s["stop"]), int(s["hits"]), int(s["score"]), int(s["quick_score"]), int(s["slow_score"]),
-                           int(s["paired_score"]), bool(s["perfect"]), bool(s["semiperfect"]), bool(s["rescued"]), None)
+                           int(s["paired_score"]), bool(s["perfect"]), bool(s["semiperfect"]), bool(s["rescued"]), None if ng == 0 else [int(x) for x in s["gaps"][:ng]])
             cs = pyclip.ClipSite(site, None)
             co1 = np.array([0, len(ref8)], np.int64)
             rec["chrom"] = 1
@@ -67,5 +68,7 @@ def test_realign_new(oracle, seed, ratio, recur):
             assert (site.start, site.stop, site.score, site.slowScore, site.pairedScore, int(site.perfect), int(site.semiperfect)) == \
                    (int(e["start"]), int(e["stop"]), int(e["score"]), int(e["slow_score"]), int(e["paired_score"]), int(e["perfect"]), int(e["semiperfect"])), (r, i)
             assert R.fills - f0 == nf, (r, i, R.fills - f0, nf)
+            assert ([] if site.gaps is None else list(site.gaps)) == e["gaps"][: int(e["ngaps"])].tolist(), (r, i, site.gaps, e["gaps"], e["ngaps"])
+            gapped += ng > 0
             done += 1; indel += (b"D" in bytes(cs.match)) or (b"I" in bytes(cs.match)); refilled += nf > 1
-    assert done > 150 and indel > 40 and refilled > 40, (done, indel, refilled)
+    assert done > 150 and indel > 40 and refilled > 40 and gapped > 10, (done, indel, refilled, gapped)
